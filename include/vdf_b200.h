@@ -1,0 +1,202 @@
+/*
+ * vdf_b200.h -- C ABI of the B200-native (sm_100a) replacement for the two data-parallel hot paths of
+ * Farmadupe/vid_dup_finder_lib.  Plain pointers and sizes only; this is what the crate's `extern "C"`
+ * block (or any other FFI: ctypes, cgo, JNI) binds.  Built by vid_dup_finder_lib_b200/csrc/Makefile into
+ * libvdf_b200.so (Python/ctypes, tests, bench) and libvdf_b200.a (the static library build.rs links).
+ *
+ * The reference has no FFI seam of its own; its seam is the public Rust API
+ * (vid_dup_finder_lib/src/lib.rs:132-140).  Each entry point below names the reference code it replaces
+ * (file:line relative to the reference repository root).  What stays in the host language above this
+ * boundary: decoding, the stable (duration, path) sort (search_algorithm.rs:55-61), the tolerance cast
+ * (search_algorithm.rs:82), index -> PathBuf, MatchGroup construction (match_group.rs:21-47).
+ *
+ * There is NO CPU fallback: every compute entry point runs CUDA kernels and returns VDF_ERR_CUDA /
+ * VDF_ERR_NO_DEVICE if it cannot.
+ *
+ * Conventions
+ *   - hashes: 16 x u64 per VideoHash, exactly `VideoHash.hash: [usize; 16]` (video_hash.rs:26-32);
+ *     bit b of the 1000-bit hash lives in word b/64, bit b%64; bits 1000..1023 are zero for real hashes
+ *     but ARE compared (video_hash.rs:311-317).
+ *   - "sorted" inputs are in the order of Search::sort: ascending (duration, src_path).
+ *   - indices fit in 32 bits (n < 2^32).
+ *   - inputs are caller-owned and read-only for the duration of the call.  `*_device` variants take
+ *     device pointers valid on the context's GPU; all others take host pointers (pinned or pageable).
+ *   - outputs in vdf_edges / vdf_groups / vdf_csr are library-allocated host buffers, released with
+ *     vdf_free_edges / vdf_free_groups / vdf_free_csr.
+ *   - return value: VDF_OK (0) or a negative error; vdf_last_error(ctx) describes the last failure.
+ *     Nothing unwinds or aborts across the boundary.
+ *   - a context is bound to one GPU (one process per GPU), owns its stream and scratch buffers, and is
+ *     NOT thread-safe: one context per host thread, or an external lock
+ *     (the reference calls VideoHashBuilder::hash from rayon workers,
+ *     vid_dup_finder_app/src/video_hash_filesystem_cache/video_hash_filesystem_cache.rs:246).
+ */
+#ifndef VDF_B200_H
+#define VDF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDF_HASH_WORDS 16 /* definitions.rs:43 */
+#define VDF_DCT_SIZE 16   /* definitions.rs:34 */
+#define VDF_HASH_BITS 1000 /* definitions.rs:42 */
+
+#define VDF_OK 0
+#define VDF_ERR_CUDA (-1)          /* a CUDA call or kernel failed */
+#define VDF_ERR_ALLOC (-2)         /* host or device allocation failed */
+#define VDF_ERR_INVALID (-3)       /* bad argument */
+#define VDF_ERR_EDGE_OVERFLOW (-4) /* more matches than the edge buffer may grow to (see "max_edges") */
+#define VDF_ERR_NO_DEVICE (-5)     /* no usable sm_100 device */
+
+/* per-stack status, mirrors vid_dup_finder_lib::Error (video_hashing/mod.rs:17-28) */
+#define VDF_STACK_OK 0
+#define VDF_STACK_NOT_ENOUGH_FRAMES 1 /* Error::NotEnoughFrames: fewer than 16 frames (dct_3d.rs:47-52) */
+#define VDF_STACK_VIDPROC 2           /* Error::VidProc: frames not all the same size (video_hash_builder.rs:169-186) */
+
+#define VDF_CROPDETECT_NONE 0      /* Cropdetect::None      (definitions.rs:46-54) */
+#define VDF_CROPDETECT_LETTERBOX 1 /* Cropdetect::Letterbox (the library default, video_hash_builder.rs:55-63) */
+
+typedef struct vdf_ctx vdf_ctx;
+
+/* (i,j) match edges of search_self, i<j, sorted by (i,j): ij[2k], ij[2k+1] */
+typedef struct {
+    uint64_t n;
+    uint64_t* ij;
+} vdf_edges;
+
+/* MatchGroups as CSR over indices into the sorted array: group g = member_idx[group_ptr[g] .. group_ptr[g+1]),
+ * matches in ascending order followed by the target LAST, groups in the reference's (reversed) order
+ * (search_algorithm.rs:136,158-161,167) */
+typedef struct {
+    uint64_t n_groups;
+    uint64_t* group_ptr;  /* n_groups + 1 */
+    uint64_t* member_idx; /* group_ptr[n_groups] */
+} vdf_groups;
+
+/* per-reference match lists: row r (caller order) = col_idx[row_ptr[r] .. row_ptr[r+1]), ascending indices
+ * into the sorted candidate array (search_algorithm.rs:63-77) */
+typedef struct {
+    uint64_t n_rows;
+    uint64_t* row_ptr; /* n_rows + 1 */
+    uint64_t* col_idx;
+} vdf_csr;
+
+/* one frame stack = the <=16 gray u8 frames VideoHashBuilder collects (video_hash_builder.rs:159-167) */
+typedef struct {
+    uint64_t offset;       /* byte offset of frame 0 from the `frames` base pointer */
+    uint64_t frame_stride; /* bytes between consecutive frames of this stack */
+    uint32_t width;        /* pixels; every frame of the stack has this size */
+    uint32_t height;
+    uint32_t pitch;        /* bytes between rows (>= width) */
+    uint32_t n_frames;     /* frames present; the first 16 are hashed, fewer -> VDF_STACK_NOT_ENOUGH_FRAMES */
+    uint32_t flags;        /* VDF_STACK_FLAG_* */
+    uint32_t reserved;
+} vdf_stack_desc;
+#define VDF_STACK_FLAG_MIXED_SIZES 1u /* host saw differing frame sizes -> VDF_STACK_VIDPROC, no GPU work */
+
+/* ------------------------------------------------------------------------------------ context */
+
+/* Binds a context to CUDA device `device_id` (one process per GPU). */
+int vdf_ctx_create(int device_id, vdf_ctx** out);
+void vdf_ctx_destroy(vdf_ctx* ctx);
+const char* vdf_last_error(const vdf_ctx* ctx);
+
+/* Multi-GPU: this context evaluates only its share (rank of world) of the pair-matrix tile blocks of
+ * vdf_search_self* / the candidate tiles of vdf_search_refs*; edge lists of all ranks are concatenated by
+ * the caller (NCCL all-gather) before vdf_group_greedy*.  Default rank 0 of 1. */
+int vdf_ctx_set_shard(vdf_ctx* ctx, uint32_t rank, uint32_t world);
+
+/* Tuning knobs: "max_edges" (edge-buffer growth cap, default 2^28), "initial_edges" (default 2^22),
+ * "search_variant" (0 = XOR+POPC, 1 = XOR + carry-save adder + POPC). */
+int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value);
+
+/* The cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the caller). */
+void* vdf_ctx_stream(vdf_ctx* ctx);
+
+/* Counters since context creation: kernels launched by this library, and bytes copied H2D / D2H. */
+void vdf_ctx_counters(const vdf_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* Device time (CUDA events on the context's stream) accumulated over the launches of one of the dominant
+ * kernels: which = 0 hamming tiles, 1 crop+resize, 2 letterbox scan, 3 DCT+pack.  reset != 0 clears the slot. */
+int vdf_ctx_kernel_time(vdf_ctx* ctx, int which, double* total_ms, uint64_t* launches, int reset);
+
+/* ------------------------------------------------------------------------------------ search path */
+
+/* Replaces the comparison loop of Search::search_self (search_algorithm.rs:81-117,140-156) together with
+ * VideoHash::hamming_distance (video_hash.rs:190-192,311-317): every pair i<j with
+ * dur[j] <= (f64(dur[i]) * 1.1) as u32 and hamming_1024(i,j) <= tol_int becomes an edge.
+ * tol_int = (tolerance * 1000.0) as u32 is computed by the caller (search_algorithm.rs:82). */
+int vdf_search_self(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint32_t* dur_sorted, uint64_t n,
+                    uint32_t tol_int, vdf_edges* out);
+
+/* Replaces the consumption rule of Search::search_self (search_algorithm.rs:131-170): targets are taken in
+ * ascending order, each consumes its still-unmatched neighbours; output order as the reference's
+ * Vec<Vec<PathBuf>> after ret.reverse().  Runs on the GPU (parallel rounds of the greedy rule). */
+int vdf_group_greedy(vdf_ctx* ctx, uint64_t n, const vdf_edges* edges, vdf_groups* out);
+
+/* vdf_search_self + vdf_group_greedy with the edge list kept in HBM: what `search()` (video_dup_finder.rs:7-13)
+ * calls.  Groups of fewer than 2 entries cannot occur (MatchGroup::new, match_group.rs:21-30). */
+int vdf_search_self_groups(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint32_t* dur_sorted, uint64_t n,
+                           uint32_t tol_int, vdf_groups* out);
+
+/* Replaces search_with_references' inner loop (video_dup_finder.rs:19-46; Search::search_one and
+ * duration_slice, search_algorithm.rs:63-77,173-185; consume = false): for each reference r, all candidates k with
+ * (f64(ref_dur[r])*0.95) as u32 <= cand_dur[k] <= (f64(ref_dur[r])*1.05) as u32 and hamming <= tol_int.
+ * Rows with no match are empty (the caller skips them, video_dup_finder.rs:38-43). */
+int vdf_search_refs(vdf_ctx* ctx, const uint64_t* cand_sorted, const uint32_t* cand_dur_sorted, uint64_t n_cand,
+                    const uint64_t* refs, const uint32_t* ref_dur, uint64_t n_ref, uint32_t tol_int, vdf_csr* out);
+
+/* Device-resident forms (HBM in, HBM out) used by pipelines that keep the table on the GPU and by the
+ * multi-GPU plumbing.  Edges are returned as sorted u64 keys (i << 32 | j), resp. (ref << 32 | cand).
+ * `capacity` is the size of d_keys_out in keys; if more matches exist, *n_out receives the required count
+ * and the call returns VDF_ERR_EDGE_OVERFLOW.  cand_index_base is added to candidate indices (a rank that
+ * holds a contiguous slice of the sorted corpus passes the slice's first global index). */
+int vdf_search_self_device(vdf_ctx* ctx, const uint64_t* d_hash_sorted, const uint32_t* d_dur_sorted, uint64_t n,
+                           uint32_t tol_int, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out);
+int vdf_search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand_sorted, const uint32_t* d_cand_dur_sorted,
+                           uint64_t n_cand, uint64_t cand_index_base, const uint64_t* d_refs,
+                           const uint32_t* d_ref_dur, uint64_t n_ref, uint32_t tol_int, uint64_t* d_keys_out,
+                           uint64_t capacity, uint64_t* n_out);
+int vdf_group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges,
+                            vdf_groups* out);
+
+/* Number of (i,j) pairs inside the duration windows, i.e. how many hamming_distance calls the reference's
+ * search_self would make with nothing consumed (throughput accounting). */
+int vdf_self_window_pairs(vdf_ctx* ctx, const uint32_t* dur_sorted, uint64_t n, uint64_t* pairs_out);
+
+void vdf_free_edges(vdf_edges* e);
+void vdf_free_groups(vdf_groups* g);
+void vdf_free_csr(vdf_csr* c);
+
+/* ------------------------------------------------------------------------------------ hashing path */
+
+/* Replaces the compute tail of gen_hash (video_hash_builder.rs:214-223): crop_video_frames (:188-212) with
+ * cropdetect_letterbox (vid_dup_finder_common/src/video_frames_gray.rs:38-128,201-210; Crop::union
+ * crop.rs:53-68), crop_resize_buf to 16x16 (vid_dup_finder_common/src/resize_gray.rs:11-54, fast_image_resize
+ * Lanczos3 u8), Dct3d::from_images + dct_3d (dct_3d.rs:15-53, raw_dct_ops.rs:107-142, f64) and the
+ * threshold / bit pack (dct_3d.rs:55-66, video_hash.rs:63-70).
+ * frames: host pointer; stacks are staged to HBM with pinned async copies.  out_hash: n x 16 u64.
+ * out_status: n x i32 (VDF_STACK_*).  out_crop: optional n x 4 u32 (left, right, top, bottom). */
+int vdf_hash_stacks(vdf_ctx* ctx, const uint8_t* frames, const vdf_stack_desc* desc, uint32_t n, int cropdetect,
+                    uint64_t* out_hash, int32_t* out_status, uint32_t* out_crop);
+
+/* Same with frames already in HBM; d_out_hash is a device pointer (n x 16 u64), status/crop are host. */
+int vdf_hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_desc* desc, uint32_t n,
+                           int cropdetect, uint64_t* d_out_hash, int32_t* out_status, uint32_t* out_crop);
+
+/* Debug / parity taps: the 16x16x16 u8 cube after crop+resize ([t][row][col]) for each stack. */
+int vdf_hash_stacks_small_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_desc* desc, uint32_t n,
+                                 int cropdetect, uint8_t* d_out_small /* n x 4096 */, uint32_t* out_crop);
+
+/* Hash from an already-resized cube (Dct3d::from_images + hash_bits only). */
+int vdf_hash_from_small(vdf_ctx* ctx, const uint8_t* small /* host, n x 4096 */, uint32_t n, uint64_t* out_hash);
+
+const char* vdf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDF_B200_H */

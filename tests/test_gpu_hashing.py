@@ -1,0 +1,193 @@
+"""GPU parity tests of the hashing path through the C ABI.  Bar: crops, the 16x16x16 resized cube and the hash
+words are BIT-EXACT against the CPU oracle (the DCT runs in f64 with the oracle's operation order, so there is no
+epsilon band); the oracle itself is anchored as tests/test_oracle_hashing.py describes."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vid_dup_finder_lib_b200 as vdf
+from oracle import vdf_oracle as o
+from tests import synth
+from tests.test_oracle_letterbox import KATS
+from vid_dup_finder_lib_b200 import _ffi
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return _ffi.default_context()
+
+
+def gpu_hash(ctx, stacks: np.ndarray, cropdetect=1):
+    """stacks [n,16,h,w] u8 (host) -> hash, status, crop via vdf_hash_stacks"""
+    n, t, h, w = stacks.shape
+    return ctx.hash_stacks(stacks.reshape(-1), _ffi.make_descs(n, w, h, t), cropdetect)
+
+
+def gpu_small(ctx, stacks: np.ndarray, cropdetect=1):
+    n, t, h, w = stacks.shape
+    d = torch.from_numpy(stacks).cuda()
+    out = torch.empty((n, 16, 16, 16), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    crop = ctx.hash_stacks_small_device(d.data_ptr(), _ffi.make_descs(n, w, h, t), cropdetect, out.data_ptr())
+    return out.cpu().numpy(), crop
+
+
+def oracle_all(stacks: np.ndarray, cropdetect=1):
+    H, S, C, M = [], [], [], []
+    for s in stacks:
+        st, h, crop, small = o.hash_stack(s, cropdetect)
+        H.append(h), S.append(st), C.append(crop), M.append(small)
+    return np.stack(H), np.array(S), np.array(C), np.stack(M)
+
+
+def test_letterbox_kat_images(ctx):
+    """the reference's KAT images (video_frames_gray.rs:225-458) at the hot path's fixed AnyColour(16) setting,
+    plus the oracle's verdict on the same images with frame 8 differing from frame 0"""
+    for name, image, _, _, _ in KATS:
+        h, w = image.shape
+        big = np.kron(image, np.ones((7, 9), np.uint8))  # keep the geometry, give the resize something to chew
+        for im in (image, big):
+            st = np.broadcast_to(im, (1, 16) + im.shape).copy()
+            _, status, crop = gpu_hash(ctx, st, 1)
+            want = o.hash_stack(st[0], 1)
+            assert status[0] == want[0] == 0 and tuple(crop[0]) == want[2], name
+            assert tuple(crop[0]) == o.letterbox_frame(im, o.LB_ANYCOLOUR, 16), name
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (256, 144), (321, 203), (640, 360), (854, 480), (1280, 720), (1920, 1080)])
+def test_crop_cube_and_hash_are_bit_exact(ctx, w, h):
+    n = 6 if w * h > 500_000 else 12
+    stacks = synth.frame_stacks(n, w, h, seed=w * 7 + h).numpy()
+    stacks[1, :, : h // 9, :] = 16            # letterbox
+    stacks[1, :, h - h // 11:, :] = 20
+    stacks[2, :, :, : w // 10] = 235          # pillarbox, bright
+    stacks[2, :, :, w - w // 13:] = 235
+    stacks[3, 8] = stacks[3, 0]
+    stacks[3, 8, : h // 6, :] = 0             # only frame 8 has a bar -> per-side min removes it
+    stacks[4] = stacks[4, 0]                  # static: every t>0 coefficient is an exact zero
+    stacks[5] = 77                            # uniform: every strip is "letterbox" -> no crop at all
+    want_h, want_s, want_c, want_m = oracle_all(stacks)
+    got_m, got_c2 = gpu_small(ctx, stacks)
+    got_h, got_s, got_c = gpu_hash(ctx, stacks)
+    assert np.array_equal(got_s, want_s)
+    assert np.array_equal(got_c, want_c) and np.array_equal(got_c2, want_c)
+    assert np.array_equal(got_m, want_m), "resized cube differs"
+    assert np.array_equal(got_h, want_h), "hash words differ"
+    assert want_c[1][2] > 0 and want_c[2][0] > 0 and tuple(want_c[3]) == (0, 0, 0, 0) and tuple(want_c[5]) == (0, 0, 0, 0)
+    bits = np.unpackbits(got_h[4].view(np.uint8), bitorder="little")
+    assert bits[100:].sum() == 0  # static stack
+
+
+def test_cropdetect_none(ctx):
+    stacks = synth.frame_stacks(4, 320, 180, seed=3).numpy()
+    stacks[:, :, :20, :] = 16
+    want_h, _, want_c, _ = oracle_all(stacks, 0)
+    got_h, got_s, got_c = gpu_hash(ctx, stacks, 0)
+    assert np.array_equal(got_h, want_h) and not got_c.any() and not got_s.any()
+    assert not np.array_equal(got_h, gpu_hash(ctx, stacks, 1)[0])
+
+
+def test_dct_threshold_pack_bit_exact(ctx):
+    rng = np.random.default_rng(11)
+    cubes = rng.integers(0, 256, (300, 16, 16, 16), dtype=np.uint8)
+    cubes[0] = 128                                   # all-zero input: every coefficient 0.0 -> empty hash
+    cubes[1] = cubes[1, 0]                           # static
+    cubes[2] = np.concatenate([cubes[2, :, :, :8], cubes[2, :, :, 7::-1]], axis=2)  # mirror-symmetric in x
+    cubes[3] = 255
+    cubes[4] = rng.integers(126, 131, (16, 16, 16))  # tiny amplitudes
+    got = ctx.hash_from_small(cubes)
+    want = np.stack([o.hash_from_small(c) for c in cubes])
+    assert np.array_equal(got, want)
+    assert not got[0].any() and (got[:, 15] >> np.uint64(40)).max() == 0  # pad bits 1000..1023 stay zero
+
+
+def test_reference_example_clips(ctx):
+    """examples/example.rs:77-82 on the decodable clips, end to end on the GPU: golden words, then search()."""
+    z = np.load(os.path.join(GOLD, "ref_clips_gray.npz"))
+    gold = json.load(open(os.path.join(GOLD, "ref_clips_hashes.json")))
+    keys = [n.replace(".", "_") for n in z["names"]] + ["cat_1_letterboxed"]
+    b = vdf.VideoHashBuilder()
+    durs = list(z["durations"]) + [45]
+    res = b.hash_many([list(z[k]) for k in keys], keys, durs)
+    for k, r in zip(keys, res):
+        assert isinstance(r, vdf.VideoHash)
+        assert [format(w, "016x") for w in r.hash] == gold[k]["hash_words_hex"], k
+    groups = vdf.search(res, vdf.DEFAULT_SEARCH_TOLERANCE)
+    assert sorted(sorted(g.duplicates()) for g in groups) == [["cat_1_letterboxed", "cat_1_mp4", "cat_3_webm"],
+                                                              ["dog_1_mp4", "dog_3_webm"]]
+    # lib.rs:26-62 doc-test: cat.1 + cat.3 match, dog.3 does not
+    sub = [res[0], res[1], res[3]]
+    g2 = vdf.search(sub, vdf.DEFAULT_SEARCH_TOLERANCE)
+    assert len(g2) == 1 and g2[0].len() == 2
+
+
+def test_errors_mirror_the_reference(ctx):
+    fr = [synth.smooth_frame(96, 64, s) for s in range(16)]
+    b = vdf.VideoHashBuilder()
+    ok = b.hash_frames(fr, "a.mp4", 12)
+    assert ok.src_path == "a.mp4" and ok.duration == 12
+    assert np.array_equal(ok.words(), o.hash_stack(np.stack(fr), 1)[1])
+    with pytest.raises(vdf.NotEnoughFrames):  # dct_3d.rs:47-52
+        b.hash_frames(fr[:15], "a", 1)
+    with pytest.raises(vdf.NotEnoughFrames):
+        b.hash_frames([], "a", 1)
+    bad = list(fr)
+    bad[5] = synth.smooth_frame(96, 66, 5)
+    with pytest.raises(vdf.VidProc):  # video_hash_builder.rs:169-186
+        b.hash_frames(bad, "a", 1)
+    more = b.hash_frames(fr + fr[:4], "a.mp4", 12)  # take(16), video_hash_builder.rs:164
+    assert more.hash == ok.hash
+    mixed = b.hash_many([fr, fr[:3], bad, fr], ["0", "1", "2", "3"], [1, 2, 3, 4])
+    assert isinstance(mixed[0], vdf.VideoHash) and isinstance(mixed[1], vdf.NotEnoughFrames)
+    assert isinstance(mixed[2], vdf.VidProc) and mixed[3].hash == ok.hash and mixed[3].duration == 4
+    no_crop = vdf.VideoHashBuilder(vdf.CreationOptions(cropdetect=vdf.Cropdetect.NONE)).hash_frames(fr, "a", 1)
+    assert np.array_equal(no_crop.words(), o.hash_stack(np.stack(fr), 0)[1])
+
+
+def test_ragged_batch_and_pitched_frames(ctx):
+    """stacks of different sizes in one call, frames with row padding (pitch > width), pinned and pageable hosts"""
+    sizes = [(160, 90), (33, 17), (640, 360), (16, 16), (7, 5), (200, 200)]
+    stacks = [synth.frame_stacks(1, w, h, seed=w)[0].numpy() for w, h in sizes]
+    descs = np.zeros(len(sizes), dtype=_ffi.STACK_DESC_DTYPE)
+    chunks, off = [], 0
+    for k, (st, (w, h)) in enumerate(zip(stacks, sizes)):
+        pitch = w + (k % 3) * 5
+        buf = np.zeros((16, h, pitch), np.uint8)
+        buf[:, :, :w] = st
+        descs[k] = (off, pitch * h, w, h, pitch, 16, 0, 0)
+        chunks.append(buf.reshape(-1))
+        off += buf.size
+    host = np.concatenate(chunks)
+    want = np.stack([o.hash_stack(st, 1)[1] for st in stacks])
+    got, status, _ = ctx.hash_stacks(host, descs, 1)
+    assert not status.any() and np.array_equal(got, want)
+    pinned = torch.from_numpy(host).pin_memory()
+    got2, _, _ = ctx.hash_stacks(pinned.numpy(), descs, 1)
+    assert np.array_equal(got2, want)
+
+
+def test_full_size_1080p_batch(ctx):
+    """BASELINE config shape: 1080p stacks resident in HBM, generated on the device; parity of a sample against
+    the oracle (which needs ~0.3 s per stack), invariants on all of them."""
+    n = 48
+    d = synth.frame_stacks(n, 1920, 1080, seed=synth.SEED, device="cuda")
+    out = torch.zeros((n, 16), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    st, crop = ctx.hash_stacks_device(d.data_ptr(), _ffi.make_descs(n, 1920, 1080), 1, out.data_ptr())
+    got = out.cpu().numpy().view(np.uint64)
+    assert not st.any()
+    assert (got[:, 15] >> np.uint64(40)).max() == 0
+    assert (crop[:, 0] + crop[:, 1] < 1920).all() and (crop[:, 2] + crop[:, 3] < 1080).all() and crop.any()
+    for s in range(0, n, 6):
+        w_st, w_h, w_crop, _ = o.hash_stack(d[s].cpu().numpy(), 1)
+        assert w_st == 0 and tuple(crop[s]) == w_crop and np.array_equal(got[s], w_h), s
+    # idempotence: hashing the same resident stacks again gives the same words
+    out2 = torch.zeros_like(out)
+    ctx.hash_stacks_device(d.data_ptr(), _ffi.make_descs(n, 1920, 1080), 1, out2.data_ptr())
+    assert torch.equal(out, out2)

@@ -1,0 +1,279 @@
+"""GPU parity tests of the search path, through the C ABI (vid_dup_finder_lib_b200._ffi) and the crate-shaped API.
+Bar: bit-exact edges, groups (order included) and per-reference match lists against the CPU oracle."""
+import numpy as np
+import pytest
+
+import vid_dup_finder_lib_b200 as vdf
+from oracle import vdf_oracle as o
+from tests import ref_fixtures as rf
+from tests import synth
+from vid_dup_finder_lib_b200 import _ffi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _ffi.default_context()
+    c.set_shard(0, 1)
+    c.set_option("search_variant", 0)
+    return c
+
+
+def _vh(hashes, durations=None, paths=None):
+    n = len(hashes)
+    durations = [0] * n if durations is None else durations
+    paths = ["p/%06d" % i for i in range(n)] if paths is None else paths
+    return [vdf.VideoHash.from_words(hashes[i], paths[i], int(durations[i])) for i in range(n)]
+
+
+# ---- the reference's own tests, through the drop-in API ------------------------------------------
+def test_searching_nothing_returns_empty_vec(ctx):  # search_algorithm.rs:203-208
+    assert vdf.search([], 1.0, ctx=ctx) == []
+
+
+def test_find_dups_finds_a_known_group(ctx):  # test_find_all.rs:137-169
+    rng = np.random.default_rng(1)
+    groups = rf.HashesWithDistanceSet(1, 50, 201, 100, rng)
+    dups = vdf.search(_vh(groups.all_members(rng)), 200 / vdf.TOLERANCE_SCALING_FACTOR, ctx=ctx)
+    assert len(dups) == 1
+    assert dups[0].len() == 50
+
+
+def test_find_dups_discriminates_by_duration(ctx):  # test_find_all.rs:176-238
+    rng = np.random.default_rng(2)
+    groups = rf.HashesWithDistanceSet(1, 100, 201, 100, rng)
+    short = groups.groups[0].members(rng)
+    hashes = short + short[:50]
+    dur = [50] * 100 + [250] * 50
+    names = ["short_%03d" % i for i in range(100)] + ["long_%03d" % i for i in range(50)]
+    perm = rng.permutation(150)
+    dups = vdf.search(_vh([hashes[i] for i in perm], [dur[i] for i in perm], [names[i] for i in perm]), 200 / 1000.0, ctx=ctx)
+    dups.sort(key=len)
+    assert len(dups) == 2
+    assert dups[1].len() == 100 and all(p.startswith("short_") for p in dups[1].duplicates())
+    assert dups[0].len() == 50 and all(p.startswith("long_") for p in dups[0].duplicates())
+
+
+def test_find_dups_discriminates_by_distance(ctx):  # test_find_all.rs:244-269
+    rng = np.random.default_rng(3)
+    sets = rf.HashesWithDistanceSet(2, 100, 150, 50, rng)
+    dups = vdf.search(_vh(sets.all_members(rng)), 100 / 1000.0, ctx=ctx)
+    dups.sort(key=len)
+    assert len(dups) == 2
+    assert dups[0].len() == 100
+    assert dups[1].len() == 110
+
+
+def test_find_with_refs(ctx):  # test_find_all.rs:273-315
+    rng = np.random.default_rng(4)
+    sets = rf.HashesWithDistanceSet(5, 100, 150, 50, rng)
+    cands = _vh(sets.all_members(rng))
+    assert len(cands) == 100 + 110 + 120 + 130 + 140
+    start = vdf.VideoHash.from_words(sets.groups[3].start_hash, "ref3", 0)
+    dups = vdf.search_with_references([start], cands, 50 / 1000.0, ctx=ctx)
+    assert len(dups) == 1
+    assert dups[0].len() == 130 and dups[0].reference() == "ref3"
+    starts = [vdf.VideoHash.from_words(sets.groups[0].start_hash, "ref0", 0),
+              vdf.VideoHash.from_words(sets.groups[4].start_hash, "ref4", 0)]
+    dups2 = vdf.search_with_references(starts, cands, 50 / 1000.0, ctx=ctx)
+    assert len(dups2) == 2
+    assert dups2[0].len() == 100 and dups2[0].reference() == "ref0"
+    assert dups2[1].len() == 140 and dups2[1].reference() == "ref4"
+
+
+def test_hamming_metric_properties_on_device(ctx):  # video_hash.rs:325-371 via the edge predicate
+    full, empty = rf.full_hash(), rf.empty_hash()
+    z = np.zeros(2, np.uint32)
+    assert len(ctx.search_self(np.stack([empty, empty]), z, 0)) == 1  # d(empty, empty) = 0
+    assert len(ctx.search_self(np.stack([full, full]), z, 0)) == 1    # d(full, full) = 0
+    assert len(ctx.search_self(np.stack([full, empty]), z, 1023)) == 0  # all 1024 bits are compared
+    assert len(ctx.search_self(np.stack([full, empty]), z, 1024)) == 1
+    rng = np.random.default_rng(2)
+    for _ in range(20):  # symmetry + exact distance: the edge appears exactly at tol = d, in either order
+        a, b = rf.random_hash(rng), rf.random_hash(rng)
+        d = o.hamming(a, b)
+        for pair in (np.stack([a, b]), np.stack([b, a])):
+            assert len(ctx.search_self(pair, z, d)) == 1 and len(ctx.search_self(pair, z, d - 1)) == 0
+
+
+# ---- randomized parity against the oracle ---------------------------------------------------------
+def _case(rng, n, n_clusters, max_flip, dur_choices):
+    base = synth.random_hashes(n_clusters, seed=int(rng.integers(1 << 30)))
+    pick = rng.integers(0, n_clusters, n)
+    flips = rng.integers(0, 1024, (n, 1024)) < rng.integers(0, max_flip + 1, (n, 1))
+    H = base[pick] ^ np.packbits(flips, axis=1, bitorder="little").view(np.uint64)
+    dur = np.sort(rng.choice(dur_choices, n).astype(np.uint32))
+    return np.ascontiguousarray(H), dur
+
+
+SIZES = [1, 2, 3, 127, 128, 129, 255, 257, 1000, 4097]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n", SIZES)
+def test_self_search_edges_and_groups_match_oracle(ctx, n, variant):
+    rng = np.random.default_rng(1000 + n)
+    ctx.set_option("search_variant", variant)
+    try:
+        for trial in range(3):
+            H, dur = _case(rng, n, max(1, n // 7), 200, [0, 9, 10, 11, 12, 100, 105, 110, 111, 121, 600] if trial else [600])
+            for tol in (0, 57, 150, 350, 1024 if n <= 300 else 420):
+                want_e = o.self_edges(H, dur, tol)
+                got_e = ctx.search_self(H, dur, tol)
+                assert np.array_equal(got_e, want_e), (n, tol, trial)
+                want_gp, want_mm = o.search_self(H, dur, tol)
+                got_gp, got_mm = ctx.search_self_groups(H, dur, tol)
+                assert np.array_equal(got_gp, want_gp) and np.array_equal(got_mm, want_mm), (n, tol, trial)
+                g2, m2 = ctx.group_greedy(n, got_e)
+                assert np.array_equal(g2, want_gp) and np.array_equal(m2, want_mm)
+    finally:
+        ctx.set_option("search_variant", 0)
+
+
+def test_greedy_rule_is_not_connected_components(ctx):
+    a = rf.empty_hash()
+    b = a.copy(); b[0] = np.uint64(0xFF)
+    c = b.copy(); c[1] = np.uint64(0xFF)
+    gp, mm = ctx.search_self_groups(np.stack([a, b, c]), np.zeros(3, np.uint32), 10)
+    assert gp.tolist() == [0, 2] and mm.tolist() == [1, 0]  # a-b-c with a!~c: {b, a}; c stays alone
+
+
+def test_long_dependency_chain(ctx):
+    """a path graph 0-1-2-...-(L-1) needs L rounds of the parallel greedy rule: targets are the even vertices."""
+    L = 600
+    edges = np.stack([np.arange(L - 1), np.arange(1, L)], axis=1).astype(np.uint64)
+    gp, mm = ctx.group_greedy(L, edges)
+    want_gp, want_mm = o.group_from_edges(L, edges)
+    assert np.array_equal(gp, want_gp) and np.array_equal(mm, want_mm)
+    assert len(gp) - 1 == L // 2
+
+
+def test_random_edge_lists_group_like_the_oracle(ctx):
+    rng = np.random.default_rng(77)
+    for n, m in [(10, 12), (200, 150), (200, 2000), (5000, 20000), (1000, 1)]:
+        i = rng.integers(0, n, m)
+        j = rng.integers(0, n, m)
+        e = np.unique(np.stack([np.minimum(i, j), np.maximum(i, j)], axis=1)[i != j], axis=0).astype(np.uint64)
+        gp, mm = ctx.group_greedy(n, e)
+        want_gp, want_mm = o.group_from_edges(n, e)
+        assert np.array_equal(gp, want_gp) and np.array_equal(mm, want_mm)
+
+
+@pytest.mark.parametrize("n_cand,n_ref", [(1, 1), (300, 5), (129, 257), (5000, 700)])
+def test_ref_search_matches_oracle(ctx, n_cand, n_ref):
+    rng = np.random.default_rng(n_cand * 31 + n_ref)
+    durs = [0, 9, 10, 11, 95, 100, 105, 106, 600, 630, 631]
+    C, cdur = _case(rng, n_cand, max(1, n_cand // 9), 150, durs)
+    R = C[rng.integers(0, n_cand, n_ref)] ^ np.packbits(rng.integers(0, 1024, (n_ref, 1024)) < 40, axis=1, bitorder="little").view(np.uint64)
+    rdur = rng.choice(durs, n_ref).astype(np.uint32)  # caller order: NOT sorted
+    for tol in (0, 60, 200, 350):
+        want_rp, want_ci = o.search_refs(C, cdur, R, rdur, tol)
+        got_rp, got_ci = ctx.search_refs(C, cdur, R, rdur, tol)
+        assert np.array_equal(got_rp, want_rp) and np.array_equal(got_ci, want_ci), tol
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    e = ctx.search_self(np.zeros((0, 16), np.uint64), np.zeros(0, np.uint32), 350)
+    assert e.shape == (0, 2)
+    gp, mm = ctx.search_self_groups(np.zeros((0, 16), np.uint64), np.zeros(0, np.uint32), 350)
+    assert gp.tolist() == [0] and len(mm) == 0
+    rp, ci = ctx.search_refs(np.zeros((0, 16), np.uint64), np.zeros(0, np.uint32), synth.random_hashes(3), np.zeros(3, np.uint32), 350)
+    assert rp.tolist() == [0, 0, 0, 0] and len(ci) == 0
+    rp, ci = ctx.search_refs(synth.random_hashes(3), np.zeros(3, np.uint32), np.zeros((0, 16), np.uint64), np.zeros(0, np.uint32), 350)
+    assert rp.tolist() == [0]
+    # maximum durations: the 1.1x window saturates at u32::MAX (Rust `as u32`)
+    h = rf.empty_hash()
+    dur = np.array([4294967295 - 5, 4294967295], np.uint32)
+    assert ctx.search_self(np.stack([h, h]), dur, 0).tolist() == [[0, 1]]
+
+
+def test_edge_buffer_grows_and_caps(ctx):
+    H = np.zeros((600, 16), np.uint64)  # all identical: 600*599/2 = 179700 edges
+    dur = np.zeros(600, np.uint32)
+    ctx.set_option("initial_edges", 1000)
+    try:
+        e = ctx.search_self(H, dur, 0)
+        assert len(e) == 600 * 599 // 2
+        gp, mm = ctx.search_self_groups(H, dur, 0)
+        assert gp.tolist() == [0, 600] and mm.tolist() == list(range(1, 600)) + [0]
+        ctx.set_option("max_edges", 5000)
+        with pytest.raises(vdf.VdfError) as ei:
+            ctx.search_self(H, dur, 0)
+        assert ei.value.code == _ffi.ERR_EDGE_OVERFLOW
+    finally:
+        ctx.set_option("initial_edges", 1 << 22)
+        ctx.set_option("max_edges", 1 << 28)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shards_partition_the_pair_matrix(ctx, world):
+    rng = np.random.default_rng(5)
+    H, dur = _case(rng, 3000, 300, 200, [600, 610, 650, 700])
+    want = o.self_edges(H, dur, 300)
+    parts = []
+    try:
+        for r in range(world):
+            ctx.set_shard(r, world)
+            parts.append(ctx.search_self(H, dur, 300))
+    finally:
+        ctx.set_shard(0, 1)
+    assert sum(len(p) for p in parts) == len(want)  # disjoint
+    allp = np.concatenate(parts)
+    allp = allp[np.lexsort((allp[:, 1], allp[:, 0]))]
+    assert np.array_equal(allp, want)
+
+
+def test_parity_at_65536_planted(ctx):
+    """full CPU-vs-GPU parity at N = 2^16 on the planted-duplicate generator (log-normal durations
+    exercise the windows)."""
+    n = 1 << 16
+    H, _ = synth.planted_hashes(n, seed=synth.SEED)
+    dur = synth.lognormal_durations(n)
+    paths = synth.paths(n)
+    order = o.sort_order(dur, paths)
+    Hs, ds = np.ascontiguousarray(H[order]), dur[order]
+    for tol in (100, 350):
+        want = o.self_edges(Hs, ds, tol)
+        got = ctx.search_self(Hs, ds, tol)
+        assert np.array_equal(got, want)
+        wgp, wmm = o.search_self(Hs, ds, tol)
+        ggp, gmm = ctx.search_self_groups(Hs, ds, tol)
+        assert np.array_equal(ggp, wgp) and np.array_equal(gmm, wmm)
+    assert ctx.self_window_pairs(ds) == o.self_window_pairs(ds)
+
+
+def test_full_size_1m_properties(ctx):
+    """BASELINE config: all-pairs on 1 M synthetic hashes (equal durations).  The oracle cannot finish 5e11
+    pairs, so: (1) every planted duplicate within tolerance of its source is found, (2) the full edge rows of
+    256 sampled entries equal the oracle's brute force over all 1 M candidates, (3) groups follow from the
+    edges by the oracle's greedy rule, (4) edges are sorted and i < j."""
+    n = 1_000_000
+    tol = 350
+    H, src = synth.planted_hashes(n, seed=synth.SEED)
+    dur = np.full(n, 600, np.uint32)
+    e = ctx.search_self(H, dur, tol)
+    assert np.all(e[:, 0] < e[:, 1])
+    keys = (e[:, 0] << np.uint64(32)) | e[:, 1]
+    assert np.all(np.diff(keys.astype(np.int64)) > 0)
+    have = set(keys.tolist())
+    # (1) planted pairs
+    dups = np.nonzero(src != np.arange(n, dtype=np.uint64))[0]
+    d = rf.popcount64(H[dups] ^ H[src[dups].astype(np.int64)])
+    close = d <= tol
+    assert close.sum() > 0.9 * len(dups)
+    for i, s in zip(dups[close][:20000], src[dups][close][:20000]):
+        a, b = (int(s), int(i)) if s < i else (int(i), int(s))
+        assert ((a << 32) | b) in have
+    # (2) sampled rows vs oracle brute force
+    rng = np.random.default_rng(9)
+    rows = np.unique(np.concatenate([rng.integers(0, n, 192), dups[:64]]))
+    rp, ci = o.search_refs(H, dur, H[rows], dur[rows], tol)
+    for k, r in enumerate(rows):
+        want = set(int(c) for c in ci[rp[k]:rp[k + 1]] if c != r)
+        got = set(e[e[:, 0] == r][:, 1].tolist()) | set(e[e[:, 1] == r][:, 0].tolist())
+        assert got == want, r
+    # (3) grouping
+    gp, mm = ctx.group_greedy(n, e)
+    wgp, wmm = o.group_from_edges(n, e)
+    assert np.array_equal(gp, wgp) and np.array_equal(mm, wmm)

@@ -1,0 +1,309 @@
+"""ctypes binding of the C ABI in include/vdf_b200.h (libvdf_b200.so, built by csrc/Makefile).
+
+There is no CPU fallback: if the shared library is missing or no sm_100 GPU is present, every entry point
+raises.  numpy arrays are host buffers; `*_device` methods take raw device pointers (e.g. torch `data_ptr()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libvdf_b200.so")
+
+OK = 0
+ERR_CUDA, ERR_ALLOC, ERR_INVALID, ERR_EDGE_OVERFLOW, ERR_NO_DEVICE = -1, -2, -3, -4, -5
+STACK_OK, STACK_NOT_ENOUGH_FRAMES, STACK_VIDPROC = 0, 1, 2
+CROPDETECT_NONE, CROPDETECT_LETTERBOX = 0, 1
+STACK_FLAG_MIXED_SIZES = 1
+
+EXPORTS = [
+    "vdf_version", "vdf_ctx_create", "vdf_ctx_destroy", "vdf_last_error", "vdf_ctx_set_shard", "vdf_ctx_set_option",
+    "vdf_ctx_stream", "vdf_ctx_counters", "vdf_ctx_kernel_time", "vdf_search_self", "vdf_group_greedy", "vdf_search_self_groups",
+    "vdf_search_refs", "vdf_search_self_device", "vdf_search_refs_device", "vdf_group_greedy_device",
+    "vdf_self_window_pairs", "vdf_free_edges", "vdf_free_groups", "vdf_free_csr", "vdf_hash_stacks",
+    "vdf_hash_stacks_device", "vdf_hash_stacks_small_device", "vdf_hash_from_small",
+]
+
+
+class VdfError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vdf_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Edges(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("ij", C.POINTER(C.c_uint64))]
+
+
+class Groups(C.Structure):
+    _fields_ = [("n_groups", C.c_uint64), ("group_ptr", C.POINTER(C.c_uint64)), ("member_idx", C.POINTER(C.c_uint64))]
+
+
+class Csr(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("row_ptr", C.POINTER(C.c_uint64)), ("col_idx", C.POINTER(C.c_uint64))]
+
+
+class StackDesc(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("frame_stride", C.c_uint64), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("pitch", C.c_uint32), ("n_frames", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+STACK_DESC_DTYPE = np.dtype([("offset", "<u8"), ("frame_stride", "<u8"), ("width", "<u4"), ("height", "<u4"),
+                             ("pitch", "<u4"), ("n_frames", "<u4"), ("flags", "<u4"), ("reserved", "<u4")])
+assert STACK_DESC_DTYPE.itemsize == C.sizeof(StackDesc) == 40
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "vdf_b200.h"))
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", csrc, "-j4"] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise RuntimeError(f"{_SO} is missing: build it with `make -C vid_dup_finder_lib_b200/csrc` "
+                           "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    L = C.CDLL(_SO)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.vdf_version.restype = C.c_char_p
+    L.vdf_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.vdf_ctx_destroy.argtypes = [vp]
+    L.vdf_ctx_destroy.restype = None
+    L.vdf_last_error.argtypes = [vp]
+    L.vdf_last_error.restype = C.c_char_p
+    L.vdf_ctx_set_shard.argtypes = [vp, u32, u32]
+    L.vdf_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.vdf_ctx_stream.argtypes = [vp]
+    L.vdf_ctx_stream.restype = vp
+    L.vdf_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.vdf_ctx_counters.restype = None
+    L.vdf_ctx_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64), i32]
+    L.vdf_search_self.argtypes = [vp, vp, vp, u64, u32, C.POINTER(Edges)]
+    L.vdf_group_greedy.argtypes = [vp, u64, C.POINTER(Edges), C.POINTER(Groups)]
+    L.vdf_search_self_groups.argtypes = [vp, vp, vp, u64, u32, C.POINTER(Groups)]
+    L.vdf_search_refs.argtypes = [vp, vp, vp, u64, vp, vp, u64, u32, C.POINTER(Csr)]
+    L.vdf_search_self_device.argtypes = [vp, vp, vp, u64, u32, vp, u64, C.POINTER(u64)]
+    L.vdf_search_refs_device.argtypes = [vp, vp, vp, u64, u64, vp, vp, u64, u32, vp, u64, C.POINTER(u64)]
+    L.vdf_group_greedy_device.argtypes = [vp, u64, vp, u64, C.POINTER(Groups)]
+    L.vdf_self_window_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    for f in ("vdf_free_edges", "vdf_free_groups", "vdf_free_csr"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = None
+    L.vdf_hash_stacks.argtypes = [vp, vp, vp, u32, i32, vp, vp, vp]
+    L.vdf_hash_stacks_device.argtypes = [vp, vp, vp, u32, i32, vp, vp, vp]
+    L.vdf_hash_stacks_small_device.argtypes = [vp, vp, vp, u32, i32, vp, vp]
+    L.vdf_hash_from_small.argtypes = [vp, vp, u32, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _hash_array(h) -> np.ndarray:
+    h = np.ascontiguousarray(h, dtype=np.uint64)
+    if h.ndim != 2 or h.shape[1] != 16:
+        raise ValueError("hashes must be [n,16] uint64")
+    return h
+
+
+def _copy_u64(ptr, n: int) -> np.ndarray:
+    if n == 0:
+        return np.zeros(0, dtype=np.uint64)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+
+def make_descs(n: int, width: int, height: int, n_frames: int = 16, pitch: Optional[int] = None) -> np.ndarray:
+    """descriptors for n same-sized stacks laid out back to back ([n][n_frames][height][pitch])"""
+    pitch = pitch or width
+    d = np.zeros(n, dtype=STACK_DESC_DTYPE)
+    fs = pitch * height
+    d["offset"] = np.arange(n, dtype=np.uint64) * np.uint64(fs * n_frames)
+    d["frame_stride"] = fs
+    d["width"], d["height"], d["pitch"], d["n_frames"] = width, height, pitch, n_frames
+    return d
+
+
+class Context:
+    """One GPU, one stream, not thread-safe (see include/vdf_b200.h)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().vdf_ctx_create(int(device), C.byref(self._h))
+        if rc != OK:
+            raise VdfError(rc, "vdf_ctx_create failed (no sm_100 device?) - this library has no CPU fallback")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().vdf_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != OK:
+            raise VdfError(rc, lib().vdf_last_error(self._h).decode(errors="replace"))
+
+    # ---- configuration
+    def set_shard(self, rank: int, world: int):
+        self._check(lib().vdf_ctx_set_shard(self._h, rank, world))
+
+    def set_option(self, key: str, value: int):
+        self._check(lib().vdf_ctx_set_option(self._h, key.encode(), int(value)))
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(lib().vdf_ctx_stream(self._h) or 0)
+
+    def counters(self) -> Tuple[int, int, int]:
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib().vdf_ctx_counters(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def kernel_time(self, which: int, reset: bool = False) -> Tuple[float, int]:
+        """(total device ms, launches) of kernel slot 0 hamming, 1 resize, 2 letterbox, 3 dct+pack"""
+        ms, cnt = C.c_double(), C.c_uint64()
+        self._check(lib().vdf_ctx_kernel_time(self._h, which, C.byref(ms), C.byref(cnt), int(reset)))
+        return ms.value, cnt.value
+
+    # ---- search path, host buffers
+    def search_self(self, hash_sorted, dur_sorted, tol_int: int) -> np.ndarray:
+        h = _hash_array(hash_sorted)
+        d = np.ascontiguousarray(dur_sorted, dtype=np.uint32)
+        e = Edges()
+        self._check(lib().vdf_search_self(self._h, _ptr(h), _ptr(d), len(d), int(tol_int), C.byref(e)))
+        out = _copy_u64(e.ij, 2 * e.n).reshape(-1, 2)
+        lib().vdf_free_edges(C.byref(e))
+        return out
+
+    def _groups(self, g: Groups):
+        ng = int(g.n_groups)
+        gp = _copy_u64(g.group_ptr, ng + 1)
+        mm = _copy_u64(g.member_idx, int(gp[-1]) if ng else 0)
+        lib().vdf_free_groups(C.byref(g))
+        return gp, mm
+
+    def group_greedy(self, n: int, edges):
+        e = np.ascontiguousarray(edges, dtype=np.uint64).reshape(-1, 2)
+        st = Edges(len(e), e.ctypes.data_as(C.POINTER(C.c_uint64)))
+        g = Groups()
+        self._check(lib().vdf_group_greedy(self._h, int(n), C.byref(st), C.byref(g)))
+        return self._groups(g)
+
+    def search_self_groups(self, hash_sorted, dur_sorted, tol_int: int):
+        h = _hash_array(hash_sorted)
+        d = np.ascontiguousarray(dur_sorted, dtype=np.uint32)
+        g = Groups()
+        self._check(lib().vdf_search_self_groups(self._h, _ptr(h), _ptr(d), len(d), int(tol_int), C.byref(g)))
+        return self._groups(g)
+
+    def search_refs(self, cand_sorted, cand_dur_sorted, refs, ref_dur, tol_int: int):
+        c = _hash_array(cand_sorted) if len(cand_sorted) else np.zeros((0, 16), np.uint64)
+        cd = np.ascontiguousarray(cand_dur_sorted, dtype=np.uint32)
+        r = _hash_array(refs) if len(refs) else np.zeros((0, 16), np.uint64)
+        rd = np.ascontiguousarray(ref_dur, dtype=np.uint32)
+        out = Csr()
+        self._check(lib().vdf_search_refs(self._h, _ptr(c), _ptr(cd), len(cd), _ptr(r), _ptr(rd), len(rd), int(tol_int),
+                                          C.byref(out)))
+        rp = _copy_u64(out.row_ptr, len(rd) + 1)
+        ci = _copy_u64(out.col_idx, int(rp[-1]))
+        lib().vdf_free_csr(C.byref(out))
+        return rp, ci
+
+    def self_window_pairs(self, dur_sorted) -> int:
+        d = np.ascontiguousarray(dur_sorted, dtype=np.uint32)
+        v = C.c_uint64()
+        self._check(lib().vdf_self_window_pairs(self._h, _ptr(d), len(d), C.byref(v)))
+        return v.value
+
+    # ---- search path, device pointers
+    def search_self_device(self, d_hash: int, d_dur: int, n: int, tol_int: int, d_keys_out: int, capacity: int) -> int:
+        cnt = C.c_uint64()
+        rc = lib().vdf_search_self_device(self._h, d_hash, d_dur, n, int(tol_int), d_keys_out, capacity, C.byref(cnt))
+        if rc == ERR_EDGE_OVERFLOW:
+            return -int(cnt.value)
+        self._check(rc)
+        return int(cnt.value)
+
+    def search_refs_device(self, d_cand: int, d_cand_dur: int, n_cand: int, cand_base: int, d_refs: int, d_ref_dur: int,
+                           n_ref: int, tol_int: int, d_keys_out: int, capacity: int) -> int:
+        cnt = C.c_uint64()
+        rc = lib().vdf_search_refs_device(self._h, d_cand, d_cand_dur, n_cand, cand_base, d_refs, d_ref_dur, n_ref,
+                                          int(tol_int), d_keys_out, capacity, C.byref(cnt))
+        if rc == ERR_EDGE_OVERFLOW:
+            return -int(cnt.value)
+        self._check(rc)
+        return int(cnt.value)
+
+    def group_greedy_device(self, n: int, d_keys_sorted: int, n_edges: int):
+        g = Groups()
+        self._check(lib().vdf_group_greedy_device(self._h, int(n), d_keys_sorted, int(n_edges), C.byref(g)))
+        return self._groups(g)
+
+    # ---- hashing path
+    def hash_stacks(self, frames: np.ndarray, descs: np.ndarray, cropdetect: int = CROPDETECT_LETTERBOX):
+        """frames: host u8 buffer; descs: STACK_DESC_DTYPE[n] -> (hash [n,16] u64, status [n] i32, crop [n,4] u32)"""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        descs = np.ascontiguousarray(descs, dtype=STACK_DESC_DTYPE)
+        n = len(descs)
+        out = np.zeros((n, 16), dtype=np.uint64)
+        st = np.zeros(n, dtype=np.int32)
+        crop = np.zeros((n, 4), dtype=np.uint32)
+        self._check(lib().vdf_hash_stacks(self._h, _ptr(frames), _ptr(descs), n, int(cropdetect), _ptr(out), _ptr(st),
+                                          _ptr(crop)))
+        return out, st, crop
+
+    def hash_stacks_device(self, d_frames: int, descs: np.ndarray, cropdetect: int, d_out_hash: int):
+        descs = np.ascontiguousarray(descs, dtype=STACK_DESC_DTYPE)
+        n = len(descs)
+        st = np.zeros(n, dtype=np.int32)
+        crop = np.zeros((n, 4), dtype=np.uint32)
+        self._check(lib().vdf_hash_stacks_device(self._h, d_frames, _ptr(descs), n, int(cropdetect), d_out_hash, _ptr(st),
+                                                 _ptr(crop)))
+        return st, crop
+
+    def hash_stacks_small_device(self, d_frames: int, descs: np.ndarray, cropdetect: int, d_out_small: int):
+        descs = np.ascontiguousarray(descs, dtype=STACK_DESC_DTYPE)
+        crop = np.zeros((len(descs), 4), dtype=np.uint32)
+        self._check(lib().vdf_hash_stacks_small_device(self._h, d_frames, _ptr(descs), len(descs), int(cropdetect),
+                                                       d_out_small, _ptr(crop)))
+        return crop
+
+    def hash_from_small(self, small: np.ndarray) -> np.ndarray:
+        small = np.ascontiguousarray(small, dtype=np.uint8).reshape(-1, 4096)
+        out = np.zeros((len(small), 16), dtype=np.uint64)
+        self._check(lib().vdf_hash_from_small(self._h, _ptr(small), len(small), _ptr(out)))
+        return out
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    """Process-wide context on LOCAL_RANK's GPU (one process per GPU)."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx

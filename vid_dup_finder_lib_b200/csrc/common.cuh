@@ -1,0 +1,173 @@
+// common.cuh -- context, scratch buffers and error plumbing shared by the kernels behind include/vdf_b200.h
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vdf_b200.h"
+
+namespace vdf {
+
+constexpr int kTile = 128;                  // hashes per tile edge
+constexpr int kWords32 = 32;                // 1024 bits as u32 words
+constexpr int kTileWords = kTile * kWords32;  // 4096 u32 = 16 KB
+
+// growable device buffer (never shrinks; owned by the context)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+// one axis of the Lanczos3 u8 resize (fast_image_resize Normalizer16) for a given input size, resident in HBM
+struct CoefTable {
+    uint32_t in_size = 0, window = 0, precision = 0;
+    uint32_t* d_bounds = nullptr;  // 16 x (start, size)
+    int16_t* d_k = nullptr;        // 16 x window
+    int8_t* d_kb = nullptr;        // tensor-core operand: [2][16][in_size padded] split hi/lo bytes (built lazily)
+    std::vector<uint32_t> h_bounds;
+    std::vector<int16_t> h_k;
+};
+
+}  // namespace vdf
+
+struct vdf_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    std::string err;
+    uint32_t rank = 0, world = 1;
+    uint64_t max_edges = 1ull << 28, initial_edges = 1ull << 22;
+    int search_variant = 0;
+    int hash_variant = 0;
+    uint64_t launches = 0, h2d = 0, d2h = 0;
+    // device time of the dominant kernels (CUDA events on `stream`): 0 hamming tiles, 1 resize, 2 letterbox, 3 dct+pack
+    cudaEvent_t kt0[4] = {nullptr, nullptr, nullptr, nullptr}, kt1[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool kt_pending[4] = {false, false, false, false};
+    double kt_ms[4] = {0, 0, 0, 0};
+    uint64_t kt_n[4] = {0, 0, 0, 0};
+
+    // search scratch
+    vdf::DevBuf row_tiles, col_tiles, row_lo, row_hi, row_id, tile_range, raw_keys, sort_tmp, misc, keys_a, keys_b;
+    vdf::DevBuf in_hash, in_dur, in_hash2, in_dur2, ref_perm, ref_key;
+    // grouping scratch
+    vdf::DevBuf g_rk, g_rks, g_state, g_parent, g_wl0, g_wla, g_wlb, g_mk, g_mks, g_flag, g_scan, g_gp, g_mem;
+    // hashing scratch
+    vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc;
+    vdf::PinnedBuf pin_a, pin_b, pin_frames[2];
+    std::map<uint32_t, vdf::CoefTable> coef_cache;
+    bool dct_consts_loaded = false;
+};
+
+#define VDF_CUDA(ctx, call)                                                                       \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                         std::to_string(__LINE__) + ")";                                          \
+            return VDF_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define VDF_ALLOC(ctx, call)                                                                      \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                         std::to_string(__LINE__) + ")";                                          \
+            cudaGetLastError();                                                                   \
+            return VDF_ERR_ALLOC;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+#define VDF_LAUNCHED(ctx)                                                                         \
+    do {                                                                                          \
+        (ctx)->launches++;                                                                        \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                         std::to_string(__LINE__) + ")";                                          \
+            return VDF_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define VDF_TRY(expr)                \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != VDF_OK) return rc__; \
+    } while (0)
+
+namespace vdf {
+// kernel timing helpers (api.cu)
+void kt_begin(vdf_ctx* ctx, int which);
+void kt_end(vdf_ctx* ctx, int which);
+void kt_collect(vdf_ctx* ctx);
+// search.cu
+int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_dur, uint64_t n, uint32_t tol,
+                       uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out);
+int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_cand_dur, uint64_t n_cand,
+                       uint64_t cand_base, const uint64_t* d_refs, const uint32_t* d_ref_dur, uint64_t n_ref,
+                       uint32_t tol, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out);
+int self_window_pairs(vdf_ctx* ctx, const uint32_t* d_dur, uint64_t n, uint64_t* pairs_out);
+int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n);
+// group.cu
+int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, vdf_groups* out);
+// hash.cu
+int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_desc* desc, uint32_t n, int cropdetect,
+                       uint64_t* d_out_hash, uint8_t* d_out_small, int32_t* out_status, uint32_t* out_crop);
+int hash_from_small_device(vdf_ctx* ctx, const uint8_t* d_small, uint32_t n, uint64_t* d_out_hash);
+void free_coef_cache(vdf_ctx* ctx);
+}  // namespace vdf

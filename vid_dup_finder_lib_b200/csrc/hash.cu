@@ -1,0 +1,536 @@
+// hash.cu -- frame stack -> VideoHash on the GPU.
+//
+// Replaces the compute tail of gen_hash (video_hash_builder.rs:214-223):
+//   H2  letterbox_side_kernel + crop_combine_kernel   <- cropdetect_letterbox / letterbox_crop / Crop::union
+//                                                        (vid_dup_finder_common/src/video_frames_gray.rs:38-128,201-210,
+//                                                         crop.rs:53-68)
+//   H3  resize kernels                                <- crop_resize_buf (resize_gray.rs:11-54): fast_image_resize
+//                                                        Lanczos3 u8 convolution, horizontal pass into a u8 temp,
+//                                                        then vertical pass, i16 coefficients, i32 accumulate
+//   H4  dct_pack_kernel                               <- Dct3d::from_images + dct_3d (dct_3d.rs:15-53,
+//                                                        raw_dct_ops.rs:107-142): f64, split-radix DCT-II(16) x3
+//   H5  (same kernel)                                 <- hash_bits + Lsb0 pack (dct_3d.rs:55-66, video_hash.rs:63-70)
+//
+// Everything integer is bit-exact by construction.  The DCT runs in f64 with explicit round-to-nearest
+// multiplies/adds (no FMA contraction) in the same operation order as a split-radix butterfly, so exact zeros
+// (static or mirror-symmetric content) stay exact zeros, as they do in the reference's rustdct butterflies.
+//
+// The i16 coefficient tables depend only on the cropped size, are generated on the host in f64 (libm sin, like
+// the reference) and cached in HBM per size.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vdf {
+
+// ================================================================================ H2: letterbox crop detect
+struct StackDev {
+    uint64_t offset, frame_stride;
+    uint32_t width, height, pitch;
+    int32_t status;
+};
+
+constexpr int kLbTol = 16;  // LetterboxColour::AnyColour(16), video_frames_gray.rs:206
+constexpr int kColPanel = 32;
+constexpr int kRowPanel = 8;
+
+// Decide one strip from its 256-bin histogram (one warp).  mode = LAST maximum (Iterator::max_by_key,
+// video_frames_gray.rs:82-87); letterbox iff count(|p - mode| <= tol) / len > 0.9 (:89-100), evaluated as
+// 10*count > 9*len (equivalent for every len < 2^28, see tests/test_oracle_letterbox.py).
+__device__ __forceinline__ bool strip_is_letterbox(const uint32_t* hist, uint32_t len, int lane) {
+    uint32_t best_c = 0;
+    int best_v = -1;
+    for (int v = lane; v < 256; v += 32) {
+        uint32_t c = hist[v];
+        if (c > best_c || (c == best_c && v > best_v)) best_c = c, best_v = v;
+    }
+    for (int o = 16; o; o >>= 1) {
+        uint32_t oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        int ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+        if (oc > best_c || (oc == best_c && ov > best_v)) best_c = oc, best_v = ov;
+    }
+    const int lo = max(best_v - kLbTol, 0), hi = min(best_v + kLbTol, 255);
+    uint32_t cnt = 0;
+    for (int v = lo + lane; v <= hi; v += 32) cnt += hist[v];
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    return 10ull * cnt > 9ull * len;
+}
+
+// grid = n_stacks * 2 frames (0 and 8: step_by(8).take(8) over 16 frames) * 4 sides; 256 threads.
+// Each CTA walks 1-px strips from its edge inwards in panels, stopping at the first non-letterbox strip.
+__global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __restrict__ frames,
+                                                             const StackDev* __restrict__ stacks,
+                                                             uint32_t* __restrict__ sides /* [n][2][4] l,r,t,b */) {
+    __shared__ uint32_t hist[kColPanel * 257];
+    __shared__ uint32_t flags[kColPanel];
+    __shared__ uint32_t s_count, s_stop;
+    const uint32_t b = blockIdx.x, side = b & 3, fr = (b >> 2) & 1, s = b >> 3;
+    const StackDev sd = stacks[s];
+    if (sd.status != VDF_STACK_OK) return;
+    const uint8_t* img = frames + sd.offset + (uint64_t)(fr * 8) * sd.frame_stride;
+    const uint32_t W = sd.width, H = sd.height, P = sd.pitch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_count = 0, s_stop = 0;
+    const bool cols = side < 2;  // 0 left, 1 right, 2 top, 3 bottom
+    const uint32_t limit = cols ? W : H, len = cols ? H : W;
+    const uint32_t panel = cols ? kColPanel : kRowPanel;
+    for (uint32_t base = 0; base < limit; base += panel) {
+        for (int q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
+        __syncthreads();
+        if (cols) {
+            const uint32_t idx = base + lane;
+            const bool act = idx < W;
+            const uint32_t x = side == 0 ? idx : W - 1 - idx;
+            for (uint32_t y = warp; y < H; y += 8)
+                if (act) atomicAdd(&hist[lane * 257 + img[(uint64_t)y * P + x]], 1u);
+        } else {
+            const uint32_t idx = base + warp;
+            if (idx < H) {
+                const uint32_t y = side == 2 ? idx : H - 1 - idx;
+                const uint8_t* row = img + (uint64_t)y * P;
+                for (uint32_t x0 = 0; x0 < W; x0 += 32) {
+                    const uint32_t x = x0 + lane;
+                    const bool act = x < W;
+                    const uint32_t v = act ? row[x] : 0x100u + lane;
+                    const uint32_t m = __match_any_sync(0xffffffffu, v);  // one atomic per distinct value
+                    if (act && lane == __ffs(m) - 1) atomicAdd(&hist[warp * 257 + v], (uint32_t)__popc(m));
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t k = warp; k < panel; k += 8) {
+            bool ok = false;
+            if (base + k < limit) ok = strip_is_letterbox(hist + k * 257, len, lane);
+            if (lane == 0) flags[k] = ok;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t c = s_count;
+            for (uint32_t k = 0; k < panel && base + k < limit; ++k) {
+                if (!flags[k]) {
+                    s_stop = 1;
+                    break;
+                }
+                ++c;
+            }
+            s_count = c;
+        }
+        __syncthreads();
+        if (s_stop) break;
+    }
+    if (tid == 0) sides[(s * 2 + fr) * 4 + side] = s_count;
+}
+
+// per frame: keep (l,r,t,b) only if at least one pixel remains each way (video_frames_gray.rs:119-127);
+// across frames 0 and 8: per-side minimum (Crop::union, crop.rs:53-68)
+__global__ void crop_combine_kernel(const StackDev* __restrict__ stacks, const uint32_t* __restrict__ sides, uint32_t n,
+                                    uint32_t* __restrict__ crop /* [n][4] */) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t out[4] = {0, 0, 0, 0};
+    if (stacks[s].status == VDF_STACK_OK) {
+        const int W = (int)stacks[s].width, H = (int)stacks[s].height;
+        for (int fr = 0; fr < 2; ++fr) {
+            uint32_t c[4];
+            for (int k = 0; k < 4; ++k) c[k] = sides[(s * 2 + fr) * 4 + k];
+            if (!(W - (int)c[0] - (int)c[1] >= 1 && H - (int)c[2] - (int)c[3] >= 1)) c[0] = c[1] = c[2] = c[3] = 0;
+            for (int k = 0; k < 4; ++k) out[k] = fr == 0 ? c[k] : min(out[k], c[k]);
+        }
+    }
+    for (int k = 0; k < 4; ++k) crop[s * 4 + k] = out[k];
+}
+
+// ================================================================================ H3: crop + Lanczos3 resize
+struct StackJob {
+    uint64_t offset, frame_stride;
+    uint32_t pitch, left, top, cw, ch;
+    int32_t status;
+    const uint32_t* bh;  // 16 x (start,size), horizontal
+    const int16_t* kh;   // 16 x win_h
+    const uint32_t* bv;
+    const int16_t* kv;
+    uint32_t win_h, prec_h, win_v, prec_v;
+};
+
+__device__ __forceinline__ uint8_t clip8(int32_t v, uint32_t precision) {
+    return (uint8_t)min(max(v >> precision, 0), 255);
+}
+
+// General path (any shape / alignment): one CTA per (stack, frame).  Horizontal pass: one thread per
+// (row, output) walks its coefficient window; the u8 intermediate [ch][16] lives in shared memory
+// (the reference rounds to u8 between the passes); vertical pass: one thread per output pixel.
+__global__ void __launch_bounds__(256) resize_general_kernel(const uint8_t* __restrict__ frames,
+                                                             const StackJob* __restrict__ jobs,
+                                                             uint8_t* __restrict__ small /* [n][16][16][16] */) {
+    extern __shared__ uint8_t tmp[];  // ch x 16
+    const uint32_t s = blockIdx.x >> 4, t = blockIdx.x & 15;
+    const StackJob j = jobs[s];
+    if (j.status != VDF_STACK_OK) return;
+    const uint8_t* img = frames + j.offset + (uint64_t)t * j.frame_stride + (uint64_t)j.top * j.pitch + j.left;
+    const int32_t init_h = 1 << (j.prec_h - 1);
+    for (uint32_t it = threadIdx.x; it < j.ch * 16; it += blockDim.x) {
+        const uint32_t row = it >> 4, o = it & 15;
+        const uint32_t s0 = j.bh[2 * o], sz = j.bh[2 * o + 1];
+        const int16_t* k = j.kh + o * j.win_h;
+        const uint8_t* p = img + (uint64_t)row * j.pitch + s0;
+        int32_t acc = init_h;
+        for (uint32_t q = 0; q < sz; ++q) acc += (int32_t)p[q] * (int32_t)k[q];
+        tmp[it] = clip8(acc, j.prec_h);
+    }
+    __syncthreads();
+    const int32_t init_v = 1 << (j.prec_v - 1);
+    for (uint32_t it = threadIdx.x; it < 256; it += blockDim.x) {
+        const uint32_t oy = it >> 4, ox = it & 15;
+        const uint32_t s0 = j.bv[2 * oy], sz = j.bv[2 * oy + 1];
+        const int16_t* k = j.kv + oy * j.win_v;
+        int32_t acc = init_v;
+        for (uint32_t q = 0; q < sz; ++q) acc += (int32_t)tmp[(s0 + q) * 16 + ox] * (int32_t)k[q];
+        small[((uint64_t)s * 16 + t) * 256 + it] = clip8(acc, j.prec_v);
+    }
+}
+
+// ================================================================================ H4 + H5: 3-D DCT, threshold, pack
+// twiddles: [0..7] n=16 (re,im) x4, [8..11] n=8 (re,im) x2, [12..13] n=4, [14] FRAC_1_SQRT_2
+__constant__ double c_tw[16];
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+__device__ __forceinline__ void dct2_2(double& b0, double& b1) {
+    const double s = dadd(b0, b1);
+    b1 = dmul(dsub(b0, b1), c_tw[14]);
+    b0 = s;
+}
+__device__ __forceinline__ void dct2_4(double* b) {
+    const double re = c_tw[12], im = c_tw[13];
+    const double lower = dsub(b[0], b[3]), upper = dsub(b[2], b[1]);
+    double e0 = dadd(b[0], b[3]), e1 = dadd(b[1], b[2]);
+    dct2_2(e0, e1);
+    b[0] = e0;
+    b[1] = dsub(dmul(lower, re), dmul(upper, im));
+    b[2] = e1;
+    b[3] = dadd(dmul(upper, re), dmul(lower, im));
+}
+// split radix: one half-size DCT-II on the mirrored sums, two quarter-size DCT-IIs on the rotated differences
+template <int N>
+__device__ __forceinline__ void dct2_sr(double* x);
+template <>
+__device__ __forceinline__ void dct2_sr<2>(double* x) {
+    dct2_2(x[0], x[1]);
+}
+template <>
+__device__ __forceinline__ void dct2_sr<4>(double* x) {
+    dct2_4(x);
+}
+template <int N>
+__device__ __forceinline__ void dct2_sr(double* x) {
+    constexpr int H = N / 2, Q = N / 4;
+    constexpr int TW = (N == 16) ? 0 : 8;
+    double d2[H], ev[Q], od[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const double bot = x[i], top = x[N - 1 - i];
+        const double hb = x[H - 1 - i], ht = x[H + i];
+        d2[i] = dadd(top, bot);
+        d2[H - 1 - i] = dadd(hb, ht);
+        const double lower = dsub(bot, top), upper = dsub(hb, ht);
+        const double re = c_tw[TW + 2 * i], im = c_tw[TW + 2 * i + 1];
+        const double c = dadd(dmul(lower, re), dmul(upper, im));
+        const double s = dsub(dmul(upper, re), dmul(lower, im));
+        ev[i] = c;
+        od[Q - 1 - i] = (i % 2 == 0) ? s : -s;
+    }
+    dct2_sr<H>(d2);
+    dct2_sr<Q>(ev);
+    dct2_sr<Q>(od);
+    x[0] = d2[0];
+    x[1] = ev[0];
+    x[2] = d2[1];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        const double c = ev[i];
+        const double s = ((i + Q) % 2 == 0) ? -od[Q - i] : od[Q - i];
+        x[4 * i - 1] = dadd(c, s);
+        x[4 * i] = d2[2 * i];
+        x[4 * i + 1] = dsub(c, s);
+        x[4 * i + 2] = d2[2 * i + 1];
+    }
+    x[N - 1] = -od[0];
+}
+
+// cube index with a 17-double row pitch: conflict-free for all three passes
+__device__ __forceinline__ int cidx(int t, int x, int y) { return (t * 16 + x) * 17 + y; }
+
+// one CTA (256 threads) per stack: small [t][row][col] u8 -> m[t][x=col][y=row] = p - 128 (dct_3d.rs:40-44,76),
+// DCT along y, x, t (raw_dct_ops.rs:107-142), bit t*100+x*10+y = coef > 0.0 (dct_3d.rs:55-66), Lsb0 words.
+__global__ void __launch_bounds__(256) dct_pack_kernel(const uint8_t* __restrict__ small, const int32_t* __restrict__ status,
+                                                       uint32_t n, uint32_t* __restrict__ out_hash /* [n][32] u32 */) {
+    __shared__ double cube[16 * 16 * 17];
+    const uint32_t s = blockIdx.x;
+    const int tid = threadIdx.x;
+    uint32_t* out = out_hash + (uint64_t)s * 32;
+    if (status && status[s] != VDF_STACK_OK) {
+        if (tid < 32) out[tid] = 0;
+        return;
+    }
+    const uint8_t* sm = small + (uint64_t)s * 4096;
+    for (int q = tid; q < 4096; q += 256) {
+        const int t = q >> 8, row = (q >> 4) & 15, col = q & 15;
+        cube[cidx(t, col, row)] = (double)sm[q] - 128.0;
+    }
+    __syncthreads();
+    double v[16];
+    {  // along y: line (t, x) = tid
+        const int t = tid >> 4, x = tid & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(t, x, k)];
+        dct2_sr<16>(v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cube[cidx(t, x, k)] = v[k];
+    }
+    __syncthreads();
+    {  // along x: line (t, y)
+        const int t = tid >> 4, y = tid & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(t, k, y)];
+        dct2_sr<16>(v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cube[cidx(t, k, y)] = v[k];
+    }
+    __syncthreads();
+    {  // along t: line (x, y)
+        const int x = tid >> 4, y = tid & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(k, x, y)];
+        dct2_sr<16>(v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cube[cidx(k, x, y)] = v[k];
+    }
+    __syncthreads();
+    for (int b = tid; b < 1024; b += 256) {
+        bool bit = false;
+        if (b < VDF_HASH_BITS) {
+            const int t = b / 100, x = (b / 10) % 10, y = b % 10;
+            bit = cube[cidx(t, x, y)] > 0.0;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if ((tid & 31) == 0) out[b >> 5] = word;
+    }
+}
+
+// ================================================================================ host side
+// fast_image_resize 5.1 (third-party, un-vendored): Lanczos3, adaptive kernel size, coefficients
+// normalised in f64 then quantised to i16 with the largest precision that keeps the maximum below 2^15.
+static double lanczos3(double x) {
+    auto sinc = [](double v) {
+        if (v == 0.0) return 1.0;
+        v *= 3.14159265358979323846;
+        return std::sin(v) / v;
+    };
+    return (x >= -3.0 && x < 3.0) ? sinc(x) * sinc(x / 3.0) : 0.0;
+}
+
+static void build_table(uint32_t in_size, CoefTable& t) {
+    const uint32_t out_size = VDF_DCT_SIZE;
+    const double scale = (double)in_size / (double)out_size;
+    const double fscale = scale > 1.0 ? scale : 1.0;
+    const double radius = 3.0 * fscale, recip = 1.0 / fscale;
+    const uint32_t window = (uint32_t)std::ceil(radius) * 2 + 1;
+    std::vector<double> w((size_t)window * out_size, 0.0);
+    t.h_bounds.assign(2 * out_size, 0);
+    for (uint32_t o = 0; o < out_size; ++o) {
+        const double in_center = ((double)o + 0.5) * scale;
+        const uint32_t x_min = (uint32_t)std::fmax(std::floor(in_center - radius), 0.0);
+        const uint32_t x_max = (uint32_t)std::fmin(std::ceil(in_center + radius), (double)in_size);
+        const double center = in_center - 0.5;
+        double* row = w.data() + (size_t)o * window;
+        uint32_t start = x_min, end = x_max, cnt = 0;
+        double sum = 0.0;
+        for (uint32_t x = x_min; x < x_max; ++x) {
+            const double v = lanczos3(((double)x - center) * recip);
+            if (x == start && v == 0.0) {
+                ++start;
+                continue;
+            }
+            row[cnt++] = v;
+            sum += v;
+        }
+        for (uint32_t q = cnt; q > 0 && end > start && row[q - 1] == 0.0; --q) --end;
+        if (sum != 0.0)
+            for (uint32_t q = 0; q < cnt; ++q) row[q] /= sum;
+        t.h_bounds[2 * o] = start;
+        t.h_bounds[2 * o + 1] = end - start;
+    }
+    double max_w = 0.0;
+    for (double v : w) max_w = std::fmax(max_w, v);
+    uint32_t precision = 0;
+    for (uint32_t cur = 0; cur < 22; ++cur) {
+        precision = cur;
+        const double nv = std::round(max_w * (double)(1 << (cur + 1)));
+        if (nv >= (double)(1 << 15)) break;
+    }
+    t.h_k.resize(w.size());
+    const double sc = (double)(1 << precision);
+    for (size_t q = 0; q < w.size(); ++q) {
+        double v = std::round(w[q] * sc);
+        v = std::fmin(std::fmax(v, -32768.0), 32767.0);
+        t.h_k[q] = (int16_t)v;
+    }
+    t.in_size = in_size;
+    t.window = window;
+    t.precision = precision;
+}
+
+static int get_table(vdf_ctx* ctx, uint32_t in_size, const CoefTable** out) {
+    auto it = ctx->coef_cache.find(in_size);
+    if (it == ctx->coef_cache.end()) {
+        CoefTable t;
+        build_table(in_size, t);
+        VDF_ALLOC(ctx, cudaMalloc(&t.d_bounds, t.h_bounds.size() * 4));
+        VDF_ALLOC(ctx, cudaMalloc(&t.d_k, t.h_k.size() * 2));
+        VDF_CUDA(ctx, cudaMemcpyAsync(t.d_bounds, t.h_bounds.data(), t.h_bounds.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        VDF_CUDA(ctx, cudaMemcpyAsync(t.d_k, t.h_k.data(), t.h_k.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors may move when the map rebalances
+        it = ctx->coef_cache.emplace(in_size, std::move(t)).first;
+    }
+    *out = &it->second;
+    return VDF_OK;
+}
+
+void free_coef_cache(vdf_ctx* ctx) {
+    for (auto& kv : ctx->coef_cache) {
+        if (kv.second.d_bounds) cudaFree(kv.second.d_bounds);
+        if (kv.second.d_k) cudaFree(kv.second.d_k);
+        if (kv.second.d_kb) cudaFree(kv.second.d_kb);
+    }
+    ctx->coef_cache.clear();
+}
+
+static int load_dct_consts(vdf_ctx* ctx) {
+    if (ctx->dct_consts_loaded) return VDF_OK;
+    // rustdct::twiddles::single_twiddle(i, fft_len).conj()
+    auto tw = [](unsigned i, unsigned fft_len, double* re, double* im) {
+        const double constant = -2.0 * 3.14159265358979323846 / (double)fft_len;
+        const double angle = constant * (double)i;
+        *re = std::cos(angle);
+        *im = -std::sin(angle);
+    };
+    double h[16] = {0};
+    for (unsigned i = 0; i < 4; ++i) tw(2 * i + 1, 64, &h[2 * i], &h[2 * i + 1]);
+    for (unsigned i = 0; i < 2; ++i) tw(2 * i + 1, 32, &h[8 + 2 * i], &h[8 + 2 * i + 1]);
+    tw(1, 16, &h[12], &h[13]);
+    h[14] = 0.70710678118654752440;  // std::f64::consts::FRAC_1_SQRT_2
+    VDF_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tw, h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->dct_consts_loaded = true;
+    return VDF_OK;
+}
+
+int hash_from_small_device(vdf_ctx* ctx, const uint8_t* d_small, uint32_t n, uint64_t* d_out_hash) {
+    if (n == 0) return VDF_OK;
+    VDF_TRY(load_dct_consts(ctx));
+    dct_pack_kernel<<<n, 256, 0, ctx->stream>>>(d_small, nullptr, n, reinterpret_cast<uint32_t*>(d_out_hash));
+    VDF_LAUNCHED(ctx);
+    return VDF_OK;
+}
+
+int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_desc* desc, uint32_t n, int cropdetect,
+                       uint64_t* d_out_hash, uint8_t* d_out_small, int32_t* out_status, uint32_t* out_crop) {
+    if (n == 0) return VDF_OK;
+    if (cropdetect != VDF_CROPDETECT_NONE && cropdetect != VDF_CROPDETECT_LETTERBOX) {
+        ctx->err = "cropdetect must be VDF_CROPDETECT_NONE or VDF_CROPDETECT_LETTERBOX";
+        return VDF_ERR_INVALID;
+    }
+    VDF_TRY(load_dct_consts(ctx));
+    cudaStream_t st = ctx->stream;
+    // status per stack, decided on the host exactly where the reference decides it
+    std::vector<StackDev> sd(n);
+    std::vector<int32_t> status(n);
+    for (uint32_t s = 0; s < n; ++s) {
+        const vdf_stack_desc& d = desc[s];
+        int32_t stt = VDF_STACK_OK;
+        if (d.flags & VDF_STACK_FLAG_MIXED_SIZES) stt = VDF_STACK_VIDPROC;         // video_hash_builder.rs:169-186
+        else if (d.n_frames < VDF_DCT_SIZE) stt = VDF_STACK_NOT_ENOUGH_FRAMES;     // dct_3d.rs:47-52
+        else if (d.width == 0 || d.height == 0 || d.pitch < d.width) {
+            ctx->err = "stack " + std::to_string(s) + ": bad geometry";
+            return VDF_ERR_INVALID;
+        }
+        status[s] = stt;
+        sd[s] = StackDev{d.offset, d.frame_stride, d.width, d.height, d.pitch, stt};
+    }
+    std::vector<uint32_t> crop((size_t)n * 4, 0);
+    if (cropdetect == VDF_CROPDETECT_LETTERBOX) {
+        VDF_ALLOC(ctx, ctx->h_desc.ensure((size_t)n * sizeof(StackDev)));
+        VDF_ALLOC(ctx, ctx->h_sides.ensure((size_t)n * 8 * 4));
+        VDF_ALLOC(ctx, ctx->h_crop.ensure((size_t)n * 4 * 4));
+        VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_desc.p, sd.data(), (size_t)n * sizeof(StackDev), cudaMemcpyHostToDevice, st));
+        VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_sides.p, 0, (size_t)n * 8 * 4, st));
+        kt_begin(ctx, 2);
+        letterbox_side_kernel<<<n * 8, 256, 0, st>>>(d_frames, ctx->h_desc.as<StackDev>(), ctx->h_sides.as<uint32_t>());
+        kt_end(ctx, 2);
+        VDF_LAUNCHED(ctx);
+        crop_combine_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctx->h_desc.as<StackDev>(), ctx->h_sides.as<uint32_t>(), n,
+                                                             ctx->h_crop.as<uint32_t>());
+        VDF_LAUNCHED(ctx);
+        VDF_CUDA(ctx, cudaMemcpyAsync(crop.data(), ctx->h_crop.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+        VDF_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    // coefficient tables for the cropped sizes (cached per size in HBM)
+    std::vector<StackJob> jobs(n);
+    uint32_t max_ch = 1;
+    for (uint32_t s = 0; s < n; ++s) {
+        StackJob& j = jobs[s];
+        std::memset(&j, 0, sizeof j);
+        j.status = status[s];
+        if (status[s] != VDF_STACK_OK) continue;
+        const vdf_stack_desc& d = desc[s];
+        const uint32_t* c = &crop[(size_t)s * 4];
+        j.offset = d.offset, j.frame_stride = d.frame_stride, j.pitch = d.pitch;
+        j.left = c[0], j.top = c[2];
+        j.cw = d.width - c[0] - c[1], j.ch = d.height - c[2] - c[3];  // Crop::as_view_args, crop.rs:92-103
+        const CoefTable *th, *tv;
+        VDF_TRY(get_table(ctx, j.cw, &th));
+        VDF_TRY(get_table(ctx, j.ch, &tv));
+        j.bh = th->d_bounds, j.kh = th->d_k, j.win_h = th->window, j.prec_h = th->precision;
+        j.bv = tv->d_bounds, j.kv = tv->d_k, j.win_v = tv->window, j.prec_v = tv->precision;
+        max_ch = std::max(max_ch, j.ch);
+    }
+    VDF_ALLOC(ctx, ctx->h_jobs.ensure((size_t)n * sizeof(StackJob) + (size_t)n * 4));
+    StackJob* d_jobs = ctx->h_jobs.as<StackJob>();
+    int32_t* d_status = reinterpret_cast<int32_t*>(d_jobs + n);
+    VDF_CUDA(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)n * sizeof(StackJob), cudaMemcpyHostToDevice, st));
+    VDF_CUDA(ctx, cudaMemcpyAsync(d_status, status.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    uint8_t* d_small = d_out_small;
+    if (!d_small) {
+        VDF_ALLOC(ctx, ctx->h_small.ensure((size_t)n * 4096));
+        d_small = ctx->h_small.as<uint8_t>();
+    }
+    const size_t smem = (size_t)max_ch * 16;
+    if (smem > 200 * 1024) {
+        ctx->err = "frame height beyond the general resize kernel's shared-memory budget";
+        return VDF_ERR_INVALID;
+    }
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        VDF_CUDA(ctx, cudaFuncSetAttribute(resize_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    kt_begin(ctx, 1);
+    resize_general_kernel<<<n * 16, 256, smem, st>>>(d_frames, d_jobs, d_small);
+    kt_end(ctx, 1);
+    VDF_LAUNCHED(ctx);
+    if (d_out_hash) {
+        kt_begin(ctx, 3);
+        dct_pack_kernel<<<n, 256, 0, st>>>(d_small, d_status, n, reinterpret_cast<uint32_t*>(d_out_hash));
+        kt_end(ctx, 3);
+        VDF_LAUNCHED(ctx);
+    }
+    VDF_CUDA(ctx, cudaStreamSynchronize(st));  // jobs/status host vectors go out of scope
+    if (out_status) std::memcpy(out_status, status.data(), (size_t)n * 4);
+    if (out_crop) std::memcpy(out_crop, crop.data(), (size_t)n * 16);
+    return VDF_OK;
+}
+
+}  // namespace vdf

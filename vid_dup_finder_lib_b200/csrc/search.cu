@@ -1,0 +1,534 @@
+// search.cu -- tiled XOR+POPC Hamming search.
+//
+// Replaces the comparison loops of Search::search_self (search_algorithm.rs:81-117,140-156) and
+// Search::search_one (search_algorithm.rs:63-77) with VideoHash::hamming_distance (video_hash.rs:311-317).
+//
+// Data layout in HBM: the sorted hash table is re-tiled once per call into
+//     tiles[tile][word32 0..31][hash 0..127]          (16 KB per tile, zero padded)
+// so that (a) one tile is ONE contiguous 16 KB block that a single cp.async.bulk (TMA bulk copy, SASS UBLKCP)
+// lands in shared memory, completing on an mbarrier, and (b) a warp reading word w of 4 consecutive hashes per
+// lane does conflict-free 128-bit shared loads.  A CTA owns a row tile (128 hashes) and streams a chunk of column
+// tiles through a 3-stage shared-memory ring; each of its 256 threads keeps an 8x8 block of pair accumulators
+// in registers.  Pairs under the tolerance are appended (atomic counter) to an edge buffer as u64 keys
+// (row << 32 | col); the window test lo[row] <= col < hi[row] is evaluated only for those rare pairs.
+// The per-row windows make the same kernel serve search_self (lo = i+1, hi = end of the 1.1x duration window)
+// and search_with_references (lo/hi = the 0.95x..1.05x duration slice of the candidate table).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace vdf {
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// TMA bulk copy global -> shared (1-D, no tensor map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ re-tiling
+// in: [n][32] u32 (hash-major, 128 B per hash); out: [ceil(n/128)][32][128] u32.  perm (optional) gathers rows.
+__global__ void __launch_bounds__(256) retile_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm,
+                                                     uint64_t n, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s[kWords32][kTile + 1];
+    const uint64_t tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    // 128 hashes x 8 uint4 = 1024 uint4 loads, coalesced along the hash
+    for (int q = tid; q < kTile * 8; q += 256) {
+        int h = q >> 3, c = q & 7;
+        uint64_t g = tile * kTile + h;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (g < n) {
+            uint64_t src = perm ? perm[g] : g;
+            v = reinterpret_cast<const uint4*>(in)[src * 8 + c];
+        }
+        s[4 * c + 0][h] = v.x;
+        s[4 * c + 1][h] = v.y;
+        s[4 * c + 2][h] = v.z;
+        s[4 * c + 3][h] = v.w;
+    }
+    __syncthreads();
+    uint32_t* o = out + tile * kTileWords;
+    for (int q = tid; q < kTileWords; q += 256) o[q] = s[q >> 7][q & 127];
+}
+
+// ------------------------------------------------------------------------------------------------ windows
+// Rust `f64 as u32` == cvt.rzi.u32.f64 (saturating, NaN -> 0)
+__device__ __forceinline__ uint32_t f64_as_u32(double v) { return __double2uint_rz(v); }
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* d, uint32_t n, uint32_t v) {  // first k: d[k] >= v
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (d[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* d, uint32_t n, uint32_t v) {  // first k: d[k] > v
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (d[mid] <= v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// search_self: candidate j of target i must satisfy i < j and dur[j] <= (f64(dur[i]) * 1.1) as u32
+// (search_algorithm.rs:99,110).  n_pad = rows rounded up to whole tiles; padded rows get an empty window.
+__global__ void self_window_kernel(const uint32_t* __restrict__ dur, uint32_t n, uint32_t n_pad,
+                                   uint32_t* __restrict__ row_lo, uint32_t* __restrict__ row_hi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    if (i >= n) {
+        row_lo[i] = 0;
+        row_hi[i] = 0;
+        return;
+    }
+    uint32_t thresh = f64_as_u32((double)dur[i] * 1.1);
+    row_lo[i] = i + 1;
+    row_hi[i] = upper_bound_u32(dur, n, thresh);
+}
+
+// search_with_references: duration_slice (search_algorithm.rs:173-185), rows in the (sorted-by-lo) internal order
+__global__ void ref_window_kernel(const uint32_t* __restrict__ cand_dur, uint32_t n_cand,
+                                  const uint32_t* __restrict__ ref_dur, const uint32_t* __restrict__ perm, uint32_t n_ref,
+                                  uint32_t n_pad, uint32_t* __restrict__ row_lo, uint32_t* __restrict__ row_hi) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    if (r >= n_ref) {
+        row_lo[r] = 0;
+        row_hi[r] = 0;
+        return;
+    }
+    uint32_t d = ref_dur[perm ? perm[r] : r];
+    uint32_t lo_d = f64_as_u32((double)d * 0.95), hi_d = f64_as_u32((double)d * 1.05);
+    row_lo[r] = lower_bound_u32(cand_dur, n_cand, lo_d);
+    row_hi[r] = upper_bound_u32(cand_dur, n_cand, hi_d);
+}
+
+// sort key for the references: start of their duration slice (so that a row tile's slices overlap)
+__global__ void ref_sortkey_kernel(const uint32_t* __restrict__ ref_dur, uint32_t n_ref, uint32_t* __restrict__ key,
+                                   uint32_t* __restrict__ idx) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_ref) return;
+    key[r] = ref_dur[r];
+    idx[r] = r;
+}
+
+// per row tile: the range of column tiles any of its rows can match; misc[0] = max span, misc[1..2] = pair count
+__global__ void tile_range_kernel(const uint32_t* __restrict__ row_lo, const uint32_t* __restrict__ row_hi,
+                                  uint32_t n_row_tiles, uint2* __restrict__ tile_range,
+                                  unsigned long long* __restrict__ misc) {
+    uint32_t I = blockIdx.x;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    unsigned long long pairs = 0;
+    for (int r = threadIdx.x; r < kTile; r += blockDim.x) {
+        uint32_t a = row_lo[I * kTile + r], b = row_hi[I * kTile + r];
+        if (a < b) {
+            lo = min(lo, a);
+            hi = max(hi, b);
+            pairs += b - a;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+    }
+    __shared__ uint32_t slo[4], shi[4];
+    __shared__ unsigned long long sp[4];
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) slo[w] = lo, shi[w] = hi, sp[w] = pairs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) lo = min(lo, slo[k]), hi = max(hi, shi[k]), pairs += sp[k];
+        uint2 r = make_uint2(0, 0);
+        if (lo < hi) r = make_uint2(lo / kTile, (hi + kTile - 1) / kTile);
+        tile_range[I] = r;
+        atomicMax(&misc[0], (unsigned long long)(r.y - r.x));
+        atomicAdd(&misc[1], pairs);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the hot kernel
+constexpr int kStages = 3;
+constexpr int kHamThreads = 256;
+constexpr size_t kHamSmem = (size_t)(1 + kStages) * kTileWords * 4 + 64;
+
+struct HamParams {
+    const uint32_t* row_tiles;
+    const uint32_t* col_tiles;
+    const uint32_t* row_lo;
+    const uint32_t* row_hi;
+    const uint32_t* row_id;  // nullable: output row index = internal row index
+    const uint2* tile_range;
+    uint64_t* keys;
+    unsigned long long* counter;
+    uint64_t capacity;
+    uint64_t col_base;
+    uint32_t chunk;  // column tiles per CTA
+    uint32_t tol;
+    uint32_t rank, world;
+};
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// VARIANT 0: acc += popc(a ^ b) per 32-bit word: 32 POPC per pair (the reference's 16 x POPCNT64).
+// VARIANT 1: a carry-save adder folds two XOR words into a running "ones" word and pops only the carries:
+//            17 POPC + 64 LOP3 per pair -- trades quarter-rate POPC issue slots for full-rate LOP3.
+template <int VARIANT>
+__global__ void __launch_bounds__(kHamThreads, VARIANT == 0 ? 2 : 1) hamming_tiles_kernel(const HamParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* sB = sA + kTileWords;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * kTileWords);  // [kStages] col stages, [kStages] = row tile
+
+    const uint32_t I = blockIdx.x, c = blockIdx.y;  // x = row tile (up to 2^31-1), y = chunk
+    if (p.world > 1 && ((I + c) % p.world) != p.rank) return;  // block-cyclic deal of (row tile, chunk) units to ranks
+    const uint2 rng = p.tile_range[I];
+    const uint32_t jt0 = rng.x + c * p.chunk;
+    if (jt0 >= rng.y) return;
+    const uint32_t ntiles = min(p.chunk, rng.y - jt0);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s <= kStages; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bars[kStages], kTileWords * 4);
+        bulk_g2s(sA, p.row_tiles + (size_t)I * kTileWords, kTileWords * 4, &bars[kStages]);
+        for (uint32_t s = 0; s < kStages && s < ntiles; ++s) {
+            mbar_expect_tx(&bars[s], kTileWords * 4);
+            bulk_g2s(sB + s * kTileWords, p.col_tiles + (size_t)(jt0 + s) * kTileWords, kTileWords * 4, &bars[s]);
+        }
+    }
+    // thread (ty, tx) owns rows {4ty..4ty+3, 64+4ty..} x cols {4tx..4tx+3, 64+4tx..}
+    const int ty = tid >> 4, tx = tid & 15;
+    const uint32_t* pa = sA + ty * 4;
+    mbar_wait(&bars[kStages], 0);
+
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        const uint32_t s = t % kStages;
+        mbar_wait(&bars[s], (t / kStages) & 1);
+        const uint32_t* pb = sB + s * kTileWords + tx * 4;
+
+        uint32_t acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0;
+
+        if (VARIANT == 0) {
+#pragma unroll 2
+            for (int w = 0; w < kWords32; ++w) {
+                const uint4 a0 = *reinterpret_cast<const uint4*>(pa + w * kTile);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(pa + w * kTile + 64);
+                const uint4 b0 = *reinterpret_cast<const uint4*>(pb + w * kTile);
+                const uint4 b1 = *reinterpret_cast<const uint4*>(pb + w * kTile + 64);
+                const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] += __popc(a[i] ^ b[j]);
+            }
+        } else {
+            uint32_t ones[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ones[i][j] = 0;
+#pragma unroll 1
+            for (int w = 0; w < kWords32; w += 2) {
+                const uint4 a0 = *reinterpret_cast<const uint4*>(pa + w * kTile);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(pa + w * kTile + 64);
+                const uint4 b0 = *reinterpret_cast<const uint4*>(pb + w * kTile);
+                const uint4 b1 = *reinterpret_cast<const uint4*>(pb + w * kTile + 64);
+                const uint4 c0 = *reinterpret_cast<const uint4*>(pa + (w + 1) * kTile);
+                const uint4 c1 = *reinterpret_cast<const uint4*>(pa + (w + 1) * kTile + 64);
+                const uint4 d0 = *reinterpret_cast<const uint4*>(pb + (w + 1) * kTile);
+                const uint4 d1 = *reinterpret_cast<const uint4*>(pb + (w + 1) * kTile + 64);
+                const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const uint32_t d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t x0 = a[i] ^ b[j], x1 = cc[i] ^ d[j];
+                        const uint32_t carry = maj3(ones[i][j], x0, x1);
+                        ones[i][j] = xor3(ones[i][j], x0, x1);
+                        acc[i][j] += __popc(carry);
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 2 * acc[i][j] + __popc(ones[i][j]);
+        }
+
+        // rare path: pairs under the tolerance -> window test -> append
+        // (one min-reduction and a single branch keep the hot path's instruction footprint small)
+        uint32_t best = acc[0][0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) best = min(best, acc[i][j]);
+        if (best <= p.tol) {
+            uint64_t mask = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mask |= (uint64_t)(acc[i][j] <= p.tol) << (i * 8 + j);
+            const uint32_t col0 = (jt0 + t) * kTile;
+            while (mask) {
+                const int b = __ffsll((long long)mask) - 1;
+                mask &= mask - 1;
+                const int i = b >> 3, j = b & 7;
+                const uint32_t gi = I * kTile + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+                const uint32_t gj = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
+                    const unsigned long long slot = atomicAdd(p.counter, 1ull);
+                    if (slot < p.capacity) {
+                        const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
+                        p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
+                    }
+                }
+            }
+        }
+
+        __syncthreads();  // every thread is done with stage s
+        if (tid == 0 && t + kStages < ntiles) {
+            mbar_expect_tx(&bars[s], kTileWords * 4);
+            bulk_g2s(sB + s * kTileWords, p.col_tiles + (size_t)(jt0 + t + kStages) * kTileWords, kTileWords * 4, &bars[s]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n) {
+    if (n == 0) return VDF_OK;
+    size_t tmp = 0;
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_in, d_out, (size_t)n, 0, 64, ctx->stream));
+    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp, d_in, d_out, (size_t)n, 0, 64, ctx->stream));
+    ctx->launches += 4;  // cub's histogram + onesweep passes (approximate; library kernels)
+    return VDF_OK;
+}
+
+static int set_ham_attrs(vdf_ctx* ctx) {
+    static bool done = false;
+    if (done) return VDF_OK;
+    VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHamSmem));
+    VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHamSmem));
+    done = true;
+    return VDF_OK;
+}
+
+// shared tail of both searches: tile ranges, the hot kernel, count read-back, key sort
+static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const uint32_t* row_tiles, const uint32_t* col_tiles,
+                     const uint32_t* row_id, uint64_t col_base, uint32_t tol, uint64_t* d_keys_out, uint64_t capacity,
+                     uint64_t* n_out) {
+    VDF_TRY(set_ham_attrs(ctx));
+    VDF_ALLOC(ctx, ctx->tile_range.ensure((size_t)n_row_tiles * sizeof(uint2)));
+    VDF_ALLOC(ctx, ctx->misc.ensure(64));
+    VDF_ALLOC(ctx, ctx->raw_keys.ensure((size_t)(capacity ? capacity : 1) * 8));
+    unsigned long long* misc = ctx->misc.as<unsigned long long>();
+    VDF_CUDA(ctx, cudaMemsetAsync(misc, 0, 64, ctx->stream));
+    tile_range_kernel<<<n_row_tiles, 128, 0, ctx->stream>>>(ctx->row_lo.as<uint32_t>(), ctx->row_hi.as<uint32_t>(),
+                                                             n_row_tiles, ctx->tile_range.as<uint2>(), misc);
+    VDF_LAUNCHED(ctx);
+    unsigned long long h_misc[4] = {0, 0, 0, 0};
+    VDF_CUDA(ctx, cudaMemcpyAsync(h_misc, misc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t max_span = (uint32_t)h_misc[0];
+    *n_out = 0;
+    if (max_span == 0) return VDF_OK;
+
+    // chunk: enough column tiles per CTA to amortise the row-tile load, small enough to balance 148 SMs
+    uint32_t chunk = 32;
+    while (chunk > 4 && (uint64_t)n_row_tiles * ((max_span + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 8 * ctx->world)
+        chunk >>= 1;
+    HamParams p;
+    p.row_tiles = row_tiles;
+    p.col_tiles = col_tiles;
+    p.row_lo = ctx->row_lo.as<uint32_t>();
+    p.row_hi = ctx->row_hi.as<uint32_t>();
+    p.row_id = row_id;
+    p.tile_range = ctx->tile_range.as<uint2>();
+    p.keys = ctx->raw_keys.as<uint64_t>();
+    p.counter = misc + 2;
+    p.capacity = capacity;
+    p.col_base = col_base;
+    p.chunk = chunk;
+    p.tol = tol;
+    p.rank = ctx->rank;
+    p.world = ctx->world;
+    dim3 grid(n_row_tiles, (max_span + chunk - 1) / chunk);
+    while (grid.y > 65535) {  // only reachable beyond ~268M columns
+        chunk *= 2;
+        p.chunk = chunk;
+        grid.y = (max_span + chunk - 1) / chunk;
+    }
+    kt_begin(ctx, 0);
+    if (ctx->search_variant == 1)
+        hamming_tiles_kernel<1><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
+    else
+        hamming_tiles_kernel<0><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
+    kt_end(ctx, 0);
+    VDF_LAUNCHED(ctx);
+    unsigned long long cnt = 0;
+    VDF_CUDA(ctx, cudaMemcpyAsync(&cnt, misc + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = cnt;
+    if (cnt > capacity) {
+        ctx->err = "edge buffer overflow: " + std::to_string(cnt) + " matches > capacity " + std::to_string(capacity);
+        return VDF_ERR_EDGE_OVERFLOW;
+    }
+    return sort_keys(ctx, ctx->raw_keys.as<uint64_t>(), d_keys_out, cnt);
+}
+
+int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_dur, uint64_t n, uint32_t tol,
+                       uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+    *n_out = 0;
+    if (n == 0) return VDF_OK;  // search_algorithm.rs:88-90
+    if (n >= 0xFFFFFF00ull) {
+        ctx->err = "n must be < 2^32";
+        return VDF_ERR_INVALID;
+    }
+    const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
+    const uint32_t n_pad = T * kTile;
+    VDF_ALLOC(ctx, ctx->row_tiles.ensure((size_t)T * kTileWords * 4));
+    VDF_ALLOC(ctx, ctx->row_lo.ensure((size_t)n_pad * 4));
+    VDF_ALLOC(ctx, ctx->row_hi.ensure((size_t)n_pad * 4));
+    retile_kernel<<<T, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), nullptr, n,
+                                              ctx->row_tiles.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    self_window_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(d_dur, (uint32_t)n, n_pad, ctx->row_lo.as<uint32_t>(),
+                                                                     ctx->row_hi.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    return run_tiles(ctx, T, ctx->row_tiles.as<uint32_t>(), ctx->row_tiles.as<uint32_t>(), nullptr, 0, tol, d_keys_out,
+                     capacity, n_out);
+}
+
+int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_cand_dur, uint64_t n_cand,
+                       uint64_t cand_base, const uint64_t* d_refs, const uint32_t* d_ref_dur, uint64_t n_ref,
+                       uint32_t tol, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+    *n_out = 0;
+    if (n_cand == 0 || n_ref == 0) return VDF_OK;
+    if (n_cand >= 0xFFFFFF00ull || n_ref >= 0xFFFFFF00ull || cand_base + n_cand > 0xFFFFFFFFull) {
+        ctx->err = "indices must fit in 32 bits";
+        return VDF_ERR_INVALID;
+    }
+    const uint32_t TC = (uint32_t)((n_cand + kTile - 1) / kTile);
+    const uint32_t TR = (uint32_t)((n_ref + kTile - 1) / kTile);
+    const uint32_t r_pad = TR * kTile;
+    VDF_ALLOC(ctx, ctx->col_tiles.ensure((size_t)TC * kTileWords * 4));
+    VDF_ALLOC(ctx, ctx->row_tiles.ensure((size_t)TR * kTileWords * 4));
+    VDF_ALLOC(ctx, ctx->row_lo.ensure((size_t)r_pad * 4));
+    VDF_ALLOC(ctx, ctx->row_hi.ensure((size_t)r_pad * 4));
+    VDF_ALLOC(ctx, ctx->ref_key.ensure((size_t)n_ref * 4 * 3));
+    VDF_ALLOC(ctx, ctx->ref_perm.ensure((size_t)r_pad * 4));
+    // order the references by duration so that the 128 rows of a tile have overlapping slices
+    uint32_t* key_in = ctx->ref_key.as<uint32_t>();
+    uint32_t* key_out = key_in + n_ref;
+    uint32_t* idx_in = key_out + n_ref;
+    uint32_t* perm = ctx->ref_perm.as<uint32_t>();
+    ref_sortkey_kernel<<<(uint32_t)((n_ref + 255) / 256), 256, 0, ctx->stream>>>(d_ref_dur, (uint32_t)n_ref, key_in, idx_in);
+    VDF_LAUNCHED(ctx);
+    size_t tmp = 0;
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32, ctx->stream));
+    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32,
+                                                  ctx->stream));
+    ctx->launches += 3;
+    retile_kernel<<<TC, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cand), nullptr, n_cand,
+                                               ctx->col_tiles.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    retile_kernel<<<TR, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_refs), perm, n_ref,
+                                               ctx->row_tiles.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    ref_window_kernel<<<(r_pad + 255) / 256, 256, 0, ctx->stream>>>(d_cand_dur, (uint32_t)n_cand, d_ref_dur, perm,
+                                                                    (uint32_t)n_ref, r_pad, ctx->row_lo.as<uint32_t>(),
+                                                                    ctx->row_hi.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    // in multi-GPU use every rank holds a different candidate slice and evaluates ALL of its tiles
+    const uint32_t world = ctx->world, rank = ctx->rank;
+    ctx->world = 1, ctx->rank = 0;
+    int rc = run_tiles(ctx, TR, ctx->row_tiles.as<uint32_t>(), ctx->col_tiles.as<uint32_t>(), perm, cand_base, tol,
+                       d_keys_out, capacity, n_out);
+    ctx->world = world, ctx->rank = rank;
+    return rc;
+}
+
+__global__ void window_pairs_kernel(const uint32_t* __restrict__ dur, uint32_t n, unsigned long long* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (i < n) {
+        uint32_t thresh = f64_as_u32((double)dur[i] * 1.1);
+        v = upper_bound_u32(dur, n, thresh) - (i + 1);
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
+int self_window_pairs(vdf_ctx* ctx, const uint32_t* d_dur, uint64_t n, uint64_t* pairs_out) {
+    *pairs_out = 0;
+    if (n == 0) return VDF_OK;
+    VDF_ALLOC(ctx, ctx->misc.ensure(64));
+    VDF_CUDA(ctx, cudaMemsetAsync(ctx->misc.p, 0, 8, ctx->stream));
+    window_pairs_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(d_dur, (uint32_t)n,
+                                                                             ctx->misc.as<unsigned long long>());
+    VDF_LAUNCHED(ctx);
+    unsigned long long v = 0;
+    VDF_CUDA(ctx, cudaMemcpyAsync(&v, ctx->misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *pairs_out = v;
+    return VDF_OK;
+}
+
+}  // namespace vdf

@@ -1,0 +1,167 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests).
+
+How the two paths shard:
+  * hashing            - by stack, contiguous ranges, no exchange while hashing; one all-gather of the 128-byte
+                         hashes afterwards so that every rank holds the table the search needs.
+  * search_self        - every rank holds the full sorted table; the (row tile, chunk) units of the pair matrix are
+                         dealt block-cyclically to the ranks inside the kernel (vdf_ctx_set_shard); ONE exchange:
+                         a variable-length all-gather of the per-rank edge lists; the greedy grouping is replicated.
+  * search_with_refs   - the sorted candidate table is cut into contiguous slices, the references are replicated;
+                         per-rank (ref, cand) keys are all-gathered and merged by a sort.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _ffi
+from .definitions import tolerance_to_int
+from .match_group import MatchGroup
+from .video_hash import HashTable, as_table, sort_order
+
+
+def world_info(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous [begin, end) of n items for `rank`; sizes differ by at most one"""
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def allgather_varlen(local: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenation over ranks (in rank order) of 1-D tensors of different lengths."""
+    rank, world = world_info(group)
+    if world == 1:
+        return local
+    cnt = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    m = max(counts)
+    if m == 0:
+        return local[:0]
+    padded = torch.zeros(m, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
+def merge_keys(local_keys: torch.Tensor, group=None) -> torch.Tensor:
+    """all ranks' u64 keys (carried as int64; indices < 2^31 keep them non-negative), globally sorted"""
+    allk = allgather_varlen(local_keys, group)
+    return torch.sort(allk).values if allk.numel() else allk
+
+
+def _run_growing(fn, device, initial: int = 1 << 22):
+    cap = initial
+    while True:
+        keys = torch.empty(cap, dtype=torch.int64, device=device)
+        torch.cuda.current_stream().synchronize()
+        cnt = fn(keys.data_ptr(), cap)
+        if cnt >= 0:
+            return keys[:cnt]
+        cap = -cnt + 1024
+
+
+def search_self_keys(ctx: _ffi.Context, d_hash: torch.Tensor, d_dur: torch.Tensor, tol_int: int, group=None) -> torch.Tensor:
+    """This rank's share of the pair matrix, then the edge all-gather: sorted (i << 32 | j) keys of ALL ranks."""
+    rank, world = world_info(group)
+    n = d_dur.numel()
+    ctx.set_shard(rank, world)
+    try:
+        local = _run_growing(lambda p, cap: ctx.search_self_device(d_hash.data_ptr(), d_dur.data_ptr(), n, tol_int, p, cap),
+                             d_hash.device)
+    finally:
+        ctx.set_shard(0, 1)
+    return merge_keys(local, group)
+
+
+def search_refs_keys(ctx: _ffi.Context, d_cand_slice: torch.Tensor, d_cand_dur_slice: torch.Tensor, cand_base: int,
+                     d_refs: torch.Tensor, d_ref_dur: torch.Tensor, tol_int: int, group=None) -> torch.Tensor:
+    local = _run_growing(
+        lambda p, cap: ctx.search_refs_device(d_cand_slice.data_ptr(), d_cand_dur_slice.data_ptr(), d_cand_dur_slice.numel(),
+                                              cand_base, d_refs.data_ptr(), d_ref_dur.data_ptr(), d_ref_dur.numel(), tol_int,
+                                              p, cap), d_refs.device)
+    return merge_keys(local, group)
+
+
+def csr_from_keys(keys: np.ndarray, n_rows: int) -> Tuple[np.ndarray, np.ndarray]:
+    """sorted (row << 32 | col) keys -> (row_ptr, col_idx)"""
+    keys = np.asarray(keys).astype(np.uint64)
+    rows = (keys >> np.uint64(32)).astype(np.int64)
+    rp = np.zeros(n_rows + 1, dtype=np.uint64)
+    np.add.at(rp, rows + 1, 1)
+    return np.cumsum(rp).astype(np.uint64), keys & np.uint64(0xFFFFFFFF)
+
+
+def _to_dev(a: np.ndarray, device) -> torch.Tensor:
+    t = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a.view(np.int32) if a.dtype == np.uint32 else a)
+    return t.to(device, non_blocking=False)
+
+
+def search(hashes, tolerance: float, ctx: Optional[_ffi.Context] = None, group=None) -> List[MatchGroup]:
+    """`search` (video_dup_finder.rs:7-13) over all ranks of the process group; every rank gets the full result."""
+    ctx = ctx or _ffi.default_context()
+    table = as_table(hashes)
+    n = len(table)
+    if n == 0:
+        return []
+    dev = torch.device("cuda", ctx.device)
+    order = sort_order(table.durations, table.paths)
+    d_hash = _to_dev(np.ascontiguousarray(table.hashes[order]), dev)
+    d_dur = _to_dev(np.ascontiguousarray(table.durations[order]), dev)
+    keys = search_self_keys(ctx, d_hash, d_dur, tolerance_to_int(tolerance), group)
+    torch.cuda.current_stream().synchronize()
+    gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
+    paths = table.paths
+    out = []
+    for g in range(len(gp) - 1):
+        members = [paths[order[k]] for k in mm[gp[g]:gp[g + 1]]]
+        if len(members) >= 2:
+            out.append(MatchGroup.new(members))
+    return out
+
+
+def search_with_references(ref_hashes, new_hashes, tolerance: float, ctx: Optional[_ffi.Context] = None,
+                           group=None) -> List[MatchGroup]:
+    """`search_with_references` (video_dup_finder.rs:19-46) with the sorted candidate table sliced over the ranks."""
+    ctx = ctx or _ffi.default_context()
+    refs, cands = as_table(ref_hashes), as_table(new_hashes)
+    if len(refs) == 0 or len(cands) == 0:
+        return []
+    rank, world = world_info(group)
+    dev = torch.device("cuda", ctx.device)
+    order = sort_order(cands.durations, cands.paths)
+    b, e = shard_range(len(cands), rank, world)
+    sl = order[b:e]
+    d_c = _to_dev(np.ascontiguousarray(cands.hashes[sl]).reshape(-1, 16), dev)
+    d_cd = _to_dev(np.ascontiguousarray(cands.durations[sl]), dev)
+    d_r = _to_dev(refs.hashes, dev)
+    d_rd = _to_dev(refs.durations, dev)
+    keys = search_refs_keys(ctx, d_c, d_cd, b, d_r, d_rd, tolerance_to_int(tolerance), group)
+    rp, ci = csr_from_keys(keys.cpu().numpy(), len(refs))
+    out = []
+    for r in range(len(refs)):
+        if rp[r + 1] > rp[r]:
+            out.append(MatchGroup.new_with_reference(refs.paths[r], [cands.paths[order[int(k)]] for k in ci[int(rp[r]):int(rp[r + 1])]]))
+    return out
+
+
+def hash_stacks_sharded(ctx: _ffi.Context, d_frames: torch.Tensor, descs: np.ndarray, cropdetect: int, group=None):
+    """Hash this rank's stacks (descs index into d_frames, which holds only local stacks), then all-gather the
+    128-byte hashes so that every rank holds the table in rank order.  -> ([n_total,16] int64 tensor, status)"""
+    n = len(descs)
+    out = torch.zeros((n, 16), dtype=torch.int64, device=d_frames.device)
+    torch.cuda.current_stream().synchronize()
+    status, _ = ctx.hash_stacks_device(d_frames.data_ptr(), descs, cropdetect, out.data_ptr())
+    allh = allgather_varlen(out.reshape(-1), group).reshape(-1, 16)
+    return allh, status
