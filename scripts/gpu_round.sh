@@ -1,0 +1,30 @@
+#!/bin/bash
+# One GPU-box session: microbench, parity tests, smoke, bench, ncu launch list + full captures.
+# Run under gpurun from the repo root; everything worth keeping lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.csv 2>&1
+nproc > gpurun_out/host.txt; grep -m1 'model name' /proc/cpuinfo >> gpurun_out/host.txt
+STEP=${1:-all}
+if [[ $STEP == all || $STEP == micro ]]; then
+  timeout 180 ./vid_dup_finder_lib_b200/vdf_microbench > gpurun_out/microbench.jsonl 2>&1; echo "microbench rc=$?"
+fi
+if [[ $STEP == all || $STEP == test ]]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
+fi
+if [[ $STEP == all || $STEP == smoke ]]; then
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
+fi
+if [[ $STEP == all || $STEP == bench ]]; then
+  timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+  timeout 600 python bench.py --steps 3 --warmup 3 --variant 1 --no-secondary --no-cpu-baseline > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err; echo "bench v1 rc=$?"; tail -c 1500 gpurun_out/bench_v1.json
+fi
+if [[ $STEP == all || $STEP == ncu ]]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 1 --stacks 64 > gpurun_out/bench_under_ncu.json 2>&1; echo "ncu list rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tiles -c 1 -f -o gpurun_out/prof_hamming \
+      python bench.py --steps 1 --warmup 0 --n 262144 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming.log 2>&1; echo "ncu hamming rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize -c 1 -f -o gpurun_out/prof_resize \
+      python bench.py --workload hash --steps 1 --warmup 0 --stacks 32 --no-cpu-baseline > gpurun_out/ncu_resize.log 2>&1; echo "ncu resize rc=$?"
+fi
+ls -la gpurun_out | head -30
