@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1_000_000, help="hashes in the all-pairs search")
     ap.add_argument("--tol", type=float, default=0.35)
     ap.add_argument("--variant", type=int, default=-1, help="search kernel variant (-1: library default)")
+    ap.add_argument("--hash-variant", type=int, default=-1, help="resize kernel: 0 IMMA 8 warps, 1 general, 2 IMMA 4 warps")
     ap.add_argument("--stacks", type=int, default=256, help="1080p stacks resident in HBM per GPU (8.5 GB at 256)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
@@ -204,6 +205,8 @@ def main():
     ctx = _ffi.default_context()
     if args.variant >= 0:
         ctx.set_option("search_variant", args.variant)
+    if args.hash_variant >= 0:
+        ctx.set_option("hash_variant", args.hash_variant)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
@@ -358,7 +361,8 @@ def main():
                "clocks": cs.summary(),
                "config": {"workload": f"frame-stack hashing, {w}x{h}x16 u8 stacks resident in HBM, letterbox cropdetect",
                           "stacks_per_gpu_per_step": ns, "parallelism": f"stack shard x{world}",
-                          "l2": f"pool of {ns * stack_bytes / 1e9:.1f} GB per GPU >> L2, no flush"}}
+                          "l2": f"pool of {ns * stack_bytes / 1e9:.1f} GB per GPU >> L2, no flush",
+                          "hash_variant": args.hash_variant}}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from concurrent.futures import ThreadPoolExecutor
 

@@ -19,6 +19,13 @@ if [[ $STEP == all || $STEP == bench ]]; then
   timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
   timeout 600 python bench.py --steps 3 --warmup 3 --variant 1 --no-secondary --no-cpu-baseline > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err; echo "bench v1 rc=$?"; tail -c 1500 gpurun_out/bench_v1.json
 fi
+if [[ $STEP == hash ]]; then
+  for v in 0 2 1; do
+    timeout 600 python bench.py --workload hash --steps 5 --warmup 3 --hash-variant $v --no-cpu-baseline > gpurun_out/bench_hash_v$v.json 2> gpurun_out/bench_hash_v$v.err; echo "bench hash v$v rc=$?"; tail -c 1800 gpurun_out/bench_hash_v$v.json; tail -3 gpurun_out/bench_hash_v$v.err
+  done
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize_mma -c 1 -f -o gpurun_out/prof_resize_mma \
+      python bench.py --workload hash --steps 1 --warmup 0 --stacks 32 --no-cpu-baseline > gpurun_out/ncu_resize_mma.log 2>&1; echo "ncu resize_mma rc=$?"
+fi
 if [[ $STEP == all || $STEP == ncu ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 1 --stacks 64 > gpurun_out/bench_under_ncu.json 2>&1; echo "ncu list rc=$?"

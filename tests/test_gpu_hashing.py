@@ -60,8 +60,18 @@ def test_letterbox_kat_images(ctx):
             assert tuple(crop[0]) == o.letterbox_frame(im, o.LB_ANYCOLOUR, 16), name
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["imma8", "general", "imma4"])
 @pytest.mark.parametrize("w,h", [(64, 48), (256, 144), (321, 203), (640, 360), (854, 480), (1280, 720), (1920, 1080)])
-def test_crop_cube_and_hash_are_bit_exact(ctx, w, h):
+def test_crop_cube_and_hash_are_bit_exact(ctx, w, h, variant):
+    """variant 0/2: tensor-core (IMMA) resize where rows are 16-byte aligned, general kernel elsewhere; 1: general"""
+    ctx.set_option("hash_variant", variant)
+    try:
+        _check_bit_exact(ctx, w, h)
+    finally:
+        ctx.set_option("hash_variant", 0)
+
+
+def _check_bit_exact(ctx, w, h):
     n = 6 if w * h > 500_000 else 12
     stacks = synth.frame_stacks(n, w, h, seed=w * 7 + h).numpy()
     stacks[1, :, : h // 9, :] = 16            # letterbox
@@ -79,7 +89,8 @@ def test_crop_cube_and_hash_are_bit_exact(ctx, w, h):
     assert np.array_equal(got_c, want_c) and np.array_equal(got_c2, want_c)
     assert np.array_equal(got_m, want_m), "resized cube differs"
     assert np.array_equal(got_h, want_h), "hash words differ"
-    assert want_c[1][2] > 0 and want_c[2][0] > 0 and tuple(want_c[3]) == (0, 0, 0, 0) and tuple(want_c[5]) == (0, 0, 0, 0)
+    # (smooth content can itself pass the strip test at small sizes, so only the planted geometry is asserted)
+    assert want_c[1][2] >= h // 9 and want_c[2][0] >= w // 10 and want_c[3][2] < h // 6 and tuple(want_c[5]) == (0, 0, 0, 0)
     bits = np.unpackbits(got_h[4].view(np.uint8), bitorder="little")
     assert bits[100:].sum() == 0  # static stack
 

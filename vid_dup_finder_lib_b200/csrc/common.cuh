@@ -109,6 +109,7 @@ struct vdf_ctx {
     vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc;
     vdf::PinnedBuf pin_a, pin_b, pin_frames[2];
     std::map<uint32_t, vdf::CoefTable> coef_cache;
+    std::map<uint64_t, void*> bfrag_cache;  // (cropped width << 8 | shift) -> IMMA B fragments in HBM
     bool dct_consts_loaded = false;
 };
 

@@ -151,6 +151,11 @@ struct StackJob {
     const uint32_t* bv;
     const int16_t* kv;
     uint32_t win_h, prec_h, win_v, prec_v;
+    // tensor-core path (resize_mma_kernel): present iff the stack's addresses are 16-byte aligned
+    const uint2* kb;     // horizontal coefficients as IMMA B fragments: [k-step][n-tile 0..3][lane] (b0, b1)
+    uint32_t x0_al;      // first column loaded = left rounded down to 16
+    uint32_t n_kch;      // 128-pixel k-chunks covering [x0_al, left + cw)
+    uint32_t fast;       // 1: resize_mma_kernel, 0: resize_general_kernel
 };
 
 __device__ __forceinline__ uint8_t clip8(int32_t v, uint32_t precision) {
@@ -166,7 +171,7 @@ __global__ void __launch_bounds__(256) resize_general_kernel(const uint8_t* __re
     extern __shared__ uint8_t tmp[];  // ch x 16
     const uint32_t s = blockIdx.x >> 4, t = blockIdx.x & 15;
     const StackJob j = jobs[s];
-    if (j.status != VDF_STACK_OK) return;
+    if (j.status != VDF_STACK_OK || j.fast) return;
     const uint8_t* img = frames + j.offset + (uint64_t)t * j.frame_stride + (uint64_t)j.top * j.pitch + j.left;
     const int32_t init_h = 1 << (j.prec_h - 1);
     for (uint32_t it = threadIdx.x; it < j.ch * 16; it += blockDim.x) {
@@ -187,6 +192,164 @@ __global__ void __launch_bounds__(256) resize_general_kernel(const uint8_t* __re
         int32_t acc = init_v;
         for (uint32_t q = 0; q < sz; ++q) acc += (int32_t)tmp[(s0 + q) * 16 + ox] * (int32_t)k[q];
         small[((uint64_t)s * 16 + t) * 256 + it] = clip8(acc, j.prec_v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core path.  The horizontal pass is an exact integer contraction out[row][o] = sum_x k[o][x] * p[row][x]
+// with u8 pixels and i16 coefficients; at ~6 multiply-adds per source byte it is far beyond what the CUDA-core
+// integer pipes sustain at HBM speed (measured: IMAD/dp4a 64-92 ops/clk/SM vs 142 needed).  The i16 coefficient is
+// split as k = 256*kh + kl (kh signed byte, kl unsigned byte) and the pass runs on the integer tensor path:
+// A = pixels [rows x 32] u8 straight from the frame, B = coefficient bytes, 4 n-tiles = {kh, kl} x {outputs 0-7,
+// 8-15}, s32 accumulators (exact: |sum| < 2^31 by fast_image_resize's own precision rule).
+// One CTA per (stack, frame).  Pixels stream HBM -> shared memory in 128-byte k-chunks of kRows rows through a
+// kRStages-deep cp.async ring (16-byte async copies, zero-filled outside the frame), ldmatrix feeds the A fragments,
+// the coefficient fragments ride along in the same ring.  The u8 intermediate [ch][16] stays in shared memory
+// (the reference rounds to u8 between the passes); the vertical pass is one thread per output pixel.
+constexpr int kRStages = 3;
+constexpr int kKch = 128;              // pixels per k-chunk (4 IMMA k-steps)
+constexpr int kRowPitch = kKch + 16;   // shared-memory row pitch: ldmatrix rows land on distinct banks
+constexpr int kBFragBytes = 4 * 4 * 32 * 8;  // per k-chunk: 4 k-steps x 4 n-tiles x 32 lanes x (b0,b1)
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+__device__ __forceinline__ void imma_u8s8(int32_t (&c)[4], const uint32_t (&a)[4], uint2 b) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ void imma_u8u8(int32_t (&c)[4], const uint32_t (&a)[4], uint2 b) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+template <int WARPS>
+struct ResizeMma {
+    static constexpr int kThreads = WARPS * 32;
+    static constexpr int kRows = WARPS * 32;  // rows per row block: two m16 tiles per warp
+    static constexpr int kStageBytes = kRows * kRowPitch + kBFragBytes;
+    static constexpr int kRingBytes = kRStages * kStageBytes;
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
+    resize_mma_kernel(const uint8_t* __restrict__ frames, const StackJob* __restrict__ jobs, uint8_t* __restrict__ small) {
+    using Cfg = ResizeMma<WARPS>;
+    extern __shared__ __align__(128) uint8_t smem_dyn[];
+    uint8_t* ring = smem_dyn;
+    uint8_t* tmp = smem_dyn + Cfg::kRingBytes;  // ch x 16
+    const uint32_t s = blockIdx.x >> 4, t = blockIdx.x & 15;
+    const StackJob j = jobs[s];
+    if (j.status != VDF_STACK_OK || !j.fast) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* img = frames + j.offset + (uint64_t)t * j.frame_stride + (uint64_t)j.top * j.pitch + j.x0_al;
+    const uint32_t n_rb = (j.ch + Cfg::kRows - 1) / Cfg::kRows;
+    const uint32_t total = n_rb * j.n_kch;
+
+    auto issue = [&](uint32_t it) {  // async copies for iteration it = (row block, k-chunk) into stage it % kRStages
+        if (it < total) {
+            const uint32_t rb = it / j.n_kch, kc = it - rb * j.n_kch;
+            uint8_t* st = ring + (it % kRStages) * Cfg::kStageBytes;
+            const uint32_t c = tid & 7;
+            const uint32_t xb = j.x0_al + kc * kKch + c * 16;  // byte offset inside the frame row
+            for (uint32_t r = tid >> 3; r < (uint32_t)Cfg::kRows; r += Cfg::kThreads / 8) {
+                const uint32_t row = rb * Cfg::kRows + r;
+                const bool ok = row < j.ch && xb < j.pitch;
+                const uint8_t* src = ok ? img + (uint64_t)row * j.pitch + kc * kKch + c * 16 : img;
+                cp_async16(st + r * kRowPitch + c * 16, src, ok ? 16u : 0u);
+            }
+            const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(j.kb) + (size_t)kc * kBFragBytes;
+            for (uint32_t q = tid; q < kBFragBytes / 16; q += Cfg::kThreads)
+                cp_async16(st + Cfg::kRows * kRowPitch + q * 16, bsrc + q * 16, 16u);
+        }
+        cp_async_commit();
+    };
+
+    int32_t acc[2][4][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
+
+    for (uint32_t it = 0; it < kRStages - 1; ++it) issue(it);
+    const int32_t round_h = 1 << (j.prec_h - 1);
+    // ldmatrix lane -> (row, byte) inside a 16 x 32-byte A tile: lanes 0-7 rows 0-7 k 0-15, 8-15 rows 8-15 k 0-15,
+    // 16-23 rows 0-7 k 16-31, 24-31 rows 8-15 k 16-31  (= registers a0..a3 of mma.m16n8k32)
+    const uint32_t lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lbyte = (lane >> 4) * 16;
+
+    for (uint32_t it = 0; it < total; ++it) {
+        cp_async_wait<kRStages - 2>();
+        __syncthreads();
+        issue(it + kRStages - 1);
+        const uint8_t* st = ring + (it % kRStages) * Cfg::kStageBytes;
+        const uint2* sb = reinterpret_cast<const uint2*>(st + Cfg::kRows * kRowPitch);
+        const uint8_t* arow = st + (warp * 32 + lrow) * kRowPitch + lbyte;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a0[4], a1[4];
+            ldmatrix_x4(a0, arow + ks * 32);
+            ldmatrix_x4(a1, arow + 16 * kRowPitch + ks * 32);
+            const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b1 = sb[(ks * 4 + 1) * 32 + lane];
+            const uint2 b2 = sb[(ks * 4 + 2) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
+            imma_u8s8(acc[0][0], a0, b0);
+            imma_u8s8(acc[1][0], a1, b0);
+            imma_u8s8(acc[0][1], a0, b1);
+            imma_u8s8(acc[1][1], a1, b1);
+            imma_u8u8(acc[0][2], a0, b2);
+            imma_u8u8(acc[1][2], a1, b2);
+            imma_u8u8(acc[0][3], a0, b3);
+            imma_u8u8(acc[1][3], a1, b3);
+        }
+        const uint32_t rb = it / j.n_kch, kc = it - rb * j.n_kch;
+        if (kc + 1 == j.n_kch) {  // row block finished: k = 256*kh + kl, round, shift, clamp -> u8 intermediate
+            const uint32_t g = lane >> 2, q2 = (lane & 3) * 2;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t row = rb * Cfg::kRows + warp * 32 + mt * 16 + g + half * 8;
+#pragma unroll
+                    for (int oct = 0; oct < 2; ++oct)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int32_t v = acc[mt][oct][half * 2 + e] * 256 + acc[mt][2 + oct][half * 2 + e] + round_h;
+                            if (row < j.ch) tmp[row * 16 + oct * 8 + q2 + e] = clip8(v, j.prec_h);
+                        }
+                }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const int32_t init_v = 1 << (j.prec_v - 1);
+    for (uint32_t it = tid; it < 256; it += Cfg::kThreads) {
+        const uint32_t oy = it >> 4, ox = it & 15;
+        const uint32_t s0 = j.bv[2 * oy], sz = j.bv[2 * oy + 1];
+        const int16_t* k = j.kv + oy * j.win_v;
+        int32_t a = init_v;
+        for (uint32_t q = 0; q < sz; ++q) a += (int32_t)tmp[(s0 + q) * 16 + ox] * (int32_t)k[q];
+        small[((uint64_t)s * 16 + t) * 256 + it] = clip8(a, j.prec_v);
     }
 }
 
@@ -406,6 +569,43 @@ void free_coef_cache(vdf_ctx* ctx) {
         if (kv.second.d_kb) cudaFree(kv.second.d_kb);
     }
     ctx->coef_cache.clear();
+    for (auto& kv : ctx->bfrag_cache) cudaFree(kv.second);
+    ctx->bfrag_cache.clear();
+}
+
+// IMMA B fragments of the horizontal coefficients for a crop that starts `shift` bytes after a 16-byte boundary:
+// [k-step][n-tile][lane] -> (b0, b1); n-tiles 0,1 = high bytes (signed) of outputs 0-7 / 8-15, 2,3 = low bytes.
+// mma.m16n8k32 B layout: b0 holds k = 4*(lane%4)+0..3, b1 the same +16, column n = lane/4.
+static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const uint2** out) {
+    const uint64_t key = ((uint64_t)t.in_size << 8) | shift;
+    auto it = ctx->bfrag_cache.find(key);
+    if (it == ctx->bfrag_cache.end()) {
+        const uint32_t n_kch = (shift + t.in_size + kKch - 1) / kKch, ksteps = n_kch * 4;
+        std::vector<uint32_t> frag((size_t)ksteps * 4 * 32 * 2);
+        for (uint32_t ks = 0; ks < ksteps; ++ks)
+            for (uint32_t nt = 0; nt < 4; ++nt)
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    for (uint32_t reg = 0; reg < 2; ++reg) {
+                        uint32_t word = 0;
+                        const uint32_t o = (nt & 1) * 8 + lane / 4;
+                        const uint32_t start = t.h_bounds[2 * o], size = t.h_bounds[2 * o + 1];
+                        for (uint32_t i = 0; i < 4; ++i) {
+                            const int64_t x = (int64_t)ks * 32 + (lane % 4) * 4 + i + reg * 16 - shift;
+                            int k = 0;
+                            if (x >= (int64_t)start && x < (int64_t)start + size) k = t.h_k[(size_t)o * t.window + (x - start)];
+                            const uint32_t byte = nt < 2 ? (uint32_t)((k >> 8) & 0xFF) : (uint32_t)(k & 0xFF);
+                            word |= byte << (8 * i);
+                        }
+                        frag[(((size_t)ks * 4 + nt) * 32 + lane) * 2 + reg] = word;
+                    }
+        void* d = nullptr;
+        VDF_ALLOC(ctx, cudaMalloc(&d, frag.size() * 4));
+        VDF_CUDA(ctx, cudaMemcpyAsync(d, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        it = ctx->bfrag_cache.emplace(key, d).first;
+    }
+    *out = reinterpret_cast<const uint2*>(it->second);
+    return VDF_OK;
 }
 
 static int load_dct_consts(vdf_ctx* ctx) {
@@ -480,6 +680,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     // coefficient tables for the cropped sizes (cached per size in HBM)
     std::vector<StackJob> jobs(n);
     uint32_t max_ch = 1;
+    bool any_fast = false, any_slow = false;
     for (uint32_t s = 0; s < n; ++s) {
         StackJob& j = jobs[s];
         std::memset(&j, 0, sizeof j);
@@ -496,6 +697,19 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         j.bh = th->d_bounds, j.kh = th->d_k, j.win_h = th->window, j.prec_h = th->precision;
         j.bv = tv->d_bounds, j.kv = tv->d_k, j.win_v = tv->window, j.prec_v = tv->precision;
         max_ch = std::max(max_ch, j.ch);
+        // tensor-core path needs 16-byte aligned rows (cp.async 16 B): base, frame stride and pitch
+        const bool aligned = ((reinterpret_cast<uintptr_t>(d_frames) + d.offset) % 16 == 0) && d.frame_stride % 16 == 0 &&
+                             d.pitch % 16 == 0;
+        if (aligned && ctx->hash_variant != 1) {
+            j.x0_al = j.left & ~15u;
+            const uint32_t shift = j.left - j.x0_al;
+            j.n_kch = (shift + j.cw + kKch - 1) / kKch;
+            VDF_TRY(get_bfrags(ctx, *th, shift, &j.kb));
+            j.fast = 1;
+            any_fast = true;
+        } else {
+            any_slow = true;
+        }
     }
     VDF_ALLOC(ctx, ctx->h_jobs.ensure((size_t)n * sizeof(StackJob) + (size_t)n * 4));
     StackJob* d_jobs = ctx->h_jobs.as<StackJob>();
@@ -507,20 +721,38 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         VDF_ALLOC(ctx, ctx->h_small.ensure((size_t)n * 4096));
         d_small = ctx->h_small.as<uint8_t>();
     }
-    const size_t smem = (size_t)max_ch * 16;
-    if (smem > 200 * 1024) {
-        ctx->err = "frame height beyond the general resize kernel's shared-memory budget";
+    const size_t tmp_bytes = (size_t)max_ch * 16;
+    const bool four_warps = ctx->hash_variant == 2;
+    const size_t ring = four_warps ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
+    if (tmp_bytes + ring > 220 * 1024) {
+        ctx->err = "frame height beyond the resize kernels' shared-memory budget";
         return VDF_ERR_INVALID;
     }
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        VDF_CUDA(ctx, cudaFuncSetAttribute(resize_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    static size_t smem_set[3] = {0, 0, 0};
+    auto want_smem = [&](int slot, const void* fn, size_t bytes) -> int {
+        if (bytes > 48 * 1024 && bytes > smem_set[slot]) {
+            VDF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            smem_set[slot] = bytes;
+        }
+        return VDF_OK;
+    };
     kt_begin(ctx, 1);
-    resize_general_kernel<<<n * 16, 256, smem, st>>>(d_frames, d_jobs, d_small);
+    if (any_fast) {
+        if (four_warps) {
+            VDF_TRY(want_smem(1, (const void*)resize_mma_kernel<4>, tmp_bytes + ring));
+            resize_mma_kernel<4><<<n * 16, 128, tmp_bytes + ring, st>>>(d_frames, d_jobs, d_small);
+        } else {
+            VDF_TRY(want_smem(2, (const void*)resize_mma_kernel<8>, tmp_bytes + ring));
+            resize_mma_kernel<8><<<n * 16, 256, tmp_bytes + ring, st>>>(d_frames, d_jobs, d_small);
+        }
+        VDF_LAUNCHED(ctx);
+    }
+    if (any_slow) {
+        VDF_TRY(want_smem(0, (const void*)resize_general_kernel, tmp_bytes));
+        resize_general_kernel<<<n * 16, 256, tmp_bytes, st>>>(d_frames, d_jobs, d_small);
+        VDF_LAUNCHED(ctx);
+    }
     kt_end(ctx, 1);
-    VDF_LAUNCHED(ctx);
     if (d_out_hash) {
         kt_begin(ctx, 3);
         dct_pack_kernel<<<n, 256, 0, st>>>(d_small, d_status, n, reinterpret_cast<uint32_t*>(d_out_hash));
