@@ -349,6 +349,7 @@ def main():
         ne = min(ns, 32)
         host = pool[:ne].cpu().pin_memory()
         hd = _ffi.make_descs(ne, w, h)
+        ctx.hash_stacks(host.numpy().reshape(-1), hd, _ffi.CROPDETECT_LETTERBOX)  # warm-up: staging buffers get allocated
         barrier()
         t0 = time.perf_counter()
         got, st, _ = ctx.hash_stacks(host.numpy().reshape(-1), hd, _ffi.CROPDETECT_LETTERBOX)

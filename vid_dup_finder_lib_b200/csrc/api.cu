@@ -430,6 +430,12 @@ int vdf_hash_stacks(vdf_ctx* ctx, const uint8_t* frames, const vdf_stack_desc* d
             if (sb) {
                 const uint8_t* src = frames + d.offset;
                 const size_t fb = (size_t)d.width * d.height;
+                const bool contiguous = d.pitch == d.width && d.frame_stride == fb;
+                if (contiguous && src_pinned) {  // one 16-frame copy instead of 16 strided ones
+                    VDF_CUDA(ctx, cudaMemcpyAsync(dev + off, src, sb, cudaMemcpyHostToDevice, ctx->copy_stream));
+                } else if (contiguous) {
+                    std::memcpy(ctx->pin_frames[buf].as<uint8_t>() + off, src, sb);
+                } else
                 for (uint32_t f = 0; f < VDF_DCT_SIZE; ++f) {
                     const uint8_t* fs = src + (size_t)f * d.frame_stride;
                     if (src_pinned) {

@@ -76,25 +76,41 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
     const uint32_t limit = cols ? W : H, len = cols ? H : W;
     const uint32_t panel = cols ? kColPanel : kRowPanel;
     for (uint32_t base = 0; base < limit; base += panel) {
-        for (int q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
+        for (uint32_t q = tid; q < panel * 257; q += 256) hist[q] = 0;
         __syncthreads();
         if (cols) {
             const uint32_t idx = base + lane;
             const bool act = idx < W;
             const uint32_t x = side == 0 ? idx : W - 1 - idx;
-            for (uint32_t y = warp; y < H; y += 8)
-                if (act) atomicAdd(&hist[lane * 257 + img[(uint64_t)y * P + x]], 1u);
+            // 16 independent loads in flight per lane before the (shared-memory) histogram updates
+            for (uint32_t y0 = warp; y0 < H; y0 += 8 * 16) {
+                uint32_t v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const uint32_t y = y0 + 8 * u;
+                    v[u] = (act && y < H) ? (uint32_t)__ldg(img + (uint64_t)y * P + x) : 0xFFFFu;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    if (v[u] != 0xFFFFu) atomicAdd(&hist[lane * 257 + v[u]], 1u);
+            }
         } else {
             const uint32_t idx = base + warp;
             if (idx < H) {
                 const uint32_t y = side == 2 ? idx : H - 1 - idx;
                 const uint8_t* row = img + (uint64_t)y * P;
-                for (uint32_t x0 = 0; x0 < W; x0 += 32) {
-                    const uint32_t x = x0 + lane;
-                    const bool act = x < W;
-                    const uint32_t v = act ? row[x] : 0x100u + lane;
-                    const uint32_t m = __match_any_sync(0xffffffffu, v);  // one atomic per distinct value
-                    if (act && lane == __ffs(m) - 1) atomicAdd(&hist[warp * 257 + v], (uint32_t)__popc(m));
+                for (uint32_t x0 = 0; x0 < W; x0 += 32 * 16) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t x = x0 + u * 32 + lane;
+                        v[u] = x < W ? (uint32_t)__ldg(row + x) : 0x100u + lane;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t m = __match_any_sync(0xffffffffu, v[u]);  // one atomic per distinct value
+                        if (v[u] < 0x100u && lane == __ffs(m) - 1) atomicAdd(&hist[warp * 257 + v[u]], (uint32_t)__popc(m));
+                    }
                 }
             }
         }
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(256) resize_general_kernel(const uint8_t* __re
 // kRStages-deep cp.async ring (16-byte async copies, zero-filled outside the frame), ldmatrix feeds the A fragments,
 // the coefficient fragments ride along in the same ring.  The u8 intermediate [ch][16] stays in shared memory
 // (the reference rounds to u8 between the passes); the vertical pass is one thread per output pixel.
-constexpr int kRStages = 3;
+constexpr int kRStagesMax = 4;
 constexpr int kKch = 128;              // pixels per k-chunk (4 IMMA k-steps)
 constexpr int kRowPitch = kKch + 16;   // shared-memory row pitch: ldmatrix rows land on distinct banks
 constexpr int kBFragBytes = 4 * 4 * 32 * 8;  // per k-chunk: 4 k-steps x 4 n-tiles x 32 lanes x (b0,b1)
@@ -242,7 +258,8 @@ struct ResizeMma {
     static constexpr int kThreads = WARPS * 32;
     static constexpr int kRows = WARPS * 32;  // rows per row block: two m16 tiles per warp
     static constexpr int kStageBytes = kRows * kRowPitch + kBFragBytes;
-    static constexpr int kRingBytes = kRStages * kStageBytes;
+    static constexpr int kStages = WARPS == 4 ? 4 : 3;  // deeper ring for the small-CTA config (two CTAs per SM)
+    static constexpr int kRingBytes = kStages * kStageBytes;
 };
 
 template <int WARPS>
@@ -260,10 +277,10 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
     const uint32_t n_rb = (j.ch + Cfg::kRows - 1) / Cfg::kRows;
     const uint32_t total = n_rb * j.n_kch;
 
-    auto issue = [&](uint32_t it) {  // async copies for iteration it = (row block, k-chunk) into stage it % kRStages
+    auto issue = [&](uint32_t it) {  // async copies for iteration it = (row block, k-chunk) into stage it % Cfg::kStages
         if (it < total) {
             const uint32_t rb = it / j.n_kch, kc = it - rb * j.n_kch;
-            uint8_t* st = ring + (it % kRStages) * Cfg::kStageBytes;
+            uint8_t* st = ring + (it % Cfg::kStages) * Cfg::kStageBytes;
             const uint32_t c = tid & 7;
             const uint32_t xb = j.x0_al + kc * kKch + c * 16;  // byte offset inside the frame row
             for (uint32_t r = tid >> 3; r < (uint32_t)Cfg::kRows; r += Cfg::kThreads / 8) {
@@ -287,17 +304,17 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
 
-    for (uint32_t it = 0; it < kRStages - 1; ++it) issue(it);
+    for (uint32_t it = 0; it < Cfg::kStages - 1; ++it) issue(it);
     const int32_t round_h = 1 << (j.prec_h - 1);
     // ldmatrix lane -> (row, byte) inside a 16 x 32-byte A tile: lanes 0-7 rows 0-7 k 0-15, 8-15 rows 8-15 k 0-15,
     // 16-23 rows 0-7 k 16-31, 24-31 rows 8-15 k 16-31  (= registers a0..a3 of mma.m16n8k32)
     const uint32_t lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lbyte = (lane >> 4) * 16;
 
     for (uint32_t it = 0; it < total; ++it) {
-        cp_async_wait<kRStages - 2>();
+        cp_async_wait<Cfg::kStages - 2>();
         __syncthreads();
-        issue(it + kRStages - 1);
-        const uint8_t* st = ring + (it % kRStages) * Cfg::kStageBytes;
+        issue(it + Cfg::kStages - 1);
+        const uint8_t* st = ring + (it % Cfg::kStages) * Cfg::kStageBytes;
         const uint2* sb = reinterpret_cast<const uint2*>(st + Cfg::kRows * kRowPitch);
         const uint8_t* arow = st + (warp * 32 + lrow) * kRowPitch + lbyte;
 #pragma unroll
@@ -722,7 +739,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         d_small = ctx->h_small.as<uint8_t>();
     }
     const size_t tmp_bytes = (size_t)max_ch * 16;
-    const bool four_warps = ctx->hash_variant == 2;
+    const bool four_warps = ctx->hash_variant != 2;  // default: 4 warps, two CTAs per SM
     const size_t ring = four_warps ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
     if (tmp_bytes + ring > 220 * 1024) {
         ctx->err = "frame height beyond the resize kernels' shared-memory budget";

@@ -28,7 +28,12 @@ __global__ void __launch_bounds__(256) rate_kernel(uint32_t* out, uint32_t seed)
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
-            if (OP == 0) v[k] = __popc(v[k]) + 0x55u;  // POPC (+ 1 add)
+            if (OP == 0) {  // POPC fed by a full-rate LOP3 and drained by an add: bound by the POPC pipe alone
+                uint32_t x, pc;
+                asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x) : "r"(v[k]), "r"(a[k]), "r"(seed));
+                asm volatile("popc.b32 %0, %1;" : "=r"(pc) : "r"(x));
+                v[k] += pc;
+            }
             if (OP == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[k]) : "r"(a[k]), "r"(seed));
             if (OP == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(v[k]) : "r"(a[k]));
             if (OP == 3) asm volatile("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(v[k]) : "r"(a[k]), "r"(seed));

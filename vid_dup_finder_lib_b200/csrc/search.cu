@@ -201,11 +201,18 @@ struct HamParams {
     uint32_t chunk;  // column tiles per CTA
     uint32_t tol;
     uint32_t rank, world;
+    uint32_t one;  // = 1, opaque to the compiler: IMAD acc = x * one + acc keeps the accumulate adds on the FMA pipe
 };
 
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// integer multiply-add: issues on the FMA pipe, leaving the ALU pipe to the LOP3s
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
@@ -302,13 +309,13 @@ __global__ void __launch_bounds__(kHamThreads, VARIANT == 0 ? 2 : 1) hamming_til
                         const uint32_t x0 = a[i] ^ b[j], x1 = cc[i] ^ d[j];
                         const uint32_t carry = maj3(ones[i][j], x0, x1);
                         ones[i][j] = xor3(ones[i][j], x0, x1);
-                        acc[i][j] += __popc(carry);
+                        acc[i][j] = imad(__popc(carry), p.one, acc[i][j]);
                     }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = 2 * acc[i][j] + __popc(ones[i][j]);
+                for (int j = 0; j < 8; ++j) acc[i][j] = imad(acc[i][j], p.one + p.one, __popc(ones[i][j]));
         }
 
         // rare path: pairs under the tolerance -> window test -> append
@@ -408,6 +415,7 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const uint32_t* row_til
     p.tol = tol;
     p.rank = ctx->rank;
     p.world = ctx->world;
+    p.one = 1;
     dim3 grid(n_row_tiles, (max_span + chunk - 1) / chunk);
     while (grid.y > 65535) {  // only reachable beyond ~268M columns
         chunk *= 2;
