@@ -35,3 +35,15 @@ if [[ $STEP == all || $STEP == ncu ]]; then
       python bench.py --workload hash --steps 1 --warmup 0 --stacks 32 --no-cpu-baseline > gpurun_out/ncu_resize.log 2>&1; echo "ncu resize rc=$?"
 fi
 ls -la gpurun_out | head -30
+if [[ $STEP == exp ]]; then
+  timeout 900 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "edges_and_groups" > gpurun_out/pytest_variants.log 2>&1; echo "pytest variants rc=$?"; tail -3 gpurun_out/pytest_variants.log
+  for v in 2 1 0; do
+    timeout 600 python bench.py --steps 3 --warmup 2 --variant $v --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_sv$v.json 2> gpurun_out/bench_sv$v.err; echo "bench search v$v rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_sv$v.json'));print(d['value'], d['roofline']['kernel_ms_per_launch'])"
+  done
+  for v in 1 2; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tiles -c 1 -f -o gpurun_out/prof_hamming_v$v \
+      python bench.py --steps 1 --warmup 0 --n 262144 --variant $v --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming_v$v.log 2>&1; echo "ncu hamming v$v rc=$?"
+  done
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_side -c 1 -f -o gpurun_out/prof_letterbox \
+      python bench.py --workload hash --steps 1 --warmup 0 --stacks 256 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
+fi

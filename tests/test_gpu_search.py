@@ -110,7 +110,7 @@ def _case(rng, n, n_clusters, max_flip, dur_choices):
 SIZES = [1, 2, 3, 127, 128, 129, 255, 257, 1000, 4097]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["popc", "csa8x8", "csa8x4"])
 @pytest.mark.parametrize("n", SIZES)
 def test_self_search_edges_and_groups_match_oracle(ctx, n, variant):
     rng = np.random.default_rng(1000 + n)

@@ -356,6 +356,112 @@ __global__ void __launch_bounds__(kHamThreads, VARIANT == 0 ? 2 : 1) hamming_til
     }
 }
 
+// VARIANT 2: the carry-save scheme of variant 1 on an 8x4 register block (two passes over the halves of each
+// column tile): ~half the registers, so two CTAs (16 warps) share an SM and hide the LOP3 -> POPC -> IMAD latencies.
+__global__ void __launch_bounds__(kHamThreads, 2) hamming_tiles_csa4_kernel(const HamParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* sB = sA + kTileWords;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * kTileWords);
+
+    const uint32_t I = blockIdx.x, c = blockIdx.y;
+    if (p.world > 1 && ((I + c) % p.world) != p.rank) return;
+    const uint2 rng = p.tile_range[I];
+    const uint32_t jt0 = rng.x + c * p.chunk;
+    if (jt0 >= rng.y) return;
+    const uint32_t ntiles = min(p.chunk, rng.y - jt0);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s <= kStages; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bars[kStages], kTileWords * 4);
+        bulk_g2s(sA, p.row_tiles + (size_t)I * kTileWords, kTileWords * 4, &bars[kStages]);
+        for (uint32_t s = 0; s < kStages && s < ntiles; ++s) {
+            mbar_expect_tx(&bars[s], kTileWords * 4);
+            bulk_g2s(sB + s * kTileWords, p.col_tiles + (size_t)(jt0 + s) * kTileWords, kTileWords * 4, &bars[s]);
+        }
+    }
+    // thread (ty, tx): rows {4ty..4ty+3, 64+4ty..}; per pass h: cols 64h + 4tx..4tx+3
+    const int ty = tid >> 4, tx = tid & 15;
+    const uint32_t* pa = sA + ty * 4;
+    mbar_wait(&bars[kStages], 0);
+
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        const uint32_t s = t % kStages;
+        mbar_wait(&bars[s], (t / kStages) & 1);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t* pb = sB + s * kTileWords + h * 64 + tx * 4;
+            uint32_t acc[8][4], ones[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0, ones[i][j] = 0;
+#pragma unroll 1
+            for (int w = 0; w < kWords32; w += 2) {
+                const uint4 a0 = *reinterpret_cast<const uint4*>(pa + w * kTile);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(pa + w * kTile + 64);
+                const uint4 b0 = *reinterpret_cast<const uint4*>(pb + w * kTile);
+                const uint4 c0 = *reinterpret_cast<const uint4*>(pa + (w + 1) * kTile);
+                const uint4 c1 = *reinterpret_cast<const uint4*>(pa + (w + 1) * kTile + 64);
+                const uint4 d0 = *reinterpret_cast<const uint4*>(pb + (w + 1) * kTile);
+                const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const uint32_t b[4] = {b0.x, b0.y, b0.z, b0.w};
+                const uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const uint32_t d[4] = {d0.x, d0.y, d0.z, d0.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t x0 = a[i] ^ b[j], x1 = cc[i] ^ d[j];
+                        const uint32_t carry = maj3(ones[i][j], x0, x1);
+                        ones[i][j] = xor3(ones[i][j], x0, x1);
+                        acc[i][j] = imad(__popc(carry), p.one, acc[i][j]);
+                    }
+            }
+            uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j] = imad(acc[i][j], p.one + p.one, __popc(ones[i][j]));
+                    best = min(best, acc[i][j]);
+                }
+            if (best <= p.tol) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mask |= (uint32_t)(acc[i][j] <= p.tol) << (i * 4 + j);
+                const uint32_t col0 = (jt0 + t) * kTile + h * 64 + tx * 4;
+                while (mask) {
+                    const int b = __ffs((int)mask) - 1;
+                    mask &= mask - 1;
+                    const int i = b >> 2, j = b & 3;
+                    const uint32_t gi = I * kTile + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+                    const uint32_t gj = col0 + j;
+                    if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
+                        const unsigned long long slot = atomicAdd(p.counter, 1ull);
+                        if (slot < p.capacity) {
+                            const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
+                            p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + kStages < ntiles) {
+            mbar_expect_tx(&bars[s], kTileWords * 4);
+            bulk_g2s(sB + s * kTileWords, p.col_tiles + (size_t)(jt0 + t + kStages) * kTileWords, kTileWords * 4, &bars[s]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n) {
     if (n == 0) return VDF_OK;
@@ -372,6 +478,7 @@ static int set_ham_attrs(vdf_ctx* ctx) {
     if (done) return VDF_OK;
     VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHamSmem));
     VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHamSmem));
+    VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tiles_csa4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHamSmem));
     done = true;
     return VDF_OK;
 }
@@ -423,7 +530,9 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const uint32_t* row_til
         grid.y = (max_span + chunk - 1) / chunk;
     }
     kt_begin(ctx, 0);
-    if (ctx->search_variant == 1)
+    if (ctx->search_variant == 2)
+        hamming_tiles_csa4_kernel<<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
+    else if (ctx->search_variant == 1)
         hamming_tiles_kernel<1><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
     else
         hamming_tiles_kernel<0><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
