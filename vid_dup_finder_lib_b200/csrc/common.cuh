@@ -91,7 +91,8 @@ struct vdf_ctx {
     std::string err;
     uint32_t rank = 0, world = 1;
     uint64_t max_edges = 1ull << 28, initial_edges = 1ull << 22;
-    int search_variant = 1;  // 1: XOR + carry-save adder + POPC (default), 0: plain XOR + POPC
+    int search_variant = 2;  // 0: plain XOR + POPC; 1: XOR + carry-save adder + POPC, 8x8 pairs/thread;
+                             // 2 (default): carry-save on 8x4 pairs/thread, two CTAs per SM
     int hash_variant = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0;
     // device time of the dominant kernels (CUDA events on `stream`): 0 hamming tiles, 1 resize, 2 letterbox, 3 dct+pack

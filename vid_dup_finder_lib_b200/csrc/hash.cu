@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
     const uint32_t limit = cols ? W : H, len = cols ? H : W;
     const uint32_t panel = cols ? kColPanel : kRowPanel;
     for (uint32_t base = 0; base < limit; base += panel) {
-        for (uint32_t q = tid; q < panel * 257; q += 256) hist[q] = 0;
+        for (uint32_t q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
         __syncthreads();
         if (cols) {
             const uint32_t idx = base + lane;
@@ -99,25 +99,52 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
             if (idx < H) {
                 const uint32_t y = side == 2 ? idx : H - 1 - idx;
                 const uint8_t* row = img + (uint64_t)y * P;
-                for (uint32_t x0 = 0; x0 < W; x0 += 32 * 16) {
+                // four sub-histograms per row (lane & 3) keep same-value lanes from piling onto one counter
+                uint32_t* h4 = hist + (warp * 4) * 257;
+                uint32_t* hs = h4 + (lane & 3) * 257;
+                uint32_t x_done = 0;
+                if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // whole row in flight: up to 16 x 4 pixels per lane
+                    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+                    const uint32_t W4 = W >> 2;
+                    for (uint32_t q0 = 0; q0 < W4; q0 += 32 * 16) {
+                        uint32_t v[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const uint32_t q = q0 + u * 32 + lane;
+                            v[u] = q < W4 ? __ldg(row4 + q) : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            if (q0 + u * 32 + lane < W4) {
+                                atomicAdd(&hs[v[u] & 255u], 1u);
+                                atomicAdd(&hs[(v[u] >> 8) & 255u], 1u);
+                                atomicAdd(&hs[(v[u] >> 16) & 255u], 1u);
+                                atomicAdd(&hs[v[u] >> 24], 1u);
+                            }
+                        }
+                    }
+                    x_done = W4 << 2;
+                }
+                for (uint32_t x0 = x_done; x0 < W; x0 += 32 * 16) {
                     uint32_t v[16];
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
                         const uint32_t x = x0 + u * 32 + lane;
-                        v[u] = x < W ? (uint32_t)__ldg(row + x) : 0x100u + lane;
+                        v[u] = x < W ? (uint32_t)__ldg(row + x) : 0x100u;
                     }
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const uint32_t m = __match_any_sync(0xffffffffu, v[u]);  // one atomic per distinct value
-                        if (v[u] < 0x100u && lane == __ffs(m) - 1) atomicAdd(&hist[warp * 257 + v[u]], (uint32_t)__popc(m));
-                    }
+                    for (int u = 0; u < 16; ++u)
+                        if (v[u] < 0x100u) atomicAdd(&hs[v[u]], 1u);
                 }
+                __syncwarp();
+                for (int v = lane; v < 256; v += 32) h4[v] += h4[257 + v] + h4[514 + v] + h4[771 + v];
+                __syncwarp();
             }
         }
         __syncthreads();
         for (uint32_t k = warp; k < panel; k += 8) {
             bool ok = false;
-            if (base + k < limit) ok = strip_is_letterbox(hist + k * 257, len, lane);
+            if (base + k < limit) ok = strip_is_letterbox(hist + (cols ? k : k * 4) * 257, len, lane);
             if (lane == 0) flags[k] = ok;
         }
         __syncthreads();
@@ -169,6 +196,7 @@ struct StackJob {
     uint32_t win_h, prec_h, win_v, prec_v;
     // tensor-core path (resize_mma_kernel): present iff the stack's addresses are 16-byte aligned
     const uint2* kb;     // horizontal coefficients as IMMA B fragments: [k-step][n-tile 0..3][lane] (b0, b1)
+    const uint8_t* kmask;  // per k-chunk: bit (2*ks + octet) set iff outputs 8*octet..+7 have a tap in k-step ks
     uint32_t x0_al;      // first column loaded = left rounded down to 16
     uint32_t n_kch;      // 128-pixel k-chunks covering [x0_al, left + cw)
     uint32_t fast;       // 1: resize_mma_kernel, 0: resize_general_kernel
@@ -317,23 +345,29 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
         const uint8_t* st = ring + (it % Cfg::kStages) * Cfg::kStageBytes;
         const uint2* sb = reinterpret_cast<const uint2*>(st + Cfg::kRows * kRowPitch);
         const uint8_t* arow = st + (warp * 32 + lrow) * kRowPitch + lbyte;
+        const uint32_t rb = it / j.n_kch, kc = it - rb * j.n_kch;
+        const uint32_t tapmask = __ldg(j.kmask + kc);  // the coefficient band is ~7 outputs wide: skip all-zero n-tiles
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
+            if (((tapmask >> (2 * ks)) & 3u) == 0) continue;
             uint32_t a0[4], a1[4];
             ldmatrix_x4(a0, arow + ks * 32);
             ldmatrix_x4(a1, arow + 16 * kRowPitch + ks * 32);
-            const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b1 = sb[(ks * 4 + 1) * 32 + lane];
-            const uint2 b2 = sb[(ks * 4 + 2) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
-            imma_u8s8(acc[0][0], a0, b0);
-            imma_u8s8(acc[1][0], a1, b0);
-            imma_u8s8(acc[0][1], a0, b1);
-            imma_u8s8(acc[1][1], a1, b1);
-            imma_u8u8(acc[0][2], a0, b2);
-            imma_u8u8(acc[1][2], a1, b2);
-            imma_u8u8(acc[0][3], a0, b3);
-            imma_u8u8(acc[1][3], a1, b3);
+            if (tapmask & (1u << (2 * ks))) {  // outputs 0-7: high bytes (n-tile 0), low bytes (n-tile 2)
+                const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b2 = sb[(ks * 4 + 2) * 32 + lane];
+                imma_u8s8(acc[0][0], a0, b0);
+                imma_u8s8(acc[1][0], a1, b0);
+                imma_u8u8(acc[0][2], a0, b2);
+                imma_u8u8(acc[1][2], a1, b2);
+            }
+            if (tapmask & (2u << (2 * ks))) {  // outputs 8-15
+                const uint2 b1 = sb[(ks * 4 + 1) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
+                imma_u8s8(acc[0][1], a0, b1);
+                imma_u8s8(acc[1][1], a1, b1);
+                imma_u8u8(acc[0][3], a0, b3);
+                imma_u8u8(acc[1][3], a1, b3);
+            }
         }
-        const uint32_t rb = it / j.n_kch, kc = it - rb * j.n_kch;
         if (kc + 1 == j.n_kch) {  // row block finished: k = 256*kh + kl, round, shift, clamp -> u8 intermediate
             const uint32_t g = lane >> 2, q2 = (lane & 3) * 2;
 #pragma unroll
@@ -593,7 +627,7 @@ void free_coef_cache(vdf_ctx* ctx) {
 // IMMA B fragments of the horizontal coefficients for a crop that starts `shift` bytes after a 16-byte boundary:
 // [k-step][n-tile][lane] -> (b0, b1); n-tiles 0,1 = high bytes (signed) of outputs 0-7 / 8-15, 2,3 = low bytes.
 // mma.m16n8k32 B layout: b0 holds k = 4*(lane%4)+0..3, b1 the same +16, column n = lane/4.
-static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const uint2** out) {
+static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const uint2** out, const uint8_t** mask_out) {
     const uint64_t key = ((uint64_t)t.in_size << 8) | shift;
     auto it = ctx->bfrag_cache.find(key);
     if (it == ctx->bfrag_cache.end()) {
@@ -615,6 +649,19 @@ static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const ui
                         }
                         frag[(((size_t)ks * 4 + nt) * 32 + lane) * 2 + reg] = word;
                     }
+        // tap masks, appended behind the fragments: per k-chunk bit (2*ks + octet)
+        const size_t frag_words = frag.size();
+        frag.resize(frag_words + (n_kch + 3) / 4, 0u);
+        uint8_t* masks = reinterpret_cast<uint8_t*>(frag.data() + frag_words);
+        for (uint32_t ks = 0; ks < ksteps; ++ks)
+            for (uint32_t oct = 0; oct < 2; ++oct) {
+                bool any = false;
+                for (uint32_t lane = 0; lane < 32 && !any; ++lane)
+                    for (uint32_t reg = 0; reg < 2 && !any; ++reg)
+                        any = frag[(((size_t)ks * 4 + oct) * 32 + lane) * 2 + reg] != 0 ||
+                              frag[(((size_t)ks * 4 + 2 + oct) * 32 + lane) * 2 + reg] != 0;
+                if (any) masks[ks / 4] |= (uint8_t)(1u << (2 * (ks % 4) + oct));
+            }
         void* d = nullptr;
         VDF_ALLOC(ctx, cudaMalloc(&d, frag.size() * 4));
         VDF_CUDA(ctx, cudaMemcpyAsync(d, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -622,6 +669,7 @@ static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const ui
         it = ctx->bfrag_cache.emplace(key, d).first;
     }
     *out = reinterpret_cast<const uint2*>(it->second);
+    *mask_out = reinterpret_cast<const uint8_t*>(it->second) + (size_t)((shift + t.in_size + kKch - 1) / kKch) * kBFragBytes;
     return VDF_OK;
 }
 
@@ -721,7 +769,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
             j.x0_al = j.left & ~15u;
             const uint32_t shift = j.left - j.x0_al;
             j.n_kch = (shift + j.cw + kKch - 1) / kKch;
-            VDF_TRY(get_bfrags(ctx, *th, shift, &j.kb));
+            VDF_TRY(get_bfrags(ctx, *th, shift, &j.kb, &j.kmask));
             j.fast = 1;
             any_fast = true;
         } else {
