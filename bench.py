@@ -34,7 +34,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="search", choices=["search", "hash"])
+    ap.add_argument("--workload", default="search", choices=["search", "hash", "refs"])
+    ap.add_argument("--n-query", type=int, default=100_000)
+    ap.add_argument("--n-corpus", type=int, default=10_000_000)
     ap.add_argument("--n", type=int, default=1_000_000, help="hashes in the all-pairs search")
     ap.add_argument("--tol", type=float, default=0.35)
     ap.add_argument("--variant", type=int, default=-1, help="search kernel variant (-1: library default)")
@@ -314,6 +316,53 @@ def main():
                                              "(the reference's search is single-threaded)"}
         return out
 
+    # ---------------------------------------------------------------- query-vs-reference workload (BASELINE configs[3])
+    def bench_refs(steps, warmup):
+        """search_with_references: --n-query hashes against a sorted table of --n-corpus hashes whose contiguous slices
+        are spread over the ranks (each rank: all queries x its slice); keys are all-gathered and merged."""
+        nq, nc, tol_int = args.n_query, args.n_corpus, tolerance_to_int(args.tol)
+        corpus, _ = synth.planted_hashes(nc)
+        rng = np.random.default_rng(7)
+        queries = synth.random_hashes(nq, seed=synth.SEED + 1)
+        hit = rng.integers(0, nq, nq // 20)  # 5 % of the queries are perturbed copies of corpus entries
+        flips = np.packbits(rng.integers(0, 1024, (len(hit), 1024)) < 100, axis=1, bitorder="little").view(np.uint64)
+        queries[hit] = corpus[rng.integers(0, nc, len(hit))] ^ flips
+        cdur = np.full(nc, 600, np.uint32)
+        qdur = np.full(nq, 600, np.uint32)
+        b, e = vdist.shard_range(nc, rank, world)
+        with torch.cuda.stream(stream):
+            d_c = torch.from_numpy(corpus[b:e].view(np.int64)).to(dev)
+            d_cd = torch.from_numpy(cdur[b:e].view(np.int32)).to(dev)
+            d_q = torch.from_numpy(queries.view(np.int64)).to(dev)
+            d_qd = torch.from_numpy(qdur.view(np.int32)).to(dev)
+        result = {}
+
+        def step():
+            keys = vdist.search_refs_keys(ctx, d_c, d_cd, b, d_q, d_qd, tol_int)
+            result["matches"] = int(keys.numel())
+
+        with ClockSampler(local) as cs:
+            with torch.cuda.stream(stream):
+                for _ in range(warmup):
+                    step()
+            ctx.kernel_time(0, reset=True)
+            l0 = ctx.counters()[0]
+            secs = timed(step, steps, 0, True)
+        launches = ctx.counters()[0] - l0
+        k_ms, k_n = ctx.kernel_time(0, reset=True)
+        pairs = nq * nc
+        popc_peak, popc_src = popc_peak_gpopc(sm_count, sm_max_mhz)
+        achieved = PAIR_POPC32 * (pairs / world) / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+        return {"metric": "hamming_pair_comparisons_per_s", "value": pairs * steps / secs, "unit": "pairs/s",
+                "ms_per_step": secs / steps * 1e3, "scaling": "strong", "dtype": "u32",
+                "roofline": {"bound": "int_popc", "kernel": "hamming_tiles kernel", "achieved": achieved, "peak": popc_peak,
+                             "unit": "GPOPC32/s", "frac": (achieved / popc_peak) if achieved else None, "traffic": None,
+                             "peak_source": popc_src, "kernel_ms_per_launch": k_ms / max(k_n, 1)},
+                "gpu_launches": int(launches), "clocks": cs.summary(),
+                "config": {"workload": f"search_with_references, {nq} queries x {nc} sorted table entries, equal durations, "
+                                       f"tolerance {args.tol}", "matches": result.get("matches"),
+                           "parallelism": f"table slice x{world}", "l2": "512 MiB write between timed steps"}}
+
     # ---------------------------------------------------------------- hashing workload
     def bench_hash(steps, warmup):
         w, h, ns = args.width, args.height, args.stacks
@@ -391,6 +440,8 @@ def main():
                 line["secondary"] = bench_hash(max(2, args.steps), max(3, args.warmup))
             except Exception as e:  # the secondary metric must not take the headline down with it
                 line["secondary"] = {"error": repr(e)}
+    elif args.workload == "refs":
+        line = bench_refs(args.steps, args.warmup)
     else:
         line = bench_hash(args.steps, args.warmup)
     line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,

@@ -20,7 +20,7 @@ if [[ $STEP == all || $STEP == bench ]]; then
   timeout 600 python bench.py --steps 3 --warmup 3 --variant 1 --no-secondary --no-cpu-baseline > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err; echo "bench v1 rc=$?"; tail -c 1500 gpurun_out/bench_v1.json
 fi
 if [[ $STEP == hash ]]; then
-  for v in 0 2 1; do
+  for v in 0 3 2; do
     timeout 600 python bench.py --workload hash --steps 5 --warmup 3 --hash-variant $v --no-cpu-baseline > gpurun_out/bench_hash_v$v.json 2> gpurun_out/bench_hash_v$v.err; echo "bench hash v$v rc=$?"; tail -c 1800 gpurun_out/bench_hash_v$v.json; tail -3 gpurun_out/bench_hash_v$v.err
   done
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize_mma -c 1 -f -o gpurun_out/prof_resize_mma \
@@ -46,4 +46,10 @@ if [[ $STEP == exp ]]; then
   done
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_side -c 1 -f -o gpurun_out/prof_letterbox \
       python bench.py --workload hash --steps 1 --warmup 0 --stacks 256 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
+fi
+if [[ $STEP == multi ]]; then
+  N=${2:-2}
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 scripts/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "dist_check rc=$?"; tail -6 gpurun_out/dist_check_$N.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_g$N.json 2> gpurun_out/bench_g$N.err; echo "bench x$N rc=$?"; tail -c 1500 gpurun_out/bench_g$N.json; tail -3 gpurun_out/bench_g$N.err
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus $N --steps 1 --warmup 0 --n 100000 > gpurun_out/bench_ref_g$N.json 2>&1; echo "bench ref x$N rc=$?"
 fi

@@ -294,7 +294,10 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
     resize_mma_kernel(const uint8_t* __restrict__ frames, const StackJob* __restrict__ jobs, uint8_t* __restrict__ small) {
     using Cfg = ResizeMma<WARPS>;
+    constexpr int kRowsPerPass = Cfg::kThreads / 8;        // rows covered by one 16-byte copy per thread
+    constexpr int kCopies = Cfg::kRows / kRowsPerPass;     // pixel copies per thread per stage
     extern __shared__ __align__(128) uint8_t smem_dyn[];
+    __shared__ uint8_t s_mask[256];
     uint8_t* ring = smem_dyn;
     uint8_t* tmp = smem_dyn + Cfg::kRingBytes;  // ch x 16
     const uint32_t s = blockIdx.x >> 4, t = blockIdx.x & 15;
@@ -305,21 +308,36 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
     const uint32_t n_rb = (j.ch + Cfg::kRows - 1) / Cfg::kRows;
     const uint32_t total = n_rb * j.n_kch;
 
-    auto issue = [&](uint32_t it) {  // async copies for iteration it = (row block, k-chunk) into stage it % Cfg::kStages
-        if (it < total) {
-            const uint32_t rb = it / j.n_kch, kc = it - rb * j.n_kch;
-            uint8_t* st = ring + (it % Cfg::kStages) * Cfg::kStageBytes;
-            const uint32_t c = tid & 7;
-            const uint32_t xb = j.x0_al + kc * kKch + c * 16;  // byte offset inside the frame row
-            for (uint32_t r = tid >> 3; r < (uint32_t)Cfg::kRows; r += Cfg::kThreads / 8) {
-                const uint32_t row = rb * Cfg::kRows + r;
-                const bool ok = row < j.ch && xb < j.pitch;
-                const uint8_t* src = ok ? img + (uint64_t)row * j.pitch + kc * kKch + c * 16 : img;
-                cp_async16(st + r * kRowPitch + c * 16, src, ok ? 16u : 0u);
+    // ---- producer: (row block, k-chunk) advance incrementally, no divisions or 64-bit multiplies per copy
+    const uint32_t c16 = (tid & 7) * 16, r0 = tid >> 3;
+    const uint64_t row_step = (uint64_t)kRowsPerPass * j.pitch;
+    const uint8_t* g_rb = img + (uint64_t)r0 * j.pitch + c16;  // this thread's first row of the current row block
+    const uint32_t sdst0 = r0 * kRowPitch + c16;
+    uint32_t p_it = 0, p_kc = 0, p_row0 = r0, p_stage = 0;
+    auto issue = [&]() {
+        if (p_it < total) {
+            uint8_t* st = ring + p_stage * Cfg::kStageBytes;
+            const bool xok = j.x0_al + p_kc * kKch + c16 < j.pitch;
+            const uint8_t* g = g_rb + p_kc * kKch;
+            uint32_t row = p_row0;
+#pragma unroll
+            for (int i = 0; i < kCopies; ++i) {
+                const bool ok = xok && row < j.ch;
+                cp_async16(st + sdst0 + i * kRowsPerPass * kRowPitch, ok ? g : img, ok ? 16u : 0u);
+                g += row_step;
+                row += kRowsPerPass;
             }
-            const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(j.kb) + (size_t)kc * kBFragBytes;
-            for (uint32_t q = tid; q < kBFragBytes / 16; q += Cfg::kThreads)
-                cp_async16(st + Cfg::kRows * kRowPitch + q * 16, bsrc + q * 16, 16u);
+            const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(j.kb) + (size_t)p_kc * kBFragBytes + tid * 16;
+#pragma unroll
+            for (int q = 0; q < kBFragBytes / 16 / Cfg::kThreads; ++q)
+                cp_async16(st + Cfg::kRows * kRowPitch + tid * 16 + q * Cfg::kThreads * 16, bsrc + q * Cfg::kThreads * 16, 16u);
+            ++p_it;
+            if (++p_stage == Cfg::kStages) p_stage = 0;
+            if (++p_kc == j.n_kch) {
+                p_kc = 0;
+                p_row0 += Cfg::kRows;
+                g_rb += (uint64_t)Cfg::kRows * j.pitch;
+            }
         }
         cp_async_commit();
     };
@@ -332,35 +350,61 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
 
-    for (uint32_t it = 0; it < Cfg::kStages - 1; ++it) issue(it);
+    for (int q = 0; q < Cfg::kStages - 1; ++q) issue();
+    // tap masks of all k-chunks (<= 256 chunks) live in shared memory: no global load per iteration
+    for (uint32_t q = tid; q < j.n_kch && q < 256; q += Cfg::kThreads) s_mask[q] = j.kmask[q];
     const int32_t round_h = 1 << (j.prec_h - 1);
     // ldmatrix lane -> (row, byte) inside a 16 x 32-byte A tile: lanes 0-7 rows 0-7 k 0-15, 8-15 rows 8-15 k 0-15,
     // 16-23 rows 0-7 k 16-31, 24-31 rows 8-15 k 16-31  (= registers a0..a3 of mma.m16n8k32)
     const uint32_t lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lbyte = (lane >> 4) * 16;
+    const uint32_t a_off = (warp * 32 + lrow) * kRowPitch + lbyte;
 
+    uint32_t c_kc = 0, c_rb = 0, c_stage = 0;
     for (uint32_t it = 0; it < total; ++it) {
         cp_async_wait<Cfg::kStages - 2>();
         __syncthreads();
-        issue(it + Cfg::kStages - 1);
-        const uint8_t* st = ring + (it % Cfg::kStages) * Cfg::kStageBytes;
+        issue();
+        const uint8_t* st = ring + c_stage * Cfg::kStageBytes;
         const uint2* sb = reinterpret_cast<const uint2*>(st + Cfg::kRows * kRowPitch);
-        const uint8_t* arow = st + (warp * 32 + lrow) * kRowPitch + lbyte;
-        const uint32_t rb = it / j.n_kch, kc = it - rb * j.n_kch;
-        const uint32_t tapmask = __ldg(j.kmask + kc);  // the coefficient band is ~7 outputs wide: skip all-zero n-tiles
+        const uint8_t* arow = st + a_off;
+        const uint32_t tapmask = s_mask[c_kc];  // the coefficient band is ~7 outputs wide
+        // three straight-line bodies per k-chunk: taps only in outputs 0-7, only in 8-15, or in both
+        const bool lo_oct = (tapmask & 0x55u) != 0, hi_oct = (tapmask & 0xAAu) != 0;
+        if (lo_oct && hi_oct) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            if (((tapmask >> (2 * ks)) & 3u) == 0) continue;
-            uint32_t a0[4], a1[4];
-            ldmatrix_x4(a0, arow + ks * 32);
-            ldmatrix_x4(a1, arow + 16 * kRowPitch + ks * 32);
-            if (tapmask & (1u << (2 * ks))) {  // outputs 0-7: high bytes (n-tile 0), low bytes (n-tile 2)
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t a0[4], a1[4];
+                ldmatrix_x4(a0, arow + ks * 32);
+                ldmatrix_x4(a1, arow + 16 * kRowPitch + ks * 32);
+                const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b1 = sb[(ks * 4 + 1) * 32 + lane];
+                const uint2 b2 = sb[(ks * 4 + 2) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
+                imma_u8s8(acc[0][0], a0, b0);
+                imma_u8s8(acc[1][0], a1, b0);
+                imma_u8s8(acc[0][1], a0, b1);
+                imma_u8s8(acc[1][1], a1, b1);
+                imma_u8u8(acc[0][2], a0, b2);
+                imma_u8u8(acc[1][2], a1, b2);
+                imma_u8u8(acc[0][3], a0, b3);
+                imma_u8u8(acc[1][3], a1, b3);
+            }
+        } else if (lo_oct) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t a0[4], a1[4];
+                ldmatrix_x4(a0, arow + ks * 32);
+                ldmatrix_x4(a1, arow + 16 * kRowPitch + ks * 32);
                 const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b2 = sb[(ks * 4 + 2) * 32 + lane];
                 imma_u8s8(acc[0][0], a0, b0);
                 imma_u8s8(acc[1][0], a1, b0);
                 imma_u8u8(acc[0][2], a0, b2);
                 imma_u8u8(acc[1][2], a1, b2);
             }
-            if (tapmask & (2u << (2 * ks))) {  // outputs 8-15
+        } else if (hi_oct) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t a0[4], a1[4];
+                ldmatrix_x4(a0, arow + ks * 32);
+                ldmatrix_x4(a1, arow + 16 * kRowPitch + ks * 32);
                 const uint2 b1 = sb[(ks * 4 + 1) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
                 imma_u8s8(acc[0][1], a0, b1);
                 imma_u8s8(acc[1][1], a1, b1);
@@ -368,13 +412,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
                 imma_u8u8(acc[1][3], a1, b3);
             }
         }
-        if (kc + 1 == j.n_kch) {  // row block finished: k = 256*kh + kl, round, shift, clamp -> u8 intermediate
+        if (++c_stage == Cfg::kStages) c_stage = 0;
+        if (++c_kc == j.n_kch) {  // row block finished: k = 256*kh + kl, round, shift, clamp -> u8 intermediate
             const uint32_t g = lane >> 2, q2 = (lane & 3) * 2;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    const uint32_t row = rb * Cfg::kRows + warp * 32 + mt * 16 + g + half * 8;
+                    const uint32_t row = c_rb * Cfg::kRows + warp * 32 + mt * 16 + g + half * 8;
 #pragma unroll
                     for (int oct = 0; oct < 2; ++oct)
 #pragma unroll
@@ -389,17 +434,25 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
                 for (int b = 0; b < 4; ++b)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
+            c_kc = 0;
+            ++c_rb;
         }
     }
     cp_async_wait<0>();
+    __syncthreads();
+    // vertical pass: the 16 x win_v coefficient table is staged in the (now idle) ring, one thread per output pixel
+    int16_t* skv = reinterpret_cast<int16_t*>(ring);
+    for (uint32_t q = tid; q < 16 * j.win_v; q += Cfg::kThreads) skv[q] = __ldg(j.kv + q);
     __syncthreads();
     const int32_t init_v = 1 << (j.prec_v - 1);
     for (uint32_t it = tid; it < 256; it += Cfg::kThreads) {
         const uint32_t oy = it >> 4, ox = it & 15;
         const uint32_t s0 = j.bv[2 * oy], sz = j.bv[2 * oy + 1];
-        const int16_t* k = j.kv + oy * j.win_v;
+        const int16_t* k = skv + oy * j.win_v;
+        const uint8_t* px = tmp + s0 * 16 + ox;
         int32_t a = init_v;
-        for (uint32_t q = 0; q < sz; ++q) a += (int32_t)tmp[(s0 + q) * 16 + ox] * (int32_t)k[q];
+#pragma unroll 8
+        for (uint32_t q = 0; q < sz; ++q) a += (int32_t)px[q * 16] * (int32_t)k[q];
         small[((uint64_t)s * 16 + t) * 256 + it] = clip8(a, j.prec_v);
     }
 }
@@ -628,7 +681,8 @@ void free_coef_cache(vdf_ctx* ctx) {
 // [k-step][n-tile][lane] -> (b0, b1); n-tiles 0,1 = high bytes (signed) of outputs 0-7 / 8-15, 2,3 = low bytes.
 // mma.m16n8k32 B layout: b0 holds k = 4*(lane%4)+0..3, b1 the same +16, column n = lane/4.
 static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const uint2** out, const uint8_t** mask_out) {
-    const uint64_t key = ((uint64_t)t.in_size << 8) | shift;
+    const bool dense = ctx->hash_variant == 3;  // experiment knob: never skip coefficient tiles
+    const uint64_t key = ((uint64_t)t.in_size << 8) | shift | (dense ? 1ull << 62 : 0);
     auto it = ctx->bfrag_cache.find(key);
     if (it == ctx->bfrag_cache.end()) {
         const uint32_t n_kch = (shift + t.in_size + kKch - 1) / kKch, ksteps = n_kch * 4;
@@ -660,7 +714,7 @@ static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const ui
                     for (uint32_t reg = 0; reg < 2 && !any; ++reg)
                         any = frag[(((size_t)ks * 4 + oct) * 32 + lane) * 2 + reg] != 0 ||
                               frag[(((size_t)ks * 4 + 2 + oct) * 32 + lane) * 2 + reg] != 0;
-                if (any) masks[ks / 4] |= (uint8_t)(1u << (2 * (ks % 4) + oct));
+                if (any || dense) masks[ks / 4] |= (uint8_t)(1u << (2 * (ks % 4) + oct));
             }
         void* d = nullptr;
         VDF_ALLOC(ctx, cudaMalloc(&d, frag.size() * 4));
@@ -765,9 +819,11 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         // tensor-core path needs 16-byte aligned rows (cp.async 16 B): base, frame stride and pitch
         const bool aligned = ((reinterpret_cast<uintptr_t>(d_frames) + d.offset) % 16 == 0) && d.frame_stride % 16 == 0 &&
                              d.pitch % 16 == 0;
-        if (aligned && ctx->hash_variant != 1) {
+        const uint32_t shift = j.left & 15u;
+        const size_t ring_bytes = ctx->hash_variant != 2 ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
+        const bool fits = (shift + j.cw + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring_bytes;
+        if (aligned && fits && ctx->hash_variant != 1) {
             j.x0_al = j.left & ~15u;
-            const uint32_t shift = j.left - j.x0_al;
             j.n_kch = (shift + j.cw + kKch - 1) / kKch;
             VDF_TRY(get_bfrags(ctx, *th, shift, &j.kb, &j.kmask));
             j.fast = 1;
