@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--workload", default="search", choices=["search", "hash", "refs"])
     ap.add_argument("--n-query", type=int, default=100_000)
     ap.add_argument("--n-corpus", type=int, default=10_000_000)
-    ap.add_argument("--n", type=int, default=1_000_000, help="hashes in the all-pairs search")
+    ap.add_argument("--n-hashes", "--n", dest="n", type=int, default=1_000_000, help="hashes in the all-pairs search")
     ap.add_argument("--tol", type=float, default=0.35)
     ap.add_argument("--variant", type=int, default=-1, help="search kernel variant (-1: library default)")
     ap.add_argument("--hash-variant", type=int, default=-1, help="resize kernel: 0 IMMA 8 warps, 1 general, 2 IMMA 4 warps")
@@ -172,18 +172,31 @@ def run_reference(args):
         sample = f"{per} synthetic {args.width}x{args.height} stacks per step, {cores} threads"
         config = {"workload": f"frame-stack hashing, {args.width}x{args.height}x16 u8 stacks, letterbox cropdetect"}
     v = units / dt
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": v, "unit": unit, "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def emit(line: dict):
+    """the ONE JSON line goes to the real stdout; everything libraries print (NCCL banner, torchrun notes) was
+    re-routed to stderr by main()"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # stray prints from native libraries must not pollute the JSON line
     if args.impl == "reference":
         return run_reference(args)
 
@@ -447,7 +460,7 @@ def main():
     line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
                  "data": "synthetic", "impl": "ours"})
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,7 +30,7 @@ if [[ $STEP == all || $STEP == ncu ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 1 --stacks 64 > gpurun_out/bench_under_ncu.json 2>&1; echo "ncu list rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tiles -c 1 -f -o gpurun_out/prof_hamming \
-      python bench.py --steps 1 --warmup 0 --n 262144 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming.log 2>&1; echo "ncu hamming rc=$?"
+      python bench.py --steps 1 --warmup 0 --n-hashes 262144 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming.log 2>&1; echo "ncu hamming rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize -c 1 -f -o gpurun_out/prof_resize \
       python bench.py --workload hash --steps 1 --warmup 0 --stacks 32 --no-cpu-baseline > gpurun_out/ncu_resize.log 2>&1; echo "ncu resize rc=$?"
 fi
@@ -42,7 +42,7 @@ if [[ $STEP == exp ]]; then
   done
   for v in 1 2; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tiles -c 1 -f -o gpurun_out/prof_hamming_v$v \
-      python bench.py --steps 1 --warmup 0 --n 262144 --variant $v --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming_v$v.log 2>&1; echo "ncu hamming v$v rc=$?"
+      python bench.py --steps 1 --warmup 0 --n-hashes 262144 --variant $v --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming_v$v.log 2>&1; echo "ncu hamming v$v rc=$?"
   done
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_side -c 1 -f -o gpurun_out/prof_letterbox \
       python bench.py --workload hash --steps 1 --warmup 0 --stacks 256 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
@@ -51,5 +51,5 @@ if [[ $STEP == multi ]]; then
   N=${2:-2}
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 scripts/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "dist_check rc=$?"; tail -6 gpurun_out/dist_check_$N.log
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_g$N.json 2> gpurun_out/bench_g$N.err; echo "bench x$N rc=$?"; tail -c 1500 gpurun_out/bench_g$N.json; tail -3 gpurun_out/bench_g$N.err
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus $N --steps 1 --warmup 0 --n 100000 > gpurun_out/bench_ref_g$N.json 2>&1; echo "bench ref x$N rc=$?"
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus $N --steps 1 --warmup 0 --n-hashes 100000 > gpurun_out/bench_ref_g$N.json 2>&1; echo "bench ref x$N rc=$?"
 fi
