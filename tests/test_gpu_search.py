@@ -110,7 +110,7 @@ def _case(rng, n, n_clusters, max_flip, dur_choices):
 SIZES = [1, 2, 3, 127, 128, 129, 255, 257, 1000, 4097]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["popc", "csa8x8", "csa8x4"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["popc", "csa8x8", "csa8x4", "tcgen05"])
 @pytest.mark.parametrize("n", SIZES)
 def test_self_search_edges_and_groups_match_oracle(ctx, n, variant):
     rng = np.random.default_rng(1000 + n)
@@ -160,8 +160,17 @@ def test_random_edge_lists_group_like_the_oracle(ctx):
         assert np.array_equal(gp, want_gp) and np.array_equal(mm, want_mm)
 
 
+@pytest.mark.parametrize("variant", [0, 3], ids=["popc", "tcgen05"])
 @pytest.mark.parametrize("n_cand,n_ref", [(1, 1), (300, 5), (129, 257), (5000, 700)])
-def test_ref_search_matches_oracle(ctx, n_cand, n_ref):
+def test_ref_search_matches_oracle(ctx, n_cand, n_ref, variant):
+    ctx.set_option("search_variant", variant)
+    try:
+        _ref_search_case(ctx, n_cand, n_ref)
+    finally:
+        ctx.set_option("search_variant", 0)
+
+
+def _ref_search_case(ctx, n_cand, n_ref):
     rng = np.random.default_rng(n_cand * 31 + n_ref)
     durs = [0, 9, 10, 11, 95, 100, 105, 106, 600, 630, 631]
     C, cdur = _case(rng, n_cand, max(1, n_cand // 9), 150, durs)

@@ -56,7 +56,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
                       &ctx->g_rks,     &ctx->g_state,   &ctx->g_parent, &ctx->g_wl0,   &ctx->g_wla,   &ctx->g_wlb,
                       &ctx->g_mk,      &ctx->g_mks,     &ctx->g_flag,   &ctx->g_scan,  &ctx->g_gp,    &ctx->g_mem,
                       &ctx->h_frames[0], &ctx->h_frames[1], &ctx->h_jobs, &ctx->h_sides, &ctx->h_crop, &ctx->h_small,
-                      &ctx->h_hash,    &ctx->h_desc};
+                      &ctx->h_hash,    &ctx->h_desc,    &ctx->exp_rows, &ctx->exp_cols, &ctx->pc_rows, &ctx->pc_cols};
     for (DevBuf* b : bufs) b->release();
     ctx->pin_a.release();
     ctx->pin_b.release();
@@ -94,7 +94,7 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "max_edges" && value > 0) ctx->max_edges = (uint64_t)value;
     else if (k == "initial_edges" && value > 0) ctx->initial_edges = (uint64_t)value;
-    else if (k == "search_variant" && (value >= 0 && value <= 2)) ctx->search_variant = (int)value;
+    else if (k == "search_variant" && (value >= 0 && value <= 3)) ctx->search_variant = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;
     else {
         ctx->err = "unknown option or bad value: " + k;

@@ -104,6 +104,7 @@ struct vdf_ctx {
     // search scratch
     vdf::DevBuf row_tiles, col_tiles, row_lo, row_hi, row_id, tile_range, raw_keys, sort_tmp, misc, keys_a, keys_b;
     vdf::DevBuf in_hash, in_dur, in_hash2, in_dur2, ref_perm, ref_key;
+    vdf::DevBuf exp_rows, exp_cols, pc_rows, pc_cols;  // tensor-core search: byte-expanded tiles + popcounts
     // grouping scratch
     vdf::DevBuf g_rk, g_rks, g_state, g_parent, g_wl0, g_wla, g_wlb, g_mk, g_mks, g_flag, g_scan, g_gp, g_mem;
     // hashing scratch
@@ -165,6 +166,11 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
                        uint32_t tol, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out);
 int self_window_pairs(vdf_ctx* ctx, const uint32_t* d_dur, uint64_t n, uint64_t* pairs_out);
 int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n);
+// search_tc.cu
+int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& exp, DevBuf& pc);
+int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t max_span_tiles, const uint8_t* row_exp, const uint8_t* col_exp,
+              const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
+              uint64_t capacity, unsigned long long* counter);
 // group.cu
 int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, vdf_groups* out);
 // hash.cu

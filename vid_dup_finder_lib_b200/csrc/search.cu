@@ -484,9 +484,11 @@ static int set_ham_attrs(vdf_ctx* ctx) {
 }
 
 // shared tail of both searches: tile ranges, the hot kernel, count read-back, key sort
-static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const uint32_t* row_tiles, const uint32_t* col_tiles,
-                     const uint32_t* row_id, uint64_t col_base, uint32_t tol, uint64_t* d_keys_out, uint64_t capacity,
-                     uint64_t* n_out) {
+static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const void* row_data, const void* col_data,
+                     const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
+                     uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+    const uint32_t* row_tiles = static_cast<const uint32_t*>(row_data);
+    const uint32_t* col_tiles = static_cast<const uint32_t*>(col_data);
     VDF_TRY(set_ham_attrs(ctx));
     VDF_ALLOC(ctx, ctx->tile_range.ensure((size_t)n_row_tiles * sizeof(uint2)));
     VDF_ALLOC(ctx, ctx->misc.ensure(64));
@@ -529,6 +531,10 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const uint32_t* row_til
         p.chunk = chunk;
         grid.y = (max_span + chunk - 1) / chunk;
     }
+    if (ctx->search_variant == 3) {  // tensor-core path: byte-expanded operands, tcgen05.mma kind::i8
+        VDF_TRY(tc_launch(ctx, n_row_tiles, max_span, static_cast<const uint8_t*>(row_data), static_cast<const uint8_t*>(col_data),
+                          row_pc, col_pc, row_id, col_base, tol, capacity, misc + 2));
+    } else {
     kt_begin(ctx, 0);
     if (ctx->search_variant == 2)
         hamming_tiles_csa4_kernel<<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
@@ -538,6 +544,7 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const uint32_t* row_til
         hamming_tiles_kernel<0><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
     kt_end(ctx, 0);
     VDF_LAUNCHED(ctx);
+    }
     unsigned long long cnt = 0;
     VDF_CUDA(ctx, cudaMemcpyAsync(&cnt, misc + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
     VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -562,14 +569,20 @@ int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_d
     VDF_ALLOC(ctx, ctx->row_tiles.ensure((size_t)T * kTileWords * 4));
     VDF_ALLOC(ctx, ctx->row_lo.ensure((size_t)n_pad * 4));
     VDF_ALLOC(ctx, ctx->row_hi.ensure((size_t)n_pad * 4));
-    retile_kernel<<<T, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), nullptr, n,
-                                              ctx->row_tiles.as<uint32_t>());
-    VDF_LAUNCHED(ctx);
+    const bool tc = ctx->search_variant == 3;
+    if (tc) {
+        VDF_TRY(tc_expand(ctx, d_hash, nullptr, n, ctx->exp_rows, ctx->pc_rows));
+    } else {
+        retile_kernel<<<T, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), nullptr, n,
+                                                  ctx->row_tiles.as<uint32_t>());
+        VDF_LAUNCHED(ctx);
+    }
     self_window_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(d_dur, (uint32_t)n, n_pad, ctx->row_lo.as<uint32_t>(),
                                                                      ctx->row_hi.as<uint32_t>());
     VDF_LAUNCHED(ctx);
-    return run_tiles(ctx, T, ctx->row_tiles.as<uint32_t>(), ctx->row_tiles.as<uint32_t>(), nullptr, 0, tol, d_keys_out,
-                     capacity, n_out);
+    const void* data = tc ? ctx->exp_rows.p : ctx->row_tiles.p;
+    return run_tiles(ctx, T, data, data, ctx->pc_rows.as<uint32_t>(), ctx->pc_rows.as<uint32_t>(), nullptr, 0, tol,
+                     d_keys_out, capacity, n_out);
 }
 
 int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_cand_dur, uint64_t n_cand,
@@ -603,12 +616,18 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
     VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32,
                                                   ctx->stream));
     ctx->launches += 3;
-    retile_kernel<<<TC, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cand), nullptr, n_cand,
-                                               ctx->col_tiles.as<uint32_t>());
-    VDF_LAUNCHED(ctx);
-    retile_kernel<<<TR, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_refs), perm, n_ref,
-                                               ctx->row_tiles.as<uint32_t>());
-    VDF_LAUNCHED(ctx);
+    const bool tc = ctx->search_variant == 3;
+    if (tc) {
+        VDF_TRY(tc_expand(ctx, d_cand, nullptr, n_cand, ctx->exp_cols, ctx->pc_cols));
+        VDF_TRY(tc_expand(ctx, d_refs, perm, n_ref, ctx->exp_rows, ctx->pc_rows));
+    } else {
+        retile_kernel<<<TC, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cand), nullptr, n_cand,
+                                                   ctx->col_tiles.as<uint32_t>());
+        VDF_LAUNCHED(ctx);
+        retile_kernel<<<TR, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_refs), perm, n_ref,
+                                                   ctx->row_tiles.as<uint32_t>());
+        VDF_LAUNCHED(ctx);
+    }
     ref_window_kernel<<<(r_pad + 255) / 256, 256, 0, ctx->stream>>>(d_cand_dur, (uint32_t)n_cand, d_ref_dur, perm,
                                                                     (uint32_t)n_ref, r_pad, ctx->row_lo.as<uint32_t>(),
                                                                     ctx->row_hi.as<uint32_t>());
@@ -616,8 +635,9 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
     // in multi-GPU use every rank holds a different candidate slice and evaluates ALL of its tiles
     const uint32_t world = ctx->world, rank = ctx->rank;
     ctx->world = 1, ctx->rank = 0;
-    int rc = run_tiles(ctx, TR, ctx->row_tiles.as<uint32_t>(), ctx->col_tiles.as<uint32_t>(), perm, cand_base, tol,
-                       d_keys_out, capacity, n_out);
+    int rc = run_tiles(ctx, TR, tc ? ctx->exp_rows.p : ctx->row_tiles.p, tc ? ctx->exp_cols.p : ctx->col_tiles.p,
+                       ctx->pc_rows.as<uint32_t>(), ctx->pc_cols.as<uint32_t>(), perm, cand_base, tol, d_keys_out, capacity,
+                       n_out);
     ctx->world = world, ctx->rank = rank;
     return rc;
 }

@@ -1,0 +1,325 @@
+// search_tc.cu -- tensor-core Hamming search, search_variant 3.
+//
+// hamming(a, b) = pc(a) + pc(b) - 2 * <a, b> with the 1024 bits of a hash expanded to 1024 bytes in {0, 1}: the
+// all-pairs comparison becomes an exact u8 x u8 -> s32 contraction with K = 1024 that runs on the 5th-generation
+// tensor cores (tcgen05.mma kind::i8, SASS UTCIMMA), accumulators in tensor memory.  A pair matches iff
+//     2 * dot(i, j) - pc(j) >= pc(i) - tol.
+// Results are bit-identical to the XOR+POPC kernels (integers throughout); this kernel is selected with
+// search_variant = 3 and is validated against the same oracle tests.
+//
+// Layout in HBM (expand_tiles_kernel): exp[tile][kc 0..7][row 0..127][128 B], i.e. per 128-hash tile eight K-chunks of
+// 128 bytes per row, each chunk block (16 KB) stored exactly as the UMMA K-major SWIZZLE_128B canonical layout wants it
+// in shared memory (16-byte unit u of row r lives at unit u ^ (r & 7)), so plain 1-D TMA bulk copies stage operands.
+//
+// CTA = 6 warps, one per SM (192 KB of shared memory): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane,
+// owns the TMEM allocation), warps 2-5 = epilogue (tcgen05.ld, one accumulator row per thread).  The row tile (A, 128
+// hashes x 1024 B = 128 KB) stays resident; column super-tiles (B, 256 hashes) stream through a 2-stage ring of
+// 32 KB K-chunks; each super-tile is 8 chunks x 4 MMAs of 128x256x32; two 256-column TMEM accumulators let the
+// epilogue of super-tile t overlap the MMAs of t+1.
+#include "common.cuh"
+
+namespace vdf {
+
+constexpr int kTcChunkBytes = kTile * 128;        // one K-chunk of one tile: 16 KB
+constexpr int kTcTileBytes = 8 * kTcChunkBytes;   // expanded tile: 128 KB
+constexpr int kTcStages = 2;
+constexpr int kTcStageBytes = 2 * kTcChunkBytes;  // 256 columns x 128 B
+constexpr int kTcThreads = 192;
+constexpr size_t kTcSmem = (size_t)kTcTileBytes + kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(tc_smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(tc_smem_u32(bar))
+                 : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start >> 4 in [0,14), LBO in
+// [16,30) (ignored for swizzled K-major, 1), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B = 2 in [61,64)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = unsigned 8 bit (0), both K-major,
+// N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+constexpr uint32_t kTcIdesc = (2u << 4) | (32u << 17) | (8u << 24);
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kTcIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+#define TC_R8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+// 32 TMEM lanes (one per thread of the warp) x 64 consecutive 32-bit columns
+__device__ __forceinline__ void tc_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,"
+        "%62,%63}, [%64];"
+        : TC_R8(v, 0), TC_R8(v, 8), TC_R8(v, 16), TC_R8(v, 24), TC_R8(v, 32), TC_R8(v, 40), TC_R8(v, 48), TC_R8(v, 56)
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ expansion
+// bits -> {0,1} bytes in the swizzled K-major tile layout, plus per-hash popcounts.  grid = (tiles, 8 K-chunks).
+__global__ void __launch_bounds__(256) expand_tiles_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm,
+                                                           uint64_t n, uint8_t* __restrict__ exp, uint32_t* __restrict__ pc) {
+    const uint64_t tile = blockIdx.x;
+    const uint32_t kc = blockIdx.y;  // bits kc*128 .. kc*128+127 = u32 words kc*4 .. kc*4+3
+    uint8_t* dst = exp + tile * (uint64_t)kTcTileBytes + (uint64_t)kc * kTcChunkBytes;
+    for (uint32_t q = threadIdx.x; q < kTile * 8; q += 256) {
+        const uint32_t row = q >> 3, unit = q & 7;  // 16-byte unit = 16 bits of the hash
+        const uint64_t g = tile * kTile + row;
+        uint32_t bits = 0;
+        if (g < n) {
+            const uint64_t src = perm ? perm[g] : g;
+            bits = (in[src * 32 + kc * 4 + (unit >> 1)] >> ((unit & 1) * 16)) & 0xFFFFu;
+        }
+        uint4 v;  // nibble * 0x00204081 spreads bit i of the nibble to bit 0 of byte i
+        v.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
+        v.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+        v.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+        v.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+        *reinterpret_cast<uint4*>(dst + row * 128 + ((unit ^ (row & 7)) << 4)) = v;
+    }
+    if (kc == 0) {
+        for (uint32_t row = threadIdx.x; row < (uint32_t)kTile; row += 256) {
+            const uint64_t g = tile * kTile + row;
+            uint32_t c = 0;
+            if (g < n) {
+                const uint64_t src = perm ? perm[g] : g;
+                for (int w = 0; w < 32; ++w) c += __popc(in[src * 32 + w]);
+            }
+            pc[g] = c;
+        }
+    }
+}
+
+struct TcParams {
+    const uint8_t* row_exp;
+    const uint8_t* col_exp;
+    const uint32_t* row_pc;
+    const uint32_t* col_pc;
+    const uint32_t* row_lo;
+    const uint32_t* row_hi;
+    const uint32_t* row_id;
+    const uint2* tile_range;  // in 128-hash column tiles
+    uint64_t* keys;
+    unsigned long long* counter;
+    uint64_t capacity;
+    uint64_t col_base;
+    uint32_t chunk;  // column SUPER-tiles (256 hashes) per CTA
+    uint32_t tol;
+    uint32_t rank, world;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned tiles
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = base;
+    uint8_t* sB = base + kTcTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * kTcStageBytes);
+    uint64_t* full = bars;                    // [kTcStages]
+    uint64_t* empty = bars + kTcStages;       // [kTcStages]
+    uint64_t* a_full = bars + 2 * kTcStages;  // [1]
+    uint64_t* acc_full = a_full + 1;          // [2]
+    uint64_t* acc_empty = acc_full + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const uint32_t I = blockIdx.x, c = blockIdx.y;
+    if (p.world > 1 && ((I + c) % p.world) != p.rank) return;
+    const uint2 rng = p.tile_range[I];
+    const uint32_t st_begin = rng.x / 2, st_end = (rng.y + 1) / 2;  // super-tiles covering the 128-tile range
+    const uint32_t st0 = st_begin + c * p.chunk;
+    if (rng.x >= rng.y || st0 >= st_end) return;
+    const uint32_t n_st = min(p.chunk, st_end - st0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) tc_mbar_init(&full[s], 1), tc_mbar_init(&empty[s], 1);
+        tc_mbar_init(a_full, 1);
+        for (int b = 0; b < 2; ++b) tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // the MMA warp owns all 512 TMEM columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer
+            tc_mbar_expect_tx(a_full, kTcTileBytes);
+            for (int kc = 0; kc < 8; ++kc)
+                tc_bulk_g2s(sA + kc * kTcChunkBytes, p.row_exp + (size_t)I * kTcTileBytes + (size_t)kc * kTcChunkBytes,
+                            kTcChunkBytes, a_full);
+            uint32_t it = 0;
+            for (uint32_t s = 0; s < n_st; ++s) {
+                const uint8_t* t0 = p.col_exp + (size_t)(2 * (st0 + s)) * kTcTileBytes;
+                for (int kc = 0; kc < 8; ++kc, ++it) {
+                    const uint32_t stage = it % kTcStages;
+                    tc_mbar_wait(&empty[stage], ((it / kTcStages) & 1) ^ 1);
+                    tc_mbar_expect_tx(&full[stage], kTcStageBytes);
+                    uint8_t* d = sB + stage * kTcStageBytes;
+                    tc_bulk_g2s(d, t0 + (size_t)kc * kTcChunkBytes, kTcChunkBytes, &full[stage]);
+                    tc_bulk_g2s(d + kTcChunkBytes, t0 + kTcTileBytes + (size_t)kc * kTcChunkBytes, kTcChunkBytes, &full[stage]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer
+            tc_mbar_wait(a_full, 0);
+            const uint32_t a_addr = tc_smem_u32(sA), b_addr = tc_smem_u32(sB);
+            uint32_t it = 0;
+            for (uint32_t s = 0; s < n_st; ++s) {
+                const uint32_t buf = s & 1;
+                tc_mbar_wait(&acc_empty[buf], ((s >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kc = 0; kc < 8; ++kc, ++it) {
+                    const uint32_t stage = it % kTcStages;
+                    tc_mbar_wait(&full[stage], (it / kTcStages) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        tc_mma(d_tmem, tc_desc(a_addr + kc * kTcChunkBytes + ks * 32),
+                               tc_desc(b_addr + stage * kTcStageBytes + ks * 32), (kc | ks) != 0);
+                    tc_commit(&empty[stage]);  // the stage is free once these MMAs have read it
+                }
+                tc_commit(&acc_full[buf]);
+            }
+        }
+    } else {  // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31, one accumulator row per thread
+        const uint32_t quarter = warp & 3;
+        const uint32_t row = quarter * 32 + lane;
+        const uint32_t gi = I * kTile + row;
+        const int thr = (int)p.row_pc[gi] - (int)p.tol;
+        for (uint32_t s = 0; s < n_st; ++s) {
+            const uint32_t buf = s & 1;
+            tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
+            tc_fence_after();
+            const uint32_t col_first = (st0 + s) * 256;
+            for (int q = 0; q < 4; ++q) {
+                uint32_t v[64];
+                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the rare emit path
+                tc_ld64(tmem_base + buf * 256 + q * 64 + ((quarter * 32) << 16), v);
+                const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
+                int best = -0x7FFFFFFF;
+#pragma unroll
+                for (int k4 = 0; k4 < 16; ++k4) {
+                    const uint4 pj = __ldg(pcj + k4);
+                    const int t0 = 2 * (int)v[4 * k4 + 0] - (int)pj.x, t1 = 2 * (int)v[4 * k4 + 1] - (int)pj.y;
+                    const int t2 = 2 * (int)v[4 * k4 + 2] - (int)pj.z, t3 = 2 * (int)v[4 * k4 + 3] - (int)pj.w;
+                    v[4 * k4 + 0] = (uint32_t)t0, v[4 * k4 + 1] = (uint32_t)t1;
+                    v[4 * k4 + 2] = (uint32_t)t2, v[4 * k4 + 3] = (uint32_t)t3;
+                    best = max(best, max(max(t0, t1), max(t2, t3)));
+                }
+                if (best >= thr) {  // rare: at least one of these 64 pairs is within the tolerance
+                    uint64_t mask = 0;
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) mask |= (uint64_t)((int)v[k] >= thr) << k;
+                    while (mask) {
+                        const int k = __ffsll((long long)mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t gj = col_first + q * 64 + k;
+                        if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
+                            const unsigned long long slot = atomicAdd(p.counter, 1ull);
+                            if (slot < p.capacity) {
+                                const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
+                                p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& exp, DevBuf& pc) {
+    const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
+    const uint32_t T2 = (T + 1) & ~1u;  // super-tiles read tile pairs: keep an even number of (zero) tiles
+    VDF_ALLOC(ctx, exp.ensure((size_t)T2 * kTcTileBytes));
+    VDF_ALLOC(ctx, pc.ensure((size_t)T2 * kTile * 4));
+    if (T2 > T) {
+        VDF_CUDA(ctx, cudaMemsetAsync(exp.as<uint8_t>() + (size_t)T * kTcTileBytes, 0, kTcTileBytes, ctx->stream));
+        VDF_CUDA(ctx, cudaMemsetAsync(pc.as<uint32_t>() + (size_t)T * kTile, 0, kTile * 4, ctx->stream));
+    }
+    expand_tiles_kernel<<<dim3(T, 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), perm, n,
+                                                            exp.as<uint8_t>(), pc.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    return VDF_OK;
+}
+
+int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t max_span_tiles, const uint8_t* row_exp, const uint8_t* col_exp,
+              const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
+              uint64_t capacity, unsigned long long* counter) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        attr_done = true;
+    }
+    const uint32_t span_st = max_span_tiles / 2 + 2;  // super-tiles a row tile's range can touch
+    uint32_t chunk = 32;
+    while (chunk > 2 && (uint64_t)n_row_tiles * ((span_st + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 4 * ctx->world)
+        chunk >>= 1;
+    TcParams p;
+    p.row_exp = row_exp, p.col_exp = col_exp, p.row_pc = row_pc, p.col_pc = col_pc;
+    p.row_lo = ctx->row_lo.as<uint32_t>(), p.row_hi = ctx->row_hi.as<uint32_t>(), p.row_id = row_id;
+    p.tile_range = ctx->tile_range.as<uint2>();
+    p.keys = ctx->raw_keys.as<uint64_t>(), p.counter = counter, p.capacity = capacity, p.col_base = col_base;
+    p.chunk = chunk, p.tol = tol, p.rank = ctx->rank, p.world = ctx->world;
+    dim3 grid(n_row_tiles, (span_st + chunk - 1) / chunk);
+    kt_begin(ctx, 0);
+    hamming_tc_kernel<<<grid, kTcThreads, kTcSmem, ctx->stream>>>(p);
+    kt_end(ctx, 0);
+    VDF_LAUNCHED(ctx);
+    return VDF_OK;
+}
+
+}  // namespace vdf
