@@ -53,6 +53,16 @@ if [[ $STEP == multi ]]; then
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_g$N.json 2> gpurun_out/bench_g$N.err; echo "bench x$N rc=$?"; tail -c 1500 gpurun_out/bench_g$N.json; tail -3 gpurun_out/bench_g$N.err
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus $N --steps 1 --warmup 0 --n-hashes 100000 > gpurun_out/bench_ref_g$N.json 2>&1; echo "bench ref x$N rc=$?"
 fi
+if [[ $STEP == tc2 ]]; then
+  timeout 300 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "2cta" > gpurun_out/pytest_tc2.log 2>&1; echo "pytest tc2 rc=$?"; tail -25 gpurun_out/pytest_tc2.log
+  for v in 4 3; do
+    timeout 300 python bench.py --steps 3 --warmup 2 --variant $v --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_sv$v.json 2> gpurun_out/bench_sv$v.err; echo "bench search v$v rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_sv$v.json'));print(d['value'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_sv$v.err
+  done
+  for v in 4 3; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:hamming_tc -c 1 -f -o gpurun_out/prof_hamming_v$v \
+      python bench.py --steps 1 --warmup 0 --n-hashes 262144 --variant $v --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming_v$v.log 2>&1; echo "ncu hamming v$v rc=$?"
+  done
+fi
 if [[ $STEP == tc ]]; then
   timeout 600 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "tcgen05" > gpurun_out/pytest_tc.log 2>&1; echo "pytest tc rc=$?"; tail -25 gpurun_out/pytest_tc.log
   for v in 3 2; do

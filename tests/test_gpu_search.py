@@ -110,7 +110,7 @@ def _case(rng, n, n_clusters, max_flip, dur_choices):
 SIZES = [1, 2, 3, 127, 128, 129, 255, 257, 1000, 4097]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["popc", "csa8x8", "csa8x4", "tcgen05"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=["popc", "csa8x8", "csa8x4", "tcgen05", "tcgen05_2cta"])
 @pytest.mark.parametrize("n", SIZES)
 def test_self_search_edges_and_groups_match_oracle(ctx, n, variant):
     rng = np.random.default_rng(1000 + n)
@@ -160,7 +160,7 @@ def test_random_edge_lists_group_like_the_oracle(ctx):
         assert np.array_equal(gp, want_gp) and np.array_equal(mm, want_mm)
 
 
-@pytest.mark.parametrize("variant", [0, 3], ids=["popc", "tcgen05"])
+@pytest.mark.parametrize("variant", [0, 3, 4], ids=["popc", "tcgen05", "tcgen05_2cta"])
 @pytest.mark.parametrize("n_cand,n_ref", [(1, 1), (300, 5), (129, 257), (5000, 700)])
 def test_ref_search_matches_oracle(ctx, n_cand, n_ref, variant):
     ctx.set_option("search_variant", variant)
@@ -215,18 +215,21 @@ def test_edge_buffer_grows_and_caps(ctx):
         ctx.set_option("max_edges", 1 << 28)
 
 
+@pytest.mark.parametrize("variant", [0, 2, 4], ids=["popc", "csa8x4", "tcgen05_2cta"])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_shards_partition_the_pair_matrix(ctx, world):
+def test_shards_partition_the_pair_matrix(ctx, world, variant):
     rng = np.random.default_rng(5)
     H, dur = _case(rng, 3000, 300, 200, [600, 610, 650, 700])
     want = o.self_edges(H, dur, 300)
     parts = []
+    ctx.set_option("search_variant", variant)
     try:
         for r in range(world):
             ctx.set_shard(r, world)
             parts.append(ctx.search_self(H, dur, 300))
     finally:
         ctx.set_shard(0, 1)
+        ctx.set_option("search_variant", 0)
     assert sum(len(p) for p in parts) == len(want)  # disjoint
     allp = np.concatenate(parts)
     allp = allp[np.lexsort((allp[:, 1], allp[:, 0]))]

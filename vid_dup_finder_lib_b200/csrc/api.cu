@@ -94,7 +94,7 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "max_edges" && value > 0) ctx->max_edges = (uint64_t)value;
     else if (k == "initial_edges" && value > 0) ctx->initial_edges = (uint64_t)value;
-    else if (k == "search_variant" && (value >= 0 && value <= 3)) ctx->search_variant = (int)value;
+    else if (k == "search_variant" && (value >= 0 && value <= 4)) ctx->search_variant = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;
     else {
         ctx->err = "unknown option or bad value: " + k;

@@ -168,9 +168,9 @@ int self_window_pairs(vdf_ctx* ctx, const uint32_t* d_dur, uint64_t n, uint64_t*
 int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n);
 // search_tc.cu
 int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& exp, DevBuf& pc);
-int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t max_span_tiles, const uint8_t* row_exp, const uint8_t* col_exp,
-              const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
-              uint64_t capacity, unsigned long long* counter);
+int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t max_span_tiles, const uint8_t* row_exp,
+              const uint8_t* col_exp, const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base,
+              uint32_t tol, uint64_t capacity, unsigned long long* counter);
 // group.cu
 int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, vdf_groups* out);
 // hash.cu

@@ -484,7 +484,7 @@ static int set_ham_attrs(vdf_ctx* ctx) {
 }
 
 // shared tail of both searches: tile ranges, the hot kernel, count read-back, key sort
-static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const void* row_data, const void* col_data,
+static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, const void* row_data, const void* col_data,
                      const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
                      uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
     const uint32_t* row_tiles = static_cast<const uint32_t*>(row_data);
@@ -531,8 +531,8 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, const void* row_data, c
         p.chunk = chunk;
         grid.y = (max_span + chunk - 1) / chunk;
     }
-    if (ctx->search_variant == 3) {  // tensor-core path: byte-expanded operands, tcgen05.mma kind::i8
-        VDF_TRY(tc_launch(ctx, n_row_tiles, max_span, static_cast<const uint8_t*>(row_data), static_cast<const uint8_t*>(col_data),
+    if (ctx->search_variant >= 3) {  // tensor-core path: byte-expanded operands, tcgen05.mma kind::i8
+        VDF_TRY(tc_launch(ctx, n_row_tiles, n_col_tiles, max_span, static_cast<const uint8_t*>(row_data), static_cast<const uint8_t*>(col_data),
                           row_pc, col_pc, row_id, col_base, tol, capacity, misc + 2));
     } else {
     kt_begin(ctx, 0);
@@ -569,7 +569,7 @@ int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_d
     VDF_ALLOC(ctx, ctx->row_tiles.ensure((size_t)T * kTileWords * 4));
     VDF_ALLOC(ctx, ctx->row_lo.ensure((size_t)n_pad * 4));
     VDF_ALLOC(ctx, ctx->row_hi.ensure((size_t)n_pad * 4));
-    const bool tc = ctx->search_variant == 3;
+    const bool tc = ctx->search_variant >= 3;
     if (tc) {
         VDF_TRY(tc_expand(ctx, d_hash, nullptr, n, ctx->exp_rows, ctx->pc_rows));
     } else {
@@ -581,7 +581,7 @@ int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_d
                                                                      ctx->row_hi.as<uint32_t>());
     VDF_LAUNCHED(ctx);
     const void* data = tc ? ctx->exp_rows.p : ctx->row_tiles.p;
-    return run_tiles(ctx, T, data, data, ctx->pc_rows.as<uint32_t>(), ctx->pc_rows.as<uint32_t>(), nullptr, 0, tol,
+    return run_tiles(ctx, T, T, data, data, ctx->pc_rows.as<uint32_t>(), ctx->pc_rows.as<uint32_t>(), nullptr, 0, tol,
                      d_keys_out, capacity, n_out);
 }
 
@@ -616,7 +616,7 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
     VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32,
                                                   ctx->stream));
     ctx->launches += 3;
-    const bool tc = ctx->search_variant == 3;
+    const bool tc = ctx->search_variant >= 3;
     if (tc) {
         VDF_TRY(tc_expand(ctx, d_cand, nullptr, n_cand, ctx->exp_cols, ctx->pc_cols));
         VDF_TRY(tc_expand(ctx, d_refs, perm, n_ref, ctx->exp_rows, ctx->pc_rows));
@@ -635,7 +635,7 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
     // in multi-GPU use every rank holds a different candidate slice and evaluates ALL of its tiles
     const uint32_t world = ctx->world, rank = ctx->rank;
     ctx->world = 1, ctx->rank = 0;
-    int rc = run_tiles(ctx, TR, tc ? ctx->exp_rows.p : ctx->row_tiles.p, tc ? ctx->exp_cols.p : ctx->col_tiles.p,
+    int rc = run_tiles(ctx, TR, TC, tc ? ctx->exp_rows.p : ctx->row_tiles.p, tc ? ctx->exp_cols.p : ctx->col_tiles.p,
                        ctx->pc_rows.as<uint32_t>(), ctx->pc_cols.as<uint32_t>(), perm, cand_base, tol, d_keys_out, capacity,
                        n_out);
     ctx->world = world, ctx->rank = rank;

@@ -280,6 +280,213 @@ __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const TcParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair kernel
+// search_variant 4: the same contraction on a CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256).  The pair
+// owns a row super-tile of 256 hashes (each CTA keeps its own 128 rows resident) and each CTA stages only ITS half of
+// every column super-tile (128 hashes x 128 B per K-chunk), so the L2 -> SM operand traffic and the shared-memory
+// operand reads per pair of hashes are half of variant 3's, and the freed shared memory makes the ring 4 deep.
+//   * full[stage] of the leader CTA counts two arrivals: its own producer's expect_tx and a relayed arrive from the
+//     peer (an otherwise idle lane of the peer waits for its local bulk copies, then arrives on the leader's barrier
+//     through a mapa'd shared::cluster address);
+//   * the leader's tcgen05.commit multicasts to empty[stage] / acc_full[buf] of BOTH CTAs;
+//   * acc_empty[buf] lives in the leader and counts the 8 epilogue warps of the pair.
+// Column chunks are absolute (chunk c = super-tiles [c*chunk, (c+1)*chunk)), so that the pairs resident at the same
+// time stream the same column tiles through L2.
+constexpr int kTc2Stages = 4;
+constexpr int kTc2StageBytes = kTcChunkBytes;  // this CTA's 128 columns x 128 B
+constexpr size_t kTc2Smem = (size_t)kTcTileBytes + kTc2Stages * kTc2StageBytes + 1024 /*align*/ + 256 /*barriers*/;
+// instruction descriptor as kTcIdesc with M = 256 (>> 4 at bit 24)
+constexpr uint32_t kTc2Idesc = (2u << 4) | (32u << 17) | (16u << 24);
+
+__device__ __forceinline__ uint32_t tc_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  CTA-scope semantics on purpose:
+// everything these barriers order is async-proxy traffic (bulk copies -> shared memory -> UMMA, tensor memory), and a
+// cluster-scope acquire makes ptxas invalidate the whole L1 (CCTL.IVALL) after every wait -- 41 % of all stall samples in
+// the first capture of this kernel (profiles/r01_hamming_tc2_ncu.txt)
+__device__ __forceinline__ void tc_mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(tc_smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kTc2Idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at this offset in both CTAs
+__device__ __forceinline__ void tc2_commit(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            tc_smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) hamming_tc2_kernel(const TcParams p, uint32_t n_row_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = base;
+    uint8_t* sB = base + kTcTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTc2Stages * kTc2StageBytes);
+    uint64_t* full = bars;                     // [kTc2Stages]
+    uint64_t* empty = bars + kTc2Stages;       // [kTc2Stages]
+    uint64_t* a_full = bars + 2 * kTc2Stages;  // [1]
+    uint64_t* acc_full = a_full + 1;           // [2]
+    uint64_t* acc_empty = acc_full + 2;        // [2]  (leader's copy is the live one)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const uint32_t cr = tc_cluster_rank();  // 0 = leader (issues the MMAs), 1 = peer
+    const uint32_t P = blockIdx.x >> 1, c = blockIdx.y;
+    if (p.world > 1 && ((P + c) % p.world) != p.rank) return;
+    // column super-tiles this pair needs: the union of its two row tiles' ranges
+    const uint2 r0 = p.tile_range[2 * P];
+    const uint2 r1 = (2 * P + 1 < n_row_tiles) ? p.tile_range[2 * P + 1] : make_uint2(0, 0);
+    uint32_t t_lo = 0xFFFFFFFFu, t_hi = 0;
+    if (r0.x < r0.y) t_lo = r0.x, t_hi = r0.y;
+    if (r1.x < r1.y) t_lo = min(t_lo, r1.x), t_hi = max(t_hi, r1.y);
+    if (t_lo >= t_hi) return;
+    const uint32_t st0 = max(t_lo / 2, c * p.chunk), st1 = min((t_hi + 1) / 2, (c + 1) * p.chunk);
+    if (st0 >= st1) return;  // the same decision in both CTAs of the pair
+    const uint32_t n_st = st1 - st0;
+    const uint32_t I = 2 * P + cr;  // this CTA's row tile
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        const uint32_t producers = cr == 0 ? 2 : 1;  // leader: own expect_tx + the peer's relayed arrive
+        for (int s = 0; s < kTc2Stages; ++s) tc_mbar_init(&full[s], producers), tc_mbar_init(&empty[s], 1);
+        tc_mbar_init(a_full, producers);
+        for (int b = 0; b < 2; ++b) tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // the same warp of both CTAs allocates the pair's tensor memory (512 columns each)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_cluster_sync();  // barriers of both CTAs are initialised before anyone arrives remotely
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer: this CTA's 128 rows, then its half of every column super-tile
+            tc_mbar_expect_tx(a_full, kTcTileBytes);
+            for (int kc = 0; kc < 8; ++kc)
+                tc_bulk_g2s(sA + kc * kTcChunkBytes, p.row_exp + (size_t)I * kTcTileBytes + (size_t)kc * kTcChunkBytes,
+                            kTcChunkBytes, a_full);
+            uint32_t it = 0;
+            for (uint32_t s = 0; s < n_st; ++s) {
+                const uint8_t* t0 = p.col_exp + (size_t)(2 * (st0 + s) + cr) * kTcTileBytes;
+                for (int kc = 0; kc < 8; ++kc, ++it) {
+                    const uint32_t stage = it % kTc2Stages;
+                    tc_mbar_wait(&empty[stage], ((it / kTc2Stages) & 1) ^ 1);
+                    tc_mbar_expect_tx(&full[stage], kTc2StageBytes);
+                    tc_bulk_g2s(sB + stage * kTc2StageBytes, t0 + (size_t)kc * kTcChunkBytes, kTcChunkBytes, &full[stage]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && cr == 0) {  // ===== MMA issuer (leader CTA only)
+            tc_mbar_wait(a_full, 0);
+            const uint32_t a_addr = tc_smem_u32(sA), b_addr = tc_smem_u32(sB);
+            uint32_t it = 0;
+            for (uint32_t s = 0; s < n_st; ++s) {
+                const uint32_t buf = s & 1;
+                tc_mbar_wait(&acc_empty[buf], ((s >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kc = 0; kc < 8; ++kc, ++it) {
+                    const uint32_t stage = it % kTc2Stages;
+                    tc_mbar_wait(&full[stage], (it / kTc2Stages) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        tc2_mma(d_tmem, tc_desc(a_addr + kc * kTcChunkBytes + ks * 32),
+                                tc_desc(b_addr + stage * kTc2StageBytes + ks * 32), (kc | ks) != 0);
+                    tc2_commit(&empty[stage]);  // frees the stage in both CTAs
+                }
+                tc2_commit(&acc_full[buf]);
+            }
+        } else if (lane == 0) {  // ===== peer CTA: relay "my half has landed" to the leader's barriers
+            tc_mbar_wait(a_full, 0);
+            tc_mbar_arrive_remote(a_full, 0);
+            const uint32_t total = n_st * 8;
+            for (uint32_t it = 0; it < total; ++it) {
+                const uint32_t stage = it % kTc2Stages;
+                tc_mbar_wait(&full[stage], (it / kTc2Stages) & 1);
+                tc_mbar_arrive_remote(&full[stage], 0);
+            }
+        }
+    } else {  // ===== epilogue (both CTAs): warp w reads TMEM lanes 32*(w%4) .. +31 of its own CTA
+        const uint32_t quarter = warp & 3;
+        const uint32_t row = quarter * 32 + lane;
+        const uint32_t gi = I * kTile + row;
+        const bool live = I < n_row_tiles;
+        const int thr = live ? (int)p.row_pc[gi] - (int)p.tol : 0x7FFFFFFF;
+        for (uint32_t s = 0; s < n_st; ++s) {
+            const uint32_t buf = s & 1;
+            tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
+            tc_fence_after();
+            const uint32_t col_first = (st0 + s) * 256;
+            for (int q = 0; q < 4; ++q) {
+                uint32_t v[64];
+                __syncwarp();
+                tc_ld64(tmem_base + buf * 256 + q * 64 + ((quarter * 32) << 16), v);
+                const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
+                int best = -0x7FFFFFFF;
+#pragma unroll
+                for (int k4 = 0; k4 < 16; ++k4) {
+                    const uint4 pj = __ldg(pcj + k4);
+                    const int t0 = 2 * (int)v[4 * k4 + 0] - (int)pj.x, t1 = 2 * (int)v[4 * k4 + 1] - (int)pj.y;
+                    const int t2 = 2 * (int)v[4 * k4 + 2] - (int)pj.z, t3 = 2 * (int)v[4 * k4 + 3] - (int)pj.w;
+                    v[4 * k4 + 0] = (uint32_t)t0, v[4 * k4 + 1] = (uint32_t)t1;
+                    v[4 * k4 + 2] = (uint32_t)t2, v[4 * k4 + 3] = (uint32_t)t3;
+                    best = max(best, max(max(t0, t1), max(t2, t3)));
+                }
+                if (best >= thr) {  // rare
+                    uint64_t mask = 0;
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) mask |= (uint64_t)((int)v[k] >= thr) << k;
+                    while (mask) {
+                        const int k = __ffsll((long long)mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t gj = col_first + q * 64 + k;
+                        if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
+                            const unsigned long long slot = atomicAdd(p.counter, 1ull);
+                            if (slot < p.capacity) {
+                                const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
+                                p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive_remote(&acc_empty[buf], 0);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    tc_cluster_sync();  // neither CTA may exit (or free tensor memory) while its partner can still touch it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& exp, DevBuf& pc) {
     const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
@@ -296,24 +503,39 @@ int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64
     return VDF_OK;
 }
 
-int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t max_span_tiles, const uint8_t* row_exp, const uint8_t* col_exp,
-              const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
-              uint64_t capacity, unsigned long long* counter) {
+int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t max_span_tiles, const uint8_t* row_exp,
+              const uint8_t* col_exp, const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base,
+              uint32_t tol, uint64_t capacity, unsigned long long* counter) {
     static bool attr_done = false;
     if (!attr_done) {
         VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc2Smem));
         attr_done = true;
     }
-    const uint32_t span_st = max_span_tiles / 2 + 2;  // super-tiles a row tile's range can touch
-    uint32_t chunk = 32;
-    while (chunk > 2 && (uint64_t)n_row_tiles * ((span_st + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 4 * ctx->world)
-        chunk >>= 1;
     TcParams p;
     p.row_exp = row_exp, p.col_exp = col_exp, p.row_pc = row_pc, p.col_pc = col_pc;
     p.row_lo = ctx->row_lo.as<uint32_t>(), p.row_hi = ctx->row_hi.as<uint32_t>(), p.row_id = row_id;
     p.tile_range = ctx->tile_range.as<uint2>();
     p.keys = ctx->raw_keys.as<uint64_t>(), p.counter = counter, p.capacity = capacity, p.col_base = col_base;
-    p.chunk = chunk, p.tol = tol, p.rank = ctx->rank, p.world = ctx->world;
+    p.tol = tol, p.rank = ctx->rank, p.world = ctx->world;
+    if (ctx->search_variant == 4) {  // CTA pairs: 256-row super-tiles x absolute chunks of column super-tiles
+        const uint32_t n_pairs = (n_row_tiles + 1) / 2, n_st = (n_col_tiles + 1) / 2;
+        uint32_t chunk = 32;
+        while (chunk > 2 && (uint64_t)n_pairs * ((n_st + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 4 * ctx->world) chunk >>= 1;
+        while ((n_st + chunk - 1) / chunk > 65535) chunk *= 2;
+        p.chunk = chunk;
+        dim3 grid(2 * n_pairs, (n_st + chunk - 1) / chunk);
+        kt_begin(ctx, 0);
+        hamming_tc2_kernel<<<grid, kTcThreads, kTc2Smem, ctx->stream>>>(p, n_row_tiles);
+        kt_end(ctx, 0);
+        VDF_LAUNCHED(ctx);
+        return VDF_OK;
+    }
+    const uint32_t span_st = max_span_tiles / 2 + 2;  // super-tiles a row tile's range can touch
+    uint32_t chunk = 32;
+    while (chunk > 2 && (uint64_t)n_row_tiles * ((span_st + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 4 * ctx->world)
+        chunk >>= 1;
+    p.chunk = chunk;
     dim3 grid(n_row_tiles, (span_st + chunk - 1) / chunk);
     kt_begin(ctx, 0);
     hamming_tc_kernel<<<grid, kTcThreads, kTcSmem, ctx->stream>>>(p);
