@@ -52,32 +52,68 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML from a
+    thread of this process (nvidia_ml_py): a looping `nvidia-smi` child stalls kernel launches for milliseconds at a
+    time, which shows up as idle gaps in a device-timed step; nvidia-smi remains the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index: int, period_s: float = 0.1):
+        self.index, self.period, self.proc, self.lines = index, period_s, None, []
+        self.sm, self.mx, self.reasons, self.stop, self.t, self.how = [], [], set(), threading.Event(), None, None
+
+    def _nvml_loop(self, nv, h):
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(mx)
+                r = int(reasons_fn(h))
+                self.reasons.update(k for k, bit in names.items() if r & bit)
+            except Exception:
+                pass
+            self.stop.wait(self.period)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.t.start()
+            self.how = "nvml"
+            return self
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
         return self
 
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             time.sleep(0.25)
             self.proc.terminate()
+        if self.t:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons = list(self.sm), list(self.mx), set(self.reasons)
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
@@ -90,8 +126,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": self.how}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "how": self.how}
 
 
 def measured_peaks():
@@ -100,6 +137,49 @@ def measured_peaks():
         d = json.load(open(p))
         return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured (MEASURED_PEAKS.json)"
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+DEFAULT_SEARCH_VARIANT = 5   # vdf_ctx::search_variant in csrc/common.cuh
+PAIR_MACS = 1024             # tensor-core variants: hamming = pc(a) + pc(b) - 2 <a, b>, one u8 MAC per stored bit
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from `ncu --set full` captures
+
+
+def ncu_traffic(kernel: str, key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` at workload `key`, recorded from an
+    `ncu --set full` capture (scripts/summarize_profiles.py writes profiles/traffic.json); None if not captured."""
+    try:
+        return json.load(open(TRAFFIC_FILE))[kernel][key]
+    except Exception:
+        return None
+
+
+def search_roofline(variant: int, pairs_per_launch: float, k_ms: float, k_n: int, sm_count: int, sm_max_mhz: float, n_key=None):
+    ms = k_ms / max(k_n, 1)
+    if variant >= 3:
+        # tensor-bound: 2 x 1024 8-bit integer ops per pair on tcgen05.mma kind::i8
+        p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        bf16 = json.load(open(p)).get("bf16_tflops") if os.path.exists(p) else None
+        peak, src = (2.0 * bf16, "2 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json, burst): 8-bit operands run at twice "
+                     "the bf16 rate") if bf16 else (4500.0, "fallback: nominal dense 8-bit peak (B200_PROFILING.md)")
+        pipe = sm_count * 8192 * 2 * sm_max_mhz * 1e6 / 1e12  # 8192 u8 MAC/clk/SM (128x256x32 per 128 clk)
+        achieved = 2.0 * PAIR_MACS * pairs_per_launch / (ms * 1e-3) / 1e12 if k_n else None
+        kname = {3: "hamming_tc_kernel", 4: "hamming_tc2_kernel", 5: "hamming_tc5_kernel"}[variant]
+        return {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(kname, n_key) if n_key else None,
+                "peak_source": src, "pipe_peak": pipe, "pipe_frac": (achieved / pipe) if achieved else None,
+                "pipe_peak_source": "148 SMs x 8192 u8 MAC/clk/SM x 2 x max SM clock (tcgen05 issue floor, B300_MICROARCH.md)",
+                "kernel_ms_per_launch": ms, "kernel_launches_timed": k_n, "algorithmic_ops_per_pair": 2 * PAIR_MACS,
+                "popc_equivalent": {"algorithmic_popc32_per_pair": PAIR_POPC32,
+                                    "frac_of_popc_peak": PAIR_POPC32 * pairs_per_launch / (ms * 1e-3) / 1e9 /
+                                    popc_peak_gpopc(sm_count, sm_max_mhz)[0] if k_n else None}}
+    popc_peak, popc_src = popc_peak_gpopc(sm_count, sm_max_mhz)
+    achieved = PAIR_POPC32 * pairs_per_launch / (ms * 1e-3) / 1e9 if k_n else None
+    kname = "hamming_tiles_csa4_kernel" if variant == 2 else "hamming_tiles_kernel"
+    return {"bound": "int_popc", "kernel": kname, "achieved": achieved, "peak": popc_peak,
+            "unit": "GPOPC32/s", "frac": (achieved / popc_peak) if achieved else None,
+            "traffic": ncu_traffic(kname, n_key) if n_key else None,
+            "peak_source": popc_src, "kernel_ms_per_launch": ms, "kernel_launches_timed": k_n,
+            "algorithmic_popc32_per_pair": PAIR_POPC32}
 
 
 def popc_peak_gpopc(sm_count: int, sm_max_mhz: float):
@@ -287,14 +367,9 @@ def main():
         launches = ctx.counters()[0] - l0
         k_ms, k_n = ctx.kernel_time(0, reset=True)
         value = pairs * steps / secs
-        # roofline of the dominant kernel (hamming_tiles_kernel): this rank's share of the pairs per launch
-        popc_peak, popc_src = popc_peak_gpopc(sm_count, sm_max_mhz)
-        pairs_per_launch = pairs / world
-        achieved = PAIR_POPC32 * pairs_per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
-        roof = {"bound": "int_popc", "kernel": "hamming_tiles_kernel", "achieved": achieved, "peak": popc_peak,
-                "unit": "GPOPC32/s", "frac": (achieved / popc_peak) if achieved else None, "traffic": None,
-                "peak_source": popc_src, "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_launches_timed": k_n,
-                "algorithmic_popc32_per_pair": PAIR_POPC32}
+        # roofline of the dominant kernel: this rank's share of the pairs per launch
+        variant = args.variant if args.variant >= 0 else DEFAULT_SEARCH_VARIANT
+        roof = search_roofline(variant, pairs / world, k_ms, k_n, sm_count, sm_max_mhz, n_key=f"self_{n}_x{world}")
         # e2e: host arrays -> public API (sort, H2D, kernels, D2H, MatchGroups)
         e_steps = max(1, min(args.e2e_steps, steps))
         c0 = ctx.counters()
@@ -305,17 +380,24 @@ def main():
         barrier()
         e_secs = max_over_ranks(time.perf_counter() - t0)
         c1 = ctx.counters()
-        e2e = {"value": pairs * e_steps / e_secs, "unit": "pairs/s", "h2d_bytes_per_step": int(H.nbytes + dur.nbytes),
+        e2e = {"value": pairs * e_steps / e_secs, "unit": "pairs/s", "h2d_bytes_per_step": int((c1[1] - c0[1]) // e_steps),
                "d2h_bytes_per_step": int((c1[2] - c0[2]) // e_steps), "steps": e_steps, "groups": len(groups),
+               "ms_per_call": e_secs / e_steps * 1e3,
                "api": "vid_dup_finder_lib_b200.dist.search(HashTable, tolerance) -> [MatchGroup]"}
+        if world == 1:
+            ph = ctx.last_phases()
+            e2e["phases_ms_last_call"] = {"host_sort": ph[0], "gather_and_h2d_enqueue": ph[1], "device_incl_d2h": ph[2],
+                                          "index_remap": ph[3], "note": "inside vdf_search (csrc/host.cu); the rest of the "
+                                          "call is building the MatchGroup objects"}
         out = {"metric": "hamming_pair_comparisons_per_s", "value": value, "unit": "pairs/s", "ms_per_step": secs / steps * 1e3,
-               "scaling": "strong", "dtype": "u32", "roofline": roof, "e2e": e2e, "gpu_launches": int(launches),
+               "scaling": "strong", "dtype": "u8 x u8 -> s32" if variant >= 3 else "u32", "roofline": roof, "e2e": e2e,
+               "gpu_launches": int(launches),
                "clocks": cs.summary(),
                "config": {"workload": f"all-pairs search (find_all_matches), {n} synthetic hashes, equal durations, "
                                       f"tolerance {args.tol}", "n_hashes": n, "tol_int": tol_int, "pairs_per_step": pairs,
                           "edges": result.get("edges"), "groups": result.get("groups"), "parallelism": f"tile-block shard x{world}",
                           "l2": "512 MiB write between timed steps (hash table 128 MB ~ L2 126 MB)",
-                          "search_variant": args.variant}}
+                          "search_variant": variant}}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from oracle import vdf_oracle as o
 
@@ -364,13 +446,10 @@ def main():
         launches = ctx.counters()[0] - l0
         k_ms, k_n = ctx.kernel_time(0, reset=True)
         pairs = nq * nc
-        popc_peak, popc_src = popc_peak_gpopc(sm_count, sm_max_mhz)
-        achieved = PAIR_POPC32 * (pairs / world) / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+        variant = args.variant if args.variant >= 0 else DEFAULT_SEARCH_VARIANT
         return {"metric": "hamming_pair_comparisons_per_s", "value": pairs * steps / secs, "unit": "pairs/s",
-                "ms_per_step": secs / steps * 1e3, "scaling": "strong", "dtype": "u32",
-                "roofline": {"bound": "int_popc", "kernel": "hamming_tiles kernel", "achieved": achieved, "peak": popc_peak,
-                             "unit": "GPOPC32/s", "frac": (achieved / popc_peak) if achieved else None, "traffic": None,
-                             "peak_source": popc_src, "kernel_ms_per_launch": k_ms / max(k_n, 1)},
+                "ms_per_step": secs / steps * 1e3, "scaling": "strong", "dtype": "u8 x u8 -> s32" if variant >= 3 else "u32",
+                "roofline": search_roofline(variant, pairs / world, k_ms, k_n, sm_count, sm_max_mhz),
                 "gpu_launches": int(launches), "clocks": cs.summary(),
                 "config": {"workload": f"search_with_references, {nq} queries x {nc} sorted table entries, equal durations, "
                                        f"tolerance {args.tol}", "matches": result.get("matches"),

@@ -218,24 +218,35 @@ class MatchGroup {
 
 // ---- search (video_dup_finder.rs) -----------------------------------------------------------------------------
 namespace detail {
-// Search::sort, search_algorithm.rs:55-61: stable, key (duration, src_path)
-inline std::vector<uint32_t> sort_order(const std::vector<VideoHash>& v) {
-    std::vector<uint32_t> order(v.size());
-    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        if (v[a].duration() != v[b].duration()) return v[a].duration() < v[b].duration();
-        return path_cmp(v[a].src_path(), v[b].src_path()) < 0;
-    });
-    return order;
-}
-inline void gather(const std::vector<VideoHash>& v, const std::vector<uint32_t>& order, std::vector<uint64_t>& words,
-                   std::vector<uint32_t>& dur) {
-    words.resize(order.size() * HASH_WORDS);
-    dur.resize(order.size());
-    for (size_t k = 0; k < order.size(); ++k) {
-        std::memcpy(&words[k * HASH_WORDS], v[order[k]].words().data(), HASH_WORDS * 8);
-        dur[k] = v[order[k]].duration();
+// Vec<VideoHash> -> the struct-of-arrays the C ABI takes (caller's order; paths as one blob + n+1 offsets)
+struct Soa {
+    std::vector<uint64_t> words;
+    std::vector<uint32_t> dur;
+    std::vector<char> blob;
+    std::vector<uint64_t> off;
+    explicit Soa(const std::vector<VideoHash>& v, bool with_paths = true) {
+        words.resize(v.size() * HASH_WORDS);
+        dur.resize(v.size());
+        off.assign(v.size() + 1, 0);
+        size_t total = 0;
+        for (size_t k = 0; k < v.size(); ++k) {
+            std::memcpy(&words[k * HASH_WORDS], v[k].words().data(), HASH_WORDS * 8);
+            dur[k] = v[k].duration();
+            if (with_paths) total += v[k].src_path().size();
+            off[k + 1] = total;
+        }
+        blob.resize(total + 1);
+        if (with_paths)
+            for (size_t k = 0; k < v.size(); ++k) std::memcpy(blob.data() + off[k], v[k].src_path().data(), v[k].src_path().size());
     }
+};
+// Search::sort, search_algorithm.rs:55-61 (stable, key (duration, src_path)) as the library computes it
+inline std::vector<uint64_t> sort_order(const std::vector<VideoHash>& v) {
+    Soa soa(v);
+    std::vector<uint64_t> order(v.size());
+    if (vdf_sort_order(soa.dur.data(), soa.blob.data(), soa.off.data(), v.size(), order.data()) != VDF_OK)
+        throw DeviceError(VDF_ERR_INVALID, "vdf_sort_order");
+    return order;
 }
 }  // namespace detail
 
@@ -243,15 +254,13 @@ inline void gather(const std::vector<VideoHash>& v, const std::vector<uint32_t>&
 inline std::vector<MatchGroup> search(const std::vector<VideoHash>& hashes, double tolerance, Context& ctx) {
     std::vector<MatchGroup> out;
     if (hashes.empty()) return out;  // search_algorithm.rs:88-90
-    const auto order = detail::sort_order(hashes);
-    std::vector<uint64_t> words;
-    std::vector<uint32_t> dur;
-    detail::gather(hashes, order, words, dur);
+    detail::Soa soa(hashes);         // the caller's order: the library sorts (vdf_search, csrc/host.cu)
     vdf_groups g{};
-    ctx.check(vdf_search_self_groups(ctx.get(), words.data(), dur.data(), hashes.size(), tolerance_to_int(tolerance), &g));
+    ctx.check(vdf_search(ctx.get(), soa.words.data(), soa.dur.data(), soa.blob.data(), soa.off.data(), hashes.size(), tolerance, &g));
+    out.reserve(g.n_groups);
     for (uint64_t k = 0; k < g.n_groups; ++k) {
         std::vector<std::string> paths;
-        for (uint64_t m = g.group_ptr[k]; m < g.group_ptr[k + 1]; ++m) paths.push_back(hashes[order[g.member_idx[m]]].src_path());
+        for (uint64_t m = g.group_ptr[k]; m < g.group_ptr[k + 1]; ++m) paths.push_back(hashes[g.member_idx[m]].src_path());
         auto mg = MatchGroup::create(std::move(paths));  // .filter_map(|x| MatchGroup::new(x).ok())
         if (auto* ok = std::get_if<MatchGroup>(&mg)) out.push_back(std::move(*ok));
     }
@@ -264,20 +273,14 @@ inline std::vector<MatchGroup> search_with_references(const std::vector<VideoHas
                                                       const std::vector<VideoHash>& new_hashes, double tolerance, Context& ctx) {
     std::vector<MatchGroup> out;
     if (ref_hashes.empty() || new_hashes.empty()) return out;
-    const auto order = detail::sort_order(new_hashes);
-    std::vector<uint64_t> cw, rw;
-    std::vector<uint32_t> cd, rd;
-    detail::gather(new_hashes, order, cw, cd);
-    std::vector<uint32_t> ident(ref_hashes.size());
-    for (uint32_t i = 0; i < ident.size(); ++i) ident[i] = i;
-    detail::gather(ref_hashes, ident, rw, rd);  // references keep the caller's order
+    detail::Soa refs(ref_hashes, false), cands(new_hashes);  // references keep the caller's order and need no paths
     vdf_csr c{};
-    ctx.check(vdf_search_refs(ctx.get(), cw.data(), cd.data(), new_hashes.size(), rw.data(), rd.data(), ref_hashes.size(),
-                              tolerance_to_int(tolerance), &c));
+    ctx.check(vdf_search_with_references(ctx.get(), refs.words.data(), refs.dur.data(), ref_hashes.size(), cands.words.data(),
+                                         cands.dur.data(), cands.blob.data(), cands.off.data(), new_hashes.size(), tolerance, &c));
     for (uint64_t r = 0; r < c.n_rows; ++r) {
         if (c.row_ptr[r + 1] == c.row_ptr[r]) continue;  // video_dup_finder.rs:38-43
         std::vector<std::string> paths;
-        for (uint64_t m = c.row_ptr[r]; m < c.row_ptr[r + 1]; ++m) paths.push_back(new_hashes[order[c.col_idx[m]]].src_path());
+        for (uint64_t m = c.row_ptr[r]; m < c.row_ptr[r + 1]; ++m) paths.push_back(new_hashes[c.col_idx[m]].src_path());
         auto mg = MatchGroup::create_with_reference(ref_hashes[r].src_path(), std::move(paths));
         if (auto* ok = std::get_if<MatchGroup>(&mg)) out.push_back(std::move(*ok));
     }

@@ -110,7 +110,10 @@ const char* vdf_last_error(const vdf_ctx* ctx);
 int vdf_ctx_set_shard(vdf_ctx* ctx, uint32_t rank, uint32_t world);
 
 /* Tuning knobs: "max_edges" (edge-buffer growth cap, default 2^28), "initial_edges" (default 2^22),
- * "search_variant" (0 = XOR+POPC, 1 = XOR + carry-save adder + POPC). */
+ * "search_variant": 0 = XOR+POPC; 1, 2 = XOR + carry-save adders + POPC (8x8 / 8x4 pairs per thread);
+ *   3 = tcgen05.mma kind::i8 on byte-expanded tiles; 4 = the same on CTA pairs (cta_group::2);
+ *   5 (default) = CTA pairs on packed tiles, bits expanded to bytes inside the kernel.  All six are bit-identical.
+ * "tc_chunk": column super-tiles per work unit of variants 4/5 (0 = automatic); "hash_variant": resize kernel choice. */
 int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value);
 
 /* The cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the caller). */
@@ -166,6 +169,35 @@ int vdf_group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sor
 /* Number of (i,j) pairs inside the duration windows, i.e. how many hamming_distance calls the reference's
  * search_self would make with nothing consumed (throughput accounting). */
 int vdf_self_window_pairs(vdf_ctx* ctx, const uint32_t* dur_sorted, uint64_t n, uint64_t* pairs_out);
+
+/* ---- the crate's two public search functions, whole ------------------------------------------------------------
+ * Inputs in the CALLER's order, struct-of-arrays: hashes [n][16] u64, durations [n] u32, and the src_paths as one
+ * byte blob with n+1 offsets (path i = path_blob[path_off[i] .. path_off[i+1]), no terminators).  The library does
+ * what video_dup_finder.rs does around the comparison loops: the stable (duration, src_path) sort of Search::sort
+ * (search_algorithm.rs:55-61; Rust Unix `Path` ordering = component-wise), tol_int = (tolerance * 1000.0) as u32
+ * (search_algorithm.rs:82), the GPU search, and the mapping back, so every index that comes out refers to the
+ * caller's arrays.  The sort and the staging copies are multi-threaded host code (csrc/host.cu). */
+
+/* Replaces Search::sort (search_algorithm.rs:55-61): order_out[k] = index of the k-th entry in sorted order. */
+int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint64_t* path_off, uint64_t n,
+                   uint64_t* order_out);
+
+/* Replaces `search(hashes, tolerance)` (video_dup_finder.rs:7-13): groups exactly as the reference returns them
+ * (matches in sorted order, the target last, groups by descending target; every group has >= 2 entries), with
+ * member_idx holding the caller's indices.  The caller builds MatchGroup::new(paths of members). */
+int vdf_search(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, const char* path_blob,
+               const uint64_t* path_off, uint64_t n, double tolerance, vdf_groups* out);
+
+/* Replaces `search_with_references(ref_hashes, new_hashes, tolerance)` (video_dup_finder.rs:19-46): row r = the
+ * entries of new_hashes (caller's indices, in sorted order) matching reference r inside its duration slice; empty
+ * rows are the references the caller skips (video_dup_finder.rs:38-43). */
+int vdf_search_with_references(vdf_ctx* ctx, const uint64_t* ref_hashes, const uint32_t* ref_durations, uint64_t n_ref,
+                               const uint64_t* new_hashes, const uint32_t* new_durations, const char* new_path_blob,
+                               const uint64_t* new_path_off, uint64_t n_new, double tolerance, vdf_csr* out);
+
+/* Wall-clock milliseconds of the phases of the last vdf_search / vdf_search_with_references call:
+ * [0] host sort, [1] gather into pinned memory + H2D enqueue, [2] device work incl. result D2H, [3] index remap. */
+int vdf_ctx_last_phases(const vdf_ctx* ctx, double* ms4);
 
 void vdf_free_edges(vdf_edges* e);
 void vdf_free_groups(vdf_groups* g);

@@ -17,7 +17,7 @@ if [[ $STEP == all || $STEP == smoke ]]; then
 fi
 if [[ $STEP == all || $STEP == bench ]]; then
   timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-  timeout 600 python bench.py --steps 3 --warmup 3 --variant 1 --no-secondary --no-cpu-baseline > gpurun_out/bench_v1.json 2> gpurun_out/bench_v1.err; echo "bench v1 rc=$?"; tail -c 1500 gpurun_out/bench_v1.json
+  timeout 600 python bench.py --steps 2 --warmup 1 --variant 0 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_v0.json 2> gpurun_out/bench_v0.err; echo "bench v0 rc=$?"; tail -c 1500 gpurun_out/bench_v0.json
 fi
 if [[ $STEP == hash ]]; then
   for v in 0 3 2; do
@@ -55,12 +55,19 @@ if [[ $STEP == multi ]]; then
 fi
 if [[ $STEP == tc2 ]]; then
   timeout 300 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "2cta" > gpurun_out/pytest_tc2.log 2>&1; echo "pytest tc2 rc=$?"; tail -25 gpurun_out/pytest_tc2.log
-  for v in 4 3; do
+  for v in 5 4; do
     timeout 300 python bench.py --steps 3 --warmup 2 --variant $v --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_sv$v.json 2> gpurun_out/bench_sv$v.err; echo "bench search v$v rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_sv$v.json'));print(d['value'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_sv$v.err
   done
-  for v in 4 3; do
+  for v in 5; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:hamming_tc -c 1 -f -o gpurun_out/prof_hamming_v$v \
       python bench.py --steps 1 --warmup 0 --n-hashes 262144 --variant $v --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming_v$v.log 2>&1; echo "ncu hamming v$v rc=$?"
+  done
+fi
+if [[ $STEP == list5 ]]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v5.csv \
+      python bench.py --steps 1 --warmup 1 --variant 5 --no-cpu-baseline --no-secondary --e2e-steps 1 > gpurun_out/bench_under_ncu_v5.json 2>&1; echo "ncu list rc=$?"
+  for i in 1 2; do
+  timeout 300 python bench.py --steps 3 --warmup 2 --variant 5 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_sv5_$i.json 2> gpurun_out/bench_sv5_$i.err; echo "bench search v5 rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_sv5_$i.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"
   done
 fi
 if [[ $STEP == tc ]]; then

@@ -176,7 +176,36 @@ static int test_hash_frames(Context& ctx) {
     return 0;
 }
 
-int main() {
+// host-only: Search::sort as the library computes it (vdf_sort_order, multi-threaded) against a plain stable sort with the
+// component-wise comparator of this header; needs no GPU
+static int test_sort_order_host_only() {
+    std::vector<VideoHash> v;
+    const char* pieces[] = {"a", "b", "-", ".", "/", "..", "_", "0", "v", "\x01", " ", "ab", "~"};
+    uint64_t s = 88172645463325252ull;
+    auto rnd = [&]() { s ^= s << 13, s ^= s >> 7, s ^= s << 17; return s; };
+    for (int i = 0; i < 40000; ++i) {
+        std::string p;
+        const int n = 1 + (int)(rnd() % 8);
+        for (int k = 0; k < n; ++k) p += pieces[rnd() % 13];
+        v.push_back(VideoHash::empty_hash(p).with_duration((uint32_t)(rnd() % 3)));
+    }
+    for (int i = 0; i < 500; ++i) v.push_back(v[(size_t)i * 7]);  // exact ties: stability
+    std::vector<uint64_t> want(v.size());
+    for (size_t i = 0; i < want.size(); ++i) want[i] = i;
+    std::stable_sort(want.begin(), want.end(), [&](uint64_t a, uint64_t b) {
+        if (v[a].duration() != v[b].duration()) return v[a].duration() < v[b].duration();
+        return path_cmp(v[a].src_path(), v[b].src_path()) < 0;
+    });
+    CHECK(detail::sort_order(v) == want);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && std::string(argv[1]) == "--host-only") {
+        int r = test_sort_order_host_only();
+        std::printf("%s test_sort_order_host_only\n", r ? "FAILED" : "ok    ");
+        return r;
+    }
     try {
         Context ctx(0);
         int fails = 0;

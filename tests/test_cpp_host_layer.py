@@ -33,6 +33,13 @@ def test_cpp_host_layer_compiles_and_fails_loudly_without_gpu():
     assert r.returncode == 2 and "vdf_ctx_create failed" in r.stdout  # DeviceError, no CPU fallback
 
 
+def test_cpp_host_layer_sort_order_without_gpu():
+    """Search::sort through the C ABI (vdf_sort_order) against std::stable_sort with the header's Rust-Path comparator"""
+    _build()
+    r = subprocess.run([EXE, "--host-only"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_host_layer_reference_tests():
     _build()

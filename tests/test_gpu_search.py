@@ -10,13 +10,14 @@ from tests import synth
 from vid_dup_finder_lib_b200 import _ffi
 
 pytestmark = pytest.mark.gpu
+DEFAULT_VARIANT = 5  # tcgen05 cta_group::2 on packed tiles (common.cuh: vdf_ctx::search_variant)
 
 
 @pytest.fixture(scope="module")
 def ctx():
     c = _ffi.default_context()
     c.set_shard(0, 1)
-    c.set_option("search_variant", 0)
+    c.set_option("search_variant", DEFAULT_VARIANT)  # everything not parametrized runs the library default
     return c
 
 
@@ -110,7 +111,7 @@ def _case(rng, n, n_clusters, max_flip, dur_choices):
 SIZES = [1, 2, 3, 127, 128, 129, 255, 257, 1000, 4097]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=["popc", "csa8x8", "csa8x4", "tcgen05", "tcgen05_2cta"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=["popc", "csa8x8", "csa8x4", "tcgen05", "tcgen05_2cta", "tcgen05_2cta_packed"])
 @pytest.mark.parametrize("n", SIZES)
 def test_self_search_edges_and_groups_match_oracle(ctx, n, variant):
     rng = np.random.default_rng(1000 + n)
@@ -128,7 +129,37 @@ def test_self_search_edges_and_groups_match_oracle(ctx, n, variant):
                 g2, m2 = ctx.group_greedy(n, got_e)
                 assert np.array_equal(g2, want_gp) and np.array_equal(m2, want_mm)
     finally:
-        ctx.set_option("search_variant", 0)
+        ctx.set_option("search_variant", DEFAULT_VARIANT)
+
+
+def test_public_api_in_caller_order_matches_oracle(ctx):
+    """vdf_search / vdf_search_with_references take the caller's order and awkward paths; groups (content AND order) must
+    equal the oracle's sort + greedy walk mapped back to paths (video_dup_finder.rs:7-46)."""
+    rng = np.random.default_rng(77)
+    n = 3000
+    H, dur = _case(rng, n, 250, 180, [0, 9, 10, 11, 12, 100, 105, 110, 111, 600])
+    dur = dur[rng.permutation(n)]  # caller order: unsorted durations
+    pieces = ["a", "b", "-", ".", "/", "..", "_", "0", "v", "ab"]
+    paths = ["".join(rng.choice(pieces, int(rng.integers(1, 7)))) + "/%05d" % i for i in range(n)]
+    table = vdf.HashTable(H, dur, paths)
+    order = o.sort_order(dur, paths)
+    Hs, ds = np.ascontiguousarray(H[order]), dur[order]
+    for tol in (0.0, 0.15, 0.35):
+        tol_int = o.tolerance_int(tol)
+        wgp, wmm = o.search_self(Hs, ds, tol_int)
+        want = [[paths[order[int(k)]] for k in wmm[int(wgp[g]):int(wgp[g + 1])]] for g in range(len(wgp) - 1)]
+        got = vdf.search(table, tol, ctx=ctx)
+        assert [list(g.duplicates()) for g in got] == [w for w in want if len(w) >= 2]
+        assert all(g.reference() is None for g in got)
+    nr = 200
+    R = H[rng.integers(0, n, nr)] ^ np.packbits(rng.integers(0, 1024, (nr, 1024)) < 30, axis=1, bitorder="little").view(np.uint64)
+    rdur = rng.choice([9, 10, 100, 105, 600], nr).astype(np.uint32)
+    rpaths = ["ref/%d" % i for i in range(nr)]
+    rp, ci = o.search_refs(Hs, ds, R, rdur, 200)
+    want = [(rpaths[r], [paths[order[int(k)]] for k in ci[int(rp[r]):int(rp[r + 1])]]) for r in range(nr) if rp[r + 1] > rp[r]]
+    got = vdf.search_with_references(vdf.HashTable(R, rdur, rpaths), table, 0.2, ctx=ctx)
+    assert [(g.reference(), list(g.duplicates())) for g in got] == want
+    assert sum(ctx.last_phases()) > 0
 
 
 def test_greedy_rule_is_not_connected_components(ctx):
@@ -160,14 +191,14 @@ def test_random_edge_lists_group_like_the_oracle(ctx):
         assert np.array_equal(gp, want_gp) and np.array_equal(mm, want_mm)
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4], ids=["popc", "tcgen05", "tcgen05_2cta"])
+@pytest.mark.parametrize("variant", [0, 3, 4, 5], ids=["popc", "tcgen05", "tcgen05_2cta", "tcgen05_2cta_packed"])
 @pytest.mark.parametrize("n_cand,n_ref", [(1, 1), (300, 5), (129, 257), (5000, 700)])
 def test_ref_search_matches_oracle(ctx, n_cand, n_ref, variant):
     ctx.set_option("search_variant", variant)
     try:
         _ref_search_case(ctx, n_cand, n_ref)
     finally:
-        ctx.set_option("search_variant", 0)
+        ctx.set_option("search_variant", DEFAULT_VARIANT)
 
 
 def _ref_search_case(ctx, n_cand, n_ref):
@@ -215,7 +246,7 @@ def test_edge_buffer_grows_and_caps(ctx):
         ctx.set_option("max_edges", 1 << 28)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 4], ids=["popc", "csa8x4", "tcgen05_2cta"])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5], ids=["popc", "csa8x4", "tcgen05_2cta", "tcgen05_2cta_packed"])
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_shards_partition_the_pair_matrix(ctx, world, variant):
     rng = np.random.default_rng(5)
@@ -229,7 +260,7 @@ def test_shards_partition_the_pair_matrix(ctx, world, variant):
             parts.append(ctx.search_self(H, dur, 300))
     finally:
         ctx.set_shard(0, 1)
-        ctx.set_option("search_variant", 0)
+        ctx.set_option("search_variant", DEFAULT_VARIANT)
     assert sum(len(p) for p in parts) == len(want)  # disjoint
     allp = np.concatenate(parts)
     allp = allp[np.lexsort((allp[:, 1], allp[:, 0]))]

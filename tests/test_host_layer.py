@@ -101,6 +101,36 @@ def test_sort_order_matches_oracle_on_awkward_paths():
     assert path_components("./a//b/./c/") == [(2, b""), (4, b"a"), (4, b"b"), (4, b"c")]
 
 
+def test_native_sort_order_matches_the_python_rule_and_the_oracle():
+    """vdf_sort_order (csrc/host.cu, multi-threaded) is Search::sort (search_algorithm.rs:55-61): stable, by
+    (duration, Rust Unix Path order).  Awkward components, control bytes, prefixes, ties, and a size that takes the
+    threaded merge path."""
+    rng = np.random.default_rng(3)
+    pieces = ["a", "b", "-", ".", "/", "..", "_", "0", "v", "\x01", " ", "ab", "~", "\u00e9"]
+    paths = ["".join(rng.choice(pieces, int(rng.integers(1, 9)))) for _ in range(6000)]
+    paths += ["v/%08d" % i for i in rng.permutation(300)] + ["/", "//", ".", "./", "..", "a", "a/", "a/.", "./a", "/a", "a/b", "a-b"]
+    paths += paths[:500]  # exact ties: the sort must be stable
+    dur = rng.integers(0, 4, len(paths)).astype(np.uint32)
+    tb = vdf.HashTable(np.zeros((len(paths), 16), np.uint64), dur, paths)
+    got = _ffi.sort_order(dur, *tb.path_blob())
+    assert np.array_equal(got, o.sort_order(dur, paths))
+    assert np.array_equal(got, sort_order(dur, paths))
+    n = 300_000  # > 8192 per thread: parallel runs + merges
+    big = ["v/%08d" % i for i in rng.permutation(n)]
+    bd = rng.integers(590, 600, n).astype(np.uint32)
+    tb = vdf.HashTable(np.zeros((n, 16), np.uint64), bd, big)
+    assert np.array_equal(_ffi.sort_order(bd, *tb.path_blob()), sort_order(bd, big))
+    assert len(_ffi.sort_order(np.zeros(0, np.uint32), *vdf.HashTable(np.zeros((0, 16), np.uint64), [], []).path_blob())) == 0
+
+
+def test_match_groups_from_csr():
+    paths = ["p%d" % i for i in range(6)]
+    g = vdf.MatchGroup.from_csr(paths, [0, 2, 3, 6], [4, 1, 5, 0, 2, 3])
+    assert [list(x.duplicates()) for x in g] == [["p4", "p1"], ["p0", "p2", "p3"]]  # rows of one entry are not groups
+    r = vdf.MatchGroup.from_csr(paths, [0, 0, 2], [3, 1], references=["r0", "r1"])
+    assert len(r) == 1 and r[0].reference() == "r1" and list(r[0].duplicates()) == ["p3", "p1"]
+
+
 def test_constants_and_video_hash_accessors():
     assert (HASH_BITS, HASH_WORDS, vdf.DEFAULT_SEARCH_TOLERANCE, vdf.TOLERANCE_SCALING_FACTOR) == (1000, 16, 0.35, 1000.0)
     a = vdf.VideoHash.from_words([0] * 16, "a", 3)

@@ -27,6 +27,7 @@ EXPORTS = [
     "vdf_search_refs", "vdf_search_self_device", "vdf_search_refs_device", "vdf_group_greedy_device",
     "vdf_self_window_pairs", "vdf_free_edges", "vdf_free_groups", "vdf_free_csr", "vdf_hash_stacks",
     "vdf_hash_stacks_device", "vdf_hash_stacks_small_device", "vdf_hash_from_small",
+    "vdf_sort_order", "vdf_search", "vdf_search_with_references", "vdf_ctx_last_phases",
 ]
 
 
@@ -102,6 +103,10 @@ def lib() -> C.CDLL:
     L.vdf_search_refs_device.argtypes = [vp, vp, vp, u64, u64, vp, vp, u64, u32, vp, u64, C.POINTER(u64)]
     L.vdf_group_greedy_device.argtypes = [vp, u64, vp, u64, C.POINTER(Groups)]
     L.vdf_self_window_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.vdf_sort_order.argtypes = [vp, vp, vp, u64, vp]
+    L.vdf_search.argtypes = [vp, vp, vp, vp, vp, u64, C.c_double, C.POINTER(Groups)]
+    L.vdf_search_with_references.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, u64, C.c_double, C.POINTER(Csr)]
+    L.vdf_ctx_last_phases.argtypes = [vp, C.POINTER(C.c_double)]
     for f in ("vdf_free_edges", "vdf_free_groups", "vdf_free_csr"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = None
@@ -128,6 +133,16 @@ def _copy_u64(ptr, n: int) -> np.ndarray:
     if n == 0:
         return np.zeros(0, dtype=np.uint64)
     return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+
+def sort_order(durations, path_blob: np.ndarray, path_off: np.ndarray) -> np.ndarray:
+    """vdf_sort_order: Search::sort's permutation (stable, (duration, Rust Path order)); host-only, needs no GPU"""
+    d = np.ascontiguousarray(durations, dtype=np.uint32)
+    out = np.empty(len(d), dtype=np.uint64)
+    rc = lib().vdf_sort_order(_ptr(d), _ptr(path_blob), _ptr(path_off), len(d), _ptr(out))
+    if rc != 0:
+        raise VdfError(rc, "vdf_sort_order")
+    return out.astype(np.int64)
 
 
 def make_descs(n: int, width: int, height: int, n_frames: int = 16, pitch: Optional[int] = None) -> np.ndarray:
@@ -237,6 +252,37 @@ class Context:
         v = C.c_uint64()
         self._check(lib().vdf_self_window_pairs(self._h, _ptr(d), len(d), C.byref(v)))
         return v.value
+
+    # ---- the crate's public search functions, whole: inputs in the caller's order, indices of the caller's arrays out
+    def search(self, hashes, durations, path_blob: np.ndarray, path_off: np.ndarray, tolerance: float):
+        """vdf_search -> (group_ptr, member_idx): member_idx indexes the caller's arrays"""
+        h = _hash_array(hashes) if len(durations) else np.zeros((0, 16), np.uint64)
+        d = np.ascontiguousarray(durations, dtype=np.uint32)
+        g = Groups()
+        self._check(lib().vdf_search(self._h, _ptr(h), _ptr(d), _ptr(path_blob), _ptr(path_off), len(d), float(tolerance),
+                                     C.byref(g)))
+        return self._groups(g)
+
+    def search_with_references(self, ref_hashes, ref_durations, new_hashes, new_durations, new_path_blob: np.ndarray,
+                               new_path_off: np.ndarray, tolerance: float):
+        """vdf_search_with_references -> (row_ptr, col_idx): col_idx indexes the caller's new_hashes arrays"""
+        r = _hash_array(ref_hashes) if len(ref_durations) else np.zeros((0, 16), np.uint64)
+        rd = np.ascontiguousarray(ref_durations, dtype=np.uint32)
+        c = _hash_array(new_hashes) if len(new_durations) else np.zeros((0, 16), np.uint64)
+        cd = np.ascontiguousarray(new_durations, dtype=np.uint32)
+        out = Csr()
+        self._check(lib().vdf_search_with_references(self._h, _ptr(r), _ptr(rd), len(rd), _ptr(c), _ptr(cd), _ptr(new_path_blob),
+                                                     _ptr(new_path_off), len(cd), float(tolerance), C.byref(out)))
+        rp = _copy_u64(out.row_ptr, len(rd) + 1)
+        ci = _copy_u64(out.col_idx, int(rp[-1]))
+        lib().vdf_free_csr(C.byref(out))
+        return rp, ci
+
+    def last_phases(self):
+        """ms of the last search()/search_with_references(): host sort, gather + H2D enqueue, device, index remap"""
+        a = (C.c_double * 4)()
+        self._check(lib().vdf_ctx_last_phases(self._h, a))
+        return [float(x) for x in a]
 
     # ---- search path, device pointers
     def search_self_device(self, d_hash: int, d_dur: int, n: int, tol_int: int, d_keys_out: int, capacity: int) -> int:

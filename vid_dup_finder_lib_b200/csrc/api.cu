@@ -50,7 +50,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
-    DevBuf* bufs[] = {&ctx->row_tiles, &ctx->col_tiles, &ctx->row_lo,   &ctx->row_hi,  &ctx->row_id,  &ctx->tile_range,
+    DevBuf* bufs[] = {&ctx->pcmin_rows, &ctx->pcmin_cols, &ctx->row_tiles, &ctx->col_tiles, &ctx->row_lo,   &ctx->row_hi,  &ctx->row_id,  &ctx->tile_range,
                       &ctx->raw_keys,  &ctx->sort_tmp,  &ctx->misc,     &ctx->keys_a,  &ctx->keys_b,  &ctx->in_hash,
                       &ctx->in_dur,    &ctx->in_hash2,  &ctx->in_dur2,  &ctx->ref_perm, &ctx->ref_key, &ctx->g_rk,
                       &ctx->g_rks,     &ctx->g_state,   &ctx->g_parent, &ctx->g_wl0,   &ctx->g_wla,   &ctx->g_wlb,
@@ -94,7 +94,8 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "max_edges" && value > 0) ctx->max_edges = (uint64_t)value;
     else if (k == "initial_edges" && value > 0) ctx->initial_edges = (uint64_t)value;
-    else if (k == "search_variant" && (value >= 0 && value <= 4)) ctx->search_variant = (int)value;
+    else if (k == "search_variant" && (value >= 0 && value <= 5)) ctx->search_variant = (int)value;
+    else if (k == "tc_chunk" && value >= 0 && value <= 65535) ctx->tc_chunk = (uint32_t)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;
     else {
         ctx->err = "unknown option or bad value: " + k;

@@ -91,10 +91,13 @@ struct vdf_ctx {
     std::string err;
     uint32_t rank = 0, world = 1;
     uint64_t max_edges = 1ull << 28, initial_edges = 1ull << 22;
-    int search_variant = 2;  // 0: plain XOR + POPC; 1: XOR + carry-save adder + POPC, 8x8 pairs/thread;
-                             // 2 (default): carry-save on 8x4 pairs/thread, two CTAs per SM
+    int search_variant = 5;  // 0: plain XOR + POPC; 1: XOR + carry-save adder + POPC, 8x8 pairs/thread;
+                             // 2: carry-save on 8x4 pairs/thread, two CTAs per SM; 3: tcgen05 kind::i8, byte-expanded
+                             // tiles in HBM; 4: the same on CTA pairs; 5 (default): CTA pairs, packed tiles (search_tc.cu)
     int hash_variant = 0;
+    uint32_t tc_chunk = 0;  // column super-tiles per CTA-pair work unit (0: automatic)
     uint64_t launches = 0, h2d = 0, d2h = 0;
+    double phase_ms[4] = {0, 0, 0, 0};  // last vdf_search*: host sort, gather + H2D enqueue, device, index remap (host.cu)
     // device time of the dominant kernels (CUDA events on `stream`): 0 hamming tiles, 1 resize, 2 letterbox, 3 dct+pack
     cudaEvent_t kt0[4] = {nullptr, nullptr, nullptr, nullptr}, kt1[4] = {nullptr, nullptr, nullptr, nullptr};
     bool kt_pending[4] = {false, false, false, false};
@@ -104,7 +107,7 @@ struct vdf_ctx {
     // search scratch
     vdf::DevBuf row_tiles, col_tiles, row_lo, row_hi, row_id, tile_range, raw_keys, sort_tmp, misc, keys_a, keys_b;
     vdf::DevBuf in_hash, in_dur, in_hash2, in_dur2, ref_perm, ref_key;
-    vdf::DevBuf exp_rows, exp_cols, pc_rows, pc_cols;  // tensor-core search: byte-expanded tiles + popcounts
+    vdf::DevBuf exp_rows, exp_cols, pc_rows, pc_cols, pcmin_rows, pcmin_cols;  // tensor-core search: byte-expanded tiles + popcounts
     // grouping scratch
     vdf::DevBuf g_rk, g_rks, g_state, g_parent, g_wl0, g_wla, g_wlb, g_mk, g_mks, g_flag, g_scan, g_gp, g_mem;
     // hashing scratch
@@ -169,8 +172,9 @@ int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n);
 // search_tc.cu
 int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& exp, DevBuf& pc);
 int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t max_span_tiles, const uint8_t* row_exp,
-              const uint8_t* col_exp, const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base,
-              uint32_t tol, uint64_t capacity, unsigned long long* counter);
+              const uint8_t* col_exp, const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* col_pcmin,
+              const uint32_t* row_id, uint64_t col_base, uint32_t tol, uint64_t capacity, unsigned long long* counter);
+int tc5_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& tiles, DevBuf& pc, DevBuf& pcmin);
 // group.cu
 int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, vdf_groups* out);
 // hash.cu

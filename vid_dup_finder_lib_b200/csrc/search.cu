@@ -485,7 +485,7 @@ static int set_ham_attrs(vdf_ctx* ctx) {
 
 // shared tail of both searches: tile ranges, the hot kernel, count read-back, key sort
 static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, const void* row_data, const void* col_data,
-                     const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
+                     const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* col_pcmin, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
                      uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
     const uint32_t* row_tiles = static_cast<const uint32_t*>(row_data);
     const uint32_t* col_tiles = static_cast<const uint32_t*>(col_data);
@@ -533,7 +533,7 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, c
     }
     if (ctx->search_variant >= 3) {  // tensor-core path: byte-expanded operands, tcgen05.mma kind::i8
         VDF_TRY(tc_launch(ctx, n_row_tiles, n_col_tiles, max_span, static_cast<const uint8_t*>(row_data), static_cast<const uint8_t*>(col_data),
-                          row_pc, col_pc, row_id, col_base, tol, capacity, misc + 2));
+                          row_pc, col_pc, col_pcmin, row_id, col_base, tol, capacity, misc + 2));
     } else {
     kt_begin(ctx, 0);
     if (ctx->search_variant == 2)
@@ -569,9 +569,11 @@ int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_d
     VDF_ALLOC(ctx, ctx->row_tiles.ensure((size_t)T * kTileWords * 4));
     VDF_ALLOC(ctx, ctx->row_lo.ensure((size_t)n_pad * 4));
     VDF_ALLOC(ctx, ctx->row_hi.ensure((size_t)n_pad * 4));
-    const bool tc = ctx->search_variant >= 3;
+    const bool tc = ctx->search_variant == 3 || ctx->search_variant == 4;  // byte-expanded operands in HBM
     if (tc) {
         VDF_TRY(tc_expand(ctx, d_hash, nullptr, n, ctx->exp_rows, ctx->pc_rows));
+    } else if (ctx->search_variant == 5) {
+        VDF_TRY(tc5_pack(ctx, d_hash, nullptr, n, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
     } else {
         retile_kernel<<<T, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), nullptr, n,
                                                   ctx->row_tiles.as<uint32_t>());
@@ -581,7 +583,8 @@ int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_d
                                                                      ctx->row_hi.as<uint32_t>());
     VDF_LAUNCHED(ctx);
     const void* data = tc ? ctx->exp_rows.p : ctx->row_tiles.p;
-    return run_tiles(ctx, T, T, data, data, ctx->pc_rows.as<uint32_t>(), ctx->pc_rows.as<uint32_t>(), nullptr, 0, tol,
+    return run_tiles(ctx, T, T, data, data, ctx->pc_rows.as<uint32_t>(), ctx->pc_rows.as<uint32_t>(),
+                     ctx->pcmin_rows.as<uint32_t>(), nullptr, 0, tol,
                      d_keys_out, capacity, n_out);
 }
 
@@ -616,10 +619,13 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
     VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32,
                                                   ctx->stream));
     ctx->launches += 3;
-    const bool tc = ctx->search_variant >= 3;
+    const bool tc = ctx->search_variant == 3 || ctx->search_variant == 4;
     if (tc) {
         VDF_TRY(tc_expand(ctx, d_cand, nullptr, n_cand, ctx->exp_cols, ctx->pc_cols));
         VDF_TRY(tc_expand(ctx, d_refs, perm, n_ref, ctx->exp_rows, ctx->pc_rows));
+    } else if (ctx->search_variant == 5) {
+        VDF_TRY(tc5_pack(ctx, d_cand, nullptr, n_cand, ctx->col_tiles, ctx->pc_cols, ctx->pcmin_cols));
+        VDF_TRY(tc5_pack(ctx, d_refs, perm, n_ref, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
     } else {
         retile_kernel<<<TC, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cand), nullptr, n_cand,
                                                    ctx->col_tiles.as<uint32_t>());
@@ -636,7 +642,8 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
     const uint32_t world = ctx->world, rank = ctx->rank;
     ctx->world = 1, ctx->rank = 0;
     int rc = run_tiles(ctx, TR, TC, tc ? ctx->exp_rows.p : ctx->row_tiles.p, tc ? ctx->exp_cols.p : ctx->col_tiles.p,
-                       ctx->pc_rows.as<uint32_t>(), ctx->pc_cols.as<uint32_t>(), perm, cand_base, tol, d_keys_out, capacity,
+                       ctx->pc_rows.as<uint32_t>(), ctx->pc_cols.as<uint32_t>(), ctx->pcmin_cols.as<uint32_t>(), perm, cand_base, tol,
+                       d_keys_out, capacity,
                        n_out);
     ctx->world = world, ctx->rank = rank;
     return rc;

@@ -73,6 +73,14 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar))
                  : "memory");
 }
+// one lane of a converged warp (the same lane every time): the canonical predicate for issuing tcgen05.mma / commit.
+// Keeping the MMA warp converged and electing here lets ptxas keep barrier addresses and descriptors in uniform
+// registers; a `lane == 0` branch around the loop costs a vote loop (ELECT / BRA.U.ANY) per UTCIMMA instead.
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -130,6 +138,7 @@ struct TcParams {
     const uint8_t* col_exp;
     const uint32_t* row_pc;
     const uint32_t* col_pc;
+    const uint32_t* col_pcmin;  // variant 5: min of col_pc over each group of 64 columns
     const uint32_t* row_lo;
     const uint32_t* row_hi;
     const uint32_t* row_id;
@@ -397,26 +406,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) hammi
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && cr == 0) {  // ===== MMA issuer (leader CTA only)
+        if (cr == 0) {  // ===== MMA issuer (leader CTA only): converged warp, one elected lane issues
             tc_mbar_wait(a_full, 0);
-            const uint32_t a_addr = tc_smem_u32(sA), b_addr = tc_smem_u32(sB);
-            uint32_t it = 0;
+            const uint64_t a_desc = tc_desc(tc_smem_u32(sA)), b_desc = tc_desc(tc_smem_u32(sB));
             for (uint32_t s = 0; s < n_st; ++s) {
                 const uint32_t buf = s & 1;
                 tc_mbar_wait(&acc_empty[buf], ((s >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 256;
-                for (int kc = 0; kc < 8; ++kc, ++it) {
-                    const uint32_t stage = it % kTc2Stages;
-                    tc_mbar_wait(&full[stage], (it / kTc2Stages) & 1);
-                    tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        tc2_mma(d_tmem, tc_desc(a_addr + kc * kTcChunkBytes + ks * 32),
-                                tc_desc(b_addr + stage * kTc2StageBytes + ks * 32), (kc | ks) != 0);
-                    tc2_commit(&empty[stage]);  // frees the stage in both CTAs
+                for (int kc = 0; kc < 8; ++kc) {  // it = 8 s + kc: stage and parity are compile-time (8 = 2 x kTc2Stages)
+                    static_assert(kTc2Stages == 4, "stage/parity folding below assumes 4 stages");
+                    tc_mbar_wait(&full[kc & 3], (kc >> 2) & 1);
+                    tc_fence_after();
+                    if (tc_elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            tc2_mma(d_tmem, a_desc + ((kc * kTcChunkBytes + ks * 32) >> 4),
+                                    b_desc + (((kc & 3) * kTc2StageBytes + ks * 32) >> 4), (kc | ks) != 0);
+                        tc2_commit(&empty[kc & 3]);  // frees the stage in both CTAs
+                        if (kc == 7) tc2_commit(&acc_full[buf]);
+                    }
+                    __syncwarp();
                 }
-                tc2_commit(&acc_full[buf]);
             }
         } else if (lane == 0) {  // ===== peer CTA: relay "my half has landed" to the leader's barriers
             tc_mbar_wait(a_full, 0);
@@ -487,6 +499,279 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) hammi
     }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA pair, packed operands
+// search_variant 5: variant 4 with the bit -> byte expansion moved INTO the kernel.  HBM keeps only packed tiles
+// (pk[tile][K-chunk 0..7][hash 0..127][4 x u32], 16 KB per 128 hashes), so the operand traffic from L2 is 1/8 of variant
+// 4's and no byte-expanded copy of the table (1 GB per million hashes) exists.  Four expander warps turn each K-chunk of
+// this CTA's column tile (128 hashes x 128 bits, read from a packed tile that a bulk copy landed in shared memory a whole
+// tile ahead) into the 128 x 128 B swizzled UMMA operand stage, make the writes visible to the async proxy
+// (fence.proxy.async) and arrive on the LEADER's full[stage] (8 arrivals: 4 warps x 2 CTAs).  A stage is refilled from
+// shared memory instead of from L2, so the ring turn-around drops from ~2000 to a few hundred cycles.
+//
+// Operand values: bit m (0..7) of every byte group becomes the byte  bit << m  in B and  bit << (7 - m)  in A, so every
+// common bit contributes exactly 2^7 to the u8 x u8 -> s32 dot product (<= 2^17 in total) and the B expansion is one
+// PRMT (replicate a source byte) + two LOP3 (mask) per eight output bytes.  dot = acc >> 7.
+constexpr int kTc5Threads = 320;  // warp 0 bulk-copy producer, 1 MMA, 2-5 epilogue, 6-9 expanders
+constexpr int kTc5PackedBufs = 2;
+constexpr size_t kTc5Smem =
+    (size_t)kTcTileBytes + kTc2Stages * kTc2StageBytes + kTc5PackedBufs * (size_t)kTileWords * 4 + 1024 /*align*/ + 256;
+
+__device__ __forceinline__ void tc_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// lane -> (row-in-8, word): lanes of a quarter-warp cover rows 2q, 2q+1 x words 0..3, so that their 16-byte stores hit
+// eight different 16-byte bank groups of the 128 B-swizzled line pair; the packed reads of a warp are 128 contiguous bytes
+__device__ __forceinline__ int tc5_lane_row(int lane) { return ((lane >> 3) << 1) | ((lane >> 2) & 1); }
+
+// B operand: one packed u32 -> 32 bytes (bit m of byte group -> bit << m)
+__device__ __forceinline__ void tc5_expand_b(uint32_t bits, uint8_t* line, int w, int rsw) {
+    uint4 lo, hi;
+    const uint32_t b0 = __byte_perm(bits, 0, 0x0000), b1 = __byte_perm(bits, 0, 0x1111);
+    const uint32_t b2 = __byte_perm(bits, 0, 0x2222), b3 = __byte_perm(bits, 0, 0x3333);
+    lo.x = b0 & 0x08040201u, lo.y = b0 & 0x80402010u, lo.z = b1 & 0x08040201u, lo.w = b1 & 0x80402010u;
+    hi.x = b2 & 0x08040201u, hi.y = b2 & 0x80402010u, hi.z = b3 & 0x08040201u, hi.w = b3 & 0x80402010u;
+    *reinterpret_cast<uint4*>(line + (((2 * w) ^ rsw) << 4)) = lo;
+    *reinterpret_cast<uint4*>(line + (((2 * w + 1) ^ rsw) << 4)) = hi;
+}
+// A operand: bit m of byte group -> bit << (7 - m)   (once per work unit: speed is irrelevant)
+__device__ __forceinline__ uint32_t tc5_a_word(uint32_t nib, bool upper) {
+    const uint32_t s = (nib * 0x00204081u) & 0x01010101u;  // byte i = bit i of the nibble
+    const uint32_t v = ((s & 0x00000001u) << 7) | ((s & 0x00000100u) << 6) | ((s & 0x00010000u) << 5) | ((s & 0x01000000u) << 4);
+    return upper ? (v >> 4) : v;
+}
+__device__ __forceinline__ void tc5_expand_a(uint32_t bits, uint8_t* line, int w, int rsw) {
+    uint4 lo, hi;
+    lo.x = tc5_a_word(bits & 0xFu, false), lo.y = tc5_a_word((bits >> 4) & 0xFu, true);
+    lo.z = tc5_a_word((bits >> 8) & 0xFu, false), lo.w = tc5_a_word((bits >> 12) & 0xFu, true);
+    hi.x = tc5_a_word((bits >> 16) & 0xFu, false), hi.y = tc5_a_word((bits >> 20) & 0xFu, true);
+    hi.z = tc5_a_word((bits >> 24) & 0xFu, false), hi.w = tc5_a_word(bits >> 28, true);
+    *reinterpret_cast<uint4*>(line + (((2 * w) ^ rsw) << 4)) = lo;
+    *reinterpret_cast<uint4*>(line + (((2 * w + 1) ^ rsw) << 4)) = hi;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc5Threads, 1)
+    hamming_tc5_kernel(const TcParams p, uint32_t n_row_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned tiles (offset arithmetic keeps the pointers in the shared space)
+    uint8_t* base = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = base + kTcTileBytes;
+    uint32_t* sP = reinterpret_cast<uint32_t*>(sB + kTc2Stages * kTc2StageBytes);  // [2][8 kc][128 rows][4] packed tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTc5PackedBufs * kTileWords);
+    uint64_t* full = bars;                     // [kTc2Stages]  leader: 8 expander-warp arrivals
+    uint64_t* empty = bars + kTc2Stages;       // [kTc2Stages]  commit multicast
+    uint64_t* pfull = bars + 2 * kTc2Stages;   // [2] packed tile landed
+    uint64_t* pempty = pfull + 2;              // [2] 4 expander warps done with it
+    uint64_t* acc_full = pempty + 2;           // [2]
+    uint64_t* acc_empty = acc_full + 2;        // [2]  (leader's copy is the live one)
+    uint64_t* a_full = acc_empty + 2;          // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+
+    const uint32_t cr = tc_cluster_rank();
+    const uint32_t P = blockIdx.x >> 1, c = blockIdx.y;
+    if (p.world > 1 && ((P + c) % p.world) != p.rank) return;
+    const uint2 r0 = p.tile_range[2 * P];
+    const uint2 r1 = (2 * P + 1 < n_row_tiles) ? p.tile_range[2 * P + 1] : make_uint2(0, 0);
+    uint32_t t_lo = 0xFFFFFFFFu, t_hi = 0;
+    if (r0.x < r0.y) t_lo = r0.x, t_hi = r0.y;
+    if (r1.x < r1.y) t_lo = min(t_lo, r1.x), t_hi = max(t_hi, r1.y);
+    if (t_lo >= t_hi) return;
+    const uint32_t st0 = max(t_lo / 2, c * p.chunk), st1 = min((t_hi + 1) / 2, (c + 1) * p.chunk);
+    if (st0 >= st1) return;
+    const uint32_t n_st = st1 - st0;
+    const uint32_t I = 2 * P + cr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t* row_tiles = reinterpret_cast<const uint32_t*>(p.row_exp);
+    const uint32_t* col_tiles = reinterpret_cast<const uint32_t*>(p.col_exp);
+
+    if (tid == 0) {
+        for (int s = 0; s < kTc2Stages; ++s) tc_mbar_init(&full[s], 8), tc_mbar_init(&empty[s], 1);
+        for (int b = 0; b < 2; ++b) {
+            tc_mbar_init(&pfull[b], 1), tc_mbar_init(&pempty[b], 4);
+            tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 8);
+        }
+        tc_mbar_init(a_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // this CTA's 128 packed rows land in packed buffer 0 and are expanded by everybody below
+        tc_mbar_expect_tx(a_full, kTileWords * 4);
+        tc_bulk_g2s(sP, row_tiles + (size_t)I * kTileWords, kTileWords * 4, a_full);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();  // barrier init visible to this CTA's waiters
+    tc_mbar_wait(a_full, 0);
+    {
+        const int w = lane & 3, r8 = tc5_lane_row(lane);
+        for (int item = warp; item < 8 * 16; item += kTc5Threads / 32) {  // (K-chunk, 8-row group)
+            const int kc = item >> 4, row = (item & 15) * 8 + r8;
+            tc5_expand_a(sP[(kc * kTile + row) * 4 + w], sA + kc * kTcChunkBytes + row * 128, w, r8);
+        }
+    }
+    tc_fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_cluster_sync();  // both A halves expanded, both CTAs' barriers initialised, tensor memory allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== bulk-copy producer: this CTA's packed column tile of every super-tile, one tile ahead
+            for (uint32_t s = 0; s < n_st; ++s) {
+                const uint32_t pb = s & 1;
+                tc_mbar_wait(&pempty[pb], ((s >> 1) & 1) ^ 1);
+                tc_mbar_expect_tx(&pfull[pb], kTileWords * 4);
+                tc_bulk_g2s(sP + pb * kTileWords, col_tiles + (size_t)(2 * (st0 + s) + cr) * kTileWords, kTileWords * 4, &pfull[pb]);
+            }
+        }
+    } else if (warp == 1) {
+        if (cr == 0) {  // ===== MMA issuer (leader CTA only): converged warp, one elected lane issues
+            const uint64_t a_desc = tc_desc(tc_smem_u32(sA)), b_desc = tc_desc(tc_smem_u32(sB));
+            for (uint32_t s = 0; s < n_st; ++s) {
+                const uint32_t buf = s & 1;
+                tc_mbar_wait(&acc_empty[buf], ((s >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) {  // it = 8 s + kc: stage and parity are compile-time (8 = 2 x kTc2Stages)
+                    tc_mbar_wait(&full[kc & 3], (kc >> 2) & 1);
+                    tc_fence_after();
+                    if (tc_elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            tc2_mma(d_tmem, a_desc + ((kc * kTcChunkBytes + ks * 32) >> 4),
+                                    b_desc + (((kc & 3) * kTc2StageBytes + ks * 32) >> 4), (kc | ks) != 0);
+                        tc2_commit(&empty[kc & 3]);
+                        if (kc == 7) tc2_commit(&acc_full[buf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 6) {  // ===== expanders: warp e owns rows 32e .. 32e+31 of every stage
+        const int w = lane & 3, r8 = tc5_lane_row(lane);
+        const int row = (warp - 6) * 32 + r8;  // + 8 g
+        uint32_t it = 0;
+        for (uint32_t s = 0; s < n_st; ++s) {
+            const uint32_t pb = s & 1;
+            tc_mbar_wait(&pfull[pb], (s >> 1) & 1);
+            const uint32_t* packed = sP + pb * kTileWords + row * 4 + w;
+            for (int kc = 0; kc < 8; ++kc, ++it) {
+                uint32_t bits[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) bits[g] = packed[(kc * kTile + g * 8) * 4];
+                const uint32_t stage = it % kTc2Stages;
+                tc_mbar_wait(&empty[stage], ((it / kTc2Stages) & 1) ^ 1);
+                uint8_t* line = sB + stage * kTc2StageBytes + row * 128;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) tc5_expand_b(bits[g], line + g * 8 * 128, w, r8);
+                tc_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive_remote(&full[stage], 0);
+            }
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&pempty[pb]);
+        }
+    } else {  // ===== epilogue (warps 2-5 of both CTAs): warp w reads TMEM lanes 32*(w%4) .. +31 of its own CTA
+        const uint32_t quarter = warp & 3;
+        const uint32_t row = quarter * 32 + lane;
+        const uint32_t gi = I * kTile + row;
+        const bool live = I < n_row_tiles;
+        const int thr = live ? (int)p.row_pc[gi] - (int)p.tol : 0x7FFFFFFF;
+        for (uint32_t s = 0; s < n_st; ++s) {
+            const uint32_t buf = s & 1;
+            tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
+            tc_fence_after();
+            const uint32_t col_first = (st0 + s) * 256;
+            const uint32_t* pcmin = p.col_pcmin + (col_first >> 6);
+            for (int q = 0; q < 4; ++q) {
+                uint32_t v[64];
+                // a pair (i, j) matches iff 2 dot - pc(j) >= pc(i) - tol, with acc = 128 dot.  Screen 64 columns at once:
+                // 2 max(dot) - min(pc(j)) bounds every column's left-hand side from above, so the common case costs one
+                // 3-input max per two accumulators and no per-column load
+                const int floor_pc = (int)__ldg(pcmin + q);
+                __syncwarp();
+                tc_ld64(tmem_base + buf * 256 + q * 64 + ((quarter * 32) << 16), v);
+                uint32_t best = 0;
+#pragma unroll
+                for (int k = 0; k < 64; k += 2) best = max(best, max(v[k], v[k + 1]));
+                if ((int)(best >> 6) - floor_pc >= thr) {  // rare: exact test of the 64 columns
+                    const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
+                    uint64_t mask = 0;
+#pragma unroll
+                    for (int k4 = 0; k4 < 16; ++k4) {
+                        const uint4 pj = __ldg(pcj + k4);
+                        mask |= (uint64_t)((int)(v[4 * k4 + 0] >> 6) - (int)pj.x >= thr) << (4 * k4 + 0);
+                        mask |= (uint64_t)((int)(v[4 * k4 + 1] >> 6) - (int)pj.y >= thr) << (4 * k4 + 1);
+                        mask |= (uint64_t)((int)(v[4 * k4 + 2] >> 6) - (int)pj.z >= thr) << (4 * k4 + 2);
+                        mask |= (uint64_t)((int)(v[4 * k4 + 3] >> 6) - (int)pj.w >= thr) << (4 * k4 + 3);
+                    }
+                    while (mask) {
+                        const int k = __ffsll((long long)mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t gj = col_first + q * 64 + k;
+                        if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
+                            const unsigned long long slot = atomicAdd(p.counter, 1ull);
+                            if (slot < p.capacity) {
+                                const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
+                                p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive_remote(&acc_empty[buf], 0);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    tc_cluster_sync();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// hashes [n][32] u32 -> pk[tile][K-chunk][hash][4 u32] + per-hash popcounts (the epilogue's pc(i), pc(j)); one thread per
+// hash; tiles beyond n are zero.  perm (optional) gathers rows.
+__global__ void __launch_bounds__(kTile) tc5_pack_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm,
+                                                         uint64_t n, uint32_t* __restrict__ pk, uint32_t* __restrict__ pc,
+                                                         uint32_t* __restrict__ pcmin64) {
+    __shared__ uint32_t wmin[4];
+    const uint64_t g = (uint64_t)blockIdx.x * kTile + threadIdx.x;
+    uint4* out = reinterpret_cast<uint4*>(pk + (size_t)blockIdx.x * kTileWords) + threadIdx.x;
+    uint32_t c = 0;
+    const uint4* src = g < n ? reinterpret_cast<const uint4*>(in) + (perm ? perm[g] : g) * 8 : nullptr;
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (src) v = src[kc];
+        c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        out[kc * kTile] = v;
+    }
+    pc[g] = c;
+    const uint32_t m = __reduce_min_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 2) pcmin64[(size_t)blockIdx.x * 2 + threadIdx.x] = min(wmin[2 * threadIdx.x], wmin[2 * threadIdx.x + 1]);
+}
+
+int tc5_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& tiles, DevBuf& pc, DevBuf& pcmin) {
+    const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
+    const uint32_t T2 = (T + 1) & ~1u;  // CTA pairs read tile pairs: one zero tile of padding when T is odd
+    VDF_ALLOC(ctx, tiles.ensure((size_t)T2 * kTileWords * 4));
+    VDF_ALLOC(ctx, pc.ensure((size_t)T2 * kTile * 4));
+    VDF_ALLOC(ctx, pcmin.ensure((size_t)T2 * 2 * 4));
+    tc5_pack_kernel<<<T2, kTile, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), perm, n, tiles.as<uint32_t>(),
+                                                  pc.as<uint32_t>(), pcmin.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    return VDF_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& exp, DevBuf& pc) {
     const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
@@ -504,29 +789,37 @@ int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64
 }
 
 int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t max_span_tiles, const uint8_t* row_exp,
-              const uint8_t* col_exp, const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* row_id, uint64_t col_base,
-              uint32_t tol, uint64_t capacity, unsigned long long* counter) {
+              const uint8_t* col_exp, const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* col_pcmin,
+              const uint32_t* row_id, uint64_t col_base, uint32_t tol, uint64_t capacity, unsigned long long* counter) {
     static bool attr_done = false;
     if (!attr_done) {
         VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc2Smem));
+        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc5Smem));
         attr_done = true;
     }
     TcParams p;
-    p.row_exp = row_exp, p.col_exp = col_exp, p.row_pc = row_pc, p.col_pc = col_pc;
+    p.row_exp = row_exp, p.col_exp = col_exp, p.row_pc = row_pc, p.col_pc = col_pc, p.col_pcmin = col_pcmin;
     p.row_lo = ctx->row_lo.as<uint32_t>(), p.row_hi = ctx->row_hi.as<uint32_t>(), p.row_id = row_id;
     p.tile_range = ctx->tile_range.as<uint2>();
     p.keys = ctx->raw_keys.as<uint64_t>(), p.counter = counter, p.capacity = capacity, p.col_base = col_base;
     p.tol = tol, p.rank = ctx->rank, p.world = ctx->world;
-    if (ctx->search_variant == 4) {  // CTA pairs: 256-row super-tiles x absolute chunks of column super-tiles
+    if (ctx->search_variant >= 4) {  // CTA pairs: 256-row super-tiles x absolute chunks of column super-tiles
         const uint32_t n_pairs = (n_row_tiles + 1) / 2, n_st = (n_col_tiles + 1) / 2;
-        uint32_t chunk = 32;
-        while (chunk > 2 && (uint64_t)n_pairs * ((n_st + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 4 * ctx->world) chunk >>= 1;
+        // long chunks amortise the per-unit set-up (operand A, tensor-memory allocation, cluster syncs); keep >= 64
+        // units per resident pair for balance
+        uint32_t chunk = ctx->tc_chunk ? ctx->tc_chunk : 128;
+        while (!ctx->tc_chunk && chunk > 2 &&
+               (uint64_t)n_pairs * ((n_st + chunk - 1) / chunk) < (uint64_t)(ctx->sm_count / 2) * 64 * ctx->world)
+            chunk >>= 1;
         while ((n_st + chunk - 1) / chunk > 65535) chunk *= 2;
         p.chunk = chunk;
         dim3 grid(2 * n_pairs, (n_st + chunk - 1) / chunk);
         kt_begin(ctx, 0);
-        hamming_tc2_kernel<<<grid, kTcThreads, kTc2Smem, ctx->stream>>>(p, n_row_tiles);
+        if (ctx->search_variant == 5)
+            hamming_tc5_kernel<<<grid, kTc5Threads, kTc5Smem, ctx->stream>>>(p, n_row_tiles);
+        else
+            hamming_tc2_kernel<<<grid, kTcThreads, kTc2Smem, ctx->stream>>>(p, n_row_tiles);
         kt_end(ctx, 0);
         VDF_LAUNCHED(ctx);
         return VDF_OK;

@@ -20,7 +20,7 @@ import torch.distributed as dist
 from . import _ffi
 from .definitions import tolerance_to_int
 from .match_group import MatchGroup
-from .video_hash import HashTable, as_table, sort_order
+from .video_hash import HashTable, as_table
 
 
 def world_info(group=None) -> Tuple[int, int]:
@@ -56,7 +56,10 @@ def allgather_varlen(local: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def merge_keys(local_keys: torch.Tensor, group=None) -> torch.Tensor:
-    """all ranks' u64 keys (carried as int64; indices < 2^31 keep them non-negative), globally sorted"""
+    """all ranks' u64 keys (carried as int64; indices < 2^31 keep them non-negative), globally sorted; each rank's
+    own keys arrive sorted from the library, so a single rank has nothing to merge"""
+    if world_info(group)[1] == 1:
+        return local_keys  # the library already returns its keys sorted
     allk = allgather_varlen(local_keys, group)
     return torch.sort(allk).values if allk.numel() else allk
 
@@ -115,20 +118,18 @@ def search(hashes, tolerance: float, ctx: Optional[_ffi.Context] = None, group=N
     n = len(table)
     if n == 0:
         return []
+    if world_info(group)[1] == 1:  # one GPU: the whole function is one C-ABI call (vdf_search)
+        from .search import search as search_one
+
+        return search_one(table, tolerance, ctx)
     dev = torch.device("cuda", ctx.device)
-    order = sort_order(table.durations, table.paths)
+    order = _ffi.sort_order(table.durations, *table.path_blob())
     d_hash = _to_dev(np.ascontiguousarray(table.hashes[order]), dev)
     d_dur = _to_dev(np.ascontiguousarray(table.durations[order]), dev)
     keys = search_self_keys(ctx, d_hash, d_dur, tolerance_to_int(tolerance), group)
     torch.cuda.current_stream().synchronize()
     gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
-    paths = table.paths
-    out = []
-    for g in range(len(gp) - 1):
-        members = [paths[order[k]] for k in mm[gp[g]:gp[g + 1]]]
-        if len(members) >= 2:
-            out.append(MatchGroup.new(members))
-    return out
+    return MatchGroup.from_csr(table.paths, gp, order[mm.astype(np.int64)])
 
 
 def search_with_references(ref_hashes, new_hashes, tolerance: float, ctx: Optional[_ffi.Context] = None,
@@ -140,7 +141,7 @@ def search_with_references(ref_hashes, new_hashes, tolerance: float, ctx: Option
         return []
     rank, world = world_info(group)
     dev = torch.device("cuda", ctx.device)
-    order = sort_order(cands.durations, cands.paths)
+    order = _ffi.sort_order(cands.durations, *cands.path_blob())
     b, e = shard_range(len(cands), rank, world)
     sl = order[b:e]
     d_c = _to_dev(np.ascontiguousarray(cands.hashes[sl]).reshape(-1, 16), dev)
@@ -149,11 +150,7 @@ def search_with_references(ref_hashes, new_hashes, tolerance: float, ctx: Option
     d_rd = _to_dev(refs.durations, dev)
     keys = search_refs_keys(ctx, d_c, d_cd, b, d_r, d_rd, tolerance_to_int(tolerance), group)
     rp, ci = csr_from_keys(keys.cpu().numpy(), len(refs))
-    out = []
-    for r in range(len(refs)):
-        if rp[r + 1] > rp[r]:
-            out.append(MatchGroup.new_with_reference(refs.paths[r], [cands.paths[order[int(k)]] for k in ci[int(rp[r]):int(rp[r + 1])]]))
-    return out
+    return MatchGroup.from_csr(cands.paths, rp, order[ci.astype(np.int64)], references=refs.paths)
 
 
 def hash_stacks_sharded(ctx: _ffi.Context, d_frames: torch.Tensor, descs: np.ndarray, cropdetect: int, group=None):

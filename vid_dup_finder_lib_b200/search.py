@@ -9,17 +9,15 @@ from typing import Iterable, List, Optional
 import numpy as np
 
 from . import _ffi
-from .definitions import tolerance_to_int
 from .match_group import MatchGroup
-from .video_hash import HashTable, VideoHash, as_table, sort_order
+from .video_hash import HashTable, VideoHash, as_table
 
 
 def search_indices(table: HashTable, tolerance: float, ctx: Optional[_ffi.Context] = None):
-    """-> (order, group_ptr, member_idx): groups of indices into the SORTED table; order maps back to the input."""
+    """-> (group_ptr, member_idx): groups of indices into the table AS GIVEN (the library sorts internally)."""
     ctx = ctx or _ffi.default_context()
-    order = sort_order(table.durations, table.paths)
-    gp, mm = ctx.search_self_groups(table.hashes[order], table.durations[order], tolerance_to_int(tolerance))
-    return order, gp, mm
+    blob, off = table.path_blob()
+    return ctx.search(table.hashes, table.durations, blob, off, tolerance)
 
 
 def search(hashes: Iterable[VideoHash] | HashTable, tolerance: float, ctx: Optional[_ffi.Context] = None) -> List[MatchGroup]:
@@ -28,14 +26,8 @@ def search(hashes: Iterable[VideoHash] | HashTable, tolerance: float, ctx: Optio
     table = as_table(hashes)
     if len(table) == 0:  # search_algorithm.rs:88-90
         return []
-    order, gp, mm = search_indices(table, tolerance, ctx)
-    paths = table.paths
-    out = []
-    for g in range(len(gp) - 1):
-        members = [paths[order[k]] for k in mm[gp[g]:gp[g + 1]]]
-        if len(members) >= 2:  # MatchGroup::new(x).ok(), video_dup_finder.rs:11
-            out.append(MatchGroup.new(members))
-    return out
+    gp, mm = search_indices(table, tolerance, ctx)
+    return MatchGroup.from_csr(table.paths, gp, mm)  # MatchGroup::new(x).ok(), video_dup_finder.rs:11
 
 
 def search_with_references(ref_hashes: Iterable[VideoHash] | HashTable, new_hashes: Iterable[VideoHash] | HashTable,
@@ -46,11 +38,6 @@ def search_with_references(ref_hashes: Iterable[VideoHash] | HashTable, new_hash
     refs, cands = as_table(ref_hashes), as_table(new_hashes)
     if len(refs) == 0 or len(cands) == 0:
         return []
-    order = sort_order(cands.durations, cands.paths)
-    rp, ci = ctx.search_refs(cands.hashes[order], cands.durations[order], refs.hashes, refs.durations,
-                             tolerance_to_int(tolerance))
-    out = []
-    for r in range(len(refs)):
-        if rp[r + 1] > rp[r]:  # video_dup_finder.rs:38-43
-            out.append(MatchGroup.new_with_reference(refs.paths[r], [cands.paths[order[k]] for k in ci[rp[r]:rp[r + 1]]]))
-    return out
+    blob, off = cands.path_blob()
+    rp, ci = ctx.search_with_references(refs.hashes, refs.durations, cands.hashes, cands.durations, blob, off, tolerance)
+    return MatchGroup.from_csr(cands.paths, rp, ci, references=refs.paths)  # video_dup_finder.rs:38-43

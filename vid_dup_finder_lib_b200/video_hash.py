@@ -57,13 +57,26 @@ class VideoHash:
 class HashTable:
     """Struct-of-arrays view of many VideoHashes: hashes [n,16] u64, durations [n] u32, paths list[str]."""
 
-    __slots__ = ("hashes", "durations", "paths")
+    __slots__ = ("hashes", "durations", "paths", "_blob")
 
     def __init__(self, hashes, durations, paths: Sequence[str]):
         self.hashes = np.ascontiguousarray(hashes, dtype=np.uint64).reshape(-1, 16)
         self.durations = np.ascontiguousarray(durations, dtype=np.uint32)
         self.paths = paths
+        self._blob = None
         assert len(self.hashes) == len(self.durations) == len(paths)
+
+    def path_blob(self):
+        """(blob u8, offsets u64[n+1]): the src_paths as the C ABI takes them (include/vdf_b200.h, vdf_search); built
+        once per table"""
+        if self._blob is None:
+            enc = [os.fsencode(p) for p in self.paths]
+            off = np.zeros(len(enc) + 1, dtype=np.uint64)
+            if enc:
+                np.cumsum(np.fromiter(map(len, enc), dtype=np.uint64, count=len(enc)), out=off[1:])
+            blob = np.frombuffer(b"".join(enc), dtype=np.uint8) if enc else np.zeros(0, np.uint8)
+            self._blob = (blob if len(blob) else np.zeros(1, np.uint8), off)
+        return self._blob
 
     def __len__(self):
         return len(self.durations)
@@ -112,7 +125,9 @@ def _is_simple(b: bytes) -> bool:
 
 
 def sort_order(durations: np.ndarray, paths: Sequence[str]) -> np.ndarray:
-    """Permutation of Search::sort (search_algorithm.rs:55-61): stable, by (duration, src_path)."""
+    """Permutation of Search::sort (search_algorithm.rs:55-61): stable, by (duration, src_path).  Pure-Python statement
+    of the rule; the product path sorts natively (vdf_sort_order / vdf_search in csrc/host.cu) and
+    tests/test_host_layer.py holds the two against each other."""
     n = len(paths)
     if n == 0:
         return np.zeros(0, dtype=np.int64)
