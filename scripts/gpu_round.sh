@@ -70,6 +70,19 @@ if [[ $STEP == list5 ]]; then
   timeout 300 python bench.py --steps 3 --warmup 2 --variant 5 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_sv5_$i.json 2> gpurun_out/bench_sv5_$i.err; echo "bench search v5 rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_sv5_$i.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"
   done
 fi
+if [[ $STEP == ncu2 ]]; then
+  # launch list of the default bench command (shares of the step), then full captures of the dominant kernels at bench size
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"vdf|DeviceRadixSort|DeviceScan" -c 600 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary --e2e-steps 1 > gpurun_out/bench_under_ncu.json 2>&1; echo "ncu list rc=$?"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:vdf -c 400 --csv --log-file gpurun_out/launches_hash.csv \
+      python bench.py --workload hash --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu_hash.json 2>&1; echo "ncu list hash rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tc5 -c 1 -f -o gpurun_out/prof_hamming_tc5__self_1000000_x1 \
+      python bench.py --steps 1 --warmup 0 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming_tc5.log 2>&1; echo "ncu tc5 rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize_mma -c 1 -f -o gpurun_out/prof_resize_mma__stacks_256_1920x1080 \
+      python bench.py --workload hash --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_resize_mma.log 2>&1; echo "ncu resize rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_side -c 1 -f -o gpurun_out/prof_letterbox__stacks_256_1920x1080 \
+      python bench.py --workload hash --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
+fi
 if [[ $STEP == tc ]]; then
   timeout 600 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "tcgen05" > gpurun_out/pytest_tc.log 2>&1; echo "pytest tc rc=$?"; tail -25 gpurun_out/pytest_tc.log
   for v in 3 2; do

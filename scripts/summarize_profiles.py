@@ -38,11 +38,14 @@ KEEP = [
     "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
     "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
     "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+    "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "launch__cluster_size", "launch__cluster_max_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
 ]
 
 
-def launches(tag):
-    src = os.path.join(OUT, "launches.csv")
+def launches(tag, fname="launches.csv", suffix=""):
+    src = os.path.join(OUT, fname)
     if not os.path.exists(src):
         return
     rows = list(csv.reader(open(src)))
@@ -60,7 +63,7 @@ def launches(tag):
         t[1] += float(r[vi].replace(",", "")) * scale[r[ui]]
     allms = sum(t[1] for t in tot.values())
     ours = sum(t[1] for k, t in tot.items() if "vdf::" in k)
-    with open(os.path.join(PROF, f"{tag}_launches.txt"), "w") as f:
+    with open(os.path.join(PROF, f"{tag}_launches{suffix}.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised): compare SHARES\n")
         f.write(f"# command: see scripts/gpu_round.sh (ncu step); {sum(t[0] for t in tot.values())} launches captured, "
                 f"{allms:.3f} ms total, {100 * ours / allms:.2f}% in vdf:: kernels\n")
@@ -69,10 +72,23 @@ def launches(tag):
             f.write(f"{ms:12.3f} {100 * ms / allms:7.2f}% {n:8d}  {k[:140]}\n")
 
 
+def _bytes(v, unit):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    try:
+        return float(v.replace(",", "")) * scale[unit]
+    except Exception:
+        return None
+
+
 def ncu_summary(tag, rep, name):
+    """name may carry the workload key after a double underscore (prof_<kernel>__<key>.ncu-rep): then the DRAM traffic of
+    the captured launch goes to profiles/traffic.json[kernel][key] (bench.py's roofline.traffic)."""
     src = os.path.join(OUT, rep)
     if not os.path.exists(src):
         return
+    key = None
+    if "__" in name:
+        name, key = name.split("__", 1)
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     if len(rows) < 3:
@@ -82,6 +98,16 @@ def ncu_summary(tag, rep, name):
         f.write(f"# ncu --set full --clock-control none --import-source on, {rep}; selected metrics per captured launch\n")
         for vals in rows[2:]:
             rec = dict(zip(hdr, vals))
+            urec = dict(zip(hdr, units))
+            if key:
+                rd = _bytes(rec.get("dram__bytes_read.sum", ""), urec.get("dram__bytes_read.sum", ""))
+                wr = _bytes(rec.get("dram__bytes_write.sum", ""), urec.get("dram__bytes_write.sum", ""))
+                if rd is not None and wr is not None:
+                    tf = os.path.join(PROF, "traffic.json")
+                    t = json.load(open(tf)) if os.path.exists(tf) else {}
+                    kname = re.sub(r"<.*", "", re.sub(r"\(.*", "", rec.get("Kernel Name", "?"))).split("::")[-1].strip().split(" ")[-1]
+                    t.setdefault(kname, {})[key] = rd + wr
+                    json.dump(t, open(tf, "w"), indent=1, sort_keys=True)
             f.write(f"\n## {rec.get('Kernel Name', '?')}  grid {rec.get('Grid Size', '?')} block {rec.get('Block Size', '?')}\n")
             for h, u, v in zip(hdr, units, vals):
                 if any(h == k or (k in h and h.endswith(k)) for k in KEEP):
@@ -92,6 +118,9 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
+    for f in sorted(os.listdir(OUT)):
+        if f.startswith("launches_") and f.endswith(".csv"):
+            launches(tag, f, "_" + f[len("launches_"):-4])
     for rep in sorted(os.listdir(OUT)):
         if rep.endswith(".ncu-rep"):
             ncu_summary(tag, rep, rep[:-8].replace("prof_", ""))
@@ -102,6 +131,9 @@ def main():
         json.dump(recs, open(os.path.join(PROF, "microbench.json"), "w"), indent=1)
     for f in sorted(os.listdir(OUT)):
         if f.startswith("bench") and f.endswith(".json") and os.path.getsize(os.path.join(OUT, f)) > 10 and "under_ncu" not in f:
+            shutil.copy(os.path.join(OUT, f), os.path.join(PROF, f"{tag}_{f}"))
+    for f in sorted(os.listdir(OUT)):
+        if f.startswith("dist_check") and f.endswith(".log"):
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, f"{tag}_{f}"))
     for f in ("gpu.csv", "host.txt", "pytest_gpu.log", "smoke.log"):
         if os.path.exists(os.path.join(OUT, f)):
