@@ -140,6 +140,14 @@ int vdf_search_self(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint32_t* d
  * Vec<Vec<PathBuf>> after ret.reverse().  Runs on the GPU (parallel rounds of the greedy rule). */
 int vdf_group_greedy(vdf_ctx* ctx, uint64_t n, const vdf_edges* edges, vdf_groups* out);
 
+/* OPTIONAL, not reference behaviour: connected components of the edge graph by a lock-free GPU union-find -- what the
+ * app's DisjointSet (vid_dup_finder_app/src/app/disjoint_set.rs:22-44) computes for confirmed pairs, and a superset of
+ * every greedy group.  Same output convention as vdf_group_greedy (members ascending, the component's smallest entry
+ * last, groups by descending smallest entry).  With the context option "grouping" = 1, vdf_search and
+ * vdf_search_self_groups group this way instead of by the reference's rule (default 0). */
+int vdf_group_components(vdf_ctx* ctx, uint64_t n, const vdf_edges* edges, vdf_groups* out);
+int vdf_group_components_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64_t n_edges, vdf_groups* out);
+
 /* vdf_search_self + vdf_group_greedy with the edge list kept in HBM: what `search()` (video_dup_finder.rs:7-13)
  * calls.  Groups of fewer than 2 entries cannot occur (MatchGroup::new, match_group.rs:21-30). */
 int vdf_search_self_groups(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint32_t* dur_sorted, uint64_t n,

@@ -176,6 +176,38 @@ def group_from_edges(n: int, edges):
     return _csr(gp, mm, ng)
 
 
+def group_components(n: int, edges):
+    """Connected components of the edge graph, sequentially, in the way the app's DisjointSet accumulates pairs
+    (vid_dup_finder_app/src/app/disjoint_set.rs:22-44: new set / append / merge), written out in the library's
+    convention for its optional components mode: members ascending, the smallest entry last, groups by descending
+    smallest entry.  -> (group_ptr, member_idx)"""
+    set_of = {}
+    sets = []
+    for i, j in np.asarray(edges, dtype=np.uint64).reshape(-1, 2).tolist():
+        a, b = set_of.get(i), set_of.get(j)
+        if a is not None and a is b:
+            continue
+        if a is None and b is None:
+            t = {i, j}
+            sets.append(t)
+        elif a is None or b is None:
+            t = a if b is None else b
+            t.update((i, j))
+        else:
+            t, drop = (a, b) if len(a) >= len(b) else (b, a)
+            t.update(drop)
+            for v in drop:
+                set_of[v] = t
+            drop.clear()
+        set_of[i] = set_of[j] = t
+    comps = sorted((sorted(t) for t in sets if t), key=lambda c: -c[0])
+    gp, mm = [0], []
+    for c in comps:
+        mm.extend(c[1:] + c[:1])
+        gp.append(len(mm))
+    return np.array(gp, dtype=np.uint64), np.array(mm, dtype=np.uint64)
+
+
 def search_refs(cand_sorted, cand_dur_sorted, refs, ref_dur, tol_int: int):
     c = _hashes(cand_sorted)
     cd = np.ascontiguousarray(cand_dur_sorted, dtype=np.uint32)

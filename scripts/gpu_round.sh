@@ -83,6 +83,11 @@ if [[ $STEP == ncu2 ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_side -c 1 -f -o gpurun_out/prof_letterbox__stacks_256_1920x1080 \
       python bench.py --workload hash --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
 fi
+if [[ $STEP == big ]]; then
+  # BASELINE configs[3] and [4] sizes on one GPU: 100k queries x 10M-entry table; all-pairs over a 10M-hash corpus
+  timeout 900 python bench.py --workload refs --steps 3 --warmup 1 > gpurun_out/bench_refs_10m.json 2> gpurun_out/bench_refs_10m.err; echo "bench refs rc=$?"; tail -c 1200 gpurun_out/bench_refs_10m.json; tail -3 gpurun_out/bench_refs_10m.err
+  timeout 1200 python bench.py --n-hashes 10000000 --steps 1 --warmup 1 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_self_10m.json 2> gpurun_out/bench_self_10m.err; echo "bench 10M rc=$?"; tail -c 2500 gpurun_out/bench_self_10m.json; tail -3 gpurun_out/bench_self_10m.err
+fi
 if [[ $STEP == tc ]]; then
   timeout 600 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "tcgen05" > gpurun_out/pytest_tc.log 2>&1; echo "pytest tc rc=$?"; tail -25 gpurun_out/pytest_tc.log
   for v in 3 2; do

@@ -170,6 +170,42 @@ def test_greedy_rule_is_not_connected_components(ctx):
     assert gp.tolist() == [0, 2] and mm.tolist() == [1, 0]  # a-b-c with a!~c: {b, a}; c stays alone
 
 
+def test_components_mode_is_a_gpu_union_find(ctx):
+    """Optional grouping mode (the north-star's "GPU union-find"): connected components of the edge
+    graph, checked against the sequential DisjointSet walk (disjoint_set.rs:22-44) and against its own tests' cases
+    (disjoint_set.rs:217-335: one set, an extra item, two sets, contains_pair)."""
+    gp, mm = ctx.group_components(20, [[1, 2]])
+    assert gp.tolist() == [0, 2] and mm.tolist() == [2, 1]
+    gp, mm = ctx.group_components(20, [[1, 2], [2, 3]])  # test_insert_extra_item_to_single_set
+    assert gp.tolist() == [0, 3] and mm.tolist() == [2, 3, 1]
+    gp, mm = ctx.group_components(20, [[1, 2], [11, 12], [1, 3]])  # test_insert_two_sets / test_contains_pair
+    assert gp.tolist() == [0, 2, 5] and mm.tolist() == [12, 11, 2, 3, 1]
+    # a chain is ONE component but only {a, b} under the reference's rule
+    chain = [[0, 1], [1, 2]]
+    assert ctx.group_components(3, chain)[1].tolist() == [1, 2, 0] and ctx.group_greedy(3, chain)[1].tolist() == [1, 0]
+    rng = np.random.default_rng(21)
+    for n, ne in ((50, 30), (2000, 1500), (200000, 150000), (5000, 60000)):
+        e = rng.integers(0, n, (ne, 2)).astype(np.uint64)
+        e = np.unique(np.sort(e[e[:, 0] != e[:, 1]], axis=1), axis=0)
+        wgp, wmm = o.group_components(n, e)
+        ggp, gmm = ctx.group_components(n, e)
+        assert np.array_equal(ggp, wgp) and np.array_equal(gmm, wmm), (n, ne)
+    # through the public entry point: ctx option "grouping" = 1; star-shaped clusters come out identical in both modes
+    H, dur = _case(rng, 3000, 400, 60, [600])
+    paths = ["p/%05d" % i for i in range(len(dur))]
+    table = vdf.HashTable(H, dur, paths)
+    greedy = vdf.search(table, 0.35, ctx=ctx)
+    ctx.set_option("grouping", 1)
+    try:
+        comps = vdf.search(table, 0.35, ctx=ctx)
+        e = ctx.search_self(H, dur, 350)
+        wgp, wmm = o.group_components(len(dur), e)
+        assert [list(g.duplicates()) for g in comps] == [[paths[int(k)] for k in wmm[int(wgp[g]):int(wgp[g + 1])]] for g in range(len(wgp) - 1)]
+        assert sum(g.len() for g in comps) >= sum(g.len() for g in greedy)
+    finally:
+        ctx.set_option("grouping", 0)
+
+
 def test_long_dependency_chain(ctx):
     """a path graph 0-1-2-...-(L-1) needs L rounds of the parallel greedy rule: targets are the even vertices."""
     L = 600

@@ -27,7 +27,8 @@ EXPORTS = [
     "vdf_search_refs", "vdf_search_self_device", "vdf_search_refs_device", "vdf_group_greedy_device",
     "vdf_self_window_pairs", "vdf_free_edges", "vdf_free_groups", "vdf_free_csr", "vdf_hash_stacks",
     "vdf_hash_stacks_device", "vdf_hash_stacks_small_device", "vdf_hash_from_small",
-    "vdf_sort_order", "vdf_search", "vdf_search_with_references", "vdf_ctx_last_phases",
+    "vdf_sort_order", "vdf_search", "vdf_search_with_references", "vdf_ctx_last_phases", "vdf_group_components",
+    "vdf_group_components_device",
 ]
 
 
@@ -97,6 +98,8 @@ def lib() -> C.CDLL:
     L.vdf_ctx_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64), i32]
     L.vdf_search_self.argtypes = [vp, vp, vp, u64, u32, C.POINTER(Edges)]
     L.vdf_group_greedy.argtypes = [vp, u64, C.POINTER(Edges), C.POINTER(Groups)]
+    L.vdf_group_components.argtypes = [vp, u64, C.POINTER(Edges), C.POINTER(Groups)]
+    L.vdf_group_components_device.argtypes = [vp, u64, vp, u64, C.POINTER(Groups)]
     L.vdf_search_self_groups.argtypes = [vp, vp, vp, u64, u32, C.POINTER(Groups)]
     L.vdf_search_refs.argtypes = [vp, vp, vp, u64, vp, vp, u64, u32, C.POINTER(Csr)]
     L.vdf_search_self_device.argtypes = [vp, vp, vp, u64, u32, vp, u64, C.POINTER(u64)]
@@ -225,6 +228,14 @@ class Context:
         st = Edges(len(e), e.ctypes.data_as(C.POINTER(C.c_uint64)))
         g = Groups()
         self._check(lib().vdf_group_greedy(self._h, int(n), C.byref(st), C.byref(g)))
+        return self._groups(g)
+
+    def group_components(self, n: int, edges):
+        """connected components of the edge graph (optional mode, NOT the reference's grouping rule)"""
+        e = np.ascontiguousarray(edges, dtype=np.uint64).reshape(-1, 2)
+        st = Edges(len(e), e.ctypes.data_as(C.POINTER(C.c_uint64)))
+        g = Groups()
+        self._check(lib().vdf_group_components(self._h, int(n), C.byref(st), C.byref(g)))
         return self._groups(g)
 
     def search_self_groups(self, hash_sorted, dur_sorted, tol_int: int):

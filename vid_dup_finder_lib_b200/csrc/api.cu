@@ -96,6 +96,7 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     else if (k == "initial_edges" && value > 0) ctx->initial_edges = (uint64_t)value;
     else if (k == "search_variant" && (value >= 0 && value <= 5)) ctx->search_variant = (int)value;
     else if (k == "tc_chunk" && value >= 0 && value <= 65535) ctx->tc_chunk = (uint32_t)value;
+    else if (k == "grouping" && (value == 0 || value == 1)) ctx->grouping = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;
     else {
         ctx->err = "unknown option or bad value: " + k;
@@ -306,7 +307,39 @@ int vdf_search_self_groups(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint
     if (!out || (n && (!hash_sorted || !dur_sorted))) return VDF_ERR_INVALID;
     uint64_t ne = 0;
     if (n) VDF_TRY(self_keys_from_host(ctx, hash_sorted, dur_sorted, n, tol_int, &ne));
-    return group_greedy_device(ctx, n, ctx->keys_a.as<uint64_t>(), ne, out);
+    return group_device(ctx, n, ctx->keys_a.as<uint64_t>(), ne, out);
+}
+
+static int edges_to_device(vdf_ctx* ctx, uint64_t n, const vdf_edges* edges, uint64_t* ne_out) {
+    const uint64_t ne = edges->n;
+    std::vector<uint64_t> keys(ne);
+    for (uint64_t k = 0; k < ne; ++k) {
+        const uint64_t i = edges->ij[2 * k], j = edges->ij[2 * k + 1];
+        if (i >= j || j >= n) {
+            ctx->err = "edge list must hold i < j < n";
+            return VDF_ERR_INVALID;
+        }
+        keys[k] = (i << 32) | j;
+    }
+    if (!std::is_sorted(keys.begin(), keys.end())) std::sort(keys.begin(), keys.end());
+    VDF_TRY(upload(ctx, ctx->keys_b, keys.data(), ne * 8));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *ne_out = ne;
+    return VDF_OK;
+}
+
+int vdf_group_components(vdf_ctx* ctx, uint64_t n, const vdf_edges* edges, vdf_groups* out) {
+    VDF_TRY(enter(ctx));
+    if (!out || !edges || (edges->n && !edges->ij)) return VDF_ERR_INVALID;
+    uint64_t ne = 0;
+    VDF_TRY(edges_to_device(ctx, n, edges, &ne));
+    return group_components_device(ctx, n, ctx->keys_b.as<uint64_t>(), ne, out);
+}
+
+int vdf_group_components_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64_t n_edges, vdf_groups* out) {
+    VDF_TRY(enter(ctx));
+    if (!out) return VDF_ERR_INVALID;
+    return group_components_device(ctx, n, d_keys, n_edges, out);
 }
 
 int vdf_search_refs(vdf_ctx* ctx, const uint64_t* cand_sorted, const uint32_t* cand_dur_sorted, uint64_t n_cand,

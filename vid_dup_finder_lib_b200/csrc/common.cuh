@@ -96,6 +96,7 @@ struct vdf_ctx {
                              // tiles in HBM; 4: the same on CTA pairs; 5 (default): CTA pairs, packed tiles (search_tc.cu)
     int hash_variant = 0;
     uint32_t tc_chunk = 0;  // column super-tiles per CTA-pair work unit (0: automatic)
+    int grouping = 0;       // 0: the reference's greedy rule (parity); 1: connected components (GPU union-find, group.cu)
     uint64_t launches = 0, h2d = 0, d2h = 0;
     double phase_ms[4] = {0, 0, 0, 0};  // last vdf_search*: host sort, gather + H2D enqueue, device, index remap (host.cu)
     // device time of the dominant kernels (CUDA events on `stream`): 0 hamming tiles, 1 resize, 2 letterbox, 3 dct+pack
@@ -177,6 +178,11 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
 int tc5_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& tiles, DevBuf& pc, DevBuf& pcmin);
 // group.cu
 int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, vdf_groups* out);
+int group_components_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64_t n_edges, vdf_groups* out);
+inline int group_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, vdf_groups* out) {
+    return ctx->grouping == 1 ? group_components_device(ctx, n, d_keys_sorted, n_edges, out)
+                              : group_greedy_device(ctx, n, d_keys_sorted, n_edges, out);
+}
 // hash.cu
 int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_desc* desc, uint32_t n, int cropdetect,
                        uint64_t* d_out_hash, uint8_t* d_out_small, int32_t* out_status, uint32_t* out_crop);

@@ -10,6 +10,7 @@
 // targets from the start, so the number of rounds is the longest dependency chain (2-3 for duplicate clusters).
 // Output order follows the reference: members ascending, the target last, groups by DESCENDING target
 // (ret.reverse(), search_algorithm.rs:136,167).
+#include <algorithm>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -100,6 +101,49 @@ static int empty_groups(vdf_groups* out) {
     return (out->group_ptr && out->member_idx) ? VDF_OK : VDF_ERR_ALLOC;
 }
 
+// nm keys (~root << 32 | vertex) in g_mk -> sorted -> CSR (members ascending, the root last, groups by descending root)
+// -> host arrays
+static int finish_groups(vdf_ctx* ctx, unsigned long long nm, vdf_groups* out) {
+    const int B = 256;
+    auto blocks = [&](uint64_t items) { return (unsigned)((items + B - 1) / B); };
+    cudaStream_t st = ctx->stream;
+    if (nm == 0) return empty_groups(out);
+    VDF_TRY(sort_keys(ctx, ctx->g_mk.as<uint64_t>(), ctx->g_mks.as<uint64_t>(), nm));
+
+    VDF_ALLOC(ctx, ctx->g_flag.ensure(nm * 4));
+    VDF_ALLOC(ctx, ctx->g_scan.ensure(nm * 4));
+    VDF_ALLOC(ctx, ctx->g_gp.ensure((nm + 1) * 8));
+    VDF_ALLOC(ctx, ctx->g_mem.ensure(2 * nm * 8));
+    group_flag_kernel<<<blocks(nm), B, 0, st>>>(ctx->g_mks.as<uint64_t>(), nm, ctx->g_flag.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    size_t tmp = 0;
+    VDF_CUDA(ctx, cub::DeviceScan::InclusiveSum(nullptr, tmp, ctx->g_flag.as<uint32_t>(), ctx->g_scan.as<uint32_t>(),
+                                                (size_t)nm, st));
+    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
+    VDF_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->sort_tmp.p, tmp, ctx->g_flag.as<uint32_t>(),
+                                                ctx->g_scan.as<uint32_t>(), (size_t)nm, st));
+    ctx->launches += 1;
+    group_csr_kernel<<<blocks(nm), B, 0, st>>>(ctx->g_mks.as<uint64_t>(), ctx->g_scan.as<uint32_t>(), nm,
+                                               ctx->g_gp.as<uint64_t>(), ctx->g_mem.as<uint64_t>());
+    VDF_LAUNCHED(ctx);
+    uint32_t ng = 0;
+    VDF_CUDA(ctx, cudaMemcpyAsync(&ng, ctx->g_scan.as<uint32_t>() + (nm - 1), 4, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaStreamSynchronize(st));
+
+    out->n_groups = ng;
+    out->group_ptr = (uint64_t*)malloc((size_t)(ng + 1) * 8);
+    out->member_idx = (uint64_t*)malloc((size_t)(nm + ng) * 8);
+    if (!out->group_ptr || !out->member_idx) {
+        ctx->err = "host allocation failed";
+        return VDF_ERR_ALLOC;
+    }
+    VDF_CUDA(ctx, cudaMemcpyAsync(out->group_ptr, ctx->g_gp.p, (size_t)(ng + 1) * 8, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaMemcpyAsync(out->member_idx, ctx->g_mem.p, (size_t)(nm + ng) * 8, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->d2h += (size_t)(ng + 1) * 8 + (size_t)(nm + ng) * 8;
+    return VDF_OK;
+}
+
 int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64_t ne, vdf_groups* out) {
     out->n_groups = 0;
     out->group_ptr = nullptr;
@@ -162,41 +206,83 @@ int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64
     unsigned long long nm = 0;
     VDF_CUDA(ctx, cudaMemcpyAsync(&nm, cnt + 3, 8, cudaMemcpyDeviceToHost, st));
     VDF_CUDA(ctx, cudaStreamSynchronize(st));
-    if (nm == 0) return empty_groups(out);
-    VDF_TRY(sort_keys(ctx, ctx->g_mk.as<uint64_t>(), ctx->g_mks.as<uint64_t>(), nm));
+    return finish_groups(ctx, nm, out);
+}
 
-    VDF_ALLOC(ctx, ctx->g_flag.ensure(nm * 4));
-    VDF_ALLOC(ctx, ctx->g_scan.ensure(nm * 4));
-    VDF_ALLOC(ctx, ctx->g_gp.ensure((nm + 1) * 8));
-    VDF_ALLOC(ctx, ctx->g_mem.ensure(2 * nm * 8));
-    group_flag_kernel<<<blocks(nm), B, 0, st>>>(ctx->g_mks.as<uint64_t>(), nm, ctx->g_flag.as<uint32_t>());
-    VDF_LAUNCHED(ctx);
-    size_t tmp = 0;
-    VDF_CUDA(ctx, cub::DeviceScan::InclusiveSum(nullptr, tmp, ctx->g_flag.as<uint32_t>(), ctx->g_scan.as<uint32_t>(),
-                                                (size_t)nm, st));
-    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
-    VDF_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->sort_tmp.p, tmp, ctx->g_flag.as<uint32_t>(),
-                                                ctx->g_scan.as<uint32_t>(), (size_t)nm, st));
-    ctx->launches += 1;
-    group_csr_kernel<<<blocks(nm), B, 0, st>>>(ctx->g_mks.as<uint64_t>(), ctx->g_scan.as<uint32_t>(), nm,
-                                               ctx->g_gp.as<uint64_t>(), ctx->g_mem.as<uint64_t>());
-    VDF_LAUNCHED(ctx);
-    uint32_t ng = 0;
-    VDF_CUDA(ctx, cudaMemcpyAsync(&ng, ctx->g_scan.as<uint32_t>() + (nm - 1), 4, cudaMemcpyDeviceToHost, st));
-    VDF_CUDA(ctx, cudaStreamSynchronize(st));
-
-    out->n_groups = ng;
-    out->group_ptr = (uint64_t*)malloc((size_t)(ng + 1) * 8);
-    out->member_idx = (uint64_t*)malloc((size_t)(nm + ng) * 8);
-    if (!out->group_ptr || !out->member_idx) {
-        ctx->err = "host allocation failed";
-        return VDF_ERR_ALLOC;
+// ------------------------------------------------------------------------------------------------ connected components
+// The north-star's "GPU union-find" as an OPTIONAL grouping mode (ctx option "grouping" = 1).
+// It is NOT what the reference's search does (a chain a-b-c with a !~ c is one component but the greedy rule returns
+// {a, b} only); it is what the app's DisjointSet (vid_dup_finder_app/src/app/disjoint_set.rs:22-44) computes for confirmed
+// pairs.  Lock-free union-find: every edge hooks the larger root under the smaller one with atomicCAS (so the root of a
+// component is its smallest vertex), finds use path halving.  Output convention is the greedy mode's: members ascending,
+// the root last, groups by descending root -- for star-shaped clusters both modes return identical groups.
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t v) {
+    uint32_t p = parent[v];
+    while (p != v) {
+        const uint32_t g = parent[p];
+        if (g != p) parent[v] = g;  // path halving (benign race: only ever replaces a parent by an ancestor)
+        v = p;
+        p = g;
     }
-    VDF_CUDA(ctx, cudaMemcpyAsync(out->group_ptr, ctx->g_gp.p, (size_t)(ng + 1) * 8, cudaMemcpyDeviceToHost, st));
-    VDF_CUDA(ctx, cudaMemcpyAsync(out->member_idx, ctx->g_mem.p, (size_t)(nm + ng) * 8, cudaMemcpyDeviceToHost, st));
+    return v;
+}
+
+__global__ void uf_init_kernel(uint32_t* __restrict__ parent, uint64_t n) {
+    uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (v < n) parent[v] = (uint32_t)v;
+}
+
+__global__ void uf_union_kernel(const uint64_t* __restrict__ keys, uint64_t ne, uint32_t* parent) {
+    uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    uint32_t a = uf_find(parent, (uint32_t)(keys[e] >> 32)), b = uf_find(parent, (uint32_t)keys[e]);
+    while (a != b) {
+        if (a > b) {
+            const uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        const uint32_t old = atomicCAS(&parent[b], b, a);  // hook root b under the smaller root a
+        if (old == b) break;
+        b = uf_find(parent, old);  // b was hooked by someone else meanwhile: continue from its new root
+        a = uf_find(parent, a);
+    }
+}
+
+__global__ void uf_member_keys_kernel(uint32_t* parent, uint64_t n, uint64_t* __restrict__ mk,
+                                      unsigned long long* __restrict__ count) {
+    uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t r = uf_find(parent, (uint32_t)v);
+    if (r != (uint32_t)v) mk[atomicAdd(count, 1ull)] = ((uint64_t)(~r) << 32) | v;
+}
+
+int group_components_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64_t ne, vdf_groups* out) {
+    out->n_groups = 0;
+    out->group_ptr = nullptr;
+    out->member_idx = nullptr;
+    if (ne == 0 || n == 0) return empty_groups(out);
+    const int B = 256;
+    auto blocks = [&](uint64_t items) { return (unsigned)((items + B - 1) / B); };
+    cudaStream_t st = ctx->stream;
+    VDF_ALLOC(ctx, ctx->g_parent.ensure(n * 4));
+    VDF_ALLOC(ctx, ctx->misc.ensure(64));
+    unsigned long long* cnt = ctx->misc.as<unsigned long long>() + 4;
+    VDF_CUDA(ctx, cudaMemsetAsync(cnt, 0, 32, st));
+    uint32_t* parent = ctx->g_parent.as<uint32_t>();
+    uf_init_kernel<<<blocks(n), B, 0, st>>>(parent, n);
+    VDF_LAUNCHED(ctx);
+    uf_union_kernel<<<blocks(ne), B, 0, st>>>(d_keys, ne, parent);
+    VDF_LAUNCHED(ctx);
+    const uint64_t cap = std::min<uint64_t>(n, 2 * ne);  // every non-root vertex has an edge
+    VDF_ALLOC(ctx, ctx->g_mk.ensure(cap * 8));
+    VDF_ALLOC(ctx, ctx->g_mks.ensure(cap * 8));
+    uf_member_keys_kernel<<<blocks(n), B, 0, st>>>(parent, n, ctx->g_mk.as<uint64_t>(), cnt + 3);
+    VDF_LAUNCHED(ctx);
+    unsigned long long nm = 0;
+    VDF_CUDA(ctx, cudaMemcpyAsync(&nm, cnt + 3, 8, cudaMemcpyDeviceToHost, st));
     VDF_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->d2h += (size_t)(ng + 1) * 8 + (size_t)(nm + ng) * 8;
-    return VDF_OK;
+    return finish_groups(ctx, nm, out);
 }
 
 }  // namespace vdf

@@ -262,7 +262,7 @@ int vdf_search(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, 
             },
             &ne));
     }
-    VDF_TRY(vdf::group_greedy_device(ctx, n, ctx->keys_a.as<uint64_t>(), ne, out));
+    VDF_TRY(vdf::group_device(ctx, n, ctx->keys_a.as<uint64_t>(), ne, out));
     double t3 = now_ms();
     // sorted positions -> the caller's indices (what `entries[i].value.src_path()` resolves to in the reference)
     const uint64_t total = out->n_groups ? out->group_ptr[out->n_groups] : 0;
