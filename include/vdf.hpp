@@ -288,6 +288,24 @@ inline std::vector<MatchGroup> search_with_references(const std::vector<VideoHas
     return out;
 }
 
+// ---- the app's hash cache file (format: see vdf_cache_load in vdf_b200.h) ------------------------
+// the Ok(VideoHash) entries of a cache file, in file order -- what the app feeds `search` after loading its cache
+// (app_fns.rs:428-482); cached errors are skipped
+inline std::vector<VideoHash> load_hash_cache(const std::string& file) {
+    vdf_cache c{};
+    const int rc = vdf_cache_load(file.c_str(), &c);
+    if (rc != VDF_OK) throw DeviceError(rc, "cannot read hash cache " + file);
+    std::vector<VideoHash> out;
+    for (uint64_t i = 0; i < c.n; ++i) {
+        if (c.kind[i] != VDF_CACHE_OK) continue;
+        std::array<uint64_t, HASH_WORDS> w;
+        std::memcpy(w.data(), c.hashes + i * HASH_WORDS, HASH_WORDS * 8);
+        out.emplace_back(w, std::string(c.src_blob + c.src_off[i], c.src_blob + c.src_off[i + 1]), c.durations[i]);
+    }
+    vdf_free_cache(&c);
+    return out;
+}
+
 // ---- hashing (video_hash_builder.rs) ----------------------------------------------------------------------------
 struct CreationOptions {  // video_hash_builder.rs:17-63
     double skip_forward_amount = DEFAULT_VID_HASH_SKIP_FORWARD;

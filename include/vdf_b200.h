@@ -50,6 +50,8 @@ extern "C" {
 #define VDF_ERR_INVALID (-3)       /* bad argument */
 #define VDF_ERR_EDGE_OVERFLOW (-4) /* more matches than the edge buffer may grow to (see "max_edges") */
 #define VDF_ERR_NO_DEVICE (-5)     /* no usable sm_100 device */
+#define VDF_ERR_IO (-6)            /* a cache file could not be opened, written or renamed */
+#define VDF_ERR_FORMAT (-7)        /* a cache file is truncated or not in the expected encoding */
 
 /* per-stack status, mirrors vid_dup_finder_lib::Error (video_hashing/mod.rs:17-28) */
 #define VDF_STACK_OK 0
@@ -206,6 +208,41 @@ int vdf_search_with_references(vdf_ctx* ctx, const uint64_t* ref_hashes, const u
 /* Wall-clock milliseconds of the phases of the last vdf_search / vdf_search_with_references call:
  * [0] host sort, [1] gather into pinned memory + H2D enqueue, [2] device work incl. result D2H, [3] index remap. */
 int vdf_ctx_last_phases(const vdf_ctx* ctx, double* ms4);
+
+/* ---- the application's hash cache file (host code, csrc/cache.cu) ----------------------------------------------
+ * The app stores HashMap<PathBuf, MtimeCacheEntry<Result<VideoHash, Error>>> with bincode 2 `standard()`
+ * (vid_dup_finder_app/src/video_hash_filesystem_cache/generic_filesystem_cache/base_fs_cache.rs:26,106-112,192-196;
+ * processing_fs_cache.rs:23-27; generic_cache_if.rs:22-23; video_hash.rs:26-32; video_hashing/mod.rs:17-28) and loads it
+ * whole before every search.  vdf_cache_load reads such a file into struct-of-arrays, entry i in file order:
+ *   kind[i]                     VDF_CACHE_OK or which Error the entry caches
+ *   hashes[i][16], durations[i] the VideoHash (zero for error entries)
+ *   key_*                       the map key (the file's path); src_*: VideoHash.src_path (equal to the key when the app
+ *                               wrote the file, kept separately so that a load/save round trip is byte-faithful)
+ *   msg_*                       the String of Error::VidProc
+ *   mtime_secs/nanos[i]         MtimeCacheEntry.cache_mtime as serde writes a SystemTime
+ * so hashes/durations/src_* of the VDF_CACHE_OK entries go to vdf_search without a per-entry object ever existing.
+ * vdf_cache_save writes the same encoding (temporary file + rename, like base_fs_cache.rs:84,157). */
+#define VDF_CACHE_OK 0
+#define VDF_CACHE_ERR_NOT_VIDEO 1         /* Error::NotVideo */
+#define VDF_CACHE_ERR_VIDPROC 2           /* Error::VidProc(String) */
+#define VDF_CACHE_ERR_NOT_ENOUGH_FRAMES 3 /* Error::NotEnoughFrames */
+typedef struct {
+    uint64_t n;
+    int32_t* kind;
+    uint64_t* hashes;
+    uint32_t* durations;
+    char* key_blob;
+    uint64_t* key_off; /* n + 1 */
+    char* src_blob;
+    uint64_t* src_off; /* n + 1 */
+    char* msg_blob;
+    uint64_t* msg_off; /* n + 1 */
+    uint64_t* mtime_secs;
+    uint32_t* mtime_nanos;
+} vdf_cache;
+int vdf_cache_load(const char* file, vdf_cache* out);
+int vdf_cache_save(const char* file, const vdf_cache* cache);
+void vdf_free_cache(vdf_cache* cache);
 
 void vdf_free_edges(vdf_edges* e);
 void vdf_free_groups(vdf_groups* g);

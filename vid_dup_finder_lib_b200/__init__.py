@@ -6,6 +6,7 @@ from ._ffi import Context, VdfError, default_context
 from .crop import Crop
 from .definitions import (DEFAULT_SEARCH_TOLERANCE, DEFAULT_VID_HASH_DURATION, DEFAULT_VID_HASH_SKIP_FORWARD,
                           TOLERANCE_SCALING_FACTOR, Cropdetect)
+from .hash_cache import CacheMetadata, HashCache, load_hash_cache, save_hash_cache
 from .match_group import MatchGroup, TooFewEntries
 from .search import search, search_with_references
 from .video_hash import HashTable, VideoHash
@@ -15,5 +16,5 @@ __all__ = [
     "VideoHash", "VideoHashBuilder", "CreationOptions", "search", "search_with_references", "MatchGroup", "Error",
     "NotVideo", "VidProc", "NotEnoughFrames", "Cropdetect", "DEFAULT_SEARCH_TOLERANCE", "DEFAULT_VID_HASH_DURATION",
     "DEFAULT_VID_HASH_SKIP_FORWARD", "TOLERANCE_SCALING_FACTOR", "HashTable", "Crop", "Context", "VdfError",
-    "default_context", "TooFewEntries",
+    "default_context", "TooFewEntries", "HashCache", "CacheMetadata", "load_hash_cache", "save_hash_cache",
 ]

@@ -28,7 +28,7 @@ EXPORTS = [
     "vdf_self_window_pairs", "vdf_free_edges", "vdf_free_groups", "vdf_free_csr", "vdf_hash_stacks",
     "vdf_hash_stacks_device", "vdf_hash_stacks_small_device", "vdf_hash_from_small",
     "vdf_sort_order", "vdf_search", "vdf_search_with_references", "vdf_ctx_last_phases", "vdf_group_components",
-    "vdf_group_components_device",
+    "vdf_group_components_device", "vdf_cache_load", "vdf_cache_save", "vdf_free_cache",
 ]
 
 
