@@ -12,6 +12,7 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -381,6 +382,79 @@ class VideoHashBuilder {  // video_hash_builder.rs:70-83; decoding (:85-167) sta
   private:
     Context& ctx_;
     CreationOptions options_;
+};
+
+// Batch-oriented hashing: the per-file rayon loop of the app (video_hash_filesystem_cache.rs:237-257)
+// becomes "decode threads push(), a collector takes results"; the library batches (vdf_pipeline_*, csrc/pipeline.cu).
+// push() is thread-safe and copies the frames into pinned memory before returning.
+class HashPipeline {
+  public:
+    struct Item {
+        std::string src_path;
+        HashResult result;
+    };
+    HashPipeline(Context& ctx, CreationOptions options = {}, uint32_t max_batch_stacks = 64, uint64_t batch_bytes = 1ull << 30) {
+        if (options.cropdetect == Cropdetect::Motion) throw std::invalid_argument("Cropdetect::Motion is outside the GPU hot path");
+        const int rc = vdf_pipeline_create(ctx.get(), max_batch_stacks, batch_bytes,
+                                           options.cropdetect == Cropdetect::None ? VDF_CROPDETECT_NONE : VDF_CROPDETECT_LETTERBOX, &p_);
+        if (rc != VDF_OK) throw DeviceError(rc, "vdf_pipeline_create");
+    }
+    ~HashPipeline() { vdf_pipeline_destroy(p_); }
+    HashPipeline(const HashPipeline&) = delete;
+    HashPipeline& operator=(const HashPipeline&) = delete;
+
+    void push(const std::vector<GrayFrame>& frames, std::string src_path, uint32_t duration_secs) {
+        const size_t nf = std::min<size_t>(frames.size(), DCT_SIZE);  // take(DCT_SIZE), video_hash_builder.rs:164
+        std::vector<const uint8_t*> ptr(nf ? nf : 1, nullptr);
+        uint32_t flags = 0, w = 0, h = 0, pitch = 0;
+        for (size_t f = 0; f < nf; ++f) {
+            ptr[f] = frames[f].data;
+            if (f == 0) w = frames[f].width, h = frames[f].height, pitch = frames[f].pitch;
+            else if (frames[f].width != w || frames[f].height != h || frames[f].pitch != pitch) {
+                if (frames[f].width != w || frames[f].height != h) flags = VDF_STACK_FLAG_MIXED_SIZES;  // :169-186
+                else throw std::invalid_argument("HashPipeline::push: frames of one stack must share a pitch");
+            }
+        }
+        uint64_t tag;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            tag = meta_.size();
+            meta_.emplace_back(std::move(src_path), duration_secs);
+        }
+        const int rc = vdf_pipeline_push(p_, tag, ptr.data(), (uint32_t)nf, w, h, pitch, flags);
+        if (rc != VDF_OK) throw DeviceError(rc, vdf_pipeline_error(p_));
+    }
+    void flush() {
+        const int rc = vdf_pipeline_flush(p_);
+        if (rc != VDF_OK) throw DeviceError(rc, vdf_pipeline_error(p_));
+    }
+    // finished videos, in completion order; wait = block until at least one is ready (or nothing is in flight)
+    std::vector<Item> results(bool wait = false) {
+        std::vector<vdf_pipeline_result> buf(1024);
+        uint32_t n = 0;
+        const int rc = vdf_pipeline_poll(p_, buf.data(), (uint32_t)buf.size(), &n, wait ? 1 : 0);
+        if (rc != VDF_OK) throw DeviceError(rc, vdf_pipeline_error(p_));
+        std::vector<Item> out;
+        std::lock_guard<std::mutex> lk(m_);
+        for (uint32_t k = 0; k < n; ++k) {
+            const auto& meta = meta_[buf[k].tag];
+            if (buf[k].status == VDF_STACK_OK) {
+                std::array<uint64_t, HASH_WORDS> w;
+                std::memcpy(w.data(), buf[k].hash, sizeof w);
+                out.push_back({meta.first, VideoHash(w, meta.first, meta.second)});
+            } else if (buf[k].status == VDF_STACK_VIDPROC) {
+                out.push_back({meta.first, Error{Error::VidProc, "frames not all same size"}});
+            } else {
+                out.push_back({meta.first, Error{Error::NotEnoughFrames, ""}});
+            }
+        }
+        return out;
+    }
+
+  private:
+    vdf_hash_pipeline* p_ = nullptr;
+    std::mutex m_;
+    std::vector<std::pair<std::string, uint32_t>> meta_;
 };
 
 }  // namespace vdf

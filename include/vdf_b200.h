@@ -271,6 +271,31 @@ int vdf_hash_stacks_small_device(vdf_ctx* ctx, const uint8_t* d_frames, const vd
 /* Hash from an already-resized cube (Dct3d::from_images + hash_bits only). */
 int vdf_hash_from_small(vdf_ctx* ctx, const uint8_t* small /* host, n x 4096 */, uint32_t n, uint64_t* out_hash);
 
+/* ---- batch-oriented hashing (csrc/pipeline.cu) ------------------------------------------------------------------
+ * Replaces the app's per-file loop (video_hash_filesystem_cache.rs:237-257: one rayon worker decodes AND hashes one
+ * file): decode threads push their <= 16 decoded gray frames, a worker thread owned by the pipeline hashes them in
+ * batches through vdf_hash_stacks, a collector polls results.  vdf_pipeline_push may be called from any number of
+ * threads and copies the frames into pinned memory before it returns (the caller may reuse its buffers); it blocks
+ * while both batch buffers are full.  While the pipeline exists the context must not be used by other threads.
+ * status/hash/crop of a result are exactly vdf_hash_stacks' outputs for that stack; a negative status is a library
+ * error (vdf_pipeline_error). */
+typedef struct vdf_hash_pipeline vdf_hash_pipeline;
+typedef struct {
+    uint64_t tag;      /* the caller's id of the video */
+    int32_t status;    /* VDF_STACK_OK / VDF_STACK_NOT_ENOUGH_FRAMES / VDF_STACK_VIDPROC, or a negative VDF_ERR_* */
+    uint32_t crop[4];  /* left, right, top, bottom */
+    uint64_t hash[16]; /* VideoHash.hash */
+} vdf_pipeline_result;
+int vdf_pipeline_create(vdf_ctx* ctx, uint32_t max_batch_stacks, uint64_t batch_bytes, int cropdetect, vdf_hash_pipeline** out);
+int vdf_pipeline_push(vdf_hash_pipeline* p, uint64_t tag, const uint8_t* const* frames, uint32_t n_frames, uint32_t width,
+                      uint32_t height, uint32_t pitch, uint32_t flags);
+/* submit the partly filled batch and wait until everything pushed so far has a result */
+int vdf_pipeline_flush(vdf_hash_pipeline* p);
+/* take up to max_results finished results; wait != 0 blocks until there is one (or nothing is in flight) */
+int vdf_pipeline_poll(vdf_hash_pipeline* p, vdf_pipeline_result* out, uint32_t max_results, uint32_t* n_out, int wait);
+const char* vdf_pipeline_error(const vdf_hash_pipeline* p);
+void vdf_pipeline_destroy(vdf_hash_pipeline* p);
+
 const char* vdf_version(void);
 
 #ifdef __cplusplus

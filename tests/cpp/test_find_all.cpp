@@ -3,6 +3,7 @@
 // Build + run: see tests/test_cpp_host_layer.py (needs a B200: the host layer has no CPU fallback).
 #include <cstdio>
 #include <random>
+#include <thread>
 
 #include "vdf.hpp"
 
@@ -167,6 +168,19 @@ static int test_hash_frames(Context& ctx) {
     CHECK(std::get<VideoHash>(ra).hamming_distance(std::get<VideoHash>(rb)) == 0);  // the crop removes the bars exactly
     auto groups = search({std::get<VideoHash>(ra), std::get<VideoHash>(rb)}, DEFAULT_SEARCH_TOLERANCE, ctx);
     CHECK(groups.size() == 1 && groups[0].len() == 2);
+    {  // the same two videos (plus a short one) through the batch pipeline, pushed from two threads
+        HashPipeline pipe(ctx, {}, 2, (uint64_t)16 * (W + 40) * (H + 30) * 2 + 4096);
+        std::thread t1([&] { pipe.push(fa, "a.mp4", 30); pipe.push(std::vector<GrayFrame>(fa.begin(), fa.begin() + 5), "short.mp4", 1); });
+        std::thread t2([&] { pipe.push(fb, "b.mp4", 31); });
+        t1.join(), t2.join();
+        pipe.flush();
+        auto items = pipe.results();
+        CHECK(items.size() == 3);
+        for (const auto& it : items) {
+            if (it.src_path == "short.mp4") CHECK(std::holds_alternative<Error>(it.result) && std::get<Error>(it.result).kind == Error::NotEnoughFrames);
+            else CHECK(std::holds_alternative<VideoHash>(it.result) && std::get<VideoHash>(it.result).hamming_distance(std::get<VideoHash>(ra)) == 0);
+        }
+    }
     fa.pop_back();
     auto rc = builder.hash_frames(fa, "c.mp4", 30);
     CHECK(std::holds_alternative<Error>(rc) && std::get<Error>(rc).kind == Error::NotEnoughFrames);

@@ -20,7 +20,7 @@ def _build():
     if os.path.exists(EXE) and all(os.path.getmtime(d) <= os.path.getmtime(EXE) for d in deps):
         return
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-L", PKG,
-                           "-lvdf_b200", f"-Wl,-rpath,{PKG}", "-o", EXE])
+                           "-lvdf_b200", "-lpthread", f"-Wl,-rpath,{PKG}", "-o", EXE])
 
 
 def test_cpp_host_layer_compiles_and_fails_loudly_without_gpu():

@@ -183,6 +183,63 @@ def test_ragged_batch_and_pitched_frames(ctx):
     assert np.array_equal(got2, want)
 
 
+def test_hash_pipeline_many_producers(ctx):
+    """decode threads push stacks, the library batches them (here: tiny batches, so producers block and
+    batches alternate), results come back tagged; every hash / error equals the direct call's and the oracle's."""
+    import threading
+
+    from vid_dup_finder_lib_b200.pipeline import HashPipeline
+
+    sizes = [(160, 90), (64, 48), (320, 180), (33, 17)]
+    stacks = {}
+    for tag in range(48):
+        w, h = sizes[tag % len(sizes)]
+        st = synth.frame_stacks(1, w, h, seed=100 + tag)[0].numpy()
+        if tag % 11 == 5:
+            stacks[tag] = list(st[:9])  # NotEnoughFrames
+        elif tag % 11 == 7:
+            stacks[tag] = list(st[:8]) + list(synth.frame_stacks(1, w + 2, h, seed=tag)[0].numpy()[:8])  # VidProc
+        elif tag % 11 == 9:
+            stacks[tag] = [np.asfortranarray(f) for f in st] + [st[0]] * 3  # > 16 frames (take(16)), non-contiguous arrays
+        else:
+            stacks[tag] = list(st)
+    got = {}
+    with HashPipeline(vdf.CreationOptions(), ctx=ctx, max_batch_stacks=5, batch_bytes=3 * 16 * 320 * 180 + 4096) as p:
+        def producer(k):
+            for tag in range(k, 48, 4):
+                p.push(tag, stacks[tag])
+
+        def collector():
+            while len(got) < 48:
+                for tag, val, crop in p.results(wait=True):
+                    got[tag] = (val, crop)
+                if not th_alive():
+                    p.flush()
+
+        threads = [threading.Thread(target=producer, args=(k,)) for k in range(4)]
+        th_alive = lambda: any(t.is_alive() for t in threads)
+        for t in threads:
+            t.start()
+        c = threading.Thread(target=collector)
+        c.start()
+        for t in threads:
+            t.join(timeout=120)
+        p.flush()
+        c.join(timeout=120)
+        assert not c.is_alive() and len(got) == 48
+    for tag, (val, crop) in got.items():
+        fr = stacks[tag]
+        if tag % 11 == 5:
+            assert isinstance(val, vdf.NotEnoughFrames)
+        elif tag % 11 == 7:
+            assert isinstance(val, vdf.VidProc)
+        else:
+            cube = np.stack(fr[:16])
+            _, want_hash, want_crop, _ = o.hash_stack(cube, 1)
+            assert np.array_equal(val, want_hash), tag
+            assert tuple(int(x) for x in crop) == tuple(int(x) for x in want_crop), tag
+
+
 def test_full_size_1080p_batch(ctx):
     """BASELINE config shape: 1080p stacks resident in HBM, generated on the device; parity of a sample against
     the oracle (which needs ~0.3 s per stack), invariants on all of them."""

@@ -8,6 +8,7 @@ from .definitions import (DEFAULT_SEARCH_TOLERANCE, DEFAULT_VID_HASH_DURATION, D
                           TOLERANCE_SCALING_FACTOR, Cropdetect)
 from .hash_cache import CacheMetadata, HashCache, load_hash_cache, save_hash_cache
 from .match_group import MatchGroup, TooFewEntries
+from .pipeline import HashPipeline
 from .search import search, search_with_references
 from .video_hash import HashTable, VideoHash
 from .video_hash_builder import (CreationOptions, Error, NotEnoughFrames, NotVideo, VideoHashBuilder, VidProc)
@@ -16,5 +17,5 @@ __all__ = [
     "VideoHash", "VideoHashBuilder", "CreationOptions", "search", "search_with_references", "MatchGroup", "Error",
     "NotVideo", "VidProc", "NotEnoughFrames", "Cropdetect", "DEFAULT_SEARCH_TOLERANCE", "DEFAULT_VID_HASH_DURATION",
     "DEFAULT_VID_HASH_SKIP_FORWARD", "TOLERANCE_SCALING_FACTOR", "HashTable", "Crop", "Context", "VdfError",
-    "default_context", "TooFewEntries", "HashCache", "CacheMetadata", "load_hash_cache", "save_hash_cache",
+    "default_context", "TooFewEntries", "HashCache", "CacheMetadata", "load_hash_cache", "save_hash_cache", "HashPipeline",
 ]

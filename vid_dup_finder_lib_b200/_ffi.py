@@ -29,6 +29,7 @@ EXPORTS = [
     "vdf_hash_stacks_device", "vdf_hash_stacks_small_device", "vdf_hash_from_small",
     "vdf_sort_order", "vdf_search", "vdf_search_with_references", "vdf_ctx_last_phases", "vdf_group_components",
     "vdf_group_components_device", "vdf_cache_load", "vdf_cache_save", "vdf_free_cache",
+    "vdf_pipeline_create", "vdf_pipeline_push", "vdf_pipeline_flush", "vdf_pipeline_poll", "vdf_pipeline_error", "vdf_pipeline_destroy",
 ]
 
 
