@@ -249,6 +249,23 @@ def _ref_search_case(ctx, n_cand, n_ref):
         assert np.array_equal(got_rp, want_rp) and np.array_equal(got_ci, want_ci), tol
 
 
+def test_saturated_tolerance_matches_everything_in_the_window(ctx):
+    """(tolerance * 1000.0) as u32 saturates (search_algorithm.rs:82): a huge tolerance must behave like 1024 on every kernel"""
+    rng = np.random.default_rng(8)
+    H, dur = _case(rng, 700, 100, 300, [10, 11, 100])
+    want = o.self_edges(H, dur, 0xFFFFFFFF)
+    assert len(want) == o.self_window_pairs(dur)
+    for variant in (0, 2, 3, 4, 5):
+        ctx.set_option("search_variant", variant)
+        try:
+            for tol in (1024, 1025, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF):
+                assert np.array_equal(ctx.search_self(H, dur, tol), want), (variant, tol)
+        finally:
+            ctx.set_option("search_variant", DEFAULT_VARIANT)
+    g = vdf.search(vdf.HashTable(H, dur, ["p/%04d" % i for i in range(700)]), 1e12, ctx=ctx)
+    assert sum(x.len() for x in g) > 0
+
+
 def test_empty_and_degenerate_inputs(ctx):
     e = ctx.search_self(np.zeros((0, 16), np.uint64), np.zeros(0, np.uint32), 350)
     assert e.shape == (0, 2)

@@ -250,7 +250,6 @@ __global__ void __launch_bounds__(256) resize_general_kernel(const uint8_t* __re
 // kRStages-deep cp.async ring (16-byte async copies, zero-filled outside the frame), ldmatrix feeds the A fragments,
 // the coefficient fragments ride along in the same ring.  The u8 intermediate [ch][16] stays in shared memory
 // (the reference rounds to u8 between the passes); the vertical pass is one thread per output pixel.
-constexpr int kRStagesMax = 4;
 constexpr int kKch = 128;              // pixels per k-chunk (4 IMMA k-steps)
 constexpr int kRowPitch = kKch + 16;   // shared-memory row pitch: ldmatrix rows land on distinct banks
 constexpr int kBFragBytes = 4 * 4 * 32 * 8;  // per k-chunk: 4 k-steps x 4 n-tiles x 32 lanes x (b0,b1)

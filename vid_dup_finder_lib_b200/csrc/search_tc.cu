@@ -803,7 +803,8 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
     p.row_lo = ctx->row_lo.as<uint32_t>(), p.row_hi = ctx->row_hi.as<uint32_t>(), p.row_id = row_id;
     p.tile_range = ctx->tile_range.as<uint2>();
     p.keys = ctx->raw_keys.as<uint64_t>(), p.counter = counter, p.capacity = capacity, p.col_base = col_base;
-    p.tol = tol, p.rank = ctx->rank, p.world = ctx->world;
+    p.tol = tol > 1024u ? 1024u : tol;  // no distance exceeds 1024 (and the epilogue's threshold is a signed int)
+    p.rank = ctx->rank, p.world = ctx->world;
     if (ctx->search_variant >= 4) {  // CTA pairs: 256-row super-tiles x absolute chunks of column super-tiles
         const uint32_t n_pairs = (n_row_tiles + 1) / 2, n_st = (n_col_tiles + 1) / 2;
         // long chunks amortise the per-unit set-up (operand A, tensor-memory allocation, cluster syncs); keep >= 64
