@@ -36,6 +36,8 @@ int vdf_ctx_create(int device_id, vdf_ctx** out) {
     for (int k = 0; k < 2; ++k) {
         cudaEventCreateWithFlags(&ctx->ev_copy[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_chunk[2 * k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_chunk[2 * k + 1], cudaEventDisableTiming);
     }
     for (int k = 0; k < 4; ++k) {
         cudaEventCreate(&ctx->kt0[k]);
@@ -66,6 +68,8 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
     for (int k = 0; k < 2; ++k) {
         if (ctx->ev_copy[k]) cudaEventDestroy(ctx->ev_copy[k]);
         if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+        if (ctx->ev_chunk[2 * k]) cudaEventDestroy(ctx->ev_chunk[2 * k]);
+        if (ctx->ev_chunk[2 * k + 1]) cudaEventDestroy(ctx->ev_chunk[2 * k + 1]);
     }
     for (int k = 0; k < 4; ++k) {
         if (ctx->kt0[k]) cudaEventDestroy(ctx->kt0[k]);
@@ -96,6 +100,7 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     else if (k == "initial_edges" && value > 0) ctx->initial_edges = (uint64_t)value;
     else if (k == "search_variant" && (value >= 0 && value <= 5)) ctx->search_variant = (int)value;
     else if (k == "tc_chunk" && value >= 0 && value <= 65535) ctx->tc_chunk = (uint32_t)value;
+    else if (k == "hash_chunks" && value >= 1 && value <= 4) ctx->hash_chunks = (uint32_t)value;
     else if (k == "grouping" && (value == 0 || value == 1)) ctx->grouping = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;
     else {

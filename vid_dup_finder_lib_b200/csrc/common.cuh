@@ -88,6 +88,7 @@ struct vdf_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};  // hash.cu: crops of chunk k are back on the host
     std::string err;
     uint32_t rank = 0, world = 1;
     uint64_t max_edges = 1ull << 28, initial_edges = 1ull << 22;
@@ -96,6 +97,7 @@ struct vdf_ctx {
                              // tiles in HBM; 4: the same on CTA pairs; 5 (default): CTA pairs, packed tiles (search_tc.cu)
     int hash_variant = 0;
     uint32_t tc_chunk = 0;  // column super-tiles per CTA-pair work unit (0: automatic)
+    uint32_t hash_chunks = 1;  // hash.cu: software-pipeline chunks per call (1: letterbox, then resize, over the whole batch)
     int grouping = 0;       // 0: the reference's greedy rule (parity); 1: connected components (GPU union-find, group.cu)
     uint64_t launches = 0, h2d = 0, d2h = 0;
     double phase_ms[4] = {0, 0, 0, 0};  // last vdf_search*: host sort, gather + H2D enqueue, device, index remap (host.cu)

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                                                              uint32_t* __restrict__ sides /* [n][2][4] l,r,t,b */) {
     __shared__ uint32_t hist[kColPanel * 257];
     __shared__ uint32_t flags[kColPanel];
+    __shared__ uint32_t narrow[kRowPanel];  // row strips decided by their value range alone
     __shared__ uint32_t s_count, s_stop;
     const uint32_t b = blockIdx.x, side = b & 3, fr = (b >> 2) & 1, s = b >> 3;
     const StackDev sd = stacks[s];
@@ -77,8 +78,34 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
     const uint32_t panel = cols ? kColPanel : kRowPanel;
     for (uint32_t base = 0; base < limit; base += panel) {
         for (uint32_t q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
+        if (tid < kRowPanel) narrow[tid] = 0;
         __syncthreads();
-        if (cols) {
+        const uint32_t px0 = side == 0 ? base : W - 32 - base;  // first pixel column of a full 32-column panel
+        if (cols && base + kColPanel <= W && ((reinterpret_cast<uintptr_t>(img) | P | px0) & 3) == 0) {
+            // full, 4-byte aligned panel: 8 word loads cover a row of the panel, 32 rows per pass, 16 passes in flight --
+            // a 1080-row panel takes 3 dependent round trips to memory instead of 9 with one byte per lane
+            const uint32_t wq = tid & 7, r0 = tid >> 3;
+            const uint32_t* col4 = reinterpret_cast<const uint32_t*>(img + px0) + wq;
+            const uint32_t P4 = P >> 2;
+            for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
+                uint32_t v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const uint32_t y = y0 + 32 * u;
+                    v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    if (y0 + 32 * u < H) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const uint32_t c = 4 * wq + b, k = side == 0 ? c : 31 - c;  // strip index inside the panel
+                            atomicAdd(&hist[k * 257 + ((v[u] >> (8 * b)) & 255u)], 1u);
+                        }
+                    }
+                }
+            }
+        } else if (cols) {
             const uint32_t idx = base + lane;
             const bool act = idx < W;
             const uint32_t x = side == 0 ? idx : W - 1 - idx;
@@ -103,9 +130,46 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                 uint32_t* h4 = hist + (warp * 4) * 257;
                 uint32_t* hs = h4 + (lane & 3) * 257;
                 uint32_t x_done = 0;
-                if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // whole row in flight: up to 16 x 4 pixels per lane
+                const uint32_t W4 = W >> 2;
+                if ((reinterpret_cast<uintptr_t>(row) & 3) == 0 && W4 <= 32 * 16) {
+                    // the whole row is in registers (<= 2048 px): look at its value range before touching the histogram.
+                    // A strip whose values span <= tol is letterbox whatever its mode is (every pixel is within tol of every
+                    // other one: count == len, 10 len > 9 len) -- exact, it is what real bars look like, and it skips the
+                    // same-address shared atomics that a near-uniform row would serialise on.
                     const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
-                    const uint32_t W4 = W >> 2;
+                    uint32_t v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t q = u * 32 + lane;
+                        v[u] = q < W4 ? __ldg(row4 + q) : 0u;
+                    }
+                    const uint32_t xt = (W4 << 2) + lane;  // the <= 3 pixels after the last whole word
+                    const uint32_t tail = xt < W ? (uint32_t)__ldg(row + xt) : 0x100u;
+                    uint32_t mn4 = 0xFFFFFFFFu, mx4 = 0u;
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (u * 32 + lane < W4) mn4 = __vminu4(mn4, v[u]), mx4 = __vmaxu4(mx4, v[u]);
+                    uint32_t mn = min(min(mn4 & 255u, (mn4 >> 8) & 255u), min((mn4 >> 16) & 255u, mn4 >> 24));
+                    uint32_t mx = max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
+                    if (tail < 0x100u) mn = min(mn, tail), mx = max(mx, tail);
+                    mn = __reduce_min_sync(0xffffffffu, mn), mx = __reduce_max_sync(0xffffffffu, mx);
+                    if (mx - mn <= (uint32_t)kLbTol) {
+                        if (lane == 0) narrow[warp] = 1u;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            if (u * 32 + lane < W4) {
+                                atomicAdd(&hs[v[u] & 255u], 1u);
+                                atomicAdd(&hs[(v[u] >> 8) & 255u], 1u);
+                                atomicAdd(&hs[(v[u] >> 16) & 255u], 1u);
+                                atomicAdd(&hs[v[u] >> 24], 1u);
+                            }
+                        }
+                        if (tail < 0x100u) atomicAdd(&hs[tail], 1u);
+                    }
+                    x_done = W;
+                } else if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // long rows: up to 16 x 4 pixels per lane in flight
+                    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
                     for (uint32_t q0 = 0; q0 < W4; q0 += 32 * 16) {
                         uint32_t v[16];
 #pragma unroll
@@ -144,7 +208,7 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
         __syncthreads();
         for (uint32_t k = warp; k < panel; k += 8) {
             bool ok = false;
-            if (base + k < limit) ok = strip_is_letterbox(hist + (cols ? k : k * 4) * 257, len, lane);
+            if (base + k < limit) ok = (!cols && narrow[k]) || strip_is_letterbox(hist + (cols ? k : k * 4) * 257, len, lane);
             if (lane == 0) flags[k] = ok;
         }
         __syncthreads();
@@ -778,7 +842,20 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         status[s] = stt;
         sd[s] = StackDev{d.offset, d.frame_stride, d.width, d.height, d.pitch, stt};
     }
-    std::vector<uint32_t> crop((size_t)n * 4, 0);
+    // Software pipeline over chunks of stacks: the crops have to visit the host (the i16 coefficient tables depend on the
+    // cropped size and are made with libm sin, like the reference), so all letterbox chunks are enqueued first, each
+    // followed by an async read-back of its crops into pinned memory and an event; the host then builds chunk k's resize
+    // jobs while the GPU is still busy with later letterbox chunks / earlier resize chunks.  One stream, no idle gap.
+    const uint32_t kMaxChunks = 4;
+    const uint32_t n_chunks = std::max(1u, std::min(std::min(kMaxChunks, ctx->hash_chunks), n / 32));
+    auto chunk_begin = [&](uint32_t k) { return (uint32_t)((uint64_t)n * k / n_chunks); };
+    VDF_ALLOC(ctx, ctx->pin_a.ensure((size_t)n * 16));
+    uint32_t* crop = ctx->pin_a.as<uint32_t>();
+    std::memset(crop, 0, (size_t)n * 16);
+    VDF_ALLOC(ctx, ctx->h_jobs.ensure((size_t)n * sizeof(StackJob) + (size_t)n * 4));
+    StackJob* d_jobs = ctx->h_jobs.as<StackJob>();
+    int32_t* d_status = reinterpret_cast<int32_t*>(d_jobs + n);
+    VDF_CUDA(ctx, cudaMemcpyAsync(d_status, status.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     if (cropdetect == VDF_CROPDETECT_LETTERBOX) {
         VDF_ALLOC(ctx, ctx->h_desc.ensure((size_t)n * sizeof(StackDev)));
         VDF_ALLOC(ctx, ctx->h_sides.ensure((size_t)n * 8 * 4));
@@ -786,68 +863,28 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_desc.p, sd.data(), (size_t)n * sizeof(StackDev), cudaMemcpyHostToDevice, st));
         VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_sides.p, 0, (size_t)n * 8 * 4, st));
         kt_begin(ctx, 2);
-        letterbox_side_kernel<<<n * 8, 256, 0, st>>>(d_frames, ctx->h_desc.as<StackDev>(), ctx->h_sides.as<uint32_t>());
-        kt_end(ctx, 2);
-        VDF_LAUNCHED(ctx);
-        crop_combine_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctx->h_desc.as<StackDev>(), ctx->h_sides.as<uint32_t>(), n,
-                                                             ctx->h_crop.as<uint32_t>());
-        VDF_LAUNCHED(ctx);
-        VDF_CUDA(ctx, cudaMemcpyAsync(crop.data(), ctx->h_crop.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-        VDF_CUDA(ctx, cudaStreamSynchronize(st));
-    }
-    // coefficient tables for the cropped sizes (cached per size in HBM)
-    std::vector<StackJob> jobs(n);
-    uint32_t max_ch = 1;
-    bool any_fast = false, any_slow = false;
-    for (uint32_t s = 0; s < n; ++s) {
-        StackJob& j = jobs[s];
-        std::memset(&j, 0, sizeof j);
-        j.status = status[s];
-        if (status[s] != VDF_STACK_OK) continue;
-        const vdf_stack_desc& d = desc[s];
-        const uint32_t* c = &crop[(size_t)s * 4];
-        j.offset = d.offset, j.frame_stride = d.frame_stride, j.pitch = d.pitch;
-        j.left = c[0], j.top = c[2];
-        j.cw = d.width - c[0] - c[1], j.ch = d.height - c[2] - c[3];  // Crop::as_view_args, crop.rs:92-103
-        const CoefTable *th, *tv;
-        VDF_TRY(get_table(ctx, j.cw, &th));
-        VDF_TRY(get_table(ctx, j.ch, &tv));
-        j.bh = th->d_bounds, j.kh = th->d_k, j.win_h = th->window, j.prec_h = th->precision;
-        j.bv = tv->d_bounds, j.kv = tv->d_k, j.win_v = tv->window, j.prec_v = tv->precision;
-        max_ch = std::max(max_ch, j.ch);
-        // tensor-core path needs 16-byte aligned rows (cp.async 16 B): base, frame stride and pitch
-        const bool aligned = ((reinterpret_cast<uintptr_t>(d_frames) + d.offset) % 16 == 0) && d.frame_stride % 16 == 0 &&
-                             d.pitch % 16 == 0;
-        const uint32_t shift = j.left & 15u;
-        const size_t ring_bytes = ctx->hash_variant != 2 ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
-        const bool fits = (shift + j.cw + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring_bytes;
-        if (aligned && fits && ctx->hash_variant != 1) {
-            j.x0_al = j.left & ~15u;
-            j.n_kch = (shift + j.cw + kKch - 1) / kKch;
-            VDF_TRY(get_bfrags(ctx, *th, shift, &j.kb, &j.kmask));
-            j.fast = 1;
-            any_fast = true;
-        } else {
-            any_slow = true;
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            const uint32_t s0 = chunk_begin(k), cnt = chunk_begin(k + 1) - s0;
+            letterbox_side_kernel<<<cnt * 8, 256, 0, st>>>(d_frames, ctx->h_desc.as<StackDev>() + s0,
+                                                          ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8);
+            VDF_LAUNCHED(ctx);
+            crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(ctx->h_desc.as<StackDev>() + s0,
+                                                                   ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt,
+                                                                   ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4);
+            VDF_LAUNCHED(ctx);
+            VDF_CUDA(ctx, cudaMemcpyAsync(crop + (size_t)s0 * 4, ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4, (size_t)cnt * 16,
+                                          cudaMemcpyDeviceToHost, st));
+            VDF_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[k], st));
         }
+        kt_end(ctx, 2);
     }
-    VDF_ALLOC(ctx, ctx->h_jobs.ensure((size_t)n * sizeof(StackJob) + (size_t)n * 4));
-    StackJob* d_jobs = ctx->h_jobs.as<StackJob>();
-    int32_t* d_status = reinterpret_cast<int32_t*>(d_jobs + n);
-    VDF_CUDA(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)n * sizeof(StackJob), cudaMemcpyHostToDevice, st));
-    VDF_CUDA(ctx, cudaMemcpyAsync(d_status, status.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     uint8_t* d_small = d_out_small;
     if (!d_small) {
         VDF_ALLOC(ctx, ctx->h_small.ensure((size_t)n * 4096));
         d_small = ctx->h_small.as<uint8_t>();
     }
-    const size_t tmp_bytes = (size_t)max_ch * 16;
     const bool four_warps = ctx->hash_variant != 2;  // default: 4 warps, two CTAs per SM
     const size_t ring = four_warps ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
-    if (tmp_bytes + ring > 220 * 1024) {
-        ctx->err = "frame height beyond the resize kernels' shared-memory budget";
-        return VDF_ERR_INVALID;
-    }
     static size_t smem_set[3] = {0, 0, 0};
     auto want_smem = [&](int slot, const void* fn, size_t bytes) -> int {
         if (bytes > 48 * 1024 && bytes > smem_set[slot]) {
@@ -856,21 +893,66 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         }
         return VDF_OK;
     };
-    kt_begin(ctx, 1);
-    if (any_fast) {
-        if (four_warps) {
-            VDF_TRY(want_smem(1, (const void*)resize_mma_kernel<4>, tmp_bytes + ring));
-            resize_mma_kernel<4><<<n * 16, 128, tmp_bytes + ring, st>>>(d_frames, d_jobs, d_small);
-        } else {
-            VDF_TRY(want_smem(2, (const void*)resize_mma_kernel<8>, tmp_bytes + ring));
-            resize_mma_kernel<8><<<n * 16, 256, tmp_bytes + ring, st>>>(d_frames, d_jobs, d_small);
+    std::vector<StackJob> jobs(n);
+    for (uint32_t k = 0; k < n_chunks; ++k) {
+        const uint32_t s0 = chunk_begin(k), s1 = chunk_begin(k + 1), cnt = s1 - s0;
+        if (cropdetect == VDF_CROPDETECT_LETTERBOX) VDF_CUDA(ctx, cudaEventSynchronize(ctx->ev_chunk[k]));
+        // coefficient tables for the cropped sizes (cached per size in HBM)
+        uint32_t max_ch = 1;
+        bool any_fast = false, any_slow = false;
+        for (uint32_t s = s0; s < s1; ++s) {
+            StackJob& j = jobs[s];
+            std::memset(&j, 0, sizeof j);
+            j.status = status[s];
+            if (status[s] != VDF_STACK_OK) continue;
+            const vdf_stack_desc& d = desc[s];
+            const uint32_t* c = &crop[(size_t)s * 4];
+            j.offset = d.offset, j.frame_stride = d.frame_stride, j.pitch = d.pitch;
+            j.left = c[0], j.top = c[2];
+            j.cw = d.width - c[0] - c[1], j.ch = d.height - c[2] - c[3];  // Crop::as_view_args, crop.rs:92-103
+            const CoefTable *th, *tv;
+            VDF_TRY(get_table(ctx, j.cw, &th));
+            VDF_TRY(get_table(ctx, j.ch, &tv));
+            j.bh = th->d_bounds, j.kh = th->d_k, j.win_h = th->window, j.prec_h = th->precision;
+            j.bv = tv->d_bounds, j.kv = tv->d_k, j.win_v = tv->window, j.prec_v = tv->precision;
+            max_ch = std::max(max_ch, j.ch);
+            // tensor-core path needs 16-byte aligned rows (cp.async 16 B): base, frame stride and pitch
+            const bool aligned = ((reinterpret_cast<uintptr_t>(d_frames) + d.offset) % 16 == 0) && d.frame_stride % 16 == 0 &&
+                                 d.pitch % 16 == 0;
+            const uint32_t shift = j.left & 15u;
+            const bool fits = (shift + j.cw + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring;
+            if (aligned && fits && ctx->hash_variant != 1) {
+                j.x0_al = j.left & ~15u;
+                j.n_kch = (shift + j.cw + kKch - 1) / kKch;
+                VDF_TRY(get_bfrags(ctx, *th, shift, &j.kb, &j.kmask));
+                j.fast = 1;
+                any_fast = true;
+            } else {
+                any_slow = true;
+            }
         }
-        VDF_LAUNCHED(ctx);
-    }
-    if (any_slow) {
-        VDF_TRY(want_smem(0, (const void*)resize_general_kernel, tmp_bytes));
-        resize_general_kernel<<<n * 16, 256, tmp_bytes, st>>>(d_frames, d_jobs, d_small);
-        VDF_LAUNCHED(ctx);
+        VDF_CUDA(ctx, cudaMemcpyAsync(d_jobs + s0, jobs.data() + s0, (size_t)cnt * sizeof(StackJob), cudaMemcpyHostToDevice, st));
+        const size_t tmp_bytes = (size_t)max_ch * 16;
+        if (tmp_bytes + ring > 220 * 1024) {
+            ctx->err = "frame height beyond the resize kernels' shared-memory budget";
+            return VDF_ERR_INVALID;
+        }
+        if (k == 0) kt_begin(ctx, 1);
+        if (any_fast) {
+            if (four_warps) {
+                VDF_TRY(want_smem(1, (const void*)resize_mma_kernel<4>, tmp_bytes + ring));
+                resize_mma_kernel<4><<<cnt * 16, 128, tmp_bytes + ring, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096);
+            } else {
+                VDF_TRY(want_smem(2, (const void*)resize_mma_kernel<8>, tmp_bytes + ring));
+                resize_mma_kernel<8><<<cnt * 16, 256, tmp_bytes + ring, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096);
+            }
+            VDF_LAUNCHED(ctx);
+        }
+        if (any_slow) {
+            VDF_TRY(want_smem(0, (const void*)resize_general_kernel, tmp_bytes));
+            resize_general_kernel<<<cnt * 16, 256, tmp_bytes, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096);
+            VDF_LAUNCHED(ctx);
+        }
     }
     kt_end(ctx, 1);
     if (d_out_hash) {
@@ -881,7 +963,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     }
     VDF_CUDA(ctx, cudaStreamSynchronize(st));  // jobs/status host vectors go out of scope
     if (out_status) std::memcpy(out_status, status.data(), (size_t)n * 4);
-    if (out_crop) std::memcpy(out_crop, crop.data(), (size_t)n * 16);
+    if (out_crop) std::memcpy(out_crop, crop, (size_t)n * 16);
     return VDF_OK;
 }
 
