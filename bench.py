@@ -13,6 +13,7 @@ in the same run and reported under "secondary" with its own HBM roofline; `--wor
 public API with host buffers; `cpu_baseline` times the oracle port on a bounded sample on this box's host cores.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -59,7 +60,7 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int, period_s: float = 0.1):
+    def __init__(self, index: int, period_s: float = float(os.environ.get("VDF_CLOCK_PERIOD_S", "0.1"))):
         self.index, self.period, self.proc, self.lines = index, period_s, None, []
         self.sm, self.mx, self.reasons, self.stop, self.t, self.how = [], [], set(), threading.Event(), None, None
 
@@ -327,15 +328,23 @@ def main():
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 step()
+            gc.collect()
+            gc.disable()  # a generation-2 collection between two launches would show up as GPU idle time
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
             e0.record(stream)
             for _ in range(steps):
                 if flush_l2:
                     flush.fill_(1)
                 step()
             e1.record(stream)
+            w1 = time.perf_counter()
             barrier()
+            gc.enable()
+        if os.environ.get("VDF_BENCH_DEBUG"):
+            print(f"[timed] events {e0.elapsed_time(e1):.1f} ms, host wall {1e3 * (w1 - w0):.1f} ms, barrier {1e3 * (time.perf_counter() - w1):.1f} ms",
+                  file=sys.stderr)
         return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
     # ---------------------------------------------------------------- search workload
@@ -351,11 +360,19 @@ def main():
             d_dur = torch.from_numpy(dur.view(np.int32)).to(dev)
         result = {}
 
+        dbg = os.environ.get("VDF_BENCH_DEBUG")
+
         def step():
+            t0 = time.perf_counter()
             keys = vdist.search_self_keys(ctx, d_hash, d_dur, tol_int)
+            t1 = time.perf_counter()
             torch.cuda.current_stream().synchronize()
+            t2 = time.perf_counter()
             gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
+            t3 = time.perf_counter()
             result["edges"], result["groups"] = int(keys.numel()), len(gp) - 1
+            if dbg:
+                print(f"[step] keys {1e3 * (t1 - t0):.1f} ms, sync {1e3 * (t2 - t1):.1f} ms, group {1e3 * (t3 - t2):.1f} ms", file=sys.stderr)
 
         with ClockSampler(local) as cs:
             with torch.cuda.stream(stream):

@@ -110,7 +110,7 @@ struct vdf_ctx {
     // search scratch
     vdf::DevBuf row_tiles, col_tiles, row_lo, row_hi, row_id, tile_range, raw_keys, sort_tmp, misc, keys_a, keys_b;
     vdf::DevBuf in_hash, in_dur, in_hash2, in_dur2, ref_perm, ref_key;
-    vdf::DevBuf exp_rows, exp_cols, pc_rows, pc_cols, pcmin_rows, pcmin_cols;  // tensor-core search: byte-expanded tiles + popcounts
+    vdf::DevBuf exp_rows, exp_cols, pc_rows, pc_cols, pcmin_rows, pcmin_cols, unit_cnt, unit_off;  // tensor-core search: byte-expanded tiles + popcounts
     // grouping scratch
     vdf::DevBuf g_rk, g_rks, g_state, g_parent, g_wl0, g_wla, g_wlb, g_mk, g_mks, g_flag, g_scan, g_gp, g_mem;
     // hashing scratch

@@ -16,6 +16,8 @@
 // hashes x 1024 B = 128 KB) stays resident; column super-tiles (B, 256 hashes) stream through a 2-stage ring of
 // 32 KB K-chunks; each super-tile is 8 chunks x 4 MMAs of 128x256x32; two 256-column TMEM accumulators let the
 // epilogue of super-tile t overlap the MMAs of t+1.
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 namespace vdf {
@@ -150,6 +152,8 @@ struct TcParams {
     uint32_t chunk;  // column SUPER-tiles (256 hashes) per CTA
     uint32_t tol;
     uint32_t rank, world;
+    const uint32_t* unit_off;  // variant 5: exclusive scan of the work units each row pair owns on this rank
+    uint32_t n_pairs;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const TcParams p) {
@@ -548,6 +552,37 @@ __device__ __forceinline__ void tc5_expand_a(uint32_t bits, uint8_t* line, int w
     *reinterpret_cast<uint4*>(line + (((2 * w + 1) ^ rsw) << 4)) = hi;
 }
 
+// Work units of variant 5.  A unit = (row pair P, absolute chunk c of column super-tiles); pair P needs the chunks that
+// intersect the union of its two row tiles' column ranges, and rank r owns those with (P + c) % world == r.  The grid
+// holds exactly the owned units (an exclusive scan over the pairs maps blockIdx -> (P, k-th owned chunk)): a 2-D grid
+// with early exits launches ~8x more clusters than it uses on 8 GPUs, and an empty cluster still costs about a
+// microsecond of an SM pair.
+__device__ __forceinline__ bool tc5_pair_chunks(const TcParams& p, uint32_t n_row_tiles, uint32_t P, uint32_t* st_lo,
+                                                uint32_t* st_hi, uint32_t* c_first, uint32_t* n_owned) {
+    const uint2 r0 = p.tile_range[2 * P];
+    const uint2 r1 = (2 * P + 1 < n_row_tiles) ? p.tile_range[2 * P + 1] : make_uint2(0, 0);
+    uint32_t t_lo = 0xFFFFFFFFu, t_hi = 0;
+    if (r0.x < r0.y) t_lo = r0.x, t_hi = r0.y;
+    if (r1.x < r1.y) t_lo = min(t_lo, r1.x), t_hi = max(t_hi, r1.y);
+    *n_owned = 0;
+    if (t_lo >= t_hi) return false;
+    *st_lo = t_lo / 2, *st_hi = (t_hi + 1) / 2;  // column super-tiles [st_lo, st_hi)
+    const uint32_t c_lo = *st_lo / p.chunk, c_hi = (*st_hi - 1) / p.chunk;
+    const uint32_t skip = (p.rank + p.world - (P + c_lo) % p.world) % p.world;  // first owned chunk at or after c_lo
+    *c_first = c_lo + skip;
+    if (*c_first > c_hi) return false;
+    *n_owned = (c_hi - *c_first) / p.world + 1;
+    return true;
+}
+
+__global__ void tc5_units_kernel(const TcParams p, uint32_t n_row_tiles, uint32_t* __restrict__ cnt) {
+    const uint32_t P = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P > p.n_pairs) return;
+    uint32_t a, b, c, n = 0;
+    if (P < p.n_pairs) tc5_pair_chunks(p, n_row_tiles, P, &a, &b, &c, &n);
+    cnt[P] = n;  // cnt[n_pairs] = 0: the scan's last element is the total
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc5Threads, 1)
     hamming_tc5_kernel(const TcParams p, uint32_t n_row_tiles) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -567,15 +602,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc5Threads, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
 
     const uint32_t cr = tc_cluster_rank();
-    const uint32_t P = blockIdx.x >> 1, c = blockIdx.y;
-    if (p.world > 1 && ((P + c) % p.world) != p.rank) return;
-    const uint2 r0 = p.tile_range[2 * P];
-    const uint2 r1 = (2 * P + 1 < n_row_tiles) ? p.tile_range[2 * P + 1] : make_uint2(0, 0);
-    uint32_t t_lo = 0xFFFFFFFFu, t_hi = 0;
-    if (r0.x < r0.y) t_lo = r0.x, t_hi = r0.y;
-    if (r1.x < r1.y) t_lo = min(t_lo, r1.x), t_hi = max(t_hi, r1.y);
-    if (t_lo >= t_hi) return;
-    const uint32_t st0 = max(t_lo / 2, c * p.chunk), st1 = min((t_hi + 1) / 2, (c + 1) * p.chunk);
+    // blockIdx.x >> 1 = the unit; the pair that owns it = the last P with unit_off[P] <= unit
+    const uint32_t unit = blockIdx.x >> 1;
+    uint32_t lo = 0, hi = p.n_pairs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(p.unit_off + mid) <= unit) lo = mid;
+        else hi = mid;
+    }
+    const uint32_t P = lo;
+    uint32_t st_lo, st_hi, c_first, n_owned;
+    if (!tc5_pair_chunks(p, n_row_tiles, P, &st_lo, &st_hi, &c_first, &n_owned)) return;  // cannot happen for a listed unit
+    const uint32_t c = c_first + (unit - __ldg(p.unit_off + P)) * p.world;
+    const uint32_t st0 = max(st_lo, c * p.chunk), st1 = min(st_hi, (c + 1) * p.chunk);
     if (st0 >= st1) return;
     const uint32_t n_st = st1 - st0;
     const uint32_t I = 2 * P + cr;
@@ -805,6 +844,7 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
     p.keys = ctx->raw_keys.as<uint64_t>(), p.counter = counter, p.capacity = capacity, p.col_base = col_base;
     p.tol = tol > 1024u ? 1024u : tol;  // no distance exceeds 1024 (and the epilogue's threshold is a signed int)
     p.rank = ctx->rank, p.world = ctx->world;
+    p.unit_off = nullptr, p.n_pairs = 0;
     if (ctx->search_variant >= 4) {  // CTA pairs: 256-row super-tiles x absolute chunks of column super-tiles
         const uint32_t n_pairs = (n_row_tiles + 1) / 2, n_st = (n_col_tiles + 1) / 2;
         // long chunks amortise the per-unit set-up (operand A, tensor-memory allocation, cluster syncs); keep >= 64
@@ -815,12 +855,37 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
             chunk >>= 1;
         while ((n_st + chunk - 1) / chunk > 65535) chunk *= 2;
         p.chunk = chunk;
+        if (ctx->search_variant == 5) {  // 1-D grid over exactly the units this rank owns
+            p.n_pairs = n_pairs;
+            VDF_ALLOC(ctx, ctx->unit_cnt.ensure((size_t)(n_pairs + 1) * 4));
+            VDF_ALLOC(ctx, ctx->unit_off.ensure((size_t)(n_pairs + 1) * 4));
+            p.unit_off = ctx->unit_off.as<uint32_t>();
+            tc5_units_kernel<<<(n_pairs + 1 + 255) / 256, 256, 0, ctx->stream>>>(p, n_row_tiles, ctx->unit_cnt.as<uint32_t>());
+            VDF_LAUNCHED(ctx);
+            size_t tmp = 0;
+            VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->unit_cnt.as<uint32_t>(), ctx->unit_off.as<uint32_t>(),
+                                                        (size_t)n_pairs + 1, ctx->stream));
+            VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
+            VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tmp, ctx->unit_cnt.as<uint32_t>(),
+                                                        ctx->unit_off.as<uint32_t>(), (size_t)n_pairs + 1, ctx->stream));
+            ctx->launches += 1;
+            uint32_t n_units = 0;
+            VDF_CUDA(ctx, cudaMemcpyAsync(&n_units, ctx->unit_off.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (n_units == 0) return VDF_OK;
+            if (n_units > 0x3FFFFFFFu) {
+                ctx->err = "too many work units for one launch";
+                return VDF_ERR_INVALID;
+            }
+            kt_begin(ctx, 0);
+            hamming_tc5_kernel<<<2 * n_units, kTc5Threads, kTc5Smem, ctx->stream>>>(p, n_row_tiles);
+            kt_end(ctx, 0);
+            VDF_LAUNCHED(ctx);
+            return VDF_OK;
+        }
         dim3 grid(2 * n_pairs, (n_st + chunk - 1) / chunk);
         kt_begin(ctx, 0);
-        if (ctx->search_variant == 5)
-            hamming_tc5_kernel<<<grid, kTc5Threads, kTc5Smem, ctx->stream>>>(p, n_row_tiles);
-        else
-            hamming_tc2_kernel<<<grid, kTcThreads, kTc2Smem, ctx->stream>>>(p, n_row_tiles);
+        hamming_tc2_kernel<<<grid, kTcThreads, kTc2Smem, ctx->stream>>>(p, n_row_tiles);
         kt_end(ctx, 0);
         VDF_LAUNCHED(ctx);
         return VDF_OK;
