@@ -157,18 +157,21 @@ def ncu_traffic(kernel: str, key: str):
 def search_roofline(variant: int, pairs_per_launch: float, k_ms: float, k_n: int, sm_count: int, sm_max_mhz: float, n_key=None):
     ms = k_ms / max(k_n, 1)
     if variant >= 3:
-        # tensor-bound: 2 x 1024 8-bit integer ops per pair on tcgen05.mma kind::i8
+        # tensor-bound: 2 x 1024 operand-width integer ops per pair on tcgen05.mma (kind::i8, or kind::mxf4 for variant 6)
         p = os.path.join(ROOT, "MEASURED_PEAKS.json")
         bf16 = json.load(open(p)).get("bf16_tflops") if os.path.exists(p) else None
-        peak, src = (2.0 * bf16, "2 x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json, burst): 8-bit operands run at twice "
-                     "the bf16 rate") if bf16 else (4500.0, "fallback: nominal dense 8-bit peak (B200_PROFILING.md)")
-        pipe = sm_count * 8192 * 2 * sm_max_mhz * 1e6 / 1e12  # 8192 u8 MAC/clk/SM (128x256x32 per 128 clk)
+        rate = 4.0 if variant == 6 else 2.0   # 4-bit operands issue at four times the bf16 rate, 8-bit at twice
+        macs = 16384 if variant == 6 else 8192  # MAC/clk/SM: 128 x 256 x {64 | 32} per 128 clk
+        what = "4-bit" if variant == 6 else "8-bit"
+        peak, src = (rate * bf16, f"{rate:g} x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json, burst): {what} operands run at "
+                     f"{rate:g}x the bf16 rate") if bf16 else (2250.0 * rate, f"fallback: nominal dense {what} peak (B200_PROFILING.md)")
+        pipe = sm_count * macs * 2 * sm_max_mhz * 1e6 / 1e12
         achieved = 2.0 * PAIR_MACS * pairs_per_launch / (ms * 1e-3) / 1e12 if k_n else None
-        kname = {3: "hamming_tc_kernel", 4: "hamming_tc2_kernel", 5: "hamming_tc5_kernel"}[variant]
+        kname = {3: "hamming_tc_kernel", 4: "hamming_tc2_kernel", 5: "hamming_tc5_kernel", 6: "hamming_tc6_kernel"}[variant]
         return {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(kname, n_key) if n_key else None,
                 "peak_source": src, "pipe_peak": pipe, "pipe_frac": (achieved / pipe) if achieved else None,
-                "pipe_peak_source": "148 SMs x 8192 u8 MAC/clk/SM x 2 x max SM clock (tcgen05 issue floor, B300_MICROARCH.md)",
+                "pipe_peak_source": f"148 SMs x {macs} {what} MAC/clk/SM x 2 x max SM clock (tcgen05 issue floor, B300_MICROARCH.md)",
                 "kernel_ms_per_launch": ms, "kernel_launches_timed": k_n, "algorithmic_ops_per_pair": 2 * PAIR_MACS,
                 "popc_equivalent": {"algorithmic_popc32_per_pair": PAIR_POPC32,
                                     "frac_of_popc_peak": PAIR_POPC32 * pairs_per_launch / (ms * 1e-3) / 1e9 /

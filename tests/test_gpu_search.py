@@ -111,7 +111,7 @@ def _case(rng, n, n_clusters, max_flip, dur_choices):
 SIZES = [1, 2, 3, 127, 128, 129, 255, 257, 1000, 4097]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=["popc", "csa8x8", "csa8x4", "tcgen05", "tcgen05_2cta", "tcgen05_2cta_packed"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6], ids=["popc", "csa8x8", "csa8x4", "tcgen05", "tcgen05_2cta", "tcgen05_2cta_packed", "tcgen05_mxf4"])
 @pytest.mark.parametrize("n", SIZES)
 def test_self_search_edges_and_groups_match_oracle(ctx, n, variant):
     rng = np.random.default_rng(1000 + n)
@@ -227,7 +227,7 @@ def test_random_edge_lists_group_like_the_oracle(ctx):
         assert np.array_equal(gp, want_gp) and np.array_equal(mm, want_mm)
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4, 5], ids=["popc", "tcgen05", "tcgen05_2cta", "tcgen05_2cta_packed"])
+@pytest.mark.parametrize("variant", [0, 3, 4, 5, 6], ids=["popc", "tcgen05", "tcgen05_2cta", "tcgen05_2cta_packed", "tcgen05_mxf4"])
 @pytest.mark.parametrize("n_cand,n_ref", [(1, 1), (300, 5), (129, 257), (5000, 700)])
 def test_ref_search_matches_oracle(ctx, n_cand, n_ref, variant):
     ctx.set_option("search_variant", variant)
@@ -255,7 +255,7 @@ def test_saturated_tolerance_matches_everything_in_the_window(ctx):
     H, dur = _case(rng, 700, 100, 300, [10, 11, 100])
     want = o.self_edges(H, dur, 0xFFFFFFFF)
     assert len(want) == o.self_window_pairs(dur)
-    for variant in (0, 2, 3, 4, 5):
+    for variant in (0, 2, 3, 4, 5, 6):
         ctx.set_option("search_variant", variant)
         try:
             for tol in (1024, 1025, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF):
@@ -299,7 +299,7 @@ def test_edge_buffer_grows_and_caps(ctx):
         ctx.set_option("max_edges", 1 << 28)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 4, 5], ids=["popc", "csa8x4", "tcgen05_2cta", "tcgen05_2cta_packed"])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5, 6], ids=["popc", "csa8x4", "tcgen05_2cta", "tcgen05_2cta_packed", "tcgen05_mxf4"])
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_shards_partition_the_pair_matrix(ctx, world, variant):
     rng = np.random.default_rng(5)

@@ -178,6 +178,8 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
               const uint8_t* col_exp, const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* col_pcmin,
               const uint32_t* row_id, uint64_t col_base, uint32_t tol, uint64_t capacity, unsigned long long* counter);
 int tc5_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& tiles, DevBuf& pc, DevBuf& pcmin);
+int tc6_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, bool as_columns, DevBuf& tiles, DevBuf& pc,
+             DevBuf& pcmin);
 // group.cu
 int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, vdf_groups* out);
 int group_components_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64_t n_edges, vdf_groups* out);

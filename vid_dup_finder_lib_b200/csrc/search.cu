@@ -574,6 +574,9 @@ int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_d
         VDF_TRY(tc_expand(ctx, d_hash, nullptr, n, ctx->exp_rows, ctx->pc_rows));
     } else if (ctx->search_variant == 5) {
         VDF_TRY(tc5_pack(ctx, d_hash, nullptr, n, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
+    } else if (ctx->search_variant == 6) {
+        VDF_TRY(tc6_pack(ctx, d_hash, nullptr, n, false, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
+        VDF_TRY(tc6_pack(ctx, d_hash, nullptr, n, true, ctx->col_tiles, ctx->pc_cols, ctx->pcmin_cols));
     } else {
         retile_kernel<<<T, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), nullptr, n,
                                                   ctx->row_tiles.as<uint32_t>());
@@ -583,6 +586,9 @@ int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_d
                                                                      ctx->row_hi.as<uint32_t>());
     VDF_LAUNCHED(ctx);
     const void* data = tc ? ctx->exp_rows.p : ctx->row_tiles.p;
+    if (ctx->search_variant == 6)
+        return run_tiles(ctx, T, T, data, ctx->col_tiles.p, ctx->pc_rows.as<uint32_t>(), ctx->pc_cols.as<uint32_t>(),
+                         ctx->pcmin_cols.as<uint32_t>(), nullptr, 0, tol, d_keys_out, capacity, n_out);
     return run_tiles(ctx, T, T, data, data, ctx->pc_rows.as<uint32_t>(), ctx->pc_rows.as<uint32_t>(),
                      ctx->pcmin_rows.as<uint32_t>(), nullptr, 0, tol,
                      d_keys_out, capacity, n_out);
@@ -626,6 +632,9 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
     } else if (ctx->search_variant == 5) {
         VDF_TRY(tc5_pack(ctx, d_cand, nullptr, n_cand, ctx->col_tiles, ctx->pc_cols, ctx->pcmin_cols));
         VDF_TRY(tc5_pack(ctx, d_refs, perm, n_ref, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
+    } else if (ctx->search_variant == 6) {
+        VDF_TRY(tc6_pack(ctx, d_cand, nullptr, n_cand, true, ctx->col_tiles, ctx->pc_cols, ctx->pcmin_cols));
+        VDF_TRY(tc6_pack(ctx, d_refs, perm, n_ref, false, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
     } else {
         retile_kernel<<<TC, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cand), nullptr, n_cand,
                                                    ctx->col_tiles.as<uint32_t>());

@@ -811,6 +811,327 @@ int tc5_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_
     return VDF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ CTA pair, 4-bit operands
+// search_variant 6 (experimental): variant 5 with the bits expanded to e2m1 nibbles ({0, 1.0}) and
+// tcgen05.mma kind::mxf4 (block-scaled, K = 64 per instruction, fp32 accumulators: exact, every partial sum is an
+// integer <= 1024), which issues at twice the kind::i8 rate.  Block scales are the constant 1.0 (UE8M0 0x7F): the tensor-
+// memory columns the scale factors live in are filled with 0x7F bytes once, so their layout does not matter.  Those
+// columns have to come out of the accumulators' 512, hence super-tiles of 192 columns (two 192-column accumulators at
+// [0,192) and [192,384), scale factors in [384,512)) and column tiles of 96 hashes.  Operands are half the size of
+// variant 5's (A: 64 KB per CTA), which pays for an 8-stage ring.  K order: nibble j of output word m of a unit holds bit
+// 4j + m of the packed word -- any permutation of K is fine as long as A and B use the same one.
+constexpr int kT6Cols = 96;                          // hashes per column tile (one CTA's half of a super-tile)
+constexpr int kT6Chunk = 128;                        // bytes per row per K-chunk = 256 bits
+constexpr int kT6ABytes = 4 * kTile * kT6Chunk;      // 64 KB
+constexpr int kT6StageBytes = kT6Cols * kT6Chunk;    // 12 KB
+constexpr int kT6Stages = 8;
+constexpr int kT6PackedBytes = kT6Cols * 128;        // packed column tile: 96 x 128 B = 12 KB; packed row tile: 16 KB
+constexpr size_t kTc6Smem = (size_t)kT6ABytes + kT6Stages * kT6StageBytes + 2 * kTileWords * 4 /* packed A, then 2 packed column tiles */ + 1024 + 256;
+// block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): a/b format E2M1 = 1 at [7,10) / [10,13),
+// K-major, N >> 3 at [17,23), scale format UE8M0 = 1 at bit 23, M >> 4 at [24,29), scale-factor ids 0, K = 64
+constexpr uint32_t kTc6Idesc = (1u << 7) | (1u << 10) | ((192u >> 3) << 17) | (1u << 23) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ void tc6_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t sfa, uint32_t sfb, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kTc6Idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+        : "memory");
+}
+// one packed u32 -> one 16-byte unit of e2m1 nibbles (0x2 = 1.0)
+__device__ __forceinline__ uint4 tc6_expand(uint32_t w) {
+    return make_uint4((w << 1) & 0x22222222u, w & 0x22222222u, (w >> 1) & 0x22222222u, (w >> 2) & 0x22222222u);
+}
+#define TC_RI8(v, o) "r"(v[o]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(
+            taddr),
+        TC_RI8(v, 0), TC_RI8(v, 8), TC_RI8(v, 16), TC_RI8(v, 24)
+        : "memory");
+}
+
+// hashes [n][32] u32 -> pk[tile][K-chunk 0..3][row 0..T-1][8 x u32] + pc + pcmin64 (as tc5_pack_kernel, tile size T)
+template <int T>
+__global__ void __launch_bounds__(128) tc6_pack_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm, uint64_t n,
+                                                       uint32_t* __restrict__ pk, uint32_t* __restrict__ pc) {
+    if ((int)threadIdx.x >= T) return;
+    const uint64_t g = (uint64_t)blockIdx.x * T + threadIdx.x;
+    uint4* out = reinterpret_cast<uint4*>(pk + (size_t)blockIdx.x * T * 32) + threadIdx.x * 2;
+    uint32_t c = 0;
+    const uint4* src = g < n ? reinterpret_cast<const uint4*>(in) + (perm ? perm[g] : g) * 8 : nullptr;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {  // q = 16-byte piece of the hash; K-chunk kc = q / 2 holds pieces 2kc, 2kc+1
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (src) v = src[q];
+        c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        out[(q >> 1) * T * 2 + (q & 1)] = v;
+    }
+    pc[g] = c;
+}
+__global__ void pcmin64_kernel(const uint32_t* __restrict__ pc, uint64_t n_groups, uint32_t* __restrict__ pcmin) {
+    const uint64_t g = blockIdx.x * (uint64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t m = __reduce_min_sync(0xffffffffu, min(pc[g * 64 + lane], pc[g * 64 + 32 + lane]));
+    if (lane == 0) pcmin[g] = m;
+}
+
+__device__ __forceinline__ bool tc6_pair_chunks(const TcParams& p, uint32_t n_row_tiles, uint32_t P, uint32_t* st_lo,
+                                                uint32_t* st_hi, uint32_t* c_first, uint32_t* n_owned) {
+    const uint2 r0 = p.tile_range[2 * P];
+    const uint2 r1 = (2 * P + 1 < n_row_tiles) ? p.tile_range[2 * P + 1] : make_uint2(0, 0);
+    uint32_t t_lo = 0xFFFFFFFFu, t_hi = 0;
+    if (r0.x < r0.y) t_lo = r0.x, t_hi = r0.y;
+    if (r1.x < r1.y) t_lo = min(t_lo, r1.x), t_hi = max(t_hi, r1.y);
+    *n_owned = 0;
+    if (t_lo >= t_hi) return false;
+    // tile_range counts 128-hash tiles; super-tiles here are 192 columns
+    *st_lo = (uint32_t)(((uint64_t)t_lo * kTile) / (2 * kT6Cols));
+    *st_hi = (uint32_t)(((uint64_t)t_hi * kTile + 2 * kT6Cols - 1) / (2 * kT6Cols));
+    const uint32_t c_lo = *st_lo / p.chunk, c_hi = (*st_hi - 1) / p.chunk;
+    const uint32_t skip = (p.rank + p.world - (P + c_lo) % p.world) % p.world;
+    *c_first = c_lo + skip;
+    if (*c_first > c_hi) return false;
+    *n_owned = (c_hi - *c_first) / p.world + 1;
+    return true;
+}
+__global__ void tc6_units_kernel(const TcParams p, uint32_t n_row_tiles, uint32_t* __restrict__ cnt) {
+    const uint32_t P = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P > p.n_pairs) return;
+    uint32_t a, b, c, n = 0;
+    if (P < p.n_pairs) tc6_pair_chunks(p, n_row_tiles, P, &a, &b, &c, &n);
+    cnt[P] = n;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc5Threads, 1)
+    hamming_tc6_kernel(const TcParams p, uint32_t n_row_tiles, uint32_t n_col_st) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;                                                             // 4 K-chunks x 128 rows x 128 B
+    uint8_t* sB = base + kT6ABytes;                                                 // ring: 8 x (96 rows x 128 B)
+    uint32_t* sP = reinterpret_cast<uint32_t*>(sB + kT6Stages * kT6StageBytes);     // packed A tile (16 KB), then 2 x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + 2 * kTileWords * 4);  // slots for column tiles
+    uint64_t* full = bars;                      // [8]  leader: 8 expander-warp arrivals
+    uint64_t* empty = bars + kT6Stages;         // [8]  commit multicast
+    uint64_t* pfull = bars + 2 * kT6Stages;     // [2]
+    uint64_t* pempty = pfull + 2;               // [2]
+    uint64_t* acc_full = pempty + 2;            // [2]
+    uint64_t* acc_empty = acc_full + 2;         // [2]
+    uint64_t* a_full = acc_empty + 2;           // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+
+    const uint32_t cr = tc_cluster_rank();
+    const uint32_t unit = blockIdx.x >> 1;
+    uint32_t lo = 0, hi = p.n_pairs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(p.unit_off + mid) <= unit) lo = mid;
+        else hi = mid;
+    }
+    const uint32_t P = lo;
+    uint32_t st_lo, st_hi, c_first, n_owned;
+    if (!tc6_pair_chunks(p, n_row_tiles, P, &st_lo, &st_hi, &c_first, &n_owned)) return;
+    const uint32_t c = c_first + (unit - __ldg(p.unit_off + P)) * p.world;
+    const uint32_t st0 = max(st_lo, c * p.chunk), st1 = min(min(st_hi, n_col_st), (c + 1) * p.chunk);
+    if (st0 >= st1) return;
+    const uint32_t n_st = st1 - st0;
+    const uint32_t I = 2 * P + cr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t* row_tiles = reinterpret_cast<const uint32_t*>(p.row_exp);
+    const uint32_t* col_tiles = reinterpret_cast<const uint32_t*>(p.col_exp);
+
+    if (tid == 0) {
+        for (int s = 0; s < kT6Stages; ++s) tc_mbar_init(&full[s], 8), tc_mbar_init(&empty[s], 1);
+        for (int b = 0; b < 2; ++b) {
+            tc_mbar_init(&pfull[b], 1), tc_mbar_init(&pempty[b], 4);
+            tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 8);
+        }
+        tc_mbar_init(a_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tc_mbar_expect_tx(a_full, kTileWords * 4);
+        tc_bulk_g2s(sP, row_tiles + (size_t)I * kTileWords, kTileWords * 4, a_full);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 2 && warp < 6) {  // constant block scales: 0x7F (UE8M0 1.0) in every byte of columns [384, 512), all lanes
+        uint32_t ones[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) ones[k] = 0x7F7F7F7Fu;
+        const uint32_t lanes = ((uint32_t)(warp & 3) * 32) << 16;
+        for (int q = 0; q < 4; ++q) tc_st32(tmem_base + lanes + 384 + q * 32, ones);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_mbar_wait(a_full, 0);
+    {   // A: 4 K-chunks x 128 rows; a warp covers 4 rows x 8 packed words (one 128 B line per quarter-warp)
+        const int w = lane & 7, r4 = lane >> 3;
+        for (int item = warp; item < 4 * 32; item += kTc5Threads / 32) {  // (K-chunk, 4-row group)
+            const int kc = item >> 5, row = (item & 31) * 4 + r4;
+            *reinterpret_cast<uint4*>(sA + kc * (kTile * kT6Chunk) + row * 128 + ((w ^ (row & 7)) << 4)) =
+                tc6_expand(sP[(kc * kTile + row) * 8 + w]);
+        }
+    }
+    tc_fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_cluster_sync();
+    tc_fence_after();
+    const uint32_t sfa = tmem_base + 384, sfb = tmem_base + 448;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== bulk-copy producer: this CTA's packed column tile (96 hashes) of every super-tile
+            for (uint32_t s = 0; s < n_st; ++s) {
+                const uint32_t pb = s & 1;
+                tc_mbar_wait(&pempty[pb], ((s >> 1) & 1) ^ 1);
+                tc_mbar_expect_tx(&pfull[pb], kT6PackedBytes);
+                tc_bulk_g2s(sP + pb * kTileWords, col_tiles + (size_t)(2 * (st0 + s) + cr) * (kT6PackedBytes / 4), kT6PackedBytes,
+                            &pfull[pb]);
+            }
+        }
+    } else if (warp == 1) {
+        if (cr == 0) {  // ===== MMA issuer
+            const uint64_t a_desc = tc_desc(tc_smem_u32(sA)), b_desc = tc_desc(tc_smem_u32(sB));
+            for (uint32_t s = 0; s < n_st; ++s) {
+                const uint32_t buf = s & 1;
+                tc_mbar_wait(&acc_empty[buf], ((s >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 192;
+#pragma unroll
+                for (int kc = 0; kc < 4; ++kc) {  // it = 4 s + kc: stage = 4 (s & 1) + kc, parity = (s >> 1) & 1
+                    const uint32_t stage = buf * 4 + kc;
+                    tc_mbar_wait(&full[stage], (s >> 1) & 1);
+                    tc_fence_after();
+                    if (tc_elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            tc6_mma(d_tmem, a_desc + ((kc * (kTile * kT6Chunk) + ks * 32) >> 4),
+                                    b_desc + ((stage * kT6StageBytes + ks * 32) >> 4), sfa, sfb, (kc | ks) != 0);
+                        tc2_commit(&empty[stage]);
+                        if (kc == 3) tc2_commit(&acc_full[buf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 6) {  // ===== expanders: a warp writes 4 rows x 8 units per iteration; warp e takes groups e, e+4, ..
+        const int w = lane & 7, r4 = lane >> 3;
+        uint32_t it = 0;
+        for (uint32_t s = 0; s < n_st; ++s) {
+            const uint32_t pb = s & 1;
+            tc_mbar_wait(&pfull[pb], (s >> 1) & 1);
+            const uint32_t* packed = sP + pb * kTileWords;
+            for (int kc = 0; kc < 4; ++kc, ++it) {
+                uint32_t bits[6];
+#pragma unroll
+                for (int g = 0; g < 6; ++g) bits[g] = packed[(kc * kT6Cols + ((warp - 6) + 4 * g) * 4 + r4) * 8 + w];
+                const uint32_t stage = it % kT6Stages;
+                tc_mbar_wait(&empty[stage], ((it / kT6Stages) & 1) ^ 1);
+                uint8_t* dst = sB + stage * kT6StageBytes;
+#pragma unroll
+                for (int g = 0; g < 6; ++g) {
+                    const int row = ((warp - 6) + 4 * g) * 4 + r4;
+                    *reinterpret_cast<uint4*>(dst + row * 128 + ((w ^ (row & 7)) << 4)) = tc6_expand(bits[g]);
+                }
+                tc_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive_remote(&full[stage], 0);
+            }
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&pempty[pb]);
+        }
+    } else {  // ===== epilogue
+        const uint32_t quarter = warp & 3;
+        const uint32_t row = quarter * 32 + lane;
+        const uint32_t gi = I * kTile + row;
+        const bool live = I < n_row_tiles;
+        const int thr = live ? (int)p.row_pc[gi] - (int)p.tol : 0x7FFFFFFF;
+        for (uint32_t s = 0; s < n_st; ++s) {
+            const uint32_t buf = s & 1;
+            tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
+            tc_fence_after();
+            const uint32_t col_first = (st0 + s) * (2 * kT6Cols);
+            const uint32_t* pcmin = p.col_pcmin + (col_first >> 6);
+            for (int q = 0; q < 3; ++q) {
+                uint32_t v[64];
+                const int floor_pc = (int)__ldg(pcmin + q);
+                __syncwarp();
+                tc_ld64(tmem_base + buf * 192 + q * 64 + ((quarter * 32) << 16), v);
+                uint32_t best = 0;  // accumulators are non-negative floats: their bit patterns order like the values
+#pragma unroll
+                for (int k = 0; k < 64; k += 2) best = max(best, max(v[k], v[k + 1]));
+                if (2 * (int)__uint_as_float(best) - floor_pc >= thr) {  // rare: exact test of the 64 columns
+                    const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
+                    uint64_t mask = 0;
+#pragma unroll
+                    for (int k4 = 0; k4 < 16; ++k4) {
+                        const uint4 pj = __ldg(pcj + k4);
+                        mask |= (uint64_t)(2 * (int)__uint_as_float(v[4 * k4 + 0]) - (int)pj.x >= thr) << (4 * k4 + 0);
+                        mask |= (uint64_t)(2 * (int)__uint_as_float(v[4 * k4 + 1]) - (int)pj.y >= thr) << (4 * k4 + 1);
+                        mask |= (uint64_t)(2 * (int)__uint_as_float(v[4 * k4 + 2]) - (int)pj.z >= thr) << (4 * k4 + 2);
+                        mask |= (uint64_t)(2 * (int)__uint_as_float(v[4 * k4 + 3]) - (int)pj.w >= thr) << (4 * k4 + 3);
+                    }
+                    while (mask) {
+                        const int k = __ffsll((long long)mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t gj = col_first + q * 64 + k;
+                        if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
+                            const unsigned long long slot = atomicAdd(p.counter, 1ull);
+                            if (slot < p.capacity) {
+                                const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
+                                p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive_remote(&acc_empty[buf], 0);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    tc_cluster_sync();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// rows: tiles of 128 hashes (+ pc); columns: tiles of 96 hashes padded to whole super-tiles (+ pc, pcmin)
+int tc6_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, bool as_columns, DevBuf& tiles, DevBuf& pc,
+             DevBuf& pcmin) {
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(d_hash);
+    if (!as_columns) {
+        const uint32_t T = (uint32_t)((n + kTile - 1) / kTile), T2 = (T + 1) & ~1u;
+        VDF_ALLOC(ctx, tiles.ensure((size_t)T2 * kTileWords * 4));
+        VDF_ALLOC(ctx, pc.ensure((size_t)T2 * kTile * 4));
+        tc6_pack_kernel<kTile><<<T2, 128, 0, ctx->stream>>>(in, perm, n, tiles.as<uint32_t>(), pc.as<uint32_t>());
+        VDF_LAUNCHED(ctx);
+        return VDF_OK;
+    }
+    // cover n rounded up to whole 128-hash tiles (the tile ranges count those), in whole super-tiles: T2 * 96 is a
+    // multiple of 192 and of 64
+    const uint64_t n128 = (n + kTile - 1) / kTile * kTile;
+    const uint32_t T = (uint32_t)((n128 + kT6Cols - 1) / kT6Cols), T2 = (T + 1) & ~1u;
+    VDF_ALLOC(ctx, tiles.ensure((size_t)T2 * kT6PackedBytes));
+    VDF_ALLOC(ctx, pc.ensure((size_t)T2 * kT6Cols * 4));
+    VDF_ALLOC(ctx, pcmin.ensure((size_t)T2 * kT6Cols / 64 * 4));
+    tc6_pack_kernel<kT6Cols><<<T2, 128, 0, ctx->stream>>>(in, perm, n, tiles.as<uint32_t>(), pc.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    const uint64_t groups = (uint64_t)T2 * kT6Cols / 64;
+    pcmin64_kernel<<<(unsigned)((groups + 7) / 8), 256, 0, ctx->stream>>>(pc.as<uint32_t>(), groups, pcmin.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    return VDF_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& exp, DevBuf& pc) {
     const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
@@ -855,6 +1176,39 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
             chunk >>= 1;
         while ((n_st + chunk - 1) / chunk > 65535) chunk *= 2;
         p.chunk = chunk;
+        if (ctx->search_variant == 6) {  // as variant 5, super-tiles of 192 columns
+            static bool attr6 = false;
+            if (!attr6) {
+                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+                attr6 = true;
+            }
+            const uint32_t n_col_st = (uint32_t)(((uint64_t)n_col_tiles * kTile + 2 * kT6Cols - 1) / (2 * kT6Cols));
+            uint32_t ch = ctx->tc_chunk ? ctx->tc_chunk : 128;
+            while (!ctx->tc_chunk && ch > 2 && (uint64_t)n_pairs * ((n_col_st + ch - 1) / ch) < (uint64_t)(ctx->sm_count / 2) * 64 * ctx->world)
+                ch >>= 1;
+            p.chunk = ch;
+            p.n_pairs = n_pairs;
+            VDF_ALLOC(ctx, ctx->unit_cnt.ensure((size_t)(n_pairs + 1) * 4));
+            VDF_ALLOC(ctx, ctx->unit_off.ensure((size_t)(n_pairs + 1) * 4));
+            p.unit_off = ctx->unit_off.as<uint32_t>();
+            tc6_units_kernel<<<(n_pairs + 1 + 255) / 256, 256, 0, ctx->stream>>>(p, n_row_tiles, ctx->unit_cnt.as<uint32_t>());
+            VDF_LAUNCHED(ctx);
+            size_t tmp = 0;
+            VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->unit_cnt.as<uint32_t>(), ctx->unit_off.as<uint32_t>(),
+                                                        (size_t)n_pairs + 1, ctx->stream));
+            VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
+            VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tmp, ctx->unit_cnt.as<uint32_t>(),
+                                                        ctx->unit_off.as<uint32_t>(), (size_t)n_pairs + 1, ctx->stream));
+            uint32_t n_units = 0;
+            VDF_CUDA(ctx, cudaMemcpyAsync(&n_units, ctx->unit_off.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (n_units == 0) return VDF_OK;
+            kt_begin(ctx, 0);
+            hamming_tc6_kernel<<<2 * n_units, kTc5Threads, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
+            kt_end(ctx, 0);
+            VDF_LAUNCHED(ctx);
+            return VDF_OK;
+        }
         if (ctx->search_variant == 5) {  // 1-D grid over exactly the units this rank owns
             p.n_pairs = n_pairs;
             VDF_ALLOC(ctx, ctx->unit_cnt.ensure((size_t)(n_pairs + 1) * 4));
