@@ -140,7 +140,7 @@ def measured_peaks():
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
-DEFAULT_SEARCH_VARIANT = 5   # vdf_ctx::search_variant in csrc/common.cuh
+DEFAULT_SEARCH_VARIANT = 6   # vdf_ctx::search_variant in csrc/common.cuh
 PAIR_MACS = 1024             # tensor-core variants: hamming = pc(a) + pc(b) - 2 <a, b>, one u8 MAC per stored bit
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from `ncu --set full` captures
 

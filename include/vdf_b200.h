@@ -114,7 +114,8 @@ int vdf_ctx_set_shard(vdf_ctx* ctx, uint32_t rank, uint32_t world);
 /* Tuning knobs: "max_edges" (edge-buffer growth cap, default 2^28), "initial_edges" (default 2^22),
  * "search_variant": 0 = XOR+POPC; 1, 2 = XOR + carry-save adders + POPC (8x8 / 8x4 pairs per thread);
  *   3 = tcgen05.mma kind::i8 on byte-expanded tiles; 4 = the same on CTA pairs (cta_group::2);
- *   5 (default) = CTA pairs on packed tiles, bits expanded to bytes inside the kernel.  All six are bit-identical.
+ *   5 = CTA pairs on packed tiles, bits expanded to bytes inside the kernel; 6 (default) = the same with the bits
+ *   expanded to e2m1 nibbles and tcgen05.mma kind::mxf4 (twice the kind::i8 rate).  All seven are bit-identical.
  * "tc_chunk": column super-tiles per work unit of variants 4/5 (0 = automatic); "hash_variant": resize kernel choice. */
 int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value);
 

@@ -10,7 +10,7 @@ from tests import synth
 from vid_dup_finder_lib_b200 import _ffi
 
 pytestmark = pytest.mark.gpu
-DEFAULT_VARIANT = 5  # tcgen05 cta_group::2 on packed tiles (common.cuh: vdf_ctx::search_variant)
+DEFAULT_VARIANT = 6  # tcgen05 cta_group::2, kind::mxf4, packed tiles (common.cuh: vdf_ctx::search_variant)
 
 
 @pytest.fixture(scope="module")

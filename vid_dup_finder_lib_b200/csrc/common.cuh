@@ -92,9 +92,10 @@ struct vdf_ctx {
     std::string err;
     uint32_t rank = 0, world = 1;
     uint64_t max_edges = 1ull << 28, initial_edges = 1ull << 22;
-    int search_variant = 5;  // 0: plain XOR + POPC; 1: XOR + carry-save adder + POPC, 8x8 pairs/thread;
+    int search_variant = 6;  // 0: plain XOR + POPC; 1: XOR + carry-save adder + POPC, 8x8 pairs/thread;
                              // 2: carry-save on 8x4 pairs/thread, two CTAs per SM; 3: tcgen05 kind::i8, byte-expanded
-                             // tiles in HBM; 4: the same on CTA pairs; 5 (default): CTA pairs, packed tiles (search_tc.cu)
+                             // tiles in HBM; 4: the same on CTA pairs; 5: CTA pairs, packed tiles, kind::i8;
+                             // 6 (default): CTA pairs, packed tiles, kind::mxf4 on e2m1 {0, 1} operands (search_tc.cu)
     int hash_variant = 0;
     uint32_t tc_chunk = 0;  // column super-tiles per CTA-pair work unit (0: automatic)
     uint32_t hash_chunks = 1;  // hash.cu: software-pipeline chunks per call (1: letterbox, then resize, over the whole batch)
