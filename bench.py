@@ -331,21 +331,30 @@ def main():
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 step()
+            if flush_l2:
+                flush.fill_(1)  # the first launch of torch's fill kernel loads its module (5 ms .. 1 s): not inside the timing
             gc.collect()
             gc.disable()  # a generation-2 collection between two launches would show up as GPU idle time
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             w0 = time.perf_counter()
             e0.record(stream)
+            dbg_t = []
             for _ in range(steps):
                 if flush_l2:
+                    t_a = time.perf_counter()
                     flush.fill_(1)
+                    t_b = time.perf_counter()
+                    if os.environ.get("VDF_BENCH_DEBUG"):
+                        stream.synchronize()
+                        dbg_t.append((1e3 * (t_b - t_a), 1e3 * (time.perf_counter() - t_b)))
                 step()
             e1.record(stream)
             w1 = time.perf_counter()
             barrier()
             gc.enable()
         if os.environ.get("VDF_BENCH_DEBUG"):
+            print("[timed] flush (launch ms, gpu ms):", [(round(a, 2), round(b, 2)) for a, b in dbg_t], file=sys.stderr)
             print(f"[timed] events {e0.elapsed_time(e1):.1f} ms, host wall {1e3 * (w1 - w0):.1f} ms, barrier {1e3 * (time.perf_counter() - w1):.1f} ms",
                   file=sys.stderr)
         return max_over_ranks(e0.elapsed_time(e1) * 1e-3)

@@ -825,6 +825,8 @@ constexpr int kT6Chunk = 128;                        // bytes per row per K-chun
 constexpr int kT6ABytes = 4 * kTile * kT6Chunk;      // 64 KB
 constexpr int kT6StageBytes = kT6Cols * kT6Chunk;    // 12 KB
 constexpr int kT6Stages = 8;
+constexpr int kT6Expanders = 4;                      // expander warps (24 four-row groups per stage: 4 each)
+constexpr int kTc6Threads = (6 + kT6Expanders) * 32; // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. expanders
 constexpr int kT6PackedBytes = kT6Cols * 128;        // packed column tile: 96 x 128 B = 12 KB; packed row tile: 16 KB
 constexpr size_t kTc6Smem = (size_t)kT6ABytes + kT6Stages * kT6StageBytes + 2 * kTileWords * 4 /* packed A, then 2 packed column tiles */ + 1024 + 256;
 // block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): a/b format E2M1 = 1 at [7,10) / [10,13),
@@ -905,7 +907,7 @@ __global__ void tc6_units_kernel(const TcParams p, uint32_t n_row_tiles, uint32_
     cnt[P] = n;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc5Threads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
     hamming_tc6_kernel(const TcParams p, uint32_t n_row_tiles, uint32_t n_col_st) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -943,9 +945,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc5Threads, 1)
     const uint32_t* col_tiles = reinterpret_cast<const uint32_t*>(p.col_exp);
 
     if (tid == 0) {
-        for (int s = 0; s < kT6Stages; ++s) tc_mbar_init(&full[s], 8), tc_mbar_init(&empty[s], 1);
+        for (int s = 0; s < kT6Stages; ++s) tc_mbar_init(&full[s], 2 * kT6Expanders), tc_mbar_init(&empty[s], 1);
         for (int b = 0; b < 2; ++b) {
-            tc_mbar_init(&pfull[b], 1), tc_mbar_init(&pempty[b], 4);
+            tc_mbar_init(&pfull[b], 1), tc_mbar_init(&pempty[b], kT6Expanders);
             tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 8);
         }
         tc_mbar_init(a_full, 1);
@@ -971,7 +973,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc5Threads, 1)
     tc_mbar_wait(a_full, 0);
     {   // A: 4 K-chunks x 128 rows; a warp covers 4 rows x 8 packed words (one 128 B line per quarter-warp)
         const int w = lane & 7, r4 = lane >> 3;
-        for (int item = warp; item < 4 * 32; item += kTc5Threads / 32) {  // (K-chunk, 4-row group)
+        for (int item = warp; item < 4 * 32; item += kTc6Threads / 32) {  // (K-chunk, 4-row group)
             const int kc = item >> 5, row = (item & 31) * 4 + r4;
             *reinterpret_cast<uint4*>(sA + kc * (kTile * kT6Chunk) + row * 128 + ((w ^ (row & 7)) << 4)) =
                 tc6_expand(sP[(kc * kTile + row) * 8 + w]);
@@ -1019,28 +1021,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc5Threads, 1)
                 }
             }
         }
-    } else if (warp >= 6) {  // ===== expanders: a warp writes 4 rows x 8 units per iteration; warp e takes groups e, e+4, ..
+    } else if (warp >= 6) {  // ===== expanders: a warp writes 4 rows x 8 units per iteration; warp e takes groups e, e+6, ..
+        constexpr int kG = 24 / kT6Expanders;  // four-row groups per warp per stage
         const int w = lane & 7, r4 = lane >> 3;
+        const int row0 = (warp - 6) * 4 + r4;  // + 4 * kT6Expanders * g
         uint32_t it = 0;
         for (uint32_t s = 0; s < n_st; ++s) {
             const uint32_t pb = s & 1;
             tc_mbar_wait(&pfull[pb], (s >> 1) & 1);
-            const uint32_t* packed = sP + pb * kTileWords;
-            for (int kc = 0; kc < 4; ++kc, ++it) {
-                uint32_t bits[6];
+            const uint32_t* packed = sP + pb * kTileWords + row0 * 8 + w;
+            uint32_t bits[kG];
 #pragma unroll
-                for (int g = 0; g < 6; ++g) bits[g] = packed[(kc * kT6Cols + ((warp - 6) + 4 * g) * 4 + r4) * 8 + w];
+            for (int g = 0; g < kG; ++g) bits[g] = packed[g * (4 * kT6Expanders * 8)];
+            for (int kc = 0; kc < 4; ++kc, ++it) {
+                uint32_t next[kG];  // the next K-chunk's words are in flight while this one is expanded
+#pragma unroll
+                for (int g = 0; g < kG; ++g) next[g] = kc < 3 ? packed[((kc + 1) * kT6Cols + g * (4 * kT6Expanders)) * 8] : 0u;
                 const uint32_t stage = it % kT6Stages;
                 tc_mbar_wait(&empty[stage], ((it / kT6Stages) & 1) ^ 1);
                 uint8_t* dst = sB + stage * kT6StageBytes;
 #pragma unroll
-                for (int g = 0; g < 6; ++g) {
-                    const int row = ((warp - 6) + 4 * g) * 4 + r4;
+                for (int g = 0; g < kG; ++g) {
+                    const int row = row0 + 4 * kT6Expanders * g;
                     *reinterpret_cast<uint4*>(dst + row * 128 + ((w ^ (row & 7)) << 4)) = tc6_expand(bits[g]);
                 }
                 tc_fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive_remote(&full[stage], 0);
+#pragma unroll
+                for (int g = 0; g < kG; ++g) bits[g] = next[g];
             }
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&pempty[pb]);
@@ -1204,7 +1213,7 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
             VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (n_units == 0) return VDF_OK;
             kt_begin(ctx, 0);
-            hamming_tc6_kernel<<<2 * n_units, kTc5Threads, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
+            hamming_tc6_kernel<<<2 * n_units, kTc6Threads, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
             kt_end(ctx, 0);
             VDF_LAUNCHED(ctx);
             return VDF_OK;
