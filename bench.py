@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--stacks", type=int, default=256, help="1080p stacks resident in HBM per GPU (8.5 GB at 256)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT", help="extra vdf_ctx_set_option (kernel experiments)")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -163,15 +164,22 @@ def search_roofline(variant: int, pairs_per_launch: float, k_ms: float, k_n: int
         rate = 4.0 if variant == 6 else 2.0   # 4-bit operands issue at four times the bf16 rate, 8-bit at twice
         macs = 16384 if variant == 6 else 8192  # MAC/clk/SM: 128 x 256 x {64 | 32} per 128 clk
         what = "4-bit" if variant == 6 else "8-bit"
-        peak, src = (rate * bf16, f"{rate:g} x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json, burst): {what} operands run at "
-                     f"{rate:g}x the bf16 rate") if bf16 else (2250.0 * rate, f"fallback: nominal dense {what} peak (B200_PROFILING.md)")
+        bf16_peak, bf16_src = (rate * bf16, f"{rate:g} x measured dense bf16 TFLOP/s (MEASURED_PEAKS.json, burst): {what} operands run "
+                               f"at {rate:g}x the bf16 rate") if bf16 else (2250.0 * rate, f"fallback: nominal dense {what} peak (B200_PROFILING.md)")
         pipe = sm_count * macs * 2 * sm_max_mhz * 1e6 / 1e12
+        # peak = the tcgen05 issue rate measured on this pool's B200 by csrc/microbench.cu (same instruction shape, same operand
+        # encoding, resident operands, nothing else running; sustained run) -- the way the POPC roofline is defined
+        peak, src = umma_peak_tops("tcgen05_mxf4_2cta_m256n192k64" if variant == 6 else "tcgen05_i8_2cta_m256n256k32")
+        if peak is None:
+            peak, src = bf16_peak, bf16_src
         achieved = 2.0 * PAIR_MACS * pairs_per_launch / (ms * 1e-3) / 1e12 if k_n else None
         kname = {3: "hamming_tc_kernel", 4: "hamming_tc2_kernel", 5: "hamming_tc5_kernel", 6: "hamming_tc6_kernel"}[variant]
         return {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(kname, n_key) if n_key else None,
                 "peak_source": src, "pipe_peak": pipe, "pipe_frac": (achieved / pipe) if achieved else None,
-                "pipe_peak_source": f"148 SMs x {macs} {what} MAC/clk/SM x 2 x max SM clock (tcgen05 issue floor, B300_MICROARCH.md)",
+                "pipe_peak_source": f"148 SMs x {macs} {what} MAC/clk/SM x 2 x max SM clock (nominal tcgen05 issue floor, B300_MICROARCH.md)",
+                "cublas_scaled_peak": bf16_peak, "cublas_scaled_frac": (achieved / bf16_peak) if achieved else None,
+                "cublas_scaled_peak_source": bf16_src,
                 "kernel_ms_per_launch": ms, "kernel_launches_timed": k_n, "algorithmic_ops_per_pair": 2 * PAIR_MACS,
                 "popc_equivalent": {"algorithmic_popc32_per_pair": PAIR_POPC32,
                                     "frac_of_popc_peak": PAIR_POPC32 * pairs_per_launch / (ms * 1e-3) / 1e9 /
@@ -184,6 +192,17 @@ def search_roofline(variant: int, pairs_per_launch: float, k_ms: float, k_n: int
             "traffic": ncu_traffic(kname, n_key) if n_key else None,
             "peak_source": popc_src, "kernel_ms_per_launch": ms, "kernel_launches_timed": k_n,
             "algorithmic_popc32_per_pair": PAIR_POPC32}
+
+
+def umma_peak_tops(op: str):
+    """Measured tcgen05.mma issue rate (2 ops per MAC) from profiles/microbench.json; (None, None) if not recorded."""
+    p = os.path.join(ROOT, "profiles", "microbench.json")
+    try:
+        recs = [r for r in json.load(open(p)) if r.get("op") == op]
+        best = [r for r in recs if r.get("run") == "sustained"] or recs
+        return best[0]["ops_per_s"] / 1e12, f"measured {op} issue rate, sustained run (csrc/microbench.cu -> profiles/microbench.json)"
+    except Exception:
+        return None, None
 
 
 def popc_peak_gpopc(sm_count: int, sm_max_mhz: float):
@@ -306,6 +325,9 @@ def main():
         ctx.set_option("search_variant", args.variant)
     if args.hash_variant >= 0:
         ctx.set_option("hash_variant", args.hash_variant)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
@@ -421,7 +443,7 @@ def main():
                                           "index_remap": ph[3], "note": "inside vdf_search (csrc/host.cu); the rest of the "
                                           "call is building the MatchGroup objects"}
         out = {"metric": "hamming_pair_comparisons_per_s", "value": value, "unit": "pairs/s", "ms_per_step": secs / steps * 1e3,
-               "scaling": "strong", "dtype": "u8 x u8 -> s32" if variant >= 3 else "u32", "roofline": roof, "e2e": e2e,
+               "scaling": "strong", "dtype": "e2m1 x e2m1 -> f32 (exact)" if variant == 6 else "u8 x u8 -> s32" if variant >= 3 else "u32", "roofline": roof, "e2e": e2e,
                "gpu_launches": int(launches),
                "clocks": cs.summary(),
                "config": {"workload": f"all-pairs search (find_all_matches), {n} synthetic hashes, equal durations, "
@@ -479,7 +501,7 @@ def main():
         pairs = nq * nc
         variant = args.variant if args.variant >= 0 else DEFAULT_SEARCH_VARIANT
         return {"metric": "hamming_pair_comparisons_per_s", "value": pairs * steps / secs, "unit": "pairs/s",
-                "ms_per_step": secs / steps * 1e3, "scaling": "strong", "dtype": "u8 x u8 -> s32" if variant >= 3 else "u32",
+                "ms_per_step": secs / steps * 1e3, "scaling": "strong", "dtype": "e2m1 x e2m1 -> f32 (exact)" if variant == 6 else "u8 x u8 -> s32" if variant >= 3 else "u32",
                 "roofline": search_roofline(variant, pairs / world, k_ms, k_n, sm_count, sm_max_mhz),
                 "gpu_launches": int(launches), "clocks": cs.summary(),
                 "config": {"workload": f"search_with_references, {nq} queries x {nc} sorted table entries, equal durations, "

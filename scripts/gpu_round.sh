@@ -83,6 +83,25 @@ if [[ $STEP == ncu2 ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_side -c 1 -f -o gpurun_out/prof_letterbox__stacks_256_1920x1080 \
       python bench.py --workload hash --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
 fi
+if [[ $STEP == r6 ]]; then
+  # refresh of the tracked evidence with search variant 6 (kind::mxf4) as the library default
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
+  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+  timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "bench reference rc=$?"; tail -c 1500 gpurun_out/bench_reference.json
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary --e2e-steps 1 > gpurun_out/bench_under_ncu.json 2>&1; echo "ncu list rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tc6 -c 1 -f -o gpurun_out/prof_hamming_tc6__self_1000000_x1 \
+      python bench.py --steps 1 --warmup 0 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming_tc6.log 2>&1; echo "ncu tc6 rc=$?"
+fi
+if [[ $STEP == x7 ]]; then
+  # variant-6 experiments: expander warps x work-unit order; tcgen05 issue-rate microbenchmark
+  timeout 300 ./vid_dup_finder_lib_b200/vdf_microbench > gpurun_out/microbench.jsonl 2>&1; echo "microbench rc=$?"; tail -5 gpurun_out/microbench.jsonl
+  timeout 900 python -m pytest tests/test_gpu_search.py -m gpu -x -q > gpurun_out/pytest_search.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_search.log
+  for o in 0 1; do for e in 4 6 8; do
+    timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_expanders=$e --opt tc_unit_order=$o --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x7_e${e}_o${o}.json 2> gpurun_out/bench_x7_e${e}_o${o}.err; echo "bench e=$e o=$o rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x7_e${e}_o${o}.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x7_e${e}_o${o}.err
+  done; done
+fi
 if [[ $STEP == big ]]; then
   # BASELINE configs[3] and [4] sizes on one GPU: 100k queries x 10M-entry table; all-pairs over a 10M-hash corpus
   timeout 900 python bench.py --workload refs --steps 3 --warmup 1 > gpurun_out/bench_refs_10m.json 2> gpurun_out/bench_refs_10m.err; echo "bench refs rc=$?"; tail -c 1200 gpurun_out/bench_refs_10m.json; tail -3 gpurun_out/bench_refs_10m.err

@@ -320,6 +320,33 @@ def test_shards_partition_the_pair_matrix(ctx, world, variant):
     assert np.array_equal(allp, want)
 
 
+@pytest.mark.parametrize("expanders,order", [(4, 1), (6, 0), (8, 0), (8, 1)])
+def test_variant6_kernel_options_do_not_change_results(ctx, expanders, order):
+    """expander-warp count and work-unit order (chunk-major / row-pair-major) of the kind::mxf4 kernel, incl. a sharded run
+    with small chunks so that the unit list has many chunks per row pair"""
+    rng = np.random.default_rng(77)
+    H, dur = _case(rng, 5000, 400, 200, [600, 610, 650, 700])
+    want = o.self_edges(H, dur, 320)
+    ctx.set_option("search_variant", 6)
+    ctx.set_option("tc_expanders", expanders)
+    ctx.set_option("tc_unit_order", order)
+    ctx.set_option("tc_chunk", 2)
+    try:
+        assert np.array_equal(ctx.search_self(H, dur, 320), want)
+        parts = []
+        for r in range(3):
+            ctx.set_shard(r, 3)
+            parts.append(ctx.search_self(H, dur, 320))
+        allp = np.concatenate(parts)
+        assert np.array_equal(allp[np.lexsort((allp[:, 1], allp[:, 0]))], want)
+    finally:
+        ctx.set_shard(0, 1)
+        ctx.set_option("tc_chunk", 0)
+        ctx.set_option("tc_unit_order", 0)
+        ctx.set_option("tc_expanders", 0)
+        ctx.set_option("search_variant", DEFAULT_VARIANT)
+
+
 def test_parity_at_65536_planted(ctx):
     """full CPU-vs-GPU parity at N = 2^16 on the planted-duplicate generator (log-normal durations
     exercise the windows)."""

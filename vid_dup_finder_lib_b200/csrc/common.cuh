@@ -98,6 +98,8 @@ struct vdf_ctx {
                              // 6 (default): CTA pairs, packed tiles, kind::mxf4 on e2m1 {0, 1} operands (search_tc.cu)
     int hash_variant = 0;
     uint32_t tc_chunk = 0;  // column super-tiles per CTA-pair work unit (0: automatic)
+    uint32_t tc_unit_order = 0;  // variant 6 work-unit order: 0 chunk-major (L2-friendly, default), 1 row-pair-major
+    uint32_t tc_expanders = 0;  // expander warps of the variant-6 kernel: 4, 6 or 8 (0: default)
     uint32_t hash_chunks = 1;  // hash.cu: software-pipeline chunks per call (1: letterbox, then resize, over the whole batch)
     int grouping = 0;       // 0: the reference's greedy rule (parity); 1: connected components (GPU union-find, group.cu)
     uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -111,7 +113,7 @@ struct vdf_ctx {
     // search scratch
     vdf::DevBuf row_tiles, col_tiles, row_lo, row_hi, row_id, tile_range, raw_keys, sort_tmp, misc, keys_a, keys_b;
     vdf::DevBuf in_hash, in_dur, in_hash2, in_dur2, ref_perm, ref_key;
-    vdf::DevBuf exp_rows, exp_cols, pc_rows, pc_cols, pcmin_rows, pcmin_cols, unit_cnt, unit_off;  // tensor-core search: byte-expanded tiles + popcounts
+    vdf::DevBuf exp_rows, exp_cols, pc_rows, pc_cols, pcmin_rows, pcmin_cols, unit_cnt, unit_off, unit_list_a, unit_list_b;  // tensor-core search: byte-expanded tiles + popcounts
     // grouping scratch
     vdf::DevBuf g_rk, g_rks, g_state, g_parent, g_wl0, g_wla, g_wlb, g_mk, g_mks, g_flag, g_scan, g_gp, g_mem;
     // hashing scratch

@@ -75,6 +75,147 @@ __global__ void __launch_bounds__(256) stream_read_kernel(const uint4* __restric
     if (acc == 0xdeadbeef) out[0] = acc;
 }
 
+
+// ------------------------------------------------------------------------------------------------ tcgen05 issue rate
+// The rate the tensor-core search kernels (search_tc.cu, variants 5 and 6) are bounded by: one CTA pair per two SMs issues
+// back-to-back tcgen05.mma.cta_group::2 on resident shared-memory operands (random {0,1}-valued data in the same SWIZZLE_128B
+// K-major layout and value encoding as the search kernel, so the power draw is comparable), two accumulators in flight,
+// nothing else running.  KIND 0: kind::i8, M 256 x N 256 x K 32.  KIND 1: kind::mxf4 (block scales 1.0), M 256 x N 192 x K 64.
+__device__ __forceinline__ uint32_t mb_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(mb_smem(bar)), "r"(parity)
+                     : "memory");
+}
+__device__ __forceinline__ uint64_t mb_desc(uint32_t a) {  // K-major SWIZZLE_128B, SBO 1024 B (as search_tc.cu tc_desc)
+    return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_kernel(uint32_t iters, uint32_t seed, uint32_t* out) {
+    extern __shared__ __align__(1024) uint8_t mb_raw[];
+    uint8_t* base = mb_raw + ((1024u - (mb_smem(mb_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;            // 4 K-chunks x 128 rows x 128 B
+    uint8_t* sB = base + 65536;    // 4 K-chunks x 128 rows x 128 B (kind::mxf4 reads 96 rows of each)
+    uint64_t* done = reinterpret_cast<uint64_t*>(base + 131072);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(done + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t cr;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
+    uint32_t x = seed * 2654435761u + blockIdx.x * 40503u + tid * 9781u + 1u;
+    for (int i = tid; i < 131072 / 4; i += 128) {  // random bits in the operand encodings of the search kernels
+        x ^= x << 13, x ^= x >> 17, x ^= x << 5;
+        reinterpret_cast<uint32_t*>(base)[i] = KIND == 0 ? (x & 0x01010101u) << (i & 7) : (x & 0x22222222u);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb_smem(&done[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb_smem(&done[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mb_smem(slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t tmem = *slot;
+    if (KIND == 1) {  // UE8M0 1.0 in every byte of columns [384, 512)
+        const uint32_t lanes = ((uint32_t)warp * 32) << 16;
+        for (int c = 384; c < 512; c += 8)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(tmem + lanes + c), "r"(0x7F7F7F7Fu)
+                         : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0 && cr == 0) {
+        const uint64_t da = mb_desc(mb_smem(sA)), db = mb_desc(mb_smem(sB));
+        constexpr uint32_t idesc_i8 = (2u << 4) | (32u << 17) | (16u << 24);
+        constexpr uint32_t idesc_f4 = (1u << 7) | (1u << 10) | ((192u >> 3) << 17) | (1u << 23) | ((256u >> 4) << 24);
+        constexpr uint32_t N = KIND == 0 ? 256 : 192;
+        for (uint32_t it = 0; it < iters; ++it) {
+            const uint32_t buf = it & 1;
+            if (it >= 2) mb_wait(&done[buf], ((it >> 1) - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t pred;
+            asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+            if (pred) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint64_t off = (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4);
+                    if (KIND == 0)
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
+                                         tmem + buf * N),
+                                     "l"(da + off), "l"(db + off), "r"(idesc_i8), "r"((uint32_t)(k != 0))
+                                     : "memory");
+                    else
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(
+                                tmem + buf * N),
+                            "l"(da + off), "l"(db + off), "r"(idesc_f4), "r"((uint32_t)(k != 0)), "r"(tmem + 384), "r"(tmem + 448)
+                            : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                                 mb_smem(&done[buf])),
+                             "h"((uint16_t)1)
+                             : "memory");
+            }
+            __syncwarp();
+        }
+        if (iters >= 2) mb_wait(&done[iters & 1], ((iters >> 1) - 1) & 1);  // batch iters - 2
+        if (iters >= 1) mb_wait(&done[(iters - 1) & 1], (((iters - 1) >> 1)) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+    if (iters == 0xFFFFFFFFu) out[0] = tmem;
+}
+
+// tensor-memory read rate: every warp of the CTA streams tcgen05.ld.32x32b.x64 (8 KB per warp-load) over its lane quarter;
+// this is what bounds the epilogue of the search kernels (one fp32 / s32 accumulator read per pair)
+#define MB_R8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+__global__ void __launch_bounds__(256, 1) ldtm_rate_kernel(uint32_t iters, uint32_t* out) {
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mb_smem(&slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = slot + (((uint32_t)(warp & 3) * 32) << 16);
+    uint32_t sink = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        uint32_t v[64];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+            "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,"
+            "%62,%63}, [%64];"
+            : MB_R8(v, 0), MB_R8(v, 8), MB_R8(v, 16), MB_R8(v, 24), MB_R8(v, 32), MB_R8(v, 40), MB_R8(v, 48), MB_R8(v, 56)
+            : "r"(tmem + ((it & 7) * 64))
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 64; k += 16) sink ^= v[k];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512u) : "memory");
+    if (sink == 0x12345678u) out[0] = sink;
+}
+
 template <typename F>
 static float time_ms(F&& launch, int reps = 5) {
     cudaEvent_t a, b;
@@ -123,6 +264,34 @@ int main() {
         double macs = (double)blocks * 8 * ITERS * 4 * (16.0 * 8 * 32);
         printf("{\"op\": \"imma_m16n8k32_u8s8\", \"ms\": %.3f, \"macs_per_s\": %.4e, \"macs_per_clk_per_sm_at_max_clock\": %.1f}\n",
                ms, macs / (ms * 1e-3), macs / (ms * 1e-3) / ((double)clk_khz * 1e3) / sms);
+    }
+    for (int kind = 0; kind < 2; ++kind) {  // tcgen05 issue rate: burst (~10 ms) and sustained (~150 ms, the power-capped state)
+        const size_t smem = 131072 + 1024 + 64;
+        if (kind == 0) CK(cudaFuncSetAttribute(umma_rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CK(cudaFuncSetAttribute(umma_rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const double macs_per_batch = 16.0 * 256 * (kind == 0 ? 256.0 * 32 : 192.0 * 64);
+        for (int len = 0; len < 2; ++len) {
+            const uint32_t iters = (len == 0 ? 10000u : 150000u);
+            const int pairs = sms / 2;
+            float ms = time_ms([&] {
+                if (kind == 0) umma_rate_kernel<0><<<2 * pairs, 128, smem>>>(iters, 7, d_out);
+                else umma_rate_kernel<1><<<2 * pairs, 128, smem>>>(iters, 7, d_out);
+            }, 3);
+            CK(cudaGetLastError());
+            const double macs = macs_per_batch * iters * pairs;
+            printf("{\"op\": \"%s\", \"run\": \"%s\", \"ms\": %.3f, \"macs_per_s\": %.4e, \"ops_per_s\": %.4e, "
+                   "\"macs_per_clk_per_sm_at_max_clock\": %.1f}\n",
+                   kind == 0 ? "tcgen05_i8_2cta_m256n256k32" : "tcgen05_mxf4_2cta_m256n192k64", len == 0 ? "burst" : "sustained", ms,
+                   macs / (ms * 1e-3), 2 * macs / (ms * 1e-3), macs / (ms * 1e-3) / ((double)clk_khz * 1e3) / (2 * pairs));
+        }
+    }
+    for (int warps = 4; warps <= 8; warps += 4) {
+        const uint32_t iters = 20000;
+        float ms = time_ms([&] { ldtm_rate_kernel<<<sms, warps * 32>>>(iters, d_out); }, 3);
+        CK(cudaGetLastError());
+        const double bytes = (double)sms * warps * iters * 8192.0;
+        printf("{\"op\": \"tcgen05_ld_32x32b_x64\", \"warps\": %d, \"ms\": %.3f, \"bytes_per_s\": %.4e, \"bytes_per_clk_per_sm_at_max_clock\": %.1f}\n",
+               warps, ms, bytes / (ms * 1e-3), bytes / (ms * 1e-3) / ((double)clk_khz * 1e3) / sms);
     }
     {
         size_t bytes = (size_t)8 << 30;

@@ -16,6 +16,7 @@
 // hashes x 1024 B = 128 KB) stays resident; column super-tiles (B, 256 hashes) stream through a 2-stage ring of
 // 32 KB K-chunks; each super-tile is 8 chunks x 4 MMAs of 128x256x32; two 256-column TMEM accumulators let the
 // epilogue of super-tile t overlap the MMAs of t+1.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -154,6 +155,7 @@ struct TcParams {
     uint32_t rank, world;
     const uint32_t* unit_off;  // variant 5: exclusive scan of the work units each row pair owns on this rank
     uint32_t n_pairs;
+    const uint64_t* unit_list;  // variant 6: (chunk << 32 | row pair) of every unit this rank owns, chunk-major
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const TcParams p) {
@@ -825,8 +827,9 @@ constexpr int kT6Chunk = 128;                        // bytes per row per K-chun
 constexpr int kT6ABytes = 4 * kTile * kT6Chunk;      // 64 KB
 constexpr int kT6StageBytes = kT6Cols * kT6Chunk;    // 12 KB
 constexpr int kT6Stages = 8;
-constexpr int kT6Expanders = 4;                      // expander warps (24 four-row groups per stage: 4 each)
-constexpr int kTc6Threads = (6 + kT6Expanders) * 32; // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. expanders
+constexpr uint32_t kT6DefaultExpanders = 4;
+// expander warps E (template parameter: 4, 6 or 8; 24 four-row groups per stage, 24 / E each); threads = (6 + E) * 32:
+// warp 0 producer, 1 MMA, 2-5 epilogue, 6.. expanders
 constexpr int kT6PackedBytes = kT6Cols * 128;        // packed column tile: 96 x 128 B = 12 KB; packed row tile: 16 KB
 constexpr size_t kTc6Smem = (size_t)kT6ABytes + kT6Stages * kT6StageBytes + 2 * kTileWords * 4 /* packed A, then 2 packed column tiles */ + 1024 + 256;
 // block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): a/b format E2M1 = 1 at [7,10) / [10,13),
@@ -907,8 +910,22 @@ __global__ void tc6_units_kernel(const TcParams p, uint32_t n_row_tiles, uint32_
     cnt[P] = n;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
+// the units of row pair P, in P-major order; a stable sort on the chunk bits then makes the list chunk-major, so that the
+// CTA pairs resident together walk the SAME column chunk (3 MB) and the packed column tiles are served by L2.  In P-major
+// order 74 resident pairs stream 74 different chunks (230 MB > L2) and every launch re-reads the table from HBM ~600 times.
+__global__ void tc6_unit_list_kernel(const TcParams p, uint32_t n_row_tiles, uint64_t* __restrict__ list) {
+    const uint32_t P = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= p.n_pairs) return;
+    uint32_t a, b, c_first, n = 0;
+    if (!tc6_pair_chunks(p, n_row_tiles, P, &a, &b, &c_first, &n)) return;
+    uint64_t* out = list + p.unit_off[P];
+    for (uint32_t k = 0; k < n; ++k) out[k] = ((uint64_t)(c_first + k * p.world) << 32) | P;
+}
+
+template <int kT6Expanders>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((6 + kT6Expanders) * 32, 1)
     hamming_tc6_kernel(const TcParams p, uint32_t n_row_tiles, uint32_t n_col_st) {
+    constexpr int kTc6Threads = (6 + kT6Expanders) * 32;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = base;                                                             // 4 K-chunks x 128 rows x 128 B
@@ -925,17 +942,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
 
     const uint32_t cr = tc_cluster_rank();
-    const uint32_t unit = blockIdx.x >> 1;
-    uint32_t lo = 0, hi = p.n_pairs;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(p.unit_off + mid) <= unit) lo = mid;
-        else hi = mid;
-    }
-    const uint32_t P = lo;
+    const uint64_t unit = __ldg(p.unit_list + (blockIdx.x >> 1));
+    const uint32_t P = (uint32_t)unit, c = (uint32_t)(unit >> 32);
     uint32_t st_lo, st_hi, c_first, n_owned;
     if (!tc6_pair_chunks(p, n_row_tiles, P, &st_lo, &st_hi, &c_first, &n_owned)) return;
-    const uint32_t c = c_first + (unit - __ldg(p.unit_off + P)) * p.world;
     const uint32_t st0 = max(st_lo, c * p.chunk), st1 = min(min(st_hi, n_col_st), (c + 1) * p.chunk);
     if (st0 >= st1) return;
     const uint32_t n_st = st1 - st0;
@@ -1174,7 +1184,7 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
     p.keys = ctx->raw_keys.as<uint64_t>(), p.counter = counter, p.capacity = capacity, p.col_base = col_base;
     p.tol = tol > 1024u ? 1024u : tol;  // no distance exceeds 1024 (and the epilogue's threshold is a signed int)
     p.rank = ctx->rank, p.world = ctx->world;
-    p.unit_off = nullptr, p.n_pairs = 0;
+    p.unit_off = nullptr, p.n_pairs = 0, p.unit_list = nullptr;
     if (ctx->search_variant >= 4) {  // CTA pairs: 256-row super-tiles x absolute chunks of column super-tiles
         const uint32_t n_pairs = (n_row_tiles + 1) / 2, n_st = (n_col_tiles + 1) / 2;
         // long chunks amortise the per-unit set-up (operand A, tensor-memory allocation, cluster syncs); keep >= 64
@@ -1188,7 +1198,9 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
         if (ctx->search_variant == 6) {  // as variant 5, super-tiles of 192 columns
             static bool attr6 = false;
             if (!attr6) {
-                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
                 attr6 = true;
             }
             const uint32_t n_col_st = (uint32_t)(((uint64_t)n_col_tiles * kTile + 2 * kT6Cols - 1) / (2 * kT6Cols));
@@ -1212,8 +1224,35 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
             VDF_CUDA(ctx, cudaMemcpyAsync(&n_units, ctx->unit_off.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, ctx->stream));
             VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (n_units == 0) return VDF_OK;
+            if (n_units > 0x3FFFFFFFu) {
+                ctx->err = "too many work units for one launch";
+                return VDF_ERR_INVALID;
+            }
+            {   // explicit unit list, chunk-major (stable radix sort on the chunk bits of a P-major list)
+                VDF_ALLOC(ctx, ctx->unit_list_a.ensure((size_t)n_units * 8));
+                VDF_ALLOC(ctx, ctx->unit_list_b.ensure((size_t)n_units * 8));
+                tc6_unit_list_kernel<<<(n_pairs + 255) / 256, 256, 0, ctx->stream>>>(p, n_row_tiles, ctx->unit_list_a.as<uint64_t>());
+                VDF_LAUNCHED(ctx);
+                p.unit_list = ctx->unit_list_a.as<uint64_t>();
+                const uint32_t n_chunks = (n_col_st + ch - 1) / ch;
+                int cbits = 1;
+                while ((1u << cbits) < n_chunks) ++cbits;
+                if (ctx->tc_unit_order == 0 && n_chunks > 1) {
+                    size_t tmp2 = 0;
+                    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp2, ctx->unit_list_a.as<uint64_t>(), ctx->unit_list_b.as<uint64_t>(),
+                                                                 (size_t)n_units, 32, 32 + cbits, ctx->stream));
+                    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp2));
+                    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp2, ctx->unit_list_a.as<uint64_t>(),
+                                                                 ctx->unit_list_b.as<uint64_t>(), (size_t)n_units, 32, 32 + cbits, ctx->stream));
+                    ctx->launches += 1;
+                    p.unit_list = ctx->unit_list_b.as<uint64_t>();
+                }
+            }
             kt_begin(ctx, 0);
-            hamming_tc6_kernel<<<2 * n_units, kTc6Threads, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
+            const uint32_t ex = ctx->tc_expanders ? ctx->tc_expanders : kT6DefaultExpanders;
+            if (ex == 8) hamming_tc6_kernel<8><<<2 * n_units, (6 + 8) * 32, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
+            else if (ex == 6) hamming_tc6_kernel<6><<<2 * n_units, (6 + 6) * 32, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
+            else hamming_tc6_kernel<4><<<2 * n_units, (6 + 4) * 32, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
             kt_end(ctx, 0);
             VDF_LAUNCHED(ctx);
             return VDF_OK;
