@@ -116,8 +116,9 @@ int vdf_ctx_set_shard(vdf_ctx* ctx, uint32_t rank, uint32_t world);
  *   3 = tcgen05.mma kind::i8 on byte-expanded tiles; 4 = the same on CTA pairs (cta_group::2);
  *   5 = CTA pairs on packed tiles, bits expanded to bytes inside the kernel; 6 (default) = the same with the bits
  *   expanded to e2m1 nibbles and tcgen05.mma kind::mxf4 (twice the kind::i8 rate).  All seven are bit-identical.
- * "tc_chunk": column super-tiles per work unit of variants 4-6 (0 = automatic); "tc_expanders": expander warps of the
- * variant-6 kernel (4, 6, 8; 0 = default); "tc_unit_order": variant-6 work-unit order (0 chunk-major, 1 row-pair-major); "hash_variant": resize kernel choice. */
+ * "tc_chunk": column super-tiles per work unit of variants 4-6 (0 = automatic); "tc_unit_order": variant-6 work-unit order
+ * (0 chunk-major, 1 row-pair-major); "tc_a_tmem": variant 6 keeps three quarters of the row operand in tensor memory (1,
+ * default) or all of it in shared memory (0); "hash_variant": resize kernel choice. */
 int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value);
 
 /* The cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the caller). */

@@ -320,16 +320,16 @@ def test_shards_partition_the_pair_matrix(ctx, world, variant):
     assert np.array_equal(allp, want)
 
 
-@pytest.mark.parametrize("expanders,order", [(4, 1), (6, 0), (8, 0), (8, 1)])
-def test_variant6_kernel_options_do_not_change_results(ctx, expanders, order):
-    """expander-warp count and work-unit order (chunk-major / row-pair-major) of the kind::mxf4 kernel, incl. a sharded run
-    with small chunks so that the unit list has many chunks per row pair"""
+@pytest.mark.parametrize("order,a_tmem", [(0, 0), (1, 0), (1, 1)])
+def test_variant6_kernel_options_do_not_change_results(ctx, order, a_tmem):
+    """work-unit order (chunk-major / row-pair-major) and row operand placement (tensor memory / shared memory) of the
+    kind::mxf4 kernel, incl. a sharded run with small chunks so that the unit list has many chunks per row pair"""
     rng = np.random.default_rng(77)
     H, dur = _case(rng, 5000, 400, 200, [600, 610, 650, 700])
     want = o.self_edges(H, dur, 320)
     ctx.set_option("search_variant", 6)
-    ctx.set_option("tc_expanders", expanders)
     ctx.set_option("tc_unit_order", order)
+    ctx.set_option("tc_a_tmem", a_tmem)
     ctx.set_option("tc_chunk", 2)
     try:
         assert np.array_equal(ctx.search_self(H, dur, 320), want)
@@ -342,8 +342,8 @@ def test_variant6_kernel_options_do_not_change_results(ctx, expanders, order):
     finally:
         ctx.set_shard(0, 1)
         ctx.set_option("tc_chunk", 0)
+        ctx.set_option("tc_a_tmem", 1)
         ctx.set_option("tc_unit_order", 0)
-        ctx.set_option("tc_expanders", 0)
         ctx.set_option("search_variant", DEFAULT_VARIANT)
 
 

@@ -101,7 +101,7 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     else if (k == "search_variant" && (value >= 0 && value <= 6)) ctx->search_variant = (int)value;
     else if (k == "tc_chunk" && value >= 0 && value <= 65535) ctx->tc_chunk = (uint32_t)value;
     else if (k == "tc_unit_order" && (value == 0 || value == 1)) ctx->tc_unit_order = (uint32_t)value;
-    else if (k == "tc_expanders" && (value == 0 || value == 4 || value == 6 || value == 8)) ctx->tc_expanders = (uint32_t)value;
+    else if (k == "tc_a_tmem" && (value == 0 || value == 1)) ctx->tc_a_tmem = (uint32_t)value;
     else if (k == "hash_chunks" && value >= 1 && value <= 4) ctx->hash_chunks = (uint32_t)value;
     else if (k == "grouping" && (value == 0 || value == 1)) ctx->grouping = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;

@@ -99,7 +99,7 @@ struct vdf_ctx {
     int hash_variant = 0;
     uint32_t tc_chunk = 0;  // column super-tiles per CTA-pair work unit (0: automatic)
     uint32_t tc_unit_order = 0;  // variant 6 work-unit order: 0 chunk-major (L2-friendly, default), 1 row-pair-major
-    uint32_t tc_expanders = 0;  // expander warps of the variant-6 kernel: 4, 6 or 8 (0: default)
+    uint32_t tc_a_tmem = 1;     // variant 6: three quarters of the row operand in tensor memory (0: all of it in shared memory)
     uint32_t hash_chunks = 1;  // hash.cu: software-pipeline chunks per call (1: letterbox, then resize, over the whole batch)
     int grouping = 0;       // 0: the reference's greedy rule (parity); 1: connected components (GPU union-find, group.cu)
     uint64_t launches = 0, h2d = 0, d2h = 0;

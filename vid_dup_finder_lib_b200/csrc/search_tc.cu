@@ -827,10 +827,10 @@ constexpr int kT6Chunk = 128;                        // bytes per row per K-chun
 constexpr int kT6ABytes = 4 * kTile * kT6Chunk;      // 64 KB
 constexpr int kT6StageBytes = kT6Cols * kT6Chunk;    // 12 KB
 constexpr int kT6Stages = 8;
-constexpr uint32_t kT6DefaultExpanders = 4;
-// expander warps E (template parameter: 4, 6 or 8; 24 four-row groups per stage, 24 / E each); threads = (6 + E) * 32:
-// warp 0 producer, 1 MMA, 2-5 epilogue, 6.. expanders
+constexpr int kT6Expanders = 4;                      // expander warps (24 four-row groups per stage: 6 each)
+constexpr int kTc6Threads = (6 + kT6Expanders) * 32; // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. expanders
 constexpr int kT6PackedBytes = kT6Cols * 128;        // packed column tile: 96 x 128 B = 12 KB; packed row tile: 16 KB
+// all-shared form: A 64 KB + ring + 2 packed slots; kATmem form: A chunk 3 (16 KB) + ring + 4 packed slots (smaller)
 constexpr size_t kTc6Smem = (size_t)kT6ABytes + kT6Stages * kT6StageBytes + 2 * kTileWords * 4 /* packed A, then 2 packed column tiles */ + 1024 + 256;
 // block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): a/b format E2M1 = 1 at [7,10) / [10,13),
 // K-major, N >> 3 at [17,23), scale format UE8M0 = 1 at bit 23, M >> 4 at [24,29), scale-factor ids 0, K = 64
@@ -841,6 +841,14 @@ __device__ __forceinline__ void tc6_mma(uint32_t tmem_d, uint64_t da, uint64_t d
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(kTc6Idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+        : "memory");
+}
+// the same with operand A read from tensor memory (8 columns = 64 e2m1 values per lane and instruction)
+__device__ __forceinline__ void tc6_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t sfa, uint32_t sfb, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(kTc6Idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
         : "memory");
 }
 // one packed u32 -> one 16-byte unit of e2m1 nibbles (0x2 = 1.0)
@@ -922,21 +930,26 @@ __global__ void tc6_unit_list_kernel(const TcParams p, uint32_t n_row_tiles, uin
     for (uint32_t k = 0; k < n; ++k) out[k] = ((uint64_t)(c_first + k * p.world) << 32) | P;
 }
 
-template <int kT6Expanders>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((6 + kT6Expanders) * 32, 1)
+// kATmem: K-chunks 0-2 of the row operand live in tensor memory (columns [384, 480), written once per unit with tcgen05.st)
+// and only chunk 3 in shared memory; scale factors in [480, 512).  The shared-memory data pipe is what bounds the all-smem
+// form (ncu: 50 % tensor-core operand reads + 32 % expander stores at 86 % tensor-pipe activity); reading three quarters of
+// A from tensor memory takes the operand reads from 7 KB to 4 KB per instruction.
+template <bool kATmem>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
     hamming_tc6_kernel(const TcParams p, uint32_t n_row_tiles, uint32_t n_col_st) {
-    constexpr int kTc6Threads = (6 + kT6Expanders) * 32;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = base;                                                             // 4 K-chunks x 128 rows x 128 B
-    uint8_t* sB = base + kT6ABytes;                                                 // ring: 8 x (96 rows x 128 B)
+    constexpr int kPB = kATmem ? 4 : 2;  // packed column-tile buffers (16 KB slots; slot 0 holds the packed row tile first)
+    constexpr int kASmem = kATmem ? kTile * kT6Chunk : kT6ABytes;  // only K-chunk 3 of A lives in shared memory with kATmem
+    uint8_t* sB = base + kASmem;                                                    // ring: 8 x (96 rows x 128 B)
     uint32_t* sP = reinterpret_cast<uint32_t*>(sB + kT6Stages * kT6StageBytes);     // packed A tile (16 KB), then 2 x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + 2 * kTileWords * 4);  // slots for column tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + kPB * kTileWords * 4);  // slots for column tiles
     uint64_t* full = bars;                      // [8]  leader: 8 expander-warp arrivals
     uint64_t* empty = bars + kT6Stages;         // [8]  commit multicast
-    uint64_t* pfull = bars + 2 * kT6Stages;     // [2]
-    uint64_t* pempty = pfull + 2;               // [2]
-    uint64_t* acc_full = pempty + 2;            // [2]
+    uint64_t* pfull = bars + 2 * kT6Stages;     // [kPB]
+    uint64_t* pempty = pfull + kPB;             // [kPB]
+    uint64_t* acc_full = pempty + kPB;          // [2]
     uint64_t* acc_empty = acc_full + 2;         // [2]
     uint64_t* a_full = acc_empty + 2;           // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
@@ -956,10 +969,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((6 + kT6Expanders) *
 
     if (tid == 0) {
         for (int s = 0; s < kT6Stages; ++s) tc_mbar_init(&full[s], 2 * kT6Expanders), tc_mbar_init(&empty[s], 1);
-        for (int b = 0; b < 2; ++b) {
-            tc_mbar_init(&pfull[b], 1), tc_mbar_init(&pempty[b], kT6Expanders);
-            tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 8);
-        }
+        for (int b = 0; b < kPB; ++b) tc_mbar_init(&pfull[b], 1), tc_mbar_init(&pempty[b], kT6Expanders);
+        for (int b = 0; b < 2; ++b) tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 8);
         tc_mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tc_mbar_expect_tx(a_full, kTileWords * 4);
@@ -972,20 +983,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((6 + kT6Expanders) *
     }
     __syncthreads();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= 2 && warp < 6) {  // constant block scales: 0x7F (UE8M0 1.0) in every byte of columns [384, 512), all lanes
+    constexpr uint32_t kSfCol = kATmem ? 480u : 384u;
+    if (warp >= 2 && warp < 6) {  // constant block scales: 0x7F (UE8M0 1.0) in every byte of columns [kSfCol, 512), all lanes
         uint32_t ones[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) ones[k] = 0x7F7F7F7Fu;
         const uint32_t lanes = ((uint32_t)(warp & 3) * 32) << 16;
-        for (int q = 0; q < 4; ++q) tc_st32(tmem_base + lanes + 384 + q * 32, ones);
+        for (uint32_t c = kSfCol; c < 512; c += 32) tc_st32(tmem_base + lanes + c, ones);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_mbar_wait(a_full, 0);
-    {   // A: 4 K-chunks x 128 rows; a warp covers 4 rows x 8 packed words (one 128 B line per quarter-warp)
+    if (kATmem && warp >= 2 && warp < 6) {  // A chunks 0-2 -> tensor memory: lane = row, column 384 + 32 kc + 4 w + m
+        const uint32_t row = (uint32_t)(warp & 3) * 32 + lane;
+        for (int kc = 0; kc < 3; ++kc) {
+            const uint4* src = reinterpret_cast<const uint4*>(sP + (kc * kTile + row) * 8);
+            const uint4 p0 = src[0], p1 = src[1];
+            const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            uint32_t v[32];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const uint4 e = tc6_expand(pw[w]);
+                v[4 * w] = e.x, v[4 * w + 1] = e.y, v[4 * w + 2] = e.z, v[4 * w + 3] = e.w;
+            }
+            tc_st32(tmem_base + ((row & ~31u) << 16) + 384 + kc * 32, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    {   // A -> shared memory: K-chunks x 128 rows; a warp covers 4 rows x 8 packed words (one 128 B line per quarter-warp)
         const int w = lane & 7, r4 = lane >> 3;
-        for (int item = warp; item < 4 * 32; item += kTc6Threads / 32) {  // (K-chunk, 4-row group)
+        for (int item = warp + (kATmem ? 3 * 32 : 0); item < 4 * 32; item += kTc6Threads / 32) {  // (K-chunk, 4-row group)
             const int kc = item >> 5, row = (item & 31) * 4 + r4;
-            *reinterpret_cast<uint4*>(sA + kc * (kTile * kT6Chunk) + row * 128 + ((w ^ (row & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(sA + (kATmem ? 0 : kc) * (kTile * kT6Chunk) + row * 128 + ((w ^ (row & 7)) << 4)) =
                 tc6_expand(sP[(kc * kTile + row) * 8 + w]);
         }
     }
@@ -994,13 +1022,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((6 + kT6Expanders) *
     __syncthreads();
     tc_cluster_sync();
     tc_fence_after();
-    const uint32_t sfa = tmem_base + 384, sfb = tmem_base + 448;
+    const uint32_t sfa = tmem_base + kSfCol, sfb = tmem_base + kSfCol + (kATmem ? 16u : 64u);
 
     if (warp == 0) {
         if (lane == 0) {  // ===== bulk-copy producer: this CTA's packed column tile (96 hashes) of every super-tile
             for (uint32_t s = 0; s < n_st; ++s) {
-                const uint32_t pb = s & 1;
-                tc_mbar_wait(&pempty[pb], ((s >> 1) & 1) ^ 1);
+                const uint32_t pb = s % kPB;
+                tc_mbar_wait(&pempty[pb], ((s / kPB) & 1) ^ 1);
                 tc_mbar_expect_tx(&pfull[pb], kT6PackedBytes);
                 tc_bulk_g2s(sP + pb * kTileWords, col_tiles + (size_t)(2 * (st0 + s) + cr) * (kT6PackedBytes / 4), kT6PackedBytes,
                             &pfull[pb]);
@@ -1021,9 +1049,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((6 + kT6Expanders) *
                     tc_fence_after();
                     if (tc_elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            tc6_mma(d_tmem, a_desc + ((kc * (kTile * kT6Chunk) + ks * 32) >> 4),
-                                    b_desc + ((stage * kT6StageBytes + ks * 32) >> 4), sfa, sfb, (kc | ks) != 0);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (kATmem && kc < 3)
+                                tc6_mma_ts(d_tmem, tmem_base + 384 + kc * 32 + ks * 8, b_desc + ((stage * kT6StageBytes + ks * 32) >> 4),
+                                           sfa, sfb, (kc | ks) != 0);
+                            else
+                                tc6_mma(d_tmem, a_desc + (((kATmem ? 0 : kc) * (kTile * kT6Chunk) + ks * 32) >> 4),
+                                        b_desc + ((stage * kT6StageBytes + ks * 32) >> 4), sfa, sfb, (kc | ks) != 0);
+                        }
                         tc2_commit(&empty[stage]);
                         if (kc == 3) tc2_commit(&acc_full[buf]);
                     }
@@ -1031,22 +1064,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((6 + kT6Expanders) *
                 }
             }
         }
-    } else if (warp >= 6) {  // ===== expanders: a warp writes 4 rows x 8 units per iteration; warp e takes groups e, e+6, ..
+    } else if (warp >= 6) {  // ===== expanders: a warp writes 4 rows x 8 units per group, 6 groups per stage
+        // Measured alternatives that did not help (1 M hashes, ms per launch): 6 or 8 warps on every stage (133.6 / 138.1
+        // against 130.7), two teams of four warps on alternate stages (132.8 against 131.6), one fence.proxy.async per 2 / 4
+        // stages (123.3 / 123.6 against 122.6).
         constexpr int kG = 24 / kT6Expanders;  // four-row groups per warp per stage
         const int w = lane & 7, r4 = lane >> 3;
         const int row0 = (warp - 6) * 4 + r4;  // + 4 * kT6Expanders * g
-        uint32_t it = 0;
         for (uint32_t s = 0; s < n_st; ++s) {
-            const uint32_t pb = s & 1;
-            tc_mbar_wait(&pfull[pb], (s >> 1) & 1);
+            const uint32_t pb = s % kPB;
+            tc_mbar_wait(&pfull[pb], (s / kPB) & 1);
             const uint32_t* packed = sP + pb * kTileWords + row0 * 8 + w;
-            uint32_t bits[kG];
+            for (int kc = 0; kc < 4; ++kc) {
+                uint32_t bits[kG];
 #pragma unroll
-            for (int g = 0; g < kG; ++g) bits[g] = packed[g * (4 * kT6Expanders * 8)];
-            for (int kc = 0; kc < 4; ++kc, ++it) {
-                uint32_t next[kG];  // the next K-chunk's words are in flight while this one is expanded
-#pragma unroll
-                for (int g = 0; g < kG; ++g) next[g] = kc < 3 ? packed[((kc + 1) * kT6Cols + g * (4 * kT6Expanders)) * 8] : 0u;
+                for (int g = 0; g < kG; ++g) bits[g] = packed[(kc * kT6Cols + g * (4 * kT6Expanders)) * 8];
+                const uint32_t it = 4 * s + kc;
                 const uint32_t stage = it % kT6Stages;
                 tc_mbar_wait(&empty[stage], ((it / kT6Stages) & 1) ^ 1);
                 uint8_t* dst = sB + stage * kT6StageBytes;
@@ -1058,8 +1091,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((6 + kT6Expanders) *
                 tc_fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive_remote(&full[stage], 0);
-#pragma unroll
-                for (int g = 0; g < kG; ++g) bits[g] = next[g];
             }
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&pempty[pb]);
@@ -1198,13 +1229,15 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
         if (ctx->search_variant == 6) {  // as variant 5, super-tiles of 192 columns
             static bool attr6 = false;
             if (!attr6) {
-                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
-                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
-                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
                 attr6 = true;
             }
             const uint32_t n_col_st = (uint32_t)(((uint64_t)n_col_tiles * kTile + 2 * kT6Cols - 1) / (2 * kT6Cols));
-            uint32_t ch = ctx->tc_chunk ? ctx->tc_chunk : 128;
+            // a unit costs ~5 us of set-up and drain (tensor-memory allocation, row operand load + expansion, cluster syncs,
+            // the last epilogue) next to 0.84 us per super-tile: measured at 1 M hashes, 130.0 / 127.3 / 125.8 / 125.0 / 124.5 ms
+            // for chunks of 128 / 256 / 512 / 1024 / 2048.  Long chunks, as long as >= 64 units per resident pair keep the tail short.
+            uint32_t ch = ctx->tc_chunk ? ctx->tc_chunk : 2048;
             while (!ctx->tc_chunk && ch > 2 && (uint64_t)n_pairs * ((n_col_st + ch - 1) / ch) < (uint64_t)(ctx->sm_count / 2) * 64 * ctx->world)
                 ch >>= 1;
             p.chunk = ch;
@@ -1249,10 +1282,8 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
                 }
             }
             kt_begin(ctx, 0);
-            const uint32_t ex = ctx->tc_expanders ? ctx->tc_expanders : kT6DefaultExpanders;
-            if (ex == 8) hamming_tc6_kernel<8><<<2 * n_units, (6 + 8) * 32, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
-            else if (ex == 6) hamming_tc6_kernel<6><<<2 * n_units, (6 + 6) * 32, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
-            else hamming_tc6_kernel<4><<<2 * n_units, (6 + 4) * 32, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
+            if (ctx->tc_a_tmem) hamming_tc6_kernel<true><<<2 * n_units, kTc6Threads, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
+            else hamming_tc6_kernel<false><<<2 * n_units, kTc6Threads, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
             kt_end(ctx, 0);
             VDF_LAUNCHED(ctx);
             return VDF_OK;
