@@ -195,6 +195,15 @@ int vdf_self_window_pairs(vdf_ctx* ctx, const uint32_t* dur_sorted, uint64_t n, 
 int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint64_t* path_off, uint64_t n,
                    uint64_t* order_out);
 
+/* `Search::seed` + `sort` (search_algorithm.rs:31-34,55-61) with the sorted table left RESIDENT in HBM: the stable
+ * (duration, Path) permutation goes to order_out[n]; hashes and durations are gathered in that order through pinned
+ * memory and uploaded on the context's stream.  *d_hash_sorted / *d_dur_sorted are device pointers owned by the context,
+ * valid until the next vdf_stage_sorted / vdf_search* call on it; they feed vdf_search_self_device on every rank of a
+ * multi-GPU search (vid_dup_finder_lib_b200/dist.py). */
+int vdf_stage_sorted(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, const char* path_blob,
+                     const uint64_t* path_off, uint64_t n, uint64_t* order_out, const uint64_t** d_hash_sorted,
+                     const uint32_t** d_dur_sorted);
+
 /* Replaces `search(hashes, tolerance)` (video_dup_finder.rs:7-13): groups exactly as the reference returns them
  * (matches in sorted order, the target last, groups by descending target; every group has >= 2 entries), with
  * member_idx holding the caller's indices.  The caller builds MatchGroup::new(paths of members). */

@@ -133,6 +133,13 @@ if [[ $STEP == x12 ]]; then
     timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_expanders=$1 --opt tc_fence_batch=$2 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x12_e$1_f$2.json 2> gpurun_out/bench_x12_e$1_f$2.err; echo "bench e=$1 fence_batch=$2 rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x12_e$1_f$2.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x12_e$1_f$2.err
   done
 fi
+if [[ $STEP == x13 ]]; then
+  timeout 900 python -m pytest tests/test_gpu_search.py -m gpu -x -q > gpurun_out/pytest_search.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_search.log
+  for i in 1 2; do
+    timeout 300 python bench.py --steps 5 --warmup 3 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x13_$i.json 2> gpurun_out/bench_x13_$i.err; echo "bench rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x13_$i.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x13_$i.err
+  done
+  VDF_BENCH_DEBUG=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x13_dbg.json 2> gpurun_out/bench_x13_dbg.err; tail -12 gpurun_out/bench_x13_dbg.err
+fi
 if [[ $STEP == big ]]; then
   # BASELINE configs[3] and [4] sizes on one GPU: 100k queries x 10M-entry table; all-pairs over a 10M-hash corpus
   timeout 900 python bench.py --workload refs --steps 3 --warmup 1 > gpurun_out/bench_refs_10m.json 2> gpurun_out/bench_refs_10m.err; echo "bench refs rc=$?"; tail -c 1200 gpurun_out/bench_refs_10m.json; tail -3 gpurun_out/bench_refs_10m.err

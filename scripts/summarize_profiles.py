@@ -131,6 +131,10 @@ def main():
         json.dump(recs, open(os.path.join(PROF, "microbench.json"), "w"), indent=1)
     for f in sorted(os.listdir(OUT)):
         if f.startswith("bench") and f.endswith(".json") and os.path.getsize(os.path.join(OUT, f)) > 10 and "under_ncu" not in f:
+            if f.startswith("bench_x"):  # kernel experiments (option sweeps): kept apart from the headline evidence
+                os.makedirs(os.path.join(PROF, "experiments"), exist_ok=True)
+                shutil.copy(os.path.join(OUT, f), os.path.join(PROF, "experiments", f"{tag}_{f}"))
+                continue
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, f"{tag}_{f}"))
     for f in sorted(os.listdir(OUT)):
         if f.startswith("dist_check") and f.endswith(".log"):

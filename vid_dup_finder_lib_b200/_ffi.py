@@ -22,7 +22,7 @@ CROPDETECT_NONE, CROPDETECT_LETTERBOX = 0, 1
 STACK_FLAG_MIXED_SIZES = 1
 
 EXPORTS = [
-    "vdf_version", "vdf_ctx_create", "vdf_ctx_destroy", "vdf_last_error", "vdf_ctx_set_shard", "vdf_ctx_set_option",
+    "vdf_version", "vdf_ctx_create", "vdf_ctx_destroy", "vdf_last_error", "vdf_ctx_set_shard", "vdf_ctx_set_option", "vdf_stage_sorted",
     "vdf_ctx_stream", "vdf_ctx_counters", "vdf_ctx_kernel_time", "vdf_search_self", "vdf_group_greedy", "vdf_search_self_groups",
     "vdf_search_refs", "vdf_search_self_device", "vdf_search_refs_device", "vdf_group_greedy_device",
     "vdf_self_window_pairs", "vdf_free_edges", "vdf_free_groups", "vdf_free_csr", "vdf_hash_stacks",
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
     L.vdf_last_error.restype = C.c_char_p
     L.vdf_ctx_set_shard.argtypes = [vp, u32, u32]
     L.vdf_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.vdf_stage_sorted.argtypes = [vp, vp, vp, vp, vp, u64, vp, C.POINTER(vp), C.POINTER(vp)]
     L.vdf_ctx_stream.argtypes = [vp]
     L.vdf_ctx_stream.restype = vp
     L.vdf_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -223,6 +224,16 @@ class Context:
         mm = _copy_u64(g.member_idx, int(gp[-1]) if ng else 0)
         lib().vdf_free_groups(C.byref(g))
         return gp, mm
+
+    def stage_sorted(self, hashes, durations, path_blob: np.ndarray, path_off: np.ndarray):
+        """vdf_stage_sorted: -> (order [n] int64, device pointer of the sorted hashes, device pointer of the sorted durations)"""
+        h = _hash_array(hashes)
+        d = np.ascontiguousarray(durations, dtype=np.uint32)
+        order = np.empty(len(d), dtype=np.uint64)
+        ph, pd = C.c_void_p(), C.c_void_p()
+        self._check(lib().vdf_stage_sorted(self._h, _ptr(h), _ptr(d), _ptr(path_blob), _ptr(path_off), len(d), _ptr(order),
+                                           C.byref(ph), C.byref(pd)))
+        return order.view(np.int64), int(ph.value or 0), int(pd.value or 0)
 
     def group_greedy(self, n: int, edges):
         e = np.ascontiguousarray(edges, dtype=np.uint64).reshape(-1, 2)

@@ -52,7 +52,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
-    DevBuf* bufs[] = {&ctx->unit_cnt, &ctx->unit_off, &ctx->pcmin_rows, &ctx->pcmin_cols, &ctx->row_tiles, &ctx->col_tiles, &ctx->row_lo,   &ctx->row_hi,  &ctx->row_id,  &ctx->tile_range,
+    DevBuf* bufs[] = {&ctx->unit_cnt, &ctx->unit_off, &ctx->unit_list_a, &ctx->unit_list_b, &ctx->pcmin_rows, &ctx->pcmin_cols, &ctx->row_tiles, &ctx->col_tiles, &ctx->row_lo,   &ctx->row_hi,  &ctx->row_id,  &ctx->tile_range,
                       &ctx->raw_keys,  &ctx->sort_tmp,  &ctx->misc,     &ctx->keys_a,  &ctx->keys_b,  &ctx->in_hash,
                       &ctx->in_dur,    &ctx->in_hash2,  &ctx->in_dur2,  &ctx->ref_perm, &ctx->ref_key, &ctx->g_rk,
                       &ctx->g_rks,     &ctx->g_state,   &ctx->g_parent, &ctx->g_wl0,   &ctx->g_wla,   &ctx->g_wlb,
@@ -62,6 +62,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     ctx->pin_a.release();
     ctx->pin_b.release();
+    ctx->h_groups.release();
     ctx->pin_frames[0].release();
     ctx->pin_frames[1].release();
     free_coef_cache(ctx);

@@ -118,7 +118,7 @@ struct vdf_ctx {
     vdf::DevBuf g_rk, g_rks, g_state, g_parent, g_wl0, g_wla, g_wlb, g_mk, g_mks, g_flag, g_scan, g_gp, g_mem;
     // hashing scratch
     vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc;
-    vdf::PinnedBuf pin_a, pin_b, pin_frames[2];
+    vdf::PinnedBuf pin_a, pin_b, pin_frames[2], h_groups;  // h_groups: staging of the group CSR on its way to the caller
     std::map<uint32_t, vdf::CoefTable> coef_cache;
     std::map<uint64_t, void*> bfrag_cache;  // (cropped width << 8 | shift) -> IMMA B fragments in HBM
     bool dct_consts_loaded = false;

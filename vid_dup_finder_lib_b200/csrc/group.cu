@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace vdf {
@@ -137,9 +139,14 @@ static int finish_groups(vdf_ctx* ctx, unsigned long long nm, vdf_groups* out) {
         ctx->err = "host allocation failed";
         return VDF_ERR_ALLOC;
     }
-    VDF_CUDA(ctx, cudaMemcpyAsync(out->group_ptr, ctx->g_gp.p, (size_t)(ng + 1) * 8, cudaMemcpyDeviceToHost, st));
-    VDF_CUDA(ctx, cudaMemcpyAsync(out->member_idx, ctx->g_mem.p, (size_t)(nm + ng) * 8, cudaMemcpyDeviceToHost, st));
+    // through pinned staging: a device -> pageable copy of these ~2 MB costs more than the rest of the grouping
+    const size_t gp_bytes = (size_t)(ng + 1) * 8, mem_bytes = (size_t)(nm + ng) * 8;
+    VDF_CUDA(ctx, ctx->h_groups.ensure(gp_bytes + mem_bytes));
+    VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_groups.p, ctx->g_gp.p, gp_bytes, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_groups.as<uint8_t>() + gp_bytes, ctx->g_mem.p, mem_bytes, cudaMemcpyDeviceToHost, st));
     VDF_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(out->group_ptr, ctx->h_groups.p, gp_bytes);
+    memcpy(out->member_idx, ctx->h_groups.as<uint8_t>() + gp_bytes, mem_bytes);
     ctx->d2h += (size_t)(ng + 1) * 8 + (size_t)(nm + ng) * 8;
     return VDF_OK;
 }

@@ -236,6 +236,29 @@ int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint6
     return VDF_OK;
 }
 
+int vdf_stage_sorted(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, const char* path_blob, const uint64_t* path_off,
+                     uint64_t n, uint64_t* order_out, const uint64_t** d_hash_sorted, const uint32_t** d_dur_sorted) {
+    VDF_TRY(enter(ctx));
+    if (!order_out || !d_hash_sorted || !d_dur_sorted || (n && (!hashes || !durations || !path_off))) return VDF_ERR_INVALID;
+    if (n >= 0xFFFFFF00ull) {
+        ctx->err = "n must be < 2^32";
+        return VDF_ERR_INVALID;
+    }
+    double t0 = now_ms();
+    std::vector<SortKey> keys;
+    VDF_TRY(sort_order_impl(durations, path_blob, path_off, n, keys));
+    double t1 = now_ms();
+    if (n) VDF_TRY(stage_sorted(ctx, hashes, durations, keys, ctx->in_hash, ctx->in_dur, ctx->pin_a, ctx->pin_b));
+    parallel_for(n, n_threads(n), [&](uint64_t b, uint64_t e, unsigned) {
+        for (uint64_t k = b; k < e; ++k) order_out[k] = keys[k].idx;
+    });
+    double t2 = now_ms();
+    ctx->phase_ms[0] = t1 - t0, ctx->phase_ms[1] = t2 - t1, ctx->phase_ms[2] = 0, ctx->phase_ms[3] = 0;
+    *d_hash_sorted = ctx->in_hash.as<uint64_t>();
+    *d_dur_sorted = ctx->in_dur.as<uint32_t>();
+    return VDF_OK;
+}
+
 int vdf_search(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, const char* path_blob, const uint64_t* path_off,
                uint64_t n, double tolerance, vdf_groups* out) {
     VDF_TRY(enter(ctx));

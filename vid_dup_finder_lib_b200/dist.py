@@ -75,14 +75,18 @@ def _run_growing(fn, device, initial: int = 1 << 22):
         cap = -cnt + 1024
 
 
-def search_self_keys(ctx: _ffi.Context, d_hash: torch.Tensor, d_dur: torch.Tensor, tol_int: int, group=None) -> torch.Tensor:
-    """This rank's share of the pair matrix, then the edge all-gather: sorted (i << 32 | j) keys of ALL ranks."""
+def search_self_keys(ctx: _ffi.Context, d_hash, d_dur, tol_int: int, group=None, n: Optional[int] = None,
+                     device=None) -> torch.Tensor:
+    """This rank's share of the pair matrix, then the edge all-gather: sorted (i << 32 | j) keys of ALL ranks.
+    d_hash / d_dur: the sorted table resident in HBM, as torch tensors or as raw device pointers (then pass n, device)."""
     rank, world = world_info(group)
-    n = d_dur.numel()
+    if isinstance(d_hash, torch.Tensor):
+        n, device, p_hash, p_dur = d_dur.numel(), d_hash.device, d_hash.data_ptr(), d_dur.data_ptr()
+    else:
+        p_hash, p_dur = int(d_hash), int(d_dur)
     ctx.set_shard(rank, world)
     try:
-        local = _run_growing(lambda p, cap: ctx.search_self_device(d_hash.data_ptr(), d_dur.data_ptr(), n, tol_int, p, cap),
-                             d_hash.device)
+        local = _run_growing(lambda p, cap: ctx.search_self_device(p_hash, p_dur, n, tol_int, p, cap), device)
     finally:
         ctx.set_shard(0, 1)
     return merge_keys(local, group)
@@ -123,12 +127,12 @@ def search(hashes, tolerance: float, ctx: Optional[_ffi.Context] = None, group=N
 
         return search_one(table, tolerance, ctx)
     dev = torch.device("cuda", ctx.device)
-    order = _ffi.sort_order(table.durations, *table.path_blob())
-    d_hash = _to_dev(np.ascontiguousarray(table.hashes[order]), dev)
-    d_dur = _to_dev(np.ascontiguousarray(table.durations[order]), dev)
-    keys = search_self_keys(ctx, d_hash, d_dur, tolerance_to_int(tolerance), group)
-    torch.cuda.current_stream().synchronize()
-    gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
+    # native host side of vdf_search: multi-threaded (duration, Path) sort, gather through pinned memory, async upload
+    order, p_hash, p_dur = ctx.stage_sorted(table.hashes, table.durations, *table.path_blob())
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)):
+        keys = search_self_keys(ctx, p_hash, p_dur, tolerance_to_int(tolerance), group, n=n, device=dev)
+        torch.cuda.current_stream().synchronize()
+        gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
     return MatchGroup.from_csr(table.paths, gp, order[mm.astype(np.int64)])
 
 
