@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--stacks", type=int, default=256, help="1080p stacks resident in HBM per GPU (8.5 GB at 256)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU edge exchange: fused into the pair kernel over NVLink peer memory, or an NCCL all-gather")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT", help="extra vdf_ctx_set_option (kernel experiments)")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -330,6 +332,11 @@ def main():
         ctx.set_option(k, int(v))
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    fused = world > 1 and args.exchange == "peer" and args.workload in ("search", "refs") and (args.variant in (-1, 6))
+    if fused:
+        vdist.enable_peer_exchange(ctx, capacity=1 << 22)
+    exchange_note = ("edges appended to every rank's buffer by the pair kernel over NVLink peer memory" if fused else
+                     "NCCL all-gather of per-rank edge lists") if world > 1 else "single GPU"
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -448,7 +455,7 @@ def main():
                "clocks": cs.summary(),
                "config": {"workload": f"all-pairs search (find_all_matches), {n} synthetic hashes, equal durations, "
                                       f"tolerance {args.tol}", "n_hashes": n, "tol_int": tol_int, "pairs_per_step": pairs,
-                          "edges": result.get("edges"), "groups": result.get("groups"), "parallelism": f"tile-block shard x{world}",
+                          "edges": result.get("edges"), "groups": result.get("groups"), "parallelism": f"tile-block shard x{world}", "exchange": exchange_note,
                           "l2": "512 MiB write between timed steps (hash table 128 MB ~ L2 126 MB)",
                           "search_variant": variant}}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -506,7 +513,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": cs.summary(),
                 "config": {"workload": f"search_with_references, {nq} queries x {nc} sorted table entries, equal durations, "
                                        f"tolerance {args.tol}", "matches": result.get("matches"),
-                           "parallelism": f"table slice x{world}", "l2": "512 MiB write between timed steps"}}
+                           "parallelism": f"table slice x{world}", "exchange": exchange_note, "l2": "512 MiB write between timed steps"}}
 
     # ---------------------------------------------------------------- hashing workload
     def bench_hash(steps, warmup):
@@ -595,6 +602,8 @@ def main():
     if rank == 0:
         emit(line)
     if world > 1:
+        if fused:
+            vdist.disable_peer_exchange(ctx)
         dist.destroy_process_group()
 
 

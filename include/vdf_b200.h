@@ -111,6 +111,25 @@ const char* vdf_last_error(const vdf_ctx* ctx);
  * the caller (NCCL all-gather) before vdf_group_greedy*.  Default rank 0 of 1. */
 int vdf_ctx_set_shard(vdf_ctx* ctx, uint32_t rank, uint32_t world);
 
+/* Edge exchange of a multi-GPU search over NVLink peer memory, fused into the pair kernel (search_variant 6): instead of
+ * gathering per-rank edge lists with a collective, the kernel that finds a match takes a slot
+ * from its local counter and stores the key into its own segment of EVERY rank's exchange buffer (plain remote stores over
+ * NVLink, overlapped with the math); a flag barrier in peer memory publishes the per-rank counts and ends the call, after
+ * which vdf_search_self_device / vdf_search_refs_device return the sorted keys of ALL ranks on every rank.  One process per
+ * GPU, <= 8 GPUs of one node.
+ *   vdf_peer_alloc: (re)allocates this rank's buffer for capacity_keys matches (total over all ranks; each rank may
+ *                   contribute capacity_keys / world) and writes its CUDA IPC handle (64 bytes);
+ *   the caller exchanges the handles of all ranks (any control-plane channel; dist.py uses all_gather_object);
+ *   vdf_peer_open:  maps the peers' buffers (handles = world x 64 bytes in rank order) - every rank must have returned from
+ *                   vdf_peer_open before any rank searches (a host barrier);
+ *   option "exchange" = 1 switches the searches to the exchange; all ranks must then make the same sequence of search calls
+ *                   (how the work is divided - vdf_ctx_set_shard for the self search, candidate slices for the reference
+ *                   search - is independent of it).  VDF_ERR_EDGE_OVERFLOW is returned on every rank alike, with the same
+ *                   count, when some rank's matches exceed its segment: re-allocate larger on all ranks and repeat. */
+int vdf_peer_alloc(vdf_ctx* ctx, uint64_t capacity_keys, unsigned char handle_out[64]);
+int vdf_peer_open(vdf_ctx* ctx, uint32_t rank, uint32_t world, const unsigned char* handles);
+int vdf_peer_close(vdf_ctx* ctx);
+
 /* Tuning knobs: "max_edges" (edge-buffer growth cap, default 2^28), "initial_edges" (default 2^22),
  * "search_variant": 0 = XOR+POPC; 1, 2 = XOR + carry-save adders + POPC (8x8 / 8x4 pairs per thread);
  *   3 = tcgen05.mma kind::i8 on byte-expanded tiles; 4 = the same on CTA pairs (cta_group::2);

@@ -28,32 +28,48 @@ def main():
     ctx = _ffi.default_context()
     ok = True
 
-    # search: planted duplicates, log-normal durations
     n = 30000
     H, _ = synth.planted_hashes(n, seed=11, dup_frac_den=4)
     dur = synth.lognormal_durations(n, seed=11)
     paths = synth.paths(n)
     table = vdf.HashTable(H, dur, paths)
-    for tol in (0.1, 0.35):
-        groups = vdist.search(table, tol, ctx=ctx)
-        order = o.sort_order(dur, paths)
-        gp, mm = o.search_self(H[order], dur[order], o.tolerance_int(tol))
-        want = [[paths[order[k]] for k in mm[gp[g]:gp[g + 1]]] for g in range(len(gp) - 1)]
-        got = [list(g.duplicates()) for g in groups]
-        ok &= got == want
-        if rank == 0:
-            print(f"search tol={tol}: {len(got)} groups, parity={'ok' if got == want else 'MISMATCH'}")
 
-    # search_with_references: candidate slices per rank
-    refs = vdf.HashTable(H[::97][:200], dur[::97][:200], ["ref/%04d" % i for i in range(200)])
-    got = vdist.search_with_references(refs, table, 0.3, ctx=ctx)
-    order = o.sort_order(dur, paths)
-    rp, ci = o.search_refs(H[order], dur[order], refs.hashes, refs.durations, o.tolerance_int(0.3))
-    want = [(refs.paths[r], [paths[order[k]] for k in ci[rp[r]:rp[r + 1]]]) for r in range(200) if rp[r + 1] > rp[r]]
-    got2 = [(g.reference(), list(g.duplicates())) for g in got]
-    ok &= got2 == want
-    if rank == 0:
-        print(f"search_with_references: {len(got2)} groups, parity={'ok' if got2 == want else 'MISMATCH'}")
+    def check_searches(label):
+        ok = True
+        # search: planted duplicates, log-normal durations
+        for tol in (0.1, 0.35):
+            groups = vdist.search(table, tol, ctx=ctx)
+            order = o.sort_order(dur, paths)
+            gp, mm = o.search_self(H[order], dur[order], o.tolerance_int(tol))
+            want = [[paths[order[k]] for k in mm[gp[g]:gp[g + 1]]] for g in range(len(gp) - 1)]
+            got = [list(g.duplicates()) for g in groups]
+            ok &= got == want
+            if rank == 0:
+                print(f"[{label}] search tol={tol}: {len(got)} groups, parity={'ok' if got == want else 'MISMATCH'}")
+
+        # search_with_references: candidate slices per rank
+        refs = vdf.HashTable(H[::97][:200], dur[::97][:200], ["ref/%04d" % i for i in range(200)])
+        got = vdist.search_with_references(refs, table, 0.3, ctx=ctx)
+        order = o.sort_order(dur, paths)
+        rp, ci = o.search_refs(H[order], dur[order], refs.hashes, refs.durations, o.tolerance_int(0.3))
+        want = [(refs.paths[r], [paths[order[k]] for k in ci[rp[r]:rp[r + 1]]]) for r in range(200) if rp[r + 1] > rp[r]]
+        got2 = [(g.reference(), list(g.duplicates())) for g in got]
+        ok &= got2 == want
+        if rank == 0:
+            print(f"[{label}] search_with_references: {len(got2)} groups, parity={'ok' if got2 == want else 'MISMATCH'}")
+        return ok
+
+    ok &= check_searches("nccl all-gather")
+    # the same searches with the exchange fused into the pair kernel (appends over NVLink peer memory); the first capacity
+    # is too small on purpose: every rank sees the overflow with the same count and re-allocates with the others
+    vdist.enable_peer_exchange(ctx, capacity=100)
+    ok &= check_searches("peer-memory exchange")
+    ok &= ctx.peer_capacity > 100
+    for _ in range(20):  # alternate the two halves of the exchange buffer a few more times
+        got = vdist.search(table, 0.2, ctx=ctx)
+    want_n = len(got)
+    ok &= all(len(vdist.search(table, 0.2, ctx=ctx)) == want_n for _ in range(3))
+    vdist.disable_peer_exchange(ctx)
 
     # hashing: stacks sharded by rank, hashes all-gathered in rank order
     per = 6

@@ -22,7 +22,7 @@ CROPDETECT_NONE, CROPDETECT_LETTERBOX = 0, 1
 STACK_FLAG_MIXED_SIZES = 1
 
 EXPORTS = [
-    "vdf_version", "vdf_ctx_create", "vdf_ctx_destroy", "vdf_last_error", "vdf_ctx_set_shard", "vdf_ctx_set_option", "vdf_stage_sorted",
+    "vdf_version", "vdf_ctx_create", "vdf_ctx_destroy", "vdf_last_error", "vdf_ctx_set_shard", "vdf_ctx_set_option", "vdf_stage_sorted", "vdf_peer_alloc", "vdf_peer_open", "vdf_peer_close",
     "vdf_ctx_stream", "vdf_ctx_counters", "vdf_ctx_kernel_time", "vdf_search_self", "vdf_group_greedy", "vdf_search_self_groups",
     "vdf_search_refs", "vdf_search_self_device", "vdf_search_refs_device", "vdf_group_greedy_device",
     "vdf_self_window_pairs", "vdf_free_edges", "vdf_free_groups", "vdf_free_csr", "vdf_hash_stacks",
@@ -93,6 +93,9 @@ def lib() -> C.CDLL:
     L.vdf_ctx_set_shard.argtypes = [vp, u32, u32]
     L.vdf_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.vdf_stage_sorted.argtypes = [vp, vp, vp, vp, vp, u64, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.vdf_peer_alloc.argtypes = [vp, u64, vp]
+    L.vdf_peer_open.argtypes = [vp, u32, u32, vp]
+    L.vdf_peer_close.argtypes = [vp]
     L.vdf_ctx_stream.argtypes = [vp]
     L.vdf_ctx_stream.restype = vp
     L.vdf_ctx_counters.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -170,6 +173,7 @@ class Context:
         if rc != OK:
             raise VdfError(rc, "vdf_ctx_create failed (no sm_100 device?) - this library has no CPU fallback")
         self.device = device
+        self.peer_capacity, self.peer_world = 0, 0  # edge exchange over peer memory (peer_alloc / peer_open)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -325,6 +329,22 @@ class Context:
             return -int(cnt.value)
         self._check(rc)
         return int(cnt.value)
+
+    # ---- edge exchange over NVLink peer memory (include/vdf_b200.h: vdf_peer_*) ----
+    def peer_alloc(self, capacity_keys: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(lib().vdf_peer_alloc(self._h, int(capacity_keys), buf))
+        self.peer_capacity, self.peer_world = int(capacity_keys), 0
+        return buf.raw
+
+    def peer_open(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == 64 * world
+        self._check(lib().vdf_peer_open(self._h, int(rank), int(world), C.c_char_p(handles)))
+        self.peer_world = int(world)
+
+    def peer_close(self):
+        self._check(lib().vdf_peer_close(self._h))
+        self.peer_capacity, self.peer_world = 0, 0
 
     def group_greedy_device(self, n: int, d_keys_sorted: int, n_edges: int):
         g = Groups()

@@ -47,6 +47,8 @@ int vdf_ctx_create(int device_id, vdf_ctx** out) {
     return VDF_OK;
 }
 
+static void peer_release(vdf_ctx* ctx);
+
 void vdf_ctx_destroy(vdf_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -63,6 +65,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
     ctx->pin_a.release();
     ctx->pin_b.release();
     ctx->h_groups.release();
+    peer_release(ctx);
     ctx->pin_frames[0].release();
     ctx->pin_frames[1].release();
     free_coef_cache(ctx);
@@ -105,11 +108,81 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     else if (k == "tc_a_tmem" && (value == 0 || value == 1)) ctx->tc_a_tmem = (uint32_t)value;
     else if (k == "hash_chunks" && value >= 1 && value <= 4) ctx->hash_chunks = (uint32_t)value;
     else if (k == "grouping" && (value == 0 || value == 1)) ctx->grouping = (int)value;
+    else if (k == "exchange" && (value == 0 || value == 1)) ctx->exchange = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;
     else {
         ctx->err = "unknown option or bad value: " + k;
         return VDF_ERR_INVALID;
     }
+    return VDF_OK;
+}
+
+// ---- edge exchange over peer memory (common.cuh: PeerExchange) ----------------------------------------------------
+static void peer_release(vdf_ctx* ctx) {
+    PeerExchange& px = ctx->peer;
+    for (uint32_t r = 0; r < px.world; ++r)
+        if (r != px.rank && px.mapped[r]) cudaIpcCloseMemHandle(px.mapped[r]);
+    if (px.local) cudaFree(px.local);
+    px = PeerExchange();
+    ctx->exchange = 0;
+}
+
+int vdf_peer_alloc(vdf_ctx* ctx, uint64_t capacity_keys, unsigned char handle_out[64]) {
+    if (!ctx || !handle_out || capacity_keys == 0) return VDF_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    ctx->err.clear();
+    VDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    peer_release(ctx);
+    PeerExchange& px = ctx->peer;
+    px.cap = (capacity_keys + 31) / 32 * 32;
+    const size_t bytes = 2 * (256 + px.cap * 8);
+    VDF_ALLOC(ctx, cudaMalloc(&px.local, bytes));
+    VDF_CUDA(ctx, cudaMemset(px.local, 0, bytes));
+    cudaIpcMemHandle_t h;
+    VDF_CUDA(ctx, cudaIpcGetMemHandle(&h, px.local));
+    memcpy(handle_out, &h, 64);
+    return VDF_OK;
+}
+
+int vdf_peer_open(vdf_ctx* ctx, uint32_t rank, uint32_t world, const unsigned char* handles) {
+    if (!ctx || !handles) return VDF_ERR_INVALID;
+    ctx->err.clear();
+    PeerExchange& px = ctx->peer;
+    if (!px.local || px.world) {
+        ctx->err = "vdf_peer_open: call vdf_peer_alloc first (once per vdf_peer_open)";
+        return VDF_ERR_INVALID;
+    }
+    if (world < 2 || world > (uint32_t)kMaxPeers || rank >= world) {
+        ctx->err = "vdf_peer_open: 2 <= world <= 8 GPUs of one node, rank < world";
+        return VDF_ERR_INVALID;
+    }
+    VDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t r = 0; r < world; ++r) {
+        if (r == rank) {
+            px.mapped[r] = px.local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&px.mapped[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e);
+            cudaGetLastError();
+            for (uint32_t q = 0; q < r; ++q)
+                if (q != rank && px.mapped[q]) cudaIpcCloseMemHandle(px.mapped[q]), px.mapped[q] = nullptr;
+            return VDF_ERR_CUDA;
+        }
+    }
+    px.rank = rank, px.world = world, px.epoch = 0;
+    return VDF_OK;
+}
+
+int vdf_peer_close(vdf_ctx* ctx) {
+    if (!ctx) return VDF_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    peer_release(ctx);
     return VDF_OK;
 }
 

@@ -69,6 +69,45 @@ struct PinnedBuf {
     }
 };
 
+// Edge exchange over NVLink peer memory (multi-GPU search, one process per GPU): every rank owns a buffer of two halves
+// {arrived u64 @0, seg_count[8] u64 @128, keys[world][seg_cap] @256} that all peers map through CUDA IPC.  The pair kernel
+// takes a slot from its LOCAL match counter and stores the key into segment `rank` of EVERY rank's buffer at that slot: plain
+// remote stores over NVLink, fire and forget, overlapped with the math (a remote atomic per match was tried first: its round
+// trip stalls the epilogue warp ~3 us per match and cost 1.4 ms per 62 ms launch on 2 GPUs).  At the end of the call each
+// rank publishes its count into seg_count[rank] of every buffer and signals `arrived`; when all ranks have signalled, every
+// rank holds the whole edge list: no collective call, no count exchange through the host.  Calls alternate between the
+// halves, so a fast rank's next call never writes into memory a slow rank is still reading; `arrived` only grows.
+constexpr int kMaxPeers = 8;
+struct PeerPtrs {
+    uint8_t* base[kMaxPeers];  // mapped buffer of every rank (base[rank] is the local one)
+    uint64_t half_bytes;       // 256 + world * seg_cap * 8
+    uint64_t seg_cap;          // keys one rank can contribute
+    uint32_t world, half, rank;
+    __host__ __device__ unsigned long long* arrived(uint32_t r) const {
+        return reinterpret_cast<unsigned long long*>(base[r] + half * half_bytes);
+    }
+    __host__ __device__ unsigned long long* seg_count(uint32_t r, uint32_t writer) const {
+        return reinterpret_cast<unsigned long long*>(base[r] + half * half_bytes + 128) + writer;
+    }
+    __host__ __device__ uint64_t* keys(uint32_t r, uint32_t writer) const {
+        return reinterpret_cast<uint64_t*>(base[r] + half * half_bytes + 256) + writer * seg_cap;
+    }
+};
+struct PeerExchange {
+    uint32_t world = 0, rank = 0;  // world 0: not set up
+    uint64_t cap = 0;              // keys per half over all writers
+    void* local = nullptr;
+    void* mapped[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t epoch = 0;  // exchange calls so far (all ranks make the same calls)
+    PeerPtrs ptrs(uint32_t half) const {
+        PeerPtrs pp;
+        for (uint32_t r = 0; r < (uint32_t)kMaxPeers; ++r) pp.base[r] = static_cast<uint8_t*>(mapped[r]);
+        pp.seg_cap = world ? cap / world : 0;
+        pp.half_bytes = 256 + cap * 8, pp.world = world, pp.half = half, pp.rank = rank;
+        return pp;
+    }
+};
+
 // one axis of the Lanczos3 u8 resize (fast_image_resize Normalizer16) for a given input size, resident in HBM
 struct CoefTable {
     uint32_t in_size = 0, window = 0, precision = 0;
@@ -101,6 +140,8 @@ struct vdf_ctx {
     uint32_t tc_unit_order = 0;  // variant 6 work-unit order: 0 chunk-major (L2-friendly, default), 1 row-pair-major
     uint32_t tc_a_tmem = 1;     // variant 6: three quarters of the row operand in tensor memory (0: all of it in shared memory)
     uint32_t hash_chunks = 1;  // hash.cu: software-pipeline chunks per call (1: letterbox, then resize, over the whole batch)
+    int exchange = 0;       // 1: searches append their matches to every rank's peer buffer (vdf_peer_*), see PeerExchange
+    vdf::PeerExchange peer;
     int grouping = 0;       // 0: the reference's greedy rule (parity); 1: connected components (GPU union-find, group.cu)
     uint64_t launches = 0, h2d = 0, d2h = 0;
     double phase_ms[4] = {0, 0, 0, 0};  // last vdf_search*: host sort, gather + H2D enqueue, device, index remap (host.cu)

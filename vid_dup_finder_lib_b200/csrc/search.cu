@@ -462,6 +462,55 @@ __global__ void __launch_bounds__(kHamThreads, 2) hamming_tiles_csa4_kernel(cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------ peer exchange
+// End of an exchange call: publish this rank's match count into every rank's buffer and signal; then wait until all ranks
+// have signalled.  The key stores of the pair kernel are ordered before the signal by the kernel boundary and a system-scope
+// fence; the wait is an acquire load at system scope.  `arrived` only ever grows (world per call on this half), so nothing
+// is reset across ranks.  A wait longer than `timeout_ns` (a dead peer) sets *timed_out instead of hanging the GPU.
+__global__ void peer_barrier_kernel(PeerPtrs pp, const unsigned long long* __restrict__ local_count, unsigned long long target,
+                                    unsigned long long timeout_ns, uint32_t* timed_out) {
+    if (threadIdx.x < pp.world) {
+        *pp.seg_count(threadIdx.x, pp.rank) = *local_count;
+        __threadfence_system();
+        atomicAdd_system(pp.arrived(threadIdx.x), 1ull);
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long t0, t1, seen;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long* mine = pp.arrived(pp.rank);
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+            if (seen >= target) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                *timed_out = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+}
+// the world segments of this rank's buffer -> one contiguous list; out[0] = total, out[1] = largest segment count
+__global__ void peer_compact_kernel(PeerPtrs pp, uint64_t* __restrict__ dst, uint64_t dst_cap, unsigned long long* __restrict__ out) {
+    unsigned long long off[kMaxPeers + 1];
+    unsigned long long biggest = 0;
+    off[0] = 0;
+    for (uint32_t w = 0; w < pp.world; ++w) {
+        const unsigned long long c = *pp.seg_count(pp.rank, w);
+        biggest = c > biggest ? c : biggest;
+        off[w + 1] = off[w] + (c < pp.seg_cap ? c : pp.seg_cap);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = off[pp.world], out[1] = biggest;
+    const unsigned long long total = off[pp.world] < dst_cap ? off[pp.world] : dst_cap;
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < total;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t w = 0;
+        while (k >= off[w + 1]) ++w;
+        dst[k] = pp.keys(pp.rank, w)[k - off[w]];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n) {
     if (n == 0) return VDF_OK;
@@ -503,7 +552,21 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, c
     VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const uint32_t max_span = (uint32_t)h_misc[0];
     *n_out = 0;
-    if (max_span == 0) return VDF_OK;
+    PeerPtrs pp;
+    pp.world = 0;
+    if (ctx->exchange) {  // matches of ALL ranks arrive in this rank's peer buffer (common.cuh: PeerExchange)
+        if (ctx->search_variant != 6) {
+            ctx->err = "peer exchange: only the default kernel (search_variant 6) stores to peer buffers";
+            return VDF_ERR_INVALID;
+        }
+        if (!ctx->peer.world) {
+            ctx->err = "peer exchange: call vdf_peer_alloc / vdf_peer_open first";
+            return VDF_ERR_INVALID;
+        }
+        pp = ctx->peer.ptrs((uint32_t)(ctx->peer.epoch & 1));
+    }
+    if (max_span == 0 && !pp.world) return VDF_OK;
+    if (max_span != 0) {
 
     // chunk: enough column tiles per CTA to amortise the row-tile load, small enough to balance 148 SMs
     uint32_t chunk = 32;
@@ -545,7 +608,40 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, c
     kt_end(ctx, 0);
     VDF_LAUNCHED(ctx);
     }
+    }  // max_span != 0
     unsigned long long cnt = 0;
+    const uint64_t* raw = ctx->raw_keys.as<uint64_t>();
+    if (pp.world) {
+        uint32_t* flag = reinterpret_cast<uint32_t*>(misc + 3);  // zeroed with misc above
+        const unsigned long long target = (unsigned long long)pp.world * (ctx->peer.epoch / 2 + 1);
+        peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(pp, misc + 2, target, 20ull * 1000 * 1000 * 1000, flag);
+        VDF_LAUNCHED(ctx);
+        ctx->peer.epoch += 1;
+        const uint64_t raw_cap = capacity ? capacity : 1;
+        peer_compact_kernel<<<64, 256, 0, ctx->stream>>>(pp, ctx->raw_keys.as<uint64_t>(), raw_cap, misc + 4);
+        VDF_LAUNCHED(ctx);
+        unsigned long long h_out[2] = {0, 0};
+        uint32_t timed_out = 0;
+        VDF_CUDA(ctx, cudaMemcpyAsync(h_out, misc + 4, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        VDF_CUDA(ctx, cudaMemcpyAsync(&timed_out, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (timed_out) {
+            ctx->err = "peer exchange: a rank did not finish its search within 20 s";
+            return VDF_ERR_CUDA;
+        }
+        cnt = h_out[0];
+        *n_out = cnt;
+        if (h_out[1] > pp.seg_cap) {  // some rank found more than a segment holds: every rank sees this alike
+            *n_out = h_out[1] * pp.world;
+            ctx->err = "edge buffer overflow: " + std::to_string(h_out[1]) + " matches on one rank > segment capacity " + std::to_string(pp.seg_cap);
+            return VDF_ERR_EDGE_OVERFLOW;
+        }
+        if (cnt > capacity) {
+            ctx->err = "edge buffer overflow: " + std::to_string(cnt) + " matches > capacity " + std::to_string(capacity);
+            return VDF_ERR_EDGE_OVERFLOW;
+        }
+        return sort_keys(ctx, raw, d_keys_out, cnt);
+    }
     VDF_CUDA(ctx, cudaMemcpyAsync(&cnt, misc + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
     VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *n_out = cnt;
@@ -553,7 +649,7 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, c
         ctx->err = "edge buffer overflow: " + std::to_string(cnt) + " matches > capacity " + std::to_string(capacity);
         return VDF_ERR_EDGE_OVERFLOW;
     }
-    return sort_keys(ctx, ctx->raw_keys.as<uint64_t>(), d_keys_out, cnt);
+    return sort_keys(ctx, raw, d_keys_out, cnt);
 }
 
 int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_dur, uint64_t n, uint32_t tol,

@@ -156,6 +156,7 @@ struct TcParams {
     const uint32_t* unit_off;  // variant 5: exclusive scan of the work units each row pair owns on this rank
     uint32_t n_pairs;
     const uint64_t* unit_list;  // variant 6: (chunk << 32 | row pair) of every unit this rank owns, chunk-major
+    PeerPtrs peers;             // variant 6: peers.world > 0 => matches go to every rank's exchange buffer (common.cuh)
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const TcParams p) {
@@ -1131,10 +1132,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
                         mask &= mask - 1;
                         const uint32_t gj = col_first + q * 64 + k;
                         if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
-                            const unsigned long long slot = atomicAdd(p.counter, 1ull);
-                            if (slot < p.capacity) {
-                                const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
-                                p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
+                            const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
+                            const uint64_t key = (rid << 32) | (uint64_t)(gj + p.col_base);
+                            if (p.peers.world) {  // fused exchange: this rank's segment of every rank's buffer, over NVLink
+                                const unsigned long long slot = atomicAdd(p.counter, 1ull);
+                                if (slot < p.peers.seg_cap)
+                                    for (uint32_t r = 0; r < p.peers.world; ++r) p.peers.keys(r, p.peers.rank)[slot] = key;
+                            } else {
+                                const unsigned long long slot = atomicAdd(p.counter, 1ull);
+                                if (slot < p.capacity) p.keys[slot] = key;
                             }
                         }
                     }
@@ -1216,6 +1222,14 @@ int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t
     p.tol = tol > 1024u ? 1024u : tol;  // no distance exceeds 1024 (and the epilogue's threshold is a signed int)
     p.rank = ctx->rank, p.world = ctx->world;
     p.unit_off = nullptr, p.n_pairs = 0, p.unit_list = nullptr;
+    p.peers.world = 0;
+    if (ctx->exchange) {
+        if (ctx->search_variant != 6 || !ctx->peer.world) {
+            ctx->err = "the peer exchange needs search_variant 6 and vdf_peer_open";
+            return VDF_ERR_INVALID;
+        }
+        p.peers = ctx->peer.ptrs((uint32_t)(ctx->peer.epoch & 1));
+    }
     if (ctx->search_variant >= 4) {  // CTA pairs: 256-row super-tiles x absolute chunks of column super-tiles
         const uint32_t n_pairs = (n_row_tiles + 1) / 2, n_st = (n_col_tiles + 1) / 2;
         // long chunks amortise the per-unit set-up (operand A, tensor-memory allocation, cluster syncs); keep >= 64

@@ -4,8 +4,11 @@ How the two paths shard:
   * hashing            - by stack, contiguous ranges, no exchange while hashing; one all-gather of the 128-byte
                          hashes afterwards so that every rank holds the table the search needs.
   * search_self        - every rank holds the full sorted table; the (row tile, chunk) units of the pair matrix are
-                         dealt block-cyclically to the ranks inside the kernel (vdf_ctx_set_shard); ONE exchange:
-                         a variable-length all-gather of the per-rank edge lists; the greedy grouping is replicated.
+                         dealt block-cyclically to the ranks inside the kernel (vdf_ctx_set_shard); ONE exchange of
+                         edges; the greedy grouping is replicated.  The exchange is fused into the pair kernel when
+                         `enable_peer_exchange` has been called: every match is appended to every rank's buffer over
+                         NVLink peer memory by the kernel that found it (include/vdf_b200.h: vdf_peer_*).  Without
+                         it: a variable-length NCCL all-gather of the per-rank edge lists.
   * search_with_refs   - the sorted candidate table is cut into contiguous slices, the references are replicated;
                          per-rank (ref, cand) keys are all-gathered and merged by a sort.
 """
@@ -75,30 +78,80 @@ def _run_growing(fn, device, initial: int = 1 << 22):
         cap = -cnt + 1024
 
 
+def enable_peer_exchange(ctx: _ffi.Context, group=None, capacity: int = 1 << 22) -> bool:
+    """Set up the fused edge exchange (one buffer per rank, mapped by all peers through CUDA IPC).  Collective: every rank
+    of the group calls it with the same capacity (matches of ALL ranks that must fit).  False on a single rank."""
+    rank, world = world_info(group)
+    if world < 2:
+        return False
+    if world > 8:
+        raise ValueError("the peer exchange covers the <= 8 GPUs of one node")
+    handle = ctx.peer_alloc(capacity)
+    handles: List[Optional[bytes]] = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    ctx.peer_open(rank, world, b"".join(handles))
+    dist.barrier(group=group)  # every rank has mapped every buffer before anyone appends
+    return True
+
+
+def disable_peer_exchange(ctx: _ffi.Context, group=None):
+    if ctx.peer_world:
+        torch.cuda.synchronize()
+        dist.barrier(group=group)  # nobody is still appending to a buffer about to be freed
+        ctx.peer_close()
+
+
+def _run_exchange(ctx: _ffi.Context, fn, device, group):
+    """fn with the library's "exchange" option on: returns the sorted keys of ALL ranks.  An overflow is reported with the same
+    global count on every rank, so all ranks re-allocate (collectively) and retry together."""
+    while True:
+        cap = ctx.peer_capacity
+        keys = torch.empty(cap, dtype=torch.int64, device=device)
+        torch.cuda.current_stream().synchronize()
+        ctx.set_option("exchange", 1)
+        try:
+            cnt = fn(keys.data_ptr(), cap)
+        finally:
+            ctx.set_option("exchange", 0)
+        if cnt >= 0:
+            return keys[:cnt]
+        need = -cnt
+        disable_peer_exchange(ctx, group)
+        enable_peer_exchange(ctx, group, need + need // 16 + 1024)
+
+
 def search_self_keys(ctx: _ffi.Context, d_hash, d_dur, tol_int: int, group=None, n: Optional[int] = None,
                      device=None) -> torch.Tensor:
-    """This rank's share of the pair matrix, then the edge all-gather: sorted (i << 32 | j) keys of ALL ranks.
+    """This rank's share of the pair matrix and the edge exchange: sorted (i << 32 | j) keys of ALL ranks.
     d_hash / d_dur: the sorted table resident in HBM, as torch tensors or as raw device pointers (then pass n, device)."""
     rank, world = world_info(group)
     if isinstance(d_hash, torch.Tensor):
         n, device, p_hash, p_dur = d_dur.numel(), d_hash.device, d_hash.data_ptr(), d_dur.data_ptr()
     else:
         p_hash, p_dur = int(d_hash), int(d_dur)
+    fused = world > 1 and ctx.peer_world == world
     ctx.set_shard(rank, world)
     try:
-        local = _run_growing(lambda p, cap: ctx.search_self_device(p_hash, p_dur, n, tol_int, p, cap), device)
+        run = lambda p, cap: ctx.search_self_device(p_hash, p_dur, n, tol_int, p, cap)  # noqa: E731
+        if fused:
+            return _run_exchange(ctx, run, device, group)
+        local = _run_growing(run, device)
     finally:
         ctx.set_shard(0, 1)
     return merge_keys(local, group)
 
 
 def search_refs_keys(ctx: _ffi.Context, d_cand_slice: torch.Tensor, d_cand_dur_slice: torch.Tensor, cand_base: int,
-                     d_refs: torch.Tensor, d_ref_dur: torch.Tensor, tol_int: int, group=None) -> torch.Tensor:
-    local = _run_growing(
-        lambda p, cap: ctx.search_refs_device(d_cand_slice.data_ptr(), d_cand_dur_slice.data_ptr(), d_cand_dur_slice.numel(),
-                                              cand_base, d_refs.data_ptr(), d_ref_dur.data_ptr(), d_ref_dur.numel(), tol_int,
-                                              p, cap), d_refs.device)
-    return merge_keys(local, group)
+                     d_refs: torch.Tensor, d_ref_dur: torch.Tensor, tol_int: int, group=None, allow_fused: bool = True) -> torch.Tensor:
+    """allow_fused=False when some rank may hold an empty candidate slice: the fused exchange ends in a barrier that every
+    rank must reach, and the library returns early on empty inputs"""
+    run = lambda p, cap: ctx.search_refs_device(d_cand_slice.data_ptr(), d_cand_dur_slice.data_ptr(),  # noqa: E731
+                                                d_cand_dur_slice.numel(), cand_base, d_refs.data_ptr(), d_ref_dur.data_ptr(),
+                                                d_ref_dur.numel(), tol_int, p, cap)
+    world = world_info(group)[1]
+    if allow_fused and world > 1 and ctx.peer_world == world:
+        return _run_exchange(ctx, run, d_refs.device, group)
+    return merge_keys(_run_growing(run, d_refs.device), group)
 
 
 def csr_from_keys(keys: np.ndarray, n_rows: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -152,7 +205,7 @@ def search_with_references(ref_hashes, new_hashes, tolerance: float, ctx: Option
     d_cd = _to_dev(np.ascontiguousarray(cands.durations[sl]), dev)
     d_r = _to_dev(refs.hashes, dev)
     d_rd = _to_dev(refs.durations, dev)
-    keys = search_refs_keys(ctx, d_c, d_cd, b, d_r, d_rd, tolerance_to_int(tolerance), group)
+    keys = search_refs_keys(ctx, d_c, d_cd, b, d_r, d_rd, tolerance_to_int(tolerance), group, allow_fused=len(cands) >= world)
     rp, ci = csr_from_keys(keys.cpu().numpy(), len(refs))
     return MatchGroup.from_csr(cands.paths, rp, order[ci.astype(np.int64)], references=refs.paths)
 
