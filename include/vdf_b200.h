@@ -216,12 +216,13 @@ int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint6
 
 /* `Search::seed` + `sort` (search_algorithm.rs:31-34,55-61) with the sorted table left RESIDENT in HBM: the stable
  * (duration, Path) permutation goes to order_out[n]; hashes and durations are gathered in that order through pinned
- * memory and uploaded on the context's stream.  *d_hash_sorted / *d_dur_sorted are device pointers owned by the context,
- * valid until the next vdf_stage_sorted / vdf_search* call on it; they feed vdf_search_self_device on every rank of a
- * multi-GPU search (vid_dup_finder_lib_b200/dist.py). */
+ * memory and uploaded on the context's stream - into d_hash_dst / d_dur_dst (n x 128 B / n x 4 B of device memory owned by
+ * the caller) when given, else into buffers owned by the context, valid until its next vdf_stage_sorted / vdf_search* call.
+ * *d_hash_sorted / *d_dur_sorted receive the device pointers; they feed vdf_search_self_device.  In a multi-GPU search one
+ * rank stages and broadcasts the table, the others skip the host sort (vid_dup_finder_lib_b200/dist.py). */
 int vdf_stage_sorted(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, const char* path_blob,
-                     const uint64_t* path_off, uint64_t n, uint64_t* order_out, const uint64_t** d_hash_sorted,
-                     const uint32_t** d_dur_sorted);
+                     const uint64_t* path_off, uint64_t n, uint64_t* order_out, uint64_t* d_hash_dst, uint32_t* d_dur_dst,
+                     const uint64_t** d_hash_sorted, const uint32_t** d_dur_sorted);
 
 /* Replaces `search(hashes, tolerance)` (video_dup_finder.rs:7-13): groups exactly as the reference returns them
  * (matches in sorted order, the target last, groups by descending target; every group has >= 2 entries), with

@@ -144,7 +144,7 @@ if [[ $STEP == xg ]]; then
   # multi-GPU: parity of both exchange modes, then the bench with each (same box, back to back)
   N=${2:-2}
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 scripts/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "dist_check rc=$?"; grep -v "^W1\|OMP_NUM\|^\*\*\*" gpurun_out/dist_check_$N.log | tail -9
-  for ex in peer nccl; do
+  for ex in peer; do
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 5 --warmup 3 --exchange $ex --no-secondary --no-cpu-baseline > gpurun_out/bench_xg${N}_$ex.json 2> gpurun_out/bench_xg${N}_$ex.err; echo "bench x$N $ex rc=$?"; python -c "import json;d=json.loads(open('gpurun_out/bench_xg${N}_$ex.json').read().strip().splitlines()[-1]);print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'], d['e2e']['ms_per_call'])"
   done
 fi

@@ -92,7 +92,7 @@ def lib() -> C.CDLL:
     L.vdf_last_error.restype = C.c_char_p
     L.vdf_ctx_set_shard.argtypes = [vp, u32, u32]
     L.vdf_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
-    L.vdf_stage_sorted.argtypes = [vp, vp, vp, vp, vp, u64, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.vdf_stage_sorted.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     L.vdf_peer_alloc.argtypes = [vp, u64, vp]
     L.vdf_peer_open.argtypes = [vp, u32, u32, vp]
     L.vdf_peer_close.argtypes = [vp]
@@ -229,14 +229,15 @@ class Context:
         lib().vdf_free_groups(C.byref(g))
         return gp, mm
 
-    def stage_sorted(self, hashes, durations, path_blob: np.ndarray, path_off: np.ndarray):
-        """vdf_stage_sorted: -> (order [n] int64, device pointer of the sorted hashes, device pointer of the sorted durations)"""
+    def stage_sorted(self, hashes, durations, path_blob: np.ndarray, path_off: np.ndarray, d_hash_dst: int = 0, d_dur_dst: int = 0):
+        """vdf_stage_sorted: -> (order [n] int64, device pointer of the sorted hashes, device pointer of the sorted durations);
+        d_hash_dst / d_dur_dst: caller-owned device buffers to upload into (0: buffers owned by the context)"""
         h = _hash_array(hashes)
         d = np.ascontiguousarray(durations, dtype=np.uint32)
         order = np.empty(len(d), dtype=np.uint64)
         ph, pd = C.c_void_p(), C.c_void_p()
         self._check(lib().vdf_stage_sorted(self._h, _ptr(h), _ptr(d), _ptr(path_blob), _ptr(path_off), len(d), _ptr(order),
-                                           C.byref(ph), C.byref(pd)))
+                                           C.c_void_p(d_hash_dst or None), C.c_void_p(d_dur_dst or None), C.byref(ph), C.byref(pd)))
         return order.view(np.int64), int(ph.value or 0), int(pd.value or 0)
 
     def group_greedy(self, n: int, edges):

@@ -237,9 +237,11 @@ int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint6
 }
 
 int vdf_stage_sorted(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, const char* path_blob, const uint64_t* path_off,
-                     uint64_t n, uint64_t* order_out, const uint64_t** d_hash_sorted, const uint32_t** d_dur_sorted) {
+                     uint64_t n, uint64_t* order_out, uint64_t* d_hash_dst, uint32_t* d_dur_dst, const uint64_t** d_hash_sorted,
+                     const uint32_t** d_dur_sorted) {
     VDF_TRY(enter(ctx));
-    if (!order_out || !d_hash_sorted || !d_dur_sorted || (n && (!hashes || !durations || !path_off))) return VDF_ERR_INVALID;
+    if (!order_out || !d_hash_sorted || !d_dur_sorted || (n && (!hashes || !durations || !path_off)) || (!d_hash_dst != !d_dur_dst))
+        return VDF_ERR_INVALID;
     if (n >= 0xFFFFFF00ull) {
         ctx->err = "n must be < 2^32";
         return VDF_ERR_INVALID;
@@ -249,13 +251,19 @@ int vdf_stage_sorted(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durat
     VDF_TRY(sort_order_impl(durations, path_blob, path_off, n, keys));
     double t1 = now_ms();
     if (n) VDF_TRY(stage_sorted(ctx, hashes, durations, keys, ctx->in_hash, ctx->in_dur, ctx->pin_a, ctx->pin_b));
+    *d_hash_sorted = ctx->in_hash.as<uint64_t>();
+    *d_dur_sorted = ctx->in_dur.as<uint32_t>();
+    if (n && d_hash_dst) {  // the caller's buffers (e.g. tensors it will broadcast to the other ranks)
+        VDF_CUDA(ctx, cudaMemcpyAsync(d_hash_dst, ctx->in_hash.p, n * 128, cudaMemcpyDeviceToDevice, ctx->stream));
+        VDF_CUDA(ctx, cudaMemcpyAsync(d_dur_dst, ctx->in_dur.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        *d_hash_sorted = d_hash_dst;
+        *d_dur_sorted = d_dur_dst;
+    }
     parallel_for(n, n_threads(n), [&](uint64_t b, uint64_t e, unsigned) {
         for (uint64_t k = b; k < e; ++k) order_out[k] = keys[k].idx;
     });
     double t2 = now_ms();
     ctx->phase_ms[0] = t1 - t0, ctx->phase_ms[1] = t2 - t1, ctx->phase_ms[2] = 0, ctx->phase_ms[3] = 0;
-    *d_hash_sorted = ctx->in_hash.as<uint64_t>();
-    *d_dur_sorted = ctx->in_dur.as<uint32_t>();
     return VDF_OK;
 }
 

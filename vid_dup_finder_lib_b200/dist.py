@@ -180,10 +180,24 @@ def search(hashes, tolerance: float, ctx: Optional[_ffi.Context] = None, group=N
 
         return search_one(table, tolerance, ctx)
     dev = torch.device("cuda", ctx.device)
-    # native host side of vdf_search: multi-threaded (duration, Path) sort, gather through pinned memory, async upload
-    order, p_hash, p_dur = ctx.stage_sorted(table.hashes, table.durations, *table.path_blob())
+    # Rank 0 does the native host side of vdf_search (multi-threaded (duration, Path) sort, gather through pinned memory,
+    # upload) and broadcasts the sorted table and the permutation over NVLink: eight ranks sorting the same million paths on
+    # the same host cores would take longer than the whole device side.
+    rank = world_info(group)[0]
     with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)):
-        keys = search_self_keys(ctx, p_hash, p_dur, tolerance_to_int(tolerance), group, n=n, device=dev)
+        d_hash = torch.empty((n, 16), dtype=torch.int64, device=dev)
+        d_dur = torch.empty(n, dtype=torch.int32, device=dev)
+        d_order = torch.empty(n, dtype=torch.int64, device=dev)
+        if rank == 0:
+            order, _, _ = ctx.stage_sorted(table.hashes, table.durations, *table.path_blob(), d_hash_dst=d_hash.data_ptr(),
+                                           d_dur_dst=d_dur.data_ptr())
+            d_order.copy_(torch.from_numpy(order), non_blocking=False)
+        dist.broadcast(d_hash, 0, group=group)
+        dist.broadcast(d_dur, 0, group=group)
+        dist.broadcast(d_order, 0, group=group)
+        keys = search_self_keys(ctx, d_hash, d_dur, tolerance_to_int(tolerance), group)
+        if rank != 0:
+            order = d_order.cpu().numpy()
         torch.cuda.current_stream().synchronize()
         gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
     return MatchGroup.from_csr(table.paths, gp, order[mm.astype(np.int64)])
