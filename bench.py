@@ -334,7 +334,11 @@ def main():
     dev = torch.device("cuda", local)
     fused = world > 1 and args.exchange == "peer" and args.workload in ("search", "refs") and (args.variant in (-1, 6))
     if fused:
-        vdist.enable_peer_exchange(ctx, capacity=1 << 22)
+        try:
+            vdist.enable_peer_exchange(ctx, capacity=1 << 22)
+        except Exception as e:  # e.g. CUDA IPC unavailable in this container: all ranks fail alike and use the collective
+            print(f"[bench] peer exchange unavailable ({e!r}); falling back to the NCCL all-gather", file=sys.stderr)
+            fused = False
     exchange_note = ("edges appended to every rank's buffer by the pair kernel over NVLink peer memory" if fused else
                      "NCCL all-gather of per-rank edge lists") if world > 1 else "single GPU"
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
