@@ -576,7 +576,7 @@ def main():
             from oracle import vdf_oracle as o
 
             cores = os.cpu_count() or 1
-            nb = min(ns, max(cores, 8))
+            nb = min(ns, 128, 4 * max(cores, 2))  # four stacks per thread: ~1 s of CPU work on the box
             hs = pool[:nb].cpu().numpy()
             t0 = time.perf_counter()
             with ThreadPoolExecutor(cores) as ex:
