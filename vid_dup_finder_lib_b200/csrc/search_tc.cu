@@ -1068,7 +1068,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
     } else if (warp >= 6) {  // ===== expanders: a warp writes 4 rows x 8 units per group, 6 groups per stage
         // Measured alternatives that did not help (1 M hashes, ms per launch): 6 or 8 warps on every stage (133.6 / 138.1
         // against 130.7), two teams of four warps on alternate stages (132.8 against 131.6), one fence.proxy.async per 2 / 4
-        // stages (123.3 / 123.6 against 122.6).
+        // stages (123.3 / 123.6 against 122.6), probing the next stage's `empty` barrier with mbarrier.test_wait before this
+        // stage's stores (123.7 against 121.2).
         constexpr int kG = 24 / kT6Expanders;  // four-row groups per warp per stage
         const int w = lane & 7, r4 = lane >> 3;
         const int row0 = (warp - 6) * 4 + r4;  // + 4 * kT6Expanders * g
