@@ -148,6 +148,11 @@ if [[ $STEP == xg ]]; then
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 5 --warmup 3 --exchange $ex --no-secondary --no-cpu-baseline > gpurun_out/bench_xg${N}_$ex.json 2> gpurun_out/bench_xg${N}_$ex.err; echo "bench x$N $ex rc=$?"; python -c "import json;d=json.loads(open('gpurun_out/bench_xg${N}_$ex.json').read().strip().splitlines()[-1]);print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'], d['e2e']['ms_per_call'])"
   done
 fi
+if [[ $STEP == sanitize ]]; then
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_search.py tests/test_gpu_hashing.py -m gpu -x -q \
+      -k "variant6_kernel_options or (edges_and_groups and tcgen05_mxf4 and (129 or 1000)) or find_with_refs or known_group or components_mode or letterbox_kat or cropdetect_none or dct_threshold" \
+      > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitizer_memcheck.log
+fi
 if [[ $STEP == big ]]; then
   # BASELINE configs[3] and [4] sizes on one GPU: 100k queries x 10M-entry table; all-pairs over a 10M-hash corpus
   timeout 900 python bench.py --workload refs --steps 3 --warmup 1 > gpurun_out/bench_refs_10m.json 2> gpurun_out/bench_refs_10m.err; echo "bench refs rc=$?"; tail -c 1200 gpurun_out/bench_refs_10m.json; tail -3 gpurun_out/bench_refs_10m.err

@@ -139,7 +139,7 @@ def main():
     for f in sorted(os.listdir(OUT)):
         if f.startswith("dist_check") and f.endswith(".log"):
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, f"{tag}_{f}"))
-    for f in ("gpu.csv", "host.txt", "pytest_gpu.log", "smoke.log"):
+    for f in ("gpu.csv", "host.txt", "pytest_gpu.log", "smoke.log", "sanitizer_memcheck.log"):
         if os.path.exists(os.path.join(OUT, f)):
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, f"{tag}_{f}"))
     print("profiles/:", sorted(os.listdir(PROF)))
