@@ -66,6 +66,68 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+class _StubCtx:
+    """stands in for _ffi.Context in the collective logic of the fused exchange (set-up, overflow -> all ranks re-allocate
+    together -> retry); the real thing needs >= 2 GPUs and is checked by scripts/dist_check.py"""
+
+    def __init__(self, rank):
+        self.rank, self.peer_capacity, self.peer_world, self.log = rank, 0, 0, []
+
+    def peer_alloc(self, cap):
+        self.peer_capacity, self.peer_world = int(cap), 0
+        self.log.append(("alloc", int(cap)))
+        return bytes([self.rank]) * 64
+
+    def peer_open(self, rank, world, handles):
+        assert rank == self.rank and handles == b"".join(bytes([r]) * 64 for r in range(world))  # rank order
+        self.peer_world = world
+        self.log.append(("open", world))
+
+    def peer_close(self):
+        self.peer_capacity, self.peer_world = 0, 0
+        self.log.append(("close",))
+
+    def set_option(self, k, v):
+        self.log.append((k, v))
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ctx = _StubCtx(rank)
+        assert vdist.enable_peer_exchange(ctx, capacity=100)
+        total = 700  # matches over all ranks: the same count reaches every rank, as from the library
+
+        def fn(ptr, cap):
+            return total if cap >= total else -total
+
+        keys = vdist._run_exchange(ctx, fn, torch.device("cpu"), None)
+        ok = keys.numel() == total and ctx.peer_world == world and ctx.peer_capacity >= total
+        ok &= [e for e in ctx.log if e[0] in ("alloc", "close")] == [("alloc", 100), ("close",), ("alloc", ctx.peer_capacity)]
+        ok &= ctx.log.count(("exchange", 1)) == 2 and ctx.log[-1] == ("exchange", 0)
+        vdist.disable_peer_exchange(ctx)
+        ok &= ctx.peer_world == 0
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_exchange_collective_logic():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_edge_allgather_and_merge(world):
     ctx = mp.get_context("spawn")

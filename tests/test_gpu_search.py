@@ -162,6 +162,58 @@ def test_public_api_in_caller_order_matches_oracle(ctx):
     assert sum(ctx.last_phases()) > 0
 
 
+def test_stage_sorted_leaves_the_sorted_table_resident(ctx):
+    """vdf_stage_sorted = Search::seed + sort with the table left in HBM: the permutation is the oracle's, and the device
+    pointers it returns feed vdf_search_self_device (what every rank of a multi-GPU search does) - also when the upload goes
+    into caller-owned buffers"""
+    import torch
+
+    rng = np.random.default_rng(78)
+    n = 2500
+    H, dur = _case(rng, n, 200, 180, [0, 9, 10, 11, 12, 100, 105, 110, 111, 600])
+    dur = dur[rng.permutation(n)]
+    pieces = ["a", "b", "-", ".", "/", "..", "_", "0", "v", "ab"]
+    paths = ["".join(rng.choice(pieces, int(rng.integers(1, 7)))) + "/%05d" % i for i in range(n)]
+    table = vdf.HashTable(H, dur, paths)
+    want_order = o.sort_order(dur, paths)
+    want_keys = o.self_edges(np.ascontiguousarray(H[want_order]), dur[want_order], 300)
+    dev = torch.device("cuda", ctx.device)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    with torch.cuda.stream(stream):
+        keys = torch.empty(1 << 16, dtype=torch.int64, device=dev)
+        own_h = torch.empty((n, 16), dtype=torch.int64, device=dev)
+        own_d = torch.empty(n, dtype=torch.int32, device=dev)
+        for dst in ((0, 0), (own_h.data_ptr(), own_d.data_ptr())):
+            order, p_hash, p_dur = ctx.stage_sorted(table.hashes, table.durations, *table.path_blob(), d_hash_dst=dst[0], d_dur_dst=dst[1])
+            assert np.array_equal(order, want_order)
+            if dst[0]:
+                assert (p_hash, p_dur) == dst
+            torch.cuda.current_stream().synchronize()
+            cnt = ctx.search_self_device(p_hash, p_dur, n, 300, keys.data_ptr(), keys.numel())
+            got = keys[:cnt].cpu().numpy().view(np.uint64)
+            assert np.array_equal(np.stack([got >> np.uint64(32), got & np.uint64(0xFFFFFFFF)], axis=1), want_keys)
+        assert np.array_equal(own_d.cpu().numpy().view(np.uint32), dur[want_order])
+        assert np.array_equal(own_h.cpu().numpy().view(np.uint64), H[want_order])
+
+
+def test_peer_exchange_needs_its_set_up(ctx):
+    """the fused exchange refuses to run half configured (its real test needs >= 2 GPUs: scripts/dist_check.py)"""
+    H, dur = _case(np.random.default_rng(5), 300, 30, 100, [600])
+    with pytest.raises(_ffi.VdfError):
+        ctx.peer_open(0, 2, b"\0" * 128)  # no vdf_peer_alloc before
+    ctx.set_option("exchange", 1)
+    try:
+        with pytest.raises(_ffi.VdfError):
+            ctx.search_self(H, dur, 300)  # "exchange" on, no peers mapped
+    finally:
+        ctx.set_option("exchange", 0)
+    assert len(ctx.peer_alloc(1000)) == 64  # allocation and IPC export work on one GPU; world >= 2 is required to open
+    with pytest.raises(_ffi.VdfError):
+        ctx.peer_open(0, 1, b"\0" * 64)
+    ctx.peer_close()
+    assert np.array_equal(ctx.search_self(H, dur, 300), o.self_edges(H, dur, 300))
+
+
 def test_greedy_rule_is_not_connected_components(ctx):
     a = rf.empty_hash()
     b = a.copy(); b[0] = np.uint64(0xFF)

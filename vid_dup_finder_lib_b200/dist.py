@@ -67,11 +67,16 @@ def merge_keys(local_keys: torch.Tensor, group=None) -> torch.Tensor:
     return torch.sort(allk).values if allk.numel() else allk
 
 
+def _sync(device):
+    if torch.device(device).type == "cuda":
+        torch.cuda.current_stream().synchronize()
+
+
 def _run_growing(fn, device, initial: int = 1 << 22):
     cap = initial
     while True:
         keys = torch.empty(cap, dtype=torch.int64, device=device)
-        torch.cuda.current_stream().synchronize()
+        _sync(device)
         cnt = fn(keys.data_ptr(), cap)
         if cnt >= 0:
             return keys[:cnt]
@@ -96,7 +101,8 @@ def enable_peer_exchange(ctx: _ffi.Context, group=None, capacity: int = 1 << 22)
 
 def disable_peer_exchange(ctx: _ffi.Context, group=None):
     if ctx.peer_world:
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
         dist.barrier(group=group)  # nobody is still appending to a buffer about to be freed
         ctx.peer_close()
 
@@ -107,7 +113,7 @@ def _run_exchange(ctx: _ffi.Context, fn, device, group):
     while True:
         cap = ctx.peer_capacity
         keys = torch.empty(cap, dtype=torch.int64, device=device)
-        torch.cuda.current_stream().synchronize()
+        _sync(device)
         ctx.set_option("exchange", 1)
         try:
             cnt = fn(keys.data_ptr(), cap)
