@@ -120,6 +120,15 @@ def test_native_sort_order_matches_the_python_rule_and_the_oracle():
     bd = rng.integers(590, 600, n).astype(np.uint32)
     tb = vdf.HashTable(np.zeros((n, 16), np.uint64), bd, big)
     assert np.array_equal(_ffi.sort_order(bd, *tb.path_blob()), sort_order(bd, big))
+    # a library under one directory: the bytes all paths share are skipped by the sort keys; entries that ARE the shared
+    # prefix, entries sharing only part of it, exact ties spread over all threads' runs
+    n = 120_000
+    deep = ["/data/videos/collection_%03d/clip_%08d.mp4" % (i % 500, i) for i in rng.permutation(n)]
+    for extra in ([], ["/data/videos/collection_", "/data/videos/collection_001", "/data/videos"], ["/data", "/", "relative/clip.mp4"]):
+        ps = deep + extra + deep[:2000]
+        dd = rng.integers(598, 600, len(ps)).astype(np.uint32)
+        tb = vdf.HashTable(np.zeros((len(ps), 16), np.uint64), dd, ps)
+        assert np.array_equal(_ffi.sort_order(dd, *tb.path_blob()), o.sort_order(dd, ps)), extra
     assert len(_ffi.sort_order(np.zeros(0, np.uint32), *vdf.HashTable(np.zeros((0, 16), np.uint64), [], []).path_blob())) == 0
 
 

@@ -84,19 +84,23 @@ size_t encode_path(const char* p, size_t len, uint8_t* out) {  // out == nullptr
 struct SortKey {
     uint32_t dur;
     uint32_t idx;
-    uint64_t prefix;  // first 8 encoded bytes, big-endian, zero padded
+    uint64_t prefix, prefix2;  // encoded bytes 0-7 and 8-15, big-endian, zero padded
 };
+constexpr uint64_t kPrefixBytes = 16;
 
 struct KeyLess {
     const uint8_t* enc;
     const uint64_t* eoff;
+    uint64_t skip;  // bytes shared by ALL encoded paths (their common directory prefix): never compared
     bool operator()(const SortKey& a, const SortKey& b) const {
         if (a.dur != b.dur) return a.dur < b.dur;
         if (a.prefix != b.prefix) return a.prefix < b.prefix;
-        const uint64_t la = eoff[a.idx + 1] - eoff[a.idx], lb = eoff[b.idx + 1] - eoff[b.idx];
-        if (la > 8 || lb > 8) {
-            const uint64_t sa = la > 8 ? la - 8 : 0, sb = lb > 8 ? lb - 8 : 0;
-            const int c = memcmp(enc + eoff[a.idx] + (la > 8 ? 8 : la), enc + eoff[b.idx] + (lb > 8 ? 8 : lb), std::min(sa, sb));
+        if (a.prefix2 != b.prefix2) return a.prefix2 < b.prefix2;
+        const uint64_t la = eoff[a.idx + 1] - eoff[a.idx] - skip, lb = eoff[b.idx + 1] - eoff[b.idx] - skip;
+        if (la > kPrefixBytes || lb > kPrefixBytes) {
+            const uint64_t sa = la > kPrefixBytes ? la - kPrefixBytes : 0, sb = lb > kPrefixBytes ? lb - kPrefixBytes : 0;
+            const int c = memcmp(enc + eoff[a.idx] + skip + (la > kPrefixBytes ? kPrefixBytes : la),
+                                 enc + eoff[b.idx] + skip + (lb > kPrefixBytes ? kPrefixBytes : lb), std::min(sa, sb));
             if (c) return c < 0;
             if (sa != sb) return sa < sb;
         } else if (la != lb) {
@@ -119,15 +123,35 @@ int sort_order_impl(const uint32_t* dur, const char* paths, const uint64_t* off,
     for (uint64_t i = 0; i < n; ++i) eoff[i + 1] += eoff[i];
     std::vector<uint8_t> enc(eoff[n] + 8, 0);
     parallel_for(n, t, [&](uint64_t b, uint64_t e, unsigned) {
+        for (uint64_t i = b; i < e; ++i) encode_path(paths + off[i], off[i + 1] - off[i], enc.data() + eoff[i]);
+    });
+    // the bytes every path shares (a library usually lives under one directory) carry no order: the in-key prefixes start
+    // after them, so they hold the bytes that actually tell paths apart
+    std::vector<uint64_t> lcp(t, ~0ull);
+    parallel_for(n, t, [&](uint64_t b, uint64_t e, unsigned th) {
+        uint64_t m = eoff[1] - eoff[0];
+        for (uint64_t i = b; i < e && m; ++i) {
+            const uint64_t l = std::min(m, eoff[i + 1] - eoff[i]);
+            uint64_t k = 0;
+            while (k < l && enc[eoff[i] + k] == enc[k]) ++k;
+            m = k;
+        }
+        lcp[th] = m;
+    });
+    uint64_t skip = eoff[1] - eoff[0];
+    for (unsigned k = 0; k < t; ++k)
+        if (lcp[k] != ~0ull) skip = std::min(skip, lcp[k]);
+    parallel_for(n, t, [&](uint64_t b, uint64_t e, unsigned) {
         for (uint64_t i = b; i < e; ++i) {
-            encode_path(paths + off[i], off[i + 1] - off[i], enc.data() + eoff[i]);
-            const uint64_t l = eoff[i + 1] - eoff[i];
-            uint64_t pre = 0;
-            for (uint64_t k = 0; k < 8; ++k) pre = (pre << 8) | (k < l ? enc[eoff[i] + k] : 0);
-            keys[i] = SortKey{dur[i], (uint32_t)i, pre};
+            const uint64_t l = eoff[i + 1] - eoff[i] - skip;
+            const uint8_t* p = enc.data() + eoff[i] + skip;
+            uint64_t pre = 0, pre2 = 0;
+            for (uint64_t k = 0; k < 8; ++k) pre = (pre << 8) | (k < l ? p[k] : 0);
+            for (uint64_t k = 8; k < 16; ++k) pre2 = (pre2 << 8) | (k < l ? p[k] : 0);
+            keys[i] = SortKey{dur[i], (uint32_t)i, pre, pre2};
         }
     });
-    KeyLess less{enc.data(), eoff.data()};
+    KeyLess less{enc.data(), eoff.data(), skip};
     if (dbg) fprintf(stderr, "[vdf] sort: encode %.1f ms (%u threads)\n", now_ms() - d0, t), d0 = now_ms();
     if (t <= 1) {
         std::sort(keys.begin(), keys.end(), less);
@@ -140,23 +164,60 @@ int sort_order_impl(const uint32_t* dur, const char* paths, const uint64_t* off,
         for (uint64_t k = b; k < e; ++k) std::sort(keys.begin() + cut[k], keys.begin() + cut[k + 1], less);
     });
     if (dbg) fprintf(stderr, "[vdf] sort: runs %.1f ms\n", now_ms() - d0), d0 = now_ms();
-    std::vector<SortKey> tmp(n);
-    std::vector<SortKey>*src = &keys, *dst = &tmp;
-    while (cut.size() > 2) {
-        const size_t runs = cut.size() - 1, pairs = runs / 2;
-        std::vector<uint64_t> next;
-        for (size_t k = 0; k + 1 < cut.size(); k += 2) next.push_back(cut[k]);
-        next.push_back(n);
-        parallel_for(pairs + (runs & 1), (unsigned)(pairs + (runs & 1)), [&](uint64_t b, uint64_t e, unsigned) {
-            for (uint64_t k = b; k < e; ++k) {
-                const uint64_t lo = cut[2 * k], mid = cut[std::min<size_t>(2 * k + 1, runs)], hi = cut[std::min<size_t>(2 * k + 2, runs)];
-                std::merge(src->begin() + lo, src->begin() + mid, src->begin() + mid, src->begin() + hi, dst->begin() + lo, less);
-            }
-        });
-        std::swap(src, dst);
-        cut.swap(next);
+    // t sorted runs -> t disjoint key ranges (splitters from a regular sample of the runs), one thread per range: every
+    // thread merges its t run segments on its own, so all merge passes run t-wide (pairwise merging of whole runs leaves the
+    // last pass, over all n keys, to a single thread)
+    std::vector<SortKey> sample;
+    const uint64_t stride = std::max<uint64_t>(1, n / ((uint64_t)t * 64));
+    for (unsigned r = 0; r < t; ++r)
+        for (uint64_t i = cut[r] + stride / 2; i < cut[r + 1]; i += stride) sample.push_back(keys[i]);
+    std::sort(sample.begin(), sample.end(), less);
+    std::vector<uint64_t> pos((size_t)t * (t + 1));  // pos[r * (t + 1) + j]: first key of run r that belongs to range j or later
+    for (unsigned r = 0; r < t; ++r) {
+        pos[(size_t)r * (t + 1)] = cut[r];
+        pos[(size_t)r * (t + 1) + t] = cut[r + 1];
     }
-    if (src != &keys) keys.swap(tmp);
+    parallel_for(t, t, [&](uint64_t b, uint64_t e, unsigned) {
+        for (uint64_t r = b; r < e; ++r)
+            for (unsigned j = 1; j < t; ++j) {
+                const SortKey& sp = sample[std::min<size_t>(sample.size() - 1, sample.size() * j / t)];
+                pos[r * (t + 1) + j] = (uint64_t)(std::lower_bound(keys.begin() + cut[r], keys.begin() + cut[r + 1], sp, less) - keys.begin());
+            }
+    });
+    std::vector<uint64_t> out_off(t + 1, 0);
+    for (unsigned j = 0; j < t; ++j) {
+        uint64_t sz = 0;
+        for (unsigned r = 0; r < t; ++r) sz += pos[(size_t)r * (t + 1) + j + 1] - pos[(size_t)r * (t + 1) + j];
+        out_off[j + 1] = out_off[j] + sz;
+    }
+    std::vector<SortKey> tmp(n), tmp2(n);
+    parallel_for(t, t, [&](uint64_t b, uint64_t e, unsigned) {
+        for (uint64_t j = b; j < e; ++j) {
+            // gather the t segments of range j back to back, then pairwise merges inside [out_off[j], out_off[j + 1])
+            std::vector<uint64_t> seg(1, out_off[j]);
+            uint64_t w = out_off[j];
+            for (unsigned r = 0; r < t; ++r) {
+                const uint64_t lo = pos[(size_t)r * (t + 1) + j], hi = pos[(size_t)r * (t + 1) + j + 1];
+                std::copy(keys.begin() + lo, keys.begin() + hi, tmp.begin() + w);
+                w += hi - lo;
+                seg.push_back(w);
+            }
+            std::vector<SortKey>*src = &tmp, *dst = &tmp2;
+            while (seg.size() > 2) {
+                std::vector<uint64_t> next;
+                for (size_t k = 0; k + 1 < seg.size(); k += 2) {
+                    const uint64_t lo = seg[k], mid = seg[k + 1], hi = seg[std::min(k + 2, seg.size() - 1)];
+                    std::merge(src->begin() + lo, src->begin() + mid, src->begin() + mid, src->begin() + hi, dst->begin() + lo, less);
+                    next.push_back(lo);
+                }
+                next.push_back(seg.back());
+                std::swap(src, dst);
+                seg.swap(next);
+            }
+            if (src != &tmp) std::copy(src->begin() + out_off[j], src->begin() + out_off[j + 1], tmp.begin() + out_off[j]);
+        }
+    });
+    keys.swap(tmp);
     if (dbg) fprintf(stderr, "[vdf] sort: merges %.1f ms\n", now_ms() - d0);
     return VDF_OK;
 }
