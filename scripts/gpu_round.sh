@@ -94,43 +94,11 @@ if [[ $STEP == r6 ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tc6 -c 1 -f -o gpurun_out/prof_hamming_tc6__self_1000000_x1 \
       python bench.py --steps 1 --warmup 0 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_hamming_tc6.log 2>&1; echo "ncu tc6 rc=$?"
 fi
-if [[ $STEP == x7 ]]; then
-  # variant-6 experiments: expander warps x work-unit order; tcgen05 issue-rate microbenchmark
-  timeout 300 ./vid_dup_finder_lib_b200/vdf_microbench > gpurun_out/microbench.jsonl 2>&1; echo "microbench rc=$?"; tail -5 gpurun_out/microbench.jsonl
-  timeout 900 python -m pytest tests/test_gpu_search.py -m gpu -x -q > gpurun_out/pytest_search.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_search.log
-  for o in 0 1; do for e in 4 6 8; do
-    timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_expanders=$e --opt tc_unit_order=$o --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x7_e${e}_o${o}.json 2> gpurun_out/bench_x7_e${e}_o${o}.err; echo "bench e=$e o=$o rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x7_e${e}_o${o}.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x7_e${e}_o${o}.err
-  done; done
-fi
-if [[ $STEP == x8 ]]; then
-  # variant 6 with three quarters of the row operand in tensor memory; TMEM read-rate microbenchmark
-  timeout 300 ./vid_dup_finder_lib_b200/vdf_microbench > gpurun_out/microbench.jsonl 2>&1; echo "microbench rc=$?"; tail -4 gpurun_out/microbench.jsonl
-  timeout 600 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "variant6_kernel_options" > gpurun_out/pytest_x8.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_x8.log
-  for a in 0 1; do
-    timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_a_tmem=$a --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x8_a${a}.json 2> gpurun_out/bench_x8_a${a}.err; echo "bench a_tmem=$a rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x8_a${a}.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x8_a${a}.err
-  done
-fi
-if [[ $STEP == x9 ]]; then
-  timeout 600 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "variant6_kernel_options" > gpurun_out/pytest_x9.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_x9.log
-  for a in 0 1; do for e in 4 8; do
-    timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_a_tmem=$a --opt tc_expanders=$e --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x9_a${a}_e${e}.json 2> gpurun_out/bench_x9_a${a}_e${e}.err; echo "bench a_tmem=$a e=$e rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x9_a${a}_e${e}.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x9_a${a}_e${e}.err
-  done; done
-fi
+# (the x7-x12 option sweeps whose bench lines are in profiles/experiments/ used kernel options that were removed again once
+# measured: expander warp counts and teams, fence batching, timing-only debug forms - see the comments in csrc/search_tc.cu)
 if [[ $STEP == x10 ]]; then
   for c in 64 256 512 1024 2048; do
-    timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_a_tmem=1 --opt tc_chunk=$c --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x10_c${c}.json 2> gpurun_out/bench_x10_c${c}.err; echo "bench chunk=$c rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x10_c${c}.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x10_c${c}.err
-  done
-fi
-if [[ $STEP == x11 ]]; then
-  # where does the steady state lose time?  (debug forms give wrong results on purpose; thresholds are disabled in them)
-  for d in 0 1 3 4 7; do
-    timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_debug=$d --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x11_d${d}.json 2> gpurun_out/bench_x11_d${d}.err; echo "bench debug=$d rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x11_d${d}.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x11_d${d}.err
-  done
-fi
-if [[ $STEP == x12 ]]; then
-  timeout 600 python -m pytest tests/test_gpu_search.py -m gpu -x -q -k "variant6_kernel_options" > gpurun_out/pytest_x12.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_x12.log
-  for cfg in "4 1" "4 2" "4 4" "8 1" "8 2"; do set -- $cfg
-    timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_expanders=$1 --opt tc_fence_batch=$2 --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x12_e$1_f$2.json 2> gpurun_out/bench_x12_e$1_f$2.err; echo "bench e=$1 fence_batch=$2 rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x12_e$1_f$2.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x12_e$1_f$2.err
+    timeout 300 python bench.py --steps 3 --warmup 2 --opt tc_chunk=$c --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_x10_c${c}.json 2> gpurun_out/bench_x10_c${c}.err; echo "bench chunk=$c rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_x10_c${c}.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'])"; tail -2 gpurun_out/bench_x10_c${c}.err
   done
 fi
 if [[ $STEP == x13 ]]; then
