@@ -121,6 +121,12 @@ if [[ $STEP == sanitize ]]; then
       -k "variant6_kernel_options or (edges_and_groups and tcgen05_mxf4 and (129 or 1000)) or find_with_refs or known_group or components_mode or letterbox_kat or cropdetect_none or dct_threshold" \
       > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitizer_memcheck.log
 fi
+if [[ $STEP == sweep ]]; then
+  # BASELINE config 2: tolerance sweep of the 1 M all-pairs search (0.42 stresses the edge buffer)
+  for t in 0.0 0.1 0.2 0.3 0.4 0.42; do
+    timeout 300 python bench.py --steps 2 --warmup 1 --tol $t --no-secondary --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_tol_$t.json 2> gpurun_out/bench_tol_$t.err; echo "bench tol=$t rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_tol_$t.json'));print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['config']['edges'], d['config']['groups'], d['e2e']['ms_per_call'])"
+  done
+fi
 if [[ $STEP == big ]]; then
   # BASELINE configs[3] and [4] sizes on one GPU: 100k queries x 10M-entry table; all-pairs over a 10M-hash corpus
   timeout 900 python bench.py --workload refs --steps 3 --warmup 1 > gpurun_out/bench_refs_10m.json 2> gpurun_out/bench_refs_10m.err; echo "bench refs rc=$?"; tail -c 1200 gpurun_out/bench_refs_10m.json; tail -3 gpurun_out/bench_refs_10m.err

@@ -1103,6 +1103,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
         const uint32_t gi = I * kTile + row;
         const bool live = I < n_row_tiles;
         const int thr = live ? (int)p.row_pc[gi] - (int)p.tol : 0x7FFFFFFF;
+        const float thr_f = live ? (float)thr - 8388608.0f : 3.0e38f;  // 2 dot - pc(j) - 2^23 >= thr - 2^23, all exact in fp32
         for (uint32_t s = 0; s < n_st; ++s) {
             const uint32_t buf = s & 1;
             tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
@@ -1117,16 +1118,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
                 uint32_t best = 0;  // accumulators are non-negative floats: their bit patterns order like the values
 #pragma unroll
                 for (int k = 0; k < 64; k += 2) best = max(best, max(v[k], v[k + 1]));
-                if (2 * (int)__uint_as_float(best) - floor_pc >= thr) {  // rare: exact test of the 64 columns
+                if (2 * (int)__uint_as_float(best) - floor_pc >= thr) {
+                    // The bound above is loose (largest dot and smallest popcount of 64 columns rarely belong to the same
+                    // column): at tolerance 0.4 it lets most groups of random hashes through.  Second screen, exact and on
+                    // the FMA pipe only: the largest 2 dot - pc(j) of the group.  0x4B000000 | pc is the float 2^23 + pc, so
+                    // fma(dot, 2, -(2^23 + pc)) = 2 dot - pc - 2^23 exactly - no int<->float conversions (XU pipe, 16 per
+                    // clock: 64 of them per thread cost as much as the group's MMAs and made the 1 M launch 2.5x slower
+                    // at tolerance 0.4).
                     const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
-                    uint64_t mask = 0;
+                    float top = -3.0e38f;
 #pragma unroll
                     for (int k4 = 0; k4 < 16; ++k4) {
                         const uint4 pj = __ldg(pcj + k4);
-                        mask |= (uint64_t)(2 * (int)__uint_as_float(v[4 * k4 + 0]) - (int)pj.x >= thr) << (4 * k4 + 0);
-                        mask |= (uint64_t)(2 * (int)__uint_as_float(v[4 * k4 + 1]) - (int)pj.y >= thr) << (4 * k4 + 1);
-                        mask |= (uint64_t)(2 * (int)__uint_as_float(v[4 * k4 + 2]) - (int)pj.z >= thr) << (4 * k4 + 2);
-                        mask |= (uint64_t)(2 * (int)__uint_as_float(v[4 * k4 + 3]) - (int)pj.w >= thr) << (4 * k4 + 3);
+                        top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)));
+                        top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)));
+                        top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)));
+                        top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)));
+                    }
+                    uint64_t mask = 0;
+                    if (top >= thr_f) {  // a pair of this row with one of the 64 columns is within the tolerance
+#pragma unroll
+                        for (int k4 = 0; k4 < 16; ++k4) {
+                            const uint4 pj = __ldg(pcj + k4);
+                            mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)) >= thr_f) << (4 * k4 + 0);
+                            mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)) >= thr_f) << (4 * k4 + 1);
+                            mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)) >= thr_f) << (4 * k4 + 2);
+                            mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)) >= thr_f) << (4 * k4 + 3);
+                        }
                     }
                     while (mask) {
                         const int k = __ffsll((long long)mask) - 1;
