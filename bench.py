@@ -254,6 +254,28 @@ def run_reference(args):
         metric, unit, used = "hamming_pair_comparisons_per_s", "pairs/s", 1
         sample = f"{rows_per_step} random rows x {n} candidates per step (same table, tol {tol}), 1 thread"
         config = {"workload": f"all-pairs search, {n} synthetic hashes, equal durations, tolerance {args.tol}"}
+    elif args.workload == "refs":
+        # search_with_references: every query walks its whole duration slice of the sorted table (search_algorithm.rs:40-53)
+        nq, nc = args.n_query, args.n_corpus
+        n_tab = min(nc, 1_000_000)  # a bounded slice of the table: the cost per (query, entry) pair does not depend on its length
+        H, _ = synth.planted_hashes(n_tab)
+        dur = np.full(n_tab, 600, np.uint32)
+        Q = synth.random_hashes(max(8, int(2.0e9 // n_tab)), seed=synth.SEED + 1)
+        qd = np.full(len(Q), 600, np.uint32)
+        tol = o.tolerance_int(args.tol)
+
+        def step():
+            o.search_refs(H, dur, Q, qd, tol)
+            return len(Q) * n_tab
+
+        for _ in range(min(args.warmup, 1)):
+            step()
+        t0 = time.perf_counter()
+        units = sum(step() for _ in range(args.steps))
+        dt = time.perf_counter() - t0
+        metric, unit, used = "hamming_pair_comparisons_per_s", "pairs/s", 1
+        sample = f"{len(Q)} queries x {n_tab} table entries per step (tol {tol}), 1 thread"
+        config = {"workload": f"search_with_references, {nq} queries x {nc} sorted table entries, equal durations, tolerance {args.tol}"}
     else:
         from concurrent.futures import ThreadPoolExecutor
 
