@@ -172,6 +172,15 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.vdf_version()
 
 
+def test_integration_doc_binds_every_declared_symbol():
+    """INTEGRATION.md shows the reference-side (Rust) binding of every entry point the header declares"""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vdf_b200.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(vdf_[a-z_0-9]+)\s*\(", hdr))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    bound = set(re.findall(r"pub fn (vdf_[a-z_0-9]+)\s*\(", doc))
+    assert declared <= bound, sorted(declared - bound)
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
 
