@@ -25,7 +25,8 @@
  *     vdf_free_edges / vdf_free_groups / vdf_free_csr.
  *   - return value: VDF_OK (0) or a negative error; vdf_last_error(ctx) describes the last failure.
  *     Nothing unwinds or aborts across the boundary.
- *   - a context is bound to one GPU (one process per GPU), owns its stream and scratch buffers, and is
+ *   - a context is bound to one GPU (vdf_ctx_create; one process per GPU) or to several GPUs of one node
+ *     (vdf_ctx_create_multi; one process drives them all), owns its streams and scratch buffers, and is
  *     NOT thread-safe: one context per host thread, or an external lock
  *     (the reference calls VideoHashBuilder::hash from rayon workers,
  *     vid_dup_finder_app/src/video_hash_filesystem_cache/video_hash_filesystem_cache.rs:246).
@@ -62,6 +63,7 @@ extern "C" {
 #define VDF_CROPDETECT_LETTERBOX 1 /* Cropdetect::Letterbox (the library default, video_hash_builder.rs:55-63) */
 
 typedef struct vdf_ctx vdf_ctx;
+typedef struct vdf_table vdf_table; /* `Search` (search_algorithm.rs:5-23): a sorted table prepared for searching, resident in HBM */
 
 /* (i,j) match edges of search_self, i<j, sorted by (i,j): ij[2k], ij[2k+1] */
 typedef struct {
@@ -103,6 +105,14 @@ typedef struct {
 
 /* Binds a context to CUDA device `device_id` (one process per GPU). */
 int vdf_ctx_create(int device_id, vdf_ctx** out);
+/* One context over n_dev (1..8) distinct GPUs of one node, driven from this process: peer access is
+ * enabled between them and vdf_search, vdf_search_with_references and vdf_hash_stacks use all of them transparently -- the
+ * caller's table is staged and sorted once on dev_ids[0] and copied GPU -> GPU, every device evaluates its share of the
+ * pair matrix (one host thread per device for the duration of the call), matches travel through the fused peer-memory
+ * exchange, grouping runs on dev_ids[0]; stacks are hashed in contiguous shards.  Results are identical to a one-device
+ * context's.  All other entry points act on dev_ids[0].  vdf_ctx_set_option reaches every device. */
+int vdf_ctx_create_multi(const int* dev_ids, int n_dev, vdf_ctx** out);
+int vdf_ctx_device_count(const vdf_ctx* ctx);
 void vdf_ctx_destroy(vdf_ctx* ctx);
 const char* vdf_last_error(const vdf_ctx* ctx);
 
@@ -130,14 +140,19 @@ int vdf_peer_alloc(vdf_ctx* ctx, uint64_t capacity_keys, unsigned char handle_ou
 int vdf_peer_open(vdf_ctx* ctx, uint32_t rank, uint32_t world, const unsigned char* handles);
 int vdf_peer_close(vdf_ctx* ctx);
 
-/* Tuning knobs: "max_edges" (edge-buffer growth cap, default 2^28), "initial_edges" (default 2^22),
+/* Tuning knobs: "max_edges" (edge-buffer growth cap, default 2^28, at most 2^32 - 2), "initial_edges" (default 2^22),
  * "search_variant": 0 = XOR+POPC; 1, 2 = XOR + carry-save adders + POPC (8x8 / 8x4 pairs per thread);
- *   3 = tcgen05.mma kind::i8 on byte-expanded tiles; 4 = the same on CTA pairs (cta_group::2);
- *   5 = CTA pairs on packed tiles, bits expanded to bytes inside the kernel; 6 (default) = the same with the bits
- *   expanded to e2m1 nibbles and tcgen05.mma kind::mxf4 (twice the kind::i8 rate).  All seven are bit-identical.
- * "tc_chunk": column super-tiles per work unit of variants 4-6 (0 = automatic); "tc_unit_order": variant-6 work-unit order
+ *   5 = tcgen05.mma kind::i8 on CTA pairs (cta_group::2), packed tiles, bits expanded to bytes inside the kernel;
+ *   6 (default) = the same with the bits expanded to e2m1 nibbles and tcgen05.mma kind::mxf4 (twice the kind::i8 rate).
+ *   All five are bit-identical.  (3 and 4 of round 1, byte-expanded tiles in HBM, were removed: strictly dominated.)
+ * "tc_chunk": column super-tiles per work unit of variants 5, 6 (0 = automatic); "tc_unit_order": variant-6 work-unit order
  * (0 chunk-major, 1 row-pair-major); "tc_a_tmem": variant 6 keeps three quarters of the row operand in tensor memory (1,
- * default) or all of it in shared memory (0); "hash_variant": resize kernel choice. */
+ * default) or all of it in shared memory (0); "tc_fold": -1 (default) variant 6 folds the column popcounts into the free K
+ * positions 1000..1023 whenever no hash of either operand sets those bits (every real VideoHash: dct_3d.rs:55-66), which
+ * makes its 64-column screen exact at any tolerance; 0 = always the popcount-screen epilogue;
+ * "peer_timeout_ms": how long the peer exchange waits for the slowest rank (0 = automatic, grows with the problem);
+ * "hash_variant": resize kernel choice; "hash_overlap": 1 (default) runs the letterbox scan of chunk k+1 beside the resize
+ * of chunk k on a second stream. */
 int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value);
 
 /* The cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the caller). */
@@ -195,8 +210,28 @@ int vdf_search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand_sorted, const ui
                            uint64_t n_cand, uint64_t cand_index_base, const uint64_t* d_refs,
                            const uint32_t* d_ref_dur, uint64_t n_ref, uint32_t tol_int, uint64_t* d_keys_out,
                            uint64_t capacity, uint64_t* n_out);
-int vdf_group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges,
+/* d_remap (optional, n x u32 in HBM): every index written to `out` is d_remap[sorted position] -- how vdf_search hands back
+ * the caller's indices without a host pass.  Groups by the context's "grouping" option (default: the reference's rule). */
+int vdf_group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, const uint32_t* d_remap,
                             vdf_groups* out);
+
+/* ---- prepared tables ----------------------------------------------------------------------------------------------
+ * `Search::from(hashes)` (search_algorithm.rs:188-198) builds the sorted table once; `search_self(tolerance)` and
+ * `search_with_references` (:81, :40) then run on it any number of times.  A vdf_table is that object with the table
+ * resident in HBM in the pair kernels' layout (packed tiles, popcounts, fold units) together with the duration windows and
+ * the work-unit list of the context's current shard: searching it launches the pair kernel, reads one match count and
+ * groups -- nothing is re-packed.  vdf_table_create takes host arrays in sorted order and owns its copy;
+ * vdf_table_create_device takes device arrays that must stay valid and unchanged while the table lives.  A table belongs
+ * to the context it was created with; destroy it before the context. */
+int vdf_table_create(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint32_t* dur_sorted, uint64_t n, vdf_table** out);
+int vdf_table_create_device(vdf_ctx* ctx, const uint64_t* d_hash_sorted, const uint32_t* d_dur_sorted, uint64_t n, vdf_table** out);
+void vdf_table_destroy(vdf_table* table);
+uint64_t vdf_table_len(const vdf_table* table);
+/* as vdf_search_self_device / vdf_search_self_groups / vdf_search_refs_device, on a prepared table */
+int vdf_table_search_self_device(vdf_table* table, uint32_t tol_int, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out);
+int vdf_table_search_self_groups(vdf_table* table, uint32_t tol_int, vdf_groups* out);
+int vdf_table_search_refs_device(vdf_table* cand_table, uint64_t cand_index_base, const uint64_t* d_refs, const uint32_t* d_ref_dur,
+                                 uint64_t n_ref, uint32_t tol_int, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out);
 
 /* Number of (i,j) pairs inside the duration windows, i.e. how many hamming_distance calls the reference's
  * search_self would make with nothing consumed (throughput accounting). */
@@ -208,7 +243,8 @@ int vdf_self_window_pairs(vdf_ctx* ctx, const uint32_t* dur_sorted, uint64_t n, 
  * what video_dup_finder.rs does around the comparison loops: the stable (duration, src_path) sort of Search::sort
  * (search_algorithm.rs:55-61; Rust Unix `Path` ordering = component-wise), tol_int = (tolerance * 1000.0) as u32
  * (search_algorithm.rs:82), the GPU search, and the mapping back, so every index that comes out refers to the
- * caller's arrays.  The sort and the staging copies are multi-threaded host code (csrc/host.cu). */
+ * caller's arrays.  Host threads only cut 20-byte sort keys and copy the hashes to pinned memory; the sort itself, the
+ * gather into sorted order and the mapping back run on the GPU (csrc/host.cu). */
 
 /* Replaces Search::sort (search_algorithm.rs:55-61): order_out[k] = index of the k-th entry in sorted order. */
 int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint64_t* path_off, uint64_t n,
@@ -237,8 +273,9 @@ int vdf_search_with_references(vdf_ctx* ctx, const uint64_t* ref_hashes, const u
                                const uint64_t* new_hashes, const uint32_t* new_durations, const char* new_path_blob,
                                const uint64_t* new_path_off, uint64_t n_new, double tolerance, vdf_csr* out);
 
-/* Wall-clock milliseconds of the phases of the last vdf_search / vdf_search_with_references call:
- * [0] host sort, [1] gather into pinned memory + H2D enqueue, [2] device work incl. result D2H, [3] index remap. */
+/* Wall-clock milliseconds of the phases of the last vdf_search / vdf_search_with_references / vdf_stage_sorted call:
+ * [0] sort keys cut on the host, [1] hashes to pinned memory + uploads + GPU sort, [2] device work incl. result D2H,
+ * [3] 0 (the index remap is part of the device work since round 2). */
 int vdf_ctx_last_phases(const vdf_ctx* ctx, double* ms4);
 
 /* ---- the application's hash cache file (host code, csrc/cache.cu) ----------------------------------------------

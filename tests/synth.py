@@ -35,10 +35,11 @@ def random_hashes(n: int, seed: int = SEED, start: int = 0) -> np.ndarray:
     return h
 
 
-def planted_hashes(n: int, seed: int = SEED, dup_frac_den: int = 10, max_flip: int = 300, chunk: int = 1 << 15):
+def planted_hashes(n: int, seed: int = SEED, dup_frac_den: int = 10, max_flip: int = 300, chunk: int = 1 << 15, pad_flips: bool = False):
     """[n,16] u64 where ~1/dup_frac_den of the entries are copies of the BASE hash of a random earlier entry
-    with each of the 1024 bits flipped with probability k/1024, k ~ U[0, max_flip].  -> (hashes, src) with
-    src[i] = i for base entries."""
+    with each of the 1000 hash bits flipped with probability k/1024, k ~ U[0, max_flip].  -> (hashes, src) with
+    src[i] = i for base entries.  Bits 1000..1023 stay zero, as in every real VideoHash (dct_3d.rs:55-66 writes 1000
+    bits); pad_flips=True flips them too (round 1's generator; the test helpers of video_hash.rs:265-280 make such hashes)."""
     h = random_hashes(n, seed)
     idx = np.arange(n, dtype=np.uint64)
     is_dup = (_stream(seed, idx, 100) % np.uint64(dup_frac_den) == 0) & (idx > 0)
@@ -52,6 +53,8 @@ def planted_hashes(n: int, seed: int = SEED, dup_frac_den: int = 10, max_flip: i
         rng = np.random.Generator(np.random.Philox(key=seed + 7, counter=[0, 0, 0, a]))
         u = rng.integers(0, 1024, (len(dd), 1024), dtype=np.int16)
         flip = np.packbits(u < k[:, None], axis=1, bitorder="little").view(np.uint64)
+        if not pad_flips:
+            flip[:, 15] &= np.uint64((1 << 40) - 1)
         h[dd] = base[src[dd].astype(np.int64)] ^ flip
     return h, src
 

@@ -2,12 +2,12 @@
 public API (vid_dup_finder_lib/src/lib.rs:132-140): VideoHash creation from decoded frame stacks, `search`,
 `search_with_references`, `MatchGroup`, the tolerance option.  All bulk compute runs in hand-written CUDA
 kernels through the C ABI in include/vdf_b200.h; there is no CPU fallback."""
-from ._ffi import Context, VdfError, default_context
+from ._ffi import Context, Table, VdfError, default_context
 from .crop import Crop
 from .definitions import (DEFAULT_SEARCH_TOLERANCE, DEFAULT_VID_HASH_DURATION, DEFAULT_VID_HASH_SKIP_FORWARD,
                           TOLERANCE_SCALING_FACTOR, Cropdetect)
 from .hash_cache import CacheMetadata, HashCache, load_hash_cache, save_hash_cache
-from .match_group import MatchGroup, TooFewEntries
+from .match_group import MatchGroup, MatchGroups, TooFewEntries
 from .pipeline import HashPipeline
 from .search import search, search_with_references
 from .video_hash import HashTable, VideoHash
@@ -17,5 +17,5 @@ __all__ = [
     "VideoHash", "VideoHashBuilder", "CreationOptions", "search", "search_with_references", "MatchGroup", "Error",
     "NotVideo", "VidProc", "NotEnoughFrames", "Cropdetect", "DEFAULT_SEARCH_TOLERANCE", "DEFAULT_VID_HASH_DURATION",
     "DEFAULT_VID_HASH_SKIP_FORWARD", "TOLERANCE_SCALING_FACTOR", "HashTable", "Crop", "Context", "VdfError",
-    "default_context", "TooFewEntries", "HashCache", "CacheMetadata", "load_hash_cache", "save_hash_cache", "HashPipeline",
+    "default_context", "TooFewEntries", "MatchGroups", "Table", "HashCache", "CacheMetadata", "load_hash_cache", "save_hash_cache", "HashPipeline",
 ]

@@ -30,6 +30,8 @@ EXPORTS = [
     "vdf_sort_order", "vdf_search", "vdf_search_with_references", "vdf_ctx_last_phases", "vdf_group_components",
     "vdf_group_components_device", "vdf_cache_load", "vdf_cache_save", "vdf_free_cache",
     "vdf_pipeline_create", "vdf_pipeline_push", "vdf_pipeline_flush", "vdf_pipeline_poll", "vdf_pipeline_error", "vdf_pipeline_destroy",
+    "vdf_ctx_create_multi", "vdf_ctx_device_count", "vdf_table_create", "vdf_table_create_device", "vdf_table_destroy", "vdf_table_len",
+    "vdf_table_search_self_device", "vdf_table_search_self_groups", "vdf_table_search_refs_device",
 ]
 
 
@@ -86,6 +88,17 @@ def lib() -> C.CDLL:
     vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
     L.vdf_version.restype = C.c_char_p
     L.vdf_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.vdf_ctx_create_multi.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
+    L.vdf_ctx_device_count.argtypes = [vp]
+    L.vdf_table_create.argtypes = [vp, vp, vp, u64, C.POINTER(vp)]
+    L.vdf_table_create_device.argtypes = [vp, vp, vp, u64, C.POINTER(vp)]
+    L.vdf_table_destroy.argtypes = [vp]
+    L.vdf_table_destroy.restype = None
+    L.vdf_table_len.argtypes = [vp]
+    L.vdf_table_len.restype = u64
+    L.vdf_table_search_self_device.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
+    L.vdf_table_search_self_groups.argtypes = [vp, u32, C.POINTER(Groups)]
+    L.vdf_table_search_refs_device.argtypes = [vp, u64, vp, vp, u64, u32, vp, u64, C.POINTER(u64)]
     L.vdf_ctx_destroy.argtypes = [vp]
     L.vdf_ctx_destroy.restype = None
     L.vdf_last_error.argtypes = [vp]
@@ -109,7 +122,7 @@ def lib() -> C.CDLL:
     L.vdf_search_refs.argtypes = [vp, vp, vp, u64, vp, vp, u64, u32, C.POINTER(Csr)]
     L.vdf_search_self_device.argtypes = [vp, vp, vp, u64, u32, vp, u64, C.POINTER(u64)]
     L.vdf_search_refs_device.argtypes = [vp, vp, vp, u64, u64, vp, vp, u64, u32, vp, u64, C.POINTER(u64)]
-    L.vdf_group_greedy_device.argtypes = [vp, u64, vp, u64, C.POINTER(Groups)]
+    L.vdf_group_greedy_device.argtypes = [vp, u64, vp, u64, vp, C.POINTER(Groups)]
     L.vdf_self_window_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.vdf_sort_order.argtypes = [vp, vp, vp, u64, vp]
     L.vdf_search.argtypes = [vp, vp, vp, vp, vp, u64, C.c_double, C.POINTER(Groups)]
@@ -165,15 +178,26 @@ def make_descs(n: int, width: int, height: int, n_frames: int = 16, pitch: Optio
 
 
 class Context:
-    """One GPU, one stream, not thread-safe (see include/vdf_b200.h)."""
+    """One GPU (device: int) or several GPUs of one node driven from this process (device: a list of ids,
+    vdf_ctx_create_multi); one stream per GPU, not thread-safe (see include/vdf_b200.h)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self._h = C.c_void_p()
-        rc = lib().vdf_ctx_create(int(device), C.byref(self._h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = lib().vdf_ctx_create_multi(ids, len(device), C.byref(self._h))
+            self.devices, device = [int(d) for d in device], int(device[0])
+        else:
+            rc = lib().vdf_ctx_create(int(device), C.byref(self._h))
+            self.devices = [int(device)]
         if rc != OK:
             raise VdfError(rc, "vdf_ctx_create failed (no sm_100 device?) - this library has no CPU fallback")
         self.device = device
         self.peer_capacity, self.peer_world = 0, 0  # edge exchange over peer memory (peer_alloc / peer_open)
+
+    @property
+    def device_count(self) -> int:
+        return int(lib().vdf_ctx_device_count(self._h))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -347,10 +371,24 @@ class Context:
         self._check(lib().vdf_peer_close(self._h))
         self.peer_capacity, self.peer_world = 0, 0
 
-    def group_greedy_device(self, n: int, d_keys_sorted: int, n_edges: int):
+    def group_greedy_device(self, n: int, d_keys_sorted: int, n_edges: int, d_remap: int = 0):
+        """d_remap: device pointer of n x u32, sorted position -> index to report (0: report sorted positions)"""
         g = Groups()
-        self._check(lib().vdf_group_greedy_device(self._h, int(n), d_keys_sorted, int(n_edges), C.byref(g)))
+        self._check(lib().vdf_group_greedy_device(self._h, int(n), d_keys_sorted, int(n_edges), C.c_void_p(d_remap or None), C.byref(g)))
         return self._groups(g)
+
+    # ---- prepared tables (`Search::from` once, `search_self` / `search_with_references` many times)
+    def table_create(self, hash_sorted, dur_sorted) -> "Table":
+        h = _hash_array(hash_sorted) if len(dur_sorted) else np.zeros((0, 16), np.uint64)
+        d = np.ascontiguousarray(dur_sorted, dtype=np.uint32)
+        t = C.c_void_p()
+        self._check(lib().vdf_table_create(self._h, _ptr(h), _ptr(d), len(d), C.byref(t)))
+        return Table(self, t)
+
+    def table_create_device(self, d_hash_sorted: int, d_dur_sorted: int, n: int, keepalive=None) -> "Table":
+        t = C.c_void_p()
+        self._check(lib().vdf_table_create_device(self._h, d_hash_sorted, d_dur_sorted, int(n), C.byref(t)))
+        return Table(self, t, keepalive)
 
     # ---- hashing path
     def hash_stacks(self, frames: np.ndarray, descs: np.ndarray, cropdetect: int = CROPDETECT_LETTERBOX):
@@ -386,6 +424,50 @@ class Context:
         out = np.zeros((len(small), 16), dtype=np.uint64)
         self._check(lib().vdf_hash_from_small(self._h, _ptr(small), len(small), _ptr(out)))
         return out
+
+
+class Table:
+    """vdf_table: the sorted table resident in HBM in the pair kernels' layout (include/vdf_b200.h, "prepared tables")."""
+
+    def __init__(self, ctx: Context, handle, keepalive=None):
+        self.ctx, self._t, self._keepalive = ctx, handle, keepalive
+
+    def close(self):
+        if getattr(self, "_t", None) and self._t.value and self.ctx._h.value:
+            lib().vdf_table_destroy(self._t)
+        self._t = C.c_void_p()
+        self._keepalive = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(lib().vdf_table_len(self._t))
+
+    def search_self_device(self, tol_int: int, d_keys_out: int, capacity: int) -> int:
+        cnt = C.c_uint64()
+        rc = lib().vdf_table_search_self_device(self._t, int(tol_int), d_keys_out, capacity, C.byref(cnt))
+        if rc == ERR_EDGE_OVERFLOW:
+            return -int(cnt.value)
+        self.ctx._check(rc)
+        return int(cnt.value)
+
+    def search_self_groups(self, tol_int: int):
+        g = Groups()
+        self.ctx._check(lib().vdf_table_search_self_groups(self._t, int(tol_int), C.byref(g)))
+        return self.ctx._groups(g)
+
+    def search_refs_device(self, cand_base: int, d_refs: int, d_ref_dur: int, n_ref: int, tol_int: int, d_keys_out: int, capacity: int) -> int:
+        cnt = C.c_uint64()
+        rc = lib().vdf_table_search_refs_device(self._t, int(cand_base), d_refs, d_ref_dur, int(n_ref), int(tol_int), d_keys_out, capacity,
+                                                C.byref(cnt))
+        if rc == ERR_EDGE_OVERFLOW:
+            return -int(cnt.value)
+        self.ctx._check(rc)
+        return int(cnt.value)
 
 
 _default_ctx: Optional[Context] = None

@@ -10,7 +10,7 @@ using namespace vdf;
 
 extern "C" {
 
-const char* vdf_version(void) { return "vdf_b200 0.1.0 (sm_100a)"; }
+const char* vdf_version(void) { return "vdf_b200 0.2.0 (sm_100a)"; }
 
 int vdf_ctx_create(int device_id, vdf_ctx** out) {
     if (!out) return VDF_ERR_INVALID;
@@ -47,23 +47,33 @@ int vdf_ctx_create(int device_id, vdf_ctx** out) {
     return VDF_OK;
 }
 
-static void peer_release(vdf_ctx* ctx);
 
 void vdf_ctx_destroy(vdf_ctx* ctx) {
     if (!ctx) return;
+    for (int r = 1; r < ctx->sub_count; ++r) {  // a multi-GPU context owns the contexts of its other devices
+        if (ctx->sub[r]) vdf_ctx_destroy(ctx->sub[r]);
+        ctx->sub[r] = nullptr;
+    }
+    ctx->sub_count = 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
-    DevBuf* bufs[] = {&ctx->unit_cnt, &ctx->unit_off, &ctx->unit_list_a, &ctx->unit_list_b, &ctx->pcmin_rows, &ctx->pcmin_cols, &ctx->row_tiles, &ctx->col_tiles, &ctx->row_lo,   &ctx->row_hi,  &ctx->row_id,  &ctx->tile_range,
-                      &ctx->raw_keys,  &ctx->sort_tmp,  &ctx->misc,     &ctx->keys_a,  &ctx->keys_b,  &ctx->in_hash,
+    DevBuf* bufs[] = {&ctx->raw_keys,  &ctx->sort_tmp,  &ctx->misc,     &ctx->keys_a,  &ctx->keys_b,  &ctx->in_hash,
                       &ctx->in_dur,    &ctx->in_hash2,  &ctx->in_dur2,  &ctx->ref_perm, &ctx->ref_key, &ctx->g_rk,
                       &ctx->g_rks,     &ctx->g_state,   &ctx->g_parent, &ctx->g_wl0,   &ctx->g_wla,   &ctx->g_wlb,
                       &ctx->g_mk,      &ctx->g_mks,     &ctx->g_flag,   &ctx->g_scan,  &ctx->g_gp,    &ctx->g_mem,
+                      &ctx->g_cnt,     &ctx->g_gstart,  &ctx->sk_a,     &ctx->sk_b,    &ctx->sk_c,    &ctx->sk_d,
+                      &ctx->sk_order,  &ctx->sk_rank,   &ctx->ref_rows.tiles, &ctx->ref_rows.pc, &ctx->ref_rows.pcmin,
                       &ctx->h_frames[0], &ctx->h_frames[1], &ctx->h_jobs, &ctx->h_sides, &ctx->h_crop, &ctx->h_small,
-                      &ctx->h_hash,    &ctx->h_desc,    &ctx->exp_rows, &ctx->exp_cols, &ctx->pc_rows, &ctx->pc_cols};
+                      &ctx->h_hash,    &ctx->h_desc};
+    ctx->tmp_self.release();
+    ctx->tmp_cand.release();
+    ctx->ref_plan.release();
     for (DevBuf* b : bufs) b->release();
     ctx->pin_a.release();
     ctx->pin_b.release();
+    ctx->pin_c.release();
+    ctx->h_misc.release();
     ctx->h_groups.release();
     peer_release(ctx);
     ctx->pin_frames[0].release();
@@ -100,9 +110,14 @@ int vdf_ctx_set_shard(vdf_ctx* ctx, uint32_t rank, uint32_t world) {
 int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return VDF_ERR_INVALID;
     const std::string k(key);
-    if (k == "max_edges" && value > 0) ctx->max_edges = (uint64_t)value;
+    for (int r = 1; r < ctx->sub_count; ++r)  // every device of a multi-GPU context runs with the same knobs
+        if (k != "exchange") VDF_TRY(vdf_ctx_set_option(ctx->sub[r], key, value));
+    // the grouping indexes edges with 32 bits (group.cu)
+    if (k == "max_edges" && value > 0) ctx->max_edges = std::min<uint64_t>((uint64_t)value, 0xFFFFFFFEull);
     else if (k == "initial_edges" && value > 0) ctx->initial_edges = (uint64_t)value;
-    else if (k == "search_variant" && (value >= 0 && value <= 6)) ctx->search_variant = (int)value;
+    else if (k == "search_variant" && ((value >= 0 && value <= 2) || value == 5 || value == 6)) ctx->search_variant = (int)value;
+    else if (k == "tc_fold" && (value == -1 || value == 0)) ctx->tc_fold = (int)value;
+    else if (k == "peer_timeout_ms" && value >= 0) ctx->peer_timeout_ms = (uint64_t)value;
     else if (k == "tc_chunk" && value >= 0 && value <= 65535) ctx->tc_chunk = (uint32_t)value;
     else if (k == "tc_unit_order" && (value == 0 || value == 1)) ctx->tc_unit_order = (uint32_t)value;
     else if (k == "tc_a_tmem" && (value == 0 || value == 1)) ctx->tc_a_tmem = (uint32_t)value;
@@ -118,14 +133,17 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
 }
 
 // ---- edge exchange over peer memory (common.cuh: PeerExchange) ----------------------------------------------------
-static void peer_release(vdf_ctx* ctx) {
+}  // extern "C"
+void vdf::peer_release(vdf_ctx* ctx) {
     PeerExchange& px = ctx->peer;
     for (uint32_t r = 0; r < px.world; ++r)
-        if (r != px.rank && px.mapped[r]) cudaIpcCloseMemHandle(px.mapped[r]);
+        if (px.ipc && r != px.rank && px.mapped[r]) cudaIpcCloseMemHandle(px.mapped[r]);
     if (px.local) cudaFree(px.local);
     px = PeerExchange();
     ctx->exchange = 0;
+    ctx->peer_dead = false;
 }
+extern "C" {
 
 int vdf_peer_alloc(vdf_ctx* ctx, uint64_t capacity_keys, unsigned char handle_out[64]) {
     if (!ctx || !handle_out || capacity_keys == 0) return VDF_ERR_INVALID;
@@ -174,7 +192,7 @@ int vdf_peer_open(vdf_ctx* ctx, uint32_t rank, uint32_t world, const unsigned ch
             return VDF_ERR_CUDA;
         }
     }
-    px.rank = rank, px.world = world, px.epoch = 0;
+    px.rank = rank, px.world = world, px.epoch = 0, px.ipc = true;
     return VDF_OK;
 }
 
@@ -314,10 +332,98 @@ int vdf_search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand_sorted, const ui
     return rc;
 }
 
-int vdf_group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, vdf_groups* out) {
+int vdf_group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, const uint32_t* d_remap,
+                            vdf_groups* out) {
     VDF_TRY(enter(ctx));
     if (!out) return VDF_ERR_INVALID;
-    return group_greedy_device(ctx, n, d_keys_sorted, n_edges, out);
+    return group_device(ctx, n, d_keys_sorted, n_edges, d_remap, out);
+}
+
+// ---- prepared tables: `Search::from(hashes)` once, `search_self(tolerance)` / `search_with_references` many times ----
+int vdf_table_create_device(vdf_ctx* ctx, const uint64_t* d_hash_sorted, const uint32_t* d_dur_sorted, uint64_t n, vdf_table** out) {
+    VDF_TRY(enter(ctx));
+    if (!out || (n && (!d_hash_sorted || !d_dur_sorted))) return VDF_ERR_INVALID;
+    *out = nullptr;
+    if (n >= 0xFFFFFF00ull) {
+        ctx->err = "n must be < 2^32";
+        return VDF_ERR_INVALID;
+    }
+    vdf_table* t = new (std::nothrow) vdf_table();
+    if (!t) return VDF_ERR_ALLOC;
+    t->ctx = ctx;
+    int rc = table_prepare(ctx, t->t, d_hash_sorted, nullptr, d_dur_sorted, n, true, true);
+    if (rc == VDF_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) ctx->err = "vdf_table_create: packing failed", rc = VDF_ERR_CUDA;
+    if (rc != VDF_OK) {
+        t->t.release();
+        delete t;
+        return rc;
+    }
+    *out = t;
+    return VDF_OK;
+}
+
+int vdf_table_create(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint32_t* dur_sorted, uint64_t n, vdf_table** out) {
+    VDF_TRY(enter(ctx));
+    if (!out || (n && (!hash_sorted || !dur_sorted))) return VDF_ERR_INVALID;
+    *out = nullptr;
+    vdf_table* t = new (std::nothrow) vdf_table();
+    if (!t) return VDF_ERR_ALLOC;
+    t->ctx = ctx;
+    int rc = upload(ctx, t->own_hash, hash_sorted, n * 128);
+    if (rc == VDF_OK) rc = upload(ctx, t->own_dur, dur_sorted, n * 4);
+    if (rc == VDF_OK) rc = table_prepare(ctx, t->t, t->own_hash.as<uint64_t>(), nullptr, t->own_dur.as<uint32_t>(), n, true, true);
+    if (rc == VDF_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) ctx->err = "vdf_table_create: upload failed", rc = VDF_ERR_CUDA;
+    if (rc != VDF_OK) {
+        t->t.release(), t->own_hash.release(), t->own_dur.release();
+        delete t;
+        return rc;
+    }
+    *out = t;
+    return VDF_OK;
+}
+
+void vdf_table_destroy(vdf_table* t) {
+    if (!t) return;
+    if (t->ctx) {
+        cudaSetDevice(t->ctx->device);
+        cudaStreamSynchronize(t->ctx->stream);
+    }
+    t->t.release();
+    t->own_hash.release();
+    t->own_dur.release();
+    delete t;
+}
+
+uint64_t vdf_table_len(const vdf_table* t) { return t ? t->t.n : 0; }
+
+int vdf_table_search_self_device(vdf_table* t, uint32_t tol_int, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+    if (!t) return VDF_ERR_INVALID;
+    VDF_TRY(enter(t->ctx));
+    if (!n_out || (capacity && !d_keys_out)) return VDF_ERR_INVALID;
+    int rc = table_search_self(t->ctx, t->t, tol_int, d_keys_out, capacity, n_out);
+    cudaStreamSynchronize(t->ctx->stream);  // d_keys_out is read by the caller's own stream next
+    return rc;
+}
+
+int vdf_table_search_self_groups(vdf_table* t, uint32_t tol_int, vdf_groups* out) {
+    if (!t) return VDF_ERR_INVALID;
+    vdf_ctx* ctx = t->ctx;
+    VDF_TRY(enter(ctx));
+    if (!out) return VDF_ERR_INVALID;
+    uint64_t ne = 0;
+    VDF_TRY(with_growing_keys(
+        ctx, [&](uint64_t* keys, uint64_t cap, uint64_t* cnt) { return table_search_self(ctx, t->t, tol_int, keys, cap, cnt); }, &ne));
+    return group_device(ctx, t->t.n, ctx->keys_a.as<uint64_t>(), ne, nullptr, out);
+}
+
+int vdf_table_search_refs_device(vdf_table* cand, uint64_t cand_index_base, const uint64_t* d_refs, const uint32_t* d_ref_dur, uint64_t n_ref,
+                                 uint32_t tol_int, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+    if (!cand) return VDF_ERR_INVALID;
+    VDF_TRY(enter(cand->ctx));
+    if (!n_out || (capacity && !d_keys_out) || (n_ref && (!d_refs || !d_ref_dur))) return VDF_ERR_INVALID;
+    int rc = table_search_refs(cand->ctx, cand->t, cand_index_base, d_refs, d_ref_dur, n_ref, tol_int, d_keys_out, capacity, n_out);
+    cudaStreamSynchronize(cand->ctx->stream);
+    return rc;
 }
 
 static int self_keys_from_host(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint32_t* dur_sorted, uint64_t n,
@@ -379,7 +485,7 @@ int vdf_group_greedy(vdf_ctx* ctx, uint64_t n, const vdf_edges* edges, vdf_group
     if (!std::is_sorted(keys.begin(), keys.end())) std::sort(keys.begin(), keys.end());
     VDF_TRY(upload(ctx, ctx->keys_b, keys.data(), ne * 8));
     VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return group_greedy_device(ctx, n, ctx->keys_b.as<uint64_t>(), ne, out);
+    return group_greedy_device(ctx, n, ctx->keys_b.as<uint64_t>(), ne, nullptr, out);
 }
 
 int vdf_search_self_groups(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint32_t* dur_sorted, uint64_t n,
@@ -388,7 +494,7 @@ int vdf_search_self_groups(vdf_ctx* ctx, const uint64_t* hash_sorted, const uint
     if (!out || (n && (!hash_sorted || !dur_sorted))) return VDF_ERR_INVALID;
     uint64_t ne = 0;
     if (n) VDF_TRY(self_keys_from_host(ctx, hash_sorted, dur_sorted, n, tol_int, &ne));
-    return group_device(ctx, n, ctx->keys_a.as<uint64_t>(), ne, out);
+    return group_device(ctx, n, ctx->keys_a.as<uint64_t>(), ne, nullptr, out);
 }
 
 static int edges_to_device(vdf_ctx* ctx, uint64_t n, const vdf_edges* edges, uint64_t* ne_out) {
@@ -414,13 +520,13 @@ int vdf_group_components(vdf_ctx* ctx, uint64_t n, const vdf_edges* edges, vdf_g
     if (!out || !edges || (edges->n && !edges->ij)) return VDF_ERR_INVALID;
     uint64_t ne = 0;
     VDF_TRY(edges_to_device(ctx, n, edges, &ne));
-    return group_components_device(ctx, n, ctx->keys_b.as<uint64_t>(), ne, out);
+    return group_components_device(ctx, n, ctx->keys_b.as<uint64_t>(), ne, nullptr, out);
 }
 
 int vdf_group_components_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64_t n_edges, vdf_groups* out) {
     VDF_TRY(enter(ctx));
     if (!out) return VDF_ERR_INVALID;
-    return group_components_device(ctx, n, d_keys, n_edges, out);
+    return group_components_device(ctx, n, d_keys, n_edges, nullptr, out);
 }
 
 int vdf_search_refs(vdf_ctx* ctx, const uint64_t* cand_sorted, const uint32_t* cand_dur_sorted, uint64_t n_cand,
@@ -504,6 +610,15 @@ int vdf_hash_stacks(vdf_ctx* ctx, const uint8_t* frames, const vdf_stack_desc* d
     VDF_TRY(enter(ctx));
     if (n && (!frames || !desc || !out_hash)) return VDF_ERR_INVALID;
     if (n == 0) return VDF_OK;
+    if (ctx->sub_count > 1) return mgpu_hash_stacks(ctx, frames, desc, n, cropdetect, out_hash, out_status, out_crop);
+    return hash_stacks_host(ctx, frames, desc, n, cropdetect, out_hash, out_status, out_crop);
+}
+
+}  // extern "C"
+
+int vdf::hash_stacks_host(vdf_ctx* ctx, const uint8_t* frames, const vdf_stack_desc* desc, uint32_t n, int cropdetect, uint64_t* out_hash,
+                          int32_t* out_status, uint32_t* out_crop) {
+    VDF_TRY(enter(ctx));
     const size_t kBatchBytes = (size_t)512 << 20;
     cudaPointerAttributes attr;
     bool src_pinned = false;
@@ -594,5 +709,3 @@ int vdf_hash_stacks(vdf_ctx* ctx, const uint8_t* frames, const vdf_stack_desc* d
     }
     return VDF_OK;
 }
-
-}  // extern "C"

@@ -885,11 +885,10 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     }
     const bool four_warps = ctx->hash_variant != 2;  // default: 4 warps, two CTAs per SM
     const size_t ring = four_warps ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
-    static size_t smem_set[3] = {0, 0, 0};
-    auto want_smem = [&](int slot, const void* fn, size_t bytes) -> int {
-        if (bytes > 48 * 1024 && bytes > smem_set[slot]) {
+    auto want_smem = [&](int slot, const void* fn, size_t bytes) -> int {  // per device, hence kept in the context
+        if (bytes > 48 * 1024 && bytes > ctx->hash_smem_set[slot]) {
             VDF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            smem_set[slot] = bytes;
+            ctx->hash_smem_set[slot] = bytes;
         }
         return VDF_OK;
     };

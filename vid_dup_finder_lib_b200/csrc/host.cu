@@ -3,8 +3,17 @@
 // (duration, src_path) sort of Search::sort (search_algorithm.rs:55-61, Rust `Path` ordering), the tolerance cast
 // (search_algorithm.rs:82) and the mapping of sorted positions back to the caller's entries -- written natively so that a
 // caller hands over its hashes in ITS order (struct-of-arrays, paths as one byte blob) and gets groups of ITS indices back.
-// Multi-threaded (std::thread): the sort is the only O(n log n) host step on the path and at 1 M entries it costs more
-// than the GPU's all-pairs comparison when done on one core.  No comparison work happens here: there is no CPU fallback.
+// The (duration, Path) sort is the only O(n log n) step around the comparison and at 1 M entries a host sort costs a third of
+// the GPU's all-pairs time, so vdf_search / vdf_search_with_references / vdf_stage_sorted sort ON THE GPU: host threads only
+// re-encode each path so that byte order equals Rust's component order and cut a 16-byte key after the bytes all paths share
+// (two streaming passes, no per-path allocation); the GPU radix-sorts (duration, key, index) while the host is still copying
+// the hashes into pinned memory; entries whose 20-byte keys tie (rare: paths that agree beyond their first 16 distinguishing
+// bytes) are put in order on the host inside their runs only.  The table is uploaded in the CALLER's order and gathered by
+// the sorted permutation when it is packed for the pair kernel, and group members are mapped back to the caller's indices
+// on the device.  vdf_sort_order (no context, no GPU) keeps the multi-threaded host merge sort.
+// No comparison work happens here: there is no CPU fallback.
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -222,12 +231,187 @@ int sort_order_impl(const uint32_t* dur, const char* paths, const uint64_t* off,
     return VDF_OK;
 }
 
-// (tolerance * 1000.0) as u32: truncating, saturating, NaN -> 0 (search_algorithm.rs:82)
-uint32_t tolerance_to_int(double tolerance) {
-    const double v = tolerance * 1000.0;
-    if (!(v == v) || v <= 0.0) return 0;
-    if (v >= 4294967295.0) return 4294967295u;
-    return (uint32_t)v;
+// encode_path, stopping once `cap` bytes are written: -> bytes written (<= cap)
+size_t encode_path_capped(const char* p, size_t len, uint8_t* out, size_t cap) {
+    size_t w = 0;
+    auto put = [&](uint8_t b) {
+        if (w < cap) out[w] = b;
+        ++w;
+    };
+    size_t i = 0;
+    const bool absolute = len > 0 && p[0] == '/';
+    if (absolute) put(1), put(0);
+    bool first_piece = true;
+    while (i <= len && w < cap) {
+        size_t j = i;
+        while (j < len && p[j] != '/') ++j;
+        const size_t l = j - i;
+        if (l == 0) {
+        } else if (l == 1 && p[i] == '.') {
+            if (first_piece && !absolute) put(2), put(0);
+        } else if (l == 2 && p[i] == '.' && p[i + 1] == '.') {
+            put(3), put(0);
+        } else {
+            put(4);
+            for (size_t k = i; k < j && w < cap; ++k) put((uint8_t)p[k]);
+            put(0);
+        }
+        first_piece = false;
+        i = j + 1;
+    }
+    return std::min(w, cap);
+}
+
+// (duration, 16 encoded bytes after the common prefix) per entry, struct-of-arrays in pinned memory:
+// pd[n] u32, p1[n] u64, p2[n] u64 (big-endian, zero padded).  Two streaming passes over the paths.
+void build_prefix_keys(const uint32_t* dur, const char* paths, const uint64_t* off, uint64_t n, uint32_t* pd, uint64_t* p1, uint64_t* p2,
+                       uint64_t* skip_out) {
+    const unsigned t = n_threads(n);
+    std::vector<uint8_t> e0(encode_path(paths + off[0], off[1] - off[0], nullptr));
+    encode_path(paths + off[0], off[1] - off[0], e0.data());
+    std::vector<uint64_t> lcp(t, e0.size());
+    parallel_for(n, t, [&](uint64_t b, uint64_t e, unsigned th) {
+        uint64_t m = e0.size();
+        std::vector<uint8_t> buf(e0.size() + 1);
+        for (uint64_t i = b; i < e && m; ++i) {
+            const size_t w = encode_path_capped(paths + off[i], off[i + 1] - off[i], buf.data(), m);
+            uint64_t k = 0;
+            while (k < w && buf[k] == e0[k]) ++k;
+            m = k;
+        }
+        lcp[th] = m;
+    });
+    uint64_t skip = e0.size();
+    for (unsigned k = 0; k < t; ++k) skip = std::min(skip, lcp[k]);
+    if (n == 1) skip = 0;
+    parallel_for(n, t, [&](uint64_t b, uint64_t e, unsigned) {
+        std::vector<uint8_t> buf(skip + kPrefixBytes);
+        for (uint64_t i = b; i < e; ++i) {
+            const size_t w = encode_path_capped(paths + off[i], off[i + 1] - off[i], buf.data(), skip + kPrefixBytes);
+            const uint64_t l = w > skip ? w - skip : 0;
+            const uint8_t* p = buf.data() + skip;
+            uint64_t a = 0, c = 0;
+            for (uint64_t k = 0; k < 8; ++k) a = (a << 8) | (k < l ? p[k] : 0);
+            for (uint64_t k = 8; k < 16; ++k) c = (c << 8) | (k < l ? p[k] : 0);
+            pd[i] = dur[i], p1[i] = a, p2[i] = c;
+        }
+    });
+    *skip_out = skip;
+}
+
+__global__ void iota_kernel(uint32_t* __restrict__ a, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (uint32_t)i;
+}
+template <typename T>
+__global__ void gather_kernel(const T* __restrict__ in, const uint32_t* __restrict__ idx, uint64_t n, T* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[idx[i]];
+}
+// adjacent entries of the sorted order whose whole 20-byte keys are equal: their order is not decided yet
+__global__ void tie_count_kernel(const uint32_t* __restrict__ ds, const uint64_t* __restrict__ p1, const uint64_t* __restrict__ p2,
+                                 const uint32_t* __restrict__ order, uint64_t n, unsigned long long* __restrict__ ties) {
+    uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (k == 0 || k >= n) return;
+    const uint32_t a = order[k - 1], b = order[k];
+    if (ds[k - 1] == ds[k] && p1[a] == p1[b] && p2[a] == p2[b]) atomicAdd(ties, 1ull);
+}
+__global__ void widen_kernel(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// Search::sort (search_algorithm.rs:55-61) on the GPU.  In: the pinned key arrays of build_prefix_keys.  Out, in HBM:
+// ctx->sk_order[k] = the caller's index of the k-th sorted entry, ctx->in_dur = the durations in sorted order.
+// Three stable LSD passes (key bytes 8-15, key bytes 0-7, duration) carry the permutation; equal keys keep index order.
+int gpu_sort(vdf_ctx* ctx, const uint32_t* dur, const char* paths, const uint64_t* off, uint64_t n, const uint32_t* pd, const uint64_t* p1,
+             const uint64_t* p2, uint64_t skip) {
+    cudaStream_t st = ctx->stream;
+    const unsigned B = 256, G = (unsigned)((n + B - 1) / B);
+    VDF_ALLOC(ctx, ctx->sk_a.ensure(n * 4));
+    VDF_ALLOC(ctx, ctx->sk_b.ensure(n * 8));
+    VDF_ALLOC(ctx, ctx->sk_c.ensure(n * 8));
+    VDF_ALLOC(ctx, ctx->sk_d.ensure(n * (8 + 8 + 4 + 4 + 4) + 64));
+    VDF_ALLOC(ctx, ctx->sk_order.ensure(n * 4));
+    VDF_ALLOC(ctx, ctx->in_dur.ensure(n * 4));
+    VDF_CUDA(ctx, cudaMemcpyAsync(ctx->sk_a.p, pd, n * 4, cudaMemcpyHostToDevice, st));
+    VDF_CUDA(ctx, cudaMemcpyAsync(ctx->sk_b.p, p1, n * 8, cudaMemcpyHostToDevice, st));
+    VDF_CUDA(ctx, cudaMemcpyAsync(ctx->sk_c.p, p2, n * 8, cudaMemcpyHostToDevice, st));
+    ctx->h2d += n * 20;
+    uint64_t* k0 = ctx->sk_d.as<uint64_t>();
+    uint64_t* k1 = k0 + n;
+    uint32_t* ia = reinterpret_cast<uint32_t*>(k1 + n);
+    uint32_t* ib = ia + n;
+    uint32_t* d0 = ib + n;
+    unsigned long long* ties = reinterpret_cast<unsigned long long*>(ctx->sk_d.as<uint8_t>() + ((n * 28 + 7) / 8) * 8);
+    const uint32_t* d_dur = ctx->sk_a.as<uint32_t>();
+    const uint64_t* d_p1 = ctx->sk_b.as<uint64_t>();
+    const uint64_t* d_p2 = ctx->sk_c.as<uint64_t>();
+    uint32_t* order = ctx->sk_order.as<uint32_t>();
+    uint32_t* ds = ctx->in_dur.as<uint32_t>();
+    size_t tmp = 0, tmp32 = 0;
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_p2, k1, ia, ib, (size_t)n, 0, 64, st));
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp32, d0, ds, ia, order, (size_t)n, 0, 32, st));
+    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(std::max(tmp, tmp32)));
+    VDF_CUDA(ctx, cudaMemsetAsync(ties, 0, 8, st));
+    iota_kernel<<<G, B, 0, st>>>(ia, n);
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp, d_p2, k1, ia, ib, (size_t)n, 0, 64, st));
+    gather_kernel<uint64_t><<<G, B, 0, st>>>(d_p1, ib, n, k0);
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp, k0, k1, ib, ia, (size_t)n, 0, 64, st));
+    gather_kernel<uint32_t><<<G, B, 0, st>>>(d_dur, ia, n, d0);
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp32, d0, ds, ia, order, (size_t)n, 0, 32, st));
+    tie_count_kernel<<<G, B, 0, st>>>(ds, d_p1, d_p2, order, n, ties);
+    ctx->launches += 4 + 3 * 4;
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        ctx->err = std::string("gpu_sort: ") + cudaGetErrorString(le);
+        return VDF_ERR_CUDA;
+    }
+    VDF_ALLOC(ctx, ctx->h_misc.ensure(256));
+    unsigned long long* h = ctx->h_misc.as<unsigned long long>();
+    VDF_CUDA(ctx, cudaMemcpyAsync(h + 16, ties, 8, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h[16] == 0) return VDF_OK;
+    // Ties: bring the order back and finish the comparison inside every run of equal keys with the full encodings.  The GPU
+    // sort is stable, so a run lists its entries by ascending index, and a stable sort by the encoded bytes completes it.
+    std::vector<uint32_t> ord(n);
+    VDF_CUDA(ctx, cudaMemcpyAsync(ord.data(), order, n * 4, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->d2h += n * 4;
+    auto same = [&](uint32_t a, uint32_t b) { return pd[a] == pd[b] && p1[a] == p1[b] && p2[a] == p2[b]; };
+    parallel_for(n, n_threads(n), [&](uint64_t b, uint64_t e, unsigned) {
+        std::vector<std::pair<std::string, uint32_t>> run;
+        uint64_t k = b;
+        while (k < e) {
+            if (k > 0 && same(ord[k - 1], ord[k])) {  // inside a run that an earlier range owns
+                ++k;
+                continue;
+            }
+            uint64_t r = k + 1;
+            while (r < n && same(ord[k], ord[r])) ++r;
+            if (r - k > 1) {
+                run.clear();
+                for (uint64_t q = k; q < r; ++q) {
+                    const uint32_t i = ord[q];
+                    std::string enc(encode_path(paths + off[i], off[i + 1] - off[i], nullptr), '\0');
+                    encode_path(paths + off[i], off[i + 1] - off[i], reinterpret_cast<uint8_t*>(&enc[0]));
+                    run.emplace_back(std::move(enc), i);
+                }
+                std::stable_sort(run.begin(), run.end(), [](const std::pair<std::string, uint32_t>& x, const std::pair<std::string, uint32_t>& y) {
+                    const size_t m = std::min(x.first.size(), y.first.size());
+                    const int c = memcmp(x.first.data(), y.first.data(), m);
+                    return c ? c < 0 : x.first.size() < y.first.size();
+                });
+                for (uint64_t q = k; q < r; ++q) ord[q] = run[q - k].second;
+            }
+            k = r;
+        }
+    });
+    (void)dur, (void)skip;
+    VDF_CUDA(ctx, cudaMemcpyAsync(order, ord.data(), n * 4, cudaMemcpyHostToDevice, st));
+    VDF_CUDA(ctx, cudaStreamSynchronize(st));  // `ord` goes out of scope
+    ctx->h2d += n * 4;
+    return VDF_OK;
 }
 
 int enter(vdf_ctx* ctx) {
@@ -240,26 +424,56 @@ int enter(vdf_ctx* ctx) {
     return VDF_OK;
 }
 
-// hashes / durations in sorted order -> pinned staging -> HBM (async on the context's stream)
-int stage_sorted(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* dur, const std::vector<SortKey>& keys, DevBuf& d_hash,
-                 DevBuf& d_dur, vdf::PinnedBuf& pin_h, vdf::PinnedBuf& pin_d) {
-    const uint64_t n = keys.size();
+}  // namespace
+
+// The caller's table -> HBM, sorted on the way: keys are cut on the host and sorted on the GPU (gpu_sort) while host threads
+// copy the hashes, in the CALLER's order, through pinned memory (each thread enqueues the upload of its own slice, so the
+// DMA overlaps the copying).  Out: d_hash = the unsorted hashes, ctx->sk_order = the sorted permutation, ctx->in_dur = the
+// sorted durations.  t_keys / t_stage: host milliseconds of the two phases.
+int vdf::stage_and_sort(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* dur, const char* paths, const uint64_t* off, uint64_t n,
+                        DevBuf& d_hash, vdf::PinnedBuf& pin_h, double* t_keys, double* t_stage) {
+    const double t0 = now_ms();
+    VDF_ALLOC(ctx, ctx->pin_c.ensure(n * 20));
     VDF_ALLOC(ctx, pin_h.ensure(n * 128));
-    VDF_ALLOC(ctx, pin_d.ensure(n * 4));
     VDF_ALLOC(ctx, d_hash.ensure(n * 128));
-    VDF_ALLOC(ctx, d_dur.ensure(n * 4));
-    uint64_t* ph = pin_h.as<uint64_t>();
-    uint32_t* pd = pin_d.as<uint32_t>();
-    parallel_for(n, n_threads(n), [&](uint64_t b, uint64_t e, unsigned) {
-        for (uint64_t k = b; k < e; ++k) {
-            memcpy(ph + k * 16, hashes + (uint64_t)keys[k].idx * 16, 128);
-            pd[k] = keys[k].dur;
-        }
+    uint64_t* p1 = ctx->pin_c.as<uint64_t>();
+    uint64_t* p2 = p1 + n;
+    uint32_t* pd = reinterpret_cast<uint32_t*>(p2 + n);
+    uint64_t skip = 0;
+    build_prefix_keys(dur, paths, off, n, pd, p1, p2, &skip);
+    const double t1 = now_ms();
+    // the hash upload goes first on the stream: its DMA runs while the sort kernels wait for it, and the host is free to
+    // enqueue them (enqueue order == execution order on one stream; the sort does not read the hashes)
+    uint8_t* ph = pin_h.as<uint8_t>();
+    uint8_t* dh = d_hash.as<uint8_t>();
+    const unsigned t = std::max(1u, std::min(n_threads(n), 8u));
+    std::vector<int> rcs(t, 0);
+    parallel_for(n, t, [&](uint64_t b, uint64_t e, unsigned th) {
+        if (e <= b) return;
+        cudaSetDevice(ctx->device);
+        memcpy(ph + b * 128, reinterpret_cast<const uint8_t*>(hashes) + b * 128, (e - b) * 128);
+        if (cudaMemcpyAsync(dh + b * 128, ph + b * 128, (e - b) * 128, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rcs[th] = 1;
     });
-    VDF_CUDA(ctx, cudaMemcpyAsync(d_hash.p, ph, n * 128, cudaMemcpyHostToDevice, ctx->stream));
-    VDF_CUDA(ctx, cudaMemcpyAsync(d_dur.p, pd, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->h2d += n * 132;
+    for (int r : rcs)
+        if (r) {
+            ctx->err = "upload of the hash table failed";
+            cudaGetLastError();
+            return VDF_ERR_CUDA;
+        }
+    ctx->h2d += n * 128;
+    VDF_TRY(gpu_sort(ctx, dur, paths, off, n, pd, p1, p2, skip));
+    const double t2 = now_ms();
+    if (t_keys) *t_keys = t1 - t0;
+    if (t_stage) *t_stage = t2 - t1;
     return VDF_OK;
+}
+
+namespace {
+// [n][16] u64 rows gathered by a permutation (128-byte rows, 16 bytes per thread)
+__global__ void gather_rows_kernel(const uint4* __restrict__ in, const uint32_t* __restrict__ perm, uint64_t n, uint4* __restrict__ out) {
+    const uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;  // 16-byte piece
+    if (q >= n * 8) return;
+    out[q] = in[(uint64_t)perm[q >> 3] * 8 + (q & 7)];
 }
 
 template <typename F>
@@ -285,6 +499,51 @@ int with_growing_keys(vdf_ctx* ctx, F&& run, uint64_t* n_out) {
 
 }  // namespace
 
+// (tolerance * 1000.0) as u32: truncating, saturating, NaN -> 0 (search_algorithm.rs:82)
+uint32_t vdf::tolerance_to_int(double tolerance) {
+    const double v = tolerance * 1000.0;
+    if (!(v == v) || v <= 0.0) return 0;
+    if (v >= 4294967295.0) return 4294967295u;
+    return (uint32_t)v;
+}
+
+namespace {
+// keys (ref << 32 | sorted candidate position), sorted -> CSR over the caller's candidate indices
+__global__ void ref_csr_kernel(const uint64_t* __restrict__ keys, uint64_t ne, const uint32_t* __restrict__ order, uint64_t n_ref,
+                               uint64_t* __restrict__ row_ptr, uint64_t* __restrict__ col_idx) {
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (k >= ne) return;
+    const uint64_t key = keys[k];
+    const uint32_t r = (uint32_t)(key >> 32);
+    col_idx[k] = order ? order[(uint32_t)key] : (uint32_t)key;
+    // row_ptr[q] = first key of a row >= q: rows (previous key's row, r] start here
+    const uint32_t prev = k ? (uint32_t)(keys[k - 1] >> 32) + 1 : 0;
+    for (uint64_t q = prev; q <= r; ++q) row_ptr[q] = k;
+    if (k + 1 == ne)
+        for (uint64_t q = (uint64_t)r + 1; q <= n_ref; ++q) row_ptr[q] = ne;
+}
+}  // namespace
+
+// out->row_ptr (calloc'ed, n_ref + 1) is filled, out->col_idx allocated: the CSR is built on the device (keys are sorted by
+// (ref, sorted candidate position)) with the candidates as the caller's indices
+int vdf::ref_keys_to_csr(vdf_ctx* ctx, const uint64_t* d_keys, uint64_t ne, const uint32_t* d_order, uint64_t n_ref, vdf_csr* out) {
+    out->col_idx = (uint64_t*)malloc((ne ? ne : 1) * 8);
+    if (!out->col_idx) return VDF_ERR_ALLOC;
+    if (!ne) return VDF_OK;
+    VDF_ALLOC(ctx, ctx->keys_b.ensure((n_ref + 1 + ne) * 8));
+    uint64_t* d_rp = ctx->keys_b.as<uint64_t>();
+    uint64_t* d_ci = d_rp + n_ref + 1;
+    ref_csr_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(d_keys, ne, d_order, n_ref, d_rp, d_ci);
+    VDF_LAUNCHED(ctx);
+    VDF_ALLOC(ctx, ctx->h_groups.ensure((n_ref + 1 + ne) * 8));
+    VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_groups.p, d_rp, (n_ref + 1 + ne) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out->row_ptr, ctx->h_groups.p, (n_ref + 1) * 8);
+    memcpy(out->col_idx, ctx->h_groups.as<uint64_t>() + n_ref + 1, ne * 8);
+    ctx->d2h += (n_ref + 1 + ne) * 8;
+    return VDF_OK;
+}
+
 extern "C" {
 
 int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint64_t* path_off, uint64_t n, uint64_t* order_out) {
@@ -307,24 +566,31 @@ int vdf_stage_sorted(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durat
         ctx->err = "n must be < 2^32";
         return VDF_ERR_INVALID;
     }
-    double t0 = now_ms();
-    std::vector<SortKey> keys;
-    VDF_TRY(sort_order_impl(durations, path_blob, path_off, n, keys));
-    double t1 = now_ms();
-    if (n) VDF_TRY(stage_sorted(ctx, hashes, durations, keys, ctx->in_hash, ctx->in_dur, ctx->pin_a, ctx->pin_b));
-    *d_hash_sorted = ctx->in_hash.as<uint64_t>();
-    *d_dur_sorted = ctx->in_dur.as<uint32_t>();
-    if (n && d_hash_dst) {  // the caller's buffers (e.g. tensors it will broadcast to the other ranks)
-        VDF_CUDA(ctx, cudaMemcpyAsync(d_hash_dst, ctx->in_hash.p, n * 128, cudaMemcpyDeviceToDevice, ctx->stream));
-        VDF_CUDA(ctx, cudaMemcpyAsync(d_dur_dst, ctx->in_dur.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        *d_hash_sorted = d_hash_dst;
-        *d_dur_sorted = d_dur_dst;
+    *d_hash_sorted = nullptr, *d_dur_sorted = nullptr;
+    ctx->phase_ms[0] = ctx->phase_ms[1] = ctx->phase_ms[2] = ctx->phase_ms[3] = 0;
+    if (n == 0) return VDF_OK;
+    double t_keys = 0, t_stage = 0;
+    VDF_TRY(vdf::stage_and_sort(ctx, hashes, durations, path_blob, path_off, n, ctx->in_hash2, ctx->pin_a, &t_keys, &t_stage));
+    const double t0 = now_ms();
+    uint64_t* dst_h = d_hash_dst;
+    if (!dst_h) {
+        VDF_ALLOC(ctx, ctx->in_hash.ensure(n * 128));
+        dst_h = ctx->in_hash.as<uint64_t>();
     }
-    parallel_for(n, n_threads(n), [&](uint64_t b, uint64_t e, unsigned) {
-        for (uint64_t k = b; k < e; ++k) order_out[k] = keys[k].idx;
-    });
-    double t2 = now_ms();
-    ctx->phase_ms[0] = t1 - t0, ctx->phase_ms[1] = t2 - t1, ctx->phase_ms[2] = 0, ctx->phase_ms[3] = 0;
+    gather_rows_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, ctx->stream>>>(ctx->in_hash2.as<uint4>(), ctx->sk_order.as<uint32_t>(), n,
+                                                                                reinterpret_cast<uint4*>(dst_h));
+    VDF_LAUNCHED(ctx);
+    if (d_dur_dst) VDF_CUDA(ctx, cudaMemcpyAsync(d_dur_dst, ctx->in_dur.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    *d_hash_sorted = dst_h;
+    *d_dur_sorted = d_dur_dst ? d_dur_dst : ctx->in_dur.as<uint32_t>();
+    // the permutation, widened on the device, straight into the caller's array
+    VDF_ALLOC(ctx, ctx->keys_b.ensure(n * 8));
+    widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->sk_order.as<uint32_t>(), n, ctx->keys_b.as<uint64_t>());
+    VDF_LAUNCHED(ctx);
+    VDF_CUDA(ctx, cudaMemcpyAsync(order_out, ctx->keys_b.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->d2h += n * 8;
+    ctx->phase_ms[0] = t_keys, ctx->phase_ms[1] = t_stage, ctx->phase_ms[2] = now_ms() - t0;
     return VDF_OK;
 }
 
@@ -336,31 +602,27 @@ int vdf_search(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, 
         ctx->err = "n must be < 2^32";
         return VDF_ERR_INVALID;
     }
-    double t0 = now_ms();
-    std::vector<SortKey> keys;
-    VDF_TRY(sort_order_impl(durations, path_blob, path_off, n, keys));
-    double t1 = now_ms();
+    if (ctx->sub_count > 1) return vdf::mgpu_search(ctx, hashes, durations, path_blob, path_off, n, tolerance, out);
+    double t_keys = 0, t_stage = 0;
     uint64_t ne = 0;
     if (n) {
-        VDF_TRY(stage_sorted(ctx, hashes, durations, keys, ctx->in_hash, ctx->in_dur, ctx->pin_a, ctx->pin_b));
-    }
-    double t2 = now_ms();
-    if (n) {
-        const uint32_t tol_int = tolerance_to_int(tolerance);
+        VDF_TRY(vdf::stage_and_sort(ctx, hashes, durations, path_blob, path_off, n, ctx->in_hash, ctx->pin_a, &t_keys, &t_stage));
+        const double t2 = now_ms();
+        const uint32_t tol_int = vdf::tolerance_to_int(tolerance);
+        // Search::from: the table, gathered into sorted order while it is packed
+        VDF_TRY(vdf::table_prepare(ctx, ctx->tmp_self, ctx->in_hash.as<uint64_t>(), ctx->sk_order.as<uint32_t>(), ctx->in_dur.as<uint32_t>(), n,
+                                   true, false));
         VDF_TRY(with_growing_keys(
-            ctx,
-            [&](uint64_t* k, uint64_t cap, uint64_t* cnt) {
-                return vdf::search_self_device(ctx, ctx->in_hash.as<uint64_t>(), ctx->in_dur.as<uint32_t>(), n, tol_int, k, cap, cnt);
-            },
-            &ne));
+            ctx, [&](uint64_t* k, uint64_t cap, uint64_t* cnt) { return vdf::table_search_self(ctx, ctx->tmp_self, tol_int, k, cap, cnt); }, &ne));
+        // sorted positions -> the caller's indices (what `entries[i].value.src_path()` resolves to in the reference): on the
+        // device, as the group CSR is written
+        VDF_TRY(vdf::group_device(ctx, n, ctx->keys_a.as<uint64_t>(), ne, ctx->sk_order.as<uint32_t>(), out));
+        ctx->phase_ms[2] = now_ms() - t2;
+    } else {
+        VDF_TRY(vdf::group_device(ctx, 0, nullptr, 0, nullptr, out));
+        ctx->phase_ms[2] = 0;
     }
-    VDF_TRY(vdf::group_device(ctx, n, ctx->keys_a.as<uint64_t>(), ne, out));
-    double t3 = now_ms();
-    // sorted positions -> the caller's indices (what `entries[i].value.src_path()` resolves to in the reference)
-    const uint64_t total = out->n_groups ? out->group_ptr[out->n_groups] : 0;
-    for (uint64_t k = 0; k < total; ++k) out->member_idx[k] = keys[out->member_idx[k]].idx;
-    double t4 = now_ms();
-    ctx->phase_ms[0] = t1 - t0, ctx->phase_ms[1] = t2 - t1, ctx->phase_ms[2] = t3 - t2, ctx->phase_ms[3] = t4 - t3;
+    ctx->phase_ms[0] = t_keys, ctx->phase_ms[1] = t_stage, ctx->phase_ms[3] = 0;
     return VDF_OK;
 }
 
@@ -374,50 +636,36 @@ int vdf_search_with_references(vdf_ctx* ctx, const uint64_t* ref_hashes, const u
         ctx->err = "indices must fit in 32 bits";
         return VDF_ERR_INVALID;
     }
+    if (ctx->sub_count > 1)
+        return vdf::mgpu_search_refs(ctx, ref_hashes, ref_durations, n_ref, cand_hashes, cand_durations, cand_path_blob, cand_path_off, n_cand,
+                                     tolerance, out);
     out->n_rows = n_ref;
     out->row_ptr = (uint64_t*)calloc(n_ref + 1, 8);
     out->col_idx = nullptr;
     if (!out->row_ptr) return VDF_ERR_ALLOC;
-    double t0 = now_ms();
-    std::vector<SortKey> keys;
-    VDF_TRY(sort_order_impl(cand_durations, cand_path_blob, cand_path_off, n_cand, keys));
-    double t1 = now_ms();
+    double t_keys = 0, t_stage = 0;
     uint64_t ne = 0;
-    double t2 = t1;
+    const double t2 = now_ms();
     if (n_cand && n_ref) {
-        VDF_TRY(stage_sorted(ctx, cand_hashes, cand_durations, keys, ctx->in_hash, ctx->in_dur, ctx->pin_a, ctx->pin_b));
+        VDF_TRY(vdf::stage_and_sort(ctx, cand_hashes, cand_durations, cand_path_blob, cand_path_off, n_cand, ctx->in_hash, ctx->pin_a, &t_keys, &t_stage));
         VDF_ALLOC(ctx, ctx->in_hash2.ensure(n_ref * 128));
         VDF_ALLOC(ctx, ctx->in_dur2.ensure(n_ref * 4));
         VDF_CUDA(ctx, cudaMemcpyAsync(ctx->in_hash2.p, ref_hashes, n_ref * 128, cudaMemcpyHostToDevice, ctx->stream));
         VDF_CUDA(ctx, cudaMemcpyAsync(ctx->in_dur2.p, ref_durations, n_ref * 4, cudaMemcpyHostToDevice, ctx->stream));
         ctx->h2d += n_ref * 132;
-        t2 = now_ms();
-        const uint32_t tol_int = tolerance_to_int(tolerance);
+        const uint32_t tol_int = vdf::tolerance_to_int(tolerance);
+        VDF_TRY(vdf::table_prepare(ctx, ctx->tmp_cand, ctx->in_hash.as<uint64_t>(), ctx->sk_order.as<uint32_t>(), ctx->in_dur.as<uint32_t>(),
+                                   n_cand, false, true));
         VDF_TRY(with_growing_keys(
             ctx,
             [&](uint64_t* k, uint64_t cap, uint64_t* cnt) {
-                return vdf::search_refs_device(ctx, ctx->in_hash.as<uint64_t>(), ctx->in_dur.as<uint32_t>(), n_cand, 0,
-                                               ctx->in_hash2.as<uint64_t>(), ctx->in_dur2.as<uint32_t>(), n_ref, tol_int, k, cap, cnt);
+                return vdf::table_search_refs(ctx, ctx->tmp_cand, 0, ctx->in_hash2.as<uint64_t>(), ctx->in_dur2.as<uint32_t>(), n_ref, tol_int, k, cap,
+                                              cnt);
             },
             &ne));
     }
-    out->col_idx = (uint64_t*)malloc((ne ? ne : 1) * 8);
-    if (!out->col_idx) return VDF_ERR_ALLOC;
-    double t3 = now_ms();
-    if (ne) {
-        VDF_CUDA(ctx, cudaMemcpyAsync(out->col_idx, ctx->keys_a.p, ne * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->d2h += ne * 8;
-        t3 = now_ms();
-        // keys are sorted by (ref, sorted candidate position): count per ref, map positions to the caller's indices
-        for (uint64_t k = 0; k < ne; ++k) {
-            out->row_ptr[(out->col_idx[k] >> 32) + 1]++;
-            out->col_idx[k] = keys[out->col_idx[k] & 0xFFFFFFFFull].idx;
-        }
-        for (uint64_t r = 0; r < n_ref; ++r) out->row_ptr[r + 1] += out->row_ptr[r];
-    }
-    double t4 = now_ms();
-    ctx->phase_ms[0] = t1 - t0, ctx->phase_ms[1] = t2 - t1, ctx->phase_ms[2] = t3 - t2, ctx->phase_ms[3] = t4 - t3;
+    VDF_TRY(vdf::ref_keys_to_csr(ctx, ctx->keys_a.as<uint64_t>(), ne, ctx->sk_order.as<uint32_t>(), n_ref, out));
+    ctx->phase_ms[0] = t_keys, ctx->phase_ms[1] = t_stage, ctx->phase_ms[2] = now_ms() - t2 - t_keys - t_stage, ctx->phase_ms[3] = 0;
     return VDF_OK;
 }
 

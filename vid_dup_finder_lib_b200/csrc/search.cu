@@ -522,36 +522,99 @@ int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n) {
     return VDF_OK;
 }
 
-static int set_ham_attrs(vdf_ctx* ctx) {
-    static bool done = false;
-    if (done) return VDF_OK;
+static int set_ham_attrs(vdf_ctx* ctx) {  // cudaFuncSetAttribute is per device: once per context
+    if (ctx->ham_attrs) return VDF_OK;
     VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHamSmem));
     VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHamSmem));
     VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tiles_csa4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHamSmem));
-    done = true;
+    ctx->ham_attrs = true;
     return VDF_OK;
 }
 
-// shared tail of both searches: tile ranges, the hot kernel, count read-back, key sort
-static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, const void* row_data, const void* col_data,
-                     const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* col_pcmin, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
-                     uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
-    const uint32_t* row_tiles = static_cast<const uint32_t*>(row_data);
-    const uint32_t* col_tiles = static_cast<const uint32_t*>(col_data);
-    VDF_TRY(set_ham_attrs(ctx));
-    VDF_ALLOC(ctx, ctx->tile_range.ensure((size_t)n_row_tiles * sizeof(uint2)));
+// one side of the pair matrix in the form the selected kernel reads (column role differs from row role for variant 6 only)
+static int pack_side(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, bool column_role, Packed& out,
+                     uint32_t* d_pads_or) {
+    const int v = ctx->search_variant;
+    if (v == 6) return tc6_pack(ctx, d_hash, perm, n, column_role, out, d_pads_or);
+    if (v == 5) return tc5_pack(ctx, d_hash, perm, n, out);
+    const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
+    VDF_ALLOC(ctx, out.tiles.ensure((size_t)T * kTileWords * 4));
+    retile_kernel<<<T, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), perm, n, out.tiles.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    out.n = n, out.variant = v, out.as_columns = false;
+    return VDF_OK;
+}
+
+// `Search::from(hashes)` (search_algorithm.rs:188-198): the sorted table in the kernels' layout.  Enqueue only.
+int table_prepare(vdf_ctx* ctx, Table& t, const uint64_t* d_hash, const uint32_t* d_perm, const uint32_t* d_dur_sorted, uint64_t n,
+                  bool for_self, bool for_cand) {
+    t.n = n, t.d_hash = d_hash, t.d_perm = d_perm, t.d_dur = d_dur_sorted;
+    t.self_plan.valid = false;
+    t.pads = 0, t.pads_known = false;
+    t.rows.variant = t.cols.variant = -1;
+    if (n == 0) return VDF_OK;
+    VDF_ALLOC(ctx, t.meta.ensure(64));
+    VDF_CUDA(ctx, cudaMemsetAsync(t.meta.p, 0, 64, ctx->stream));
+    const bool v6 = ctx->search_variant == 6;
+    if (for_self || !v6) VDF_TRY(pack_side(ctx, d_hash, d_perm, n, false, t.rows, t.meta.as<uint32_t>()));
+    if (v6 && (for_self || for_cand)) VDF_TRY(pack_side(ctx, d_hash, d_perm, n, true, t.cols, t.meta.as<uint32_t>()));
+    return VDF_OK;
+}
+
+static bool plan_matches(const vdf_ctx* ctx, const Plan& pl) {
+    return pl.valid && pl.variant == ctx->search_variant && pl.rank == ctx->rank && pl.world == ctx->world && pl.tc_chunk == ctx->tc_chunk &&
+           pl.unit_order == ctx->tc_unit_order && pl.tc_fold == ctx->tc_fold;
+}
+
+// windows are in pl.row_lo / row_hi: tile ranges, statistics, work units -- then ONE read-back of everything the host needs
+// to size the launch: max span, pairs in the windows, units, pad bits of the operands
+static int plan_finish(vdf_ctx* ctx, Plan& pl, uint32_t n_row_tiles, uint32_t n_col_tiles, Table* t_a, uint32_t extra_pads_slot) {
+    pl.n_row_tiles = n_row_tiles, pl.n_col_tiles = n_col_tiles;
+    pl.variant = ctx->search_variant, pl.rank = ctx->rank, pl.world = ctx->world, pl.tc_chunk = ctx->tc_chunk;
+    pl.unit_order = ctx->tc_unit_order, pl.tc_fold = ctx->tc_fold;
+    VDF_ALLOC(ctx, pl.tile_range.ensure((size_t)(n_row_tiles + 1) * sizeof(uint2)));
+    unsigned long long* stats = pl.stats.as<unsigned long long>();
+    tile_range_kernel<<<n_row_tiles, 128, 0, ctx->stream>>>(pl.row_lo.as<uint32_t>(), pl.row_hi.as<uint32_t>(), n_row_tiles,
+                                                             pl.tile_range.as<uint2>(), stats);
+    VDF_LAUNCHED(ctx);
+    if (pl.variant >= 5) VDF_TRY(tc_plan_units(ctx, pl));
+    VDF_ALLOC(ctx, ctx->h_misc.ensure(256));
+    unsigned long long* h = ctx->h_misc.as<unsigned long long>();
+    h[8] = 0;
+    VDF_CUDA(ctx, cudaMemcpyAsync(h, stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t_a && !t_a->pads_known) VDF_CUDA(ctx, cudaMemcpyAsync(h + 8, t_a->meta.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pl.max_span = (uint32_t)h[0], pl.pairs = h[1], pl.n_units = (uint32_t)h[2];
+    if (t_a && !t_a->pads_known) t_a->pads = (uint32_t)h[8], t_a->pads_known = true;
+    uint32_t pads = t_a ? t_a->pads : 0;
+    if (extra_pads_slot) pads |= (uint32_t)h[extra_pads_slot];
+    pl.fold = pl.variant == 6 && ctx->tc_fold != 0 && pads == 0;
+    if (pl.variant >= 5 && pl.n_units > 0x3FFFFFFFu) {
+        ctx->err = "too many work units for one launch";
+        return VDF_ERR_INVALID;
+    }
+    pl.valid = true;
+    return VDF_OK;
+}
+
+static int plan_alloc(vdf_ctx* ctx, Plan& pl, uint32_t rows_padded) {
+    VDF_ALLOC(ctx, pl.row_lo.ensure((size_t)rows_padded * 4));
+    VDF_ALLOC(ctx, pl.row_hi.ensure((size_t)rows_padded * 4));
+    VDF_ALLOC(ctx, pl.stats.ensure(64));
+    VDF_CUDA(ctx, cudaMemsetAsync(pl.stats.p, 0, 64, ctx->stream));
+    pl.valid = false;
+    return VDF_OK;
+}
+
+// launch the pair kernel of the plan, close the exchange if one is on, read the match count (the one host round trip of a
+// search on a prepared table), sort the keys
+static int run_plan(vdf_ctx* ctx, const Plan& pl, const Packed& rows, const Packed& cols, const uint32_t* row_id, uint64_t col_base,
+                    uint32_t tol, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+    *n_out = 0;
     VDF_ALLOC(ctx, ctx->misc.ensure(64));
     VDF_ALLOC(ctx, ctx->raw_keys.ensure((size_t)(capacity ? capacity : 1) * 8));
-    unsigned long long* misc = ctx->misc.as<unsigned long long>();
+    unsigned long long* misc = ctx->misc.as<unsigned long long>();  // [2] match counter, [3] time-out flag, [4..5] exchange totals
     VDF_CUDA(ctx, cudaMemsetAsync(misc, 0, 64, ctx->stream));
-    tile_range_kernel<<<n_row_tiles, 128, 0, ctx->stream>>>(ctx->row_lo.as<uint32_t>(), ctx->row_hi.as<uint32_t>(),
-                                                             n_row_tiles, ctx->tile_range.as<uint2>(), misc);
-    VDF_LAUNCHED(ctx);
-    unsigned long long h_misc[4] = {0, 0, 0, 0};
-    VDF_CUDA(ctx, cudaMemcpyAsync(h_misc, misc, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const uint32_t max_span = (uint32_t)h_misc[0];
-    *n_out = 0;
     PeerPtrs pp;
     pp.world = 0;
     if (ctx->exchange) {  // matches of ALL ranks arrive in this rank's peer buffer (common.cuh: PeerExchange)
@@ -563,88 +626,94 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, c
             ctx->err = "peer exchange: call vdf_peer_alloc / vdf_peer_open first";
             return VDF_ERR_INVALID;
         }
+        if (ctx->peer_dead) {
+            ctx->err = "peer exchange: an earlier exchange failed on this buffer; vdf_peer_close, then allocate and open again on every rank";
+            return VDF_ERR_INVALID;
+        }
         pp = ctx->peer.ptrs((uint32_t)(ctx->peer.epoch & 1));
     }
-    if (max_span == 0 && !pp.world) return VDF_OK;
-    if (max_span != 0) {
-
-    // chunk: enough column tiles per CTA to amortise the row-tile load, small enough to balance 148 SMs
-    uint32_t chunk = 32;
-    while (chunk > 4 && (uint64_t)n_row_tiles * ((max_span + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 8 * ctx->world)
-        chunk >>= 1;
-    HamParams p;
-    p.row_tiles = row_tiles;
-    p.col_tiles = col_tiles;
-    p.row_lo = ctx->row_lo.as<uint32_t>();
-    p.row_hi = ctx->row_hi.as<uint32_t>();
-    p.row_id = row_id;
-    p.tile_range = ctx->tile_range.as<uint2>();
-    p.keys = ctx->raw_keys.as<uint64_t>();
-    p.counter = misc + 2;
-    p.capacity = capacity;
-    p.col_base = col_base;
-    p.chunk = chunk;
-    p.tol = tol;
-    p.rank = ctx->rank;
-    p.world = ctx->world;
-    p.one = 1;
-    dim3 grid(n_row_tiles, (max_span + chunk - 1) / chunk);
-    while (grid.y > 65535) {  // only reachable beyond ~268M columns
-        chunk *= 2;
-        p.chunk = chunk;
-        grid.y = (max_span + chunk - 1) / chunk;
+    const bool any_work = pl.variant >= 5 ? pl.n_units != 0 : pl.max_span != 0;
+    if (!any_work && !pp.world) return VDF_OK;
+    // from here on a failure leaves the ranks' exchange counters out of step
+    struct DeadGuard {
+        vdf_ctx* c;
+        bool armed;
+        ~DeadGuard() {
+            if (armed) c->peer_dead = true;
+        }
+    } guard{ctx, pp.world != 0};
+    if (any_work) {
+        if (pl.variant >= 5) {
+            VDF_TRY(tc_launch(ctx, pl, rows, cols, row_id, col_base, tol, capacity, misc + 2));
+        } else {
+            VDF_TRY(set_ham_attrs(ctx));
+            // chunk: enough column tiles per CTA to amortise the row-tile load, small enough to balance 148 SMs
+            uint32_t chunk = 32;
+            while (chunk > 4 && (uint64_t)pl.n_row_tiles * ((pl.max_span + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 8 * pl.world) chunk >>= 1;
+            HamParams p;
+            p.row_tiles = rows.tiles.as<uint32_t>();
+            p.col_tiles = cols.tiles.as<uint32_t>();
+            p.row_lo = pl.row_lo.as<uint32_t>();
+            p.row_hi = pl.row_hi.as<uint32_t>();
+            p.row_id = row_id;
+            p.tile_range = pl.tile_range.as<uint2>();
+            p.keys = ctx->raw_keys.as<uint64_t>();
+            p.counter = misc + 2;
+            p.capacity = capacity;
+            p.col_base = col_base;
+            p.chunk = chunk;
+            p.tol = tol;
+            p.rank = pl.rank;
+            p.world = pl.world;
+            p.one = 1;
+            dim3 grid(pl.n_row_tiles, (pl.max_span + chunk - 1) / chunk);
+            while (grid.y > 65535) {  // only reachable beyond ~268M columns
+                chunk *= 2;
+                p.chunk = chunk;
+                grid.y = (pl.max_span + chunk - 1) / chunk;
+            }
+            kt_begin(ctx, 0);
+            if (pl.variant == 2) hamming_tiles_csa4_kernel<<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
+            else if (pl.variant == 1) hamming_tiles_kernel<1><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
+            else hamming_tiles_kernel<0><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
+            kt_end(ctx, 0);
+            VDF_LAUNCHED(ctx);
+        }
     }
-    if (ctx->search_variant >= 3) {  // tensor-core path: byte-expanded operands, tcgen05.mma kind::i8
-        VDF_TRY(tc_launch(ctx, n_row_tiles, n_col_tiles, max_span, static_cast<const uint8_t*>(row_data), static_cast<const uint8_t*>(col_data),
-                          row_pc, col_pc, col_pcmin, row_id, col_base, tol, capacity, misc + 2));
-    } else {
-    kt_begin(ctx, 0);
-    if (ctx->search_variant == 2)
-        hamming_tiles_csa4_kernel<<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
-    else if (ctx->search_variant == 1)
-        hamming_tiles_kernel<1><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
-    else
-        hamming_tiles_kernel<0><<<grid, kHamThreads, kHamSmem, ctx->stream>>>(p);
-    kt_end(ctx, 0);
-    VDF_LAUNCHED(ctx);
-    }
-    }  // max_span != 0
-    unsigned long long cnt = 0;
+    VDF_ALLOC(ctx, ctx->h_misc.ensure(256));
+    unsigned long long* h = ctx->h_misc.as<unsigned long long>();
     const uint64_t* raw = ctx->raw_keys.as<uint64_t>();
+    unsigned long long cnt = 0;
     if (pp.world) {
-        uint32_t* flag = reinterpret_cast<uint32_t*>(misc + 3);  // zeroed with misc above
         const unsigned long long target = (unsigned long long)pp.world * (ctx->peer.epoch / 2 + 1);
-        peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(pp, misc + 2, target, 20ull * 1000 * 1000 * 1000, flag);
+        // a dead peer must not hang the GPU; a slow one must not be mistaken for dead: the allowance grows with this rank's share
+        const unsigned long long timeout_ms = ctx->peer_timeout_ms ? ctx->peer_timeout_ms : 20000ull + (pl.pairs >> 26);
+        peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(pp, misc + 2, target, timeout_ms * 1000000ull, reinterpret_cast<uint32_t*>(misc + 3));
         VDF_LAUNCHED(ctx);
         ctx->peer.epoch += 1;
         const uint64_t raw_cap = capacity ? capacity : 1;
         peer_compact_kernel<<<64, 256, 0, ctx->stream>>>(pp, ctx->raw_keys.as<uint64_t>(), raw_cap, misc + 4);
         VDF_LAUNCHED(ctx);
-        unsigned long long h_out[2] = {0, 0};
-        uint32_t timed_out = 0;
-        VDF_CUDA(ctx, cudaMemcpyAsync(h_out, misc + 4, 16, cudaMemcpyDeviceToHost, ctx->stream));
-        VDF_CUDA(ctx, cudaMemcpyAsync(&timed_out, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VDF_CUDA(ctx, cudaMemcpyAsync(h, misc, 64, cudaMemcpyDeviceToHost, ctx->stream));
         VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (timed_out) {
-            ctx->err = "peer exchange: a rank did not finish its search within 20 s";
+        if ((uint32_t)h[3]) {
+            ctx->err = "peer exchange: a rank did not finish its search within " + std::to_string(timeout_ms) + " ms (option peer_timeout_ms)";
             return VDF_ERR_CUDA;
         }
-        cnt = h_out[0];
+        guard.armed = false;  // every rank passed the barrier: the counters agree again, whatever the counts say
+        cnt = h[4];
         *n_out = cnt;
-        if (h_out[1] > pp.seg_cap) {  // some rank found more than a segment holds: every rank sees this alike
-            *n_out = h_out[1] * pp.world;
-            ctx->err = "edge buffer overflow: " + std::to_string(h_out[1]) + " matches on one rank > segment capacity " + std::to_string(pp.seg_cap);
+        if (h[5] > pp.seg_cap) {  // some rank found more than a segment holds: every rank sees this alike
+            *n_out = h[5] * pp.world;
+            ctx->err = "edge buffer overflow: " + std::to_string(h[5]) + " matches on one rank > segment capacity " + std::to_string(pp.seg_cap);
             return VDF_ERR_EDGE_OVERFLOW;
         }
-        if (cnt > capacity) {
-            ctx->err = "edge buffer overflow: " + std::to_string(cnt) + " matches > capacity " + std::to_string(capacity);
-            return VDF_ERR_EDGE_OVERFLOW;
-        }
-        return sort_keys(ctx, raw, d_keys_out, cnt);
+    } else {
+        VDF_CUDA(ctx, cudaMemcpyAsync(h, misc, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cnt = h[2];
+        *n_out = cnt;
     }
-    VDF_CUDA(ctx, cudaMemcpyAsync(&cnt, misc + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *n_out = cnt;
     if (cnt > capacity) {
         ctx->err = "edge buffer overflow: " + std::to_string(cnt) + " matches > capacity " + std::to_string(capacity);
         return VDF_ERR_EDGE_OVERFLOW;
@@ -652,106 +721,105 @@ static int run_tiles(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, c
     return sort_keys(ctx, raw, d_keys_out, cnt);
 }
 
-int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_dur, uint64_t n, uint32_t tol,
-                       uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+// `Search::search_self` (search_algorithm.rs:81-171, comparison part) on a prepared table
+int table_search_self(vdf_ctx* ctx, Table& t, uint32_t tol, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
     *n_out = 0;
+    const uint64_t n = t.n;
     if (n == 0) return VDF_OK;  // search_algorithm.rs:88-90
     if (n >= 0xFFFFFF00ull) {
         ctx->err = "n must be < 2^32";
         return VDF_ERR_INVALID;
     }
-    const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
-    const uint32_t n_pad = T * kTile;
-    VDF_ALLOC(ctx, ctx->row_tiles.ensure((size_t)T * kTileWords * 4));
-    VDF_ALLOC(ctx, ctx->row_lo.ensure((size_t)n_pad * 4));
-    VDF_ALLOC(ctx, ctx->row_hi.ensure((size_t)n_pad * 4));
-    const bool tc = ctx->search_variant == 3 || ctx->search_variant == 4;  // byte-expanded operands in HBM
-    if (tc) {
-        VDF_TRY(tc_expand(ctx, d_hash, nullptr, n, ctx->exp_rows, ctx->pc_rows));
-    } else if (ctx->search_variant == 5) {
-        VDF_TRY(tc5_pack(ctx, d_hash, nullptr, n, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
-    } else if (ctx->search_variant == 6) {
-        VDF_TRY(tc6_pack(ctx, d_hash, nullptr, n, false, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
-        VDF_TRY(tc6_pack(ctx, d_hash, nullptr, n, true, ctx->col_tiles, ctx->pc_cols, ctx->pcmin_cols));
-    } else {
-        retile_kernel<<<T, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), nullptr, n,
-                                                  ctx->row_tiles.as<uint32_t>());
-        VDF_LAUNCHED(ctx);
+    const int v = ctx->search_variant;
+    if (t.rows.variant != v || (v == 6 && t.cols.variant != v)) {  // the kernel choice changed since the table was packed
+        VDF_TRY(table_prepare(ctx, t, t.d_hash, t.d_perm, t.d_dur, n, true, true));
     }
-    self_window_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(d_dur, (uint32_t)n, n_pad, ctx->row_lo.as<uint32_t>(),
-                                                                     ctx->row_hi.as<uint32_t>());
-    VDF_LAUNCHED(ctx);
-    const void* data = tc ? ctx->exp_rows.p : ctx->row_tiles.p;
-    if (ctx->search_variant == 6)
-        return run_tiles(ctx, T, T, data, ctx->col_tiles.p, ctx->pc_rows.as<uint32_t>(), ctx->pc_cols.as<uint32_t>(),
-                         ctx->pcmin_cols.as<uint32_t>(), nullptr, 0, tol, d_keys_out, capacity, n_out);
-    return run_tiles(ctx, T, T, data, data, ctx->pc_rows.as<uint32_t>(), ctx->pc_rows.as<uint32_t>(),
-                     ctx->pcmin_rows.as<uint32_t>(), nullptr, 0, tol,
-                     d_keys_out, capacity, n_out);
+    const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
+    Plan& pl = t.self_plan;
+    if (!plan_matches(ctx, pl)) {
+        const uint32_t n_pad = T * kTile;
+        VDF_TRY(plan_alloc(ctx, pl, n_pad));
+        self_window_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(t.d_dur, (uint32_t)n, n_pad, pl.row_lo.as<uint32_t>(), pl.row_hi.as<uint32_t>());
+        VDF_LAUNCHED(ctx);
+        VDF_TRY(plan_finish(ctx, pl, T, T, &t, 0));
+    }
+    return run_plan(ctx, pl, t.rows, v == 6 ? t.cols : t.rows, nullptr, 0, tol, d_keys_out, capacity, n_out);
+}
+
+int search_self_device(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* d_dur, uint64_t n, uint32_t tol,
+                       uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+    *n_out = 0;
+    if (n == 0) return VDF_OK;
+    if (n >= 0xFFFFFF00ull) {
+        ctx->err = "n must be < 2^32";
+        return VDF_ERR_INVALID;
+    }
+    VDF_TRY(table_prepare(ctx, ctx->tmp_self, d_hash, nullptr, d_dur, n, true, false));
+    return table_search_self(ctx, ctx->tmp_self, tol, d_keys_out, capacity, n_out);
+}
+
+// `Search::search_with_references` (search_algorithm.rs:40-53,63-77,173-185) on a prepared candidate table
+int table_search_refs(vdf_ctx* ctx, Table& cand, uint64_t cand_base, const uint64_t* d_refs, const uint32_t* d_ref_dur, uint64_t n_ref,
+                      uint32_t tol, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
+    *n_out = 0;
+    const uint64_t n_cand = cand.n;
+    const bool exchange = ctx->exchange != 0;
+    if ((n_cand == 0 || n_ref == 0) && !exchange) return VDF_OK;
+    if (n_cand >= 0xFFFFFF00ull || n_ref >= 0xFFFFFF00ull || cand_base + n_cand > 0xFFFFFFFFull) {
+        ctx->err = "indices must fit in 32 bits";
+        return VDF_ERR_INVALID;
+    }
+    const int v = ctx->search_variant;
+    Packed& cols = v == 6 ? cand.cols : cand.rows;
+    if (n_cand && cols.variant != v) VDF_TRY(table_prepare(ctx, cand, cand.d_hash, cand.d_perm, cand.d_dur, n_cand, false, true));
+    const uint32_t TC = (uint32_t)((n_cand + kTile - 1) / kTile);
+    const uint32_t TR = (uint32_t)((n_ref + kTile - 1) / kTile);
+    const uint32_t r_pad = TR * kTile;
+    Plan& pl = ctx->ref_plan;
+    VDF_TRY(plan_alloc(ctx, pl, r_pad ? r_pad : kTile));
+    pl.n_units = 0, pl.max_span = 0, pl.pairs = 0, pl.variant = v;
+    uint32_t* perm = nullptr;
+    if (n_cand && n_ref) {
+        VDF_ALLOC(ctx, ctx->ref_key.ensure((size_t)n_ref * 4 * 3));
+        VDF_ALLOC(ctx, ctx->ref_perm.ensure((size_t)r_pad * 4));
+        // order the references by duration so that the 128 rows of a tile have overlapping slices
+        uint32_t* key_in = ctx->ref_key.as<uint32_t>();
+        uint32_t* key_out = key_in + n_ref;
+        uint32_t* idx_in = key_out + n_ref;
+        perm = ctx->ref_perm.as<uint32_t>();
+        ref_sortkey_kernel<<<(uint32_t)((n_ref + 255) / 256), 256, 0, ctx->stream>>>(d_ref_dur, (uint32_t)n_ref, key_in, idx_in);
+        VDF_LAUNCHED(ctx);
+        size_t tmp = 0;
+        VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32, ctx->stream));
+        VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
+        VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32, ctx->stream));
+        ctx->launches += 3;
+        // pad bits of the references go to stats[3] (read back with the plan)
+        VDF_TRY(pack_side(ctx, d_refs, perm, n_ref, false, ctx->ref_rows, reinterpret_cast<uint32_t*>(pl.stats.as<unsigned long long>() + 3)));
+        ref_window_kernel<<<(r_pad + 255) / 256, 256, 0, ctx->stream>>>(cand.d_dur, (uint32_t)n_cand, d_ref_dur, perm, (uint32_t)n_ref, r_pad,
+                                                                        pl.row_lo.as<uint32_t>(), pl.row_hi.as<uint32_t>());
+        VDF_LAUNCHED(ctx);
+        // in multi-GPU use every rank holds a different candidate slice and evaluates ALL of its tiles
+        const uint32_t world = ctx->world, rank = ctx->rank;
+        ctx->world = 1, ctx->rank = 0;
+        const int rc = plan_finish(ctx, pl, TR, TC, &cand, 3);
+        ctx->world = world, ctx->rank = rank;
+        VDF_TRY(rc);
+    }
+    return run_plan(ctx, pl, ctx->ref_rows, cols, perm, cand_base, tol, d_keys_out, capacity, n_out);
 }
 
 int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_cand_dur, uint64_t n_cand,
                        uint64_t cand_base, const uint64_t* d_refs, const uint32_t* d_ref_dur, uint64_t n_ref,
                        uint32_t tol, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out) {
     *n_out = 0;
-    if (n_cand == 0 || n_ref == 0) return VDF_OK;
+    if ((n_cand == 0 || n_ref == 0) && !ctx->exchange) return VDF_OK;
     if (n_cand >= 0xFFFFFF00ull || n_ref >= 0xFFFFFF00ull || cand_base + n_cand > 0xFFFFFFFFull) {
         ctx->err = "indices must fit in 32 bits";
         return VDF_ERR_INVALID;
     }
-    const uint32_t TC = (uint32_t)((n_cand + kTile - 1) / kTile);
-    const uint32_t TR = (uint32_t)((n_ref + kTile - 1) / kTile);
-    const uint32_t r_pad = TR * kTile;
-    VDF_ALLOC(ctx, ctx->col_tiles.ensure((size_t)TC * kTileWords * 4));
-    VDF_ALLOC(ctx, ctx->row_tiles.ensure((size_t)TR * kTileWords * 4));
-    VDF_ALLOC(ctx, ctx->row_lo.ensure((size_t)r_pad * 4));
-    VDF_ALLOC(ctx, ctx->row_hi.ensure((size_t)r_pad * 4));
-    VDF_ALLOC(ctx, ctx->ref_key.ensure((size_t)n_ref * 4 * 3));
-    VDF_ALLOC(ctx, ctx->ref_perm.ensure((size_t)r_pad * 4));
-    // order the references by duration so that the 128 rows of a tile have overlapping slices
-    uint32_t* key_in = ctx->ref_key.as<uint32_t>();
-    uint32_t* key_out = key_in + n_ref;
-    uint32_t* idx_in = key_out + n_ref;
-    uint32_t* perm = ctx->ref_perm.as<uint32_t>();
-    ref_sortkey_kernel<<<(uint32_t)((n_ref + 255) / 256), 256, 0, ctx->stream>>>(d_ref_dur, (uint32_t)n_ref, key_in, idx_in);
-    VDF_LAUNCHED(ctx);
-    size_t tmp = 0;
-    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32, ctx->stream));
-    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
-    VDF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp, key_in, key_out, idx_in, perm, (size_t)n_ref, 0, 32,
-                                                  ctx->stream));
-    ctx->launches += 3;
-    const bool tc = ctx->search_variant == 3 || ctx->search_variant == 4;
-    if (tc) {
-        VDF_TRY(tc_expand(ctx, d_cand, nullptr, n_cand, ctx->exp_cols, ctx->pc_cols));
-        VDF_TRY(tc_expand(ctx, d_refs, perm, n_ref, ctx->exp_rows, ctx->pc_rows));
-    } else if (ctx->search_variant == 5) {
-        VDF_TRY(tc5_pack(ctx, d_cand, nullptr, n_cand, ctx->col_tiles, ctx->pc_cols, ctx->pcmin_cols));
-        VDF_TRY(tc5_pack(ctx, d_refs, perm, n_ref, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
-    } else if (ctx->search_variant == 6) {
-        VDF_TRY(tc6_pack(ctx, d_cand, nullptr, n_cand, true, ctx->col_tiles, ctx->pc_cols, ctx->pcmin_cols));
-        VDF_TRY(tc6_pack(ctx, d_refs, perm, n_ref, false, ctx->row_tiles, ctx->pc_rows, ctx->pcmin_rows));
-    } else {
-        retile_kernel<<<TC, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cand), nullptr, n_cand,
-                                                   ctx->col_tiles.as<uint32_t>());
-        VDF_LAUNCHED(ctx);
-        retile_kernel<<<TR, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_refs), perm, n_ref,
-                                                   ctx->row_tiles.as<uint32_t>());
-        VDF_LAUNCHED(ctx);
-    }
-    ref_window_kernel<<<(r_pad + 255) / 256, 256, 0, ctx->stream>>>(d_cand_dur, (uint32_t)n_cand, d_ref_dur, perm,
-                                                                    (uint32_t)n_ref, r_pad, ctx->row_lo.as<uint32_t>(),
-                                                                    ctx->row_hi.as<uint32_t>());
-    VDF_LAUNCHED(ctx);
-    // in multi-GPU use every rank holds a different candidate slice and evaluates ALL of its tiles
-    const uint32_t world = ctx->world, rank = ctx->rank;
-    ctx->world = 1, ctx->rank = 0;
-    int rc = run_tiles(ctx, TR, TC, tc ? ctx->exp_rows.p : ctx->row_tiles.p, tc ? ctx->exp_cols.p : ctx->col_tiles.p,
-                       ctx->pc_rows.as<uint32_t>(), ctx->pc_cols.as<uint32_t>(), ctx->pcmin_cols.as<uint32_t>(), perm, cand_base, tol,
-                       d_keys_out, capacity,
-                       n_out);
-    ctx->world = world, ctx->rank = rank;
-    return rc;
+    VDF_TRY(table_prepare(ctx, ctx->tmp_cand, d_cand, nullptr, d_cand_dur, n_cand, false, true));
+    return table_search_refs(ctx, ctx->tmp_cand, cand_base, d_refs, d_ref_dur, n_ref, tol, d_keys_out, capacity, n_out);
 }
 
 __global__ void window_pairs_kernel(const uint32_t* __restrict__ dur, uint32_t n, unsigned long long* out) {

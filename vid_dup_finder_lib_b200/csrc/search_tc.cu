@@ -1,23 +1,18 @@
-// search_tc.cu -- tensor-core Hamming search, search_variant 3.
+// search_tc.cu -- tensor-core Hamming search: search_variant 5 (kind::i8) and 6 (kind::mxf4).
 //
-// hamming(a, b) = pc(a) + pc(b) - 2 * <a, b> with the 1024 bits of a hash expanded to 1024 bytes in {0, 1}: the
-// all-pairs comparison becomes an exact u8 x u8 -> s32 contraction with K = 1024 that runs on the 5th-generation
-// tensor cores (tcgen05.mma kind::i8, SASS UTCIMMA), accumulators in tensor memory.  A pair matches iff
-//     2 * dot(i, j) - pc(j) >= pc(i) - tol.
-// Results are bit-identical to the XOR+POPC kernels (integers throughout); this kernel is selected with
-// search_variant = 3 and is validated against the same oracle tests.
+// hamming(a, b) = pc(a) + pc(b) - 2 * <a, b>: the all-pairs comparison is an exact contraction over the K = 1024 stored bits
+// of two hashes that runs on the 5th-generation tensor cores (tcgen05.mma, accumulators in tensor memory).  A pair matches
+// iff   2 * dot(i, j) - pc(j) >= pc(i) - tol.   Results are bit-identical to the XOR+POPC kernels of search.cu (integers
+// throughout) and are validated against the same oracle tests.
 //
-// Layout in HBM (expand_tiles_kernel): exp[tile][kc 0..7][row 0..127][128 B], i.e. per 128-hash tile eight K-chunks of
-// 128 bytes per row, each chunk block (16 KB) stored exactly as the UMMA K-major SWIZZLE_128B canonical layout wants it
-// in shared memory (16-byte unit u of row r lives at unit u ^ (r & 7)), so plain 1-D TMA bulk copies stage operands.
-//
-// CTA = 6 warps, one per SM (192 KB of shared memory): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane,
-// owns the TMEM allocation), warps 2-5 = epilogue (tcgen05.ld, one accumulator row per thread).  The row tile (A, 128
-// hashes x 1024 B = 128 KB) stays resident; column super-tiles (B, 256 hashes) stream through a 2-stage ring of
-// 32 KB K-chunks; each super-tile is 8 chunks x 4 MMAs of 128x256x32; two 256-column TMEM accumulators let the
-// epilogue of super-tile t overlap the MMAs of t+1.
+// HBM holds only PACKED tiles (bits); they are expanded to tensor-core operands inside the kernels.  Work unit = a CTA pair
+// (cluster of 2, tcgen05.mma.cta_group::2, M = 256) x a chunk of column super-tiles.  Round 1 also carried variants 3 and 4
+// (byte-expanded tiles in HBM, one CTA / CTA pairs): they needed 1 GB per million hashes, were bound by L2 -> SM bandwidth and
+// were strictly dominated by 5 and 6; they were removed in round 2 (the measurements stay in profiles/r01_*).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+
+#include <cstring>
 
 #include "common.cuh"
 
@@ -25,10 +20,6 @@ namespace vdf {
 
 constexpr int kTcChunkBytes = kTile * 128;        // one K-chunk of one tile: 16 KB
 constexpr int kTcTileBytes = 8 * kTcChunkBytes;   // expanded tile: 128 KB
-constexpr int kTcStages = 2;
-constexpr int kTcStageBytes = 2 * kTcChunkBytes;  // 256 columns x 128 B
-constexpr int kTcThreads = 192;
-constexpr size_t kTcSmem = (size_t)kTcTileBytes + kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
@@ -62,20 +53,6 @@ __device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t
 __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = unsigned 8 bit (0), both K-major,
-// N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
-constexpr uint32_t kTcIdesc = (2u << 4) | (32u << 17) | (8u << 24);
-
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(kTcIdesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar))
-                 : "memory");
-}
 // one lane of a converged warp (the same lane every time): the canonical predicate for issuing tcgen05.mma / commit.
 // Keeping the MMA warp converged and electing here lets ptxas keep barrier addresses and descriptors in uniform
 // registers; a `lane == 0` branch around the loop costs a vote loop (ELECT / BRA.U.ANY) per UTCIMMA instead.
@@ -101,41 +78,6 @@ __device__ __forceinline__ void tc_ld64(uint32_t taddr, uint32_t (&v)[64]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ------------------------------------------------------------------------------------------------ expansion
-// bits -> {0,1} bytes in the swizzled K-major tile layout, plus per-hash popcounts.  grid = (tiles, 8 K-chunks).
-__global__ void __launch_bounds__(256) expand_tiles_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm,
-                                                           uint64_t n, uint8_t* __restrict__ exp, uint32_t* __restrict__ pc) {
-    const uint64_t tile = blockIdx.x;
-    const uint32_t kc = blockIdx.y;  // bits kc*128 .. kc*128+127 = u32 words kc*4 .. kc*4+3
-    uint8_t* dst = exp + tile * (uint64_t)kTcTileBytes + (uint64_t)kc * kTcChunkBytes;
-    for (uint32_t q = threadIdx.x; q < kTile * 8; q += 256) {
-        const uint32_t row = q >> 3, unit = q & 7;  // 16-byte unit = 16 bits of the hash
-        const uint64_t g = tile * kTile + row;
-        uint32_t bits = 0;
-        if (g < n) {
-            const uint64_t src = perm ? perm[g] : g;
-            bits = (in[src * 32 + kc * 4 + (unit >> 1)] >> ((unit & 1) * 16)) & 0xFFFFu;
-        }
-        uint4 v;  // nibble * 0x00204081 spreads bit i of the nibble to bit 0 of byte i
-        v.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
-        v.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-        v.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-        v.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-        *reinterpret_cast<uint4*>(dst + row * 128 + ((unit ^ (row & 7)) << 4)) = v;
-    }
-    if (kc == 0) {
-        for (uint32_t row = threadIdx.x; row < (uint32_t)kTile; row += 256) {
-            const uint64_t g = tile * kTile + row;
-            uint32_t c = 0;
-            if (g < n) {
-                const uint64_t src = perm ? perm[g] : g;
-                for (int w = 0; w < 32; ++w) c += __popc(in[src * 32 + w]);
-            }
-            pc[g] = c;
-        }
-    }
-}
-
 struct TcParams {
     const uint8_t* row_exp;
     const uint8_t* col_exp;
@@ -159,159 +101,18 @@ struct TcParams {
     PeerPtrs peers;             // variant 6: peers.world > 0 => matches go to every rank's exchange buffer (common.cuh)
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1) hamming_tc_kernel(const TcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B operands need 1024-byte aligned tiles
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = base;
-    uint8_t* sB = base + kTcTileBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * kTcStageBytes);
-    uint64_t* full = bars;                    // [kTcStages]
-    uint64_t* empty = bars + kTcStages;       // [kTcStages]
-    uint64_t* a_full = bars + 2 * kTcStages;  // [1]
-    uint64_t* acc_full = a_full + 1;          // [2]
-    uint64_t* acc_empty = acc_full + 2;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const uint32_t I = blockIdx.x, c = blockIdx.y;
-    if (p.world > 1 && ((I + c) % p.world) != p.rank) return;
-    const uint2 rng = p.tile_range[I];
-    const uint32_t st_begin = rng.x / 2, st_end = (rng.y + 1) / 2;  // super-tiles covering the 128-tile range
-    const uint32_t st0 = st_begin + c * p.chunk;
-    if (rng.x >= rng.y || st0 >= st_end) return;
-    const uint32_t n_st = min(p.chunk, st_end - st0);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) tc_mbar_init(&full[s], 1), tc_mbar_init(&empty[s], 1);
-        tc_mbar_init(a_full, 1);
-        for (int b = 0; b < 2; ++b) tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 4);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {  // the MMA warp owns all 512 TMEM columns (one CTA per SM)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer
-            tc_mbar_expect_tx(a_full, kTcTileBytes);
-            for (int kc = 0; kc < 8; ++kc)
-                tc_bulk_g2s(sA + kc * kTcChunkBytes, p.row_exp + (size_t)I * kTcTileBytes + (size_t)kc * kTcChunkBytes,
-                            kTcChunkBytes, a_full);
-            uint32_t it = 0;
-            for (uint32_t s = 0; s < n_st; ++s) {
-                const uint8_t* t0 = p.col_exp + (size_t)(2 * (st0 + s)) * kTcTileBytes;
-                for (int kc = 0; kc < 8; ++kc, ++it) {
-                    const uint32_t stage = it % kTcStages;
-                    tc_mbar_wait(&empty[stage], ((it / kTcStages) & 1) ^ 1);
-                    tc_mbar_expect_tx(&full[stage], kTcStageBytes);
-                    uint8_t* d = sB + stage * kTcStageBytes;
-                    tc_bulk_g2s(d, t0 + (size_t)kc * kTcChunkBytes, kTcChunkBytes, &full[stage]);
-                    tc_bulk_g2s(d + kTcChunkBytes, t0 + kTcTileBytes + (size_t)kc * kTcChunkBytes, kTcChunkBytes, &full[stage]);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer
-            tc_mbar_wait(a_full, 0);
-            const uint32_t a_addr = tc_smem_u32(sA), b_addr = tc_smem_u32(sB);
-            uint32_t it = 0;
-            for (uint32_t s = 0; s < n_st; ++s) {
-                const uint32_t buf = s & 1;
-                tc_mbar_wait(&acc_empty[buf], ((s >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * 256;
-                for (int kc = 0; kc < 8; ++kc, ++it) {
-                    const uint32_t stage = it % kTcStages;
-                    tc_mbar_wait(&full[stage], (it / kTcStages) & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        tc_mma(d_tmem, tc_desc(a_addr + kc * kTcChunkBytes + ks * 32),
-                               tc_desc(b_addr + stage * kTcStageBytes + ks * 32), (kc | ks) != 0);
-                    tc_commit(&empty[stage]);  // the stage is free once these MMAs have read it
-                }
-                tc_commit(&acc_full[buf]);
-            }
-        }
-    } else {  // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31, one accumulator row per thread
-        const uint32_t quarter = warp & 3;
-        const uint32_t row = quarter * 32 + lane;
-        const uint32_t gi = I * kTile + row;
-        const int thr = (int)p.row_pc[gi] - (int)p.tol;
-        for (uint32_t s = 0; s < n_st; ++s) {
-            const uint32_t buf = s & 1;
-            tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
-            tc_fence_after();
-            const uint32_t col_first = (st0 + s) * 256;
-            for (int q = 0; q < 4; ++q) {
-                uint32_t v[64];
-                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the rare emit path
-                tc_ld64(tmem_base + buf * 256 + q * 64 + ((quarter * 32) << 16), v);
-                const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
-                int best = -0x7FFFFFFF;
-#pragma unroll
-                for (int k4 = 0; k4 < 16; ++k4) {
-                    const uint4 pj = __ldg(pcj + k4);
-                    const int t0 = 2 * (int)v[4 * k4 + 0] - (int)pj.x, t1 = 2 * (int)v[4 * k4 + 1] - (int)pj.y;
-                    const int t2 = 2 * (int)v[4 * k4 + 2] - (int)pj.z, t3 = 2 * (int)v[4 * k4 + 3] - (int)pj.w;
-                    v[4 * k4 + 0] = (uint32_t)t0, v[4 * k4 + 1] = (uint32_t)t1;
-                    v[4 * k4 + 2] = (uint32_t)t2, v[4 * k4 + 3] = (uint32_t)t3;
-                    best = max(best, max(max(t0, t1), max(t2, t3)));
-                }
-                if (best >= thr) {  // rare: at least one of these 64 pairs is within the tolerance
-                    uint64_t mask = 0;
-#pragma unroll
-                    for (int k = 0; k < 64; ++k) mask |= (uint64_t)((int)v[k] >= thr) << k;
-                    while (mask) {
-                        const int k = __ffsll((long long)mask) - 1;
-                        mask &= mask - 1;
-                        const uint32_t gj = col_first + q * 64 + k;
-                        if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
-                            const unsigned long long slot = atomicAdd(p.counter, 1ull);
-                            if (slot < p.capacity) {
-                                const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
-                                p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
-                            }
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ CTA-pair kernel
-// search_variant 4: the same contraction on a CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256).  The pair
-// owns a row super-tile of 256 hashes (each CTA keeps its own 128 rows resident) and each CTA stages only ITS half of
-// every column super-tile (128 hashes x 128 B per K-chunk), so the L2 -> SM operand traffic and the shared-memory
-// operand reads per pair of hashes are half of variant 3's, and the freed shared memory makes the ring 4 deep.
-//   * full[stage] of the leader CTA counts two arrivals: its own producer's expect_tx and a relayed arrive from the
-//     peer (an otherwise idle lane of the peer waits for its local bulk copies, then arrives on the leader's barrier
-//     through a mapa'd shared::cluster address);
+// ------------------------------------------------------------------------------------------------ CTA pairs
+// A CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256) owns a row super-tile of 256 hashes (each CTA keeps its own
+// 128 rows) and each CTA stages only ITS half of every column super-tile, so the L2 -> SM operand traffic and the shared-
+// memory operand reads per pair of hashes are half of a single CTA's.
 //   * the leader's tcgen05.commit multicasts to empty[stage] / acc_full[buf] of BOTH CTAs;
 //   * acc_empty[buf] lives in the leader and counts the 8 epilogue warps of the pair.
 // Column chunks are absolute (chunk c = super-tiles [c*chunk, (c+1)*chunk)), so that the pairs resident at the same
 // time stream the same column tiles through L2.
 constexpr int kTc2Stages = 4;
 constexpr int kTc2StageBytes = kTcChunkBytes;  // this CTA's 128 columns x 128 B
-constexpr size_t kTc2Smem = (size_t)kTcTileBytes + kTc2Stages * kTc2StageBytes + 1024 /*align*/ + 256 /*barriers*/;
-// instruction descriptor as kTcIdesc with M = 256 (>> 4 at bit 24)
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = unsigned 8 bit (0), both K-major,
+// N = 256 (>> 3 at bit 17), M = 256 (>> 4 at bit 24)
 constexpr uint32_t kTc2Idesc = (2u << 4) | (32u << 17) | (16u << 24);
 
 __device__ __forceinline__ uint32_t tc_cluster_rank() {
@@ -325,7 +126,7 @@ __device__ __forceinline__ void tc_cluster_sync() {
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  CTA-scope semantics on purpose:
 // everything these barriers order is async-proxy traffic (bulk copies -> shared memory -> UMMA, tensor memory), and a
 // cluster-scope acquire makes ptxas invalidate the whole L1 (CCTL.IVALL) after every wait -- 41 % of all stall samples in
-// the first capture of this kernel (profiles/r01_hamming_tc2_ncu.txt)
+// the first capture of the first CTA-pair kernel (profiles/r01_hamming_v4_ncu.txt)
 __device__ __forceinline__ void tc_mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
     asm volatile(
         "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
@@ -348,168 +149,10 @@ __device__ __forceinline__ void tc2_commit(uint64_t* bar) {
         : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) hamming_tc2_kernel(const TcParams p, uint32_t n_row_tiles) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = base;
-    uint8_t* sB = base + kTcTileBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTc2Stages * kTc2StageBytes);
-    uint64_t* full = bars;                     // [kTc2Stages]
-    uint64_t* empty = bars + kTc2Stages;       // [kTc2Stages]
-    uint64_t* a_full = bars + 2 * kTc2Stages;  // [1]
-    uint64_t* acc_full = a_full + 1;           // [2]
-    uint64_t* acc_empty = acc_full + 2;        // [2]  (leader's copy is the live one)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const uint32_t cr = tc_cluster_rank();  // 0 = leader (issues the MMAs), 1 = peer
-    const uint32_t P = blockIdx.x >> 1, c = blockIdx.y;
-    if (p.world > 1 && ((P + c) % p.world) != p.rank) return;
-    // column super-tiles this pair needs: the union of its two row tiles' ranges
-    const uint2 r0 = p.tile_range[2 * P];
-    const uint2 r1 = (2 * P + 1 < n_row_tiles) ? p.tile_range[2 * P + 1] : make_uint2(0, 0);
-    uint32_t t_lo = 0xFFFFFFFFu, t_hi = 0;
-    if (r0.x < r0.y) t_lo = r0.x, t_hi = r0.y;
-    if (r1.x < r1.y) t_lo = min(t_lo, r1.x), t_hi = max(t_hi, r1.y);
-    if (t_lo >= t_hi) return;
-    const uint32_t st0 = max(t_lo / 2, c * p.chunk), st1 = min((t_hi + 1) / 2, (c + 1) * p.chunk);
-    if (st0 >= st1) return;  // the same decision in both CTAs of the pair
-    const uint32_t n_st = st1 - st0;
-    const uint32_t I = 2 * P + cr;  // this CTA's row tile
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    if (tid == 0) {
-        const uint32_t producers = cr == 0 ? 2 : 1;  // leader: own expect_tx + the peer's relayed arrive
-        for (int s = 0; s < kTc2Stages; ++s) tc_mbar_init(&full[s], producers), tc_mbar_init(&empty[s], 1);
-        tc_mbar_init(a_full, producers);
-        for (int b = 0; b < 2; ++b) tc_mbar_init(&acc_full[b], 1), tc_mbar_init(&acc_empty[b], 8);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {  // the same warp of both CTAs allocates the pair's tensor memory (512 columns each)
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_cluster_sync();  // barriers of both CTAs are initialised before anyone arrives remotely
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer: this CTA's 128 rows, then its half of every column super-tile
-            tc_mbar_expect_tx(a_full, kTcTileBytes);
-            for (int kc = 0; kc < 8; ++kc)
-                tc_bulk_g2s(sA + kc * kTcChunkBytes, p.row_exp + (size_t)I * kTcTileBytes + (size_t)kc * kTcChunkBytes,
-                            kTcChunkBytes, a_full);
-            uint32_t it = 0;
-            for (uint32_t s = 0; s < n_st; ++s) {
-                const uint8_t* t0 = p.col_exp + (size_t)(2 * (st0 + s) + cr) * kTcTileBytes;
-                for (int kc = 0; kc < 8; ++kc, ++it) {
-                    const uint32_t stage = it % kTc2Stages;
-                    tc_mbar_wait(&empty[stage], ((it / kTc2Stages) & 1) ^ 1);
-                    tc_mbar_expect_tx(&full[stage], kTc2StageBytes);
-                    tc_bulk_g2s(sB + stage * kTc2StageBytes, t0 + (size_t)kc * kTcChunkBytes, kTcChunkBytes, &full[stage]);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (cr == 0) {  // ===== MMA issuer (leader CTA only): converged warp, one elected lane issues
-            tc_mbar_wait(a_full, 0);
-            const uint64_t a_desc = tc_desc(tc_smem_u32(sA)), b_desc = tc_desc(tc_smem_u32(sB));
-            for (uint32_t s = 0; s < n_st; ++s) {
-                const uint32_t buf = s & 1;
-                tc_mbar_wait(&acc_empty[buf], ((s >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * 256;
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {  // it = 8 s + kc: stage and parity are compile-time (8 = 2 x kTc2Stages)
-                    static_assert(kTc2Stages == 4, "stage/parity folding below assumes 4 stages");
-                    tc_mbar_wait(&full[kc & 3], (kc >> 2) & 1);
-                    tc_fence_after();
-                    if (tc_elect_one()) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            tc2_mma(d_tmem, a_desc + ((kc * kTcChunkBytes + ks * 32) >> 4),
-                                    b_desc + (((kc & 3) * kTc2StageBytes + ks * 32) >> 4), (kc | ks) != 0);
-                        tc2_commit(&empty[kc & 3]);  // frees the stage in both CTAs
-                        if (kc == 7) tc2_commit(&acc_full[buf]);
-                    }
-                    __syncwarp();
-                }
-            }
-        } else if (lane == 0) {  // ===== peer CTA: relay "my half has landed" to the leader's barriers
-            tc_mbar_wait(a_full, 0);
-            tc_mbar_arrive_remote(a_full, 0);
-            const uint32_t total = n_st * 8;
-            for (uint32_t it = 0; it < total; ++it) {
-                const uint32_t stage = it % kTc2Stages;
-                tc_mbar_wait(&full[stage], (it / kTc2Stages) & 1);
-                tc_mbar_arrive_remote(&full[stage], 0);
-            }
-        }
-    } else {  // ===== epilogue (both CTAs): warp w reads TMEM lanes 32*(w%4) .. +31 of its own CTA
-        const uint32_t quarter = warp & 3;
-        const uint32_t row = quarter * 32 + lane;
-        const uint32_t gi = I * kTile + row;
-        const bool live = I < n_row_tiles;
-        const int thr = live ? (int)p.row_pc[gi] - (int)p.tol : 0x7FFFFFFF;
-        for (uint32_t s = 0; s < n_st; ++s) {
-            const uint32_t buf = s & 1;
-            tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
-            tc_fence_after();
-            const uint32_t col_first = (st0 + s) * 256;
-            for (int q = 0; q < 4; ++q) {
-                uint32_t v[64];
-                __syncwarp();
-                tc_ld64(tmem_base + buf * 256 + q * 64 + ((quarter * 32) << 16), v);
-                const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
-                int best = -0x7FFFFFFF;
-#pragma unroll
-                for (int k4 = 0; k4 < 16; ++k4) {
-                    const uint4 pj = __ldg(pcj + k4);
-                    const int t0 = 2 * (int)v[4 * k4 + 0] - (int)pj.x, t1 = 2 * (int)v[4 * k4 + 1] - (int)pj.y;
-                    const int t2 = 2 * (int)v[4 * k4 + 2] - (int)pj.z, t3 = 2 * (int)v[4 * k4 + 3] - (int)pj.w;
-                    v[4 * k4 + 0] = (uint32_t)t0, v[4 * k4 + 1] = (uint32_t)t1;
-                    v[4 * k4 + 2] = (uint32_t)t2, v[4 * k4 + 3] = (uint32_t)t3;
-                    best = max(best, max(max(t0, t1), max(t2, t3)));
-                }
-                if (best >= thr) {  // rare
-                    uint64_t mask = 0;
-#pragma unroll
-                    for (int k = 0; k < 64; ++k) mask |= (uint64_t)((int)v[k] >= thr) << k;
-                    while (mask) {
-                        const int k = __ffsll((long long)mask) - 1;
-                        mask &= mask - 1;
-                        const uint32_t gj = col_first + q * 64 + k;
-                        if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
-                            const unsigned long long slot = atomicAdd(p.counter, 1ull);
-                            if (slot < p.capacity) {
-                                const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
-                                p.keys[slot] = (rid << 32) | (uint64_t)(gj + p.col_base);
-                            }
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive_remote(&acc_empty[buf], 0);
-        }
-    }
-    __syncwarp();
-    tc_fence_before();
-    __syncthreads();
-    tc_cluster_sync();  // neither CTA may exit (or free tensor memory) while its partner can still touch it
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ CTA pair, packed operands
-// search_variant 5: variant 4 with the bit -> byte expansion moved INTO the kernel.  HBM keeps only packed tiles
-// (pk[tile][K-chunk 0..7][hash 0..127][4 x u32], 16 KB per 128 hashes), so the operand traffic from L2 is 1/8 of variant
-// 4's and no byte-expanded copy of the table (1 GB per million hashes) exists.  Four expander warps turn each K-chunk of
+// search_variant 5: the 1024 stored bits of a hash as 1024 bytes, u8 x u8 -> s32 (kind::i8), with the bit -> byte expansion
+// INSIDE the kernel.  HBM keeps only packed tiles (pk[tile][K-chunk 0..7][hash 0..127][4 x u32], 16 KB per 128 hashes), so
+// the operand traffic from L2 is 1/8 of a byte-expanded table's and no such copy (1 GB per million hashes) exists.  Four expander warps turn each K-chunk of
 // this CTA's column tile (128 hashes x 128 bits, read from a packed tile that a bulk copy landed in shared memory a whole
 // tile ahead) into the 128 x 128 B swizzled UMMA operand stage, make the writes visible to the async proxy
 // (fence.proxy.async) and arrive on the LEADER's full[stage] (8 arrivals: 4 warps x 2 CTAs).  A stage is refilled from
@@ -802,27 +445,40 @@ __global__ void __launch_bounds__(kTile) tc5_pack_kernel(const uint32_t* __restr
     if (threadIdx.x < 2) pcmin64[(size_t)blockIdx.x * 2 + threadIdx.x] = min(wmin[2 * threadIdx.x], wmin[2 * threadIdx.x + 1]);
 }
 
-int tc5_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& tiles, DevBuf& pc, DevBuf& pcmin) {
+int tc5_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, Packed& out) {
     const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
     const uint32_t T2 = (T + 1) & ~1u;  // CTA pairs read tile pairs: one zero tile of padding when T is odd
-    VDF_ALLOC(ctx, tiles.ensure((size_t)T2 * kTileWords * 4));
-    VDF_ALLOC(ctx, pc.ensure((size_t)T2 * kTile * 4));
-    VDF_ALLOC(ctx, pcmin.ensure((size_t)T2 * 2 * 4));
-    tc5_pack_kernel<<<T2, kTile, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), perm, n, tiles.as<uint32_t>(),
-                                                  pc.as<uint32_t>(), pcmin.as<uint32_t>());
+    VDF_ALLOC(ctx, out.tiles.ensure((size_t)T2 * kTileWords * 4));
+    VDF_ALLOC(ctx, out.pc.ensure((size_t)T2 * kTile * 4));
+    VDF_ALLOC(ctx, out.pcmin.ensure((size_t)T2 * 2 * 4));
+    tc5_pack_kernel<<<T2, kTile, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), perm, n, out.tiles.as<uint32_t>(),
+                                                  out.pc.as<uint32_t>(), out.pcmin.as<uint32_t>());
     VDF_LAUNCHED(ctx);
+    out.n = n, out.variant = 5, out.as_columns = false;
     return VDF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ CTA pair, 4-bit operands
-// search_variant 6 (experimental): variant 5 with the bits expanded to e2m1 nibbles ({0, 1.0}) and
-// tcgen05.mma kind::mxf4 (block-scaled, K = 64 per instruction, fp32 accumulators: exact, every partial sum is an
-// integer <= 1024), which issues at twice the kind::i8 rate.  Block scales are the constant 1.0 (UE8M0 0x7F): the tensor-
-// memory columns the scale factors live in are filled with 0x7F bytes once, so their layout does not matter.  Those
-// columns have to come out of the accumulators' 512, hence super-tiles of 192 columns (two 192-column accumulators at
-// [0,192) and [192,384), scale factors in [384,512)) and column tiles of 96 hashes.  Operands are half the size of
-// variant 5's (A: 64 KB per CTA), which pays for an 8-stage ring.  K order: nibble j of output word m of a unit holds bit
-// 4j + m of the packed word -- any permutation of K is fine as long as A and B use the same one.
+// search_variant 6 (default): variant 5 with the bits expanded to e2m1 nibbles and tcgen05.mma kind::mxf4 (block-scaled,
+// K = 64 per instruction, fp32 accumulators: exact, every partial sum is a small integer), which issues at twice the
+// kind::i8 rate.  Block scales are the constant 1.0 (UE8M0 0x7F): the tensor-memory columns the scale factors live in are
+// filled with 0x7F bytes once, so their layout does not matter.  Those columns have to come out of the accumulators' 512,
+// hence super-tiles of 192 columns (two 192-column accumulators at [0,192) and [192,384), scale factors behind them) and
+// column tiles of 96 hashes.  Operands are half the size of variant 5's (A: 64 KB per CTA), which pays for an 8-stage ring.
+// K order: nibble j of output word m of a unit holds bit 4j + m of the packed word -- any permutation of K is fine as long
+// as A and B use the same one.
+//
+// The fold (kFold, round 2).  A real VideoHash never sets bits 1000..1023 (dct_3d.rs:55-66 writes 1000 bits), so 24 of the
+// K = 1024 positions are free.  When the pack kernels saw those bits zero in BOTH operands, the kernel puts
+//     rows:    every hash bit at 2.0 (e2m1 0x4), and the constants 6.0 x 23, 2.0 x 1 in the free positions;
+//     columns: every hash bit at 1.0 (e2m1 0x2), and kFoldC - pc(j) spelled in e2m1 digits in the free positions
+//              (3 x an integer from 23 signed digits of {0, .5, 1, 1.5, 2, 3, 4, 6} against the 6.0s, the remainder 0..2 as
+//              {0, .5, 1} against the 2.0; one precomputed 16-byte operand unit per column, appended to every packed tile)
+// so the contraction returns   acc = 2 dot(i, j) - pc(j) + kFoldC   EXACTLY (integers below 2^12) and
+//     hamming(i, j) <= tol   <=>   acc >= kFoldC + pc(i) - tol.
+// The maximum over 64 accumulators is then an exact screen at ANY tolerance and the epilogue loads no popcounts: the round-1
+// screen 2 max(dot) - min(pc(j)) stopped rejecting random hashes past tol ~0.39 (236 ms per 1 M launch at 0.40 against 120).
+// Tables with a pad bit set anywhere (the test helpers of video_hash.rs:265-280 make such hashes) take the round-1 epilogue.
 constexpr int kT6Cols = 96;                          // hashes per column tile (one CTA's half of a super-tile)
 constexpr int kT6Chunk = 128;                        // bytes per row per K-chunk = 256 bits
 constexpr int kT6ABytes = 4 * kTile * kT6Chunk;      // 64 KB
@@ -830,7 +486,10 @@ constexpr int kT6StageBytes = kT6Cols * kT6Chunk;    // 12 KB
 constexpr int kT6Stages = 8;
 constexpr int kT6Expanders = 4;                      // expander warps (24 four-row groups per stage: 6 each)
 constexpr int kTc6Threads = (6 + kT6Expanders) * 32; // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. expanders
-constexpr int kT6PackedBytes = kT6Cols * 128;        // packed column tile: 96 x 128 B = 12 KB; packed row tile: 16 KB
+constexpr int kT6PackedBytes = kT6Cols * 128;        // packed bits of a column tile: 96 x 128 B = 12 KB; packed row tile: 16 KB
+constexpr int kT6FoldBytes = kT6Cols * 16;           // + one fold unit per column
+constexpr int kT6ColTileBytes = kT6PackedBytes + kT6FoldBytes;  // 13.5 KB per column tile in HBM, one bulk copy
+constexpr int kFoldC = 800;                          // pc(j) <= 1000: kFoldC - pc(j) in [-200, 800], |.| <= 3 * 276 + 2
 // all-shared form: A 64 KB + ring + 2 packed slots; kATmem form: A chunk 3 (16 KB) + ring + 4 packed slots (smaller)
 constexpr size_t kTc6Smem = (size_t)kT6ABytes + kT6Stages * kT6StageBytes + 2 * kTileWords * 4 /* packed A, then 2 packed column tiles */ + 1024 + 256;
 // block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): a/b format E2M1 = 1 at [7,10) / [10,13),
@@ -852,9 +511,40 @@ __device__ __forceinline__ void tc6_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
         "r"(tmem_a), "l"(db), "r"(kTc6Idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
         : "memory");
 }
-// one packed u32 -> one 16-byte unit of e2m1 nibbles (0x2 = 1.0)
+// one packed u32 -> one 16-byte unit of e2m1 nibbles: 0x2 = 1.0 per set bit (columns; rows without the fold) ...
 __device__ __forceinline__ uint4 tc6_expand(uint32_t w) {
     return make_uint4((w << 1) & 0x22222222u, w & 0x22222222u, (w >> 1) & 0x22222222u, (w >> 2) & 0x22222222u);
+}
+// ... or 0x4 = 2.0 per set bit (rows with the fold)
+template <bool kFold>
+__device__ __forceinline__ uint4 tc6_expand_row(uint32_t w) {
+    if (!kFold) return tc6_expand(w);
+    return make_uint4((w << 2) & 0x44444444u, (w << 1) & 0x44444444u, w & 0x44444444u, (w >> 1) & 0x44444444u);
+}
+// Free K positions: the unit of hash word 31 (u32) holds hash bits 992..1023; nibble j of output word m is bit 4j + m, so the
+// 24 pad positions are nibbles 2..7 of all four words.  Rows carry 6.0 (0x7) in 23 of them and 2.0 (0x4) in the last.
+constexpr uint32_t kFoldRowPad = 0x77777700u, kFoldRowPadLast = 0x47777700u;
+
+// kFoldC - pc spelled in e2m1 digits (see the head of this section): out = the column's unit for hash word 31
+__device__ __forceinline__ uint4 tc6_fold_unit(uint32_t w31, uint32_t pc) {
+    const int T = kFoldC - (int)pc;
+    int r = T % 3;
+    if (r < 0) r += 3;
+    const int Q = (T - r) / 3;  // sum over 23 digits of 2 * digit
+    const uint32_t sign = Q < 0 ? 8u : 0u;
+    int q = Q < 0 ? -Q : Q;
+    const uint4 e = tc6_expand(w31);
+    uint32_t word[4] = {e.x & 0xFFu, e.y & 0xFFu, e.z & 0xFFu, e.w & 0xFFu};
+#pragma unroll
+    for (int d = 0; d < 23; ++d) {
+        // largest doubled digit value <= q from {12, 8, 6, 4, 3, 2, 1}; its e2m1 code: 1..4 -> 1..4, 6 -> 5, 8 -> 6, 12 -> 7
+        const int v = q >= 12 ? 12 : q >= 8 ? 8 : q >= 6 ? 6 : q >= 4 ? 4 : q;  // q < 4: q itself (0..3)
+        const uint32_t code = v <= 4 ? (uint32_t)v : v == 6 ? 5u : v == 8 ? 6u : 7u;
+        q -= v;
+        word[d / 6] |= (v ? (code | sign) : 0u) << (4 * (2 + d % 6));
+    }
+    word[3] |= (uint32_t)r << 28;  // digit 23 = (m 3, j 7): 0, 0.5 or 1.0 against the row's 2.0
+    return make_uint4(word[0], word[1], word[2], word[3]);
 }
 #define TC_RI8(v, o) "r"(v[o]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -866,14 +556,17 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32])
         : "memory");
 }
 
-// hashes [n][32] u32 -> pk[tile][K-chunk 0..3][row 0..T-1][8 x u32] + pc + pcmin64 (as tc5_pack_kernel, tile size T)
-template <int T>
+// hashes [n][32] u32 -> pk[tile][K-chunk 0..3][row 0..T-1][8 x u32] (+ [row][4 x u32] fold units for column tiles) + pc;
+// pads_or |= bits 1000..1023 of every hash.  One thread per hash; tiles beyond n are zero.  perm (optional) gathers rows.
+template <int T, bool kCols>
 __global__ void __launch_bounds__(128) tc6_pack_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm, uint64_t n,
-                                                       uint32_t* __restrict__ pk, uint32_t* __restrict__ pc) {
-    if ((int)threadIdx.x >= T) return;
+                                                       uint32_t* __restrict__ pk, uint32_t* __restrict__ pc, uint32_t* __restrict__ pads_or) {
+    if ((int)threadIdx.x >= T) return;  // T is a multiple of 32: whole warps leave
+    constexpr size_t kTileU32 = kCols ? kT6ColTileBytes / 4 : (size_t)T * 32;
     const uint64_t g = (uint64_t)blockIdx.x * T + threadIdx.x;
-    uint4* out = reinterpret_cast<uint4*>(pk + (size_t)blockIdx.x * T * 32) + threadIdx.x * 2;
-    uint32_t c = 0;
+    uint32_t* tile = pk + (size_t)blockIdx.x * kTileU32;
+    uint4* out = reinterpret_cast<uint4*>(tile) + threadIdx.x * 2;
+    uint32_t c = 0, w31 = 0;
     const uint4* src = g < n ? reinterpret_cast<const uint4*>(in) + (perm ? perm[g] : g) * 8 : nullptr;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {  // q = 16-byte piece of the hash; K-chunk kc = q / 2 holds pieces 2kc, 2kc+1
@@ -881,8 +574,12 @@ __global__ void __launch_bounds__(128) tc6_pack_kernel(const uint32_t* __restric
         if (src) v = src[q];
         c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
         out[(q >> 1) * T * 2 + (q & 1)] = v;
+        if (q == 7) w31 = v.w;
     }
     pc[g] = c;
+    if (kCols) reinterpret_cast<uint4*>(tile + (size_t)T * 32)[threadIdx.x] = tc6_fold_unit(w31, c);
+    const uint32_t pad = __reduce_or_sync(0xffffffffu, w31 >> 8);
+    if ((threadIdx.x & 31) == 0 && pad) atomicOr(pads_or, pad);
 }
 __global__ void pcmin64_kernel(const uint32_t* __restrict__ pc, uint64_t n_groups, uint32_t* __restrict__ pcmin) {
     const uint64_t g = blockIdx.x * (uint64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -931,11 +628,50 @@ __global__ void tc6_unit_list_kernel(const TcParams p, uint32_t n_row_tiles, uin
     for (uint32_t k = 0; k < n; ++k) out[k] = ((uint64_t)(c_first + k * p.world) << 32) | P;
 }
 
+// Append the matches of one warp (lane = row, mask = its matching columns among the 64 starting at c0) with ONE atomic per
+// warp: window test as a bit range, warp prefix sum of the counts, the last lane reserves the slots.  Converged warp only.
+__device__ __forceinline__ void tc6_emit(const TcParams& p, uint64_t mask, uint32_t c0, uint32_t gi, uint32_t win_lo, uint32_t win_hi,
+                                         int lane) {
+    if (mask) {  // columns [win_lo, win_hi) of this row, as bits relative to c0
+        const long long a = (long long)win_lo - (long long)c0, b = (long long)win_hi - (long long)c0;
+        const uint64_t below_b = b >= 64 ? ~0ull : b <= 0 ? 0ull : ((1ull << b) - 1);
+        const uint64_t below_a = a >= 64 ? ~0ull : a <= 0 ? 0ull : ((1ull << a) - 1);
+        mask &= below_b & ~below_a;
+    }
+    const uint32_t cnt = (uint32_t)__popcll(mask);
+    if (__ballot_sync(0xffffffffu, cnt != 0) == 0) return;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(p.counter, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    unsigned long long slot = base + incl - cnt;
+    if (!mask) return;
+    const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
+    while (mask) {
+        const int k = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const uint64_t key = (rid << 32) | (uint64_t)(c0 + k + p.col_base);
+        if (p.peers.world) {  // fused exchange: this rank's segment of every rank's buffer, over NVLink
+            if (slot < p.peers.seg_cap)
+                for (uint32_t r = 0; r < p.peers.world; ++r) p.peers.keys(r, p.peers.rank)[slot] = key;
+        } else if (slot < p.capacity) {
+            p.keys[slot] = key;
+        }
+        ++slot;
+    }
+}
+
 // kATmem: K-chunks 0-2 of the row operand live in tensor memory (columns [384, 480), written once per unit with tcgen05.st)
 // and only chunk 3 in shared memory; scale factors in [480, 512).  The shared-memory data pipe is what bounds the all-smem
 // form (ncu: 50 % tensor-core operand reads + 32 % expander stores at 86 % tensor-pipe activity); reading three quarters of
 // A from tensor memory takes the operand reads from 7 KB to 4 KB per instruction.
-template <bool kATmem>
+template <bool kATmem, bool kFold>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
     hamming_tc6_kernel(const TcParams p, uint32_t n_row_tiles, uint32_t n_col_st) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1003,7 +739,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
             uint32_t v[32];
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-                const uint4 e = tc6_expand(pw[w]);
+                const uint4 e = tc6_expand_row<kFold>(pw[w]);
                 v[4 * w] = e.x, v[4 * w + 1] = e.y, v[4 * w + 2] = e.z, v[4 * w + 3] = e.w;
             }
             tc_st32(tmem_base + ((row & ~31u) << 16) + 384 + kc * 32, v);
@@ -1014,8 +750,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
         const int w = lane & 7, r4 = lane >> 3;
         for (int item = warp + (kATmem ? 3 * 32 : 0); item < 4 * 32; item += kTc6Threads / 32) {  // (K-chunk, 4-row group)
             const int kc = item >> 5, row = (item & 31) * 4 + r4;
-            *reinterpret_cast<uint4*>(sA + (kATmem ? 0 : kc) * (kTile * kT6Chunk) + row * 128 + ((w ^ (row & 7)) << 4)) =
-                tc6_expand(sP[(kc * kTile + row) * 8 + w]);
+            uint4 e = tc6_expand_row<kFold>(sP[(kc * kTile + row) * 8 + w]);
+            if (kFold && kc == 3 && w == 7) e.x |= kFoldRowPad, e.y |= kFoldRowPad, e.z |= kFoldRowPad, e.w |= kFoldRowPadLast;
+            *reinterpret_cast<uint4*>(sA + (kATmem ? 0 : kc) * (kTile * kT6Chunk) + row * 128 + ((w ^ (row & 7)) << 4)) = e;
         }
     }
     tc_fence_proxy_async();
@@ -1026,12 +763,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
     const uint32_t sfa = tmem_base + kSfCol, sfb = tmem_base + kSfCol + (kATmem ? 16u : 64u);
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== bulk-copy producer: this CTA's packed column tile (96 hashes) of every super-tile
+        if (lane == 0) {  // ===== bulk-copy producer: this CTA's packed column tile (96 hashes + their fold units) of every super-tile
             for (uint32_t s = 0; s < n_st; ++s) {
                 const uint32_t pb = s % kPB;
                 tc_mbar_wait(&pempty[pb], ((s / kPB) & 1) ^ 1);
-                tc_mbar_expect_tx(&pfull[pb], kT6PackedBytes);
-                tc_bulk_g2s(sP + pb * kTileWords, col_tiles + (size_t)(2 * (st0 + s) + cr) * (kT6PackedBytes / 4), kT6PackedBytes,
+                tc_mbar_expect_tx(&pfull[pb], kT6ColTileBytes);
+                tc_bulk_g2s(sP + pb * kTileWords, col_tiles + (size_t)(2 * (st0 + s) + cr) * (kT6ColTileBytes / 4), kT6ColTileBytes,
                             &pfull[pb]);
             }
         }
@@ -1077,6 +814,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
             const uint32_t pb = s % kPB;
             tc_mbar_wait(&pfull[pb], (s / kPB) & 1);
             const uint32_t* packed = sP + pb * kTileWords + row0 * 8 + w;
+            const uint4* fold_units = reinterpret_cast<const uint4*>(sP + pb * kTileWords + kT6PackedBytes / 4);
             for (int kc = 0; kc < 4; ++kc) {
                 uint32_t bits[kG];
 #pragma unroll
@@ -1085,10 +823,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
                 const uint32_t stage = it % kT6Stages;
                 tc_mbar_wait(&empty[stage], ((it / kT6Stages) & 1) ^ 1);
                 uint8_t* dst = sB + stage * kT6StageBytes;
+                const bool folded = kFold && kc == 3 && w == 7;  // the unit of hash word 31 comes precomputed with the column's digits
 #pragma unroll
                 for (int g = 0; g < kG; ++g) {
                     const int row = row0 + 4 * kT6Expanders * g;
-                    *reinterpret_cast<uint4*>(dst + row * 128 + ((w ^ (row & 7)) << 4)) = tc6_expand(bits[g]);
+                    uint4 e = tc6_expand(bits[g]);
+                    if (folded) e = fold_units[row];
+                    *reinterpret_cast<uint4*>(dst + row * 128 + ((w ^ (row & 7)) << 4)) = e;
                 }
                 tc_fence_proxy_async();
                 __syncwarp();
@@ -1102,8 +843,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
         const uint32_t row = quarter * 32 + lane;
         const uint32_t gi = I * kTile + row;
         const bool live = I < n_row_tiles;
-        const int thr = live ? (int)p.row_pc[gi] - (int)p.tol : 0x7FFFFFFF;
-        const float thr_f = live ? (float)thr - 8388608.0f : 3.0e38f;  // 2 dot - pc(j) - 2^23 >= thr - 2^23, all exact in fp32
+        const uint32_t win_lo = live ? __ldg(p.row_lo + gi) : 0u, win_hi = live ? __ldg(p.row_hi + gi) : 0u;
+        // fold:    acc = 2 dot - pc(j) + kFoldC, a match iff acc >= kFoldC + pc(i) - tol
+        // no fold: acc = dot,                    a match iff 2 dot - pc(j) >= pc(i) - tol
+        const int thr = live ? (kFold ? kFoldC : 0) + (int)p.row_pc[gi] - (int)p.tol : 0x7FFFFFFF;
+        const float thr_f = kFold ? (float)thr : (live ? (float)thr - 8388608.0f : 3.0e38f);  // no fold: 2 dot - pc(j) - 2^23 >= thr - 2^23, exact in fp32
+        // positive floats order like their bit patterns taken as signed ints, and every negative one is a negative int:
+        // with thr > 0 the signed-int maximum of 64 accumulators passes the bit pattern of thr iff some accumulator does
+        const bool screen = thr > 0;
+        const int thr_bits = __float_as_int((float)thr);
         for (uint32_t s = 0; s < n_st; ++s) {
             const uint32_t buf = s & 1;
             tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
@@ -1112,58 +860,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
             const uint32_t* pcmin = p.col_pcmin + (col_first >> 6);
             for (int q = 0; q < 3; ++q) {
                 uint32_t v[64];
-                const int floor_pc = (int)__ldg(pcmin + q);
+                int floor_pc = 0;
+                if (!kFold) floor_pc = (int)__ldg(pcmin + q);
                 __syncwarp();
                 tc_ld64(tmem_base + buf * 192 + q * 64 + ((quarter * 32) << 16), v);
-                uint32_t best = 0;  // accumulators are non-negative floats: their bit patterns order like the values
+                uint64_t mask = 0;
+                if (kFold) {
+                    int best = (int)v[0];
 #pragma unroll
-                for (int k = 0; k < 64; k += 2) best = max(best, max(v[k], v[k + 1]));
-                if (2 * (int)__uint_as_float(best) - floor_pc >= thr) {
-                    // The bound above is loose (largest dot and smallest popcount of 64 columns rarely belong to the same
-                    // column): at tolerance 0.4 it lets most groups of random hashes through.  Second screen, exact and on
-                    // the FMA pipe only: the largest 2 dot - pc(j) of the group.  0x4B000000 | pc is the float 2^23 + pc, so
-                    // fma(dot, 2, -(2^23 + pc)) = 2 dot - pc - 2^23 exactly - no int<->float conversions (XU pipe, 16 per
-                    // clock: 64 of them per thread cost as much as the group's MMAs and made the 1 M launch 2.5x slower
-                    // at tolerance 0.4).
-                    const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
-                    float top = -3.0e38f;
+                    for (int k = 0; k < 64; k += 2) best = max(best, max((int)v[k], (int)v[k + 1]));
+                    if (!screen || best >= thr_bits) {  // exact: only a row that really has a match among these 64 columns gets here
 #pragma unroll
-                    for (int k4 = 0; k4 < 16; ++k4) {
-                        const uint4 pj = __ldg(pcj + k4);
-                        top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)));
-                        top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)));
-                        top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)));
-                        top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)));
+                        for (int k = 0; k < 64; ++k) mask |= (uint64_t)(__uint_as_float(v[k]) >= thr_f) << k;
                     }
-                    uint64_t mask = 0;
-                    if (top >= thr_f) {  // a pair of this row with one of the 64 columns is within the tolerance
+                } else {
+                    uint32_t best = 0;  // accumulators are non-negative floats: their bit patterns order like the values
+#pragma unroll
+                    for (int k = 0; k < 64; k += 2) best = max(best, max(v[k], v[k + 1]));
+                    if (2 * (int)__uint_as_float(best) - floor_pc >= thr) {
+                        // The bound above is loose (largest dot and smallest popcount of 64 columns rarely belong to the same
+                        // column): at tolerance 0.4 it lets most groups of random hashes through.  Second screen, exact and on
+                        // the FMA pipe only: the largest 2 dot - pc(j) of the group.  0x4B000000 | pc is the float 2^23 + pc, so
+                        // fma(dot, 2, -(2^23 + pc)) = 2 dot - pc - 2^23 exactly - no int<->float conversions (XU pipe, 16 per
+                        // clock: 64 of them per thread cost as much as the group's MMAs).
+                        const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
+                        float top = -3.0e38f;
 #pragma unroll
                         for (int k4 = 0; k4 < 16; ++k4) {
                             const uint4 pj = __ldg(pcj + k4);
-                            mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)) >= thr_f) << (4 * k4 + 0);
-                            mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)) >= thr_f) << (4 * k4 + 1);
-                            mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)) >= thr_f) << (4 * k4 + 2);
-                            mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)) >= thr_f) << (4 * k4 + 3);
+                            top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)));
+                            top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)));
+                            top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)));
+                            top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)));
                         }
-                    }
-                    while (mask) {
-                        const int k = __ffsll((long long)mask) - 1;
-                        mask &= mask - 1;
-                        const uint32_t gj = col_first + q * 64 + k;
-                        if (gj >= p.row_lo[gi] && gj < p.row_hi[gi]) {
-                            const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
-                            const uint64_t key = (rid << 32) | (uint64_t)(gj + p.col_base);
-                            if (p.peers.world) {  // fused exchange: this rank's segment of every rank's buffer, over NVLink
-                                const unsigned long long slot = atomicAdd(p.counter, 1ull);
-                                if (slot < p.peers.seg_cap)
-                                    for (uint32_t r = 0; r < p.peers.world; ++r) p.peers.keys(r, p.peers.rank)[slot] = key;
-                            } else {
-                                const unsigned long long slot = atomicAdd(p.counter, 1ull);
-                                if (slot < p.capacity) p.keys[slot] = key;
+                        if (top >= thr_f) {  // a pair of this row with one of the 64 columns is within the tolerance
+#pragma unroll
+                            for (int k4 = 0; k4 < 16; ++k4) {
+                                const uint4 pj = __ldg(pcj + k4);
+                                mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)) >= thr_f) << (4 * k4 + 0);
+                                mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)) >= thr_f) << (4 * k4 + 1);
+                                mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)) >= thr_f) << (4 * k4 + 2);
+                                mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)) >= thr_f) << (4 * k4 + 3);
                             }
                         }
                     }
                 }
+                __syncwarp();
+                tc6_emit(p, mask, col_first + q * 64, gi, win_lo, win_hi, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -1180,15 +923,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
     }
 }
 
-// rows: tiles of 128 hashes (+ pc); columns: tiles of 96 hashes padded to whole super-tiles (+ pc, pcmin)
-int tc6_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, bool as_columns, DevBuf& tiles, DevBuf& pc,
-             DevBuf& pcmin) {
+// ------------------------------------------------------------------------------------------------ host side
+// rows: tiles of 128 hashes (+ pc); columns: tiles of 96 hashes + fold units, padded to whole super-tiles (+ pc, pcmin)
+int tc6_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, bool as_columns, Packed& out, uint32_t* d_pads_or) {
     const uint32_t* in = reinterpret_cast<const uint32_t*>(d_hash);
+    out.n = n, out.variant = 6, out.as_columns = as_columns;
     if (!as_columns) {
         const uint32_t T = (uint32_t)((n + kTile - 1) / kTile), T2 = (T + 1) & ~1u;
-        VDF_ALLOC(ctx, tiles.ensure((size_t)T2 * kTileWords * 4));
-        VDF_ALLOC(ctx, pc.ensure((size_t)T2 * kTile * 4));
-        tc6_pack_kernel<kTile><<<T2, 128, 0, ctx->stream>>>(in, perm, n, tiles.as<uint32_t>(), pc.as<uint32_t>());
+        VDF_ALLOC(ctx, out.tiles.ensure((size_t)T2 * kTileWords * 4));
+        VDF_ALLOC(ctx, out.pc.ensure((size_t)T2 * kTile * 4));
+        tc6_pack_kernel<kTile, false><<<T2, 128, 0, ctx->stream>>>(in, perm, n, out.tiles.as<uint32_t>(), out.pc.as<uint32_t>(), d_pads_or);
         VDF_LAUNCHED(ctx);
         return VDF_OK;
     }
@@ -1196,174 +940,128 @@ int tc6_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_
     // multiple of 192 and of 64
     const uint64_t n128 = (n + kTile - 1) / kTile * kTile;
     const uint32_t T = (uint32_t)((n128 + kT6Cols - 1) / kT6Cols), T2 = (T + 1) & ~1u;
-    VDF_ALLOC(ctx, tiles.ensure((size_t)T2 * kT6PackedBytes));
-    VDF_ALLOC(ctx, pc.ensure((size_t)T2 * kT6Cols * 4));
-    VDF_ALLOC(ctx, pcmin.ensure((size_t)T2 * kT6Cols / 64 * 4));
-    tc6_pack_kernel<kT6Cols><<<T2, 128, 0, ctx->stream>>>(in, perm, n, tiles.as<uint32_t>(), pc.as<uint32_t>());
+    VDF_ALLOC(ctx, out.tiles.ensure((size_t)T2 * kT6ColTileBytes));
+    VDF_ALLOC(ctx, out.pc.ensure((size_t)T2 * kT6Cols * 4));
+    VDF_ALLOC(ctx, out.pcmin.ensure((size_t)T2 * kT6Cols / 64 * 4));
+    tc6_pack_kernel<kT6Cols, true><<<T2, 128, 0, ctx->stream>>>(in, perm, n, out.tiles.as<uint32_t>(), out.pc.as<uint32_t>(), d_pads_or);
     VDF_LAUNCHED(ctx);
     const uint64_t groups = (uint64_t)T2 * kT6Cols / 64;
-    pcmin64_kernel<<<(unsigned)((groups + 7) / 8), 256, 0, ctx->stream>>>(pc.as<uint32_t>(), groups, pcmin.as<uint32_t>());
+    pcmin64_kernel<<<(unsigned)((groups + 7) / 8), 256, 0, ctx->stream>>>(out.pc.as<uint32_t>(), groups, out.pcmin.as<uint32_t>());
     VDF_LAUNCHED(ctx);
     return VDF_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ host side
-int tc_expand(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, DevBuf& exp, DevBuf& pc) {
-    const uint32_t T = (uint32_t)((n + kTile - 1) / kTile);
-    const uint32_t T2 = (T + 1) & ~1u;  // super-tiles read tile pairs: keep an even number of (zero) tiles
-    VDF_ALLOC(ctx, exp.ensure((size_t)T2 * kTcTileBytes));
-    VDF_ALLOC(ctx, pc.ensure((size_t)T2 * kTile * 4));
-    if (T2 > T) {
-        VDF_CUDA(ctx, cudaMemsetAsync(exp.as<uint8_t>() + (size_t)T * kTcTileBytes, 0, kTcTileBytes, ctx->stream));
-        VDF_CUDA(ctx, cudaMemsetAsync(pc.as<uint32_t>() + (size_t)T * kTile, 0, kTile * 4, ctx->stream));
-    }
-    expand_tiles_kernel<<<dim3(T, 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_hash), perm, n,
-                                                            exp.as<uint8_t>(), pc.as<uint32_t>());
-    VDF_LAUNCHED(ctx);
-    return VDF_OK;
-}
-
-int tc_launch(vdf_ctx* ctx, uint32_t n_row_tiles, uint32_t n_col_tiles, uint32_t max_span_tiles, const uint8_t* row_exp,
-              const uint8_t* col_exp, const uint32_t* row_pc, const uint32_t* col_pc, const uint32_t* col_pcmin,
-              const uint32_t* row_id, uint64_t col_base, uint32_t tol, uint64_t capacity, unsigned long long* counter) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc2Smem));
-        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc5Smem));
-        attr_done = true;
-    }
+static TcParams plan_params(const Plan& pl) {
     TcParams p;
-    p.row_exp = row_exp, p.col_exp = col_exp, p.row_pc = row_pc, p.col_pc = col_pc, p.col_pcmin = col_pcmin;
-    p.row_lo = ctx->row_lo.as<uint32_t>(), p.row_hi = ctx->row_hi.as<uint32_t>(), p.row_id = row_id;
-    p.tile_range = ctx->tile_range.as<uint2>();
+    memset(&p, 0, sizeof p);
+    p.row_lo = pl.row_lo.as<uint32_t>(), p.row_hi = pl.row_hi.as<uint32_t>();
+    p.tile_range = pl.tile_range.as<uint2>();
+    p.chunk = pl.chunk;
+    p.rank = pl.rank, p.world = pl.world;
+    p.unit_off = pl.unit_off.as<uint32_t>();
+    p.n_pairs = (pl.n_row_tiles + 1) / 2;
+    p.unit_list = pl.unit_list;
+    p.peers.world = 0;
+    return p;
+}
+
+// Work units of the CTA-pair kernels for the tile ranges in `pl` (no host round trip: the unit count lands in pl.stats[2],
+// which the caller reads together with the other statistics of the plan).  The unit list is sized for its upper bound and
+// padded with ~0 entries, which a stable sort on the chunk bits leaves behind the real ones.
+int tc_plan_units(vdf_ctx* ctx, Plan& pl) {
+    const uint32_t n_pairs = (pl.n_row_tiles + 1) / 2;
+    uint32_t n_st, ch;
+    if (pl.variant == 6) {
+        n_st = (uint32_t)(((uint64_t)pl.n_col_tiles * kTile + 2 * kT6Cols - 1) / (2 * kT6Cols));
+        // a unit costs ~5 us of set-up and drain (tensor-memory allocation, row operand load + expansion, cluster syncs,
+        // the last epilogue) next to 0.84 us per super-tile: measured at 1 M hashes, 130.0 / 127.3 / 125.8 / 125.0 / 124.5 ms
+        // for chunks of 128 / 256 / 512 / 1024 / 2048.  Long chunks, as long as >= 64 units per resident pair keep the tail short.
+        ch = pl.tc_chunk ? pl.tc_chunk : 2048;
+    } else {
+        n_st = (pl.n_col_tiles + 1) / 2;
+        ch = pl.tc_chunk ? pl.tc_chunk : 128;
+    }
+    while (!pl.tc_chunk && ch > 2 && (uint64_t)n_pairs * ((n_st + ch - 1) / ch) < (uint64_t)(ctx->sm_count / 2) * 64 * pl.world) ch >>= 1;
+    while ((n_st + ch - 1) / ch > 65535) ch *= 2;
+    pl.chunk = ch;
+    VDF_ALLOC(ctx, pl.unit_cnt.ensure((size_t)(n_pairs + 1) * 4));
+    VDF_ALLOC(ctx, pl.unit_off.ensure((size_t)(n_pairs + 1) * 4));
+    TcParams p = plan_params(pl);
+    if (pl.variant == 6) tc6_units_kernel<<<(n_pairs + 1 + 255) / 256, 256, 0, ctx->stream>>>(p, pl.n_row_tiles, pl.unit_cnt.as<uint32_t>());
+    else tc5_units_kernel<<<(n_pairs + 1 + 255) / 256, 256, 0, ctx->stream>>>(p, pl.n_row_tiles, pl.unit_cnt.as<uint32_t>());
+    VDF_LAUNCHED(ctx);
+    size_t tmp = 0;
+    VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, pl.unit_cnt.as<uint32_t>(), pl.unit_off.as<uint32_t>(), (size_t)n_pairs + 1, ctx->stream));
+    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
+    VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tmp, pl.unit_cnt.as<uint32_t>(), pl.unit_off.as<uint32_t>(), (size_t)n_pairs + 1,
+                                                ctx->stream));
+    ctx->launches += 1;
+    // stats[2] (u64, zeroed by the caller) <- the unit count (u32)
+    VDF_CUDA(ctx, cudaMemcpyAsync(pl.stats.as<unsigned long long>() + 2, pl.unit_off.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    pl.unit_list = nullptr;
+    if (pl.variant != 6) return VDF_OK;
+    const uint32_t n_chunks = (n_st + ch - 1) / ch;
+    const uint64_t ub = (uint64_t)n_pairs * ((n_chunks - 1) / pl.world + 1);  // a pair owns every world-th chunk of its range
+    if (ub > 0x3FFFFFFFull) {
+        ctx->err = "too many work units for one launch";
+        return VDF_ERR_INVALID;
+    }
+    VDF_ALLOC(ctx, pl.unit_list_a.ensure((size_t)ub * 8));
+    VDF_CUDA(ctx, cudaMemsetAsync(pl.unit_list_a.p, 0xFF, (size_t)ub * 8, ctx->stream));
+    tc6_unit_list_kernel<<<(n_pairs + 255) / 256, 256, 0, ctx->stream>>>(p, pl.n_row_tiles, pl.unit_list_a.as<uint64_t>());
+    VDF_LAUNCHED(ctx);
+    pl.unit_list = pl.unit_list_a.as<uint64_t>();
+    if (pl.unit_order == 0 && n_chunks > 1) {  // chunk-major: stable radix sort on the chunk bits of the P-major list
+        int cbits = 1;
+        while ((1u << cbits) < n_chunks) ++cbits;
+        VDF_ALLOC(ctx, pl.unit_list_b.ensure((size_t)ub * 8));
+        size_t tmp2 = 0;
+        VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp2, pl.unit_list_a.as<uint64_t>(), pl.unit_list_b.as<uint64_t>(), (size_t)ub, 32,
+                                                     32 + cbits, ctx->stream));
+        VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp2));
+        VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp2, pl.unit_list_a.as<uint64_t>(), pl.unit_list_b.as<uint64_t>(), (size_t)ub,
+                                                     32, 32 + cbits, ctx->stream));
+        ctx->launches += 1;
+        pl.unit_list = pl.unit_list_b.as<uint64_t>();
+    }
+    return VDF_OK;
+}
+
+int tc_launch(vdf_ctx* ctx, const Plan& pl, const Packed& rows, const Packed& cols, const uint32_t* row_id, uint64_t col_base, uint32_t tol,
+              uint64_t capacity, unsigned long long* counter) {
+    if (!ctx->tc_attrs) {  // per device, hence per context
+        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc5Smem));
+        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+        VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
+        ctx->tc_attrs = true;
+    }
+    if (pl.n_units == 0) return VDF_OK;
+    TcParams p = plan_params(pl);
+    p.row_exp = rows.tiles.as<uint8_t>(), p.col_exp = cols.tiles.as<uint8_t>();
+    p.row_pc = rows.pc.as<uint32_t>(), p.col_pc = cols.pc.as<uint32_t>(), p.col_pcmin = cols.pcmin.as<uint32_t>();
+    p.row_id = row_id;
     p.keys = ctx->raw_keys.as<uint64_t>(), p.counter = counter, p.capacity = capacity, p.col_base = col_base;
     p.tol = tol > 1024u ? 1024u : tol;  // no distance exceeds 1024 (and the epilogue's threshold is a signed int)
-    p.rank = ctx->rank, p.world = ctx->world;
-    p.unit_off = nullptr, p.n_pairs = 0, p.unit_list = nullptr;
-    p.peers.world = 0;
     if (ctx->exchange) {
-        if (ctx->search_variant != 6 || !ctx->peer.world) {
+        if (pl.variant != 6 || !ctx->peer.world) {
             ctx->err = "the peer exchange needs search_variant 6 and vdf_peer_open";
             return VDF_ERR_INVALID;
         }
         p.peers = ctx->peer.ptrs((uint32_t)(ctx->peer.epoch & 1));
     }
-    if (ctx->search_variant >= 4) {  // CTA pairs: 256-row super-tiles x absolute chunks of column super-tiles
-        const uint32_t n_pairs = (n_row_tiles + 1) / 2, n_st = (n_col_tiles + 1) / 2;
-        // long chunks amortise the per-unit set-up (operand A, tensor-memory allocation, cluster syncs); keep >= 64
-        // units per resident pair for balance
-        uint32_t chunk = ctx->tc_chunk ? ctx->tc_chunk : 128;
-        while (!ctx->tc_chunk && chunk > 2 &&
-               (uint64_t)n_pairs * ((n_st + chunk - 1) / chunk) < (uint64_t)(ctx->sm_count / 2) * 64 * ctx->world)
-            chunk >>= 1;
-        while ((n_st + chunk - 1) / chunk > 65535) chunk *= 2;
-        p.chunk = chunk;
-        if (ctx->search_variant == 6) {  // as variant 5, super-tiles of 192 columns
-            static bool attr6 = false;
-            if (!attr6) {
-                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
-                VDF_CUDA(ctx, cudaFuncSetAttribute(hamming_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc6Smem));
-                attr6 = true;
-            }
-            const uint32_t n_col_st = (uint32_t)(((uint64_t)n_col_tiles * kTile + 2 * kT6Cols - 1) / (2 * kT6Cols));
-            // a unit costs ~5 us of set-up and drain (tensor-memory allocation, row operand load + expansion, cluster syncs,
-            // the last epilogue) next to 0.84 us per super-tile: measured at 1 M hashes, 130.0 / 127.3 / 125.8 / 125.0 / 124.5 ms
-            // for chunks of 128 / 256 / 512 / 1024 / 2048.  Long chunks, as long as >= 64 units per resident pair keep the tail short.
-            uint32_t ch = ctx->tc_chunk ? ctx->tc_chunk : 2048;
-            while (!ctx->tc_chunk && ch > 2 && (uint64_t)n_pairs * ((n_col_st + ch - 1) / ch) < (uint64_t)(ctx->sm_count / 2) * 64 * ctx->world)
-                ch >>= 1;
-            p.chunk = ch;
-            p.n_pairs = n_pairs;
-            VDF_ALLOC(ctx, ctx->unit_cnt.ensure((size_t)(n_pairs + 1) * 4));
-            VDF_ALLOC(ctx, ctx->unit_off.ensure((size_t)(n_pairs + 1) * 4));
-            p.unit_off = ctx->unit_off.as<uint32_t>();
-            tc6_units_kernel<<<(n_pairs + 1 + 255) / 256, 256, 0, ctx->stream>>>(p, n_row_tiles, ctx->unit_cnt.as<uint32_t>());
-            VDF_LAUNCHED(ctx);
-            size_t tmp = 0;
-            VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->unit_cnt.as<uint32_t>(), ctx->unit_off.as<uint32_t>(),
-                                                        (size_t)n_pairs + 1, ctx->stream));
-            VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
-            VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tmp, ctx->unit_cnt.as<uint32_t>(),
-                                                        ctx->unit_off.as<uint32_t>(), (size_t)n_pairs + 1, ctx->stream));
-            uint32_t n_units = 0;
-            VDF_CUDA(ctx, cudaMemcpyAsync(&n_units, ctx->unit_off.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (n_units == 0) return VDF_OK;
-            if (n_units > 0x3FFFFFFFu) {
-                ctx->err = "too many work units for one launch";
-                return VDF_ERR_INVALID;
-            }
-            {   // explicit unit list, chunk-major (stable radix sort on the chunk bits of a P-major list)
-                VDF_ALLOC(ctx, ctx->unit_list_a.ensure((size_t)n_units * 8));
-                VDF_ALLOC(ctx, ctx->unit_list_b.ensure((size_t)n_units * 8));
-                tc6_unit_list_kernel<<<(n_pairs + 255) / 256, 256, 0, ctx->stream>>>(p, n_row_tiles, ctx->unit_list_a.as<uint64_t>());
-                VDF_LAUNCHED(ctx);
-                p.unit_list = ctx->unit_list_a.as<uint64_t>();
-                const uint32_t n_chunks = (n_col_st + ch - 1) / ch;
-                int cbits = 1;
-                while ((1u << cbits) < n_chunks) ++cbits;
-                if (ctx->tc_unit_order == 0 && n_chunks > 1) {
-                    size_t tmp2 = 0;
-                    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp2, ctx->unit_list_a.as<uint64_t>(), ctx->unit_list_b.as<uint64_t>(),
-                                                                 (size_t)n_units, 32, 32 + cbits, ctx->stream));
-                    VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp2));
-                    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp2, ctx->unit_list_a.as<uint64_t>(),
-                                                                 ctx->unit_list_b.as<uint64_t>(), (size_t)n_units, 32, 32 + cbits, ctx->stream));
-                    ctx->launches += 1;
-                    p.unit_list = ctx->unit_list_b.as<uint64_t>();
-                }
-            }
-            kt_begin(ctx, 0);
-            if (ctx->tc_a_tmem) hamming_tc6_kernel<true><<<2 * n_units, kTc6Threads, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
-            else hamming_tc6_kernel<false><<<2 * n_units, kTc6Threads, kTc6Smem, ctx->stream>>>(p, n_row_tiles, n_col_st);
-            kt_end(ctx, 0);
-            VDF_LAUNCHED(ctx);
-            return VDF_OK;
-        }
-        if (ctx->search_variant == 5) {  // 1-D grid over exactly the units this rank owns
-            p.n_pairs = n_pairs;
-            VDF_ALLOC(ctx, ctx->unit_cnt.ensure((size_t)(n_pairs + 1) * 4));
-            VDF_ALLOC(ctx, ctx->unit_off.ensure((size_t)(n_pairs + 1) * 4));
-            p.unit_off = ctx->unit_off.as<uint32_t>();
-            tc5_units_kernel<<<(n_pairs + 1 + 255) / 256, 256, 0, ctx->stream>>>(p, n_row_tiles, ctx->unit_cnt.as<uint32_t>());
-            VDF_LAUNCHED(ctx);
-            size_t tmp = 0;
-            VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->unit_cnt.as<uint32_t>(), ctx->unit_off.as<uint32_t>(),
-                                                        (size_t)n_pairs + 1, ctx->stream));
-            VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
-            VDF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tmp, ctx->unit_cnt.as<uint32_t>(),
-                                                        ctx->unit_off.as<uint32_t>(), (size_t)n_pairs + 1, ctx->stream));
-            ctx->launches += 1;
-            uint32_t n_units = 0;
-            VDF_CUDA(ctx, cudaMemcpyAsync(&n_units, ctx->unit_off.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (n_units == 0) return VDF_OK;
-            if (n_units > 0x3FFFFFFFu) {
-                ctx->err = "too many work units for one launch";
-                return VDF_ERR_INVALID;
-            }
-            kt_begin(ctx, 0);
-            hamming_tc5_kernel<<<2 * n_units, kTc5Threads, kTc5Smem, ctx->stream>>>(p, n_row_tiles);
-            kt_end(ctx, 0);
-            VDF_LAUNCHED(ctx);
-            return VDF_OK;
-        }
-        dim3 grid(2 * n_pairs, (n_st + chunk - 1) / chunk);
-        kt_begin(ctx, 0);
-        hamming_tc2_kernel<<<grid, kTcThreads, kTc2Smem, ctx->stream>>>(p, n_row_tiles);
-        kt_end(ctx, 0);
-        VDF_LAUNCHED(ctx);
-        return VDF_OK;
-    }
-    const uint32_t span_st = max_span_tiles / 2 + 2;  // super-tiles a row tile's range can touch
-    uint32_t chunk = 32;
-    while (chunk > 2 && (uint64_t)n_row_tiles * ((span_st + chunk - 1) / chunk) < (uint64_t)ctx->sm_count * 4 * ctx->world)
-        chunk >>= 1;
-    p.chunk = chunk;
-    dim3 grid(n_row_tiles, (span_st + chunk - 1) / chunk);
     kt_begin(ctx, 0);
-    hamming_tc_kernel<<<grid, kTcThreads, kTcSmem, ctx->stream>>>(p);
+    if (pl.variant == 6) {
+        const uint32_t n_col_st = (uint32_t)(((uint64_t)pl.n_col_tiles * kTile + 2 * kT6Cols - 1) / (2 * kT6Cols));
+        const dim3 grid(2 * pl.n_units);
+        if (ctx->tc_a_tmem && pl.fold) hamming_tc6_kernel<true, true><<<grid, kTc6Threads, kTc6Smem, ctx->stream>>>(p, pl.n_row_tiles, n_col_st);
+        else if (ctx->tc_a_tmem) hamming_tc6_kernel<true, false><<<grid, kTc6Threads, kTc6Smem, ctx->stream>>>(p, pl.n_row_tiles, n_col_st);
+        else if (pl.fold) hamming_tc6_kernel<false, true><<<grid, kTc6Threads, kTc6Smem, ctx->stream>>>(p, pl.n_row_tiles, n_col_st);
+        else hamming_tc6_kernel<false, false><<<grid, kTc6Threads, kTc6Smem, ctx->stream>>>(p, pl.n_row_tiles, n_col_st);
+    } else {
+        hamming_tc5_kernel<<<2 * pl.n_units, kTc5Threads, kTc5Smem, ctx->stream>>>(p, pl.n_row_tiles);
+    }
     kt_end(ctx, 0);
     VDF_LAUNCHED(ctx);
     return VDF_OK;

@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 from . import _ffi
 from .definitions import tolerance_to_int
-from .match_group import MatchGroup
+from .match_group import MatchGroup, MatchGroups
 from .video_hash import HashTable, as_table
 
 
@@ -129,16 +129,23 @@ def _run_exchange(ctx: _ffi.Context, fn, device, group):
 def search_self_keys(ctx: _ffi.Context, d_hash, d_dur, tol_int: int, group=None, n: Optional[int] = None,
                      device=None) -> torch.Tensor:
     """This rank's share of the pair matrix and the edge exchange: sorted (i << 32 | j) keys of ALL ranks.
-    d_hash / d_dur: the sorted table resident in HBM, as torch tensors or as raw device pointers (then pass n, device)."""
+    d_hash / d_dur: the sorted table resident in HBM, as torch tensors or as raw device pointers (then pass n, device);
+    or d_hash = a prepared _ffi.Table (`Search::from` done once: nothing is re-packed per call), d_dur ignored, pass device."""
     rank, world = world_info(group)
-    if isinstance(d_hash, torch.Tensor):
+    table = d_hash if isinstance(d_hash, _ffi.Table) else None
+    if table is not None:
+        pass
+    elif isinstance(d_hash, torch.Tensor):
         n, device, p_hash, p_dur = d_dur.numel(), d_hash.device, d_hash.data_ptr(), d_dur.data_ptr()
     else:
         p_hash, p_dur = int(d_hash), int(d_dur)
     fused = world > 1 and ctx.peer_world == world
     ctx.set_shard(rank, world)
     try:
-        run = lambda p, cap: ctx.search_self_device(p_hash, p_dur, n, tol_int, p, cap)  # noqa: E731
+        if table is not None:
+            run = lambda p, cap: table.search_self_device(tol_int, p, cap)  # noqa: E731
+        else:
+            run = lambda p, cap: ctx.search_self_device(p_hash, p_dur, n, tol_int, p, cap)  # noqa: E731
         if fused:
             return _run_exchange(ctx, run, device, group)
         local = _run_growing(run, device)
@@ -147,13 +154,18 @@ def search_self_keys(ctx: _ffi.Context, d_hash, d_dur, tol_int: int, group=None,
     return merge_keys(local, group)
 
 
-def search_refs_keys(ctx: _ffi.Context, d_cand_slice: torch.Tensor, d_cand_dur_slice: torch.Tensor, cand_base: int,
+def search_refs_keys(ctx: _ffi.Context, d_cand_slice, d_cand_dur_slice, cand_base: int,
                      d_refs: torch.Tensor, d_ref_dur: torch.Tensor, tol_int: int, group=None, allow_fused: bool = True) -> torch.Tensor:
-    """allow_fused=False when some rank may hold an empty candidate slice: the fused exchange ends in a barrier that every
-    rank must reach, and the library returns early on empty inputs"""
-    run = lambda p, cap: ctx.search_refs_device(d_cand_slice.data_ptr(), d_cand_dur_slice.data_ptr(),  # noqa: E731
-                                                d_cand_dur_slice.numel(), cand_base, d_refs.data_ptr(), d_ref_dur.data_ptr(),
-                                                d_ref_dur.numel(), tol_int, p, cap)
+    """This rank's slice of the sorted candidate table against all references: sorted (ref << 32 | cand) keys of ALL ranks.
+    d_cand_slice: a tensor (with d_cand_dur_slice) or a prepared _ffi.Table of the slice.  With the exchange on, every rank
+    reaches its closing barrier even when its slice is empty."""
+    if isinstance(d_cand_slice, _ffi.Table):
+        run = lambda p, cap: d_cand_slice.search_refs_device(cand_base, d_refs.data_ptr(), d_ref_dur.data_ptr(),  # noqa: E731
+                                                             d_ref_dur.numel(), tol_int, p, cap)
+    else:
+        run = lambda p, cap: ctx.search_refs_device(d_cand_slice.data_ptr(), d_cand_dur_slice.data_ptr(),  # noqa: E731
+                                                    d_cand_dur_slice.numel(), cand_base, d_refs.data_ptr(), d_ref_dur.data_ptr(),
+                                                    d_ref_dur.numel(), tol_int, p, cap)
     world = world_info(group)[1]
     if allow_fused and world > 1 and ctx.peer_world == world:
         return _run_exchange(ctx, run, d_refs.device, group)
@@ -174,58 +186,70 @@ def _to_dev(a: np.ndarray, device) -> torch.Tensor:
     return t.to(device, non_blocking=False)
 
 
-def search(hashes, tolerance: float, ctx: Optional[_ffi.Context] = None, group=None) -> List[MatchGroup]:
+def search(hashes, tolerance: float, ctx: Optional[_ffi.Context] = None, group=None) -> MatchGroups:
     """`search` (video_dup_finder.rs:7-13) over all ranks of the process group; every rank gets the full result."""
     ctx = ctx or _ffi.default_context()
     table = as_table(hashes)
     n = len(table)
     if n == 0:
-        return []
-    if world_info(group)[1] == 1:  # one GPU: the whole function is one C-ABI call (vdf_search)
+        return MatchGroup.from_csr([], [0], [])
+    if world_info(group)[1] == 1:  # one process: the whole function is one C-ABI call (vdf_search; also a multi-device context)
         from .search import search as search_one
 
         return search_one(table, tolerance, ctx)
     dev = torch.device("cuda", ctx.device)
-    # Rank 0 does the native host side of vdf_search (multi-threaded (duration, Path) sort, gather through pinned memory,
-    # upload) and broadcasts the sorted table and the permutation over NVLink: eight ranks sorting the same million paths on
-    # the same host cores would take longer than the whole device side.
+    # Rank 0 does the host side of vdf_search once (sort keys cut by host threads, radix sort on its GPU, the hashes through
+    # pinned memory) and broadcasts the sorted table and the permutation over NVLink; all ranks then search their shares.
+    # Nothing else is serial: groups come back as a CSR of the caller's indices and become objects when looked at.
     rank = world_info(group)[0]
     with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)):
         d_hash = torch.empty((n, 16), dtype=torch.int64, device=dev)
         d_dur = torch.empty(n, dtype=torch.int32, device=dev)
-        d_order = torch.empty(n, dtype=torch.int64, device=dev)
+        d_order = torch.empty(n, dtype=torch.int32, device=dev)
         if rank == 0:
             order, _, _ = ctx.stage_sorted(table.hashes, table.durations, *table.path_blob(), d_hash_dst=d_hash.data_ptr(),
+                                           d_dur_dst=d_dur.data_ptr())
+            d_order.copy_(torch.from_numpy(order.astype(np.int32)), non_blocking=False)
+        dist.broadcast(d_hash, 0, group=group)
+        dist.broadcast(d_dur, 0, group=group)
+        dist.broadcast(d_order, 0, group=group)
+        keys = search_self_keys(ctx, d_hash, d_dur, tolerance_to_int(tolerance), group)
+        torch.cuda.current_stream().synchronize()
+        # sorted positions -> the caller's indices on the device, as the CSR is written
+        gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel(), d_remap=d_order.data_ptr())
+    return MatchGroup.from_csr(table.paths, gp, mm)
+
+
+def search_with_references(ref_hashes, new_hashes, tolerance: float, ctx: Optional[_ffi.Context] = None,
+                           group=None) -> MatchGroups:
+    """`search_with_references` (video_dup_finder.rs:19-46) with the sorted candidate table sliced over the ranks."""
+    ctx = ctx or _ffi.default_context()
+    refs, cands = as_table(ref_hashes), as_table(new_hashes)
+    if len(refs) == 0 or len(cands) == 0:
+        return MatchGroup.from_csr([], [0], [])
+    rank, world = world_info(group)
+    if world == 1:
+        from .search import search_with_references as one
+
+        return one(refs, cands, tolerance, ctx)
+    dev = torch.device("cuda", ctx.device)
+    n = len(cands)
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)):
+        d_hash = torch.empty((n, 16), dtype=torch.int64, device=dev)
+        d_dur = torch.empty(n, dtype=torch.int32, device=dev)
+        d_order = torch.empty(n, dtype=torch.int64, device=dev)
+        if rank == 0:  # Search::from(new_hashes) once, on rank 0's GPU; the sorted table travels over NVLink
+            order, _, _ = ctx.stage_sorted(cands.hashes, cands.durations, *cands.path_blob(), d_hash_dst=d_hash.data_ptr(),
                                            d_dur_dst=d_dur.data_ptr())
             d_order.copy_(torch.from_numpy(order), non_blocking=False)
         dist.broadcast(d_hash, 0, group=group)
         dist.broadcast(d_dur, 0, group=group)
         dist.broadcast(d_order, 0, group=group)
-        keys = search_self_keys(ctx, d_hash, d_dur, tolerance_to_int(tolerance), group)
-        if rank != 0:
-            order = d_order.cpu().numpy()
-        torch.cuda.current_stream().synchronize()
-        gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
-    return MatchGroup.from_csr(table.paths, gp, order[mm.astype(np.int64)])
-
-
-def search_with_references(ref_hashes, new_hashes, tolerance: float, ctx: Optional[_ffi.Context] = None,
-                           group=None) -> List[MatchGroup]:
-    """`search_with_references` (video_dup_finder.rs:19-46) with the sorted candidate table sliced over the ranks."""
-    ctx = ctx or _ffi.default_context()
-    refs, cands = as_table(ref_hashes), as_table(new_hashes)
-    if len(refs) == 0 or len(cands) == 0:
-        return []
-    rank, world = world_info(group)
-    dev = torch.device("cuda", ctx.device)
-    order = _ffi.sort_order(cands.durations, *cands.path_blob())
-    b, e = shard_range(len(cands), rank, world)
-    sl = order[b:e]
-    d_c = _to_dev(np.ascontiguousarray(cands.hashes[sl]).reshape(-1, 16), dev)
-    d_cd = _to_dev(np.ascontiguousarray(cands.durations[sl]), dev)
-    d_r = _to_dev(refs.hashes, dev)
-    d_rd = _to_dev(refs.durations, dev)
-    keys = search_refs_keys(ctx, d_c, d_cd, b, d_r, d_rd, tolerance_to_int(tolerance), group, allow_fused=len(cands) >= world)
+        b, e = shard_range(n, rank, world)
+        d_r = _to_dev(refs.hashes, dev)
+        d_rd = _to_dev(refs.durations, dev)
+        keys = search_refs_keys(ctx, d_hash[b:e], d_dur[b:e], b, d_r, d_rd, tolerance_to_int(tolerance), group)
+        order = d_order.cpu().numpy()
     rp, ci = csr_from_keys(keys.cpu().numpy(), len(refs))
     return MatchGroup.from_csr(cands.paths, rp, order[ci.astype(np.int64)], references=refs.paths)
 

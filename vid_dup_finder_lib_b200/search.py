@@ -9,7 +9,7 @@ from typing import Iterable, List, Optional
 import numpy as np
 
 from . import _ffi
-from .match_group import MatchGroup
+from .match_group import MatchGroup, MatchGroups
 from .video_hash import HashTable, VideoHash, as_table
 
 
@@ -20,24 +20,24 @@ def search_indices(table: HashTable, tolerance: float, ctx: Optional[_ffi.Contex
     return ctx.search(table.hashes, table.durations, blob, off, tolerance)
 
 
-def search(hashes: Iterable[VideoHash] | HashTable, tolerance: float, ctx: Optional[_ffi.Context] = None) -> List[MatchGroup]:
+def search(hashes: Iterable[VideoHash] | HashTable, tolerance: float, ctx: Optional[_ffi.Context] = None) -> MatchGroups:
     """video_dup_finder.rs:7-13.  Every video is matched at most once; each group lists its matches in sorted
     order followed by the group's target (search_algorithm.rs:158-161), groups in the reference's order."""
     table = as_table(hashes)
     if len(table) == 0:  # search_algorithm.rs:88-90
-        return []
+        return MatchGroup.from_csr([], [0], [])
     gp, mm = search_indices(table, tolerance, ctx)
     return MatchGroup.from_csr(table.paths, gp, mm)  # MatchGroup::new(x).ok(), video_dup_finder.rs:11
 
 
 def search_with_references(ref_hashes: Iterable[VideoHash] | HashTable, new_hashes: Iterable[VideoHash] | HashTable,
-                           tolerance: float, ctx: Optional[_ffi.Context] = None) -> List[MatchGroup]:
+                           tolerance: float, ctx: Optional[_ffi.Context] = None) -> MatchGroups:
     """video_dup_finder.rs:19-46: one group per reference (in caller order) that matched at least one entry of
     new_hashes inside its duration slice; an entry may appear under many references (consume = false)."""
     ctx = ctx or _ffi.default_context()
     refs, cands = as_table(ref_hashes), as_table(new_hashes)
     if len(refs) == 0 or len(cands) == 0:
-        return []
+        return MatchGroup.from_csr([], [0], [])
     blob, off = cands.path_blob()
     rp, ci = ctx.search_with_references(refs.hashes, refs.durations, cands.hashes, cands.durations, blob, off, tolerance)
     return MatchGroup.from_csr(cands.paths, rp, ci, references=refs.paths)  # video_dup_finder.rs:38-43

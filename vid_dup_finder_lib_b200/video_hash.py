@@ -118,8 +118,8 @@ def path_components(p: str):
 
 def _is_simple(b: bytes) -> bool:
     # no empty / '.' / '..' components and no trailing slash: component order == byte order with '/' lowest
-    if b.endswith(b"/") and len(b) > 1:
-        return False
+    if b.endswith(b"/"):  # a trailing separator is dropped, and "/" alone is the root component (Rust: "" < "/"), while numpy's
+        return False      # bytes_ comparison ignores trailing NULs and would tie it with the empty path
     return not (b"//" in b or b"/./" in b or b"/../" in b or b.startswith((b"./", b"../")) or b.endswith((b"/.", b"/.."))
                 or b in (b".", b".."))
 
