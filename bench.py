@@ -35,22 +35,32 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="search", choices=["search", "hash", "refs"])
+    ap.add_argument("--workload", default="search", choices=["search", "hash", "refs", "e2e10m", "popc"])
     ap.add_argument("--n-query", type=int, default=100_000)
     ap.add_argument("--n-corpus", type=int, default=10_000_000)
+    ap.add_argument("--n-e2e", type=int, default=10_000_000, help="hashes of the end-to-end dedup pipeline (BASELINE configs[4])")
+    ap.add_argument("--n-popc", type=int, default=262_144, help="hashes of the XOR+POPC line (secondary_popc)")
     ap.add_argument("--n-hashes", "--n", dest="n", type=int, default=1_000_000, help="hashes in the all-pairs search")
     ap.add_argument("--tol", type=float, default=0.35)
+    ap.add_argument("--tol-sweep", default="0.0,0.1,0.2,0.3,0.35,0.4,0.42", help="comma-separated tolerances of the sweep ('' = none)")
     ap.add_argument("--variant", type=int, default=-1, help="search kernel variant (-1: library default)")
-    ap.add_argument("--hash-variant", type=int, default=-1, help="resize kernel: 0 IMMA 8 warps, 1 general, 2 IMMA 4 warps")
+    ap.add_argument("--hash-variant", type=int, default=-1, help="resize kernel: 0 IMMA 4 warps, 1 general, 2 IMMA 8 warps")
     ap.add_argument("--stacks", type=int, default=256, help="1080p stacks resident in HBM per GPU (8.5 GB at 256)")
+    ap.add_argument("--hash-total", type=int, default=100_000, help="stack-hashes per hashing run (BASELINE configs[1]: 100 k stacks)")
+    ap.add_argument("--mismatch-stacks", type=int, default=1024, help="stacks compared bit by bit with the CPU oracle")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU edge exchange: fused into the pair kernel over NVLink peer memory, or an NCCL all-gather")
+    ap.add_argument("--plane", default="both", choices=["torch", "c", "both"],
+                    help="N > 1: one process per GPU over torch.distributed, the in-library plane (rank 0 drives all GPUs through one "
+                         "vdf_ctx_create_multi context, reported as e2e_cplane), or both")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT", help="extra vdf_ctx_set_option (kernel experiments)")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--secondary", default="hash,popc,refs,e2e10m", help="secondary records attached to the search line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--parity-rows", type=int, default=96, help="rows brute-forced by the CPU oracle (untimed) per search record")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -221,9 +231,62 @@ def popc_peak_gpopc(sm_count: int, sm_max_mhz: float):
     return sm_count * 16 * sm_max_mhz * 1e6 / 1e9, "documented 16 POPC/clk/SM x SMs x max SM clock"
 
 
+# ------------------------------------------------------------------------------------------------ shared by both arms
+def workload_name(kind: str, args) -> str:
+    """config.workload, identical in our arm and in the reference arm"""
+    if kind == "search":
+        return f"all-pairs search (find_all_matches), {args.n} synthetic hashes, equal durations, tolerance {args.tol}"
+    if kind == "popc":
+        return f"all-pairs search (find_all_matches), {args.n_popc} synthetic hashes, equal durations, tolerance {args.tol}"
+    if kind == "refs":
+        return (f"search_with_references, {args.n_query} queries x {args.n_corpus} sorted table entries, equal durations, "
+                f"tolerance {args.tol}")
+    if kind == "e2e10m":
+        return (f"end-to-end dedup, {args.n_e2e} frame stacks ({args.width}x{args.height}x16 u8, letterbox cropdetect) -> hashes -> "
+                f"all-pairs search -> MatchGroups, tolerance {args.tol}")
+    return f"frame-stack hashing, {args.width}x{args.height}x16 u8 stacks resident in HBM, letterbox cropdetect"
+
+
+def digest(*arrays) -> str:
+    """one short hex string over result arrays (sorted edge keys, group CSR, ...): equal at every GPU count or the runs differ"""
+    import hashlib
+
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.shape).encode())
+        h.update(a.view(np.uint8).reshape(-1).data)
+    return h.hexdigest()[:16]
+
+
+class FixedWidthPaths:
+    """"v/%08d" % (start + perm[i]) for i in range(n) without ten million str objects: a sequence for MatchGroups plus the
+    (blob, offsets) the C ABI takes"""
+
+    def __init__(self, ids: np.ndarray):
+        self.ids = np.asarray(ids, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __getitem__(self, i):
+        return "v/%08d" % int(self.ids[i])
+
+    def blob(self):
+        n = len(self.ids)
+        b = np.empty((n, 10), dtype=np.uint8)
+        b[:, 0], b[:, 1] = ord("v"), ord("/")
+        v = self.ids.copy()
+        for k in range(8):
+            b[:, 9 - k] = ord("0") + (v % 10)
+            v //= 10
+        return b.reshape(-1), np.arange(n + 1, dtype=np.uint64) * np.uint64(10)
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
-    """The reference's own CPU implementation of the path = the oracle port (the reference is Rust; no cargo here).
+    """The reference's own CPU implementation of the path = the oracle port (the reference is Rust; no cargo here), on a
+    bounded SAMPLE of our arm's workload (same config.workload string; `sample` says what was timed).
     search: Search::search_self's inner loop is single-threaded (no rayon in vid_dup_finder_lib) -> 1 thread;
     hash:   the app hashes files on a rayon pool -> all host cores."""
     from oracle import vdf_oracle as o
@@ -233,8 +296,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    if args.workload == "search":
-        n = args.n
+    kind = args.workload
+    if kind in ("search", "popc"):
+        n = args.n if kind == "search" else args.n_popc
         H, _ = synth.planted_hashes(n)
         dur = np.full(n, 600, np.uint32)
         tol = o.tolerance_int(args.tol)
@@ -246,17 +310,11 @@ def run_reference(args):
             o.search_refs(H, dur, H[rows], dur[rows], tol)
             return rows_per_step * n
 
-        for _ in range(min(args.warmup, 1)):
-            step()
-        t0 = time.perf_counter()
-        units = sum(step() for _ in range(args.steps))
-        dt = time.perf_counter() - t0
         metric, unit, used = "hamming_pair_comparisons_per_s", "pairs/s", 1
-        sample = f"{rows_per_step} random rows x {n} candidates per step (same table, tol {tol}), 1 thread"
-        config = {"workload": f"all-pairs search, {n} synthetic hashes, equal durations, tolerance {args.tol}"}
-    elif args.workload == "refs":
+        sample = f"sampled: {rows_per_step} random rows x {n} candidates per step (same table, tol {tol}), 1 thread"
+    elif kind == "refs":
         # search_with_references: every query walks its whole duration slice of the sorted table (search_algorithm.rs:40-53)
-        nq, nc = args.n_query, args.n_corpus
+        nc = args.n_corpus
         n_tab = min(nc, 1_000_000)  # a bounded slice of the table: the cost per (query, entry) pair does not depend on its length
         H, _ = synth.planted_hashes(n_tab)
         dur = np.full(n_tab, 600, np.uint32)
@@ -268,17 +326,12 @@ def run_reference(args):
             o.search_refs(H, dur, Q, qd, tol)
             return len(Q) * n_tab
 
-        for _ in range(min(args.warmup, 1)):
-            step()
-        t0 = time.perf_counter()
-        units = sum(step() for _ in range(args.steps))
-        dt = time.perf_counter() - t0
         metric, unit, used = "hamming_pair_comparisons_per_s", "pairs/s", 1
-        sample = f"{len(Q)} queries x {n_tab} table entries per step (tol {tol}), 1 thread"
-        config = {"workload": f"search_with_references, {nq} queries x {nc} sorted table entries, equal durations, tolerance {args.tol}"}
-    else:
+        sample = f"sampled: {len(Q)} queries x {n_tab} table entries per step (tol {tol}), 1 thread"
+    else:  # hash (and the hashing half of e2e10m, which the reference arm does not extrapolate)
         from concurrent.futures import ThreadPoolExecutor
 
+        kind = "hash" if kind != "e2e10m" else kind
         per = max(cores, 8)
         st = synth.frame_stacks(per, args.width, args.height).numpy()
 
@@ -290,19 +343,18 @@ def run_reference(args):
                 list(ex.map(one, range(per)))
             return per
 
-        for _ in range(min(args.warmup, 1)):
-            step()
-        t0 = time.perf_counter()
-        units = sum(step() for _ in range(args.steps))
-        dt = time.perf_counter() - t0
         metric, unit, used = "frame_stacks_hashed_per_s", "stacks/s", cores
-        sample = f"{per} synthetic {args.width}x{args.height} stacks per step, {cores} threads"
-        config = {"workload": f"frame-stack hashing, {args.width}x{args.height}x16 u8 stacks, letterbox cropdetect"}
+        sample = f"sampled: {per} synthetic {args.width}x{args.height} stacks per step, {cores} threads"
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    units = sum(step() for _ in range(args.steps))
+    dt = time.perf_counter() - t0
     v = units / dt
     emit({
         "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": {"workload": workload_name(kind, args), "sampled": sample},
         "cpu_baseline": {"value": v, "unit": unit, "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -342,8 +394,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")  # host-side barriers while rank 0 drives every GPU (--plane c)
     ctx = _ffi.default_context()
     if args.variant >= 0:
         ctx.set_option("search_variant", args.variant)
@@ -354,7 +408,7 @@ def main():
         ctx.set_option(k, int(v))
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    fused = world > 1 and args.exchange == "peer" and args.workload in ("search", "refs") and (args.variant in (-1, 6))
+    fused = world > 1 and args.exchange == "peer" and (args.variant in (-1, 6))
     if fused:
         try:
             vdist.enable_peer_exchange(ctx, capacity=1 << 22)
@@ -366,6 +420,8 @@ def main():
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    variant = args.variant if args.variant >= 0 else DEFAULT_SEARCH_VARIANT
+    dtype_of = lambda v: "e2m1 x e2m1 -> f32 (exact)" if v == 6 else "u8 x u8 -> s32" if v >= 3 else "u32"  # noqa: E731
 
     def barrier():
         torch.cuda.synchronize()
@@ -382,7 +438,8 @@ def main():
 
     def timed(step, steps, warmup, flush_l2):
         """W warm-up steps, then K steps between two CUDA events on the kernels' stream, barrier + synchronize on
-        both sides, max over ranks.  -> seconds"""
+        both sides, max over ranks.  -> seconds.  The L2 flush (a 512 MiB fill, ~0.15 ms) sits INSIDE the timed region:
+        the reported time is conservative by that much per step."""
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 step()
@@ -392,71 +449,109 @@ def main():
             gc.disable()  # a generation-2 collection between two launches would show up as GPU idle time
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            w0 = time.perf_counter()
             e0.record(stream)
-            dbg_t = []
             for _ in range(steps):
                 if flush_l2:
-                    t_a = time.perf_counter()
                     flush.fill_(1)
-                    t_b = time.perf_counter()
-                    if os.environ.get("VDF_BENCH_DEBUG"):
-                        stream.synchronize()
-                        dbg_t.append((1e3 * (t_b - t_a), 1e3 * (time.perf_counter() - t_b)))
                 step()
             e1.record(stream)
-            w1 = time.perf_counter()
             barrier()
             gc.enable()
-        if os.environ.get("VDF_BENCH_DEBUG"):
-            print("[timed] flush (launch ms, gpu ms):", [(round(a, 2), round(b, 2)) for a, b in dbg_t], file=sys.stderr)
-            print(f"[timed] events {e0.elapsed_time(e1):.1f} ms, host wall {1e3 * (w1 - w0):.1f} ms, barrier {1e3 * (time.perf_counter() - w1):.1f} ms",
-                  file=sys.stderr)
         return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
+    def parity_rows_self(H, dur, keys_np, tol_int, k_rows, seed=9):
+        """K random rows of the pair matrix brute-forced by the CPU oracle against the edges the GPU returned (untimed)"""
+        from oracle import vdf_oracle as o
+
+        n = len(dur)
+        rows = np.unique(np.random.default_rng(seed).integers(0, n, k_rows))
+        rp, ci = o.search_refs(H, dur, H[rows], dur[rows], tol_int)
+        ki, kj = (keys_np >> np.uint64(32)).astype(np.int64), (keys_np & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        bad = 0
+        for k, r in enumerate(rows.tolist()):
+            want = set(int(c) for c in ci[rp[k]:rp[k + 1]] if c != r)
+            got = set(kj[ki == r].tolist()) | set(ki[kj == r].tolist())
+            bad += got != want
+        return {"rows": int(len(rows)), "candidates_per_row": int(n), "mismatching_rows": int(bad), "ok": bad == 0,
+                "how": "oracle brute force of sampled rows vs the GPU's edge list, untimed"}
+
     # ---------------------------------------------------------------- search workload
-    def bench_search(steps, warmup):
-        n, tol_int = args.n, tolerance_to_int(args.tol)
+    def bench_search(steps, warmup, n=None, use_variant=None, light=False):
+        """all-pairs search on a resident, prepared table (`Search::from` done once, `search_self` per step).
+        light: the XOR+POPC line (no e2e, no sweep)."""
+        n = n or args.n
+        tol_int = tolerance_to_int(args.tol)
+        v = variant if use_variant is None else use_variant
+        if use_variant is not None:
+            ctx.set_option("search_variant", use_variant)
+        use_exchange = fused and v == 6
         H, _ = synth.planted_hashes(n)
         dur = np.full(n, 600, np.uint32)
-        paths = synth.paths(n)
-        table = vdf.HashTable(H, dur, paths)
         pairs = n * (n - 1) // 2
         with torch.cuda.stream(stream):
             d_hash = torch.from_numpy(H.view(np.int64)).to(dev)
             d_dur = torch.from_numpy(dur.view(np.int32)).to(dev)
-        result = {}
-
-        dbg = os.environ.get("VDF_BENCH_DEBUG")
-
-        def step():
-            t0 = time.perf_counter()
-            keys = vdist.search_self_keys(ctx, d_hash, d_dur, tol_int)
-            t1 = time.perf_counter()
             torch.cuda.current_stream().synchronize()
-            t2 = time.perf_counter()
-            gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
-            t3 = time.perf_counter()
-            result["edges"], result["groups"] = int(keys.numel()), len(gp) - 1
-            if dbg:
-                print(f"[step] keys {1e3 * (t1 - t0):.1f} ms, sync {1e3 * (t2 - t1):.1f} ms, group {1e3 * (t3 - t2):.1f} ms", file=sys.stderr)
+            tbl = ctx.table_create_device(d_hash.data_ptr(), d_dur.data_ptr(), n, keepalive=(d_hash, d_dur))
+        result = {}
+        saved_world = ctx.peer_world
+        if not use_exchange:
+            ctx.peer_world = 0  # search_self_keys then merges with the NCCL all-gather
 
-        with ClockSampler(local) as cs:
-            with torch.cuda.stream(stream):
-                for _ in range(warmup):
-                    step()
-            ctx.kernel_time(0, reset=True)
-            l0 = ctx.counters()[0]
-            secs = timed(step, steps, 0, True)
-        launches = ctx.counters()[0] - l0
-        k_ms, k_n = ctx.kernel_time(0, reset=True)
-        value = pairs * steps / secs
-        # roofline of the dominant kernel: this rank's share of the pairs per launch
-        variant = args.variant if args.variant >= 0 else DEFAULT_SEARCH_VARIANT
-        roof = search_roofline(variant, pairs / world, k_ms, k_n, sm_count, sm_max_mhz, n_key=f"self_{n}_x{world}")
-        # e2e: host arrays -> public API (sort, H2D, kernels, D2H, MatchGroups)
-        e_steps = max(1, min(args.e2e_steps, steps))
-        # the caller's order is arbitrary: a fixed shuffle of the table, so that the host-side (duration, Path) sort has real work
+        def step(t=tol_int):
+            keys = vdist.search_self_keys(ctx, tbl, None, t, device=dev)
+            torch.cuda.current_stream().synchronize()
+            gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel())
+            result["keys"], result["gp"], result["mm"] = keys, gp, mm
+
+        try:
+            with ClockSampler(local) as cs:
+                with torch.cuda.stream(stream):
+                    for _ in range(warmup):
+                        step()
+                ctx.kernel_time(0, reset=True)
+                l0 = ctx.counters()[0]
+                secs = timed(step, steps, 0, True)
+            launches = ctx.counters()[0] - l0
+            k_ms, k_n = ctx.kernel_time(0, reset=True)
+            value = pairs * steps / secs
+            roof = search_roofline(v, pairs / world, k_ms, k_n, sm_count, sm_max_mhz, n_key=f"self_{n}_x{world}")
+            keys_np = result["keys"].cpu().numpy().view(np.uint64)
+            out = {"metric": "hamming_pair_comparisons_per_s", "value": value, "unit": "pairs/s", "ms_per_step": secs / steps * 1e3,
+                   "scaling": "strong", "dtype": dtype_of(v), "roofline": roof, "gpu_launches": int(launches), "clocks": cs.summary(),
+                   "result_digest": digest(keys_np, result["gp"], result["mm"]),
+                   "config": {"workload": workload_name("search" if n == args.n else "popc", args), "n_hashes": n, "tol_int": tol_int,
+                              "pairs_per_step": pairs, "edges": int(len(keys_np)), "groups": int(len(result["gp"]) - 1),
+                              "parallelism": f"tile-block shard x{world}", "exchange": exchange_note if v == 6 else "NCCL all-gather" if world > 1 else "single GPU",
+                              "table": "prepared once (vdf_table: packed tiles, windows, work units), searched per step",
+                              "l2": "512 MiB write between timed steps, inside the timed region (hash table 128 MB ~ L2 126 MB)",
+                              "search_variant": v}}
+            if rank == 0 and not args.no_cpu_baseline and args.parity_rows > 0:
+                out["parity_sample"] = parity_rows_self(H, dur, keys_np, tol_int, args.parity_rows if not light else min(args.parity_rows, 32))
+            if light:
+                return out
+            # ---- tolerance sweep (BASELINE configs[2] is a sweep): one warm + two timed steps per tolerance
+            sweep = []
+            for ts in [x for x in args.tol_sweep.split(",") if x.strip()]:
+                t_int = tolerance_to_int(float(ts))
+                with torch.cuda.stream(stream):
+                    step(t_int)
+                ctx.kernel_time(0, reset=True)
+                s_secs = timed(lambda: step(t_int), 2, 0, True)
+                sk_ms, sk_n = ctx.kernel_time(0, reset=True)
+                r = search_roofline(v, pairs / world, sk_ms, sk_n, sm_count, sm_max_mhz)
+                sweep.append({"tolerance": float(ts), "ms_per_step": s_secs / 2 * 1e3, "kernel_ms": r["kernel_ms_per_launch"],
+                              "frac": r["frac"], "edges": int(result["keys"].numel()), "groups": int(len(result["gp"]) - 1)})
+            out["tol_sweep"] = sweep
+        finally:
+            ctx.peer_world = saved_world
+            if use_variant is not None:
+                ctx.set_option("search_variant", variant)
+            tbl.close()
+        # ---- e2e: host arrays -> public API (keys cut + GPU sort, H2D, kernels, D2H) -> MatchGroups
+        e_steps = max(1, args.e2e_steps)
+        # the caller's order is arbitrary: a fixed shuffle of the table, so that the (duration, Path) sort has real work
+        paths = synth.paths(n)
         perm = np.random.default_rng(7).permutation(n)
         table = vdf.HashTable(np.ascontiguousarray(H[perm]), dur[perm], [paths[i] for i in perm.tolist()])
         table.path_blob()  # the table owns its struct-of-arrays buffers (hashes, durations, path blob) before the call
@@ -469,25 +564,42 @@ def main():
         barrier()
         e_secs = max_over_ranks(time.perf_counter() - t0)
         c1 = ctx.counters()
-        e2e = {"value": pairs * e_steps / e_secs, "unit": "pairs/s", "h2d_bytes_per_step": int((c1[1] - c0[1]) // e_steps) if world == 1 else int(H.nbytes + dur.nbytes),  # per rank
-               "d2h_bytes_per_step": int((c1[2] - c0[2]) // e_steps), "steps": e_steps, "groups": len(groups),
-               "ms_per_call": e_secs / e_steps * 1e3,
-               "api": "vid_dup_finder_lib_b200.dist.search(HashTable, tolerance) -> [MatchGroup]",
-               "input_order": "shuffled (fixed permutation of the synthetic table)"}
-        if world == 1:
-            ph = ctx.last_phases()
-            e2e["phases_ms_last_call"] = {"host_sort": ph[0], "gather_and_h2d_enqueue": ph[1], "device_incl_d2h": ph[2],
-                                          "index_remap": ph[3], "note": "inside vdf_search (csrc/host.cu); the rest of the "
-                                          "call is building the MatchGroup objects"}
-        out = {"metric": "hamming_pair_comparisons_per_s", "value": value, "unit": "pairs/s", "ms_per_step": secs / steps * 1e3,
-               "scaling": "strong", "dtype": "e2m1 x e2m1 -> f32 (exact)" if variant == 6 else "u8 x u8 -> s32" if variant >= 3 else "u32", "roofline": roof, "e2e": e2e,
-               "gpu_launches": int(launches),
-               "clocks": cs.summary(),
-               "config": {"workload": f"all-pairs search (find_all_matches), {n} synthetic hashes, equal durations, "
-                                      f"tolerance {args.tol}", "n_hashes": n, "tol_int": tol_int, "pairs_per_step": pairs,
-                          "edges": result.get("edges"), "groups": result.get("groups"), "parallelism": f"tile-block shard x{world}", "exchange": exchange_note,
-                          "l2": "512 MiB write between timed steps (hash table 128 MB ~ L2 126 MB)",
-                          "search_variant": variant}}
+        ph = ctx.last_phases()
+        t0 = time.perf_counter()
+        n_members = sum(g.len() for g in groups)  # every MatchGroup object, with its path strings, built once
+        mat_ms = (time.perf_counter() - t0) * 1e3
+        h2d = torch.tensor([c1[1] - c0[1], c1[2] - c0[2]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(h2d, op=dist.ReduceOp.MAX)  # rank 0 stages the table; the others receive it over NVLink
+        out["e2e"] = {"value": pairs * e_steps / e_secs, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d[0].item() // e_steps),
+                      "d2h_bytes_per_step": int(h2d[1].item() // e_steps), "steps": e_steps, "groups": len(groups), "ms_per_call": e_secs / e_steps * 1e3,
+                      "api": "vid_dup_finder_lib_b200.dist.search(HashTable, tolerance) -> MatchGroups (lazy: objects are built on access)",
+                      "input_order": "shuffled (fixed permutation of the synthetic table)",
+                      "phases_ms_last_call": {"sort_keys_host": ph[0], "pinned_copy_h2d_gpu_sort": ph[1], "device_incl_d2h": ph[2],
+                                              "note": "rank 0's vdf_search / vdf_stage_sorted (csrc/host.cu); at N > 1 the search itself follows the broadcast"},
+                      "materialize_all_groups_ms": mat_ms, "members": int(n_members),
+                      "result_digest": digest(*groups.csr)}
+        # ---- the same call through ONE multi-device context: rank 0 drives all GPUs, the other ranks sit at a host barrier
+        if world > 1 and args.plane in ("c", "both"):
+            barrier()
+            cp = None
+            if rank == 0:
+                try:
+                    m = _ffi.Context(list(range(world)))
+                    vdf.search(table, args.tol, ctx=m)
+                    t0 = time.perf_counter()
+                    for _ in range(e_steps):
+                        g2 = vdf.search(table, args.tol, ctx=m)
+                    dt = time.perf_counter() - t0
+                    cp = {"value": pairs * e_steps / dt, "unit": "pairs/s", "ms_per_call": dt / e_steps * 1e3, "groups": len(g2),
+                          "result_digest": digest(*g2.csr), "devices": m.device_count,
+                          "api": "vdf_search on a vdf_ctx_create_multi context: one process, one C call, all GPUs"}
+                    m.close()
+                except Exception as e:
+                    cp = {"error": repr(e)}
+            dist.barrier(group=cpu_group)
+            if cp is not None:
+                out["e2e_cplane"] = cp
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from oracle import vdf_oracle as o
 
@@ -504,27 +616,28 @@ def main():
     # ---------------------------------------------------------------- query-vs-reference workload (BASELINE configs[3])
     def bench_refs(steps, warmup):
         """search_with_references: --n-query hashes against a sorted table of --n-corpus hashes whose contiguous slices
-        are spread over the ranks (each rank: all queries x its slice); keys are all-gathered and merged."""
+        are spread over the ranks (each rank: all queries x its prepared slice); keys reach every rank through the exchange."""
         nq, nc, tol_int = args.n_query, args.n_corpus, tolerance_to_int(args.tol)
-        corpus, _ = synth.planted_hashes(nc)
-        rng = np.random.default_rng(7)
-        queries = synth.random_hashes(nq, seed=synth.SEED + 1)
-        hit = rng.integers(0, nq, nq // 20)  # 5 % of the queries are perturbed copies of corpus entries
-        flips = np.packbits(rng.integers(0, 1024, (len(hit), 1024)) < 100, axis=1, bitorder="little").view(np.uint64)
-        queries[hit] = corpus[rng.integers(0, nc, len(hit))] ^ flips
-        cdur = np.full(nc, 600, np.uint32)
-        qdur = np.full(nq, 600, np.uint32)
-        b, e = vdist.shard_range(nc, rank, world)
         with torch.cuda.stream(stream):
-            d_c = torch.from_numpy(corpus[b:e].view(np.int64)).to(dev)
-            d_cd = torch.from_numpy(cdur[b:e].view(np.int32)).to(dev)
-            d_q = torch.from_numpy(queries.view(np.int64)).to(dev)
-            d_qd = torch.from_numpy(qdur.view(np.int32)).to(dev)
+            corpus, _ = synth.planted_hashes_torch(nc, device=dev)
+            d_q, _ = synth.planted_hashes_torch(nq, seed=synth.SEED + 1, device=dev, dup_frac_den=1 << 40)  # random queries ...
+            hit = torch.arange(0, nq, 20, device=dev)  # ... 5 % of them perturbed copies of corpus entries
+            pick = (synth._t_stream(synth.SEED + 2, hit, 0) & 0x7FFFFFFFFFFFFFFF) % nc
+            flip = synth._t_stream(synth.SEED + 2, hit[:, None] * 16 + torch.arange(16, device=dev)[None, :], 1)
+            flip = flip & synth._t_stream(synth.SEED + 2, hit[:, None] * 16 + torch.arange(16, device=dev)[None, :], 2)
+            flip = flip & synth._t_stream(synth.SEED + 2, hit[:, None] * 16 + torch.arange(16, device=dev)[None, :], 3)
+            flip[:, 15] &= (1 << 40) - 1
+            d_q[hit] = corpus[pick] ^ flip
+            d_cd = torch.full((nc,), 600, dtype=torch.int32, device=dev)
+            d_qd = torch.full((nq,), 600, dtype=torch.int32, device=dev)
+            b, e = vdist.shard_range(nc, rank, world)
+            d_c = corpus[b:e].contiguous()
+            torch.cuda.current_stream().synchronize()
+            tbl = ctx.table_create_device(d_c.data_ptr(), d_cd[b:e].data_ptr(), e - b, keepalive=(d_c, d_cd))
         result = {}
 
         def step():
-            keys = vdist.search_refs_keys(ctx, d_c, d_cd, b, d_q, d_qd, tol_int)
-            result["matches"] = int(keys.numel())
+            result["keys"] = vdist.search_refs_keys(ctx, tbl, None, b, d_q, d_qd, tol_int)
 
         with ClockSampler(local) as cs:
             with torch.cuda.stream(stream):
@@ -536,27 +649,155 @@ def main():
         launches = ctx.counters()[0] - l0
         k_ms, k_n = ctx.kernel_time(0, reset=True)
         pairs = nq * nc
-        variant = args.variant if args.variant >= 0 else DEFAULT_SEARCH_VARIANT
-        return {"metric": "hamming_pair_comparisons_per_s", "value": pairs * steps / secs, "unit": "pairs/s",
-                "ms_per_step": secs / steps * 1e3, "scaling": "strong", "dtype": "e2m1 x e2m1 -> f32 (exact)" if variant == 6 else "u8 x u8 -> s32" if variant >= 3 else "u32",
-                "roofline": search_roofline(variant, pairs / world, k_ms, k_n, sm_count, sm_max_mhz),
-                "gpu_launches": int(launches), "clocks": cs.summary(),
-                "config": {"workload": f"search_with_references, {nq} queries x {nc} sorted table entries, equal durations, "
-                                       f"tolerance {args.tol}", "matches": result.get("matches"),
-                           "parallelism": f"table slice x{world}", "exchange": exchange_note, "l2": "512 MiB write between timed steps"}}
+        keys_np = result["keys"].cpu().numpy().view(np.uint64)
+        out = {"metric": "hamming_pair_comparisons_per_s", "value": pairs * steps / secs, "unit": "pairs/s",
+               "ms_per_step": secs / steps * 1e3, "steps": steps, "scaling": "strong", "dtype": dtype_of(variant),
+               "roofline": search_roofline(variant, pairs / world, k_ms, k_n, sm_count, sm_max_mhz),
+               "gpu_launches": int(launches), "clocks": cs.summary(), "result_digest": digest(keys_np),
+               "config": {"workload": workload_name("refs", args), "matches": int(len(keys_np)),
+                          "parallelism": f"table slice x{world}", "exchange": exchange_note,
+                          "table": "each rank's slice prepared once (vdf_table), queries packed per step",
+                          "l2": "512 MiB write between timed steps, inside the timed region"}}
+        tbl.close()
+        Hc = corpus.cpu().numpy().view(np.uint64)
+        cdur = np.full(nc, 600, np.uint32)
+        Q = d_q.cpu().numpy().view(np.uint64)
+        qdur = np.full(nq, 600, np.uint32)
+        del corpus, d_c
+        if rank == 0 and not args.no_cpu_baseline and args.parity_rows > 0:
+            from oracle import vdf_oracle as o
 
-    # ---------------------------------------------------------------- hashing workload
+            k_rows = max(4, min(args.parity_rows, int(8.0e8 // nc)))
+            rows = np.unique(np.concatenate([np.random.default_rng(3).integers(0, nq, k_rows), np.arange(0, 20 * (k_rows // 2), 20) % nq]))
+            rp, ci = o.search_refs(Hc, cdur, Q[rows], qdur[rows], tol_int)
+            kr, kc = (keys_np >> np.uint64(32)).astype(np.int64), keys_np & np.uint64(0xFFFFFFFF)
+            bad = sum(not np.array_equal(kc[kr == r], ci[rp[k]:rp[k + 1]]) for k, r in enumerate(rows.tolist()))
+            out["parity_sample"] = {"rows": int(len(rows)), "candidates_per_row": int(nc), "mismatching_rows": int(bad), "ok": bad == 0,
+                                    "how": "oracle brute force of sampled query rows (half of them planted hits) vs the GPU's match lists, untimed"}
+        # e2e: host tables through the public API (sort keys + GPU sort of the 10 M table, uploads, search, CSR back)
+        ids = np.random.default_rng(11).permutation(nc)
+        cands = vdf.HashTable(Hc[ids], cdur, FixedWidthPaths(ids))
+        cands._blob = cands.paths.blob()
+        refs = vdf.HashTable(Q, qdur, FixedWidthPaths(np.arange(nq) + 10**7 * 5))
+        vdist.search_with_references(refs, cands, args.tol, ctx=ctx)
+        c0 = ctx.counters()
+        barrier()
+        t0 = time.perf_counter()
+        g = vdist.search_with_references(refs, cands, args.tol, ctx=ctx)
+        barrier()
+        e_secs = max_over_ranks(time.perf_counter() - t0)
+        c1 = ctx.counters()
+        out["e2e"] = {"value": pairs / e_secs, "unit": "pairs/s", "ms_per_call": e_secs * 1e3, "groups": len(g),
+                      "h2d_bytes_per_step": int(c1[1] - c0[1]), "d2h_bytes_per_step": int(c1[2] - c0[2]), "steps": 1,
+                      "result_digest": digest(*g.csr), "input_order": "shuffled candidate table",
+                      "api": "vid_dup_finder_lib_b200.dist.search_with_references(refs, candidates, tolerance) -> MatchGroups"}
+        return out
+
+    # ---------------------------------------------------------------- end-to-end dedup (BASELINE configs[4])
+    def bench_e2e10m():
+        """frame stacks -> hashes -> all-gather -> (duration, Path) sort -> all-pairs search -> MatchGroups, on all ranks.
+        Stacks come from a resident pool of 1080p stacks cycled to --n-e2e hash operations (one pass over distinct content
+        would need 330 TB of synthetic pixels); the hashes never leave HBM.  So that the search sees distinct entries, row r
+        of the gathered table is XORed with salt[r] = synthetic[r] ^ H(pool[r % pool]), which turns it into the synthetic
+        planted table EXACTLY IF every one of the hashes computed in the timed region is right."""
+        n, ns, tol_int = args.n_e2e, args.stacks, tolerance_to_int(args.tol)
+        w, h = args.width, args.height
+        b, e = vdist.shard_range(n, rank, world)
+        with torch.cuda.stream(stream):
+            pool = synth.frame_stacks(ns, w, h, device=dev, first_id=0)  # the same pool on every rank: row r is stack r % ns
+            descs = _ffi.make_descs(ns, w, h)
+            pool_hash = torch.zeros((ns, 16), dtype=torch.int64, device=dev)
+            torch.cuda.current_stream().synchronize()
+            ctx.hash_stacks_device(pool.data_ptr(), descs, _ffi.CROPDETECT_LETTERBOX, pool_hash.data_ptr())  # untimed: the salt
+            synth_tab, _ = synth.planted_hashes_torch(n, device=dev)
+            salt = synth_tab ^ pool_hash[torch.arange(n, device=dev) % ns]
+            del synth_tab
+            n_calls = (e - b + ns - 1) // ns
+            mine = torch.zeros((n_calls * ns, 16), dtype=torch.int64, device=dev)
+            ids = np.random.default_rng(13).permutation(n)  # path of row r = "v/%08d" % ids[r]: the caller's order is arbitrary
+            paths = FixedWidthPaths(ids)
+            blob, off = paths.blob()
+            durs = np.full(n, 600, np.uint32)
+            d_order = torch.empty(n, dtype=torch.int32, device=dev)
+            d_dur = torch.empty(n, dtype=torch.int32, device=dev)
+            torch.cuda.current_stream().synchronize()
+        # rows [b, e) of the table are stacks (b + k) % ns: rotate the descriptors so that every call hashes the right stacks
+        rot = np.roll(descs, -(b % ns))
+        ph = {}
+        ctx.kernel_time(0, reset=True)
+        l0 = ctx.counters()[0]
+        with ClockSampler(local) as cs:
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(stream):
+                for c in range(n_calls):  # H1-H5 on this rank's share
+                    ctx.hash_stacks_device(pool.data_ptr(), rot, _ffi.CROPDETECT_LETTERBOX, mine[c * ns:].data_ptr())
+                torch.cuda.current_stream().synchronize()
+                ph["hash_s"] = time.perf_counter() - t0
+                if world > 1:  # G1: one all-gather of the 128-byte hashes (ragged last share: gather padded, cut)
+                    per = (n + world - 1) // world
+                    buf = torch.zeros((world, per, 16), dtype=torch.int64, device=dev)
+                    dist.all_gather_into_tensor(buf.view(-1), torch.nn.functional.pad(mine[:e - b], (0, 0, 0, per - (e - b))).contiguous().view(-1))
+                    table = torch.cat([buf[r, :vdist.shard_range(n, r, world)[1] - vdist.shard_range(n, r, world)[0]] for r in range(world)])
+                else:
+                    table = mine[:n]
+                table = table ^ salt
+                torch.cuda.current_stream().synchronize()
+                ph["allgather_s"] = time.perf_counter() - t0 - ph["hash_s"]
+                t1 = time.perf_counter()
+                if rank == 0:  # S1: keys cut by host threads, sorted on the GPU; hashes stay where they are
+                    ctx.sort_order_device(durs, blob, off, d_order.data_ptr(), d_dur.data_ptr())
+                if world > 1:
+                    dist.broadcast(d_order, 0)
+                    dist.broadcast(d_dur, 0)
+                d_sorted = table[d_order.long()]
+                torch.cuda.current_stream().synchronize()
+                ph["sort_s"] = time.perf_counter() - t1
+                t2 = time.perf_counter()
+                keys = vdist.search_self_keys(ctx, d_sorted, d_dur, tol_int)  # S2-S3, G2
+                torch.cuda.current_stream().synchronize()
+                ph["search_s"] = time.perf_counter() - t2
+                t3 = time.perf_counter()
+                gp, mm = ctx.group_greedy_device(n, keys.data_ptr(), keys.numel(), d_remap=d_order.data_ptr())  # S4
+                groups = vdf.MatchGroup.from_csr(paths, gp, mm)
+                ph["group_s"] = time.perf_counter() - t3
+            barrier()
+            secs = max_over_ranks(time.perf_counter() - t0)
+        launches = ctx.counters()[0] - l0
+        k_ms, k_n = ctx.kernel_time(0, reset=True)
+        pairs = n * (n - 1) // 2
+        keys_np = keys.cpu().numpy().view(np.uint64)
+        out = {"metric": "e2e_dedup_hashes_per_s", "value": n / secs, "unit": "hashes/s", "seconds": secs, "steps": 1, "scaling": "strong",
+               "phases_s_rank0": ph, "search_pairs_per_s": pairs / max_over_ranks(ph["search_s"]),
+               "hash_stacks_per_s": n / max_over_ranks(ph["hash_s"]),
+               "roofline": search_roofline(variant, pairs / world, k_ms, k_n, sm_count, sm_max_mhz),
+               "gpu_launches": int(launches), "clocks": cs.summary(), "edges": int(len(keys_np)), "groups": len(groups),
+               "result_digest": digest(keys_np, gp, mm),
+               "config": {"workload": workload_name("e2e10m", args), "pool_stacks": ns,
+                          "data_flow": "pool stacks (HBM) -> vdf_hash_stacks_device -> all-gather -> xor salt -> vdf_sort_order_device -> "
+                                       "gather -> sharded search + fused exchange -> greedy groups with device remap -> CSR to host",
+                          "parallelism": f"stack shard x{world}, then tile-block shard x{world}", "exchange": exchange_note}}
+        if rank == 0 and not args.no_cpu_baseline and args.parity_rows > 0:
+            # positions are sorted positions: bring the sorted table to the host for the oracle
+            Hs = d_sorted.cpu().numpy().view(np.uint64)
+            out["parity_sample"] = parity_rows_self(Hs, durs, keys_np, tol_int, max(4, min(args.parity_rows, int(6.0e8 // n))))
+        return out
+
+    # ---------------------------------------------------------------- hashing workload (BASELINE configs[1])
     def bench_hash(steps, warmup):
+        """--hash-total stack-hashes per GPU (configs[1]: 100 k stacks) from a resident pool of --stacks 1080p stacks"""
         w, h, ns = args.width, args.height, args.stacks
+        steps = max(steps, (args.hash_total + ns - 1) // ns)
         stack_bytes = 16 * w * h
         with torch.cuda.stream(stream):
             pool = synth.frame_stacks(ns, w, h, device=dev, first_id=rank * ns)
             out = torch.zeros((ns, 16), dtype=torch.int64, device=dev)
         descs = _ffi.make_descs(ns, w, h)
         torch.cuda.synchronize()
+        crops = {}
 
         def step():
-            ctx.hash_stacks_device(pool.data_ptr(), descs, _ffi.CROPDETECT_LETTERBOX, out.data_ptr())
+            crops["c"] = ctx.hash_stacks_device(pool.data_ptr(), descs, _ffi.CROPDETECT_LETTERBOX, out.data_ptr())[1]
 
         with ClockSampler(local) as cs:
             with torch.cuda.stream(stream):
@@ -572,11 +813,18 @@ def main():
         k_ms = kt[1][0] / max(kt[1][1], 1)
         alg_bytes = ns * (stack_bytes + 128)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if kt[1][1] else None
-        roof = {"bound": "hbm", "kernel": "resize kernel (crop + Lanczos3 -> 16x16)", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+        # bytes the fused kernel actually requests: the cropped rows, in whole 128-byte chunks from the 16-byte aligned start
+        c = crops["c"].astype(np.int64)
+        cw, chh = w - c[:, 0] - c[:, 1], h - c[:, 2] - c[:, 3]
+        moved = int((16 * chh * (((c[:, 0] & 15) + cw + 127) // 128) * 128).sum()) + ns * 128
+        roof = {"bound": "hbm", "kernel": "resize_mma_kernel (crop window + Lanczos3 -> 16x16 per frame, DCT + threshold + pack in the stack's last CTA)",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+                "frac_bytes_moved": (moved / (k_ms * 1e-3) / 1e9 / hbm_peak) if kt[1][1] else None, "bytes_moved_per_launch_set": moved,
                 "traffic": ncu_traffic("resize_mma_kernel", f"stacks_{ns}_{w}x{h}"), "peak_source": peak_src,
                 "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_stack": stack_bytes + 128,
-                "step_share": {"resize": kt[1][0], "letterbox": kt[2][0], "dct_pack": kt[3][0], "unit": "ms over timed steps"}}
+                "note": "kernel_ms = CUDA events around the fused kernel's launches of one call (4 chunks of stacks; includes the job-build "
+                        "kernels and any wait for the letterbox stream)",
+                "step_share": {"resize_dct_pack": kt[1][0], "letterbox_on_its_stream": kt[2][0], "unit": "ms over timed steps"}}
         # e2e: host frames (pinned) -> vdf_hash_stacks -> host hashes, bounded to a few stacks (PCIe-bound)
         ne = min(ns, 32)
         host = pool[:ne].cpu().pin_memory()
@@ -589,11 +837,10 @@ def main():
         e_secs = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": ne * world / e_secs, "unit": "stacks/s", "h2d_bytes_per_step": int(ne * stack_bytes),
                "d2h_bytes_per_step": int(ne * 128), "stacks": ne, "api": "vdf_hash_stacks (host frames, pinned async staging)"}
-        res = {"metric": "frame_stacks_hashed_per_s", "value": value, "unit": "stacks/s", "ms_per_step": secs / steps * 1e3,
-               "scaling": "weak", "dtype": "u8/i32 resize, f64 DCT", "roofline": roof, "e2e": e2e, "gpu_launches": int(launches),
-               "clocks": cs.summary(),
-               "config": {"workload": f"frame-stack hashing, {w}x{h}x16 u8 stacks resident in HBM, letterbox cropdetect",
-                          "stacks_per_gpu_per_step": ns, "parallelism": f"stack shard x{world}",
+        res = {"metric": "frame_stacks_hashed_per_s", "value": value, "unit": "stacks/s", "ms_per_step": secs / steps * 1e3, "steps": steps,
+               "stack_hashes_per_gpu": ns * steps, "scaling": "weak", "dtype": "u8/i32 resize, f64 DCT", "roofline": roof, "e2e": e2e,
+               "gpu_launches": int(launches), "clocks": cs.summary(), "result_digest": digest(out.cpu().numpy()),
+               "config": {"workload": workload_name("hash", args), "stacks_per_gpu_per_step": ns, "parallelism": f"stack shard x{world}",
                           "l2": f"pool of {ns * stack_bytes / 1e9:.1f} GB per GPU >> L2, no flush",
                           "hash_variant": args.hash_variant}}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -602,33 +849,57 @@ def main():
             from oracle import vdf_oracle as o
 
             cores = os.cpu_count() or 1
-            nb = min(ns, 128, 4 * max(cores, 2))  # four stacks per thread: ~1 s of CPU work on the box
-            hs = pool[:nb].cpu().numpy()
-            t0 = time.perf_counter()
-            with ThreadPoolExecutor(cores) as ex:
-                ref = list(ex.map(lambda s: o.hash_stack(hs[s], 1)[1], range(nb)))
-            dt = time.perf_counter() - t0
-            gw = out[:nb].cpu().numpy().view(np.uint64)
-            diff = int(np.unpackbits((np.stack(ref) ^ gw).view(np.uint8)).sum())
-            res["cpu_baseline"] = {"value": nb / dt, "unit": "stacks/s", "cores": cores, "kind": "port",
-                                   "sample": f"{nb} of the same stacks, oracle port on {cores} threads"}
-            res["bit_mismatch"] = {"stacks": nb, "bits_differing": diff, "rate": diff / (nb * 1000.0),
+            total, diff, dt_cpu, done = max(ns, args.mismatch_stacks), 0, 0.0, 0
+            for first in range(0, total, ns):  # bit mismatches over >= 1024 distinct stacks
+                if first:
+                    with torch.cuda.stream(stream):
+                        pool.copy_(synth.frame_stacks(ns, w, h, device=dev, first_id=10_000 + first))
+                        torch.cuda.current_stream().synchronize()
+                    step()
+                hs = pool.cpu().numpy()
+                t0 = time.perf_counter()
+                with ThreadPoolExecutor(cores) as ex:
+                    ref = list(ex.map(lambda s: o.hash_stack(hs[s], 1)[1], range(ns)))
+                dt_cpu += time.perf_counter() - t0
+                gw = out.cpu().numpy().view(np.uint64)
+                diff += int(np.unpackbits((np.stack(ref) ^ gw).view(np.uint8)).sum())
+                done += ns
+            res["cpu_baseline"] = {"value": done / dt_cpu, "unit": "stacks/s", "cores": cores, "kind": "port",
+                                   "sample": f"{done} synthetic stacks (the bench pool and {done // ns - 1} more pools), oracle port on {cores} threads"}
+            res["bit_mismatch"] = {"stacks": done, "bits_differing": diff, "rate": diff / (done * 1000.0),
                                    "note": "f64 DCT in the oracle's operation order: no epsilon band"}
         return res
 
+    def guarded(fn, *a, **k):
+        try:
+            return fn(*a, **k)
+        except Exception as e:  # a secondary record must not take the headline down with it
+            import traceback
+
+            traceback.print_exc()
+            return {"error": repr(e)}
+
     if args.workload == "search":
         line = bench_search(args.steps, args.warmup)
-        if not args.no_secondary:
-            try:
-                line["secondary"] = bench_hash(max(2, args.steps), max(3, args.warmup))
-            except Exception as e:  # the secondary metric must not take the headline down with it
-                line["secondary"] = {"error": repr(e)}
+        wanted = [] if args.no_secondary else [x.strip() for x in args.secondary.split(",") if x.strip()]
+        if "hash" in wanted:
+            line["secondary"] = guarded(bench_hash, max(2, args.steps), max(3, args.warmup))
+        if "popc" in wanted:  # the north-star's graded kernel: XOR + POPC, its own roofline (integer XU pipe)
+            line["secondary_popc"] = guarded(bench_search, 2, 1, n=args.n_popc, use_variant=0, light=True)
+        if "refs" in wanted:
+            line["secondary_refs"] = guarded(bench_refs, min(max(args.steps, 1), 3), 1)
+        if "e2e10m" in wanted:
+            line["secondary_e2e"] = guarded(bench_e2e10m)
+    elif args.workload == "popc":
+        line = bench_search(args.steps, args.warmup, n=args.n_popc, use_variant=0, light=True)
     elif args.workload == "refs":
         line = bench_refs(args.steps, args.warmup)
+    elif args.workload == "e2e10m":
+        line = bench_e2e10m()
     else:
         line = bench_hash(args.steps, args.warmup)
-    line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
-                 "data": "synthetic", "impl": "ours"})
+    line.update({"n_gpus": world, "steps": line.get("steps", args.steps) if args.workload != "search" else args.steps, "warmup": args.warmup,
+                 "higher_is_better": True, "vs_baseline": None, "data": "synthetic", "impl": "ours"})
     if rank == 0:
         emit(line)
     if world > 1:

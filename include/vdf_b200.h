@@ -250,6 +250,12 @@ int vdf_self_window_pairs(vdf_ctx* ctx, const uint32_t* dur_sorted, uint64_t n, 
 int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint64_t* path_off, uint64_t n,
                    uint64_t* order_out);
 
+/* Search::sort for a table whose hashes already live in HBM (e.g. straight out of vdf_hash_stacks_device): the permutation
+ * (n x u32) and, optionally, the durations in sorted order are written to DEVICE memory; the caller gathers its hash rows by
+ * the permutation (or hands it to a kernel of its own).  Sort keys are cut on the host, the sort runs on the GPU. */
+int vdf_sort_order_device(vdf_ctx* ctx, const uint32_t* durations, const char* path_blob, const uint64_t* path_off, uint64_t n,
+                          uint32_t* d_order_out, uint32_t* d_dur_sorted_out);
+
 /* `Search::seed` + `sort` (search_algorithm.rs:31-34,55-61) with the sorted table left RESIDENT in HBM: the stable
  * (duration, Path) permutation goes to order_out[n]; hashes and durations are gathered in that order through pinned
  * memory and uploaded on the context's stream - into d_hash_dst / d_dur_dst (n x 128 B / n x 4 B of device memory owned by

@@ -118,3 +118,61 @@ def frame_stacks(n: int, w: int, h: int, seed: int = SEED, device="cpu", first_i
             img[:, :, w - r:] = (16 + torch.randint(-4, 5, (16, h, r), device=device, generator=g)).to(torch.uint8)
         out[s] = img
     return out
+
+
+# ---- large tables (10 M hashes): the same kind of data, generated with torch integer arithmetic so that the GPU box fills
+# HBM directly; bit-identical on CPU and GPU (wrapping int64 ops only), entry i depends only on (seed, i) ---------------
+def _t_splitmix64(x):
+    import torch
+
+    def lsr(v, s):  # logical shift right on int64
+        return (v >> s) & ((1 << (64 - s)) - 1)
+
+    z = x + (-7046029254386353131)  # 0x9E3779B97F4A7C15 as int64
+    z = (z ^ lsr(z, 30)) * (-4658895280553007687)  # 0xBF58476D1CE4E5B9
+    z = (z ^ lsr(z, 27)) * (-7723592293110705685)  # 0x94D049BB133111EB
+    return z ^ lsr(z, 31)
+
+
+def _t_stream(seed: int, idx, lane: int):
+    import torch
+
+    k = torch.tensor([(seed ^ (lane * 0xD1342543DE82EF95)) & 0xFFFFFFFFFFFFFFFF], dtype=torch.uint64).view(torch.int64).to(idx.device)
+    return _t_splitmix64(_t_splitmix64(k) + idx)
+
+
+def planted_hashes_torch(n: int, seed: int = SEED, device="cpu", dup_frac_den: int = 10, chunk: int = 1 << 21):
+    """[n,16] int64 tensor (the u64 words) on `device`: random 1000-bit hashes (bits 1000..1023 zero) where ~1/dup_frac_den
+    of the entries are copies of a random EARLIER base entry with a random subset of bits flipped: the AND of m in 2..6
+    random words per word, i.e. ~250, 125, 62, 31 or 16 flipped bits.  -> (hashes, src), src[i] = i for base entries."""
+    import torch
+
+    out = torch.empty((n, 16), dtype=torch.int64, device=device)
+    src = torch.empty(n, dtype=torch.int64, device=device)
+    low40 = (1 << 40) - 1
+
+    def base(idx):
+        h = torch.stack([_t_stream(seed, idx, w) for w in range(16)], dim=1)
+        h[:, 15] &= low40
+        return h
+
+    for a in range(0, n, chunk):
+        idx = torch.arange(a, min(n, a + chunk), dtype=torch.int64, device=device)
+        h = base(idx)
+        r = _t_stream(seed, idx, 100) & 0x7FFFFFFFFFFFFFFF
+        is_dup = (r % dup_frac_den == 0) & (idx > 0)
+        s = torch.where(is_dup, (_t_stream(seed, idx, 101) & 0x7FFFFFFFFFFFFFFF) % torch.clamp(idx, min=1), idx)
+        d = torch.nonzero(is_dup).flatten()
+        if d.numel():
+            di = idx[d]
+            hb = base(s[d])
+            m = 2 + (_t_stream(seed, di, 102) & 0x7FFFFFFFFFFFFFFF) % 5  # 2..6 words ANDed
+            flip = torch.full((d.numel(), 16), -1, dtype=torch.int64, device=device)
+            for k in range(6):
+                rk = torch.stack([_t_stream(seed, di, 200 + 16 * k + w) for w in range(16)], dim=1)
+                flip = torch.where((m > k)[:, None], flip & rk, flip)
+            flip[:, 15] &= low40
+            h[d] = hb ^ flip
+        out[a:a + chunk] = h
+        src[a:a + chunk] = s
+    return out, src

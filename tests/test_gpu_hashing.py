@@ -95,6 +95,31 @@ def _check_bit_exact(ctx, w, h):
     assert bits[100:].sum() == 0  # static stack
 
 
+def test_chunked_overlapped_pipeline_matches_serial(ctx):
+    """round 2 pipeline: resize jobs built on the device from the crops (sizes met for the first time take a second pass),
+    the letterbox scan of chunk k+1 on a second stream beside the resize of chunk k, DCT + pack fused into the resize kernel.
+    Every combination of the knobs gives the oracle's hashes, on a fresh context (cold tables) and again (warm)."""
+    n, w, h = 160, 256, 144
+    stacks = synth.frame_stacks(n, w, h, seed=4321).numpy()
+    rng = np.random.default_rng(5)
+    for s in range(0, n, 3):  # many distinct crop sizes: bars of different widths on different sides
+        t, b, l = int(rng.integers(0, 30)), int(rng.integers(0, 30)), int(rng.integers(0, 40))
+        stacks[s, :, :t, :] = 16
+        stacks[s, :, h - b:, :] = 18
+        stacks[s, :, :, :l] = 14
+    want_h, want_s, want_c, _ = oracle_all(stacks)
+    fresh = _ffi.Context(ctx.device)
+    try:
+        for overlap, chunks in ((1, 4), (1, 4), (0, 1), (0, 4), (1, 2)):
+            fresh.set_option("hash_overlap", overlap)
+            fresh.set_option("hash_chunks", chunks)
+            got_h, got_s, got_c = gpu_hash(fresh, stacks)
+            assert np.array_equal(got_c, want_c), (overlap, chunks)
+            assert np.array_equal(got_s, want_s) and np.array_equal(got_h, want_h), (overlap, chunks)
+    finally:
+        fresh.close()
+
+
 def test_cropdetect_none(ctx):
     stacks = synth.frame_stacks(4, 320, 180, seed=3).numpy()
     stacks[:, :, :20, :] = 16

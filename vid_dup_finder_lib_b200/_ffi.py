@@ -30,7 +30,7 @@ EXPORTS = [
     "vdf_sort_order", "vdf_search", "vdf_search_with_references", "vdf_ctx_last_phases", "vdf_group_components",
     "vdf_group_components_device", "vdf_cache_load", "vdf_cache_save", "vdf_free_cache",
     "vdf_pipeline_create", "vdf_pipeline_push", "vdf_pipeline_flush", "vdf_pipeline_poll", "vdf_pipeline_error", "vdf_pipeline_destroy",
-    "vdf_ctx_create_multi", "vdf_ctx_device_count", "vdf_table_create", "vdf_table_create_device", "vdf_table_destroy", "vdf_table_len",
+    "vdf_ctx_create_multi", "vdf_ctx_device_count", "vdf_sort_order_device", "vdf_table_create", "vdf_table_create_device", "vdf_table_destroy", "vdf_table_len",
     "vdf_table_search_self_device", "vdf_table_search_self_groups", "vdf_table_search_refs_device",
 ]
 
@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
     L.vdf_group_greedy_device.argtypes = [vp, u64, vp, u64, vp, C.POINTER(Groups)]
     L.vdf_self_window_pairs.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.vdf_sort_order.argtypes = [vp, vp, vp, u64, vp]
+    L.vdf_sort_order_device.argtypes = [vp, vp, vp, vp, u64, vp, vp]
     L.vdf_search.argtypes = [vp, vp, vp, vp, vp, u64, C.c_double, C.POINTER(Groups)]
     L.vdf_search_with_references.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, u64, C.c_double, C.POINTER(Csr)]
     L.vdf_ctx_last_phases.argtypes = [vp, C.POINTER(C.c_double)]
@@ -263,6 +264,12 @@ class Context:
         self._check(lib().vdf_stage_sorted(self._h, _ptr(h), _ptr(d), _ptr(path_blob), _ptr(path_off), len(d), _ptr(order),
                                            C.c_void_p(d_hash_dst or None), C.c_void_p(d_dur_dst or None), C.byref(ph), C.byref(pd)))
         return order.view(np.int64), int(ph.value or 0), int(pd.value or 0)
+
+    def sort_order_device(self, durations, path_blob: np.ndarray, path_off: np.ndarray, d_order_out: int, d_dur_sorted_out: int = 0):
+        """vdf_sort_order_device: Search::sort's permutation (n x u32) and the sorted durations, written to device memory"""
+        d = np.ascontiguousarray(durations, dtype=np.uint32)
+        self._check(lib().vdf_sort_order_device(self._h, _ptr(d), _ptr(path_blob), _ptr(path_off), len(d), d_order_out,
+                                                C.c_void_p(d_dur_sorted_out or None)))
 
     def group_greedy(self, n: int, edges):
         e = np.ascontiguousarray(edges, dtype=np.uint64).reshape(-1, 2)

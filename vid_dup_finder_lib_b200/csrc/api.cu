@@ -58,6 +58,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->lb_stream) cudaStreamSynchronize(ctx->lb_stream);
     DevBuf* bufs[] = {&ctx->raw_keys,  &ctx->sort_tmp,  &ctx->misc,     &ctx->keys_a,  &ctx->keys_b,  &ctx->in_hash,
                       &ctx->in_dur,    &ctx->in_hash2,  &ctx->in_dur2,  &ctx->ref_perm, &ctx->ref_key, &ctx->g_rk,
                       &ctx->g_rks,     &ctx->g_state,   &ctx->g_parent, &ctx->g_wl0,   &ctx->g_wla,   &ctx->g_wlb,
@@ -65,7 +66,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
                       &ctx->g_cnt,     &ctx->g_gstart,  &ctx->sk_a,     &ctx->sk_b,    &ctx->sk_c,    &ctx->sk_d,
                       &ctx->sk_order,  &ctx->sk_rank,   &ctx->ref_rows.tiles, &ctx->ref_rows.pc, &ctx->ref_rows.pcmin,
                       &ctx->h_frames[0], &ctx->h_frames[1], &ctx->h_jobs, &ctx->h_sides, &ctx->h_crop, &ctx->h_small,
-                      &ctx->h_hash,    &ctx->h_desc};
+                      &ctx->h_hash,    &ctx->h_desc,    &ctx->h_done};
     ctx->tmp_self.release();
     ctx->tmp_cand.release();
     ctx->ref_plan.release();
@@ -91,6 +92,8 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
     }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->lb_stream) cudaStreamDestroy(ctx->lb_stream);
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
     delete ctx;
 }
 
@@ -122,6 +125,7 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     else if (k == "tc_unit_order" && (value == 0 || value == 1)) ctx->tc_unit_order = (uint32_t)value;
     else if (k == "tc_a_tmem" && (value == 0 || value == 1)) ctx->tc_a_tmem = (uint32_t)value;
     else if (k == "hash_chunks" && value >= 1 && value <= 4) ctx->hash_chunks = (uint32_t)value;
+    else if (k == "hash_overlap" && (value == 0 || value == 1)) ctx->hash_overlap = (uint32_t)value;
     else if (k == "grouping" && (value == 0 || value == 1)) ctx->grouping = (int)value;
     else if (k == "exchange" && (value == 0 || value == 1)) ctx->exchange = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;
@@ -257,12 +261,12 @@ void kt_collect(vdf_ctx* ctx) {
         ctx->kt_pending[k] = false;
     }
 }
-void kt_begin(vdf_ctx* ctx, int which) {
+void kt_begin(vdf_ctx* ctx, int which, cudaStream_t stream) {
     if (ctx->kt_pending[which]) kt_collect(ctx);
-    cudaEventRecord(ctx->kt0[which], ctx->stream);
+    cudaEventRecord(ctx->kt0[which], stream ? stream : ctx->stream);
 }
-void kt_end(vdf_ctx* ctx, int which) {
-    cudaEventRecord(ctx->kt1[which], ctx->stream);
+void kt_end(vdf_ctx* ctx, int which, cudaStream_t stream) {
+    cudaEventRecord(ctx->kt1[which], stream ? stream : ctx->stream);
     ctx->kt_pending[which] = true;
 }
 }  // namespace vdf

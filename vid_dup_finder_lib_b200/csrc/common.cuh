@@ -182,6 +182,8 @@ struct vdf_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t lb_stream = nullptr;  // hash.cu: the letterbox scan of chunk k+1 runs beside the resize of chunk k
+    cudaEvent_t ev_in = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};  // hash.cu: crops of chunk k are back on the host
@@ -199,7 +201,8 @@ struct vdf_ctx {
     int tc_fold = -1;           // variant 6: -1 fold C - pc(j) into the contraction whenever both operands have zero pad bits
                                 // (every real VideoHash), 0 never (the popcount-screen epilogue of round 1)
     uint64_t peer_timeout_ms = 0;  // peer exchange barrier: 0 = automatic (20 s + 1 ms per 2^26 pairs in the windows)
-    uint32_t hash_chunks = 1;  // hash.cu: software-pipeline chunks per call (1: letterbox, then resize, over the whole batch)
+    uint32_t hash_chunks = 4;   // hash.cu: chunks of stacks per call (letterbox of chunk k+1 overlaps the resize of chunk k)
+    uint32_t hash_overlap = 1;  // 0: letterbox and resize on one stream (round 1's order)
     int exchange = 0;       // 1: searches append their matches to every rank's peer buffer (vdf_peer_*), see PeerExchange
     vdf::PeerExchange peer;
     bool peer_dead = false;  // an exchange call failed mid-way: counters of the ranks disagree, vdf_peer_close / alloc / open again
@@ -230,7 +233,7 @@ struct vdf_ctx {
     bool ham_attrs = false, tc_attrs = false;
     size_t hash_smem_set[3] = {0, 0, 0};
     // hashing scratch
-    vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc;
+    vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc, h_coef_lut, h_bfrag_lut, h_done;
     vdf::PinnedBuf pin_a, pin_b, pin_c, pin_frames[2], h_groups;  // h_groups: staging of the group CSR on its way to the caller
     vdf::PinnedBuf h_misc;  // landing zone of the few counters the host reads back per call
     std::map<uint32_t, vdf::CoefTable> coef_cache;
@@ -278,8 +281,8 @@ struct vdf_ctx {
 
 namespace vdf {
 // kernel timing helpers (api.cu)
-void kt_begin(vdf_ctx* ctx, int which);
-void kt_end(vdf_ctx* ctx, int which);
+void kt_begin(vdf_ctx* ctx, int which, cudaStream_t stream = nullptr);  // nullptr: the context's main stream
+void kt_end(vdf_ctx* ctx, int which, cudaStream_t stream = nullptr);
 void kt_collect(vdf_ctx* ctx);
 // search.cu
 int table_prepare(vdf_ctx* ctx, Table& t, const uint64_t* d_hash, const uint32_t* d_perm, const uint32_t* d_dur_sorted, uint64_t n,

@@ -16,7 +16,12 @@
 // (static or mirror-symmetric content) stay exact zeros, as they do in the reference's rustdct butterflies.
 //
 // The i16 coefficient tables depend only on the cropped size, are generated on the host in f64 (libm sin, like
-// the reference) and cached in HBM per size.
+// the reference) and cached in HBM per size; a lookup table in HBM (size -> table) lets a small kernel turn the crops into
+// resize jobs ON THE DEVICE, so a call runs letterbox -> jobs -> resize+DCT+pack without the host in between.  A size met
+// for the first time is a "miss": the host builds its table after the pass and only the missed stacks run again.
+// Kernels per call: the letterbox scan of frames 0 and 8 (a data-dependent pre-pass: its result moves the addresses the
+// resize reads), and ONE fused kernel per stack set that reads every pixel once and writes the 128-byte hash (crop window,
+// Lanczos3 to 16x16 per frame, and -- in the CTA that finishes a stack's 16th frame -- the 16^3 DCT, threshold and pack).
 #include <cmath>
 #include <cstring>
 
@@ -29,6 +34,8 @@ struct StackDev {
     uint64_t offset, frame_stride;
     uint32_t width, height, pitch;
     int32_t status;
+    uint32_t aligned;  // base, frame stride and pitch are multiples of 16: the tensor-core resize may take it
+    uint32_t pad;
 };
 
 constexpr int kLbTol = 16;  // LetterboxColour::AnyColour(16), video_frames_gray.rs:206
@@ -77,7 +84,10 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
     const uint32_t limit = cols ? W : H, len = cols ? H : W;
     const uint32_t panel = cols ? kColPanel : kRowPanel;
     for (uint32_t base = 0; base < limit; base += panel) {
-        for (uint32_t q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
+        // column panels histogram every strip; row panels zero a strip's histogram only if it is not decided by its value
+        // range (real bars are): zeroing 33 KB per 8-row panel was a third of a barred side's time
+        if (cols)
+            for (uint32_t q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
         if (tid < kRowPanel) narrow[tid] = 0;
         __syncthreads();
         const uint32_t px0 = side == 0 ? base : W - 32 - base;  // first pixel column of a full 32-column panel
@@ -130,6 +140,14 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                 uint32_t* h4 = hist + (warp * 4) * 257;
                 uint32_t* hs = h4 + (lane & 3) * 257;
                 uint32_t x_done = 0;
+                bool zeroed = false;
+                auto zero_h4 = [&]() {
+                    if (!zeroed) {
+                        for (int v = lane; v < 4 * 257; v += 32) h4[v] = 0;
+                        __syncwarp();
+                        zeroed = true;
+                    }
+                };
                 const uint32_t W4 = W >> 2;
                 if ((reinterpret_cast<uintptr_t>(row) & 3) == 0 && W4 <= 32 * 16) {
                     // the whole row is in registers (<= 2048 px): look at its value range before touching the histogram.
@@ -156,6 +174,7 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                     if (mx - mn <= (uint32_t)kLbTol) {
                         if (lane == 0) narrow[warp] = 1u;
                     } else {
+                        zero_h4();
 #pragma unroll
                         for (int u = 0; u < 16; ++u) {
                             if (u * 32 + lane < W4) {
@@ -169,6 +188,7 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                     }
                     x_done = W;
                 } else if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // long rows: up to 16 x 4 pixels per lane in flight
+                    zero_h4();
                     const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
                     for (uint32_t q0 = 0; q0 < W4; q0 += 32 * 16) {
                         uint32_t v[16];
@@ -189,6 +209,7 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                     }
                     x_done = W4 << 2;
                 }
+                if (x_done < W) zero_h4();
                 for (uint32_t x0 = x_done; x0 < W; x0 += 32 * 16) {
                     uint32_t v[16];
 #pragma unroll
@@ -201,7 +222,8 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                         if (v[u] < 0x100u) atomicAdd(&hs[v[u]], 1u);
                 }
                 __syncwarp();
-                for (int v = lane; v < 256; v += 32) h4[v] += h4[257 + v] + h4[514 + v] + h4[771 + v];
+                if (zeroed)
+                    for (int v = lane; v < 256; v += 32) h4[v] += h4[257 + v] + h4[514 + v] + h4[771 + v];
                 __syncwarp();
             }
         }
@@ -248,7 +270,163 @@ __global__ void crop_combine_kernel(const StackDev* __restrict__ stacks, const u
     for (int k = 0; k < 4; ++k) crop[s * 4 + k] = out[k];
 }
 
+// ================================================================================ H4 + H5: 3-D DCT, threshold, pack
+// twiddles: [0..7] n=16 (re,im) x4, [8..11] n=8 (re,im) x2, [12..13] n=4, [14] FRAC_1_SQRT_2
+__constant__ double c_tw[16];
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+__device__ __forceinline__ void dct2_2(double& b0, double& b1) {
+    const double s = dadd(b0, b1);
+    b1 = dmul(dsub(b0, b1), c_tw[14]);
+    b0 = s;
+}
+__device__ __forceinline__ void dct2_4(double* b) {
+    const double re = c_tw[12], im = c_tw[13];
+    const double lower = dsub(b[0], b[3]), upper = dsub(b[2], b[1]);
+    double e0 = dadd(b[0], b[3]), e1 = dadd(b[1], b[2]);
+    dct2_2(e0, e1);
+    b[0] = e0;
+    b[1] = dsub(dmul(lower, re), dmul(upper, im));
+    b[2] = e1;
+    b[3] = dadd(dmul(upper, re), dmul(lower, im));
+}
+// split radix: one half-size DCT-II on the mirrored sums, two quarter-size DCT-IIs on the rotated differences
+template <int N>
+__device__ __forceinline__ void dct2_sr(double* x);
+template <>
+__device__ __forceinline__ void dct2_sr<2>(double* x) {
+    dct2_2(x[0], x[1]);
+}
+template <>
+__device__ __forceinline__ void dct2_sr<4>(double* x) {
+    dct2_4(x);
+}
+template <int N>
+__device__ __forceinline__ void dct2_sr(double* x) {
+    constexpr int H = N / 2, Q = N / 4;
+    constexpr int TW = (N == 16) ? 0 : 8;
+    double d2[H], ev[Q], od[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const double bot = x[i], top = x[N - 1 - i];
+        const double hb = x[H - 1 - i], ht = x[H + i];
+        d2[i] = dadd(top, bot);
+        d2[H - 1 - i] = dadd(hb, ht);
+        const double lower = dsub(bot, top), upper = dsub(hb, ht);
+        const double re = c_tw[TW + 2 * i], im = c_tw[TW + 2 * i + 1];
+        const double c = dadd(dmul(lower, re), dmul(upper, im));
+        const double s = dsub(dmul(upper, re), dmul(lower, im));
+        ev[i] = c;
+        od[Q - 1 - i] = (i % 2 == 0) ? s : -s;
+    }
+    dct2_sr<H>(d2);
+    dct2_sr<Q>(ev);
+    dct2_sr<Q>(od);
+    x[0] = d2[0];
+    x[1] = ev[0];
+    x[2] = d2[1];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        const double c = ev[i];
+        const double s = ((i + Q) % 2 == 0) ? -od[Q - i] : od[Q - i];
+        x[4 * i - 1] = dadd(c, s);
+        x[4 * i] = d2[2 * i];
+        x[4 * i + 1] = dsub(c, s);
+        x[4 * i + 2] = d2[2 * i + 1];
+    }
+    x[N - 1] = -od[0];
+}
+
+// cube index with a 17-double row pitch: conflict-free for all three passes
+__device__ __forceinline__ int cidx(int t, int x, int y) { return (t * 16 + x) * 17 + y; }
+
+constexpr int kCubeBytes = 16 * 16 * 17 * 8;  // the f64 cube with its padded pitch: 34 816 B
+
+// One thread block (NT = 128 or 256 threads, all of them): small [t][row][col] u8 -> m[t][x=col][y=row] = p - 128
+// (dct_3d.rs:40-44,76), DCT along y, x, t (raw_dct_ops.rs:107-142), bit t*100+x*10+y = coef > 0.0 (dct_3d.rs:55-66), Lsb0
+// words.  `cube` = kCubeBytes of shared memory.
+template <int NT>
+__device__ __forceinline__ void dct_pack_block(const uint8_t* __restrict__ sm, double* cube, uint32_t* __restrict__ out, int tid) {
+    for (int q = tid; q < 4096; q += NT) {
+        const int t = q >> 8, row = (q >> 4) & 15, col = q & 15;
+        cube[cidx(t, col, row)] = (double)__ldcg(sm + q) - 128.0;  // written by other thread blocks: read through L2
+    }
+    __syncthreads();
+    double v[16];
+    for (int line = tid; line < 256; line += NT) {  // along y: line (t, x)
+        const int t = line >> 4, x = line & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(t, x, k)];
+        dct2_sr<16>(v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cube[cidx(t, x, k)] = v[k];
+    }
+    __syncthreads();
+    for (int line = tid; line < 256; line += NT) {  // along x: line (t, y)
+        const int t = line >> 4, y = line & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(t, k, y)];
+        dct2_sr<16>(v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cube[cidx(t, k, y)] = v[k];
+    }
+    __syncthreads();
+    for (int line = tid; line < 256; line += NT) {  // along t: line (x, y)
+        const int x = line >> 4, y = line & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(k, x, y)];
+        dct2_sr<16>(v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cube[cidx(k, x, y)] = v[k];
+    }
+    __syncthreads();
+    for (int b = tid; b < 1024; b += NT) {
+        bool bit = false;
+        if (b < VDF_HASH_BITS) {
+            const int t = b / 100, x = (b / 10) % 10, y = b % 10;
+            bit = cube[cidx(t, x, y)] > 0.0;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if ((tid & 31) == 0) out[b >> 5] = word;
+    }
+}
+
+// stand-alone form (Dct3d::from_images + hash_bits on an already resized cube: vdf_hash_from_small, parity taps)
+__global__ void __launch_bounds__(256) dct_pack_kernel(const uint8_t* __restrict__ small, const int32_t* __restrict__ status,
+                                                       uint32_t n, uint32_t* __restrict__ out_hash /* [n][32] u32 */) {
+    __shared__ double cube[16 * 16 * 17];
+    const uint32_t s = blockIdx.x;
+    const int tid = threadIdx.x;
+    uint32_t* out = out_hash + (uint64_t)s * 32;
+    if (status && status[s] != VDF_STACK_OK) {
+        if (tid < 32) out[tid] = 0;
+        return;
+    }
+    dct_pack_block<256>(small + (uint64_t)s * 4096, cube, out, tid);
+}
+
+// The thread block that completes a stack's 16th frame turns the stack's cube (4 KB, just written, L2-resident) into the
+// hash: every block publishes its 256 output bytes (fence), then counts itself in; the one that counts 16 hashes.
+template <int NT>
+__device__ __forceinline__ void finish_stack(uint8_t* __restrict__ small, uint32_t s, uint32_t* __restrict__ done, uint32_t* __restrict__ out_hash,
+                                             double* cube, int tid) {
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&done[s], 1u) == 15u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    dct_pack_block<NT>(small + (uint64_t)s * 4096, cube, out_hash + (uint64_t)s * 32, tid);
+}
+
+
 // ================================================================================ H3: crop + Lanczos3 resize
+constexpr int32_t kJobSkip = 100;  // internal status: nothing to do for this stack in this pass (missed table, or done already)
+
 struct StackJob {
     uint64_t offset, frame_stride;
     uint32_t pitch, left, top, cw, ch;
@@ -275,8 +453,9 @@ __device__ __forceinline__ uint8_t clip8(int32_t v, uint32_t precision) {
 // (the reference rounds to u8 between the passes); vertical pass: one thread per output pixel.
 __global__ void __launch_bounds__(256) resize_general_kernel(const uint8_t* __restrict__ frames,
                                                              const StackJob* __restrict__ jobs,
-                                                             uint8_t* __restrict__ small /* [n][16][16][16] */) {
-    extern __shared__ uint8_t tmp[];  // ch x 16
+                                                             uint8_t* small /* [n][16][16][16] */, uint32_t* __restrict__ done,
+                                                             uint32_t* __restrict__ out_hash) {
+    extern __shared__ __align__(16) uint8_t tmp[];  // ch x 16 (and the DCT cube of the stack's last frame)
     const uint32_t s = blockIdx.x >> 4, t = blockIdx.x & 15;
     const StackJob j = jobs[s];
     if (j.status != VDF_STACK_OK || j.fast) return;
@@ -301,6 +480,7 @@ __global__ void __launch_bounds__(256) resize_general_kernel(const uint8_t* __re
         for (uint32_t q = 0; q < sz; ++q) acc += (int32_t)tmp[(s0 + q) * 16 + ox] * (int32_t)k[q];
         small[((uint64_t)s * 16 + t) * 256 + it] = clip8(acc, j.prec_v);
     }
+    if (out_hash) finish_stack<256>(small, s, done, out_hash, reinterpret_cast<double*>(tmp), threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -355,7 +535,8 @@ struct ResizeMma {
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
-    resize_mma_kernel(const uint8_t* __restrict__ frames, const StackJob* __restrict__ jobs, uint8_t* __restrict__ small) {
+    resize_mma_kernel(const uint8_t* __restrict__ frames, const StackJob* __restrict__ jobs, uint8_t* small, uint32_t* __restrict__ done,
+                      uint32_t* __restrict__ out_hash) {
     using Cfg = ResizeMma<WARPS>;
     constexpr int kRowsPerPass = Cfg::kThreads / 8;        // rows covered by one 16-byte copy per thread
     constexpr int kCopies = Cfg::kRows / kRowsPerPass;     // pixel copies per thread per stage
@@ -518,136 +699,62 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
         for (uint32_t q = 0; q < sz; ++q) a += (int32_t)px[q * 16] * (int32_t)k[q];
         small[((uint64_t)s * 16 + t) * 256 + it] = clip8(a, j.prec_v);
     }
+    if (out_hash) finish_stack<Cfg::kThreads>(small, s, done, out_hash, reinterpret_cast<double*>(ring), tid);
 }
 
-// ================================================================================ H4 + H5: 3-D DCT, threshold, pack
-// twiddles: [0..7] n=16 (re,im) x4, [8..11] n=8 (re,im) x2, [12..13] n=4, [14] FRAC_1_SQRT_2
-__constant__ double c_tw[16];
+// ================================================================================ resize jobs, built on the device
+// size -> coefficient table (one axis), and (cropped width, left & 15) -> tensor-core B fragments: lookup tables in HBM that
+// the host fills as it builds tables (the arithmetic is the reference's: f64, libm sin).  A zero entry = not built yet.
+constexpr uint32_t kMaxDim = 16384;
+struct CoefRef {
+    const uint32_t* bounds;
+    const int16_t* k;
+    uint32_t window, precision;
+};
+struct BFragRef {
+    const uint2* kb;
+    const uint8_t* kmask;
+};
 
-__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-
-__device__ __forceinline__ void dct2_2(double& b0, double& b1) {
-    const double s = dadd(b0, b1);
-    b1 = dmul(dsub(b0, b1), c_tw[14]);
-    b0 = s;
-}
-__device__ __forceinline__ void dct2_4(double* b) {
-    const double re = c_tw[12], im = c_tw[13];
-    const double lower = dsub(b[0], b[3]), upper = dsub(b[2], b[1]);
-    double e0 = dadd(b[0], b[3]), e1 = dadd(b[1], b[2]);
-    dct2_2(e0, e1);
-    b[0] = e0;
-    b[1] = dsub(dmul(lower, re), dmul(upper, im));
-    b[2] = e1;
-    b[3] = dadd(dmul(upper, re), dmul(lower, im));
-}
-// split radix: one half-size DCT-II on the mirrored sums, two quarter-size DCT-IIs on the rotated differences
-template <int N>
-__device__ __forceinline__ void dct2_sr(double* x);
-template <>
-__device__ __forceinline__ void dct2_sr<2>(double* x) {
-    dct2_2(x[0], x[1]);
-}
-template <>
-__device__ __forceinline__ void dct2_sr<4>(double* x) {
-    dct2_4(x);
-}
-template <int N>
-__device__ __forceinline__ void dct2_sr(double* x) {
-    constexpr int H = N / 2, Q = N / 4;
-    constexpr int TW = (N == 16) ? 0 : 8;
-    double d2[H], ev[Q], od[Q];
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const double bot = x[i], top = x[N - 1 - i];
-        const double hb = x[H - 1 - i], ht = x[H + i];
-        d2[i] = dadd(top, bot);
-        d2[H - 1 - i] = dadd(hb, ht);
-        const double lower = dsub(bot, top), upper = dsub(hb, ht);
-        const double re = c_tw[TW + 2 * i], im = c_tw[TW + 2 * i + 1];
-        const double c = dadd(dmul(lower, re), dmul(upper, im));
-        const double s = dsub(dmul(upper, re), dmul(lower, im));
-        ev[i] = c;
-        od[Q - 1 - i] = (i % 2 == 0) ? s : -s;
-    }
-    dct2_sr<H>(d2);
-    dct2_sr<Q>(ev);
-    dct2_sr<Q>(od);
-    x[0] = d2[0];
-    x[1] = ev[0];
-    x[2] = d2[1];
-#pragma unroll
-    for (int i = 1; i < Q; ++i) {
-        const double c = ev[i];
-        const double s = ((i + Q) % 2 == 0) ? -od[Q - i] : od[Q - i];
-        x[4 * i - 1] = dadd(c, s);
-        x[4 * i] = d2[2 * i];
-        x[4 * i + 1] = dsub(c, s);
-        x[4 * i + 2] = d2[2 * i + 1];
-    }
-    x[N - 1] = -od[0];
-}
-
-// cube index with a 17-double row pitch: conflict-free for all three passes
-__device__ __forceinline__ int cidx(int t, int x, int y) { return (t * 16 + x) * 17 + y; }
-
-// one CTA (256 threads) per stack: small [t][row][col] u8 -> m[t][x=col][y=row] = p - 128 (dct_3d.rs:40-44,76),
-// DCT along y, x, t (raw_dct_ops.rs:107-142), bit t*100+x*10+y = coef > 0.0 (dct_3d.rs:55-66), Lsb0 words.
-__global__ void __launch_bounds__(256) dct_pack_kernel(const uint8_t* __restrict__ small, const int32_t* __restrict__ status,
-                                                       uint32_t n, uint32_t* __restrict__ out_hash /* [n][32] u32 */) {
-    __shared__ double cube[16 * 16 * 17];
-    const uint32_t s = blockIdx.x;
-    const int tid = threadIdx.x;
-    uint32_t* out = out_hash + (uint64_t)s * 32;
-    if (status && status[s] != VDF_STACK_OK) {
-        if (tid < 32) out[tid] = 0;
-        return;
-    }
-    const uint8_t* sm = small + (uint64_t)s * 4096;
-    for (int q = tid; q < 4096; q += 256) {
-        const int t = q >> 8, row = (q >> 4) & 15, col = q & 15;
-        cube[cidx(t, col, row)] = (double)sm[q] - 128.0;
-    }
-    __syncthreads();
-    double v[16];
-    {  // along y: line (t, x) = tid
-        const int t = tid >> 4, x = tid & 15;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(t, x, k)];
-        dct2_sr<16>(v);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) cube[cidx(t, x, k)] = v[k];
-    }
-    __syncthreads();
-    {  // along x: line (t, y)
-        const int t = tid >> 4, y = tid & 15;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(t, k, y)];
-        dct2_sr<16>(v);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) cube[cidx(t, k, y)] = v[k];
-    }
-    __syncthreads();
-    {  // along t: line (x, y)
-        const int x = tid >> 4, y = tid & 15;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = cube[cidx(k, x, y)];
-        dct2_sr<16>(v);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) cube[cidx(k, x, y)] = v[k];
-    }
-    __syncthreads();
-    for (int b = tid; b < 1024; b += 256) {
-        bool bit = false;
-        if (b < VDF_HASH_BITS) {
-            const int t = b / 100, x = (b / 10) % 10, y = b % 10;
-            bit = cube[cidx(t, x, y)] > 0.0;
+// one thread per stack: crop -> StackJob (what the host did in round 1 between two kernels, with a synchronise in between)
+__global__ void job_build_kernel(const StackDev* __restrict__ stacks, const uint32_t* __restrict__ crop, uint32_t n,
+                                 const CoefRef* __restrict__ coef_lut, const BFragRef* __restrict__ bfrag_lut, uint32_t ring_bytes,
+                                 uint32_t allow_fast, uint32_t only_missed, StackJob* __restrict__ jobs, uint32_t* __restrict__ miss,
+                                 uint32_t* __restrict__ n_miss) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    StackJob j;
+    memset(&j, 0, sizeof j);
+    const StackDev d = stacks[s];
+    j.status = d.status;
+    if (d.status == VDF_STACK_OK && only_missed && !miss[s]) j.status = kJobSkip;  // hashed in the first pass
+    if (j.status == VDF_STACK_OK) {
+        const uint32_t* c = crop + (size_t)s * 4;
+        j.offset = d.offset, j.frame_stride = d.frame_stride, j.pitch = d.pitch;
+        j.left = c[0], j.top = c[2];
+        j.cw = d.width - c[0] - c[1], j.ch = d.height - c[2] - c[3];  // Crop::as_view_args, crop.rs:92-103
+        const CoefRef th = coef_lut[j.cw], tv = coef_lut[j.ch];
+        const uint32_t shift = j.left & 15u;
+        const bool fits = (shift + j.cw + kKch - 1) / kKch <= 256 && 32u * tv.window <= ring_bytes;
+        const bool fast = d.aligned && fits && allow_fast;
+        const BFragRef bf = fast ? bfrag_lut[(size_t)j.cw * 16 + shift] : BFragRef{nullptr, nullptr};
+        if (!th.k || !tv.k || (fast && !bf.kb)) {  // a size seen for the first time: the host builds it, the stack runs again
+            miss[s] = 1;
+            atomicAdd(n_miss, 1u);
+            j.status = kJobSkip;
+        } else {
+            miss[s] = 0;
+            j.bh = th.bounds, j.kh = th.k, j.win_h = th.window, j.prec_h = th.precision;
+            j.bv = tv.bounds, j.kv = tv.k, j.win_v = tv.window, j.prec_v = tv.precision;
+            if (fast) {
+                j.x0_al = j.left & ~15u;
+                j.n_kch = (shift + j.cw + kKch - 1) / kKch;
+                j.kb = bf.kb, j.kmask = bf.kmask;
+                j.fast = 1;
+            }
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, bit);
-        if ((tid & 31) == 0) out[b >> 5] = word;
     }
+    jobs[s] = j;
 }
 
 // ================================================================================ host side
@@ -713,15 +820,27 @@ static void build_table(uint32_t in_size, CoefTable& t) {
     t.precision = precision;
 }
 
+static int ensure_luts(vdf_ctx* ctx) {
+    if (ctx->h_coef_lut.p) return VDF_OK;
+    VDF_ALLOC(ctx, ctx->h_coef_lut.ensure((size_t)(kMaxDim + 1) * sizeof(CoefRef)));
+    VDF_ALLOC(ctx, ctx->h_bfrag_lut.ensure((size_t)(kMaxDim + 1) * 16 * sizeof(BFragRef)));
+    VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_coef_lut.p, 0, (size_t)(kMaxDim + 1) * sizeof(CoefRef), ctx->stream));
+    VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_bfrag_lut.p, 0, (size_t)(kMaxDim + 1) * 16 * sizeof(BFragRef), ctx->stream));
+    return VDF_OK;
+}
+
 static int get_table(vdf_ctx* ctx, uint32_t in_size, const CoefTable** out) {
     auto it = ctx->coef_cache.find(in_size);
     if (it == ctx->coef_cache.end()) {
+        VDF_TRY(ensure_luts(ctx));
         CoefTable t;
         build_table(in_size, t);
         VDF_ALLOC(ctx, cudaMalloc(&t.d_bounds, t.h_bounds.size() * 4));
         VDF_ALLOC(ctx, cudaMalloc(&t.d_k, t.h_k.size() * 2));
         VDF_CUDA(ctx, cudaMemcpyAsync(t.d_bounds, t.h_bounds.data(), t.h_bounds.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         VDF_CUDA(ctx, cudaMemcpyAsync(t.d_k, t.h_k.data(), t.h_k.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        const CoefRef ref{t.d_bounds, t.d_k, t.window, t.precision};
+        VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_coef_lut.as<CoefRef>() + in_size, &ref, sizeof ref, cudaMemcpyHostToDevice, ctx->stream));
         VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors may move when the map rebalances
         it = ctx->coef_cache.emplace(in_size, std::move(t)).first;
     }
@@ -738,6 +857,8 @@ void free_coef_cache(vdf_ctx* ctx) {
     ctx->coef_cache.clear();
     for (auto& kv : ctx->bfrag_cache) cudaFree(kv.second);
     ctx->bfrag_cache.clear();
+    ctx->h_coef_lut.release();
+    ctx->h_bfrag_lut.release();
 }
 
 // IMMA B fragments of the horizontal coefficients for a crop that starts `shift` bytes after a 16-byte boundary:
@@ -782,6 +903,10 @@ static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const ui
         void* d = nullptr;
         VDF_ALLOC(ctx, cudaMalloc(&d, frag.size() * 4));
         VDF_CUDA(ctx, cudaMemcpyAsync(d, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        const BFragRef ref{reinterpret_cast<const uint2*>(d), reinterpret_cast<const uint8_t*>(d) + (size_t)n_kch * kBFragBytes};
+        VDF_TRY(ensure_luts(ctx));
+        VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_bfrag_lut.as<BFragRef>() + (size_t)t.in_size * 16 + shift, &ref, sizeof ref, cudaMemcpyHostToDevice,
+                                      ctx->stream));
         VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         it = ctx->bfrag_cache.emplace(key, d).first;
     }
@@ -826,142 +951,198 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         return VDF_ERR_INVALID;
     }
     VDF_TRY(load_dct_consts(ctx));
+    VDF_TRY(ensure_luts(ctx));
     cudaStream_t st = ctx->stream;
-    // status per stack, decided on the host exactly where the reference decides it
-    std::vector<StackDev> sd(n);
-    std::vector<int32_t> status(n);
+    if (!ctx->lb_stream) {
+        VDF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lb_stream, cudaStreamNonBlocking));
+        VDF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+    }
+    const bool four_warps = ctx->hash_variant != 2;  // default: 4 warps, two CTAs per SM
+    const size_t ring = four_warps ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
+    const bool allow_fast = ctx->hash_variant != 1;
+    // status per stack, decided on the host exactly where the reference decides it; tables of the UNCROPPED sizes are made
+    // sure of here (most stacks have no bars), every other size is met through a miss
+    VDF_ALLOC(ctx, ctx->pin_b.ensure((size_t)n * (sizeof(StackDev) + 4 + 4)));
+    StackDev* sd = ctx->pin_b.as<StackDev>();
+    int32_t* status = reinterpret_cast<int32_t*>(sd + n);
+    uint32_t* h_miss = reinterpret_cast<uint32_t*>(status + n);
+    uint32_t max_h = 1;
+    bool any_unaligned = false, all_fit = true;
+    uint64_t last_wh = ~0ull;
     for (uint32_t s = 0; s < n; ++s) {
         const vdf_stack_desc& d = desc[s];
         int32_t stt = VDF_STACK_OK;
         if (d.flags & VDF_STACK_FLAG_MIXED_SIZES) stt = VDF_STACK_VIDPROC;         // video_hash_builder.rs:169-186
         else if (d.n_frames < VDF_DCT_SIZE) stt = VDF_STACK_NOT_ENOUGH_FRAMES;     // dct_3d.rs:47-52
-        else if (d.width == 0 || d.height == 0 || d.pitch < d.width) {
-            ctx->err = "stack " + std::to_string(s) + ": bad geometry";
+        else if (d.width == 0 || d.height == 0 || d.pitch < d.width || d.width > kMaxDim || d.height > kMaxDim) {
+            ctx->err = "stack " + std::to_string(s) + ": bad geometry (frames up to " + std::to_string(kMaxDim) + " pixels a side)";
             return VDF_ERR_INVALID;
         }
         status[s] = stt;
-        sd[s] = StackDev{d.offset, d.frame_stride, d.width, d.height, d.pitch, stt};
+        // tensor-core path needs 16-byte aligned rows (cp.async 16 B): base, frame stride and pitch
+        const bool aligned = ((reinterpret_cast<uintptr_t>(d_frames) + d.offset) % 16 == 0) && d.frame_stride % 16 == 0 && d.pitch % 16 == 0;
+        sd[s] = StackDev{d.offset, d.frame_stride, d.width, d.height, d.pitch, stt, aligned ? 1u : 0u, 0u};
+        if (stt != VDF_STACK_OK) continue;
+        max_h = std::max(max_h, d.height);
+        any_unaligned |= !aligned;
+        const uint64_t wh = ((uint64_t)d.width << 32) | d.height;
+        if (wh != last_wh) {
+            const CoefTable *th, *tv;
+            VDF_TRY(get_table(ctx, d.width, &th));
+            VDF_TRY(get_table(ctx, d.height, &tv));
+            const bool fits = (15 + d.width + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring;  // a crop only shrinks both
+            all_fit &= fits;
+            if (aligned && fits && allow_fast) {
+                const uint2* kb;
+                const uint8_t* km;
+                VDF_TRY(get_bfrags(ctx, *th, 0, &kb, &km));
+            }
+            last_wh = wh;
+        }
     }
-    // Software pipeline over chunks of stacks: the crops have to visit the host (the i16 coefficient tables depend on the
-    // cropped size and are made with libm sin, like the reference), so all letterbox chunks are enqueued first, each
-    // followed by an async read-back of its crops into pinned memory and an event; the host then builds chunk k's resize
-    // jobs while the GPU is still busy with later letterbox chunks / earlier resize chunks.  One stream, no idle gap.
-    const uint32_t kMaxChunks = 4;
-    const uint32_t n_chunks = std::max(1u, std::min(std::min(kMaxChunks, ctx->hash_chunks), n / 32));
-    auto chunk_begin = [&](uint32_t k) { return (uint32_t)((uint64_t)n * k / n_chunks); };
+    const size_t tmp_bytes = (size_t)max_h * 16;
+    if (tmp_bytes + ring > 220 * 1024) {
+        ctx->err = "frame height beyond the resize kernels' shared-memory budget";
+        return VDF_ERR_INVALID;
+    }
     VDF_ALLOC(ctx, ctx->pin_a.ensure((size_t)n * 16));
     uint32_t* crop = ctx->pin_a.as<uint32_t>();
-    std::memset(crop, 0, (size_t)n * 16);
-    VDF_ALLOC(ctx, ctx->h_jobs.ensure((size_t)n * sizeof(StackJob) + (size_t)n * 4));
+    VDF_ALLOC(ctx, ctx->h_jobs.ensure((size_t)n * sizeof(StackJob)));
+    VDF_ALLOC(ctx, ctx->h_desc.ensure((size_t)n * sizeof(StackDev)));
+    VDF_ALLOC(ctx, ctx->h_sides.ensure((size_t)n * 8 * 4));
+    VDF_ALLOC(ctx, ctx->h_crop.ensure((size_t)n * 4 * 4));
+    VDF_ALLOC(ctx, ctx->h_done.ensure((size_t)n * 4 * 2 + 64));
     StackJob* d_jobs = ctx->h_jobs.as<StackJob>();
-    int32_t* d_status = reinterpret_cast<int32_t*>(d_jobs + n);
-    VDF_CUDA(ctx, cudaMemcpyAsync(d_status, status.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    if (cropdetect == VDF_CROPDETECT_LETTERBOX) {
-        VDF_ALLOC(ctx, ctx->h_desc.ensure((size_t)n * sizeof(StackDev)));
-        VDF_ALLOC(ctx, ctx->h_sides.ensure((size_t)n * 8 * 4));
-        VDF_ALLOC(ctx, ctx->h_crop.ensure((size_t)n * 4 * 4));
-        VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_desc.p, sd.data(), (size_t)n * sizeof(StackDev), cudaMemcpyHostToDevice, st));
-        VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_sides.p, 0, (size_t)n * 8 * 4, st));
-        kt_begin(ctx, 2);
-        for (uint32_t k = 0; k < n_chunks; ++k) {
-            const uint32_t s0 = chunk_begin(k), cnt = chunk_begin(k + 1) - s0;
-            letterbox_side_kernel<<<cnt * 8, 256, 0, st>>>(d_frames, ctx->h_desc.as<StackDev>() + s0,
-                                                          ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8);
-            VDF_LAUNCHED(ctx);
-            crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(ctx->h_desc.as<StackDev>() + s0,
-                                                                   ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt,
-                                                                   ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4);
-            VDF_LAUNCHED(ctx);
-            VDF_CUDA(ctx, cudaMemcpyAsync(crop + (size_t)s0 * 4, ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4, (size_t)cnt * 16,
-                                          cudaMemcpyDeviceToHost, st));
-            VDF_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[k], st));
-        }
-        kt_end(ctx, 2);
-    }
+    StackDev* d_sd = ctx->h_desc.as<StackDev>();
+    uint32_t* d_done = ctx->h_done.as<uint32_t>();
+    uint32_t* d_miss = d_done + n;
+    uint32_t* d_nmiss = d_miss + n;
     uint8_t* d_small = d_out_small;
     if (!d_small) {
         VDF_ALLOC(ctx, ctx->h_small.ensure((size_t)n * 4096));
         d_small = ctx->h_small.as<uint8_t>();
     }
-    const bool four_warps = ctx->hash_variant != 2;  // default: 4 warps, two CTAs per SM
-    const size_t ring = four_warps ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
-    auto want_smem = [&](int slot, const void* fn, size_t bytes) -> int {  // per device, hence kept in the context
-        if (bytes > 48 * 1024 && bytes > ctx->hash_smem_set[slot]) {
-            VDF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            ctx->hash_smem_set[slot] = bytes;
+    uint32_t* d_hash32 = reinterpret_cast<uint32_t*>(d_out_hash);
+    VDF_CUDA(ctx, cudaMemcpyAsync(d_sd, sd, (size_t)n * sizeof(StackDev), cudaMemcpyHostToDevice, st));
+    VDF_CUDA(ctx, cudaMemsetAsync(d_done, 0, (size_t)n * 8 + 64, st));
+    if (d_out_hash) VDF_CUDA(ctx, cudaMemsetAsync(d_out_hash, 0, (size_t)n * 128, st));  // stacks that are not hashed read as zero
+    // The opt-in is per device AND per function, whoever sets it last wins: every context asks for the device's maximum, once,
+    // so that contexts sharing a GPU can never lower each other's limit (kept per context because it is per device).
+    const size_t gen_smem = std::max<size_t>(tmp_bytes, kCubeBytes);
+    if (!ctx->hash_smem_set[0]) {
+        int optin = 0;
+        VDF_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        VDF_CUDA(ctx, cudaFuncSetAttribute((const void*)resize_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        VDF_CUDA(ctx, cudaFuncSetAttribute((const void*)resize_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        VDF_CUDA(ctx, cudaFuncSetAttribute((const void*)resize_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        ctx->hash_smem_set[0] = (size_t)optin;
+    }
+    if (tmp_bytes + ring > ctx->hash_smem_set[0] || gen_smem > ctx->hash_smem_set[0]) {
+        ctx->err = "frame height beyond the resize kernels' shared-memory budget";
+        return VDF_ERR_INVALID;
+    }
+    const bool run_general = any_unaligned || !all_fit || !allow_fast;
+
+    // Chunks of stacks: the letterbox scan of chunk k+1 runs on a second stream beside the resize of chunk k (the scan is a
+    // latency-bound strip walk over 0.6 % of the bytes: alone it held the GPU for 12 % of the step in round 1)
+    const uint32_t kMaxChunks = 4;
+    const uint32_t n_chunks = std::max(1u, std::min(std::min(kMaxChunks, ctx->hash_chunks), n / 32));
+    auto chunk_begin = [&](uint32_t k) { return (uint32_t)((uint64_t)n * k / n_chunks); };
+    const bool letterbox = cropdetect == VDF_CROPDETECT_LETTERBOX;
+    cudaStream_t lb = ctx->hash_overlap ? ctx->lb_stream : st;
+    if (letterbox) {
+        VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_sides.p, 0, (size_t)n * 8 * 4, st));
+        if (lb != st) {
+            VDF_CUDA(ctx, cudaEventRecord(ctx->ev_in, st));
+            VDF_CUDA(ctx, cudaStreamWaitEvent(lb, ctx->ev_in, 0));
         }
+        kt_begin(ctx, 2, lb);
+        if (lb != st) {  // all scans are enqueued up front on their own stream; the resize of chunk k waits for scan k only
+            for (uint32_t k = 0; k < n_chunks; ++k) {
+                const uint32_t s0 = chunk_begin(k), cnt = chunk_begin(k + 1) - s0;
+                letterbox_side_kernel<<<cnt * 8, 256, 0, lb>>>(d_frames, d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8);
+                VDF_LAUNCHED(ctx);
+                crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, lb>>>(d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt,
+                                                                      ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4);
+                VDF_LAUNCHED(ctx);
+                VDF_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[k], lb));
+            }
+            kt_end(ctx, 2, lb);
+        }
+    } else {
+        VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_crop.p, 0, (size_t)n * 16, st));  // Cropdetect::None: zero crop (:195-199)
+    }
+    auto run_pass = [&](bool only_missed) -> int {
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            const uint32_t s0 = chunk_begin(k), cnt = chunk_begin(k + 1) - s0;
+            if (letterbox && !only_missed) {
+                if (lb != st) {
+                    VDF_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_chunk[k], 0));
+                } else {
+                    letterbox_side_kernel<<<cnt * 8, 256, 0, st>>>(d_frames, d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8);
+                    VDF_LAUNCHED(ctx);
+                    crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt,
+                                                                          ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4);
+                    VDF_LAUNCHED(ctx);
+                    if (k == n_chunks - 1) kt_end(ctx, 2);
+                }
+            }
+            if (k == 0 && !only_missed) kt_begin(ctx, 1);
+            job_build_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(d_sd + s0, ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4, cnt,
+                                                                ctx->h_coef_lut.as<CoefRef>(), ctx->h_bfrag_lut.as<BFragRef>(), (uint32_t)ring,
+                                                                allow_fast ? 1u : 0u, only_missed ? 1u : 0u, d_jobs + s0, d_miss + s0, d_nmiss);
+            VDF_LAUNCHED(ctx);
+            if (allow_fast) {
+                if (four_warps)
+                    resize_mma_kernel<4><<<cnt * 16, 128, tmp_bytes + ring, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096, d_done + s0,
+                                                                                 d_hash32 ? d_hash32 + (size_t)s0 * 32 : nullptr);
+                else
+                    resize_mma_kernel<8><<<cnt * 16, 256, tmp_bytes + ring, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096, d_done + s0,
+                                                                                 d_hash32 ? d_hash32 + (size_t)s0 * 32 : nullptr);
+                VDF_LAUNCHED(ctx);
+            }
+            if (run_general || only_missed) {
+                resize_general_kernel<<<cnt * 16, 256, gen_smem, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096, d_done + s0,
+                                                                       d_hash32 ? d_hash32 + (size_t)s0 * 32 : nullptr);
+                VDF_LAUNCHED(ctx);
+            }
+        }
+        if (!only_missed) kt_end(ctx, 1);
         return VDF_OK;
     };
-    std::vector<StackJob> jobs(n);
-    for (uint32_t k = 0; k < n_chunks; ++k) {
-        const uint32_t s0 = chunk_begin(k), s1 = chunk_begin(k + 1), cnt = s1 - s0;
-        if (cropdetect == VDF_CROPDETECT_LETTERBOX) VDF_CUDA(ctx, cudaEventSynchronize(ctx->ev_chunk[k]));
-        // coefficient tables for the cropped sizes (cached per size in HBM)
-        uint32_t max_ch = 1;
-        bool any_fast = false, any_slow = false;
-        for (uint32_t s = s0; s < s1; ++s) {
-            StackJob& j = jobs[s];
-            std::memset(&j, 0, sizeof j);
-            j.status = status[s];
-            if (status[s] != VDF_STACK_OK) continue;
-            const vdf_stack_desc& d = desc[s];
+    VDF_TRY(run_pass(false));
+    VDF_ALLOC(ctx, ctx->h_misc.ensure(256));
+    uint32_t* h_n = reinterpret_cast<uint32_t*>(ctx->h_misc.as<unsigned long long>() + 24);
+    VDF_CUDA(ctx, cudaMemcpyAsync(crop, ctx->h_crop.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (*h_n) {  // sizes met for the first time: build their tables (host, f64 + libm sin like the reference), run those stacks
+        VDF_CUDA(ctx, cudaMemcpyAsync(h_miss, d_miss, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        VDF_CUDA(ctx, cudaStreamSynchronize(st));
+        for (uint32_t s = 0; s < n; ++s) {
+            if (!h_miss[s]) continue;
             const uint32_t* c = &crop[(size_t)s * 4];
-            j.offset = d.offset, j.frame_stride = d.frame_stride, j.pitch = d.pitch;
-            j.left = c[0], j.top = c[2];
-            j.cw = d.width - c[0] - c[1], j.ch = d.height - c[2] - c[3];  // Crop::as_view_args, crop.rs:92-103
+            const uint32_t cw = desc[s].width - c[0] - c[1], chh = desc[s].height - c[2] - c[3];
             const CoefTable *th, *tv;
-            VDF_TRY(get_table(ctx, j.cw, &th));
-            VDF_TRY(get_table(ctx, j.ch, &tv));
-            j.bh = th->d_bounds, j.kh = th->d_k, j.win_h = th->window, j.prec_h = th->precision;
-            j.bv = tv->d_bounds, j.kv = tv->d_k, j.win_v = tv->window, j.prec_v = tv->precision;
-            max_ch = std::max(max_ch, j.ch);
-            // tensor-core path needs 16-byte aligned rows (cp.async 16 B): base, frame stride and pitch
-            const bool aligned = ((reinterpret_cast<uintptr_t>(d_frames) + d.offset) % 16 == 0) && d.frame_stride % 16 == 0 &&
-                                 d.pitch % 16 == 0;
-            const uint32_t shift = j.left & 15u;
-            const bool fits = (shift + j.cw + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring;
-            if (aligned && fits && ctx->hash_variant != 1) {
-                j.x0_al = j.left & ~15u;
-                j.n_kch = (shift + j.cw + kKch - 1) / kKch;
-                VDF_TRY(get_bfrags(ctx, *th, shift, &j.kb, &j.kmask));
-                j.fast = 1;
-                any_fast = true;
-            } else {
-                any_slow = true;
+            VDF_TRY(get_table(ctx, cw, &th));
+            VDF_TRY(get_table(ctx, chh, &tv));
+            const uint32_t shift = c[0] & 15u;
+            if (sd[s].aligned && allow_fast && (shift + cw + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring) {
+                const uint2* kb;
+                const uint8_t* km;
+                VDF_TRY(get_bfrags(ctx, *th, shift, &kb, &km));
             }
         }
-        VDF_CUDA(ctx, cudaMemcpyAsync(d_jobs + s0, jobs.data() + s0, (size_t)cnt * sizeof(StackJob), cudaMemcpyHostToDevice, st));
-        const size_t tmp_bytes = (size_t)max_ch * 16;
-        if (tmp_bytes + ring > 220 * 1024) {
-            ctx->err = "frame height beyond the resize kernels' shared-memory budget";
-            return VDF_ERR_INVALID;
-        }
-        if (k == 0) kt_begin(ctx, 1);
-        if (any_fast) {
-            if (four_warps) {
-                VDF_TRY(want_smem(1, (const void*)resize_mma_kernel<4>, tmp_bytes + ring));
-                resize_mma_kernel<4><<<cnt * 16, 128, tmp_bytes + ring, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096);
-            } else {
-                VDF_TRY(want_smem(2, (const void*)resize_mma_kernel<8>, tmp_bytes + ring));
-                resize_mma_kernel<8><<<cnt * 16, 256, tmp_bytes + ring, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096);
-            }
-            VDF_LAUNCHED(ctx);
-        }
-        if (any_slow) {
-            VDF_TRY(want_smem(0, (const void*)resize_general_kernel, tmp_bytes));
-            resize_general_kernel<<<cnt * 16, 256, tmp_bytes, st>>>(d_frames, d_jobs + s0, d_small + (size_t)s0 * 4096);
-            VDF_LAUNCHED(ctx);
+        VDF_CUDA(ctx, cudaMemsetAsync(d_nmiss, 0, 4, st));
+        VDF_TRY(run_pass(true));
+        VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
+        VDF_CUDA(ctx, cudaStreamSynchronize(st));
+        if (*h_n) {
+            ctx->err = "resize tables still missing after the second pass";
+            return VDF_ERR_CUDA;
         }
     }
-    kt_end(ctx, 1);
-    if (d_out_hash) {
-        kt_begin(ctx, 3);
-        dct_pack_kernel<<<n, 256, 0, st>>>(d_small, d_status, n, reinterpret_cast<uint32_t*>(d_out_hash));
-        kt_end(ctx, 3);
-        VDF_LAUNCHED(ctx);
-    }
-    VDF_CUDA(ctx, cudaStreamSynchronize(st));  // jobs/status host vectors go out of scope
-    if (out_status) std::memcpy(out_status, status.data(), (size_t)n * 4);
+    if (out_status) std::memcpy(out_status, status, (size_t)n * 4);
     if (out_crop) std::memcpy(out_crop, crop, (size_t)n * 16);
     return VDF_OK;
 }

@@ -556,6 +556,27 @@ int vdf_sort_order(const uint32_t* durations, const char* path_blob, const uint6
     return VDF_OK;
 }
 
+int vdf_sort_order_device(vdf_ctx* ctx, const uint32_t* durations, const char* path_blob, const uint64_t* path_off, uint64_t n,
+                          uint32_t* d_order_out, uint32_t* d_dur_sorted_out) {
+    VDF_TRY(enter(ctx));
+    if ((n && (!durations || !path_off || !d_order_out)) || n >= 0xFFFFFF00ull) return VDF_ERR_INVALID;
+    if (n == 0) return VDF_OK;
+    const double t0 = now_ms();
+    VDF_ALLOC(ctx, ctx->pin_c.ensure(n * 20));
+    uint64_t* p1 = ctx->pin_c.as<uint64_t>();
+    uint64_t* p2 = p1 + n;
+    uint32_t* pd = reinterpret_cast<uint32_t*>(p2 + n);
+    uint64_t skip = 0;
+    build_prefix_keys(durations, path_blob, path_off, n, pd, p1, p2, &skip);
+    const double t1 = now_ms();
+    VDF_TRY(gpu_sort(ctx, durations, path_blob, path_off, n, pd, p1, p2, skip));
+    VDF_CUDA(ctx, cudaMemcpyAsync(d_order_out, ctx->sk_order.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_dur_sorted_out) VDF_CUDA(ctx, cudaMemcpyAsync(d_dur_sorted_out, ctx->in_dur.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->phase_ms[0] = t1 - t0, ctx->phase_ms[1] = now_ms() - t1, ctx->phase_ms[2] = ctx->phase_ms[3] = 0;
+    return VDF_OK;
+}
+
 int vdf_stage_sorted(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* durations, const char* path_blob, const uint64_t* path_off,
                      uint64_t n, uint64_t* order_out, uint64_t* d_hash_dst, uint32_t* d_dur_dst, const uint64_t** d_hash_sorted,
                      const uint32_t** d_dur_sorted) {
