@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libvdf_b200.so")
+_SO = os.environ.get("VDF_B200_SO") or os.path.join(_HERE, "libvdf_b200.so")  # the override is for kernel experiments (scripts/)
 
 OK = 0
 ERR_CUDA, ERR_ALLOC, ERR_INVALID, ERR_EDGE_OVERFLOW, ERR_NO_DEVICE = -1, -2, -3, -4, -5

@@ -279,6 +279,7 @@ static int enter(vdf_ctx* ctx) {
         ctx->err = "cudaSetDevice failed";
         return VDF_ERR_CUDA;
     }
+    cudaGetLastError();  // an error a previous call already reported must not be picked up by this one's launch checks
     return VDF_OK;
 }
 

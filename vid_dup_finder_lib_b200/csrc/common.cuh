@@ -247,6 +247,7 @@ struct vdf_ctx {
         if (e__ != cudaSuccess) {                                                                 \
             (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
                          std::to_string(__LINE__) + ")";                                          \
+            cudaGetLastError();                                                                   \
             return VDF_ERR_CUDA;                                                                  \
         }                                                                                         \
     } while (0)

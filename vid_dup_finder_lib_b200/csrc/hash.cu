@@ -1032,10 +1032,16 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     if (!ctx->hash_smem_set[0]) {
         int optin = 0;
         VDF_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-        VDF_CUDA(ctx, cudaFuncSetAttribute((const void*)resize_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        VDF_CUDA(ctx, cudaFuncSetAttribute((const void*)resize_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        VDF_CUDA(ctx, cudaFuncSetAttribute((const void*)resize_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        ctx->hash_smem_set[0] = (size_t)optin;
+        const void* fns[3] = {(const void*)resize_mma_kernel<4>, (const void*)resize_mma_kernel<8>, (const void*)resize_general_kernel};
+        size_t least = (size_t)optin;
+        for (const void* fn : fns) {  // dynamic limit = opt-in maximum minus the kernel's static shared memory
+            cudaFuncAttributes fa;
+            VDF_CUDA(ctx, cudaFuncGetAttributes(&fa, fn));
+            const size_t dyn = (size_t)optin - fa.sharedSizeBytes;
+            VDF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            least = std::min(least, dyn);
+        }
+        ctx->hash_smem_set[0] = least;
     }
     if (tmp_bytes + ring > ctx->hash_smem_set[0] || gen_smem > ctx->hash_smem_set[0]) {
         ctx->err = "frame height beyond the resize kernels' shared-memory budget";

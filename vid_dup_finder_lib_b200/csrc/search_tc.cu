@@ -12,9 +12,14 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+
 #include <cstring>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace vdf {
 
@@ -628,30 +633,27 @@ __global__ void tc6_unit_list_kernel(const TcParams p, uint32_t n_row_tiles, uin
     for (uint32_t k = 0; k < n; ++k) out[k] = ((uint64_t)(c_first + k * p.world) << 32) | P;
 }
 
-// Append the matches of one warp (lane = row, mask = its matching columns among the 64 starting at c0) with ONE atomic per
-// warp: window test as a bit range, warp prefix sum of the counts, the last lane reserves the slots.  Converged warp only.
-__device__ __forceinline__ void tc6_emit(const TcParams& p, uint64_t mask, uint32_t c0, uint32_t gi, uint32_t win_lo, uint32_t win_hi,
-                                         int lane) {
-    if (mask) {  // columns [win_lo, win_hi) of this row, as bits relative to c0
+// Append the matches of one row (mask = its matching columns among the 64 starting at c0).  Called ONLY by the lanes that
+// hold a match, so the common case (nothing within the tolerance) pays nothing: a warp-wide vote per 64 columns cost 14 % of
+// the whole kernel (144 against 126 ms per 1 M launch: the epilogue has no slack).  The lanes that did get here form a
+// coalesced group and share one atomic: at tolerances where a few per cent of all pairs match, per-match atomics on one
+// address would set the pace instead.
+__device__ __forceinline__ void tc6_emit(const TcParams& p, uint64_t mask, uint32_t c0, uint32_t gi, uint32_t win_lo, uint32_t win_hi) {
+    {   // columns [win_lo, win_hi) of this row, as bits relative to c0
         const long long a = (long long)win_lo - (long long)c0, b = (long long)win_hi - (long long)c0;
         const uint64_t below_b = b >= 64 ? ~0ull : b <= 0 ? 0ull : ((1ull << b) - 1);
         const uint64_t below_a = a >= 64 ? ~0ull : a <= 0 ? 0ull : ((1ull << a) - 1);
         mask &= below_b & ~below_a;
     }
+    const cg::coalesced_group g = cg::coalesced_threads();
     const uint32_t cnt = (uint32_t)__popcll(mask);
-    if (__ballot_sync(0xffffffffu, cnt != 0) == 0) return;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t before = cg::exclusive_scan(g, cnt, cg::plus<uint32_t>());
+    const uint32_t total = g.shfl(before + cnt, g.size() - 1);
+    if (total == 0) return;
     unsigned long long base = 0;
-    if (lane == 31) base = atomicAdd(p.counter, (unsigned long long)total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    unsigned long long slot = base + incl - cnt;
-    if (!mask) return;
+    if (g.thread_rank() == 0) base = atomicAdd(p.counter, (unsigned long long)total);
+    base = g.shfl(base, 0);
+    unsigned long long slot = base + before;
     const uint64_t rid = p.row_id ? p.row_id[gi] : gi;
     while (mask) {
         const int k = __ffsll((long long)mask) - 1;
@@ -665,6 +667,67 @@ __device__ __forceinline__ void tc6_emit(const TcParams& p, uint64_t mask, uint3
         }
         ++slot;
     }
+}
+
+// tcgen05.ld of 64 accumulator columns without the wait: the load of the next group is in flight while this one is screened
+__device__ __forceinline__ void tc_ld64_nowait(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,"
+        "%62,%63}, [%64];"
+        : TC_R8(v, 0), TC_R8(v, 8), TC_R8(v, 16), TC_R8(v, 24), TC_R8(v, 32), TC_R8(v, 40), TC_R8(v, 48), TC_R8(v, 56)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One row against 64 columns: -> the matching columns.
+//   fold:    acc = 2 dot - pc(j) + kFoldC is exact, so the signed-int maximum of the 64 bit patterns against the bit pattern
+//            of thr (> 0) is an exact screen (positive floats order like their bit patterns, negative ones are negative ints)
+//   no fold: acc = dot; first the bound 2 max(dot) - min(pc(j)), then the exact maximum of 2 dot - pc(j) on the FMA pipe
+//            (0x4B000000 | pc is the float 2^23 + pc: no int <-> float conversions, which run on the XU pipe at 16 per clock
+//            and made the 1 M launch 2.5x slower at tolerance 0.4), then the per-column mask
+template <bool kFold>
+__device__ __forceinline__ uint64_t tc6_screen(const uint32_t (&v)[64], int thr, float thr_f, bool screen, int thr_bits, int floor_pc,
+                                               const uint32_t* __restrict__ col_pc) {
+    uint64_t mask = 0;
+    if (kFold) {
+        int best = (int)v[0];
+#pragma unroll
+        for (int k = 0; k < 64; k += 2) best = max(best, max((int)v[k], (int)v[k + 1]));
+        if (!screen || best >= thr_bits) {  // only a row that really has a match among these 64 columns gets here
+#pragma unroll
+            for (int k = 0; k < 64; ++k) mask |= (uint64_t)(__uint_as_float(v[k]) >= thr_f) << k;
+        }
+    } else {
+        uint32_t best = 0;  // accumulators are non-negative floats: their bit patterns order like the values
+#pragma unroll
+        for (int k = 0; k < 64; k += 2) best = max(best, max(v[k], v[k + 1]));
+        if (2 * (int)__uint_as_float(best) - floor_pc >= thr) {
+            const uint4* pcj = reinterpret_cast<const uint4*>(col_pc);
+            float top = -3.0e38f;
+#pragma unroll
+            for (int k4 = 0; k4 < 16; ++k4) {
+                const uint4 pj = __ldg(pcj + k4);
+                top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)));
+                top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)));
+                top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)));
+                top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)));
+            }
+            if (top >= thr_f) {  // a pair of this row with one of the 64 columns is within the tolerance
+#pragma unroll
+                for (int k4 = 0; k4 < 16; ++k4) {
+                    const uint4 pj = __ldg(pcj + k4);
+                    mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)) >= thr_f) << (4 * k4 + 0);
+                    mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)) >= thr_f) << (4 * k4 + 1);
+                    mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)) >= thr_f) << (4 * k4 + 2);
+                    mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)) >= thr_f) << (4 * k4 + 3);
+                }
+            }
+        }
+    }
+    return mask;
 }
 
 // kATmem: K-chunks 0-2 of the row operand live in tensor memory (columns [384, 480), written once per unit with tcgen05.st)
@@ -815,7 +878,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
             tc_mbar_wait(&pfull[pb], (s / kPB) & 1);
             const uint32_t* packed = sP + pb * kTileWords + row0 * 8 + w;
             const uint4* fold_units = reinterpret_cast<const uint4*>(sP + pb * kTileWords + kT6PackedBytes / 4);
-            for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {  // unrolled: only K-chunk 3 carries the fold units, the other three stages pay nothing
                 uint32_t bits[kG];
 #pragma unroll
                 for (int g = 0; g < kG; ++g) bits[g] = packed[(kc * kT6Cols + g * (4 * kT6Expanders)) * 8];
@@ -823,12 +887,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
                 const uint32_t stage = it % kT6Stages;
                 tc_mbar_wait(&empty[stage], ((it / kT6Stages) & 1) ^ 1);
                 uint8_t* dst = sB + stage * kT6StageBytes;
-                const bool folded = kFold && kc == 3 && w == 7;  // the unit of hash word 31 comes precomputed with the column's digits
 #pragma unroll
                 for (int g = 0; g < kG; ++g) {
                     const int row = row0 + 4 * kT6Expanders * g;
                     uint4 e = tc6_expand(bits[g]);
-                    if (folded) e = fold_units[row];
+                    if (kFold && kc == 3 && w == 7) e = fold_units[row];  // the unit of hash word 31 comes precomputed with the column's digits
                     *reinterpret_cast<uint4*>(dst + row * 128 + ((w ^ (row & 7)) << 4)) = e;
                 }
                 tc_fence_proxy_async();
@@ -852,65 +915,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc6Threads, 1)
         // with thr > 0 the signed-int maximum of 64 accumulators passes the bit pattern of thr iff some accumulator does
         const bool screen = thr > 0;
         const int thr_bits = __float_as_int((float)thr);
+        const uint32_t lanes = (quarter * 32) << 16;
         for (uint32_t s = 0; s < n_st; ++s) {
             const uint32_t buf = s & 1;
             tc_mbar_wait(&acc_full[buf], (s >> 1) & 1);
             tc_fence_after();
             const uint32_t col_first = (st0 + s) * (2 * kT6Cols);
             const uint32_t* pcmin = p.col_pcmin + (col_first >> 6);
-            for (int q = 0; q < 3; ++q) {
-                uint32_t v[64];
-                int floor_pc = 0;
-                if (!kFold) floor_pc = (int)__ldg(pcmin + q);
-                __syncwarp();
-                tc_ld64(tmem_base + buf * 192 + q * 64 + ((quarter * 32) << 16), v);
-                uint64_t mask = 0;
-                if (kFold) {
-                    int best = (int)v[0];
-#pragma unroll
-                    for (int k = 0; k < 64; k += 2) best = max(best, max((int)v[k], (int)v[k + 1]));
-                    if (!screen || best >= thr_bits) {  // exact: only a row that really has a match among these 64 columns gets here
-#pragma unroll
-                        for (int k = 0; k < 64; ++k) mask |= (uint64_t)(__uint_as_float(v[k]) >= thr_f) << k;
-                    }
-                } else {
-                    uint32_t best = 0;  // accumulators are non-negative floats: their bit patterns order like the values
-#pragma unroll
-                    for (int k = 0; k < 64; k += 2) best = max(best, max(v[k], v[k + 1]));
-                    if (2 * (int)__uint_as_float(best) - floor_pc >= thr) {
-                        // The bound above is loose (largest dot and smallest popcount of 64 columns rarely belong to the same
-                        // column): at tolerance 0.4 it lets most groups of random hashes through.  Second screen, exact and on
-                        // the FMA pipe only: the largest 2 dot - pc(j) of the group.  0x4B000000 | pc is the float 2^23 + pc, so
-                        // fma(dot, 2, -(2^23 + pc)) = 2 dot - pc - 2^23 exactly - no int<->float conversions (XU pipe, 16 per
-                        // clock: 64 of them per thread cost as much as the group's MMAs).
-                        const uint4* pcj = reinterpret_cast<const uint4*>(p.col_pc + col_first + q * 64);
-                        float top = -3.0e38f;
-#pragma unroll
-                        for (int k4 = 0; k4 < 16; ++k4) {
-                            const uint4 pj = __ldg(pcj + k4);
-                            top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)));
-                            top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)));
-                            top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)));
-                            top = fmaxf(top, fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)));
-                        }
-                        if (top >= thr_f) {  // a pair of this row with one of the 64 columns is within the tolerance
-#pragma unroll
-                            for (int k4 = 0; k4 < 16; ++k4) {
-                                const uint4 pj = __ldg(pcj + k4);
-                                mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 0]), 2.0f, -__uint_as_float(0x4B000000u | pj.x)) >= thr_f) << (4 * k4 + 0);
-                                mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 1]), 2.0f, -__uint_as_float(0x4B000000u | pj.y)) >= thr_f) << (4 * k4 + 1);
-                                mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 2]), 2.0f, -__uint_as_float(0x4B000000u | pj.z)) >= thr_f) << (4 * k4 + 2);
-                                mask |= (uint64_t)(fmaf(__uint_as_float(v[4 * k4 + 3]), 2.0f, -__uint_as_float(0x4B000000u | pj.w)) >= thr_f) << (4 * k4 + 3);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                tc6_emit(p, mask, col_first + q * 64, gi, win_lo, win_hi, lane);
-            }
-            tc_fence_before();
+            const uint32_t acc = tmem_base + buf * 192 + lanes;
+            // Three groups of 64 columns, software-pipelined: the tensor-memory load of group q+1 is in flight while group q is
+            // screened (tcgen05.wait::ld waits for every load issued so far, so at most one is outstanding at a wait), and the
+            // accumulator goes back to the MMA warp as soon as its last column is in registers, before the last screen.
+            uint32_t va[64], vb[64];
+            int floor0 = 0, floor1 = 0, floor2 = 0;
+            if (!kFold) floor0 = (int)__ldg(pcmin), floor1 = (int)__ldg(pcmin + 1), floor2 = (int)__ldg(pcmin + 2);
+            __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the rare emit path of the previous super-tile
+            tc_ld64_nowait(acc, va);
+            tc_wait_ld();
+            tc_ld64_nowait(acc + 64, vb);
+            uint64_t mask = tc6_screen<kFold>(va, thr, thr_f, screen, thr_bits, floor0, p.col_pc + col_first);
+            if (mask) tc6_emit(p, mask, col_first, gi, win_lo, win_hi);
             __syncwarp();
+            tc_wait_ld();
+            tc_ld64_nowait(acc + 128, va);
+            mask = tc6_screen<kFold>(vb, thr, thr_f, screen, thr_bits, floor1, p.col_pc + col_first + 64);
+            if (mask) tc6_emit(p, mask, col_first + 64, gi, win_lo, win_hi);
+            __syncwarp();
+            tc_wait_ld();
+            tc_fence_before();
             if (lane == 0) tc_mbar_arrive_remote(&acc_empty[buf], 0);
+            mask = tc6_screen<kFold>(va, thr, thr_f, screen, thr_bits, floor2, p.col_pc + col_first + 128);
+            if (mask) tc6_emit(p, mask, col_first + 128, gi, win_lo, win_hi);
         }
     }
     __syncwarp();
