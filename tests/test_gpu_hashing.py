@@ -110,12 +110,13 @@ def test_chunked_overlapped_pipeline_matches_serial(ctx):
     want_h, want_s, want_c, _ = oracle_all(stacks)
     fresh = _ffi.Context(ctx.device)
     try:
-        for overlap, chunks in ((1, 4), (1, 4), (0, 1), (0, 4), (1, 2)):
+        for overlap, chunks, fuse in ((1, 4, 1), (1, 4, 1), (0, 1, 1), (0, 4, 0), (1, 2, 0), (0, 1, 0)):
             fresh.set_option("hash_overlap", overlap)
             fresh.set_option("hash_chunks", chunks)
+            fresh.set_option("hash_fuse_dct", fuse)
             got_h, got_s, got_c = gpu_hash(fresh, stacks)
-            assert np.array_equal(got_c, want_c), (overlap, chunks)
-            assert np.array_equal(got_s, want_s) and np.array_equal(got_h, want_h), (overlap, chunks)
+            assert np.array_equal(got_c, want_c), (overlap, chunks, fuse)
+            assert np.array_equal(got_s, want_s) and np.array_equal(got_h, want_h), (overlap, chunks, fuse)
     finally:
         fresh.close()
 

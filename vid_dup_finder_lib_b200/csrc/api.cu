@@ -126,6 +126,7 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     else if (k == "tc_a_tmem" && (value == 0 || value == 1)) ctx->tc_a_tmem = (uint32_t)value;
     else if (k == "hash_chunks" && value >= 1 && value <= 4) ctx->hash_chunks = (uint32_t)value;
     else if (k == "hash_overlap" && (value == 0 || value == 1)) ctx->hash_overlap = (uint32_t)value;
+    else if (k == "hash_fuse_dct" && (value == 0 || value == 1)) ctx->hash_fuse_dct = (uint32_t)value;
     else if (k == "grouping" && (value == 0 || value == 1)) ctx->grouping = (int)value;
     else if (k == "exchange" && (value == 0 || value == 1)) ctx->exchange = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;

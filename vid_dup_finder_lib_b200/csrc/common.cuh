@@ -201,8 +201,13 @@ struct vdf_ctx {
     int tc_fold = -1;           // variant 6: -1 fold C - pc(j) into the contraction whenever both operands have zero pad bits
                                 // (every real VideoHash), 0 never (the popcount-screen epilogue of round 1)
     uint64_t peer_timeout_ms = 0;  // peer exchange barrier: 0 = automatic (20 s + 1 ms per 2^26 pairs in the windows)
-    uint32_t hash_chunks = 4;   // hash.cu: chunks of stacks per call (letterbox of chunk k+1 overlaps the resize of chunk k)
-    uint32_t hash_overlap = 1;  // 0: letterbox and resize on one stream (round 1's order)
+    // hash.cu: the letterbox scan may run on a second stream, chunk k+1 beside the resize of chunk k.  Measured (256 1080p stacks):
+    // 1.88 ms per call overlapped in 4 chunks against 1.59 serial -- the latency-bound scan CTAs hold shared memory that a resize
+    // CTA needs, and with HBM saturated their own loads crawl (1.08 ms on their stream against 0.19 alone); chunks also add
+    // three kernel tails.  Default: one chunk, one stream, and a scan that is cheap on its own.
+    uint32_t hash_chunks = 1;
+    uint32_t hash_overlap = 0;
+    uint32_t hash_fuse_dct = 1;  // DCT + threshold + pack in the resize kernel (the CTA that finishes a stack); 0: a kernel of its own
     int exchange = 0;       // 1: searches append their matches to every rank's peer buffer (vdf_peer_*), see PeerExchange
     vdf::PeerExchange peer;
     bool peer_dead = false;  // an exchange call failed mid-way: counters of the ranks disagree, vdf_peer_close / alloc / open again

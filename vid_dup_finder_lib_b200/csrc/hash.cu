@@ -40,7 +40,7 @@ struct StackDev {
 
 constexpr int kLbTol = 16;  // LetterboxColour::AnyColour(16), video_frames_gray.rs:206
 constexpr int kColPanel = 32;
-constexpr int kRowPanel = 8;
+constexpr int kRowPanel = 32;
 
 // Decide one strip from its 256-bin histogram (one warp).  mode = LAST maximum (Iterator::max_by_key,
 // video_frames_gray.rs:82-87); letterbox iff count(|p - mode| <= tol) / len > 0.9 (:89-100), evaluated as
@@ -65,14 +65,21 @@ __device__ __forceinline__ bool strip_is_letterbox(const uint32_t* hist, uint32_
 }
 
 // grid = n_stacks * 2 frames (0 and 8: step_by(8).take(8) over 16 frames) * 4 sides; 256 threads.
-// Each CTA walks 1-px strips from its edge inwards in panels, stopping at the first non-letterbox strip.
+// Each CTA walks 1-px strips from its edge inwards in panels of 32, stopping at the first non-letterbox strip.
+//
+// A strip whose values span <= tol is letterbox whatever its mode is (every pixel is within tol of every other one:
+// count == len and 10 len > 9 len) -- exact, and it is what real bars look like.  So every panel is first looked at through
+// its per-strip minimum and maximum (registers, byte-wise SIMD min/max, no shared-memory traffic); histograms are built
+// only for the strips that are not decided that way -- in practice the one panel where the picture starts.  Round 1 built
+// them for every strip of every panel, 8 rows at a time: a barred side was a serial walk of up to 17 panels of zeroing,
+// shared atomics and three block barriers each, and that walk, not the bytes, was the kernel's 190 us.
 __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __restrict__ frames,
                                                              const StackDev* __restrict__ stacks,
                                                              uint32_t* __restrict__ sides /* [n][2][4] l,r,t,b */) {
-    __shared__ uint32_t hist[kColPanel * 257];
+    __shared__ uint32_t hist[kColPanel * 257];  // column panels: one histogram per strip; row panels: 4 sub-histograms per warp
     __shared__ uint32_t flags[kColPanel];
-    __shared__ uint32_t narrow[kRowPanel];  // row strips decided by their value range alone
-    __shared__ uint32_t s_count, s_stop;
+    __shared__ uint32_t s_min[kColPanel], s_max[kColPanel];
+    __shared__ uint32_t s_count, s_stop, s_need_hist;
     const uint32_t b = blockIdx.x, side = b & 3, fr = (b >> 2) & 1, s = b >> 3;
     const StackDev sd = stacks[s];
     if (sd.status != VDF_STACK_OK) return;
@@ -83,77 +90,138 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
     const bool cols = side < 2;  // 0 left, 1 right, 2 top, 3 bottom
     const uint32_t limit = cols ? W : H, len = cols ? H : W;
     const uint32_t panel = cols ? kColPanel : kRowPanel;
-    for (uint32_t base = 0; base < limit; base += panel) {
-        // column panels histogram every strip; row panels zero a strip's histogram only if it is not decided by its value
-        // range (real bars are): zeroing 33 KB per 8-row panel was a third of a barred side's time
-        if (cols)
-            for (uint32_t q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
-        if (tid < kRowPanel) narrow[tid] = 0;
+    {   // Strip 0 alone first: most frames have no bar on most sides, and one strip (one histogram, every thread a few
+        // pixels) settles that in a few microseconds; only a side whose outermost strip IS letterbox walks panels.
+        for (int q = tid; q < 256; q += 256) hist[q] = 0;
         __syncthreads();
-        const uint32_t px0 = side == 0 ? base : W - 32 - base;  // first pixel column of a full 32-column panel
-        if (cols && base + kColPanel <= W && ((reinterpret_cast<uintptr_t>(img) | P | px0) & 3) == 0) {
-            // full, 4-byte aligned panel: 8 word loads cover a row of the panel, 32 rows per pass, 16 passes in flight --
-            // a 1080-row panel takes 3 dependent round trips to memory instead of 9 with one byte per lane
+        if (cols) {
+            const uint8_t* col = img + (side == 0 ? 0u : W - 1);
+            for (uint32_t y = tid; y < H; y += 256) atomicAdd(&hist[__ldg(col + (uint64_t)y * P)], 1u);
+        } else {
+            const uint8_t* row = img + (uint64_t)(side == 2 ? 0u : H - 1) * P;
+            for (uint32_t x = tid; x < W; x += 256) atomicAdd(&hist[__ldg(row + x)], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const bool ok = strip_is_letterbox(hist, len, lane);
+            if (lane == 0) s_stop = ok ? 0u : 1u;
+        }
+        __syncthreads();
+        if (s_stop) {
+            if (tid == 0) sides[(s * 2 + fr) * 4 + side] = 0;
+            return;
+        }
+    }
+    for (uint32_t base = 0; base < limit; base += panel) {
+        if (cols) {
+            const uint32_t px0 = side == 0 ? base : W - 32 - base;  // first pixel column of a full 32-column panel
+            // full, 4-byte aligned panel: 8 word loads cover a row of the panel, 32 rows per pass, 16 passes in flight
+            const bool fast = base + kColPanel <= W && ((reinterpret_cast<uintptr_t>(img) | P | px0) & 3) == 0;
             const uint32_t wq = tid & 7, r0 = tid >> 3;
             const uint32_t* col4 = reinterpret_cast<const uint32_t*>(img + px0) + wq;
             const uint32_t P4 = P >> 2;
-            for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
-                uint32_t v[16];
+            bool need_hist = true;
+            if (fast) {  // pass A: value range of every column of the panel
+                if (tid < kColPanel) s_min[tid] = 255u, s_max[tid] = 0u;
+                if (tid == 0) s_need_hist = 0;
+                __syncthreads();
+                uint32_t mn4 = 0xFFFFFFFFu, mx4 = 0u;
+                for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
+                    uint32_t v[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const uint32_t y = y0 + 32 * u;
-                    v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t y = y0 + 32 * u;
+                        v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (y0 + 32 * u < H) mn4 = __vminu4(mn4, v[u]), mx4 = __vmaxu4(mx4, v[u]);
                 }
+                // the four row-threads of a warp that share a word column: lanes l, l^8, l^16, l^24
+                mn4 = __vminu4(mn4, __shfl_xor_sync(0xffffffffu, mn4, 8)), mx4 = __vmaxu4(mx4, __shfl_xor_sync(0xffffffffu, mx4, 8));
+                mn4 = __vminu4(mn4, __shfl_xor_sync(0xffffffffu, mn4, 16)), mx4 = __vmaxu4(mx4, __shfl_xor_sync(0xffffffffu, mx4, 16));
+                if (lane < 8) {
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    if (y0 + 32 * u < H) {
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t c = 4 * wq + q, k = side == 0 ? c : 31 - c;  // strip index inside the panel
+                        atomicMin(&s_min[k], (mn4 >> (8 * q)) & 255u);
+                        atomicMax(&s_max[k], (mx4 >> (8 * q)) & 255u);
+                    }
+                }
+                __syncthreads();
+                if (tid < kColPanel) {
+                    const bool nar = s_max[tid] - s_min[tid] <= (uint32_t)kLbTol;  // H >= 1: max >= min
+                    flags[tid] = nar;
+                    if (!nar) s_need_hist = 1;
+                }
+                __syncthreads();
+                need_hist = s_need_hist != 0;
+            }
+            if (need_hist) {  // pass B: histograms (the data of pass A comes from L1 / L2 this time)
+                for (uint32_t q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
+                __syncthreads();
+                if (fast) {
+                    for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
+                        uint32_t v[16];
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const uint32_t c = 4 * wq + b, k = side == 0 ? c : 31 - c;  // strip index inside the panel
-                            atomicAdd(&hist[k * 257 + ((v[u] >> (8 * b)) & 255u)], 1u);
+                        for (int u = 0; u < 16; ++u) {
+                            const uint32_t y = y0 + 32 * u;
+                            v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            if (y0 + 32 * u < H) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint32_t c = 4 * wq + q, k = side == 0 ? c : 31 - c;
+                                    if (!flags[k]) atomicAdd(&hist[k * 257 + ((v[u] >> (8 * q)) & 255u)], 1u);
+                                }
+                            }
                         }
                     }
-                }
-            }
-        } else if (cols) {
-            const uint32_t idx = base + lane;
-            const bool act = idx < W;
-            const uint32_t x = side == 0 ? idx : W - 1 - idx;
-            // 16 independent loads in flight per lane before the (shared-memory) histogram updates
-            for (uint32_t y0 = warp; y0 < H; y0 += 8 * 16) {
-                uint32_t v[16];
+                } else {
+                    const uint32_t idx = base + lane;
+                    const bool act = idx < W;
+                    const uint32_t x = side == 0 ? idx : W - 1 - idx;
+                    // 16 independent loads in flight per lane before the (shared-memory) histogram updates
+                    for (uint32_t y0 = warp; y0 < H; y0 += 8 * 16) {
+                        uint32_t v[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const uint32_t y = y0 + 8 * u;
-                    v[u] = (act && y < H) ? (uint32_t)__ldg(img + (uint64_t)y * P + x) : 0xFFFFu;
-                }
+                        for (int u = 0; u < 16; ++u) {
+                            const uint32_t y = y0 + 8 * u;
+                            v[u] = (act && y < H) ? (uint32_t)__ldg(img + (uint64_t)y * P + x) : 0xFFFFu;
+                        }
 #pragma unroll
-                for (int u = 0; u < 16; ++u)
-                    if (v[u] != 0xFFFFu) atomicAdd(&hist[lane * 257 + v[u]], 1u);
+                        for (int u = 0; u < 16; ++u)
+                            if (v[u] != 0xFFFFu) atomicAdd(&hist[lane * 257 + v[u]], 1u);
+                    }
+                }
+                __syncthreads();
+                for (uint32_t k = warp; k < kColPanel; k += 8) {
+                    if (fast && flags[k]) continue;  // decided by its value range
+                    bool ok = false;
+                    if (base + k < limit) ok = strip_is_letterbox(hist + k * 257, len, lane);
+                    if (lane == 0) flags[k] = ok;
+                }
+                __syncthreads();
             }
         } else {
-            const uint32_t idx = base + warp;
-            if (idx < H) {
+            // rows: warp w decides rows base + w + 8 i (i = 0..3) on its own, in its own four sub-histograms (lane & 3) that
+            // keep same-value lanes from piling onto one counter
+            uint32_t* h4 = hist + (warp * 4) * 257;
+            uint32_t* hs = h4 + (lane & 3) * 257;
+            const uint32_t W4 = W >> 2;
+            for (uint32_t i = 0; i < kRowPanel / 8; ++i) {
+                const uint32_t k = warp + 8 * i, idx = base + k;
+                if (idx >= H) {
+                    if (lane == 0) flags[k] = 0;
+                    continue;
+                }
                 const uint32_t y = side == 2 ? idx : H - 1 - idx;
                 const uint8_t* row = img + (uint64_t)y * P;
-                // four sub-histograms per row (lane & 3) keep same-value lanes from piling onto one counter
-                uint32_t* h4 = hist + (warp * 4) * 257;
-                uint32_t* hs = h4 + (lane & 3) * 257;
-                uint32_t x_done = 0;
-                bool zeroed = false;
-                auto zero_h4 = [&]() {
-                    if (!zeroed) {
-                        for (int v = lane; v < 4 * 257; v += 32) h4[v] = 0;
-                        __syncwarp();
-                        zeroed = true;
-                    }
-                };
-                const uint32_t W4 = W >> 2;
+                bool ok;
                 if ((reinterpret_cast<uintptr_t>(row) & 3) == 0 && W4 <= 32 * 16) {
-                    // the whole row is in registers (<= 2048 px): look at its value range before touching the histogram.
-                    // A strip whose values span <= tol is letterbox whatever its mode is (every pixel is within tol of every
-                    // other one: count == len, 10 len > 9 len) -- exact, it is what real bars look like, and it skips the
-                    // same-address shared atomics that a near-uniform row would serialise on.
+                    // the whole row is in registers (<= 2048 px): its value range first, the histogram only if that fails
                     const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
                     uint32_t v[16];
 #pragma unroll
@@ -171,10 +239,10 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                     uint32_t mx = max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
                     if (tail < 0x100u) mn = min(mn, tail), mx = max(mx, tail);
                     mn = __reduce_min_sync(0xffffffffu, mn), mx = __reduce_max_sync(0xffffffffu, mx);
-                    if (mx - mn <= (uint32_t)kLbTol) {
-                        if (lane == 0) narrow[warp] = 1u;
-                    } else {
-                        zero_h4();
+                    ok = mx - mn <= (uint32_t)kLbTol;
+                    if (!ok) {
+                        for (int q = lane; q < 4 * 257; q += 32) h4[q] = 0;
+                        __syncwarp();
 #pragma unroll
                         for (int u = 0; u < 16; ++u) {
                             if (u * 32 + lane < W4) {
@@ -185,55 +253,57 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                             }
                         }
                         if (tail < 0x100u) atomicAdd(&hs[tail], 1u);
+                        __syncwarp();
+                        for (int q = lane; q < 256; q += 32) h4[q] += h4[257 + q] + h4[514 + q] + h4[771 + q];
+                        __syncwarp();
+                        ok = strip_is_letterbox(h4, len, lane);
                     }
-                    x_done = W;
-                } else if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // long rows: up to 16 x 4 pixels per lane in flight
-                    zero_h4();
-                    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
-                    for (uint32_t q0 = 0; q0 < W4; q0 += 32 * 16) {
+                } else {  // long or unaligned rows: histogram straight away
+                    for (int q = lane; q < 4 * 257; q += 32) h4[q] = 0;
+                    __syncwarp();
+                    uint32_t x_done = 0;
+                    if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // up to 16 x 4 pixels per lane in flight
+                        const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+                        for (uint32_t q0 = 0; q0 < W4; q0 += 32 * 16) {
+                            uint32_t v[16];
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) {
+                                const uint32_t q = q0 + u * 32 + lane;
+                                v[u] = q < W4 ? __ldg(row4 + q) : 0u;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) {
+                                if (q0 + u * 32 + lane < W4) {
+                                    atomicAdd(&hs[v[u] & 255u], 1u);
+                                    atomicAdd(&hs[(v[u] >> 8) & 255u], 1u);
+                                    atomicAdd(&hs[(v[u] >> 16) & 255u], 1u);
+                                    atomicAdd(&hs[v[u] >> 24], 1u);
+                                }
+                            }
+                        }
+                        x_done = W4 << 2;
+                    }
+                    for (uint32_t x0 = x_done; x0 < W; x0 += 32 * 16) {
                         uint32_t v[16];
 #pragma unroll
                         for (int u = 0; u < 16; ++u) {
-                            const uint32_t q = q0 + u * 32 + lane;
-                            v[u] = q < W4 ? __ldg(row4 + q) : 0u;
+                            const uint32_t x = x0 + u * 32 + lane;
+                            v[u] = x < W ? (uint32_t)__ldg(row + x) : 0x100u;
                         }
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            if (q0 + u * 32 + lane < W4) {
-                                atomicAdd(&hs[v[u] & 255u], 1u);
-                                atomicAdd(&hs[(v[u] >> 8) & 255u], 1u);
-                                atomicAdd(&hs[(v[u] >> 16) & 255u], 1u);
-                                atomicAdd(&hs[v[u] >> 24], 1u);
-                            }
-                        }
+                        for (int u = 0; u < 16; ++u)
+                            if (v[u] < 0x100u) atomicAdd(&hs[v[u]], 1u);
                     }
-                    x_done = W4 << 2;
+                    __syncwarp();
+                    for (int q = lane; q < 256; q += 32) h4[q] += h4[257 + q] + h4[514 + q] + h4[771 + q];
+                    __syncwarp();
+                    ok = strip_is_letterbox(h4, len, lane);
                 }
-                if (x_done < W) zero_h4();
-                for (uint32_t x0 = x_done; x0 < W; x0 += 32 * 16) {
-                    uint32_t v[16];
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const uint32_t x = x0 + u * 32 + lane;
-                        v[u] = x < W ? (uint32_t)__ldg(row + x) : 0x100u;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 16; ++u)
-                        if (v[u] < 0x100u) atomicAdd(&hs[v[u]], 1u);
-                }
-                __syncwarp();
-                if (zeroed)
-                    for (int v = lane; v < 256; v += 32) h4[v] += h4[257 + v] + h4[514 + v] + h4[771 + v];
+                if (lane == 0) flags[k] = ok;
                 __syncwarp();
             }
+            __syncthreads();
         }
-        __syncthreads();
-        for (uint32_t k = warp; k < panel; k += 8) {
-            bool ok = false;
-            if (base + k < limit) ok = (!cols && narrow[k]) || strip_is_letterbox(hist + (cols ? k : k * 4) * 257, len, lane);
-            if (lane == 0) flags[k] = ok;
-        }
-        __syncthreads();
         if (tid == 0) {
             uint32_t c = s_count;
             for (uint32_t k = 0; k < panel && base + k < limit; ++k) {
@@ -407,6 +477,9 @@ __global__ void __launch_bounds__(256) dct_pack_kernel(const uint8_t* __restrict
     }
     dct_pack_block<256>(small + (uint64_t)s * 4096, cube, out, tid);
 }
+
+struct StackJob;
+__global__ void dct_pack_jobs_kernel(const uint8_t* __restrict__ small, const StackJob* __restrict__ jobs, uint32_t n, uint32_t* __restrict__ out_hash);
 
 // The thread block that completes a stack's 16th frame turns the stack's cube (4 KB, just written, L2-resident) into the
 // hash: every block publishes its 256 output bytes (fence), then counts itself in; the one that counts 16 hashes.
@@ -700,6 +773,23 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
         small[((uint64_t)s * 16 + t) * 256 + it] = clip8(a, j.prec_v);
     }
     if (out_hash) finish_stack<Cfg::kThreads>(small, s, done, out_hash, reinterpret_cast<double*>(ring), tid);
+}
+
+// stand-alone DCT + pack over the stacks of a pass (context option "hash_fuse_dct" = 0): stacks the pass skipped keep what an
+// earlier pass wrote, stacks in error read as zero
+__global__ void __launch_bounds__(256) dct_pack_jobs_kernel(const uint8_t* __restrict__ small, const StackJob* __restrict__ jobs, uint32_t n,
+                                                            uint32_t* __restrict__ out_hash) {
+    __shared__ double cube[16 * 16 * 17];
+    const uint32_t s = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int32_t status = jobs[s].status;
+    if (status == kJobSkip) return;
+    uint32_t* out = out_hash + (uint64_t)s * 32;
+    if (status != VDF_STACK_OK) {
+        if (tid < 32) out[tid] = 0;
+        return;
+    }
+    dct_pack_block<256>(small + (uint64_t)s * 4096, cube, out, tid);
 }
 
 // ================================================================================ resize jobs, built on the device
@@ -1022,10 +1112,13 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         VDF_ALLOC(ctx, ctx->h_small.ensure((size_t)n * 4096));
         d_small = ctx->h_small.as<uint8_t>();
     }
-    uint32_t* d_hash32 = reinterpret_cast<uint32_t*>(d_out_hash);
+    uint32_t* d_hash32 = ctx->hash_fuse_dct ? reinterpret_cast<uint32_t*>(d_out_hash) : nullptr;
+    bool any_bad = false;
+    for (uint32_t s = 0; s < n && !any_bad; ++s) any_bad = status[s] != VDF_STACK_OK;
+    const bool fuse = ctx->hash_fuse_dct != 0;  // DCT + pack in the resize kernel's last CTA per stack, or as a kernel of its own
     VDF_CUDA(ctx, cudaMemcpyAsync(d_sd, sd, (size_t)n * sizeof(StackDev), cudaMemcpyHostToDevice, st));
     VDF_CUDA(ctx, cudaMemsetAsync(d_done, 0, (size_t)n * 8 + 64, st));
-    if (d_out_hash) VDF_CUDA(ctx, cudaMemsetAsync(d_out_hash, 0, (size_t)n * 128, st));  // stacks that are not hashed read as zero
+    if (d_out_hash && any_bad && fuse) VDF_CUDA(ctx, cudaMemsetAsync(d_out_hash, 0, (size_t)n * 128, st));  // stacks that are not hashed read as zero
     // The opt-in is per device AND per function, whoever sets it last wins: every context asks for the device's maximum, once,
     // so that contexts sharing a GPU can never lower each other's limit (kept per context because it is per device).
     const size_t gen_smem = std::max<size_t>(tmp_bytes, kCubeBytes);
@@ -1057,7 +1150,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     const bool letterbox = cropdetect == VDF_CROPDETECT_LETTERBOX;
     cudaStream_t lb = ctx->hash_overlap ? ctx->lb_stream : st;
     if (letterbox) {
-        VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_sides.p, 0, (size_t)n * 8 * 4, st));
+        if (any_bad) VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_sides.p, 0, (size_t)n * 8 * 4, st));  // the scan writes every side of every good stack
         if (lb != st) {
             VDF_CUDA(ctx, cudaEventRecord(ctx->ev_in, st));
             VDF_CUDA(ctx, cudaStreamWaitEvent(lb, ctx->ev_in, 0));
@@ -1117,6 +1210,17 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         return VDF_OK;
     };
     VDF_TRY(run_pass(false));
+    auto separate_dct = [&]() -> int {
+        if (fuse || !d_out_hash) return VDF_OK;
+        VDF_ALLOC(ctx, ctx->h_hash.ensure(16));
+        // status per stack on the device for the stand-alone kernel: the jobs carry it (kJobSkip = missed in this pass)
+        kt_begin(ctx, 3);
+        dct_pack_jobs_kernel<<<n, 256, 0, st>>>(d_small, d_jobs, n, reinterpret_cast<uint32_t*>(d_out_hash));
+        kt_end(ctx, 3);
+        VDF_LAUNCHED(ctx);
+        return VDF_OK;
+    };
+    VDF_TRY(separate_dct());
     VDF_ALLOC(ctx, ctx->h_misc.ensure(256));
     uint32_t* h_n = reinterpret_cast<uint32_t*>(ctx->h_misc.as<unsigned long long>() + 24);
     VDF_CUDA(ctx, cudaMemcpyAsync(crop, ctx->h_crop.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
@@ -1141,6 +1245,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         }
         VDF_CUDA(ctx, cudaMemsetAsync(d_nmiss, 0, 4, st));
         VDF_TRY(run_pass(true));
+        VDF_TRY(separate_dct());
         VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
         VDF_CUDA(ctx, cudaStreamSynchronize(st));
         if (*h_n) {
