@@ -60,12 +60,18 @@ struct Error {  // vid_dup_finder_lib::Error, video_hashing/mod.rs:17-28
 };
 
 // ---- context ----------------------------------------------------------------------------------------------
-class Context {  // one GPU, one stream, not thread-safe (vdf_b200.h)
+class Context {  // one GPU and one stream -- or several GPUs of one node behind one context -- not thread-safe (vdf_b200.h)
   public:
     explicit Context(int device = 0) {
         int rc = vdf_ctx_create(device, &h_);
         if (rc != VDF_OK) throw DeviceError(rc, "vdf_ctx_create failed (no sm_100 device?)");
     }
+    // search(), search_with_references() and VideoHashBuilder then use every listed GPU (vdf_ctx_create_multi)
+    explicit Context(const std::vector<int>& devices) {
+        int rc = vdf_ctx_create_multi(devices.data(), (int)devices.size(), &h_);
+        if (rc != VDF_OK) throw DeviceError(rc, "vdf_ctx_create_multi failed (sm_100 devices with peer access?)");
+    }
+    int device_count() const { return vdf_ctx_device_count(h_); }
     ~Context() { vdf_ctx_destroy(h_); }
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
@@ -288,6 +294,49 @@ inline std::vector<MatchGroup> search_with_references(const std::vector<VideoHas
     vdf_free_csr(&c);
     return out;
 }
+
+// `Search` (search_algorithm.rs:5-53,81-198): `Search::from(hashes)` sorts once and keeps the table -- here resident in HBM
+// in the kernels' layout (vdf_table) -- and `search_self(tolerance)` runs on it any number of times (a tolerance sweep, the
+// app's repeated searches over one loaded cache).  Returned groups hold paths, in the reference's order.
+class Search {
+  public:
+    Search(const std::vector<VideoHash>& hashes, Context& ctx) : ctx_(ctx) {
+        const std::vector<uint64_t> order = detail::sort_order(hashes);  // Search::sort (:55-61)
+        std::vector<uint64_t> words(hashes.size() * HASH_WORDS);
+        std::vector<uint32_t> dur(hashes.size());
+        paths_.reserve(hashes.size());
+        for (size_t k = 0; k < order.size(); ++k) {
+            const VideoHash& h = hashes[order[k]];
+            std::memcpy(&words[k * HASH_WORDS], h.words().data(), HASH_WORDS * 8);
+            dur[k] = h.duration();
+            paths_.push_back(h.src_path());
+        }
+        ctx_.check(vdf_table_create(ctx_.get(), words.data(), dur.data(), hashes.size(), &t_));
+    }
+    ~Search() { vdf_table_destroy(t_); }
+    Search(const Search&) = delete;
+    Search& operator=(const Search&) = delete;
+    size_t len() const { return paths_.size(); }
+
+    std::vector<std::vector<std::string>> search_self(double tolerance) {  // :81-171
+        std::vector<std::vector<std::string>> out;
+        vdf_groups g{};
+        ctx_.check(vdf_table_search_self_groups(t_, tolerance_to_int(tolerance), &g));
+        out.reserve(g.n_groups);
+        for (uint64_t k = 0; k < g.n_groups; ++k) {
+            std::vector<std::string> paths;
+            for (uint64_t m = g.group_ptr[k]; m < g.group_ptr[k + 1]; ++m) paths.push_back(paths_[g.member_idx[m]]);
+            out.push_back(std::move(paths));
+        }
+        vdf_free_groups(&g);
+        return out;
+    }
+
+  private:
+    Context& ctx_;
+    vdf_table* t_ = nullptr;
+    std::vector<std::string> paths_;
+};
 
 // ---- the app's hash cache file (format: see vdf_cache_load in vdf_b200.h) ------------------------
 // the Ok(VideoHash) entries of a cache file, in file order -- what the app feeds `search` after loading its cache

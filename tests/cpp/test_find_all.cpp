@@ -192,6 +192,58 @@ static int test_hash_frames(Context& ctx) {
 
 // host-only: Search::sort as the library computes it (vdf_sort_order, multi-threaded) against a plain stable sort with the
 // component-wise comparator of this header; needs no GPU
+// `Search::from` once, `search_self` at several tolerances: the prepared table gives what the one-shot `search` gives
+static int test_prepared_search_object(Context& ctx) {
+    Rng rng(5);
+    HashesWithDistanceSet sets(3, 60, 200, 40, rng);
+    auto all = sets.all_members(rng);
+    name_all(all);
+    Search s(all, ctx);
+    CHECK(s.len() == all.size());
+    for (double tol : {0.0, 0.05, 0.1, 0.35}) {
+        const auto a = s.search_self(tol);
+        const auto b = search(all, tol, ctx);
+        CHECK(a.size() == b.size());
+        for (size_t k = 0; k < a.size(); ++k) CHECK(a[k] == b[k].duplicates());
+    }
+    return 0;
+}
+
+// one context over every GPU of the box (vdf_ctx_create_multi): the same calls, the same results; skipped below 2 GPUs
+static int test_multi_device_context(Context& ctx) {
+    int n_dev = 0;
+    for (int d = 0; d < 8; ++d) {  // probe by creating contexts: the test links against the C ABI only
+        vdf_ctx* p = nullptr;
+        if (vdf_ctx_create(d, &p) != VDF_OK) break;
+        vdf_ctx_destroy(p);
+        ++n_dev;
+    }
+    if (n_dev < 2) {
+        std::printf("       (skipped: %d GPU)\n", n_dev);
+        return 0;
+    }
+    std::vector<int> devs(n_dev);
+    for (int d = 0; d < n_dev; ++d) devs[d] = d;
+    Context multi(devs);
+    CHECK(multi.device_count() == n_dev);
+    Rng rng(6);
+    HashesWithDistanceSet sets(5, 100, 150, 50, rng);
+    auto all = sets.all_members(rng);
+    name_all(all);
+    for (double tol : {0.05, 0.1}) {
+        const auto a = search(all, tol, multi);
+        const auto b = search(all, tol, ctx);
+        CHECK(a.size() == b.size() && !a.empty());
+        for (size_t k = 0; k < a.size(); ++k) CHECK(a[k].duplicates() == b[k].duplicates());
+    }
+    std::vector<VideoHash> refs = {sets.groups[0].start_hash.with_src_path("ref0"), sets.groups[4].start_hash.with_src_path("ref4")};
+    const auto ra = search_with_references(refs, all, 0.05, multi);
+    const auto rb = search_with_references(refs, all, 0.05, ctx);
+    CHECK(ra.size() == rb.size() && ra.size() == 2);
+    for (size_t k = 0; k < ra.size(); ++k) CHECK(ra[k].duplicates() == rb[k].duplicates() && ra[k].reference() == rb[k].reference());
+    return 0;
+}
+
 static int test_sort_order_host_only() {
     std::vector<VideoHash> v;
     const char* pieces[] = {"a", "b", "-", ".", "/", "..", "_", "0", "v", "\x01", " ", "ab", "~"};
@@ -237,6 +289,8 @@ int main(int argc, char** argv) {
         RUN(test_find_with_refs);
         RUN(test_group_order_and_paths);
         RUN(test_hash_frames);
+        RUN(test_prepared_search_object);
+        RUN(test_multi_device_context);
         std::printf("%s\n", fails ? "SOME TESTS FAILED" : "ALL TESTS PASSED");
         return fails ? 1 : 0;
     } catch (const std::exception& e) {

@@ -2,8 +2,10 @@
 // POPC (the search kernel's bound), LOP3 / IADD3 (what the carry-save variant trades POPC for), dp4a / dp2a and
 // legacy IMMA (candidates for the exact-integer resize), plus a streaming read for the HBM figure.
 // Usage: vdf_microbench  -> one JSON object per line on stdout.
+#include <cublasLt.h>
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <vector>
@@ -235,6 +237,108 @@ static float time_ms(F&& launch, int reps = 5) {
     return best;
 }
 
+// An INDEPENDENT 4-bit tensor-core figure ("peak provenance"): cuBLASLt's block-scaled FP4 GEMM (NVFP4: e2m1
+// operands, one UE4M3 scale per 16 values, all scales 1.0), 8192^3, bf16 output.  Two operand fillings -- random nibbles and
+// the {0, 1.0} nibbles our kernel feeds the tensor cores -- as a burst (best of 10) and sustained for 4 s.  Same pipe as
+// tcgen05.mma kind::mxf4 (kind::mxf4nvf4 issues at the same rate); a library GEMM also moves operands and writes a result, so
+// it is a lower bound on the pipe, next to the bare issue-rate loop above.
+static int cublaslt_fp4(int sms, int clk_khz) {
+    const int64_t M = 8192, N = 8192, K = 8192;
+    cublasLtHandle_t lt;
+    if (cublasLtCreate(&lt) != CUBLAS_STATUS_SUCCESS) {
+        printf("{\"op\": \"cublaslt_nvfp4_gemm_8192\", \"error\": \"cublasLtCreate\"}\n");
+        return 0;
+    }
+    void *A, *B, *D, *sa, *sb, *ws;
+    const size_t ws_bytes = 256u << 20;
+    CK(cudaMalloc(&A, M * K / 2));
+    CK(cudaMalloc(&B, N * K / 2));
+    CK(cudaMalloc(&D, M * N * 2));
+    CK(cudaMalloc(&sa, M * K / 16 + 4096));
+    CK(cudaMalloc(&sb, N * K / 16 + 4096));
+    CK(cudaMalloc(&ws, ws_bytes));
+    CK(cudaMemset(sa, 0x38, M * K / 16 + 4096));  // UE4M3 1.0 in every scale slot: the tiled scale layout does not matter
+    CK(cudaMemset(sb, 0x38, N * K / 16 + 4096));
+    cublasLtMatmulDesc_t op;
+    cublasLtMatrixLayout_t la, lb, lc;
+    cublasLtMatmulPreference_t pref;
+    const cublasOperation_t tr = CUBLAS_OP_T, nt = CUBLAS_OP_N;
+    const cublasLtMatmulMatrixScale_t mode = CUBLASLT_MATMUL_MATRIX_SCALE_VEC16_UE4M3;
+    bool ok = cublasLtMatmulDescCreate(&op, CUBLAS_COMPUTE_32F, CUDA_R_32F) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_TRANSA, &tr, sizeof tr) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_TRANSB, &nt, sizeof nt) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_A_SCALE_MODE, &mode, sizeof mode) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_B_SCALE_MODE, &mode, sizeof mode) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_A_SCALE_POINTER, &sa, sizeof sa) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulDescSetAttribute(op, CUBLASLT_MATMUL_DESC_B_SCALE_POINTER, &sb, sizeof sb) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatrixLayoutCreate(&la, CUDA_R_4F_E2M1, K, M, K) == CUBLAS_STATUS_SUCCESS;  // A^T: K x M, K-major
+    ok = ok && cublasLtMatrixLayoutCreate(&lb, CUDA_R_4F_E2M1, K, N, K) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatrixLayoutCreate(&lc, CUDA_R_16BF, M, N, M) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulPreferenceCreate(&pref) == CUBLAS_STATUS_SUCCESS;
+    ok = ok && cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_bytes, sizeof ws_bytes) == CUBLAS_STATUS_SUCCESS;
+    cublasLtMatmulHeuristicResult_t heur;
+    int found = 0;
+    if (ok) ok = cublasLtMatmulAlgoGetHeuristic(lt, op, la, lb, lc, lc, pref, 1, &heur, &found) == CUBLAS_STATUS_SUCCESS && found > 0;
+    if (!ok) {
+        printf("{\"op\": \"cublaslt_nvfp4_gemm_8192\", \"error\": \"no FP4 block-scaled GEMM from cuBLASLt on this box\"}\n");
+        return 0;
+    }
+    const float alpha = 1.0f, beta = 0.0f;
+    auto gemm = [&]() { return cublasLtMatmul(lt, op, &alpha, A, la, B, lb, &beta, D, lc, D, lc, &heur.algo, ws, ws_bytes, 0); };
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const double flops = 2.0 * M * N * K;
+    for (int fill = 0; fill < 2; ++fill) {
+        std::vector<uint8_t> h((size_t)M * K / 2);
+        uint64_t x = 0x9E3779B97F4A7C15ull;
+        for (auto& b : h) {
+            x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+            b = fill == 0 ? (uint8_t)(x >> 32) : (uint8_t)(((x >> 32) & 1 ? 0x02 : 0) | ((x >> 33) & 1 ? 0x20 : 0));
+        }
+        CK(cudaMemcpy(A, h.data(), h.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B, h.data() + 4096, h.size() - 4096, cudaMemcpyHostToDevice));
+        if (gemm() != CUBLAS_STATUS_SUCCESS) {
+            printf("{\"op\": \"cublaslt_nvfp4_gemm_8192\", \"error\": \"cublasLtMatmul failed\"}\n");
+            return 0;
+        }
+        CK(cudaDeviceSynchronize());
+        float best = 1e30f;
+        for (int r = 0; r < 10; ++r) {
+            CK(cudaEventRecord(e0));
+            gemm();
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            best = ms < best ? ms : best;
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        int reps = 0;
+        CK(cudaEventRecord(e0));
+        while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 4.0) {
+            for (int r = 0; r < 20; ++r) gemm();
+            reps += 20;
+            CK(cudaDeviceSynchronize());
+        }
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const char* name = fill == 0 ? "random nibbles" : "{0, 1.0} nibbles";
+        printf("{\"op\": \"cublaslt_nvfp4_gemm_8192\", \"data\": \"%s\", \"run\": \"burst\", \"ms\": %.4f, \"ops_per_s\": %.4e, "
+               "\"macs_per_clk_per_sm_at_max_clock\": %.1f}\n",
+               name, best, flops / (best * 1e-3), flops / 2 / (best * 1e-3) / ((double)clk_khz * 1e3) / sms);
+        printf("{\"op\": \"cublaslt_nvfp4_gemm_8192\", \"data\": \"%s\", \"run\": \"sustained\", \"ms\": %.4f, \"gemms\": %d, \"ops_per_s\": %.4e, "
+               "\"macs_per_clk_per_sm_at_max_clock\": %.1f}\n",
+               name, ms / reps, reps, flops * reps / (ms * 1e-3), flops / 2 * reps / (ms * 1e-3) / ((double)clk_khz * 1e3) / sms);
+        fflush(stdout);
+    }
+    cudaFree(A), cudaFree(B), cudaFree(D), cudaFree(sa), cudaFree(sb), cudaFree(ws);
+    cublasLtDestroy(lt);
+    return 0;
+}
+
 int main() {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -303,5 +407,6 @@ int main() {
         cudaFree(buf);
     }
     CK(cudaDeviceSynchronize());
+    if (cublaslt_fp4(sms, clk_khz)) return 1;
     return 0;
 }
