@@ -15,14 +15,18 @@ if [[ $STEP == all || $STEP == micro ]]; then
 fi
 if [[ $STEP == all || $STEP == ncu ]]; then
   # launch list of one default step of both paths (search on the prepared table, hashing): per-launch times are cold and serialised
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+  # launch list of one default step of both paths (search on the prepared table, hashing): per-launch times are cold and serialised;
+  # only this library's kernels and cub's (torch's synthetic-data kernels are not part of a step)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled \
+      -k 'regex:^(void )?(vdf::|cub::|<unnamed>::)' -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 1 --tol-sweep "" --secondary hash --hash-total 512 --parity-rows 0 > gpurun_out/bench_under_ncu.json 2>&1; echo "ncu list rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tc6 -c 1 -f -o gpurun_out/prof_hamming_tc6__self_1000000_x1 \
       python bench.py --steps 1 --warmup 0 --no-secondary --no-cpu-baseline --e2e-steps 1 --tol-sweep "" --parity-rows 0 > gpurun_out/ncu_tc6.log 2>&1; echo "ncu tc6 rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tiles -c 1 -f -o gpurun_out/prof_hamming_popc__self_262144_x1 \
       python bench.py --workload popc --steps 1 --warmup 0 --no-cpu-baseline --parity-rows 0 > gpurun_out/ncu_popc.log 2>&1; echo "ncu popc rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize_mma -c 1 -f -o gpurun_out/prof_resize_mma__stacks_256_1920x1080 \
-      python bench.py --workload hash --steps 1 --warmup 0 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_resize.log 2>&1; echo "ncu resize rc=$?"
+  # the third launch: the first call meets crop sizes for the first time (a pass for the known sizes, a pass for the misses)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize_mma -s 2 -c 1 -f -o gpurun_out/prof_resize_mma__stacks_256_1920x1080 \
+      python bench.py --workload hash --steps 1 --warmup 1 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_resize.log 2>&1; echo "ncu resize rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_side -c 1 -f -o gpurun_out/prof_letterbox__stacks_256_1920x1080 \
       python bench.py --workload hash --steps 1 --warmup 0 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
 fi
@@ -30,6 +34,11 @@ if [[ $STEP == all || $STEP == sanitizer ]]; then
   timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_search.py tests/test_gpu_hashing.py -m gpu -q -x \
       -k "fold_is_exact and clusters or prepared_table or many_matches or sort_ties or chunked_overlapped or random_edge_lists or long_dependency or find_with_refs or cropdetect_none" \
       > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -6 gpurun_out/sanitizer_memcheck.log
+fi
+if [[ $STEP == all || $STEP == bench ]]; then
+  timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+  timeout 1500 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
+  python scripts/show_bench.py gpurun_out/bench.json
 fi
 if [[ $STEP == all || $STEP == smoke ]]; then
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log

@@ -73,7 +73,7 @@ __device__ __forceinline__ bool strip_is_letterbox(const uint32_t* hist, uint32_
 // only for the strips that are not decided that way -- in practice the one panel where the picture starts.  Round 1 built
 // them for every strip of every panel, 8 rows at a time: a barred side was a serial walk of up to 17 panels of zeroing,
 // shared atomics and three block barriers each, and that walk, not the bytes, was the kernel's 190 us.
-__global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __restrict__ frames,
+__global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* __restrict__ frames,
                                                              const StackDev* __restrict__ stacks,
                                                              uint32_t* __restrict__ sides /* [n][2][4] l,r,t,b */) {
     __shared__ uint32_t hist[kColPanel * 257];  // column panels: one histogram per strip; row panels: 4 sub-histograms per warp
@@ -126,16 +126,28 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
                 if (tid == 0) s_need_hist = 0;
                 __syncthreads();
                 uint32_t mn4 = 0xFFFFFFFFu, mx4 = 0u;
-                for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
-                    uint32_t v[16];
+                if (H <= 32 * 40) {  // up to 1280 rows (1080p): every load of the panel in flight at once, one round trip to memory
+                    uint32_t v[40];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const uint32_t y = y0 + 32 * u;
+                    for (int u = 0; u < 40; ++u) {
+                        const uint32_t y = r0 + 32 * u;
                         v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
                     }
 #pragma unroll
-                    for (int u = 0; u < 16; ++u)
-                        if (y0 + 32 * u < H) mn4 = __vminu4(mn4, v[u]), mx4 = __vmaxu4(mx4, v[u]);
+                    for (int u = 0; u < 40; ++u)
+                        if (r0 + 32 * u < H) mn4 = __vminu4(mn4, v[u]), mx4 = __vmaxu4(mx4, v[u]);
+                } else {
+                    for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
+                        uint32_t v[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const uint32_t y = y0 + 32 * u;
+                            v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; ++u)
+                            if (y0 + 32 * u < H) mn4 = __vminu4(mn4, v[u]), mx4 = __vmaxu4(mx4, v[u]);
+                    }
                 }
                 // the four row-threads of a warp that share a word column: lanes l, l^8, l^16, l^24
                 mn4 = __vminu4(mn4, __shfl_xor_sync(0xffffffffu, mn4, 8)), mx4 = __vmaxu4(mx4, __shfl_xor_sync(0xffffffffu, mx4, 8));
@@ -211,10 +223,50 @@ __global__ void __launch_bounds__(256) letterbox_side_kernel(const uint8_t* __re
             uint32_t* h4 = hist + (warp * 4) * 257;
             uint32_t* hs = h4 + (lane & 3) * 257;
             const uint32_t W4 = W >> 2;
+            // first the value range of all four rows of this warp, their loads in flight together (rows of <= 2048 px, aligned):
+            // a panel inside a bar costs one round trip to memory
+            uint32_t decided = 0;  // bit i: row i is narrow
+            if (((reinterpret_cast<uintptr_t>(img) | P) & 3) == 0 && W4 <= 32 * 16) {
+                uint32_t mn[4], mx[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t idx = base + warp + 8 * i;
+                    mn[i] = 0xFFFFFFFFu, mx[i] = 0u;
+                    if (idx < H) {
+                        const uint32_t y = side == 2 ? idx : H - 1 - idx;
+                        const uint8_t* row = img + (uint64_t)y * P;
+                        const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const uint32_t q = u * 32 + lane;
+                            if (q < W4) {
+                                const uint32_t v = __ldg(row4 + q);
+                                mn[i] = __vminu4(mn[i], v), mx[i] = __vmaxu4(mx[i], v);
+                            }
+                        }
+                        const uint32_t xt = (W4 << 2) + lane;
+                        if (xt < W) {
+                            const uint32_t t = (uint32_t)__ldg(row + xt) * 0x01010101u;
+                            mn[i] = __vminu4(mn[i], t), mx[i] = __vmaxu4(mx[i], t);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t a = min(min(mn[i] & 255u, (mn[i] >> 8) & 255u), min((mn[i] >> 16) & 255u, mn[i] >> 24));
+                    uint32_t b = max(max(mx[i] & 255u, (mx[i] >> 8) & 255u), max((mx[i] >> 16) & 255u, mx[i] >> 24));
+                    a = __reduce_min_sync(0xffffffffu, a), b = __reduce_max_sync(0xffffffffu, b);
+                    if (base + warp + 8 * i < H && b - a <= (uint32_t)kLbTol) decided |= 1u << i;
+                }
+            }
             for (uint32_t i = 0; i < kRowPanel / 8; ++i) {
                 const uint32_t k = warp + 8 * i, idx = base + k;
                 if (idx >= H) {
                     if (lane == 0) flags[k] = 0;
+                    continue;
+                }
+                if (decided & (1u << i)) {
+                    if (lane == 0) flags[k] = 1;
                     continue;
                 }
                 const uint32_t y = side == 2 ? idx : H - 1 - idx;

@@ -440,21 +440,27 @@ int vdf::stage_and_sort(vdf_ctx* ctx, const uint64_t* hashes, const uint32_t* du
     uint64_t* p1 = ctx->pin_c.as<uint64_t>();
     uint64_t* p2 = p1 + n;
     uint32_t* pd = reinterpret_cast<uint32_t*>(p2 + n);
+    // The hash upload starts first and runs BESIDE the key cutting: copier threads move the caller's (pageable) table into pinned
+    // memory slice by slice and enqueue each slice's DMA themselves; the sort kernels, enqueued behind them, do not read the hashes.
+    uint8_t* ph = pin_h.as<uint8_t>();
+    uint8_t* dh = d_hash.as<uint8_t>();
+    const unsigned tc = std::max(1u, std::min(n_threads(n), 8u));
+    std::vector<int> rcs(tc, 0);
+    std::vector<std::thread> copiers;
+    copiers.reserve(tc);
+    for (unsigned k = 0; k < tc; ++k) {
+        const uint64_t b = n * k / tc, e = n * (k + 1) / tc;
+        copiers.emplace_back([=, &rcs] {
+            if (e <= b) return;
+            cudaSetDevice(ctx->device);
+            memcpy(ph + b * 128, reinterpret_cast<const uint8_t*>(hashes) + b * 128, (e - b) * 128);
+            if (cudaMemcpyAsync(dh + b * 128, ph + b * 128, (e - b) * 128, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rcs[k] = 1;
+        });
+    }
     uint64_t skip = 0;
     build_prefix_keys(dur, paths, off, n, pd, p1, p2, &skip);
     const double t1 = now_ms();
-    // the hash upload goes first on the stream: its DMA runs while the sort kernels wait for it, and the host is free to
-    // enqueue them (enqueue order == execution order on one stream; the sort does not read the hashes)
-    uint8_t* ph = pin_h.as<uint8_t>();
-    uint8_t* dh = d_hash.as<uint8_t>();
-    const unsigned t = std::max(1u, std::min(n_threads(n), 8u));
-    std::vector<int> rcs(t, 0);
-    parallel_for(n, t, [&](uint64_t b, uint64_t e, unsigned th) {
-        if (e <= b) return;
-        cudaSetDevice(ctx->device);
-        memcpy(ph + b * 128, reinterpret_cast<const uint8_t*>(hashes) + b * 128, (e - b) * 128);
-        if (cudaMemcpyAsync(dh + b * 128, ph + b * 128, (e - b) * 128, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rcs[th] = 1;
-    });
+    for (auto& t : copiers) t.join();
     for (int r : rcs)
         if (r) {
             ctx->err = "upload of the hash table failed";
