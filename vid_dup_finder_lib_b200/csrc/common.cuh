@@ -109,6 +109,15 @@ struct PeerExchange {
     }
 };
 
+// one frame stack as the hashing kernels see it (hash.cu, motion.cu)
+struct StackDev {
+    uint64_t offset, frame_stride;
+    uint32_t width, height, pitch;
+    int32_t status;
+    uint32_t aligned;  // base, frame stride and pitch are multiples of 16: the tensor-core resize may take it
+    uint32_t pad;
+};
+
 // one axis of the Lanczos3 u8 resize (fast_image_resize Normalizer16) for a given input size, resident in HBM
 struct CoefTable {
     uint32_t in_size = 0, window = 0, precision = 0;
@@ -239,6 +248,7 @@ struct vdf_ctx {
     size_t hash_smem_set[3] = {0, 0, 0};
     // hashing scratch
     vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc, h_coef_lut, h_bfrag_lut, h_done;
+    vdf::DevBuf m_state, m_lut, m_sides, m_acc, m_a, m_b, m_c, m_f32, m_label;  // motion.cu scratch
     vdf::PinnedBuf pin_a, pin_b, pin_c, pin_frames[2], h_groups;  // h_groups: staging of the group CSR on its way to the caller
     vdf::PinnedBuf h_misc;  // landing zone of the few counters the host reads back per call
     std::map<uint32_t, vdf::CoefTable> coef_cache;
@@ -338,4 +348,8 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
                        uint64_t* d_out_hash, uint8_t* d_out_small, int32_t* out_status, uint32_t* out_crop);
 int hash_from_small_device(vdf_ctx* ctx, const uint8_t* d_small, uint32_t n, uint64_t* d_out_hash);
 void free_coef_cache(vdf_ctx* ctx);
+int letterbox_all_frames(vdf_ctx* ctx, const uint8_t* d_frames, const StackDev* d_sd, uint32_t n, const uint8_t* d_luts, uint32_t* d_sides,
+                         uint32_t* d_crop);
+// motion.cu: Cropdetect::Motion (autocrop_frames.rs:36-218) for n stacks -> d_crop [n][4] (left, right, top, bottom)
+int motion_crop_device(vdf_ctx* ctx, const uint8_t* d_frames, const StackDev* d_sd, const StackDev* h_sd, uint32_t n, uint32_t* d_crop);
 }  // namespace vdf

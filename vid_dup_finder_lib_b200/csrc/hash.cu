@@ -30,14 +30,6 @@
 namespace vdf {
 
 // ================================================================================ H2: letterbox crop detect
-struct StackDev {
-    uint64_t offset, frame_stride;
-    uint32_t width, height, pitch;
-    int32_t status;
-    uint32_t aligned;  // base, frame stride and pitch are multiples of 16: the tensor-core resize may take it
-    uint32_t pad;
-};
-
 constexpr int kLbTol = 16;  // LetterboxColour::AnyColour(16), video_frames_gray.rs:206
 constexpr int kColPanel = 32;
 constexpr int kRowPanel = 32;
@@ -73,17 +65,28 @@ __device__ __forceinline__ bool strip_is_letterbox(const uint32_t* hist, uint32_
 // only for the strips that are not decided that way -- in practice the one panel where the picture starts.  Round 1 built
 // them for every strip of every panel, 8 rows at a time: a barred side was a serial walk of up to 17 panels of zeroing,
 // shared atomics and three block barriers each, and that walk, not the bytes, was the kernel's 190 us.
+// kLut (Cropdetect::Motion, motion.cu): every pixel goes through a per-stack 256-entry table first (the contrast stretch of
+// autocrop_frames.rs:107-113, monotone, so minima and maxima map through it) and all 16 frames are scanned (n_fr = 16, step 1)
+// instead of frames 0 and 8 (n_fr = 2, step 8).
+template <bool kLut>
 __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* __restrict__ frames,
                                                              const StackDev* __restrict__ stacks,
-                                                             uint32_t* __restrict__ sides /* [n][2][4] l,r,t,b */) {
+                                                             uint32_t* __restrict__ sides /* [n][n_fr][4] l,r,t,b */, uint32_t n_fr,
+                                                             uint32_t fr_step, const uint8_t* __restrict__ luts /* [n][256] */) {
     __shared__ uint32_t hist[kColPanel * 257];  // column panels: one histogram per strip; row panels: 4 sub-histograms per warp
     __shared__ uint32_t flags[kColPanel];
     __shared__ uint32_t s_min[kColPanel], s_max[kColPanel];
     __shared__ uint32_t s_count, s_stop, s_need_hist;
-    const uint32_t b = blockIdx.x, side = b & 3, fr = (b >> 2) & 1, s = b >> 3;
+    __shared__ uint8_t s_lut[kLut ? 256 : 4];
+    const uint32_t b = blockIdx.x, side = b & 3, fr = (b >> 2) % n_fr, s = (b >> 2) / n_fr;
     const StackDev sd = stacks[s];
     if (sd.status != VDF_STACK_OK) return;
-    const uint8_t* img = frames + sd.offset + (uint64_t)(fr * 8) * sd.frame_stride;
+    if (kLut) {
+        s_lut[threadIdx.x] = luts[(size_t)s * 256 + threadIdx.x];  // 256 threads
+        __syncthreads();
+    }
+    auto M = [&](uint32_t v) -> uint32_t { return kLut ? (uint32_t)s_lut[v] : v; };
+    const uint8_t* img = frames + sd.offset + (uint64_t)(fr * fr_step) * sd.frame_stride;
     const uint32_t W = sd.width, H = sd.height, P = sd.pitch;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_count = 0, s_stop = 0;
@@ -96,10 +99,10 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
         __syncthreads();
         if (cols) {
             const uint8_t* col = img + (side == 0 ? 0u : W - 1);
-            for (uint32_t y = tid; y < H; y += 256) atomicAdd(&hist[__ldg(col + (uint64_t)y * P)], 1u);
+            for (uint32_t y = tid; y < H; y += 256) atomicAdd(&hist[M(__ldg(col + (uint64_t)y * P))], 1u);
         } else {
             const uint8_t* row = img + (uint64_t)(side == 2 ? 0u : H - 1) * P;
-            for (uint32_t x = tid; x < W; x += 256) atomicAdd(&hist[__ldg(row + x)], 1u);
+            for (uint32_t x = tid; x < W; x += 256) atomicAdd(&hist[M(__ldg(row + x))], 1u);
         }
         __syncthreads();
         if (warp == 0) {
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
         }
         __syncthreads();
         if (s_stop) {
-            if (tid == 0) sides[(s * 2 + fr) * 4 + side] = 0;
+            if (tid == 0) sides[((size_t)s * n_fr + fr) * 4 + side] = 0;
             return;
         }
     }
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
                 }
                 __syncthreads();
                 if (tid < kColPanel) {
-                    const bool nar = s_max[tid] - s_min[tid] <= (uint32_t)kLbTol;  // H >= 1: max >= min
+                    const bool nar = M(s_max[tid]) - M(s_min[tid]) <= (uint32_t)kLbTol;  // H >= 1: max >= min
                     flags[tid] = nar;
                     if (!nar) s_need_hist = 1;
                 }
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const uint32_t c = 4 * wq + q, k = side == 0 ? c : 31 - c;
-                                    if (!flags[k]) atomicAdd(&hist[k * 257 + ((v[u] >> (8 * q)) & 255u)], 1u);
+                                    if (!flags[k]) atomicAdd(&hist[k * 257 + M((v[u] >> (8 * q)) & 255u)], 1u);
                                 }
                             }
                         }
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
                         }
 #pragma unroll
                         for (int u = 0; u < 16; ++u)
-                            if (v[u] != 0xFFFFu) atomicAdd(&hist[lane * 257 + v[u]], 1u);
+                            if (v[u] != 0xFFFFu) atomicAdd(&hist[lane * 257 + M(v[u])], 1u);
                     }
                 }
                 __syncthreads();
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
                     uint32_t a = min(min(mn[i] & 255u, (mn[i] >> 8) & 255u), min((mn[i] >> 16) & 255u, mn[i] >> 24));
                     uint32_t b = max(max(mx[i] & 255u, (mx[i] >> 8) & 255u), max((mx[i] >> 16) & 255u, mx[i] >> 24));
                     a = __reduce_min_sync(0xffffffffu, a), b = __reduce_max_sync(0xffffffffu, b);
-                    if (base + warp + 8 * i < H && b - a <= (uint32_t)kLbTol) decided |= 1u << i;
+                    if (base + warp + 8 * i < H && M(b) - M(a) <= (uint32_t)kLbTol) decided |= 1u << i;
                 }
             }
             for (uint32_t i = 0; i < kRowPanel / 8; ++i) {
@@ -291,20 +294,20 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
                     uint32_t mx = max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
                     if (tail < 0x100u) mn = min(mn, tail), mx = max(mx, tail);
                     mn = __reduce_min_sync(0xffffffffu, mn), mx = __reduce_max_sync(0xffffffffu, mx);
-                    ok = mx - mn <= (uint32_t)kLbTol;
+                    ok = M(mx) - M(mn) <= (uint32_t)kLbTol;
                     if (!ok) {
                         for (int q = lane; q < 4 * 257; q += 32) h4[q] = 0;
                         __syncwarp();
 #pragma unroll
                         for (int u = 0; u < 16; ++u) {
                             if (u * 32 + lane < W4) {
-                                atomicAdd(&hs[v[u] & 255u], 1u);
-                                atomicAdd(&hs[(v[u] >> 8) & 255u], 1u);
-                                atomicAdd(&hs[(v[u] >> 16) & 255u], 1u);
-                                atomicAdd(&hs[v[u] >> 24], 1u);
+                                atomicAdd(&hs[M(v[u] & 255u)], 1u);
+                                atomicAdd(&hs[M((v[u] >> 8) & 255u)], 1u);
+                                atomicAdd(&hs[M((v[u] >> 16) & 255u)], 1u);
+                                atomicAdd(&hs[M(v[u] >> 24)], 1u);
                             }
                         }
-                        if (tail < 0x100u) atomicAdd(&hs[tail], 1u);
+                        if (tail < 0x100u) atomicAdd(&hs[M(tail)], 1u);
                         __syncwarp();
                         for (int q = lane; q < 256; q += 32) h4[q] += h4[257 + q] + h4[514 + q] + h4[771 + q];
                         __syncwarp();
@@ -326,10 +329,10 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
 #pragma unroll
                             for (int u = 0; u < 16; ++u) {
                                 if (q0 + u * 32 + lane < W4) {
-                                    atomicAdd(&hs[v[u] & 255u], 1u);
-                                    atomicAdd(&hs[(v[u] >> 8) & 255u], 1u);
-                                    atomicAdd(&hs[(v[u] >> 16) & 255u], 1u);
-                                    atomicAdd(&hs[v[u] >> 24], 1u);
+                                    atomicAdd(&hs[M(v[u] & 255u)], 1u);
+                                    atomicAdd(&hs[M((v[u] >> 8) & 255u)], 1u);
+                                    atomicAdd(&hs[M((v[u] >> 16) & 255u)], 1u);
+                                    atomicAdd(&hs[M(v[u] >> 24)], 1u);
                                 }
                             }
                         }
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
                         }
 #pragma unroll
                         for (int u = 0; u < 16; ++u)
-                            if (v[u] < 0x100u) atomicAdd(&hs[v[u]], 1u);
+                            if (v[u] < 0x100u) atomicAdd(&hs[M(v[u])], 1u);
                     }
                     __syncwarp();
                     for (int q = lane; q < 256; q += 32) h4[q] += h4[257 + q] + h4[514 + q] + h4[771 + q];
@@ -370,21 +373,21 @@ __global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* _
         __syncthreads();
         if (s_stop) break;
     }
-    if (tid == 0) sides[(s * 2 + fr) * 4 + side] = s_count;
+    if (tid == 0) sides[((size_t)s * n_fr + fr) * 4 + side] = s_count;
 }
 
 // per frame: keep (l,r,t,b) only if at least one pixel remains each way (video_frames_gray.rs:119-127);
 // across frames 0 and 8: per-side minimum (Crop::union, crop.rs:53-68)
-__global__ void crop_combine_kernel(const StackDev* __restrict__ stacks, const uint32_t* __restrict__ sides, uint32_t n,
+__global__ void crop_combine_kernel(const StackDev* __restrict__ stacks, const uint32_t* __restrict__ sides, uint32_t n, uint32_t n_fr,
                                     uint32_t* __restrict__ crop /* [n][4] */) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t out[4] = {0, 0, 0, 0};
     if (stacks[s].status == VDF_STACK_OK) {
         const int W = (int)stacks[s].width, H = (int)stacks[s].height;
-        for (int fr = 0; fr < 2; ++fr) {
+        for (uint32_t fr = 0; fr < n_fr; ++fr) {
             uint32_t c[4];
-            for (int k = 0; k < 4; ++k) c[k] = sides[(s * 2 + fr) * 4 + k];
+            for (int k = 0; k < 4; ++k) c[k] = sides[((size_t)s * n_fr + fr) * 4 + k];
             if (!(W - (int)c[0] - (int)c[1] >= 1 && H - (int)c[2] - (int)c[3] >= 1)) c[0] = c[1] = c[2] = c[3] = 0;
             for (int k = 0; k < 4; ++k) out[k] = fr == 0 ? c[k] : min(out[k], c[k]);
         }
@@ -827,6 +830,16 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
     if (out_hash) finish_stack<Cfg::kThreads>(small, s, done, out_hash, reinterpret_cast<double*>(ring), tid);
 }
 
+// the letterbox union over ALL 16 frames of every stack, each pixel through the stack's table first (motion.cu)
+int letterbox_all_frames(vdf_ctx* ctx, const uint8_t* d_frames, const StackDev* d_sd, uint32_t n, const uint8_t* d_luts, uint32_t* d_sides,
+                         uint32_t* d_crop) {
+    letterbox_side_kernel<true><<<n * 16 * 4, 256, 0, ctx->stream>>>(d_frames, d_sd, d_sides, 16u, 1u, d_luts);
+    VDF_LAUNCHED(ctx);
+    crop_combine_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_sd, d_sides, n, 16u, d_crop);
+    VDF_LAUNCHED(ctx);
+    return VDF_OK;
+}
+
 // stand-alone DCT + pack over the stacks of a pass (context option "hash_fuse_dct" = 0): stacks the pass skipped keep what an
 // earlier pass wrote, stacks in error read as zero
 __global__ void __launch_bounds__(256) dct_pack_jobs_kernel(const uint8_t* __restrict__ small, const StackJob* __restrict__ jobs, uint32_t n,
@@ -1211,9 +1224,9 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         if (lb != st) {  // all scans are enqueued up front on their own stream; the resize of chunk k waits for scan k only
             for (uint32_t k = 0; k < n_chunks; ++k) {
                 const uint32_t s0 = chunk_begin(k), cnt = chunk_begin(k + 1) - s0;
-                letterbox_side_kernel<<<cnt * 8, 256, 0, lb>>>(d_frames, d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8);
+                letterbox_side_kernel<false><<<cnt * 8, 256, 0, lb>>>(d_frames, d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, 2u, 8u, nullptr);
                 VDF_LAUNCHED(ctx);
-                crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, lb>>>(d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt,
+                crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, lb>>>(d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt, 2u,
                                                                       ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4);
                 VDF_LAUNCHED(ctx);
                 VDF_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[k], lb));
@@ -1230,9 +1243,9 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
                 if (lb != st) {
                     VDF_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_chunk[k], 0));
                 } else {
-                    letterbox_side_kernel<<<cnt * 8, 256, 0, st>>>(d_frames, d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8);
+                    letterbox_side_kernel<false><<<cnt * 8, 256, 0, st>>>(d_frames, d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, 2u, 8u, nullptr);
                     VDF_LAUNCHED(ctx);
-                    crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt,
+                    crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt, 2u,
                                                                           ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4);
                     VDF_LAUNCHED(ctx);
                     if (k == n_chunks - 1) kt_end(ctx, 2);
