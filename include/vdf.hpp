@@ -225,6 +225,9 @@ class MatchGroup {
 
 // ---- search (video_dup_finder.rs) -----------------------------------------------------------------------------
 namespace detail {
+inline int cropdetect_code(Cropdetect c) {  // definitions.rs:46-54 -> VDF_CROPDETECT_*
+    return c == Cropdetect::None ? VDF_CROPDETECT_NONE : c == Cropdetect::Letterbox ? VDF_CROPDETECT_LETTERBOX : VDF_CROPDETECT_MOTION;
+}
 // Vec<VideoHash> -> the struct-of-arrays the C ABI takes (caller's order; paths as one blob + n+1 offsets)
 struct Soa {
     std::vector<uint64_t> words;
@@ -383,7 +386,6 @@ class VideoHashBuilder {  // video_hash_builder.rs:70-83; decoding (:85-167) sta
     // many videos per launch: the frames of each stack are gathered into one staging buffer
     std::vector<HashResult> hash_many(const std::vector<std::vector<GrayFrame>>& stacks, const std::vector<std::string>& paths,
                                       const std::vector<uint32_t>& durations) {
-        if (options_.cropdetect == Cropdetect::Motion) throw std::invalid_argument("Cropdetect::Motion is outside the GPU hot path");
         const uint32_t n = (uint32_t)stacks.size();
         std::vector<vdf_stack_desc> desc(n);
         std::vector<uint8_t> buf;
@@ -411,7 +413,7 @@ class VideoHashBuilder {  // video_hash_builder.rs:70-83; decoding (:85-167) sta
         std::vector<uint64_t> words((size_t)n * HASH_WORDS);
         std::vector<int32_t> status(n);
         ctx_.check(vdf_hash_stacks(ctx_.get(), buf.data(), desc.data(), n,
-                                   options_.cropdetect == Cropdetect::None ? VDF_CROPDETECT_NONE : VDF_CROPDETECT_LETTERBOX,
+                                   detail::cropdetect_code(options_.cropdetect),
                                    words.data(), status.data(), nullptr));
         std::vector<HashResult> out;
         for (uint32_t s = 0; s < n; ++s) {
@@ -443,9 +445,7 @@ class HashPipeline {
         HashResult result;
     };
     HashPipeline(Context& ctx, CreationOptions options = {}, uint32_t max_batch_stacks = 64, uint64_t batch_bytes = 1ull << 30) {
-        if (options.cropdetect == Cropdetect::Motion) throw std::invalid_argument("Cropdetect::Motion is outside the GPU hot path");
-        const int rc = vdf_pipeline_create(ctx.get(), max_batch_stacks, batch_bytes,
-                                           options.cropdetect == Cropdetect::None ? VDF_CROPDETECT_NONE : VDF_CROPDETECT_LETTERBOX, &p_);
+        const int rc = vdf_pipeline_create(ctx.get(), max_batch_stacks, batch_bytes, detail::cropdetect_code(options.cropdetect), &p_);
         if (rc != VDF_OK) throw DeviceError(rc, "vdf_pipeline_create");
     }
     ~HashPipeline() { vdf_pipeline_destroy(p_); }

@@ -61,6 +61,8 @@ extern "C" {
 
 #define VDF_CROPDETECT_NONE 0      /* Cropdetect::None      (definitions.rs:46-54) */
 #define VDF_CROPDETECT_LETTERBOX 1 /* Cropdetect::Letterbox (the library default, video_hash_builder.rs:55-63) */
+#define VDF_CROPDETECT_MOTION 2    /* Cropdetect::Motion: MotiondetectCrop::from_frames (vid_dup_finder_common/src/motioncrop/
+                                      autocrop_frames.rs:36-218), csrc/motion.cu */
 
 typedef struct vdf_ctx vdf_ctx;
 typedef struct vdf_table vdf_table; /* `Search` (search_algorithm.rs:5-23): a sorted table prepared for searching, resident in HBM */
@@ -332,7 +334,8 @@ void vdf_free_csr(vdf_csr* c);
  * Lanczos3 u8), Dct3d::from_images + dct_3d (dct_3d.rs:15-53, raw_dct_ops.rs:107-142, f64) and the
  * threshold / bit pack (dct_3d.rs:55-66, video_hash.rs:63-70).
  * frames: host pointer; stacks are staged to HBM with pinned async copies.  out_hash: n x 16 u64.
- * out_status: n x i32 (VDF_STACK_*).  out_crop: optional n x 4 u32 (left, right, top, bottom). */
+ * out_status: n x i32 (VDF_STACK_*).  out_crop: optional n x 4 u32 (left, right, top, bottom).
+ * cropdetect: VDF_CROPDETECT_NONE / _LETTERBOX / _MOTION. */
 int vdf_hash_stacks(vdf_ctx* ctx, const uint8_t* frames, const vdf_stack_desc* desc, uint32_t n, int cropdetect,
                     uint64_t* out_hash, int32_t* out_status, uint32_t* out_crop);
 

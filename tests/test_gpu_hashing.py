@@ -285,3 +285,62 @@ def test_full_size_1080p_batch(ctx):
     out2 = torch.zeros_like(out)
     ctx.hash_stacks_device(d.data_ptr(), _ffi.make_descs(n, 1920, 1080), 1, out2.data_ptr())
     assert torch.equal(out, out2)
+
+
+def _video_in_a_frame(w, h, seed, box=None, second=None, stretch=False):
+    """a bright static surround with a darker picture that moves inside `box` = (x, y, bw, bh) -- what Cropdetect::Motion is for"""
+    rng = np.random.default_rng(seed)
+    st = np.full((16, h, w), 235, np.uint8)
+    st += rng.integers(0, 3, (1, h, w), dtype=np.uint8)  # static texture: no motion outside the boxes
+    for bx in (box, second):
+        if bx is None:
+            continue
+        x, y, bw, bh = bx
+        yy, xx = np.mgrid[0:bh, 0:bw]
+        for t in range(16):
+            pic = 90 + 60 * np.sin(2 * np.pi * (xx / bw * 2 + t / 16.0)) * np.cos(2 * np.pi * (yy / bh + t / 8.0)) + rng.integers(-6, 7, (bh, bw))
+            st[t, y:y + bh, x:x + bw] = np.clip(pic, 1, 200).astype(np.uint8)
+    if stretch:  # neither 0 nor 255 anywhere: the contrast stretch applies
+        st = (20 + st.astype(np.uint16) * 180 // 255).astype(np.uint8)
+    return st
+
+
+def test_motion_crop_matches_oracle(ctx):
+    """Cropdetect::Motion on the GPU (csrc/motion.cu) against oracle/motioncrop_oracle.py: crop and hash words, on stacks with
+    one moving picture, two (the second pass and the selection rule), none (letterbox fallback), with and without the contrast
+    stretch, below and above the 100-row limit of the opening"""
+    from oracle import motioncrop_oracle as mo
+
+    cases = [
+        _video_in_a_frame(96, 64, 1, box=(20, 12, 50, 36)),
+        _video_in_a_frame(96, 64, 2, box=(8, 6, 40, 30), second=(56, 30, 30, 28)),
+        _video_in_a_frame(96, 64, 3),
+        _video_in_a_frame(96, 64, 4, box=(20, 12, 50, 36), stretch=True),
+        _video_in_a_frame(160, 112, 5, box=(30, 20, 90, 70)),
+        _video_in_a_frame(160, 112, 6, box=(10, 10, 60, 44), second=(84, 56, 64, 48), stretch=True),
+    ]
+    lb = _video_in_a_frame(96, 64, 7, box=(20, 12, 50, 36))
+    lb[:, :6, :] = 16  # a letterbox bar on top of it all
+    cases.append(lb)
+    for k, st in enumerate(cases):
+        want = mo.cropdetect_motion(list(st))
+        got_h, got_s, got_c = gpu_hash(ctx, st[None], _ffi.CROPDETECT_MOTION)
+        assert got_s[0] == 0 and tuple(int(v) for v in got_c[0]) == tuple(want), (k, got_c[0], want)
+        l, r, t, b = want
+        h, w = st.shape[1:]
+        _, want_h, _, _ = o.hash_stack(np.ascontiguousarray(st[:, t:h - b, l:w - r]), 0)
+        assert np.array_equal(got_h[0], want_h), k
+    assert tuple(int(v) for v in gpu_hash(ctx, cases[0][None], _ffi.CROPDETECT_MOTION)[2][0]) != (0, 0, 0, 0)
+    # a batch with different sizes and an error stack in one call
+    n = 3
+    frames = np.concatenate([cases[0].reshape(-1), cases[4].reshape(-1), cases[2].reshape(-1)])
+    d = np.zeros(n, dtype=_ffi.STACK_DESC_DTYPE)
+    sizes = [(96, 64), (160, 112), (96, 64)]
+    off = 0
+    for s, (w, h) in enumerate(sizes):
+        d[s] = (off, w * h, w, h, w, 16 if s != 2 else 9, 0, 0)
+        off += 16 * w * h
+    got_h, got_s, got_c = ctx.hash_stacks(frames, d, _ffi.CROPDETECT_MOTION)
+    assert got_s.tolist() == [0, 0, _ffi.STACK_NOT_ENOUGH_FRAMES]
+    assert tuple(int(v) for v in got_c[0]) == tuple(mo.cropdetect_motion(list(cases[0])))
+    assert tuple(int(v) for v in got_c[1]) == tuple(mo.cropdetect_motion(list(cases[4])))

@@ -18,7 +18,7 @@ _SO = os.environ.get("VDF_B200_SO") or os.path.join(_HERE, "libvdf_b200.so")  # 
 OK = 0
 ERR_CUDA, ERR_ALLOC, ERR_INVALID, ERR_EDGE_OVERFLOW, ERR_NO_DEVICE = -1, -2, -3, -4, -5
 STACK_OK, STACK_NOT_ENOUGH_FRAMES, STACK_VIDPROC = 0, 1, 2
-CROPDETECT_NONE, CROPDETECT_LETTERBOX = 0, 1
+CROPDETECT_NONE, CROPDETECT_LETTERBOX, CROPDETECT_MOTION = 0, 1, 2
 STACK_FLAG_MIXED_SIZES = 1
 
 EXPORTS = [
@@ -178,6 +178,19 @@ def make_descs(n: int, width: int, height: int, n_frames: int = 16, pitch: Optio
     return d
 
 
+class _GroupsOwner:
+    """keeps a vdf_groups result alive while numpy views of it exist, then returns it to the library"""
+
+    def __init__(self, g: Groups):
+        self._g = Groups(g.n_groups, g.group_ptr, g.member_idx)
+
+    def __del__(self):
+        try:
+            lib().vdf_free_groups(C.byref(self._g))
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU (device: int) or several GPUs of one node driven from this process (device: a list of ids,
     vdf_ctx_create_multi); one stream per GPU, not thread-safe (see include/vdf_b200.h)."""
@@ -248,11 +261,18 @@ class Context:
         return out
 
     def _groups(self, g: Groups):
+        """(group_ptr, member_idx) as numpy views of the library's result block (no copy: at 1 M hashes the CSR is 2.7 MB);
+        the block goes back to the library's pool when both arrays are gone"""
         ng = int(g.n_groups)
-        gp = _copy_u64(g.group_ptr, ng + 1)
-        mm = _copy_u64(g.member_idx, int(gp[-1]) if ng else 0)
-        lib().vdf_free_groups(C.byref(g))
-        return gp, mm
+        if ng == 0:
+            lib().vdf_free_groups(C.byref(g))
+            return np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint64)
+        owner = _GroupsOwner(g)
+        total = int(g.group_ptr[ng])
+        gp_buf = (C.c_uint64 * (ng + 1)).from_address(C.addressof(g.group_ptr.contents))
+        mm_buf = (C.c_uint64 * max(total, 1)).from_address(C.addressof(g.member_idx.contents))
+        gp_buf._owner, mm_buf._owner = owner, owner
+        return np.frombuffer(gp_buf, dtype=np.uint64), np.frombuffer(mm_buf, dtype=np.uint64)[:total]
 
     def stage_sorted(self, hashes, durations, path_blob: np.ndarray, path_off: np.ndarray, d_hash_dst: int = 0, d_dur_dst: int = 0):
         """vdf_stage_sorted: -> (order [n] int64, device pointer of the sorted hashes, device pointer of the sorted durations);

@@ -235,8 +235,9 @@ void vdf_free_edges(vdf_edges* e) {
 }
 void vdf_free_groups(vdf_groups* g) {
     if (!g) return;
-    free(g->group_ptr);
-    free(g->member_idx);
+    // one block (group_ptr, then member_idx) from the library's result pool, see group.cu
+    if (g->group_ptr && g->member_idx && g->member_idx != g->group_ptr + g->n_groups + 1) free(g->member_idx);
+    vdf::result_free(g->group_ptr);
     g->group_ptr = g->member_idx = nullptr;
     g->n_groups = 0;
 }

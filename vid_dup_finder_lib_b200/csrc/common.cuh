@@ -336,6 +336,9 @@ int mgpu_search_refs(vdf_ctx* ctx, const uint64_t* ref_hashes, const uint32_t* r
                      double tolerance, vdf_csr* out);
 int mgpu_hash_stacks(vdf_ctx* ctx, const uint8_t* frames, const vdf_stack_desc* desc, uint32_t n, int cropdetect, uint64_t* out_hash,
                      int32_t* out_status, uint32_t* out_crop);
+// group.cu: host memory of results handed to the caller (a pool of pinned buffers; plain malloc when the pool is lent out)
+void* result_alloc(size_t bytes);
+void result_free(void* p);
 // group.cu (d_remap, optional: sorted position -> the caller's index, applied to every member that is written out)
 int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys_sorted, uint64_t n_edges, const uint32_t* d_remap, vdf_groups* out);
 int group_components_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64_t n_edges, const uint32_t* d_remap, vdf_groups* out);

@@ -21,6 +21,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -163,11 +164,65 @@ __global__ void group_csr_kernel(const uint64_t* __restrict__ mk, const uint32_t
     }
 }
 
+// ---- result memory ---------------------------------------------------------------------------------------------------
+// A vdf_groups is ONE block: group_ptr[n_groups + 1] followed by member_idx[].  The block comes from a small process-wide
+// pool of pinned host buffers, so the device -> host copy of a result lands where the caller reads it (round 1 copied
+// device -> pinned staging -> malloc'ed arrays: at 1 M hashes those copies were a third of a millisecond per search);
+// vdf_free_groups hands the slot back.  When every slot is lent out the block is plain malloc memory.
+namespace {
+constexpr int kResultSlots = 8;
+struct ResultSlot {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool busy = false;
+};
+ResultSlot g_slots[kResultSlots];
+std::mutex g_slots_mu;
+}  // namespace
+
+void* result_alloc(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_slots_mu);
+        for (ResultSlot& sl : g_slots) {
+            if (sl.busy) continue;
+            if (sl.cap < bytes) {
+                if (sl.p) cudaFreeHost(sl.p);
+                sl.p = nullptr, sl.cap = 0;
+                const size_t want = bytes + bytes / 4 + 4096;
+                if (cudaMallocHost(&sl.p, want) != cudaSuccess) {
+                    cudaGetLastError();
+                    sl.p = nullptr;
+                    break;
+                }
+                sl.cap = want;
+            }
+            sl.busy = true;
+            return sl.p;
+        }
+    }
+    return malloc(bytes ? bytes : 8);
+}
+
+void result_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_slots_mu);
+        for (ResultSlot& sl : g_slots)
+            if (sl.p == p) {
+                sl.busy = false;
+                return;
+            }
+    }
+    free(p);
+}
+
 static int empty_groups(vdf_groups* out) {
     out->n_groups = 0;
-    out->group_ptr = (uint64_t*)calloc(1, sizeof(uint64_t));
-    out->member_idx = (uint64_t*)calloc(1, sizeof(uint64_t));
-    return (out->group_ptr && out->member_idx) ? VDF_OK : VDF_ERR_ALLOC;
+    out->group_ptr = (uint64_t*)result_alloc(2 * sizeof(uint64_t));
+    if (!out->group_ptr) return VDF_ERR_ALLOC;
+    out->group_ptr[0] = 0, out->group_ptr[1] = 0;
+    out->member_idx = out->group_ptr + 1;
+    return VDF_OK;
 }
 
 // tot[0] = members, tot[1] = groups are final on the stream; CSR in g_gp / g_mem -> host arrays
@@ -179,21 +234,17 @@ static int fetch_groups(vdf_ctx* ctx, const unsigned long long* d_tot, vdf_group
     VDF_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t nm = h[0], ng = h[1];
     if (nm == 0) return empty_groups(out);
+    const size_t gp_bytes = (size_t)(ng + 1) * 8, mem_bytes = (size_t)(nm + ng) * 8;
     out->n_groups = ng;
-    out->group_ptr = (uint64_t*)malloc((size_t)(ng + 1) * 8);
-    out->member_idx = (uint64_t*)malloc((size_t)(nm + ng) * 8);
-    if (!out->group_ptr || !out->member_idx) {
+    out->group_ptr = (uint64_t*)result_alloc(gp_bytes + mem_bytes);  // pinned when a pool slot is free: the copies land in place
+    if (!out->group_ptr) {
         ctx->err = "host allocation failed";
         return VDF_ERR_ALLOC;
     }
-    // through pinned staging: a device -> pageable copy of these ~2 MB costs more than the rest of the grouping
-    const size_t gp_bytes = (size_t)(ng + 1) * 8, mem_bytes = (size_t)(nm + ng) * 8;
-    VDF_ALLOC(ctx, ctx->h_groups.ensure(gp_bytes + mem_bytes));
-    VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_groups.p, ctx->g_gp.p, gp_bytes, cudaMemcpyDeviceToHost, st));
-    VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_groups.as<uint8_t>() + gp_bytes, ctx->g_mem.p, mem_bytes, cudaMemcpyDeviceToHost, st));
+    out->member_idx = out->group_ptr + ng + 1;
+    VDF_CUDA(ctx, cudaMemcpyAsync(out->group_ptr, ctx->g_gp.p, gp_bytes, cudaMemcpyDeviceToHost, st));
+    VDF_CUDA(ctx, cudaMemcpyAsync(out->member_idx, ctx->g_mem.p, mem_bytes, cudaMemcpyDeviceToHost, st));
     VDF_CUDA(ctx, cudaStreamSynchronize(st));
-    memcpy(out->group_ptr, ctx->h_groups.p, gp_bytes);
-    memcpy(out->member_idx, ctx->h_groups.as<uint8_t>() + gp_bytes, mem_bytes);
     ctx->d2h += 16 + gp_bytes + mem_bytes;
     return VDF_OK;
 }

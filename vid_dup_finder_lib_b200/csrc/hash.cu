@@ -1101,8 +1101,8 @@ int hash_from_small_device(vdf_ctx* ctx, const uint8_t* d_small, uint32_t n, uin
 int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_desc* desc, uint32_t n, int cropdetect,
                        uint64_t* d_out_hash, uint8_t* d_out_small, int32_t* out_status, uint32_t* out_crop) {
     if (n == 0) return VDF_OK;
-    if (cropdetect != VDF_CROPDETECT_NONE && cropdetect != VDF_CROPDETECT_LETTERBOX) {
-        ctx->err = "cropdetect must be VDF_CROPDETECT_NONE or VDF_CROPDETECT_LETTERBOX";
+    if (cropdetect != VDF_CROPDETECT_NONE && cropdetect != VDF_CROPDETECT_LETTERBOX && cropdetect != VDF_CROPDETECT_MOTION) {
+        ctx->err = "cropdetect must be VDF_CROPDETECT_NONE, VDF_CROPDETECT_LETTERBOX or VDF_CROPDETECT_MOTION";
         return VDF_ERR_INVALID;
     }
     VDF_TRY(load_dct_consts(ctx));
@@ -1233,6 +1233,8 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
             }
             kt_end(ctx, 2, lb);
         }
+    } else if (cropdetect == VDF_CROPDETECT_MOTION) {
+        VDF_TRY(motion_crop_device(ctx, d_frames, d_sd, sd, n, ctx->h_crop.as<uint32_t>()));  // Cropdetect::Motion (motion.cu)
     } else {
         VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_crop.p, 0, (size_t)n * 16, st));  // Cropdetect::None: zero crop (:195-199)
     }

@@ -12,7 +12,7 @@ HASH_WORDS = -(-HASH_BITS // 64)  # definitions.rs:43 (usize::BITS = 64)
 
 
 class Cropdetect(enum.Enum):
-    """definitions.rs:46-54.  Motion is a non-default option outside the B200 hot path."""
+    """definitions.rs:46-54.  Letterbox is the library default; Motion is the non-default option of SURVEY.md section 8(f) N4."""
 
     NONE = 0
     LETTERBOX = 1

@@ -72,11 +72,15 @@ def _sync(device):
         torch.cuda.current_stream().synchronize()
 
 
-def _run_growing(fn, device, initial: int = 1 << 22):
+def _run_growing(fn, device, initial: int = 1 << 22, ctx=None):
     cap = initial
     while True:
-        keys = torch.empty(cap, dtype=torch.int64, device=device)
-        _sync(device)
+        if ctx is not None:
+            keys = _key_buffer(ctx, cap, device)
+            cap = keys.numel()
+        else:
+            keys = torch.empty(cap, dtype=torch.int64, device=device)
+            _sync(device)
         cnt = fn(keys.data_ptr(), cap)
         if cnt >= 0:
             return keys[:cnt]
@@ -107,13 +111,23 @@ def disable_peer_exchange(ctx: _ffi.Context, group=None):
         ctx.peer_close()
 
 
+def _key_buffer(ctx: _ffi.Context, cap: int, device) -> torch.Tensor:
+    """the context's key buffer (the result of a search is a view of it, valid until the context's next search): allocating
+    4 M keys and synchronising for every search cost a fifth of a millisecond per step"""
+    buf = getattr(ctx, "_key_buf", None)
+    if buf is None or buf.numel() < cap or buf.device != torch.device(device):
+        buf = torch.empty(cap, dtype=torch.int64, device=device)
+        _sync(device)
+        ctx._key_buf = buf
+    return buf
+
+
 def _run_exchange(ctx: _ffi.Context, fn, device, group):
     """fn with the library's "exchange" option on: returns the sorted keys of ALL ranks.  An overflow is reported with the same
     global count on every rank, so all ranks re-allocate (collectively) and retry together."""
     while True:
         cap = ctx.peer_capacity
-        keys = torch.empty(cap, dtype=torch.int64, device=device)
-        _sync(device)
+        keys = _key_buffer(ctx, cap, device)
         ctx.set_option("exchange", 1)
         try:
             cnt = fn(keys.data_ptr(), cap)
@@ -148,7 +162,7 @@ def search_self_keys(ctx: _ffi.Context, d_hash, d_dur, tol_int: int, group=None,
             run = lambda p, cap: ctx.search_self_device(p_hash, p_dur, n, tol_int, p, cap)  # noqa: E731
         if fused:
             return _run_exchange(ctx, run, device, group)
-        local = _run_growing(run, device)
+        local = _run_growing(run, device, ctx=ctx)
     finally:
         ctx.set_shard(0, 1)
     return merge_keys(local, group)
@@ -169,7 +183,7 @@ def search_refs_keys(ctx: _ffi.Context, d_cand_slice, d_cand_dur_slice, cand_bas
     world = world_info(group)[1]
     if allow_fused and world > 1 and ctx.peer_world == world:
         return _run_exchange(ctx, run, d_refs.device, group)
-    return merge_keys(_run_growing(run, d_refs.device), group)
+    return merge_keys(_run_growing(run, d_refs.device, ctx=ctx), group)
 
 
 def csr_from_keys(keys: np.ndarray, n_rows: int) -> Tuple[np.ndarray, np.ndarray]:

@@ -55,11 +55,8 @@ def frame_schedule(vid_duration: float, opts: CreationOptions = CreationOptions(
 
 
 def _cropdetect_code(c: Cropdetect) -> int:
-    if c == Cropdetect.NONE:
-        return _ffi.CROPDETECT_NONE
-    if c == Cropdetect.LETTERBOX:
-        return _ffi.CROPDETECT_LETTERBOX
-    raise NotImplementedError("Cropdetect.MOTION is outside the B200 hot path (SURVEY.md section 8(f) N4)")
+    return {Cropdetect.NONE: _ffi.CROPDETECT_NONE, Cropdetect.LETTERBOX: _ffi.CROPDETECT_LETTERBOX,
+            Cropdetect.MOTION: _ffi.CROPDETECT_MOTION}[c]  # Motion: csrc/motion.cu
 
 
 class VideoHashBuilder:
