@@ -1,5 +1,5 @@
-"""CPU restatement of `Cropdetect::Motion` (TEST INFRASTRUCTURE, groundwork for SURVEY.md section 8(f) N4; no product
-code path exists for it yet - the host layer raises for Cropdetect.Motion).
+"""CPU restatement of `Cropdetect::Motion` (TEST INFRASTRUCTURE for SURVEY.md section 8(f) N4: the product path is
+csrc/motion.cu, compared with this file bit for bit by tests/test_gpu_hashing.py::test_motion_crop_matches_oracle).
 
 Follows vid_dup_finder_common/src/motioncrop/{autocrop_frames.rs:36-316, darkest_frame.rs:19-111, frame_change.rs:15-132,
 utils.rs:8-131} and crop.rs:32-199.  The arithmetic of four un-vendored crates is restated from their published

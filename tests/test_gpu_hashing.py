@@ -318,6 +318,7 @@ def test_motion_crop_matches_oracle(ctx):
         _video_in_a_frame(96, 64, 4, box=(20, 12, 50, 36), stretch=True),
         _video_in_a_frame(160, 112, 5, box=(30, 20, 90, 70)),
         _video_in_a_frame(160, 112, 6, box=(10, 10, 60, 44), second=(84, 56, 64, 48), stretch=True),
+        _video_in_a_frame(320, 240, 11, box=(40, 30, 200, 150), second=(250, 170, 60, 56)),  # opening by 10
     ]
     lb = _video_in_a_frame(96, 64, 7, box=(20, 12, 50, 36))
     lb[:, :6, :] = 16  # a letterbox bar on top of it all

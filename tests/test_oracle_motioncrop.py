@@ -1,6 +1,6 @@
 """The reference's seven motion-crop tests (vid_dup_finder_common/src/motioncrop/test.rs:9-225) against the CPU restatement
-of `Cropdetect::Motion` (oracle/motioncrop_oracle.py).  Groundwork for SURVEY.md section 8(f) N4: there is no GPU path for
-this non-default option yet; these tests pin the oracle that path will be built against.  Frames are repeated twice, as
+of `Cropdetect::Motion` (oracle/motioncrop_oracle.py).  SURVEY.md section 8(f) N4: these tests pin the oracle
+that csrc/motion.cu is compared with (tests/test_gpu_hashing.py::test_motion_crop_matches_oracle).  Frames are repeated twice, as
 `util_generate_frames` does (test.rs:230-242); expected crops are (left, right, top, bottom)."""
 import numpy as np
 import pytest
