@@ -420,6 +420,7 @@ def main():
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    L2_BYTES = int(torch.cuda.get_device_properties(local).L2_cache_size)
     variant = args.variant if args.variant >= 0 else DEFAULT_SEARCH_VARIANT
     dtype_of = lambda v: "e2m1 x e2m1 -> f32 (exact)" if v == 6 else "u8 x u8 -> s32" if v >= 3 else "u32"  # noqa: E731
 
@@ -438,8 +439,8 @@ def main():
 
     def timed(step, steps, warmup, flush_l2):
         """W warm-up steps, then K steps between two CUDA events on the kernels' stream, barrier + synchronize on
-        both sides, max over ranks.  -> seconds.  The L2 flush (a 512 MiB fill, ~0.15 ms) sits INSIDE the timed region:
-        the reported time is conservative by that much per step."""
+        both sides, max over ranks.  -> seconds.  flush_l2 (workloads whose inputs fit the L2): a 512 MiB fill, ~0.15 ms,
+        INSIDE the timed region - the reported time is conservative by that much per step."""
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 step()
@@ -493,6 +494,13 @@ def main():
             d_dur = torch.from_numpy(dur.view(np.int32)).to(dev)
             torch.cuda.current_stream().synchronize()
             tbl = ctx.table_create_device(d_hash.data_ptr(), d_dur.data_ptr(), n, keepalive=(d_hash, d_dur))
+        # what one launch reads on this rank: the 4-bit operand tiles (512 B per hash; its share of the rows and every column)
+        # for the tensor-core kernels, the raw hashes (128 B) for the XOR+POPC ones.  Larger than twice the L2: nothing of a
+        # step survives to the next one and no flush is needed; else a 512 MiB write sits between the steps, inside the timing.
+        operand_bytes = (n // world + n) * 512 if v >= 5 else n * 128
+        flush_l2 = operand_bytes < 2 * L2_BYTES
+        l2_note = (f"operands read per launch {operand_bytes / 1e6:.0f} MB > 2 x L2 ({L2_BYTES / 1e6:.0f} MB): no flush" if not flush_l2 else
+                   f"operands {operand_bytes / 1e6:.0f} MB fit L2: 512 MiB write between timed steps, inside the timed region")
         result = {}
         saved_world = ctx.peer_world
         if not use_exchange:
@@ -511,7 +519,7 @@ def main():
                         step()
                 ctx.kernel_time(0, reset=True)
                 l0 = ctx.counters()[0]
-                secs = timed(step, steps, 0, True)
+                secs = timed(step, steps, 0, flush_l2)
             launches = ctx.counters()[0] - l0
             k_ms, k_n = ctx.kernel_time(0, reset=True)
             value = pairs * steps / secs
@@ -524,7 +532,7 @@ def main():
                               "pairs_per_step": pairs, "edges": int(len(keys_np)), "groups": int(len(result["gp"]) - 1),
                               "parallelism": f"tile-block shard x{world}", "exchange": exchange_note if v == 6 else "NCCL all-gather" if world > 1 else "single GPU",
                               "table": "prepared once (vdf_table: packed tiles, windows, work units), searched per step",
-                              "l2": "512 MiB write between timed steps, inside the timed region (hash table 128 MB ~ L2 126 MB)",
+                              "l2": l2_note,
                               "search_variant": v}}
             if rank == 0 and not args.no_cpu_baseline and args.parity_rows > 0:
                 out["parity_sample"] = parity_rows_self(H, dur, keys_np, tol_int, args.parity_rows if not light else min(args.parity_rows, 32))
@@ -537,7 +545,7 @@ def main():
                 with torch.cuda.stream(stream):
                     step(t_int)
                 ctx.kernel_time(0, reset=True)
-                s_secs = timed(lambda: step(t_int), 2, 0, True)
+                s_secs = timed(lambda: step(t_int), 2, 0, flush_l2)
                 sk_ms, sk_n = ctx.kernel_time(0, reset=True)
                 r = search_roofline(v, pairs / world, sk_ms, sk_n, sm_count, sm_max_mhz)
                 sweep.append({"tolerance": float(ts), "ms_per_step": s_secs / 2 * 1e3, "kernel_ms": r["kernel_ms_per_launch"],
@@ -645,7 +653,7 @@ def main():
                     step()
             ctx.kernel_time(0, reset=True)
             l0 = ctx.counters()[0]
-            secs = timed(step, steps, 0, True)
+            secs = timed(step, steps, 0, False)
         launches = ctx.counters()[0] - l0
         k_ms, k_n = ctx.kernel_time(0, reset=True)
         pairs = nq * nc
@@ -657,7 +665,7 @@ def main():
                "config": {"workload": workload_name("refs", args), "matches": int(len(keys_np)),
                           "parallelism": f"table slice x{world}", "exchange": exchange_note,
                           "table": "each rank's slice prepared once (vdf_table), queries packed per step",
-                          "l2": "512 MiB write between timed steps, inside the timed region"}}
+                          "l2": f"table slice operands {(e - b) * 512 / 1e6:.0f} MB per rank > 2 x L2: no flush"}}
         tbl.close()
         Hc = corpus.cpu().numpy().view(np.uint64)
         cdur = np.full(nc, 600, np.uint32)

@@ -27,7 +27,7 @@ if [[ $STEP == all || $STEP == ncu ]]; then
   # the third launch: the first call meets crop sizes for the first time (a pass for the known sizes, a pass for the misses)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize_mma -s 2 -c 1 -f -o gpurun_out/prof_resize_mma__stacks_256_1920x1080 \
       python bench.py --workload hash --steps 1 --warmup 1 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_resize.log 2>&1; echo "ncu resize rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_side -c 1 -f -o gpurun_out/prof_letterbox__stacks_256_1920x1080 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_panels -c 1 -f -o gpurun_out/prof_letterbox__stacks_256_1920x1080 \
       python bench.py --workload hash --steps 1 --warmup 0 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
 fi
 if [[ $STEP == all || $STEP == sanitizer ]]; then

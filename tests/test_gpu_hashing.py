@@ -95,6 +95,43 @@ def _check_bit_exact(ctx, w, h):
     assert bits[100:].sum() == 0  # static stack
 
 
+def test_letterbox_noisy_and_wide_bars(ctx):
+    """the scan's shortcuts against the oracle: bars whose strips span more than the tolerance but are letterbox by the 90 %
+    rule (the one-strip probe must fall through to the full histograms), bars wider than the 8 speculative panels (the serial
+    tail), bars that differ between frame 0 and frame 8, a picture that starts mid-panel, sizes that are not multiples of 32"""
+    rng = np.random.default_rng(5)
+    cases = []
+    for (w, h) in [(640, 360), (1000, 562), (1920, 1080)]:
+        base = synth.frame_stacks(6, w, h, seed=w + h, bars=False).numpy()
+        a = base[0]  # noisy letterbox: 6 % of the bar pixels are outliers (range 200, still > 90 % within 16 of the mode)
+        t, b = h // 7 + 3, h // 9 + 1
+        bar = np.where(rng.random((16, t, w)) < 0.06, 216, 16 + rng.integers(-3, 4, (16, t, w))).astype(np.uint8)
+        a[:, :t, :] = bar
+        a[:, h - b:, :] = np.where(rng.random((16, b, w)) < 0.06, 216, 18).astype(np.uint8)
+        c = base[1]  # noisy pillarbox
+        l, r = w // 8 + 5, w // 11
+        c[:, :, :l] = np.where(rng.random((16, h, l)) < 0.05, 180, 12 + rng.integers(-2, 3, (16, h, l))).astype(np.uint8)
+        c[:, :, w - r:] = np.where(rng.random((16, h, r)) < 0.05, 0, 235).astype(np.uint8)
+        d = base[2]  # bars beyond 8 panels of 32 on every side that can hold them
+        d[:, : min(300, h // 3), :] = 16
+        d[:, :, : min(290, w // 3)] = 16
+        d[:, :, w - min(270, w // 4):] = 20
+        e = base[3]  # frame 8 has a narrower bar than frame 0: the per-side minimum
+        e[:, :70, :] = 0
+        e[8, 40:70, :] = base[4][8, 40:70, :]
+        f = base[5]  # clean bar, one bright logo pixel row inside it
+        f[:, :50, :] = 16
+        f[:, 20, : w // 30] = 250
+        cases += [a, c, d, e, f]
+    for k, st in enumerate(cases):
+        want = o.hash_stack(st, 1)
+        got_h, got_s, got_c = gpu_hash(ctx, st[None], 1)
+        assert got_s[0] == want[0] == 0 and tuple(int(v) for v in got_c[0]) == tuple(want[2]), (k, got_c[0], want[2])
+        assert np.array_equal(got_h[0], want[1]), k
+    crops = [tuple(o.hash_stack(st, 1)[2]) for st in cases[:5]]
+    assert crops[0][2] >= 360 // 7 and crops[1][0] >= 640 // 8 and crops[2][0] > 200 and crops[3][2] == 40, crops
+
+
 def test_chunked_overlapped_pipeline_matches_serial(ctx):
     """round 2 pipeline: resize jobs built on the device from the crops (sizes met for the first time take a second pass),
     the letterbox scan of chunk k+1 on a second stream beside the resize of chunk k, DCT + pack fused into the resize kernel.

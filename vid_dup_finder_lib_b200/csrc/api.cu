@@ -66,7 +66,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
                       &ctx->g_cnt,     &ctx->g_gstart,  &ctx->sk_a,     &ctx->sk_b,    &ctx->sk_c,    &ctx->sk_d,
                       &ctx->sk_order,  &ctx->sk_rank,   &ctx->ref_rows.tiles, &ctx->ref_rows.pc, &ctx->ref_rows.pcmin,
                       &ctx->h_frames[0], &ctx->h_frames[1], &ctx->h_jobs, &ctx->h_sides, &ctx->h_crop, &ctx->h_small,
-                      &ctx->h_hash,    &ctx->h_desc,    &ctx->h_done};
+                      &ctx->h_hash,    &ctx->h_desc,    &ctx->h_done,   &ctx->h_lbwork};
     ctx->tmp_self.release();
     ctx->tmp_cand.release();
     ctx->ref_plan.release();

@@ -247,7 +247,7 @@ struct vdf_ctx {
     bool ham_attrs = false, tc_attrs = false;
     size_t hash_smem_set[3] = {0, 0, 0};
     // hashing scratch
-    vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc, h_coef_lut, h_bfrag_lut, h_done;
+    vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc, h_coef_lut, h_bfrag_lut, h_done, h_lbwork;
     vdf::DevBuf m_state, m_lut, m_sides, m_acc, m_a, m_b, m_c, m_f32, m_label;  // motion.cu scratch
     vdf::PinnedBuf pin_a, pin_b, pin_c, pin_frames[2], h_groups;  // h_groups: staging of the group CSR on its way to the caller
     vdf::PinnedBuf h_misc;  // landing zone of the few counters the host reads back per call
@@ -312,7 +312,8 @@ int search_refs_device(vdf_ctx* ctx, const uint64_t* d_cand, const uint32_t* d_c
                        uint64_t cand_base, const uint64_t* d_refs, const uint32_t* d_ref_dur, uint64_t n_ref,
                        uint32_t tol, uint64_t* d_keys_out, uint64_t capacity, uint64_t* n_out);
 int self_window_pairs(vdf_ctx* ctx, const uint32_t* d_dur, uint64_t n, uint64_t* pairs_out);
-int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n);
+int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n, int end_bit = 64);
+int bits_for(uint64_t n);
 // search_tc.cu
 int tc5_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, Packed& out);
 int tc6_pack(vdf_ctx* ctx, const uint64_t* d_hash, const uint32_t* perm, uint64_t n, bool as_columns, Packed& out, uint32_t* d_pads_or);

@@ -308,7 +308,7 @@ int group_greedy_device(vdf_ctx* ctx, uint64_t n, const uint64_t* d_keys, uint64
 
     swap_halves_kernel<<<blocks(ne), B, 0, st>>>(d_keys, ne, ctx->g_rk.as<uint64_t>());
     VDF_LAUNCHED(ctx);
-    VDF_TRY(sort_keys(ctx, ctx->g_rk.as<uint64_t>(), ctx->g_rks.as<uint64_t>(), ne));
+    VDF_TRY(sort_keys(ctx, ctx->g_rk.as<uint64_t>(), ctx->g_rks.as<uint64_t>(), ne, 32 + bits_for(n)));  // (j << 32 | i), both < n
     const uint64_t* rks = ctx->g_rks.as<uint64_t>();
     uint8_t* state = ctx->g_state.as<uint8_t>();
     VDF_CUDA(ctx, cudaMemsetAsync(state, kTarget, n, st));

@@ -1,7 +1,7 @@
 // hash.cu -- frame stack -> VideoHash on the GPU.
 //
 // Replaces the compute tail of gen_hash (video_hash_builder.rs:214-223):
-//   H2  letterbox_side_kernel + crop_combine_kernel   <- cropdetect_letterbox / letterbox_crop / Crop::union
+//   H2  letterbox_{strip0,panels,tail}_kernel + crop_combine_kernel   <- cropdetect_letterbox / letterbox_crop / Crop::union
 //                                                        (vid_dup_finder_common/src/video_frames_gray.rs:38-128,201-210,
 //                                                         crop.rs:53-68)
 //   H3  resize kernels                                <- crop_resize_buf (resize_gray.rs:11-54): fast_image_resize
@@ -56,324 +56,451 @@ __device__ __forceinline__ bool strip_is_letterbox(const uint32_t* hist, uint32_
     return 10ull * cnt > 9ull * len;
 }
 
-// grid = n_stacks * 2 frames (0 and 8: step_by(8).take(8) over 16 frames) * 4 sides; 256 threads.
-// Each CTA walks 1-px strips from its edge inwards in panels of 32, stopping at the first non-letterbox strip.
+// The scan of one side of one frame is a walk from the edge inwards, strip by strip, to the first strip that is not letterbox
+// (video_frames_gray.rs:38-128).  Its RESULT is "the index of the first such strip" = a minimum over strips, so the walk
+// does not have to be serial:
+//   letterbox_strip0_kernel   one CTA per (stack, frame, side): strip 0 alone.  Most sides have no bar: done, count 0.
+//                             The others go onto a work list.
+//   letterbox_panels_kernel   persistent CTAs over (listed side, panel p < kLbSpec) items, panel-major: the first kLbSpec panels
+//                             of 32 strips of every listed side at once, atomicMin of the first non-letterbox strip found.
+//                             Items whose side is already settled below their panel are skipped.
+//   letterbox_tail_kernel     the listed sides still unsettled after kLbSpec * 32 strips (bars wider than 256 px) walk on
+//                             serially; all counts are clamped to the side's length.
+// Round 2's first version walked panel after panel inside one CTA per side (up to 8 dependent round trips to memory for a
+// pillarboxed 1080p frame, 3.5 waves of CTAs): 105-120 us per 256 stacks for 0.6 % of the bytes.
 //
 // A strip whose values span <= tol is letterbox whatever its mode is (every pixel is within tol of every other one:
 // count == len and 10 len > 9 len) -- exact, and it is what real bars look like.  So every panel is first looked at through
 // its per-strip minimum and maximum (registers, byte-wise SIMD min/max, no shared-memory traffic); histograms are built
-// only for the strips that are not decided that way -- in practice the one panel where the picture starts.  Round 1 built
-// them for every strip of every panel, 8 rows at a time: a barred side was a serial walk of up to 17 panels of zeroing,
-// shared atomics and three block barriers each, and that walk, not the bytes, was the kernel's 190 us.
+// only for the strips that are not decided that way -- in practice the one panel where the picture starts.
 // kLut (Cropdetect::Motion, motion.cu): every pixel goes through a per-stack 256-entry table first (the contrast stretch of
 // autocrop_frames.rs:107-113, monotone, so minima and maxima map through it) and all 16 frames are scanned (n_fr = 16, step 1)
-// instead of frames 0 and 8 (n_fr = 2, step 8).
-template <bool kLut>
-__global__ void __launch_bounds__(256, 4) letterbox_side_kernel(const uint8_t* __restrict__ frames,
-                                                             const StackDev* __restrict__ stacks,
-                                                             uint32_t* __restrict__ sides /* [n][n_fr][4] l,r,t,b */, uint32_t n_fr,
-                                                             uint32_t fr_step, const uint8_t* __restrict__ luts /* [n][256] */) {
-    __shared__ uint32_t hist[kColPanel * 257];  // column panels: one histogram per strip; row panels: 4 sub-histograms per warp
-    __shared__ uint32_t flags[kColPanel];
-    __shared__ uint32_t s_min[kColPanel], s_max[kColPanel];
-    __shared__ uint32_t s_count, s_stop, s_need_hist;
-    __shared__ uint8_t s_lut[kLut ? 256 : 4];
-    const uint32_t b = blockIdx.x, side = b & 3, fr = (b >> 2) % n_fr, s = (b >> 2) / n_fr;
-    const StackDev sd = stacks[s];
-    if (sd.status != VDF_STACK_OK) return;
-    if (kLut) {
-        s_lut[threadIdx.x] = luts[(size_t)s * 256 + threadIdx.x];  // 256 threads
-        __syncthreads();
+// instead of frames 0 and 8 (n_fr = 2, step 8: step_by(8).take(8) over 16 frames).
+constexpr uint32_t kLbSpec = 8;            // panels examined speculatively, side by side
+constexpr uint32_t kLbNone = 0xFFFFFFFFu;  // no non-letterbox strip found yet
+
+// Byte-wise minimum / maximum through the 16-bit SIMD min / max of sm_90+ (VIMNMX[3].U16x2): a word's even and odd bytes
+// as two u16x2 values.  The byte-wise __vminu4 / __vmaxu4 are emulated on this architecture (six logic instructions each)
+// and made the scan issue-bound: 9 M of its 25 M warp instructions were their LOP3s.
+__device__ __forceinline__ uint32_t lb_even(uint32_t v) { return __byte_perm(v, 0u, 0x4240); }  // bytes 0, 2
+__device__ __forceinline__ uint32_t lb_odd(uint32_t v) { return __byte_perm(v, 0u, 0x4341); }   // bytes 1, 3
+struct LbRange4 {  // per byte lane of a word column: [even | odd] x [min | max]
+    uint32_t mn_e = 0x00FF00FFu, mn_o = 0x00FF00FFu, mx_e = 0u, mx_o = 0u;
+    __device__ __forceinline__ void add2(uint32_t a, uint32_t b) {
+        const uint32_t ae = lb_even(a), ao = lb_odd(a), be = lb_even(b), bo = lb_odd(b);
+        mn_e = __vimin3_u16x2(mn_e, ae, be), mn_o = __vimin3_u16x2(mn_o, ao, bo);
+        mx_e = __vimax3_u16x2(mx_e, ae, be), mx_o = __vimax3_u16x2(mx_o, ao, bo);
     }
-    auto M = [&](uint32_t v) -> uint32_t { return kLut ? (uint32_t)s_lut[v] : v; };
-    const uint8_t* img = frames + sd.offset + (uint64_t)(fr * fr_step) * sd.frame_stride;
-    const uint32_t W = sd.width, H = sd.height, P = sd.pitch;
+    __device__ __forceinline__ void merge(uint32_t xor_lane) {
+        mn_e = __vminu2(mn_e, __shfl_xor_sync(0xffffffffu, mn_e, xor_lane)), mn_o = __vminu2(mn_o, __shfl_xor_sync(0xffffffffu, mn_o, xor_lane));
+        mx_e = __vmaxu2(mx_e, __shfl_xor_sync(0xffffffffu, mx_e, xor_lane)), mx_o = __vmaxu2(mx_o, __shfl_xor_sync(0xffffffffu, mx_o, xor_lane));
+    }
+    __device__ __forceinline__ uint32_t mn(int q) const { return ((q & 1 ? mn_o : mn_e) >> (q & 2 ? 16 : 0)) & 0xFFFFu; }  // byte q of the word
+    __device__ __forceinline__ uint32_t mx(int q) const { return ((q & 1 ? mx_o : mx_e) >> (q & 2 ? 16 : 0)) & 0xFFFFu; }
+};
+struct LbRange1 {  // over all bytes seen
+    uint32_t mn2 = 0x00FF00FFu, mx2 = 0u;
+    __device__ __forceinline__ void add(uint32_t v) {
+        const uint32_t e = lb_even(v), o = lb_odd(v);
+        mn2 = __vimin3_u16x2(mn2, e, o), mx2 = __vimax3_u16x2(mx2, e, o);
+    }
+    __device__ __forceinline__ uint32_t mn() const { return min(mn2 & 0xFFFFu, mn2 >> 16); }
+    __device__ __forceinline__ uint32_t mx() const { return max(mx2 & 0xFFFFu, mx2 >> 16); }
+};
+
+struct LbShared {
+    uint32_t hist[kColPanel * 257];  // column panels: one histogram per strip; row panels: 4 sub-histograms per warp
+    uint32_t flags[kColPanel];       // out: strip k of the panel is letterbox
+    uint32_t mn[kColPanel], mx[kColPanel];
+    uint32_t need_hist, skip;
+    uint8_t lut[256];
+};
+
+// flags[k] <- strip base + k of `side` is letterbox, for the 32 strips of one panel (256 threads, all of them; synchronised on return)
+template <bool kLut>
+__device__ __forceinline__ void lb_panel_flags(LbShared& sh, const uint8_t* __restrict__ img, uint32_t W, uint32_t H, uint32_t P, uint32_t side,
+                                               uint32_t base) {
+    auto M = [&](uint32_t v) -> uint32_t { return kLut ? (uint32_t)sh.lut[v] : v; };
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_count = 0, s_stop = 0;
     const bool cols = side < 2;  // 0 left, 1 right, 2 top, 3 bottom
     const uint32_t limit = cols ? W : H, len = cols ? H : W;
-    const uint32_t panel = cols ? kColPanel : kRowPanel;
-    {   // Strip 0 alone first: most frames have no bar on most sides, and one strip (one histogram, every thread a few
-        // pixels) settles that in a few microseconds; only a side whose outermost strip IS letterbox walks panels.
-        for (int q = tid; q < 256; q += 256) hist[q] = 0;
-        __syncthreads();
-        if (cols) {
-            const uint8_t* col = img + (side == 0 ? 0u : W - 1);
-            for (uint32_t y = tid; y < H; y += 256) atomicAdd(&hist[M(__ldg(col + (uint64_t)y * P))], 1u);
-        } else {
-            const uint8_t* row = img + (uint64_t)(side == 2 ? 0u : H - 1) * P;
-            for (uint32_t x = tid; x < W; x += 256) atomicAdd(&hist[M(__ldg(row + x))], 1u);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const bool ok = strip_is_letterbox(hist, len, lane);
-            if (lane == 0) s_stop = ok ? 0u : 1u;
-        }
-        __syncthreads();
-        if (s_stop) {
-            if (tid == 0) sides[((size_t)s * n_fr + fr) * 4 + side] = 0;
-            return;
-        }
-    }
-    for (uint32_t base = 0; base < limit; base += panel) {
-        if (cols) {
-            const uint32_t px0 = side == 0 ? base : W - 32 - base;  // first pixel column of a full 32-column panel
-            // full, 4-byte aligned panel: 8 word loads cover a row of the panel, 32 rows per pass, 16 passes in flight
-            const bool fast = base + kColPanel <= W && ((reinterpret_cast<uintptr_t>(img) | P | px0) & 3) == 0;
-            const uint32_t wq = tid & 7, r0 = tid >> 3;
-            const uint32_t* col4 = reinterpret_cast<const uint32_t*>(img + px0) + wq;
-            const uint32_t P4 = P >> 2;
-            bool need_hist = true;
-            if (fast) {  // pass A: value range of every column of the panel
-                if (tid < kColPanel) s_min[tid] = 255u, s_max[tid] = 0u;
-                if (tid == 0) s_need_hist = 0;
-                __syncthreads();
-                uint32_t mn4 = 0xFFFFFFFFu, mx4 = 0u;
-                if (H <= 32 * 40) {  // up to 1280 rows (1080p): every load of the panel in flight at once, one round trip to memory
-                    uint32_t v[40];
+    if (cols) {
+        const uint32_t px0 = side == 0 ? base : W - 32 - base;  // first pixel column of a full 32-column panel
+        // full, 4-byte aligned panel: 8 word loads cover a row of the panel, 32 rows per pass, 16 passes in flight
+        const bool fast = base + kColPanel <= W && ((reinterpret_cast<uintptr_t>(img) | P | px0) & 3) == 0;
+        const uint32_t wq = tid & 7, r0 = tid >> 3;
+        const uint32_t* col4 = reinterpret_cast<const uint32_t*>(img + px0) + wq;
+        const uint32_t P4 = P >> 2;
+        bool need_hist = true;
+        if (fast) {  // pass A: value range of every column of the panel
+            if (tid < kColPanel) sh.mn[tid] = 255u, sh.mx[tid] = 0u;
+            if (tid == 0) sh.need_hist = 0;
+            __syncthreads();
+            // rows beyond the last one re-read the last one: harmless for a minimum / maximum, and every update is a full pair
+            LbRange4 rg;
+            if (H <= 32 * 40) {  // up to 1280 rows (1080p): every load of the panel in flight at once, one round trip to memory
+                uint32_t v[40];
 #pragma unroll
-                    for (int u = 0; u < 40; ++u) {
-                        const uint32_t y = r0 + 32 * u;
-                        v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
-                    }
+                for (int u = 0; u < 40; ++u) v[u] = __ldg(col4 + (uint64_t)min(r0 + 32 * u, H - 1) * P4);
 #pragma unroll
-                    for (int u = 0; u < 40; ++u)
-                        if (r0 + 32 * u < H) mn4 = __vminu4(mn4, v[u]), mx4 = __vmaxu4(mx4, v[u]);
-                } else {
-                    for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
-                        uint32_t v[16];
+                for (int u = 0; u < 40; u += 2) rg.add2(v[u], v[u + 1]);
+            } else {
+                for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
+                    uint32_t v[16];
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            const uint32_t y = y0 + 32 * u;
-                            v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
-                        }
+                    for (int u = 0; u < 16; ++u) v[u] = __ldg(col4 + (uint64_t)min(y0 + 32 * u, H - 1) * P4);
 #pragma unroll
-                        for (int u = 0; u < 16; ++u)
-                            if (y0 + 32 * u < H) mn4 = __vminu4(mn4, v[u]), mx4 = __vmaxu4(mx4, v[u]);
-                    }
-                }
-                // the four row-threads of a warp that share a word column: lanes l, l^8, l^16, l^24
-                mn4 = __vminu4(mn4, __shfl_xor_sync(0xffffffffu, mn4, 8)), mx4 = __vmaxu4(mx4, __shfl_xor_sync(0xffffffffu, mx4, 8));
-                mn4 = __vminu4(mn4, __shfl_xor_sync(0xffffffffu, mn4, 16)), mx4 = __vmaxu4(mx4, __shfl_xor_sync(0xffffffffu, mx4, 16));
-                if (lane < 8) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t c = 4 * wq + q, k = side == 0 ? c : 31 - c;  // strip index inside the panel
-                        atomicMin(&s_min[k], (mn4 >> (8 * q)) & 255u);
-                        atomicMax(&s_max[k], (mx4 >> (8 * q)) & 255u);
-                    }
-                }
-                __syncthreads();
-                if (tid < kColPanel) {
-                    const bool nar = M(s_max[tid]) - M(s_min[tid]) <= (uint32_t)kLbTol;  // H >= 1: max >= min
-                    flags[tid] = nar;
-                    if (!nar) s_need_hist = 1;
-                }
-                __syncthreads();
-                need_hist = s_need_hist != 0;
-            }
-            if (need_hist) {  // pass B: histograms (the data of pass A comes from L1 / L2 this time)
-                for (uint32_t q = tid; q < kColPanel * 257; q += 256) hist[q] = 0;
-                __syncthreads();
-                if (fast) {
-                    for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
-                        uint32_t v[16];
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            const uint32_t y = y0 + 32 * u;
-                            v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            if (y0 + 32 * u < H) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const uint32_t c = 4 * wq + q, k = side == 0 ? c : 31 - c;
-                                    if (!flags[k]) atomicAdd(&hist[k * 257 + M((v[u] >> (8 * q)) & 255u)], 1u);
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    const uint32_t idx = base + lane;
-                    const bool act = idx < W;
-                    const uint32_t x = side == 0 ? idx : W - 1 - idx;
-                    // 16 independent loads in flight per lane before the (shared-memory) histogram updates
-                    for (uint32_t y0 = warp; y0 < H; y0 += 8 * 16) {
-                        uint32_t v[16];
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            const uint32_t y = y0 + 8 * u;
-                            v[u] = (act && y < H) ? (uint32_t)__ldg(img + (uint64_t)y * P + x) : 0xFFFFu;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 16; ++u)
-                            if (v[u] != 0xFFFFu) atomicAdd(&hist[lane * 257 + M(v[u])], 1u);
-                    }
-                }
-                __syncthreads();
-                for (uint32_t k = warp; k < kColPanel; k += 8) {
-                    if (fast && flags[k]) continue;  // decided by its value range
-                    bool ok = false;
-                    if (base + k < limit) ok = strip_is_letterbox(hist + k * 257, len, lane);
-                    if (lane == 0) flags[k] = ok;
-                }
-                __syncthreads();
-            }
-        } else {
-            // rows: warp w decides rows base + w + 8 i (i = 0..3) on its own, in its own four sub-histograms (lane & 3) that
-            // keep same-value lanes from piling onto one counter
-            uint32_t* h4 = hist + (warp * 4) * 257;
-            uint32_t* hs = h4 + (lane & 3) * 257;
-            const uint32_t W4 = W >> 2;
-            // first the value range of all four rows of this warp, their loads in flight together (rows of <= 2048 px, aligned):
-            // a panel inside a bar costs one round trip to memory
-            uint32_t decided = 0;  // bit i: row i is narrow
-            if (((reinterpret_cast<uintptr_t>(img) | P) & 3) == 0 && W4 <= 32 * 16) {
-                uint32_t mn[4], mx[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t idx = base + warp + 8 * i;
-                    mn[i] = 0xFFFFFFFFu, mx[i] = 0u;
-                    if (idx < H) {
-                        const uint32_t y = side == 2 ? idx : H - 1 - idx;
-                        const uint8_t* row = img + (uint64_t)y * P;
-                        const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            const uint32_t q = u * 32 + lane;
-                            if (q < W4) {
-                                const uint32_t v = __ldg(row4 + q);
-                                mn[i] = __vminu4(mn[i], v), mx[i] = __vmaxu4(mx[i], v);
-                            }
-                        }
-                        const uint32_t xt = (W4 << 2) + lane;
-                        if (xt < W) {
-                            const uint32_t t = (uint32_t)__ldg(row + xt) * 0x01010101u;
-                            mn[i] = __vminu4(mn[i], t), mx[i] = __vmaxu4(mx[i], t);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t a = min(min(mn[i] & 255u, (mn[i] >> 8) & 255u), min((mn[i] >> 16) & 255u, mn[i] >> 24));
-                    uint32_t b = max(max(mx[i] & 255u, (mx[i] >> 8) & 255u), max((mx[i] >> 16) & 255u, mx[i] >> 24));
-                    a = __reduce_min_sync(0xffffffffu, a), b = __reduce_max_sync(0xffffffffu, b);
-                    if (base + warp + 8 * i < H && M(b) - M(a) <= (uint32_t)kLbTol) decided |= 1u << i;
+                    for (int u = 0; u < 16; u += 2) rg.add2(v[u], v[u + 1]);
                 }
             }
-            for (uint32_t i = 0; i < kRowPanel / 8; ++i) {
-                const uint32_t k = warp + 8 * i, idx = base + k;
-                if (idx >= H) {
-                    if (lane == 0) flags[k] = 0;
-                    continue;
+            // the four row-threads of a warp that share a word column: lanes l, l^8, l^16, l^24
+            rg.merge(8), rg.merge(16);
+            if (lane < 8) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t c = 4 * wq + q, k = side == 0 ? c : 31 - c;  // strip index inside the panel
+                    atomicMin(&sh.mn[k], rg.mn(q));
+                    atomicMax(&sh.mx[k], rg.mx(q));
                 }
-                if (decided & (1u << i)) {
-                    if (lane == 0) flags[k] = 1;
-                    continue;
+            }
+            __syncthreads();
+            if (tid < kColPanel) {
+                const bool nar = M(sh.mx[tid]) - M(sh.mn[tid]) <= (uint32_t)kLbTol;  // H >= 1: max >= min
+                sh.flags[tid] = nar;
+                if (!nar) sh.need_hist = 1;
+            }
+            __syncthreads();
+            need_hist = sh.need_hist != 0;
+            if (need_hist) {
+                // Only the FIRST strip that is not letterbox matters, and a strip with a wide value range almost always is
+                // picture: its histogram alone (256 threads on one column, data in L1 / L2 by now) settles the panel.  Only if
+                // that strip turns out to be letterbox after all (a noisy bar) do all the undecided strips get histograms.
+                const uint32_t wide = __ballot_sync(0xffffffffu, !sh.flags[lane]);  // pass A left a wide strip: wide != 0
+                const uint32_t k0 = __ffs(wide) - 1;
+                sh.hist[tid] = 0;
+                __syncthreads();
+                const uint8_t* col = img + (side == 0 ? base + k0 : W - 1 - (base + k0));
+                for (uint32_t y0 = tid; y0 < H; y0 += 256 * 8) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = y0 + 256 * u < H ? (uint32_t)__ldg(col + (uint64_t)(y0 + 256 * u) * P) : 0x100u;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (v[u] < 0x100u) atomicAdd(&sh.hist[M(v[u])], 1u);
                 }
-                const uint32_t y = side == 2 ? idx : H - 1 - idx;
-                const uint8_t* row = img + (uint64_t)y * P;
-                bool ok;
-                if ((reinterpret_cast<uintptr_t>(row) & 3) == 0 && W4 <= 32 * 16) {
-                    // the whole row is in registers (<= 2048 px): its value range first, the histogram only if that fails
-                    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+                __syncthreads();
+                if (warp == 0) {
+                    const bool ok = strip_is_letterbox(sh.hist, len, lane);
+                    if (lane == 0) sh.need_hist = ok ? 1u : 0u;  // flags[k0] stays 0 unless the full pass below says otherwise
+                }
+                __syncthreads();
+                need_hist = sh.need_hist != 0;
+            }
+        }
+        if (need_hist) {  // pass B: histograms of every undecided strip (the data of pass A comes from L1 / L2 this time)
+            for (uint32_t q = tid; q < kColPanel * 257; q += 256) sh.hist[q] = 0;
+            __syncthreads();
+            if (fast) {
+                for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
                     uint32_t v[16];
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        const uint32_t q = u * 32 + lane;
-                        v[u] = q < W4 ? __ldg(row4 + q) : 0u;
+                        const uint32_t y = y0 + 32 * u;
+                        v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
                     }
-                    const uint32_t xt = (W4 << 2) + lane;  // the <= 3 pixels after the last whole word
-                    const uint32_t tail = xt < W ? (uint32_t)__ldg(row + xt) : 0x100u;
-                    uint32_t mn4 = 0xFFFFFFFFu, mx4 = 0u;
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        if (y0 + 32 * u < H) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t c = 4 * wq + q, k = side == 0 ? c : 31 - c;
+                                if (!sh.flags[k]) atomicAdd(&sh.hist[k * 257 + M((v[u] >> (8 * q)) & 255u)], 1u);
+                            }
+                        }
+                    }
+                }
+            } else {
+                const uint32_t idx = base + lane;
+                const bool act = idx < W;
+                const uint32_t x = side == 0 ? idx : W - 1 - idx;
+                // 16 independent loads in flight per lane before the (shared-memory) histogram updates
+                for (uint32_t y0 = warp; y0 < H; y0 += 8 * 16) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t y = y0 + 8 * u;
+                        v[u] = (act && y < H) ? (uint32_t)__ldg(img + (uint64_t)y * P + x) : 0xFFFFu;
+                    }
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
-                        if (u * 32 + lane < W4) mn4 = __vminu4(mn4, v[u]), mx4 = __vmaxu4(mx4, v[u]);
-                    uint32_t mn = min(min(mn4 & 255u, (mn4 >> 8) & 255u), min((mn4 >> 16) & 255u, mn4 >> 24));
-                    uint32_t mx = max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
-                    if (tail < 0x100u) mn = min(mn, tail), mx = max(mx, tail);
-                    mn = __reduce_min_sync(0xffffffffu, mn), mx = __reduce_max_sync(0xffffffffu, mx);
-                    ok = M(mx) - M(mn) <= (uint32_t)kLbTol;
-                    if (!ok) {
-                        for (int q = lane; q < 4 * 257; q += 32) h4[q] = 0;
-                        __syncwarp();
+                        if (v[u] != 0xFFFFu) atomicAdd(&sh.hist[lane * 257 + M(v[u])], 1u);
+                }
+            }
+            __syncthreads();
+            for (uint32_t k = warp; k < kColPanel; k += 8) {
+                if (fast && sh.flags[k]) continue;  // decided by its value range
+                bool ok = false;
+                if (base + k < limit) ok = strip_is_letterbox(sh.hist + k * 257, len, lane);
+                if (lane == 0) sh.flags[k] = ok;
+            }
+            __syncthreads();
+        }
+    } else {
+        // rows: warp w decides rows base + w + 8 i (i = 0..3) on its own, in its own four sub-histograms (lane & 3) that
+        // keep same-value lanes from piling onto one counter
+        uint32_t* h4 = sh.hist + (warp * 4) * 257;
+        uint32_t* hs = h4 + (lane & 3) * 257;
+        const uint32_t W4 = W >> 2;
+        // first the value range of all four rows of this warp, their loads in flight together (rows of <= 2048 px, aligned):
+        // a panel inside a bar costs one round trip to memory
+        uint32_t decided = 0;  // bit i: row i is narrow
+        if (((reinterpret_cast<uintptr_t>(img) | P) & 3) == 0 && W4 <= 32 * 16) {
+            LbRange1 rg[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t idx = base + warp + 8 * i;
+                if (idx < H) {
+                    const uint32_t y = side == 2 ? idx : H - 1 - idx;
+                    const uint8_t* row = img + (uint64_t)y * P;
+                    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t q = u * 32 + lane;
+                        if (q < W4) rg[i].add(__ldg(row4 + q));
+                    }
+                    const uint32_t xt = (W4 << 2) + lane;
+                    if (xt < W) rg[i].add((uint32_t)__ldg(row + xt) * 0x01010101u);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t a = __reduce_min_sync(0xffffffffu, rg[i].mn()), b = __reduce_max_sync(0xffffffffu, rg[i].mx());
+                if (base + warp + 8 * i < H && M(b) - M(a) <= (uint32_t)kLbTol) decided |= 1u << i;
+            }
+        }
+        // one row (warp-wide): its value range first when it fits the registers, the histogram only if that fails
+        auto row_is_letterbox = [&](uint32_t idx) -> bool {
+            const uint32_t y = side == 2 ? idx : H - 1 - idx;
+            const uint8_t* row = img + (uint64_t)y * P;
+            bool ok;
+            if ((reinterpret_cast<uintptr_t>(row) & 3) == 0 && W4 <= 32 * 16) {
+                // the whole row is in registers (<= 2048 px): its value range first, the histogram only if that fails
+                const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+                uint32_t v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const uint32_t q = u * 32 + lane;
+                    v[u] = q < W4 ? __ldg(row4 + q) : 0u;
+                }
+                const uint32_t xt = (W4 << 2) + lane;  // the <= 3 pixels after the last whole word
+                const uint32_t tail = xt < W ? (uint32_t)__ldg(row + xt) : 0x100u;
+                LbRange1 rg;
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    if (u * 32 + lane < W4) rg.add(v[u]);
+                uint32_t mn = rg.mn(), mx = rg.mx();
+                if (tail < 0x100u) mn = min(mn, tail), mx = max(mx, tail);
+                mn = __reduce_min_sync(0xffffffffu, mn), mx = __reduce_max_sync(0xffffffffu, mx);
+                ok = M(mx) - M(mn) <= (uint32_t)kLbTol;
+                if (!ok) {
+                    for (int q = lane; q < 4 * 257; q += 32) h4[q] = 0;
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        if (u * 32 + lane < W4) {
+                            atomicAdd(&hs[M(v[u] & 255u)], 1u);
+                            atomicAdd(&hs[M((v[u] >> 8) & 255u)], 1u);
+                            atomicAdd(&hs[M((v[u] >> 16) & 255u)], 1u);
+                            atomicAdd(&hs[M(v[u] >> 24)], 1u);
+                        }
+                    }
+                    if (tail < 0x100u) atomicAdd(&hs[M(tail)], 1u);
+                    __syncwarp();
+                    for (int q = lane; q < 256; q += 32) h4[q] += h4[257 + q] + h4[514 + q] + h4[771 + q];
+                    __syncwarp();
+                    ok = strip_is_letterbox(h4, len, lane);
+                }
+            } else {  // long or unaligned rows: histogram straight away
+                for (int q = lane; q < 4 * 257; q += 32) h4[q] = 0;
+                __syncwarp();
+                uint32_t x_done = 0;
+                if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // up to 16 x 4 pixels per lane in flight
+                    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+                    for (uint32_t q0 = 0; q0 < W4; q0 += 32 * 16) {
+                        uint32_t v[16];
 #pragma unroll
                         for (int u = 0; u < 16; ++u) {
-                            if (u * 32 + lane < W4) {
+                            const uint32_t q = q0 + u * 32 + lane;
+                            v[u] = q < W4 ? __ldg(row4 + q) : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            if (q0 + u * 32 + lane < W4) {
                                 atomicAdd(&hs[M(v[u] & 255u)], 1u);
                                 atomicAdd(&hs[M((v[u] >> 8) & 255u)], 1u);
                                 atomicAdd(&hs[M((v[u] >> 16) & 255u)], 1u);
                                 atomicAdd(&hs[M(v[u] >> 24)], 1u);
                             }
                         }
-                        if (tail < 0x100u) atomicAdd(&hs[M(tail)], 1u);
-                        __syncwarp();
-                        for (int q = lane; q < 256; q += 32) h4[q] += h4[257 + q] + h4[514 + q] + h4[771 + q];
-                        __syncwarp();
-                        ok = strip_is_letterbox(h4, len, lane);
                     }
-                } else {  // long or unaligned rows: histogram straight away
-                    for (int q = lane; q < 4 * 257; q += 32) h4[q] = 0;
-                    __syncwarp();
-                    uint32_t x_done = 0;
-                    if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // up to 16 x 4 pixels per lane in flight
-                        const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
-                        for (uint32_t q0 = 0; q0 < W4; q0 += 32 * 16) {
-                            uint32_t v[16];
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) {
-                                const uint32_t q = q0 + u * 32 + lane;
-                                v[u] = q < W4 ? __ldg(row4 + q) : 0u;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) {
-                                if (q0 + u * 32 + lane < W4) {
-                                    atomicAdd(&hs[M(v[u] & 255u)], 1u);
-                                    atomicAdd(&hs[M((v[u] >> 8) & 255u)], 1u);
-                                    atomicAdd(&hs[M((v[u] >> 16) & 255u)], 1u);
-                                    atomicAdd(&hs[M(v[u] >> 24)], 1u);
-                                }
-                            }
-                        }
-                        x_done = W4 << 2;
-                    }
-                    for (uint32_t x0 = x_done; x0 < W; x0 += 32 * 16) {
-                        uint32_t v[16];
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            const uint32_t x = x0 + u * 32 + lane;
-                            v[u] = x < W ? (uint32_t)__ldg(row + x) : 0x100u;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 16; ++u)
-                            if (v[u] < 0x100u) atomicAdd(&hs[M(v[u])], 1u);
-                    }
-                    __syncwarp();
-                    for (int q = lane; q < 256; q += 32) h4[q] += h4[257 + q] + h4[514 + q] + h4[771 + q];
-                    __syncwarp();
-                    ok = strip_is_letterbox(h4, len, lane);
+                    x_done = W4 << 2;
                 }
-                if (lane == 0) flags[k] = ok;
+                for (uint32_t x0 = x_done; x0 < W; x0 += 32 * 16) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t x = x0 + u * 32 + lane;
+                        v[u] = x < W ? (uint32_t)__ldg(row + x) : 0x100u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (v[u] < 0x100u) atomicAdd(&hs[M(v[u])], 1u);
+                }
                 __syncwarp();
+                for (int q = lane; q < 256; q += 32) h4[q] += h4[257 + q] + h4[514 + q] + h4[771 + q];
+                __syncwarp();
+                ok = strip_is_letterbox(h4, len, lane);
             }
-            __syncthreads();
-        }
-        if (tid == 0) {
-            uint32_t c = s_count;
-            for (uint32_t k = 0; k < panel && base + k < limit; ++k) {
-                if (!flags[k]) {
-                    s_stop = 1;
-                    break;
-                }
-                ++c;
-            }
-            s_count = c;
+            return ok;
+        };
+        // the rows the range test has settled; of the others only the FIRST can end the walk: it alone is evaluated (by the warp
+        // that owns it) and, being wide, it almost always is picture.  Only if it is letterbox after all do the rest follow.
+#pragma unroll
+        for (uint32_t i = 0; i < kRowPanel / 8; ++i)
+            if (lane == 0) sh.flags[warp + 8 * i] = (base + warp + 8 * i < H && (decided & (1u << i))) ? 1u : 0u;
+        if (tid == 0) sh.need_hist = 0;
+        __syncthreads();
+        const uint32_t open = __ballot_sync(0xffffffffu, !sh.flags[lane] && base + lane < H);
+        if (open == 0) return;  // every row of the panel that exists is narrow
+        const uint32_t k0 = __ffs(open) - 1;
+        if (warp == (int)(k0 & 7u)) {
+            const bool ok = row_is_letterbox(base + k0);
+            if (lane == 0) sh.flags[k0] = ok, sh.need_hist = ok ? 1u : 0u;
         }
         __syncthreads();
-        if (s_stop) break;
+        if (!sh.need_hist) return;
+        for (uint32_t i = 0; i < kRowPanel / 8; ++i) {
+            const uint32_t k = warp + 8 * i, idx = base + k;
+            if (k <= k0 || idx >= H || (decided & (1u << i))) continue;
+            const bool ok = row_is_letterbox(idx);
+            if (lane == 0) sh.flags[k] = ok;
+            __syncwarp();
+        }
+        __syncthreads();
     }
-    if (tid == 0) sides[((size_t)s * n_fr + fr) * 4 + side] = s_count;
+}
+
+// first non-letterbox strip among the panel's flags (thread 0 of a CTA whose lb_panel_flags has returned), or kLbNone
+__device__ __forceinline__ uint32_t lb_first_stop(const LbShared& sh, uint32_t base, uint32_t limit) {
+    for (uint32_t k = 0; k < kColPanel && base + k < limit; ++k)
+        if (!sh.flags[k]) return base + k;
+    return kLbNone;
+}
+
+// grid = n_stacks * n_fr * 4 sides; 128 threads.  sides[b] <- 0 (strip 0 is picture) or kLbNone + an entry in the work list.
+template <bool kLut>
+__global__ void __launch_bounds__(128) letterbox_strip0_kernel(const uint8_t* __restrict__ frames, const StackDev* __restrict__ stacks,
+                                                               uint32_t* __restrict__ sides /* [n][n_fr][4] l,r,t,b */, uint32_t n_fr, uint32_t fr_step,
+                                                               const uint8_t* __restrict__ luts /* [n][256] */, uint32_t* __restrict__ work,
+                                                               uint32_t* __restrict__ n_work) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint8_t s_lut[kLut ? 256 : 4];
+    const uint32_t b = blockIdx.x, side = b & 3, fr = (b >> 2) % n_fr, s = (b >> 2) / n_fr;
+    const StackDev sd = stacks[s];
+    if (sd.status != VDF_STACK_OK) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = tid; q < 256; q += 128) {
+        hist[q] = 0;
+        if (kLut) s_lut[q] = luts[(size_t)s * 256 + q];
+    }
+    __syncthreads();
+    auto M = [&](uint32_t v) -> uint32_t { return kLut ? (uint32_t)s_lut[v] : v; };
+    const uint8_t* img = frames + sd.offset + (uint64_t)(fr * fr_step) * sd.frame_stride;
+    const uint32_t W = sd.width, H = sd.height, P = sd.pitch;
+    const bool cols = side < 2;
+    if (cols) {
+        const uint8_t* col = img + (side == 0 ? 0u : W - 1);
+        for (uint32_t y0 = tid; y0 < H; y0 += 128 * 8) {  // eight loads in flight per thread
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = y0 + 128 * u < H ? (uint32_t)__ldg(col + (uint64_t)(y0 + 128 * u) * P) : 0x100u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (v[u] < 0x100u) atomicAdd(&hist[M(v[u])], 1u);
+        }
+    } else {
+        const uint8_t* row = img + (uint64_t)(side == 2 ? 0u : H - 1) * P;
+        for (uint32_t x = tid; x < W; x += 128) atomicAdd(&hist[M(__ldg(row + x))], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const bool ok = strip_is_letterbox(hist, cols ? H : W, lane);
+        if (lane == 0) {
+            sides[b] = ok ? kLbNone : 0u;
+            if (ok) work[atomicAdd(n_work, 1u)] = b;
+        }
+    }
+}
+
+// persistent: item = p * n_work + e for panel p < kLbSpec of listed side e; 256 threads
+template <bool kLut>
+__global__ void __launch_bounds__(256, 4) letterbox_panels_kernel(const uint8_t* __restrict__ frames, const StackDev* __restrict__ stacks,
+                                                                 uint32_t* __restrict__ sides, uint32_t n_fr, uint32_t fr_step,
+                                                                 const uint8_t* __restrict__ luts, const uint32_t* __restrict__ work,
+                                                                 const uint32_t* __restrict__ n_work) {
+    __shared__ LbShared sh;
+    const uint32_t nw = *n_work;
+    const int tid = threadIdx.x;
+    for (uint32_t item = blockIdx.x; item < nw * kLbSpec; item += gridDim.x) {
+        const uint32_t p = item / nw, b = work[item % nw];
+        const uint32_t side = b & 3, fr = (b >> 2) % n_fr, s = (b >> 2) / n_fr;
+        const StackDev sd = stacks[s];
+        const uint32_t limit = side < 2 ? sd.width : sd.height, base = p * kColPanel;
+        __syncthreads();  // the previous item's flags have been read
+        if (tid == 0) sh.skip = (base >= limit || __ldcg(&sides[b]) < base) ? 1u : 0u;  // settled nearer the edge: nothing to add
+        if (kLut) sh.lut[tid] = luts[(size_t)s * 256 + tid];
+        __syncthreads();
+        if (sh.skip) continue;
+        const uint8_t* img = frames + sd.offset + (uint64_t)(fr * fr_step) * sd.frame_stride;
+        lb_panel_flags<kLut>(sh, img, sd.width, sd.height, sd.pitch, side, base);
+        if (tid == 0) {
+            const uint32_t f = lb_first_stop(sh, base, limit);
+            if (f != kLbNone) atomicMin(&sides[b], f);
+        }
+    }
+}
+
+// persistent over the listed sides: the rare serial continuation beyond kLbSpec panels, and the clamp to the side's length
+// (a side that is letterbox all the way counts every strip, video_frames_gray.rs:103-117)
+template <bool kLut>
+__global__ void __launch_bounds__(256, 4) letterbox_tail_kernel(const uint8_t* __restrict__ frames, const StackDev* __restrict__ stacks,
+                                                               uint32_t* __restrict__ sides, uint32_t n_fr, uint32_t fr_step,
+                                                               const uint8_t* __restrict__ luts, const uint32_t* __restrict__ work,
+                                                               const uint32_t* __restrict__ n_work) {
+    __shared__ LbShared sh;
+    __shared__ uint32_t s_first;
+    const uint32_t nw = *n_work;
+    const int tid = threadIdx.x;
+    for (uint32_t e = blockIdx.x; e < nw; e += gridDim.x) {
+        const uint32_t b = work[e];
+        const uint32_t side = b & 3, fr = (b >> 2) % n_fr, s = (b >> 2) / n_fr;
+        const StackDev sd = stacks[s];
+        const uint32_t limit = side < 2 ? sd.width : sd.height;
+        __syncthreads();
+        if (tid == 0) s_first = __ldcg(&sides[b]);
+        if (kLut) sh.lut[tid] = luts[(size_t)s * 256 + tid];
+        __syncthreads();
+        if (s_first == kLbNone) {
+            const uint8_t* img = frames + sd.offset + (uint64_t)(fr * fr_step) * sd.frame_stride;
+            for (uint32_t base = kLbSpec * kColPanel; base < limit; base += kColPanel) {
+                lb_panel_flags<kLut>(sh, img, sd.width, sd.height, sd.pitch, side, base);
+                if (tid == 0) s_first = lb_first_stop(sh, base, limit);
+                __syncthreads();
+                if (s_first != kLbNone) break;
+            }
+        }
+        if (tid == 0) sides[b] = min(s_first, limit);
+    }
 }
 
 // per frame: keep (l,r,t,b) only if at least one pixel remains each way (video_frames_gray.rs:119-127);
@@ -830,11 +957,35 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 1 : 2)
     if (out_hash) finish_stack<Cfg::kThreads>(small, s, done, out_hash, reinterpret_cast<double*>(ring), tid);
 }
 
+// sides[n][n_fr][4] <- letterbox strip counts of frames 0, fr_step, .. of every good stack (three launches, see above)
+static int letterbox_scan(vdf_ctx* ctx, cudaStream_t st, const uint8_t* d_frames, const StackDev* d_sd, uint32_t n, uint32_t n_fr, uint32_t fr_step,
+                          const uint8_t* d_luts, uint32_t* d_sides) {
+    if (n == 0) return VDF_OK;
+    const uint32_t n_sides = n * n_fr * 4;
+    VDF_ALLOC(ctx, ctx->h_lbwork.ensure(((size_t)n_sides + 1) * 4));
+    uint32_t* n_work = ctx->h_lbwork.as<uint32_t>();
+    uint32_t* work = n_work + 1;
+    VDF_CUDA(ctx, cudaMemsetAsync(n_work, 0, 4, st));
+    const unsigned persistent = (unsigned)ctx->sm_count * 4;
+    if (d_luts) {
+        letterbox_strip0_kernel<true><<<n_sides, 128, 0, st>>>(d_frames, d_sd, d_sides, n_fr, fr_step, d_luts, work, n_work);
+        letterbox_panels_kernel<true><<<persistent, 256, 0, st>>>(d_frames, d_sd, d_sides, n_fr, fr_step, d_luts, work, n_work);
+        letterbox_tail_kernel<true><<<persistent, 256, 0, st>>>(d_frames, d_sd, d_sides, n_fr, fr_step, d_luts, work, n_work);
+    } else {
+        letterbox_strip0_kernel<false><<<n_sides, 128, 0, st>>>(d_frames, d_sd, d_sides, n_fr, fr_step, nullptr, work, n_work);
+        letterbox_panels_kernel<false><<<persistent, 256, 0, st>>>(d_frames, d_sd, d_sides, n_fr, fr_step, nullptr, work, n_work);
+        letterbox_tail_kernel<false><<<persistent, 256, 0, st>>>(d_frames, d_sd, d_sides, n_fr, fr_step, nullptr, work, n_work);
+    }
+    ctx->launches += 2;
+    VDF_LAUNCHED(ctx);
+    return VDF_OK;
+}
+
 // the letterbox union over ALL 16 frames of every stack, each pixel through the stack's table first (motion.cu)
 int letterbox_all_frames(vdf_ctx* ctx, const uint8_t* d_frames, const StackDev* d_sd, uint32_t n, const uint8_t* d_luts, uint32_t* d_sides,
                          uint32_t* d_crop) {
-    letterbox_side_kernel<true><<<n * 16 * 4, 256, 0, ctx->stream>>>(d_frames, d_sd, d_sides, 16u, 1u, d_luts);
-    VDF_LAUNCHED(ctx);
+    VDF_CUDA(ctx, cudaMemsetAsync(d_sides, 0, (size_t)n * 16 * 4 * 4, ctx->stream));  // stacks in error are skipped by the scan
+    VDF_TRY(letterbox_scan(ctx, ctx->stream, d_frames, d_sd, n, 16u, 1u, d_luts, d_sides));
     crop_combine_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_sd, d_sides, n, 16u, d_crop);
     VDF_LAUNCHED(ctx);
     return VDF_OK;
@@ -1224,8 +1375,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         if (lb != st) {  // all scans are enqueued up front on their own stream; the resize of chunk k waits for scan k only
             for (uint32_t k = 0; k < n_chunks; ++k) {
                 const uint32_t s0 = chunk_begin(k), cnt = chunk_begin(k + 1) - s0;
-                letterbox_side_kernel<false><<<cnt * 8, 256, 0, lb>>>(d_frames, d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, 2u, 8u, nullptr);
-                VDF_LAUNCHED(ctx);
+                VDF_TRY(letterbox_scan(ctx, lb, d_frames, d_sd + s0, cnt, 2u, 8u, nullptr, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8));
                 crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, lb>>>(d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt, 2u,
                                                                       ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4);
                 VDF_LAUNCHED(ctx);
@@ -1245,8 +1395,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
                 if (lb != st) {
                     VDF_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_chunk[k], 0));
                 } else {
-                    letterbox_side_kernel<false><<<cnt * 8, 256, 0, st>>>(d_frames, d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, 2u, 8u, nullptr);
-                    VDF_LAUNCHED(ctx);
+                    VDF_TRY(letterbox_scan(ctx, st, d_frames, d_sd + s0, cnt, 2u, 8u, nullptr, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8));
                     crop_combine_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(d_sd + s0, ctx->h_sides.as<uint32_t>() + (size_t)s0 * 8, cnt, 2u,
                                                                           ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4);
                     VDF_LAUNCHED(ctx);

@@ -512,12 +512,21 @@ __global__ void peer_compact_kernel(PeerPtrs pp, uint64_t* __restrict__ dst, uin
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n) {
+// bits needed for values < n
+int bits_for(uint64_t n) {
+    int b = 1;
+    while (b < 64 && (1ull << b) < n) ++b;
+    return b;
+}
+
+// ascending radix sort of the bits [0, end_bit) of the keys: every key of the search is (index < n) << 32 | index, so the top
+// 32 - bits(n) bits are zero and one or two of the eight 8-bit passes can be left out
+int sort_keys(vdf_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n, int end_bit) {
     if (n == 0) return VDF_OK;
     size_t tmp = 0;
-    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_in, d_out, (size_t)n, 0, 64, ctx->stream));
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_in, d_out, (size_t)n, 0, end_bit, ctx->stream));
     VDF_ALLOC(ctx, ctx->sort_tmp.ensure(tmp));
-    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp, d_in, d_out, (size_t)n, 0, 64, ctx->stream));
+    VDF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp, d_in, d_out, (size_t)n, 0, end_bit, ctx->stream));
     ctx->launches += 4;  // cub's histogram + onesweep passes (approximate; library kernels)
     return VDF_OK;
 }
@@ -718,7 +727,7 @@ static int run_plan(vdf_ctx* ctx, const Plan& pl, const Packed& rows, const Pack
         ctx->err = "edge buffer overflow: " + std::to_string(cnt) + " matches > capacity " + std::to_string(capacity);
         return VDF_ERR_EDGE_OVERFLOW;
     }
-    return sort_keys(ctx, raw, d_keys_out, cnt);
+    return sort_keys(ctx, raw, d_keys_out, cnt, 32 + bits_for(rows.n));  // keys: (row index < rows.n) << 32 | column index
 }
 
 // `Search::search_self` (search_algorithm.rs:81-171, comparison part) on a prepared table
