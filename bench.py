@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--tol", type=float, default=0.35)
     ap.add_argument("--tol-sweep", default="0.0,0.1,0.2,0.3,0.35,0.4,0.42", help="comma-separated tolerances of the sweep ('' = none)")
     ap.add_argument("--variant", type=int, default=-1, help="search kernel variant (-1: library default)")
-    ap.add_argument("--hash-variant", type=int, default=-1, help="resize kernel: 0 IMMA 4 warps, 1 general, 2 IMMA 8 warps")
+    ap.add_argument("--hash-variant", type=int, default=-1, help="-1 (default) the fused persistent kernel; per-frame kernels: 0 IMMA 4 warps, 1 general, 2 IMMA 8 warps")
     ap.add_argument("--stacks", type=int, default=256, help="1080p stacks resident in HBM per GPU (8.5 GB at 256)")
     ap.add_argument("--hash-total", type=int, default=100_000, help="stack-hashes per hashing run (BASELINE configs[1]: 100 k stacks)")
     ap.add_argument("--mismatch-stacks", type=int, default=1024, help="stacks compared bit by bit with the CPU oracle")
@@ -402,6 +402,7 @@ def main():
     if args.variant >= 0:
         ctx.set_option("search_variant", args.variant)
     if args.hash_variant >= 0:
+        ctx.set_option("hash_fused", 0)
         ctx.set_option("hash_variant", args.hash_variant)
     for kv in args.opt:
         k, v = kv.split("=")
@@ -803,9 +804,10 @@ def main():
         descs = _ffi.make_descs(ns, w, h)
         torch.cuda.synchronize()
         crops = {}
+        cropdetect = int(os.environ.get("VDF_BENCH_CROPDETECT", _ffi.CROPDETECT_LETTERBOX))  # timing studies: 0 = Cropdetect::None
 
         def step():
-            crops["c"] = ctx.hash_stacks_device(pool.data_ptr(), descs, _ffi.CROPDETECT_LETTERBOX, out.data_ptr())[1]
+            crops["c"] = ctx.hash_stacks_device(pool.data_ptr(), descs, cropdetect, out.data_ptr())[1]
 
         with ClockSampler(local) as cs:
             with torch.cuda.stream(stream):

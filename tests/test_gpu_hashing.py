@@ -60,15 +60,18 @@ def test_letterbox_kat_images(ctx):
             assert tuple(crop[0]) == o.letterbox_frame(im, o.LB_ANYCOLOUR, 16), name
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["imma8", "general", "imma4"])
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2], ids=["fused", "imma4", "general", "imma8"])
 @pytest.mark.parametrize("w,h", [(64, 48), (256, 144), (321, 203), (640, 360), (854, 480), (1280, 720), (1920, 1080)])
 def test_crop_cube_and_hash_are_bit_exact(ctx, w, h, variant):
-    """variant 0/2: tensor-core (IMMA) resize where rows are 16-byte aligned, general kernel elsewhere; 1: general"""
-    ctx.set_option("hash_variant", variant)
+    """-1 (the default): hash_fused_kernel, one persistent launch per call; 0 / 2: the per-frame tensor-core (IMMA) resize kernels
+    behind the letterbox scan kernels where rows are 16-byte aligned, general kernel elsewhere; 1: general kernel only"""
+    ctx.set_option("hash_fused", 1 if variant < 0 else 0)
+    ctx.set_option("hash_variant", max(variant, 0))
     try:
         _check_bit_exact(ctx, w, h)
     finally:
         ctx.set_option("hash_variant", 0)
+        ctx.set_option("hash_fused", 1)
 
 
 def _check_bit_exact(ctx, w, h):
@@ -133,7 +136,8 @@ def test_letterbox_noisy_and_wide_bars(ctx):
 
 
 def test_chunked_overlapped_pipeline_matches_serial(ctx):
-    """round 2 pipeline: resize jobs built on the device from the crops (sizes met for the first time take a second pass),
+    """the fused kernel (cold tables: sizes met for the first time take a second pass; warm; DCT in the kernel or on its own) and the
+    per-frame pipeline it replaced: resize jobs built on the device from the crops (sizes met for the first time take a second pass),
     the letterbox scan of chunk k+1 on a second stream beside the resize of chunk k, DCT + pack fused into the resize kernel.
     Every combination of the knobs gives the oracle's hashes, on a fresh context (cold tables) and again (warm)."""
     n, w, h = 160, 256, 144
@@ -147,13 +151,15 @@ def test_chunked_overlapped_pipeline_matches_serial(ctx):
     want_h, want_s, want_c, _ = oracle_all(stacks)
     fresh = _ffi.Context(ctx.device)
     try:
-        for overlap, chunks, fuse in ((1, 4, 1), (1, 4, 1), (0, 1, 1), (0, 4, 0), (1, 2, 0), (0, 1, 0)):
+        for fused, overlap, chunks, fuse in ((1, 0, 1, 1), (1, 0, 1, 1), (1, 0, 1, 0), (0, 1, 4, 1), (0, 1, 4, 1), (0, 0, 1, 1), (0, 0, 4, 0),
+                                             (0, 1, 2, 0), (0, 0, 1, 0)):
+            fresh.set_option("hash_fused", fused)
             fresh.set_option("hash_overlap", overlap)
             fresh.set_option("hash_chunks", chunks)
             fresh.set_option("hash_fuse_dct", fuse)
             got_h, got_s, got_c = gpu_hash(fresh, stacks)
-            assert np.array_equal(got_c, want_c), (overlap, chunks, fuse)
-            assert np.array_equal(got_s, want_s) and np.array_equal(got_h, want_h), (overlap, chunks, fuse)
+            assert np.array_equal(got_c, want_c), (fused, overlap, chunks, fuse)
+            assert np.array_equal(got_s, want_s) and np.array_equal(got_h, want_h), (fused, overlap, chunks, fuse)
     finally:
         fresh.close()
 

@@ -66,7 +66,7 @@ void vdf_ctx_destroy(vdf_ctx* ctx) {
                       &ctx->g_cnt,     &ctx->g_gstart,  &ctx->sk_a,     &ctx->sk_b,    &ctx->sk_c,    &ctx->sk_d,
                       &ctx->sk_order,  &ctx->sk_rank,   &ctx->ref_rows.tiles, &ctx->ref_rows.pc, &ctx->ref_rows.pcmin,
                       &ctx->h_frames[0], &ctx->h_frames[1], &ctx->h_jobs, &ctx->h_sides, &ctx->h_crop, &ctx->h_small,
-                      &ctx->h_hash,    &ctx->h_desc,    &ctx->h_done,   &ctx->h_lbwork};
+                      &ctx->h_hash,    &ctx->h_desc,    &ctx->h_done,   &ctx->h_lbwork, &ctx->h_fctl};
     ctx->tmp_self.release();
     ctx->tmp_cand.release();
     ctx->ref_plan.release();
@@ -127,6 +127,7 @@ int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value) {
     else if (k == "hash_chunks" && value >= 1 && value <= 4) ctx->hash_chunks = (uint32_t)value;
     else if (k == "hash_overlap" && (value == 0 || value == 1)) ctx->hash_overlap = (uint32_t)value;
     else if (k == "hash_fuse_dct" && (value == 0 || value == 1)) ctx->hash_fuse_dct = (uint32_t)value;
+    else if (k == "hash_fused" && (value == 0 || value == 1)) ctx->hash_fused = (uint32_t)value;
     else if (k == "grouping" && (value == 0 || value == 1)) ctx->grouping = (int)value;
     else if (k == "exchange" && (value == 0 || value == 1)) ctx->exchange = (int)value;
     else if (k == "hash_variant" && value >= 0 && value <= 3) ctx->hash_variant = (int)value;

@@ -124,6 +124,7 @@ struct CoefTable {
     uint32_t* d_bounds = nullptr;  // 16 x (start, size)
     int16_t* d_k = nullptr;        // 16 x window
     int8_t* d_kb = nullptr;        // tensor-core operand: [2][16][in_size padded] split hi/lo bytes (built lazily)
+    void* d_kva = nullptr;         // the table as IMMA A fragments of the fused kernel's vertical pass (hash.cu get_table)
     std::vector<uint32_t> h_bounds;
     std::vector<int16_t> h_k;
 };
@@ -216,6 +217,8 @@ struct vdf_ctx {
     // three kernel tails.  Default: one chunk, one stream, and a scan that is cheap on its own.
     uint32_t hash_chunks = 1;
     uint32_t hash_overlap = 0;
+    uint32_t hash_fused = 1;     // 1 (default): hash_fused_kernel, one persistent launch per call does letterbox -> ... -> pack; 0: the
+                                 // per-frame kernels of round 1 / early round 2 (letterbox scan kernels, resize_mma_kernel)
     uint32_t hash_fuse_dct = 1;  // DCT + threshold + pack in the resize kernel (the CTA that finishes a stack); 0: a kernel of its own
     int exchange = 0;       // 1: searches append their matches to every rank's peer buffer (vdf_peer_*), see PeerExchange
     vdf::PeerExchange peer;
@@ -247,7 +250,7 @@ struct vdf_ctx {
     bool ham_attrs = false, tc_attrs = false;
     size_t hash_smem_set[3] = {0, 0, 0};
     // hashing scratch
-    vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc, h_coef_lut, h_bfrag_lut, h_done, h_lbwork;
+    vdf::DevBuf h_frames[2], h_jobs, h_sides, h_crop, h_small, h_hash, h_desc, h_coef_lut, h_bfrag_lut, h_done, h_lbwork, h_fctl;
     vdf::DevBuf m_state, m_lut, m_sides, m_acc, m_a, m_b, m_c, m_f32, m_label;  // motion.cu scratch
     vdf::PinnedBuf pin_a, pin_b, pin_c, pin_frames[2], h_groups;  // h_groups: staging of the group CSR on its way to the caller
     vdf::PinnedBuf h_misc;  // landing zone of the few counters the host reads back per call

@@ -23,6 +23,8 @@
 // resize reads), and ONE fused kernel per stack set that reads every pixel once and writes the 128-byte hash (crop window,
 // Lanczos3 to 16x16 per frame, and -- in the CTA that finishes a stack's 16th frame -- the 16^3 DCT, threshold and pack).
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -30,6 +32,14 @@
 namespace vdf {
 
 // ================================================================================ H2: letterbox crop detect
+
+// A "group" is the set of threads that runs one of the block-level device functions below: a whole thread block (BAR = 0,
+// __syncthreads) or a warp-specialised part of one (BAR = named barrier id, NT threads; the fused kernel's helper warps).
+template <int BAR, int NT>
+__device__ __forceinline__ void group_sync() {
+    if constexpr (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
+}
 constexpr int kLbTol = 16;  // LetterboxColour::AnyColour(16), video_frames_gray.rs:206
 constexpr int kColPanel = 32;
 constexpr int kRowPanel = 32;
@@ -117,16 +127,17 @@ struct LbShared {
 };
 
 // flags[k] <- strip base + k of `side` is letterbox, for the 32 strips of one panel (256 threads, all of them; synchronised on return)
-template <bool kLut>
+template <bool kLut, int NT = 256, int BAR = 0>
 __device__ __forceinline__ void lb_panel_flags(LbShared& sh, const uint8_t* __restrict__ img, uint32_t W, uint32_t H, uint32_t P, uint32_t side,
                                                uint32_t base) {
     auto M = [&](uint32_t v) -> uint32_t { return kLut ? (uint32_t)sh.lut[v] : v; };
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32, RPP = NT / 8;  // warps in the group; rows one pass of 8-lane word rows covers
+    const int tid = threadIdx.x % NT, lane = tid & 31, warp = tid >> 5;  // groups start at a multiple of NT threads
     const bool cols = side < 2;  // 0 left, 1 right, 2 top, 3 bottom
     const uint32_t limit = cols ? W : H, len = cols ? H : W;
     if (cols) {
         const uint32_t px0 = side == 0 ? base : W - 32 - base;  // first pixel column of a full 32-column panel
-        // full, 4-byte aligned panel: 8 word loads cover a row of the panel, 32 rows per pass, 16 passes in flight
+        // full, 4-byte aligned panel: 8 word loads cover a row of the panel, RPP rows per pass
         const bool fast = base + kColPanel <= W && ((reinterpret_cast<uintptr_t>(img) | P | px0) & 3) == 0;
         const uint32_t wq = tid & 7, r0 = tid >> 3;
         const uint32_t* col4 = reinterpret_cast<const uint32_t*>(img + px0) + wq;
@@ -135,23 +146,15 @@ __device__ __forceinline__ void lb_panel_flags(LbShared& sh, const uint8_t* __re
         if (fast) {  // pass A: value range of every column of the panel
             if (tid < kColPanel) sh.mn[tid] = 255u, sh.mx[tid] = 0u;
             if (tid == 0) sh.need_hist = 0;
-            __syncthreads();
+            group_sync<BAR, NT>();
             // rows beyond the last one re-read the last one: harmless for a minimum / maximum, and every update is a full pair
             LbRange4 rg;
-            if (H <= 32 * 40) {  // up to 1280 rows (1080p): every load of the panel in flight at once, one round trip to memory
+            for (uint32_t y0 = r0; y0 < H; y0 += RPP * 40) {  // 40 loads in flight per thread: 1280 rows (1080p) in one round trip at NT = 256
                 uint32_t v[40];
 #pragma unroll
-                for (int u = 0; u < 40; ++u) v[u] = __ldg(col4 + (uint64_t)min(r0 + 32 * u, H - 1) * P4);
+                for (int u = 0; u < 40; ++u) v[u] = __ldg(col4 + (uint64_t)min(y0 + RPP * u, H - 1) * P4);
 #pragma unroll
                 for (int u = 0; u < 40; u += 2) rg.add2(v[u], v[u + 1]);
-            } else {
-                for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
-                    uint32_t v[16];
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) v[u] = __ldg(col4 + (uint64_t)min(y0 + 32 * u, H - 1) * P4);
-#pragma unroll
-                    for (int u = 0; u < 16; u += 2) rg.add2(v[u], v[u + 1]);
-                }
             }
             // the four row-threads of a warp that share a word column: lanes l, l^8, l^16, l^24
             rg.merge(8), rg.merge(16);
@@ -163,13 +166,13 @@ __device__ __forceinline__ void lb_panel_flags(LbShared& sh, const uint8_t* __re
                     atomicMax(&sh.mx[k], rg.mx(q));
                 }
             }
-            __syncthreads();
+            group_sync<BAR, NT>();
             if (tid < kColPanel) {
                 const bool nar = M(sh.mx[tid]) - M(sh.mn[tid]) <= (uint32_t)kLbTol;  // H >= 1: max >= min
                 sh.flags[tid] = nar;
                 if (!nar) sh.need_hist = 1;
             }
-            __syncthreads();
+            group_sync<BAR, NT>();
             need_hist = sh.need_hist != 0;
             if (need_hist) {
                 // Only the FIRST strip that is not letterbox matters, and a strip with a wide value range almost always is
@@ -177,40 +180,40 @@ __device__ __forceinline__ void lb_panel_flags(LbShared& sh, const uint8_t* __re
                 // that strip turns out to be letterbox after all (a noisy bar) do all the undecided strips get histograms.
                 const uint32_t wide = __ballot_sync(0xffffffffu, !sh.flags[lane]);  // pass A left a wide strip: wide != 0
                 const uint32_t k0 = __ffs(wide) - 1;
-                sh.hist[tid] = 0;
-                __syncthreads();
+                for (int q = tid; q < 256; q += NT) sh.hist[q] = 0;
+                group_sync<BAR, NT>();
                 const uint8_t* col = img + (side == 0 ? base + k0 : W - 1 - (base + k0));
-                for (uint32_t y0 = tid; y0 < H; y0 += 256 * 8) {
+                for (uint32_t y0 = tid; y0 < H; y0 += NT * 8) {
                     uint32_t v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = y0 + 256 * u < H ? (uint32_t)__ldg(col + (uint64_t)(y0 + 256 * u) * P) : 0x100u;
+                    for (int u = 0; u < 8; ++u) v[u] = y0 + NT * u < H ? (uint32_t)__ldg(col + (uint64_t)(y0 + NT * u) * P) : 0x100u;
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if (v[u] < 0x100u) atomicAdd(&sh.hist[M(v[u])], 1u);
                 }
-                __syncthreads();
+                group_sync<BAR, NT>();
                 if (warp == 0) {
                     const bool ok = strip_is_letterbox(sh.hist, len, lane);
                     if (lane == 0) sh.need_hist = ok ? 1u : 0u;  // flags[k0] stays 0 unless the full pass below says otherwise
                 }
-                __syncthreads();
+                group_sync<BAR, NT>();
                 need_hist = sh.need_hist != 0;
             }
         }
         if (need_hist) {  // pass B: histograms of every undecided strip (the data of pass A comes from L1 / L2 this time)
-            for (uint32_t q = tid; q < kColPanel * 257; q += 256) sh.hist[q] = 0;
-            __syncthreads();
+            for (uint32_t q = tid; q < kColPanel * 257; q += NT) sh.hist[q] = 0;
+            group_sync<BAR, NT>();
             if (fast) {
-                for (uint32_t y0 = r0; y0 < H; y0 += 32 * 16) {
+                for (uint32_t y0 = r0; y0 < H; y0 += RPP * 16) {
                     uint32_t v[16];
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        const uint32_t y = y0 + 32 * u;
+                        const uint32_t y = y0 + RPP * u;
                         v[u] = y < H ? __ldg(col4 + (uint64_t)y * P4) : 0u;
                     }
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        if (y0 + 32 * u < H) {
+                        if (y0 + RPP * u < H) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const uint32_t c = 4 * wq + q, k = side == 0 ? c : 31 - c;
@@ -224,11 +227,11 @@ __device__ __forceinline__ void lb_panel_flags(LbShared& sh, const uint8_t* __re
                 const bool act = idx < W;
                 const uint32_t x = side == 0 ? idx : W - 1 - idx;
                 // 16 independent loads in flight per lane before the (shared-memory) histogram updates
-                for (uint32_t y0 = warp; y0 < H; y0 += 8 * 16) {
+                for (uint32_t y0 = warp; y0 < H; y0 += NW * 16) {
                     uint32_t v[16];
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        const uint32_t y = y0 + 8 * u;
+                        const uint32_t y = y0 + NW * u;
                         v[u] = (act && y < H) ? (uint32_t)__ldg(img + (uint64_t)y * P + x) : 0xFFFFu;
                     }
 #pragma unroll
@@ -236,46 +239,49 @@ __device__ __forceinline__ void lb_panel_flags(LbShared& sh, const uint8_t* __re
                         if (v[u] != 0xFFFFu) atomicAdd(&sh.hist[lane * 257 + M(v[u])], 1u);
                 }
             }
-            __syncthreads();
-            for (uint32_t k = warp; k < kColPanel; k += 8) {
+            group_sync<BAR, NT>();
+            for (uint32_t k = warp; k < kColPanel; k += NW) {
                 if (fast && sh.flags[k]) continue;  // decided by its value range
                 bool ok = false;
                 if (base + k < limit) ok = strip_is_letterbox(sh.hist + k * 257, len, lane);
                 if (lane == 0) sh.flags[k] = ok;
             }
-            __syncthreads();
+            group_sync<BAR, NT>();
         }
     } else {
-        // rows: warp w decides rows base + w + 8 i (i = 0..3) on its own, in its own four sub-histograms (lane & 3) that
+        // rows: warp w decides rows base + w + NW i (i = 0 .. 32 / NW - 1) on its own, in its own four sub-histograms (lane & 3) that
         // keep same-value lanes from piling onto one counter
+        constexpr int kRowsPerWarp = kRowPanel / NW;
         uint32_t* h4 = sh.hist + (warp * 4) * 257;
         uint32_t* hs = h4 + (lane & 3) * 257;
         const uint32_t W4 = W >> 2;
-        // first the value range of all four rows of this warp, their loads in flight together (rows of <= 2048 px, aligned):
-        // a panel inside a bar costs one round trip to memory
+        // first the value range of the rows of this warp, four rows' loads in flight together (rows of <= 2048 px, aligned):
+        // a panel inside a bar costs one round trip to memory per four rows of a warp
         uint32_t decided = 0;  // bit i: row i is narrow
         if (((reinterpret_cast<uintptr_t>(img) | P) & 3) == 0 && W4 <= 32 * 16) {
-            LbRange1 rg[4];
+            for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
+                LbRange1 rg[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t idx = base + warp + 8 * i;
-                if (idx < H) {
-                    const uint32_t y = side == 2 ? idx : H - 1 - idx;
-                    const uint8_t* row = img + (uint64_t)y * P;
-                    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t idx = base + warp + NW * (i0 + i);
+                    if (idx < H) {
+                        const uint32_t y = side == 2 ? idx : H - 1 - idx;
+                        const uint8_t* row = img + (uint64_t)y * P;
+                        const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const uint32_t q = u * 32 + lane;
-                        if (q < W4) rg[i].add(__ldg(row4 + q));
+                        for (int u = 0; u < 16; ++u) {
+                            const uint32_t q = u * 32 + lane;
+                            if (q < W4) rg[i].add(__ldg(row4 + q));
+                        }
+                        const uint32_t xt = (W4 << 2) + lane;
+                        if (xt < W) rg[i].add((uint32_t)__ldg(row + xt) * 0x01010101u);
                     }
-                    const uint32_t xt = (W4 << 2) + lane;
-                    if (xt < W) rg[i].add((uint32_t)__ldg(row + xt) * 0x01010101u);
                 }
-            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t a = __reduce_min_sync(0xffffffffu, rg[i].mn()), b = __reduce_max_sync(0xffffffffu, rg[i].mx());
-                if (base + warp + 8 * i < H && M(b) - M(a) <= (uint32_t)kLbTol) decided |= 1u << i;
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t a = __reduce_min_sync(0xffffffffu, rg[i].mn()), b = __reduce_max_sync(0xffffffffu, rg[i].mx());
+                    if (base + warp + NW * (i0 + i) < H && M(b) - M(a) <= (uint32_t)kLbTol) decided |= 1u << (i0 + i);
+                }
             }
         }
         // one row (warp-wide): its value range first when it fits the registers, the histogram only if that fails
@@ -366,27 +372,27 @@ __device__ __forceinline__ void lb_panel_flags(LbShared& sh, const uint8_t* __re
         // the rows the range test has settled; of the others only the FIRST can end the walk: it alone is evaluated (by the warp
         // that owns it) and, being wide, it almost always is picture.  Only if it is letterbox after all do the rest follow.
 #pragma unroll
-        for (uint32_t i = 0; i < kRowPanel / 8; ++i)
-            if (lane == 0) sh.flags[warp + 8 * i] = (base + warp + 8 * i < H && (decided & (1u << i))) ? 1u : 0u;
+        for (uint32_t i = 0; i < (uint32_t)kRowsPerWarp; ++i)
+            if (lane == 0) sh.flags[warp + NW * i] = (base + warp + NW * i < H && (decided & (1u << i))) ? 1u : 0u;
         if (tid == 0) sh.need_hist = 0;
-        __syncthreads();
+        group_sync<BAR, NT>();
         const uint32_t open = __ballot_sync(0xffffffffu, !sh.flags[lane] && base + lane < H);
         if (open == 0) return;  // every row of the panel that exists is narrow
         const uint32_t k0 = __ffs(open) - 1;
-        if (warp == (int)(k0 & 7u)) {
+        if (warp == (int)(k0 % NW)) {
             const bool ok = row_is_letterbox(base + k0);
             if (lane == 0) sh.flags[k0] = ok, sh.need_hist = ok ? 1u : 0u;
         }
-        __syncthreads();
+        group_sync<BAR, NT>();
         if (!sh.need_hist) return;
-        for (uint32_t i = 0; i < kRowPanel / 8; ++i) {
-            const uint32_t k = warp + 8 * i, idx = base + k;
+        for (uint32_t i = 0; i < (uint32_t)kRowsPerWarp; ++i) {
+            const uint32_t k = warp + NW * i, idx = base + k;
             if (k <= k0 || idx >= H || (decided & (1u << i))) continue;
             const bool ok = row_is_letterbox(idx);
             if (lane == 0) sh.flags[k] = ok;
             __syncwarp();
         }
-        __syncthreads();
+        group_sync<BAR, NT>();
     }
 }
 
@@ -397,6 +403,57 @@ __device__ __forceinline__ uint32_t lb_first_stop(const LbShared& sh, uint32_t b
     return kLbNone;
 }
 
+// strip 0 of one side (group of NT threads, all of them): is it letterbox?  hist = 256 shared counters, s_flag = one shared word
+template <bool kLut, int NT, int BAR>
+__device__ __forceinline__ bool lb_strip0(uint32_t* hist, uint32_t* s_flag, const uint8_t* s_lut, const uint8_t* __restrict__ img, uint32_t W, uint32_t H,
+                                          uint32_t P, uint32_t side) {
+    const int tid = threadIdx.x % NT, lane = tid & 31, warp = tid >> 5;
+    auto M = [&](uint32_t v) -> uint32_t { return kLut ? (uint32_t)s_lut[v] : v; };
+    for (int q = tid; q < 256; q += NT) hist[q] = 0;
+    group_sync<BAR, NT>();
+    const bool cols = side < 2;
+    if (cols) {
+        const uint8_t* col = img + (side == 0 ? 0u : W - 1);
+        for (uint32_t y0 = tid; y0 < H; y0 += NT * 8) {  // eight loads in flight per thread
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = y0 + NT * u < H ? (uint32_t)__ldg(col + (uint64_t)(y0 + NT * u) * P) : 0x100u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (v[u] < 0x100u) atomicAdd(&hist[M(v[u])], 1u);
+        }
+    } else {
+        const uint8_t* row = img + (uint64_t)(side == 2 ? 0u : H - 1) * P;
+        uint32_t x_done = 0;
+        if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {  // words, eight loads in flight per thread (one round trip for rows <= 4096 px at NT = 128)
+            const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+            const uint32_t W4 = W >> 2;
+            for (uint32_t q0 = tid; q0 < W4; q0 += NT * 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = q0 + NT * u < W4 ? __ldg(row4 + q0 + NT * u) : 0u;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (q0 + NT * u < W4) {
+                        atomicAdd(&hist[M(v[u] & 255u)], 1u);
+                        atomicAdd(&hist[M((v[u] >> 8) & 255u)], 1u);
+                        atomicAdd(&hist[M((v[u] >> 16) & 255u)], 1u);
+                        atomicAdd(&hist[M(v[u] >> 24)], 1u);
+                    }
+            }
+            x_done = W4 << 2;
+        }
+        for (uint32_t x = x_done + tid; x < W; x += NT) atomicAdd(&hist[M(__ldg(row + x))], 1u);
+    }
+    group_sync<BAR, NT>();
+    if (warp == 0) {
+        const bool ok = strip_is_letterbox(hist, cols ? H : W, lane);
+        if (lane == 0) *s_flag = ok ? 1u : 0u;
+    }
+    group_sync<BAR, NT>();
+    return *s_flag != 0;
+}
+
 // grid = n_stacks * n_fr * 4 sides; 128 threads.  sides[b] <- 0 (strip 0 is picture) or kLbNone + an entry in the work list.
 template <bool kLut>
 __global__ void __launch_bounds__(128) letterbox_strip0_kernel(const uint8_t* __restrict__ frames, const StackDev* __restrict__ stacks,
@@ -404,41 +461,21 @@ __global__ void __launch_bounds__(128) letterbox_strip0_kernel(const uint8_t* __
                                                                const uint8_t* __restrict__ luts /* [n][256] */, uint32_t* __restrict__ work,
                                                                uint32_t* __restrict__ n_work) {
     __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_flag;
     __shared__ uint8_t s_lut[kLut ? 256 : 4];
     const uint32_t b = blockIdx.x, side = b & 3, fr = (b >> 2) % n_fr, s = (b >> 2) / n_fr;
     const StackDev sd = stacks[s];
     if (sd.status != VDF_STACK_OK) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int q = tid; q < 256; q += 128) {
-        hist[q] = 0;
-        if (kLut) s_lut[q] = luts[(size_t)s * 256 + q];
+    const int tid = threadIdx.x;
+    if (kLut) {
+        for (int q = tid; q < 256; q += 128) s_lut[q] = luts[(size_t)s * 256 + q];
+        __syncthreads();
     }
-    __syncthreads();
-    auto M = [&](uint32_t v) -> uint32_t { return kLut ? (uint32_t)s_lut[v] : v; };
     const uint8_t* img = frames + sd.offset + (uint64_t)(fr * fr_step) * sd.frame_stride;
-    const uint32_t W = sd.width, H = sd.height, P = sd.pitch;
-    const bool cols = side < 2;
-    if (cols) {
-        const uint8_t* col = img + (side == 0 ? 0u : W - 1);
-        for (uint32_t y0 = tid; y0 < H; y0 += 128 * 8) {  // eight loads in flight per thread
-            uint32_t v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = y0 + 128 * u < H ? (uint32_t)__ldg(col + (uint64_t)(y0 + 128 * u) * P) : 0x100u;
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (v[u] < 0x100u) atomicAdd(&hist[M(v[u])], 1u);
-        }
-    } else {
-        const uint8_t* row = img + (uint64_t)(side == 2 ? 0u : H - 1) * P;
-        for (uint32_t x = tid; x < W; x += 128) atomicAdd(&hist[M(__ldg(row + x))], 1u);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const bool ok = strip_is_letterbox(hist, cols ? H : W, lane);
-        if (lane == 0) {
-            sides[b] = ok ? kLbNone : 0u;
-            if (ok) work[atomicAdd(n_work, 1u)] = b;
-        }
+    const bool ok = lb_strip0<kLut, 128, 0>(hist, &s_flag, s_lut, img, sd.width, sd.height, sd.pitch, side);
+    if (tid == 0) {
+        sides[b] = ok ? kLbNone : 0u;
+        if (ok) work[atomicAdd(n_work, 1u)] = b;
     }
 }
 
@@ -600,13 +637,13 @@ constexpr int kCubeBytes = 16 * 16 * 17 * 8;  // the f64 cube with its padded pi
 // One thread block (NT = 128 or 256 threads, all of them): small [t][row][col] u8 -> m[t][x=col][y=row] = p - 128
 // (dct_3d.rs:40-44,76), DCT along y, x, t (raw_dct_ops.rs:107-142), bit t*100+x*10+y = coef > 0.0 (dct_3d.rs:55-66), Lsb0
 // words.  `cube` = kCubeBytes of shared memory.
-template <int NT>
+template <int NT, int BAR = 0>
 __device__ __forceinline__ void dct_pack_block(const uint8_t* __restrict__ sm, double* cube, uint32_t* __restrict__ out, int tid) {
     for (int q = tid; q < 4096; q += NT) {
         const int t = q >> 8, row = (q >> 4) & 15, col = q & 15;
         cube[cidx(t, col, row)] = (double)__ldcg(sm + q) - 128.0;  // written by other thread blocks: read through L2
     }
-    __syncthreads();
+    group_sync<BAR, NT>();
     double v[16];
     for (int line = tid; line < 256; line += NT) {  // along y: line (t, x)
         const int t = line >> 4, x = line & 15;
@@ -616,7 +653,7 @@ __device__ __forceinline__ void dct_pack_block(const uint8_t* __restrict__ sm, d
 #pragma unroll
         for (int k = 0; k < 16; ++k) cube[cidx(t, x, k)] = v[k];
     }
-    __syncthreads();
+    group_sync<BAR, NT>();
     for (int line = tid; line < 256; line += NT) {  // along x: line (t, y)
         const int t = line >> 4, y = line & 15;
 #pragma unroll
@@ -625,7 +662,7 @@ __device__ __forceinline__ void dct_pack_block(const uint8_t* __restrict__ sm, d
 #pragma unroll
         for (int k = 0; k < 16; ++k) cube[cidx(t, k, y)] = v[k];
     }
-    __syncthreads();
+    group_sync<BAR, NT>();
     for (int line = tid; line < 256; line += NT) {  // along t: line (x, y)
         const int x = line >> 4, y = line & 15;
 #pragma unroll
@@ -634,7 +671,7 @@ __device__ __forceinline__ void dct_pack_block(const uint8_t* __restrict__ sm, d
 #pragma unroll
         for (int k = 0; k < 16; ++k) cube[cidx(k, x, y)] = v[k];
     }
-    __syncthreads();
+    group_sync<BAR, NT>();
     for (int b = tid; b < 1024; b += NT) {
         bool bit = false;
         if (b < VDF_HASH_BITS) {
@@ -696,7 +733,12 @@ struct StackJob {
     const uint8_t* kmask;  // per k-chunk: bit (2*ks + octet) set iff outputs 8*octet..+7 have a tap in k-step ks
     uint32_t x0_al;      // first column loaded = left rounded down to 16
     uint32_t n_kch;      // 128-pixel k-chunks covering [x0_al, left + cw)
-    uint32_t fast;       // 1: resize_mma_kernel, 0: resize_general_kernel
+    uint32_t fast;       // 1: resize_mma_kernel / hash_fused_kernel, 0: resize_general_kernel
+    // fused kernel (hash_fused_kernel)
+    const uint8_t* kb2;  // per 256-pixel k-chunk: the B fragments of its two 128-pixel halves (8 KB) + a 16-byte header {mask, mask}
+    const uint4* kva;    // vertical coefficients as IMMA A fragments: [32-row k-step][hi, lo][lane]
+    uint32_t n_kc2;      // 256-pixel k-chunks covering [x0_al, left + cw)
+    uint32_t pad2;
 };
 
 __device__ __forceinline__ uint8_t clip8(int32_t v, uint32_t precision) {
@@ -1016,51 +1058,814 @@ struct CoefRef {
     const uint32_t* bounds;
     const int16_t* k;
     uint32_t window, precision;
+    const uint4* kva;  // the same coefficients as A fragments of the vertical pass on the tensor path (fused kernel)
 };
 struct BFragRef {
     const uint2* kb;
     const uint8_t* kmask;
+    const uint8_t* kb2;  // fused kernel's form: [256-px chunk][8 KB fragments + 16-byte header]
 };
 
-// one thread per stack: crop -> StackJob (what the host did in round 1 between two kernels, with a synchronise in between)
-__global__ void job_build_kernel(const StackDev* __restrict__ stacks, const uint32_t* __restrict__ crop, uint32_t n,
-                                 const CoefRef* __restrict__ coef_lut, const BFragRef* __restrict__ bfrag_lut, uint32_t ring_bytes,
-                                 uint32_t allow_fast, uint32_t only_missed, StackJob* __restrict__ jobs, uint32_t* __restrict__ miss,
-                                 uint32_t* __restrict__ n_miss) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+// crop -> StackJob (what the host did in round 1 between two kernels, with a synchronise in between).  *missed: a size seen for
+// the first time -- the host builds its tables after the pass and the stack runs again.  max_kch / ring_bytes: limits of the
+// per-frame kernels (tap masks in shared memory, the vertical table staged in the ring); the fused kernel has neither.
+__device__ __forceinline__ StackJob make_job(const StackDev& d, const uint32_t* c, const CoefRef* __restrict__ coef_lut,
+                                             const BFragRef* __restrict__ bfrag_lut, uint32_t ring_bytes, uint32_t max_kch, bool allow_fast,
+                                             bool* missed) {
     StackJob j;
     memset(&j, 0, sizeof j);
-    const StackDev d = stacks[s];
     j.status = d.status;
-    if (d.status == VDF_STACK_OK && only_missed && !miss[s]) j.status = kJobSkip;  // hashed in the first pass
-    if (j.status == VDF_STACK_OK) {
-        const uint32_t* c = crop + (size_t)s * 4;
-        j.offset = d.offset, j.frame_stride = d.frame_stride, j.pitch = d.pitch;
-        j.left = c[0], j.top = c[2];
-        j.cw = d.width - c[0] - c[1], j.ch = d.height - c[2] - c[3];  // Crop::as_view_args, crop.rs:92-103
-        const CoefRef th = coef_lut[j.cw], tv = coef_lut[j.ch];
-        const uint32_t shift = j.left & 15u;
-        const bool fits = (shift + j.cw + kKch - 1) / kKch <= 256 && 32u * tv.window <= ring_bytes;
-        const bool fast = d.aligned && fits && allow_fast;
-        const BFragRef bf = fast ? bfrag_lut[(size_t)j.cw * 16 + shift] : BFragRef{nullptr, nullptr};
-        if (!th.k || !tv.k || (fast && !bf.kb)) {  // a size seen for the first time: the host builds it, the stack runs again
-            miss[s] = 1;
-            atomicAdd(n_miss, 1u);
-            j.status = kJobSkip;
+    *missed = false;
+    if (d.status != VDF_STACK_OK) return j;
+    j.offset = d.offset, j.frame_stride = d.frame_stride, j.pitch = d.pitch;
+    j.left = c[0], j.top = c[2];
+    j.cw = d.width - c[0] - c[1], j.ch = d.height - c[2] - c[3];  // Crop::as_view_args, crop.rs:92-103
+    const CoefRef th = coef_lut[j.cw], tv = coef_lut[j.ch];
+    const uint32_t shift = j.left & 15u;
+    const bool fits = (shift + j.cw + kKch - 1) / kKch <= max_kch && (uint64_t)32u * tv.window <= ring_bytes;
+    const bool fast = d.aligned && fits && allow_fast;
+    const BFragRef bf = fast ? bfrag_lut[(size_t)j.cw * 16 + shift] : BFragRef{nullptr, nullptr, nullptr};
+    if (!th.k || !tv.k || (fast && !bf.kb)) {
+        *missed = true;
+        j.status = kJobSkip;
+        return j;
+    }
+    j.bh = th.bounds, j.kh = th.k, j.win_h = th.window, j.prec_h = th.precision;
+    j.bv = tv.bounds, j.kv = tv.k, j.win_v = tv.window, j.prec_v = tv.precision;
+    if (fast) {
+        j.x0_al = j.left & ~15u;
+        j.n_kch = (shift + j.cw + kKch - 1) / kKch;
+        j.kb = bf.kb, j.kmask = bf.kmask;
+        j.kb2 = bf.kb2, j.kva = tv.kva, j.n_kc2 = (j.n_kch + 1) / 2;
+        j.fast = 1;
+    }
+    return j;
+}
+
+// one thread per stack.  flags / n_nofuse (fused path, crops known up front): flags[s] <- 1 "job is built"; *n_nofuse counts the
+// stacks the fused kernel will NOT hash (in error, missed, skipped, or on the general path)
+__global__ void job_build_kernel(const StackDev* __restrict__ stacks, const uint32_t* __restrict__ crop, uint32_t n,
+                                 const CoefRef* __restrict__ coef_lut, const BFragRef* __restrict__ bfrag_lut, uint32_t ring_bytes, uint32_t max_kch,
+                                 uint32_t allow_fast, uint32_t only_missed, StackJob* __restrict__ jobs, uint32_t* __restrict__ miss,
+                                 uint32_t* __restrict__ n_miss, uint32_t* __restrict__ flags, uint32_t* __restrict__ n_nofuse) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    StackDev d = stacks[s];
+    StackJob j;
+    if (d.status == VDF_STACK_OK && only_missed && !miss[s]) {  // hashed in the first pass
+        memset(&j, 0, sizeof j);
+        j.status = kJobSkip;
+    } else {
+        bool missed;
+        j = make_job(d, crop + (size_t)s * 4, coef_lut, bfrag_lut, ring_bytes, max_kch, allow_fast != 0, &missed);
+        if (d.status == VDF_STACK_OK) miss[s] = missed ? 1u : 0u;
+        if (missed) atomicAdd(n_miss, 1u);
+    }
+    jobs[s] = j;
+    if (flags) {
+        flags[s] = 1u;
+        if (!(j.status == VDF_STACK_OK && j.fast)) atomicAdd(n_nofuse, 1u);
+    }
+}
+
+// ================================================================================ the fused kernel
+// ONE launch per call does letterbox -> crop -> resize -> DCT -> threshold -> pack: sm_count persistent thread blocks of 416 threads,
+// warp-specialised into three groups that never share a barrier:
+//   pixel group   (warps 0-7)  the pixel stream.  Frames are claimed one at a time; tiles of 128 rows x 256 bytes travel HBM ->
+//                              shared memory through a 4-stage cp.async ring that never drains between frames (the producer side runs
+//                              ahead ACROSS frames); the horizontal pass is the IMMA contraction of resize_mma_kernel; the u8
+//                              intermediate of a warp's 16 rows goes through 768 bytes of shared memory straight into half a k-step of
+//                              the VERTICAL pass, also on the tensor path (A = the 16 x 32 slice of the vertical coefficients as hi / lo
+//                              bytes, B = the transposed intermediate), accumulated in registers over the frame: no per-frame
+//                              intermediate buffer, no serial tail per frame, shared memory independent of the frame height.
+//   scheduler     (warp 12)    one lane: claims the next frame, waits for its stack's job to be published, fills a slot.
+//   helper group  (warps 8-11) everything that is latency-bound: first the letterbox scan items (one per stack x frame {0, 8} x side:
+//                              strip 0, then panel after panel), the item that completes a stack's eighth side turns the crop into
+//                              the stack's resize job and publishes it; then the 16^3 DCT + threshold + pack of every stack whose
+//                              sixteenth frame the pixel groups have finished.  All of it runs in the shadow of the pixel stream.
+// Items are claimed in order from global counters and a letterbox item never waits for anything, so every wait in the kernel is
+// for work that a RUNNING group has already claimed: no deadlock, whatever the number of resident blocks.
+// Why: the per-frame kernel moved 5.5 TB/s (128-byte row segments, a vertical-pass tail and a launch slot per frame, a wave tail
+// per launch) and the letterbox scan held the GPU alone for 7 % of a step; a token consumer with this tile shape and ring reads
+// 6.7 TB/s (csrc/microbench_read.cu, profiles/r02_microbench_read.jsonl).
+constexpr int kFRows = 128, kFCols = 256, kFPitch = kFCols + 16;
+constexpr int kFStages = 4;
+constexpr int kFCoefBytes = 2 * kBFragBytes + 16;               // two 128-pixel halves + header
+constexpr int kFStageBytes = kFRows * kFPitch + kFCoefBytes;    // 43 024
+constexpr int kFSlots = 8;
+constexpr int kFSlotMasks = 72;  // frames up to 9216 pixels wide skip untapped octets; wider ones copy every fragment
+constexpr int kFTmpPitch = 48;                                  // transposed intermediate: [16 outputs][32 rows + pad], per warp
+constexpr int kFHelperBytes = kCubeBytes;                       // LbShared (33.5 KB) and the DCT cube (34 KB) share the helpers' arena
+constexpr int kFConsThreads = 256, kFProdThreads = 128, kFHelpThreads = 128;
+constexpr int kFThreads = kFConsThreads + kFProdThreads + kFHelpThreads + 64;  // + scheduler warp + finalizer warp
+constexpr uint32_t kFNoFrame = 0xFFFFFFFFu;
+
+struct FrameSlot {
+    const uint8_t* img;  // first row of the crop window, first loaded column
+    const uint8_t* kb2;
+    const uint4* kva;
+    uint32_t pitch, ch, row_bytes, n_kc, n_rb, prec_h, prec_v, out_idx /* stack * 16 + frame, or kFNoFrame: no more frames */;
+    union {
+        uint8_t masks[kFSlotMasks];  // tap masks of the 128-pixel k-chunks (kmask): the producers copy only the octets that have taps
+        unsigned long long masks8[kFSlotMasks / 8];
+    };
+};
+static_assert(sizeof(FrameSlot) == 56 + kFSlotMasks, "slot layout");
+
+struct FusedSmem {  // behind the ring and the helpers' arena
+    uint8_t tmpT[8][16 * kFTmpPitch];
+    int32_t vred[2][256];
+    FrameSlot slots[kFSlots];
+    uint32_t sched_count;  // slots filled so far (scheduler -> pixel group)
+    uint32_t p_ord;        // progress of the producers: 2 * (ordinal of the frame in production) + (past its middle) (-> scheduler)
+    uint32_t h_bcast, h_flag;
+    uint32_t abort_all;
+    uint32_t fin_stop;                 // consumers are done: frames finished in total + 1
+    uint32_t fin_out[2], fin_prec[2];  // finalizer: the frame whose vertical sums are in vred[b]
+    uint32_t pad;
+    uint64_t full[kFStages], empty[kFStages];  // mbarriers: a stage's copies have landed / its readers are done
+    uint64_t fin_full[2], fin_empty[2];        // mbarriers: all eight warps' sums are in vred[b] / vred[b] is zero again
+};
+constexpr size_t kFusedSmemBytes = (size_t)kFStages * kFStageBytes + kFHelperBytes + sizeof(FusedSmem);
+
+struct FusedArgs {
+    const uint8_t* frames;
+    const StackDev* stacks;
+    StackJob* jobs;
+    uint32_t n;
+    uint32_t n_lb_items;  // 8 per stack (letterbox cropdetect: the kernel scans, crops and builds the jobs), 0: jobs are built already
+    uint32_t* sides;      // [n][2][4]
+    uint32_t* crop;       // [n][4]
+    const CoefRef* coef_lut;
+    const BFragRef* bfrag_lut;
+    uint32_t* miss;
+    uint32_t* n_miss;
+    // control block, zeroed before the launch: ctl[0] frames claimed, [1] letterbox items claimed, [2] letterbox items finished,
+    // [3] DCT tickets taken, [4] DCT items pushed, [5] stacks this launch will not hash, [6] a wait timed out (error),
+    // [7] walk tickets taken, [12] walk items pushed, [13] strip-0 items finished; [8]-[11] statistics
+    uint32_t* ctl;
+    uint32_t* flags;       // [n] job of stack s is published
+    uint32_t* sides_done;  // [n]
+    uint32_t* done;        // [n] frames of stack s whose 16 x 16 bytes are in `small` (fused kernel) / thread blocks done (per-frame kernels)
+    uint32_t* dq;          // [n] DCT queue: stack + 1
+    uint32_t* wq;          // [8 n] letterbox walk queue: side item + 1
+    uint8_t* small;
+    uint32_t* out_hash;    // nullptr: no DCT here (context option hash_fuse_dct = 0)
+    uint32_t exp;          // experiment bits (VDF_FUSED_EXP, timing studies only -- results are wrong): 1 no contraction, 2 one consumer arrive
+};
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void imma_s8u8(int32_t (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void imma_u8u8v(int32_t (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr uint64_t kFWaitNs = 8ull * 1000 * 1000 * 1000;  // no wait in the kernel is for more than one letterbox item or one launch
+
+// ---- helper group: letterbox items, job building, DCT items (threads 256..383)
+__device__ __forceinline__ void fused_publish_job(const FusedArgs& a, uint32_t s) {  // one thread
+    const StackDev d = a.stacks[s];
+    uint32_t out[4] = {0, 0, 0, 0};
+    if (d.status == VDF_STACK_OK) {  // crop_combine_kernel's rule for frames 0 and 8
+        const int W = (int)d.width, H = (int)d.height;
+        for (uint32_t fr = 0; fr < 2; ++fr) {
+            uint32_t c[4];
+            for (int k = 0; k < 4; ++k) c[k] = __ldcg(&a.sides[((size_t)s * 2 + fr) * 4 + k]);
+            if (!(W - (int)c[0] - (int)c[1] >= 1 && H - (int)c[2] - (int)c[3] >= 1)) c[0] = c[1] = c[2] = c[3] = 0;
+            for (int k = 0; k < 4; ++k) out[k] = fr == 0 ? c[k] : min(out[k], c[k]);
+        }
+    }
+    for (int k = 0; k < 4; ++k) a.crop[(size_t)s * 4 + k] = out[k];
+    bool missed;
+    const StackJob j = make_job(d, out, a.coef_lut, a.bfrag_lut, 0xFFFFFFFFu, 0xFFFFFFFFu, true, &missed);
+    if (d.status == VDF_STACK_OK) a.miss[s] = missed ? 1u : 0u;
+    if (missed) atomicAdd(a.n_miss, 1u);
+    a.jobs[s] = j;
+    if (!(j.status == VDF_STACK_OK && j.fast)) atomicAdd(&a.ctl[5], 1u);
+    __threadfence();
+    atomicExch(&a.flags[s], 1u);
+}
+
+__device__ __forceinline__ void fused_helper(const FusedArgs& a, uint8_t* arena, FusedSmem& fs, uint64_t t_start) {
+    constexpr int NT = 128, BAR = 2;
+    LbShared& sh = *reinterpret_cast<LbShared*>(arena);
+    const int gtid = threadIdx.x - kFConsThreads - kFProdThreads;
+    auto finish_side = [&](uint32_t b, uint32_t count) {  // one thread
+        const uint32_t s = b >> 3;
+        a.sides[b] = count;
+        __threadfence();
+        if (atomicAdd(&a.sides_done[s], 1u) == 7u) {
+            __threadfence();
+            fused_publish_job(a, s);
+        }
+        __threadfence();
+        atomicAdd(&a.ctl[2], 1u);
+    };
+    // ---- letterbox items.  Two kinds.  "Strip 0 of all eight sides of stack s" (frames 0 and 8 x left, right, top, bottom), claimed in
+    // order: every load of the item is in flight at once -- one round trip to memory -- and a stack with no bar at all (most) is
+    // published right there, so nearly all of the pixel work is available within the first microseconds of the launch.  A side whose
+    // strip 0 is letterbox is queued as a "walk side b inwards, panel after panel" item; groups take walks once the stack items are
+    // all claimed, and the last walk of a stack publishes it.  Neither kind ever waits for anything.
+    const uint32_t n_stack_items = a.n_lb_items / 8u;
+    for (; a.n_lb_items;) {
+        group_sync<BAR, NT>();
+        if (gtid == 0) {
+            uint32_t item = 0;  // 0: nothing left; (s + 1): strip 0 of stack s; 0x80000000 | (b + 1): walk side b
+            for (;;) {
+                if (ld_volatile_u32(&a.ctl[1]) < n_stack_items) {
+                    const uint32_t s = atomicAdd(&a.ctl[1], 1u);
+                    if (s < n_stack_items) {
+                        item = s + 1u;
+                        break;
+                    }
+                }
+                const uint32_t head = ld_volatile_u32(&a.ctl[7]);
+                if (head < ld_acquire_u32(&a.ctl[12])) {
+                    if (atomicCAS(&a.ctl[7], head, head + 1u) != head) continue;
+                    uint32_t v;
+                    while (!(v = ld_volatile_u32(&a.wq[head]))) {}  // the pusher is between its two instructions
+                    item = 0x80000000u | v;
+                    break;
+                }
+                if (ld_acquire_u32(&a.ctl[13]) >= n_stack_items && ld_volatile_u32(&a.ctl[7]) >= ld_volatile_u32(&a.ctl[12])) break;  // all found, all taken
+                __nanosleep(200);
+            }
+            fs.h_bcast = item;
+        }
+        group_sync<BAR, NT>();
+        const uint32_t item = fs.h_bcast;
+        if (!item) break;
+        __threadfence();
+        if (!(item & 0x80000000u)) {
+            const uint32_t s = item - 1u;
+            const StackDev sd = a.stacks[s];
+            uint32_t bars = 0;  // bit (fr * 4 + side): strip 0 is letterbox
+            if (sd.status == VDF_STACK_OK) {
+                const uint32_t W = sd.width, H = sd.height, P = sd.pitch;
+                const uint8_t* f0 = a.frames + sd.offset;
+                uint32_t* hist8 = sh.hist;  // 8 x 256 counters
+                if (H <= NT * 9 && W <= NT * 16 && ((reinterpret_cast<uintptr_t>(f0) | P | sd.frame_stride) & 3) == 0) {
+                    for (int q = gtid; q < 8 * 256; q += NT) hist8[q] = 0;
+                    // columns: 9 pixels per thread and side; rows: 4 words per thread and side -- 52 loads in flight per thread
+                    uint32_t vc[4][9], vr[4][4];
+                    const uint32_t W4 = W >> 2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint8_t* img = f0 + (uint64_t)((k >> 1) * 8) * sd.frame_stride;
+                        const uint8_t* col = img + ((k & 1) ? W - 1 : 0u);
+#pragma unroll
+                        for (int u = 0; u < 9; ++u) vc[k][u] = gtid + NT * u < (int)H ? (uint32_t)__ldg(col + (uint64_t)(gtid + NT * u) * P) : 0x100u;
+                        const uint32_t* row4 = reinterpret_cast<const uint32_t*>(img + (uint64_t)((k & 1) ? H - 1 : 0u) * P);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) vr[k][u] = gtid + NT * u < (int)W4 ? __ldg(row4 + gtid + NT * u) : 0u;
+                    }
+                    group_sync<BAR, NT>();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t* hc = hist8 + ((k >> 1) * 4 + (k & 1)) * 256;      // side 0 / 1 of frame k >> 1
+                        uint32_t* hr = hist8 + ((k >> 1) * 4 + 2 + (k & 1)) * 256;  // side 2 / 3
+#pragma unroll
+                        for (int u = 0; u < 9; ++u)
+                            if (vc[k][u] < 0x100u) atomicAdd(&hc[vc[k][u]], 1u);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (gtid + NT * u < (int)W4) {
+                                atomicAdd(&hr[vr[k][u] & 255u], 1u);
+                                atomicAdd(&hr[(vr[k][u] >> 8) & 255u], 1u);
+                                atomicAdd(&hr[(vr[k][u] >> 16) & 255u], 1u);
+                                atomicAdd(&hr[vr[k][u] >> 24], 1u);
+                            }
+                        if (gtid < (int)(W & 3u)) {  // the <= 3 pixels after the last whole word of the row
+                            const uint8_t* img = f0 + (uint64_t)((k >> 1) * 8) * sd.frame_stride;
+                            atomicAdd(&hr[__ldg(img + (uint64_t)((k & 1) ? H - 1 : 0u) * P + (W4 << 2) + gtid)], 1u);
+                        }
+                    }
+                    if (gtid == 0) fs.h_flag = 0;
+                    group_sync<BAR, NT>();
+                    const int warp = gtid >> 5, lane = gtid & 31;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k8 = warp * 2 + e;  // fr * 4 + side
+                        const bool ok = strip_is_letterbox(hist8 + k8 * 256, (k8 & 2) ? W : H, lane);
+                        if (ok && lane == 0) atomicOr(&fs.h_flag, 1u << k8);
+                    }
+                    group_sync<BAR, NT>();
+                    bars = fs.h_flag;
+                } else {  // large or unaligned frames: side after side
+                    for (uint32_t k8 = 0; k8 < 8; ++k8) {
+                        const uint8_t* img = f0 + (uint64_t)((k8 >> 2) * 8) * sd.frame_stride;
+                        if (lb_strip0<false, NT, BAR>(sh.hist, &fs.h_flag, nullptr, img, W, H, P, k8 & 3)) bars |= 1u << k8;
+                        group_sync<BAR, NT>();
+                    }
+                }
+            }
+            if (gtid == 0) {
+                if (!bars) {
+                    for (uint32_t k8 = 0; k8 < 8; ++k8) a.sides[s * 8 + k8] = 0u;
+                    __threadfence();
+                    fused_publish_job(a, s);
+                    __threadfence();
+                    atomicAdd(&a.ctl[2], 8u);
+                } else {
+                    for (uint32_t k8 = 0; k8 < 8; ++k8)
+                        if (!(bars >> k8 & 1u)) a.sides[s * 8 + k8] = 0u;
+                    atomicExch(&a.sides_done[s], 8u - (uint32_t)__popc(bars));  // the walks count the rest
+                    __threadfence();
+                    atomicAdd(&a.ctl[2], 8u - (uint32_t)__popc(bars));
+                    const uint32_t idx = atomicAdd(&a.ctl[12], (uint32_t)__popc(bars));
+                    uint32_t q = 0;
+                    for (uint32_t k8 = 0; k8 < 8; ++k8)
+                        if (bars >> k8 & 1u) atomicExch(&a.wq[idx + q++], s * 8 + k8 + 1u);
+                }
+                __threadfence();
+                atomicAdd(&a.ctl[13], 1u);
+            }
         } else {
-            miss[s] = 0;
-            j.bh = th.bounds, j.kh = th.k, j.win_h = th.window, j.prec_h = th.precision;
-            j.bv = tv.bounds, j.kv = tv.k, j.win_v = tv.window, j.prec_v = tv.precision;
-            if (fast) {
-                j.x0_al = j.left & ~15u;
-                j.n_kch = (shift + j.cw + kKch - 1) / kKch;
-                j.kb = bf.kb, j.kmask = bf.kmask;
-                j.fast = 1;
+            const uint32_t b = (item & 0x7FFFFFFFu) - 1u, side = b & 3, fr = (b >> 2) & 1, s = b >> 3;
+            const StackDev sd = a.stacks[s];
+            const uint8_t* img = a.frames + sd.offset + (uint64_t)(fr * 8) * sd.frame_stride;
+            const uint32_t limit = side < 2 ? sd.width : sd.height;
+            uint32_t first = kLbNone;
+            for (uint32_t base = 0; base < limit && first == kLbNone; base += kColPanel) {
+                lb_panel_flags<false, NT, BAR>(sh, img, sd.width, sd.height, sd.pitch, side, base);
+                if (gtid == 0) fs.h_bcast = lb_first_stop(sh, base, limit);
+                group_sync<BAR, NT>();
+                first = fs.h_bcast;
+                group_sync<BAR, NT>();
+            }
+            if (gtid == 0) finish_side(b, min(first, limit));
+        }
+    }
+    if (gtid == 0 && a.n_lb_items) atomicMax(&a.ctl[10], (uint32_t)((globaltimer_ns() - t_start) >> 10));  // statistics: end of the scan
+    if (!a.out_hash) return;
+    // ---- DCT items, by ticket
+    double* cube = reinterpret_cast<double*>(arena);
+    for (;;) {
+        group_sync<BAR, NT>();
+        if (gtid == 0) {
+            const uint32_t idx = atomicAdd(&a.ctl[3], 1u);
+            uint32_t v = 0;
+            const uint64_t t0 = globaltimer_ns();
+            for (uint32_t spin = 0;; ++spin) {
+                if (idx < a.n) v = ld_volatile_u32(&a.dq[idx]);
+                if (v) break;
+                if (ld_volatile_u32(&a.ctl[6])) break;
+                if (ld_acquire_u32(&a.ctl[2]) >= a.n_lb_items) {  // every job is built: the number of stacks to hash is final
+                    const uint32_t skipped = ld_volatile_u32(&a.ctl[5]);
+                    if (idx >= a.n - min(skipped, a.n)) break;
+                }
+                __nanosleep(400);
+                if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > 8 * kFWaitNs) {
+                    atomicExch(&a.ctl[6], 3u);
+                    break;
+                }
+            }
+            fs.h_bcast = v;
+        }
+        group_sync<BAR, NT>();
+        const uint32_t v = fs.h_bcast;
+        if (!v) break;
+        __threadfence();
+        dct_pack_block<NT, BAR>(a.small + (uint64_t)(v - 1) * 4096, cube, a.out_hash + (uint64_t)(v - 1) * 32, gtid);
+    }
+}
+
+// ---- scheduler: one lane.  Frames are claimed in order, but a frame whose stack's job is not published yet (its letterbox items
+// are still walking a bar) is put aside -- up to six per block -- and the next frame is claimed instead: nobody idles behind a slow scan.
+__device__ __forceinline__ void fused_scheduler(const FusedArgs& a, FusedSmem& fs) {
+    volatile uint32_t* v_pord = &fs.p_ord;
+    volatile uint32_t* v_abort = &fs.abort_all;
+    uint32_t cur_s = 0xFFFFFFFFu;
+    StackJob job;
+    memset(&job, 0, sizeof job);
+    job.status = kJobSkip;
+    const uint32_t total = a.n * 16u;
+    constexpr int kAside = 6;
+    uint32_t aside[kAside];
+    for (int q = 0; q < kAside; ++q) aside[q] = kFNoFrame;
+    bool exhausted = false;
+    uint32_t mask_s = 0xFFFFFFFFu;
+    unsigned long long cur_masks[kFSlotMasks / 8];
+    for (uint32_t j = 0;; ++j) {
+        // A claimed frame is a frame no other block can take: the next one is claimed only when the producers are past the middle of
+        // the current one (p_prog = 2 * ordinal + past-the-middle), early enough to hide this lane's few dependent round trips to memory
+        // and late enough that the blocks finish within half a frame of each other at the end of the launch.
+        const uint32_t gate = (a.exp & 8u) ? (j >= 2 ? 2u * j - 4u : 0u) : (a.exp & 4u) ? (j >= 1 ? 2u * j - 2u : 0u) : (j >= 1 ? 2u * j - 1u : 0u);
+        while (gate > *v_pord) {
+            if (*v_abort) return;
+            __nanosleep(200);
+        }
+        FrameSlot sl;
+        memset(&sl, 0, sizeof sl);
+        sl.out_idx = kFNoFrame;
+        uint64_t t0 = 0;
+        for (uint32_t spin = 0;;) {
+            uint32_t f = kFNoFrame;
+            int free_q = -1, n_aside = 0;
+#pragma unroll
+            for (int q = 0; q < kAside; ++q) {  // a frame put aside whose job has arrived in the meantime
+                if (aside[q] == kFNoFrame) {
+                    free_q = q;
+                    continue;
+                }
+                if (f == kFNoFrame && ((aside[q] >> 4) == cur_s || ld_acquire_u32(&a.flags[aside[q] >> 4]))) f = aside[q], aside[q] = kFNoFrame, free_q = q;
+                else ++n_aside;
+            }
+            const bool room = free_q >= 0;
+            if (f == kFNoFrame && !exhausted && room) {
+                f = atomicAdd(&a.ctl[0], 1u);
+                if (f >= total) {
+                    exhausted = true;
+                    continue;
+                }
+                if (!((f >> 4) == cur_s || ld_acquire_u32(&a.flags[f >> 4]))) {
+#pragma unroll
+                    for (int q = 0; q < kAside; ++q)
+                        if (q == free_q) aside[q] = f;
+                    continue;
+                }
+            }
+            if (f == kFNoFrame) {
+                if (exhausted && n_aside == 0) break;  // nothing left anywhere
+                if (spin == 0) t0 = globaltimer_ns();
+                __nanosleep(200);
+                if (ld_volatile_u32(&a.ctl[6]) || ((++spin & 1023u) == 0u && globaltimer_ns() - t0 > kFWaitNs)) {
+                    atomicExch(&a.ctl[6], 1u);
+                    break;
+                }
+                continue;
+            }
+            if (spin) atomicAdd(&a.ctl[8], (uint32_t)((globaltimer_ns() - t0) >> 10)), spin = 0;  // statistics: ~us with nothing ready
+            const uint32_t s = f >> 4;
+            if (s != cur_s) {
+                const volatile uint64_t* src = reinterpret_cast<const volatile uint64_t*>(&a.jobs[s]);  // written by another SM
+                uint64_t* dst = reinterpret_cast<uint64_t*>(&job);
+#pragma unroll
+                for (int q = 0; q < (int)(sizeof(StackJob) / 8); ++q) dst[q] = src[q];
+                cur_s = s;
+            }
+            if (job.status == VDF_STACK_OK && job.fast) {
+                const uint32_t t = f & 15u;
+                sl.img = a.frames + job.offset + (uint64_t)t * job.frame_stride + (uint64_t)job.top * job.pitch + job.x0_al;
+                sl.kb2 = job.kb2, sl.kva = job.kva;
+                sl.pitch = job.pitch, sl.ch = job.ch, sl.row_bytes = job.pitch - job.x0_al, sl.n_kc = job.n_kc2;
+                sl.n_rb = (job.ch + kFRows - 1) / kFRows, sl.prec_h = job.prec_h, sl.prec_v = job.prec_v;
+                sl.out_idx = f;
+                if (s != mask_s) {  // the table's masks (static data, 4096-byte aligned, followed by the kb2 blob): nine words, all in flight
+                    const bool have = job.n_kch <= (uint32_t)kFSlotMasks;
+                    const unsigned long long* km = reinterpret_cast<const unsigned long long*>(job.kmask);
+#pragma unroll
+                    for (int w = 0; w < kFSlotMasks / 8; ++w) cur_masks[w] = __ldg(km + w);
+#pragma unroll
+                    for (int w = 0; w < kFSlotMasks / 8; ++w) {
+                        const uint32_t left = job.n_kch > (uint32_t)(8 * w) ? job.n_kch - 8 * w : 0u;  // bytes of this word that are masks
+                        const unsigned long long keep = left >= 8 ? ~0ull : ((1ull << (8 * left)) - 1ull);
+                        cur_masks[w] = have ? (cur_masks[w] & keep) : ~0ull;
+                    }
+                    mask_s = s;
+                }
+#pragma unroll
+                for (int w = 0; w < kFSlotMasks / 8; ++w) sl.masks8[w] = cur_masks[w];
+                break;
+            }
+        }
+        fs.slots[j % kFSlots] = sl;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t*>(&fs.sched_count) = j + 1;
+        if (sl.out_idx == kFNoFrame) return;
+    }
+}
+
+// mbarrier helpers (shared::cta)
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+// this thread's arrival happens when all of its earlier cp.async copies have landed
+__device__ __forceinline__ void mbar_arrive_on_cp_async(uint64_t* b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
+            (uint32_t)__cvta_generic_to_shared(b)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---- finalizer (one warp): per finished frame, the sum of the eight consumer warps' vertical partial sums -> round, shift, clamp ->
+// 256 bytes of the stack's 16 x 16 x 16 cube in global memory; the stack's sixteenth frame goes onto the helpers' DCT queue.
+__device__ __forceinline__ void fused_finalizer(const FusedArgs& a, FusedSmem& fs) {
+    const int lane = threadIdx.x & 31;
+    volatile uint32_t* v_stop = &fs.fin_stop;
+    for (uint32_t ord = 0;; ++ord) {
+        const uint32_t b = ord & 1u, parity = (ord >> 1) & 1u;
+        // wait for frame `ord` or for the end
+        for (;;) {
+            uint32_t ready;
+            asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ready)
+                         : "r"((uint32_t)__cvta_generic_to_shared(&fs.fin_full[b])), "r"(parity)
+                         : "memory");
+            if (ready) break;
+            const uint32_t stop = *v_stop;
+            if (stop && ord + 1u >= stop) return;
+            if (*reinterpret_cast<volatile uint32_t*>(&fs.abort_all)) return;
+            __nanosleep(100);
+        }
+        const uint32_t out = fs.fin_out[b], prec = fs.fin_prec[b];
+        int32_t* vr = fs.vred[b];
+        const int32_t init_v = 1 << (prec - 1);
+        uint32_t w[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int4 v = *reinterpret_cast<const int4*>(vr + lane * 8 + h * 4);
+            *reinterpret_cast<int4*>(vr + lane * 8 + h * 4) = make_int4(0, 0, 0, 0);
+            w[h] = (uint32_t)clip8(v.x + init_v, prec) | ((uint32_t)clip8(v.y + init_v, prec) << 8) | ((uint32_t)clip8(v.z + init_v, prec) << 16) |
+                   ((uint32_t)clip8(v.w + init_v, prec) << 24);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&fs.fin_empty[b]);
+        *reinterpret_cast<uint2*>(a.small + (uint64_t)out * 256 + lane * 8) = make_uint2(w[0], w[1]);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t s = out >> 4;
+            if (atomicAdd(&a.done[s], 1u) == 15u && a.out_hash) {
+                __threadfence();
+                const uint32_t idx = atomicAdd(&a.ctl[4], 1u);
+                atomicExch(&a.dq[idx], s + 1u);
             }
         }
     }
-    jobs[s] = j;
+}
+
+// ---- producer group (threads 256..383): the cp.async side of the ring.  It may sit in a blocked copy instruction for as long as the
+// memory system likes (that is what back-pressure looks like) without holding up a single tensor instruction of the consumers.
+__device__ __forceinline__ void fused_producer(const FusedArgs& a, uint8_t* ring, FusedSmem& fs) {
+    constexpr int NT = kFProdThreads;
+    const int tid = threadIdx.x - kFConsThreads;
+    volatile uint32_t* v_sched = &fs.sched_count;
+    // 16 threads x 16 bytes cover a 256-byte row segment, 8 rows per pass, 16 passes per tile
+    const uint32_t c16 = (tid & 15) * 16, r0 = tid >> 4;
+    uint32_t stage = 0, empty_parity = 1;  // a fresh mbarrier passes a wait on the phase before its first
+    for (uint32_t ord = 0;; ++ord) {
+        const uint64_t t0 = globaltimer_ns();
+        uint32_t spin = 0;
+        for (; *v_sched <= ord; ++spin) {
+            __nanosleep(40);
+            if ((spin & 4095u) == 4095u && globaltimer_ns() - t0 > 2 * kFWaitNs) {
+                atomicExch(&a.ctl[6], 2u);
+                fs.abort_all = 1;
+                return;
+            }
+        }
+        if (spin && tid == 0) atomicAdd(&a.ctl[ord == 0 ? 14 : 9], (uint32_t)((globaltimer_ns() - t0) >> 10));  // statistics: ~us the ring waited for its first / a later slot
+        __threadfence_block();
+        const FrameSlot& sl = fs.slots[ord % kFSlots];
+        if (sl.out_idx == kFNoFrame) return;
+        const uint8_t* img = sl.img;
+        const uint8_t* kb2 = sl.kb2;
+        const uint8_t* pm = sl.masks;
+        // this thread's four coefficient copies of a tile are all of one n-tile = one octet of outputs: ((tid >> 4) & 1); copies q = 0, 1
+        // belong to the tile's first 128-pixel half, q = 2, 3 to the second
+        const uint32_t oct_bits = 0x55u << ((tid >> 4) & 1);
+        const uint32_t n_kc = sl.n_kc, n_rb = sl.n_rb, ch = sl.ch, row_bytes = sl.row_bytes;
+        const uint64_t row_step = (uint64_t)8 * sl.pitch;
+        if (tid == 0) *reinterpret_cast<volatile uint32_t*>(&fs.p_ord) = 2u * ord + (n_rb < 2u ? 1u : 0u);
+        const uint8_t* g_rb = img + (uint64_t)r0 * sl.pitch + c16;
+        for (uint32_t rb = 0; rb < n_rb; ++rb, g_rb += 16 * row_step) {
+            if (tid == 0 && rb == n_rb / 2 && rb) *reinterpret_cast<volatile uint32_t*>(&fs.p_ord) = 2u * ord + 1u;
+            for (uint32_t kc = 0; kc < n_kc; ++kc) {
+                mbar_wait(&fs.empty[stage], empty_parity);
+                uint8_t* st = ring + (size_t)stage * kFStageBytes;
+                const bool xok = kc * kFCols + c16 < row_bytes;
+                const uint8_t* g = g_rb + kc * kFCols;
+                uint32_t row = rb * kFRows + r0;
+                uint8_t* d = st + r0 * kFPitch + c16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const bool ok = xok && row < ch;
+                    cp_async16(d + i * 8 * kFPitch, ok ? g : img, ok ? 16u : 0u);
+                    g += row_step;
+                    row += 8;
+                }
+                const uint8_t* csrc = kb2 + (size_t)kc * kFCoefBytes + tid * 16;
+                uint8_t* cdst = st + kFRows * kFPitch + tid * 16;
+                const bool wide = 2 * kc + 1 >= (uint32_t)kFSlotMasks;
+                const bool need0 = wide || (pm[2 * kc] & oct_bits), need1 = wide || (pm[2 * kc + 1] & oct_bits);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < 2 ? need0 : need1) cp_async16(cdst + q * NT * 16, csrc + q * NT * 16, 16u);
+                if (tid == 0) cp_async16(cdst + 4 * NT * 16, csrc + 4 * NT * 16, 16u);  // the header
+                mbar_arrive_on_cp_async(&fs.full[stage]);
+                if (++stage == kFStages) stage = 0, empty_parity ^= 1u;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFThreads, 1) hash_fused_kernel(const FusedArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_dyn[];
+    uint8_t* ring = smem_dyn;
+    uint8_t* arena = smem_dyn + (size_t)kFStages * kFStageBytes;
+    FusedSmem& fs = *reinterpret_cast<FusedSmem*>(arena + kFHelperBytes);
+    const int tid = threadIdx.x;
+    const uint64_t t_start = globaltimer_ns();
+    for (int q = tid; q < 512; q += kFThreads) (&fs.vred[0][0])[q] = 0;
+    if (tid == 0) {
+        fs.sched_count = 0, fs.p_ord = 0, fs.abort_all = 0;
+        for (int s = 0; s < kFStages; ++s) mbar_init(&fs.full[s], kFProdThreads), mbar_init(&fs.empty[s], kFConsThreads / 32);
+        for (int s = 0; s < 2; ++s) mbar_init(&fs.fin_full[s], kFConsThreads / 32), mbar_init(&fs.fin_empty[s], 1);
+        fs.fin_stop = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid >= kFConsThreads + kFProdThreads + kFHelpThreads + 32) {
+        fused_finalizer(a, fs);
+        return;
+    }
+    if (tid >= kFConsThreads + kFProdThreads + kFHelpThreads) {
+        if (tid == kFConsThreads + kFProdThreads + kFHelpThreads) fused_scheduler(a, fs);
+        return;
+    }
+    if (tid >= kFConsThreads + kFProdThreads) {
+        fused_helper(a, arena, fs, t_start);
+        return;
+    }
+    if (tid >= kFConsThreads) {
+        fused_producer(a, ring, fs);
+        return;
+    }
+    // ------------------------------------------------------------------------------------------------ consumer group
+    const int lane = tid & 31, warp = tid >> 5;
+    volatile uint32_t* v_sched = &fs.sched_count;
+    // warp w owns rows 16 w .. 16 w + 15 of every tile (one m16 tile), all sixteen outputs x {high, low} coefficient bytes
+    int32_t acc[4][4], vacc[2][2][4];
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int z = 0; z < 4; ++z) acc[y][z] = 0;
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y)
+#pragma unroll
+            for (int z = 0; z < 4; ++z) vacc[x][y][z] = 0;
+    const uint32_t lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lbyte = (lane >> 4) * 16;
+    const uint32_t a_off = (warp * 16 + lrow) * kFPitch + lbyte;
+    const uint32_t g = lane >> 2, q4 = lane & 3, q2 = q4 * 2;
+    uint8_t* tw = fs.tmpT[warp];
+
+    uint32_t c_ord = 0, c_kc = 0, c_rb = 0, c_stage = 0, full_parity = 0;
+    uint32_t c_nkc = 0, c_nrb = 0, c_prec_h = 0, c_prec_v = 0, c_out = kFNoFrame;
+    const uint4* c_kva = nullptr;
+    auto c_take_slot = [&]() {
+        const uint64_t t0 = globaltimer_ns();
+        for (uint32_t spin = 0; *v_sched <= c_ord; ++spin) {  // only the first frame can make the consumers wait: the producers go first
+            __nanosleep(40);
+            if ((spin & 4095u) == 4095u && globaltimer_ns() - t0 > 2 * kFWaitNs) {
+                c_out = kFNoFrame;
+                return;
+            }
+        }
+        __threadfence_block();
+        const FrameSlot& sl = fs.slots[c_ord % kFSlots];
+        c_out = sl.out_idx;
+        c_nkc = sl.n_kc, c_nrb = sl.n_rb, c_prec_h = sl.prec_h, c_prec_v = sl.prec_v, c_kva = sl.kva;
+        c_kc = 0, c_rb = 0;
+    };
+    c_take_slot();
+
+    while (c_out != kFNoFrame) {
+        mbar_wait(&fs.full[c_stage], full_parity);
+        const uint8_t* st = ring + (size_t)c_stage * kFStageBytes;
+        const uint8_t* coef = st + kFRows * kFPitch;
+        const uint32_t masks = *reinterpret_cast<const uint32_t*>(coef + 2 * kBFragBytes);
+        const bool last_kc = c_kc + 1 == c_nkc;
+        uint4 va_h = make_uint4(0, 0, 0, 0), va_l = make_uint4(0, 0, 0, 0);
+        if (last_kc) {  // the vertical k-step's A fragments: in flight under the row block's last contraction
+            const uint4* p = c_kva + ((size_t)(c_rb * 4 + (warp >> 1)) * 2) * 32 + lane;
+            va_h = __ldg(p), va_l = __ldg(p + 32);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint8_t* arow = st + a_off + h * kKch;
+            const uint2* sb = reinterpret_cast<const uint2*>(coef + h * kBFragBytes);
+            const uint32_t tapmask = (a.exp & 1u) ? 0u : (masks >> (8 * h)) & 0xFFu;
+            const bool lo_oct = (tapmask & 0x55u) != 0, hi_oct = (tapmask & 0xAAu) != 0;
+            if (lo_oct && hi_oct) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t a0[4];
+                    ldmatrix_x4(a0, arow + ks * 32);
+                    const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b1 = sb[(ks * 4 + 1) * 32 + lane];
+                    const uint2 b2 = sb[(ks * 4 + 2) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
+                    imma_u8s8(acc[0], a0, b0);
+                    imma_u8s8(acc[1], a0, b1);
+                    imma_u8u8(acc[2], a0, b2);
+                    imma_u8u8(acc[3], a0, b3);
+                }
+            } else if (lo_oct) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t a0[4];
+                    ldmatrix_x4(a0, arow + ks * 32);
+                    const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b2 = sb[(ks * 4 + 2) * 32 + lane];
+                    imma_u8s8(acc[0], a0, b0);
+                    imma_u8u8(acc[2], a0, b2);
+                }
+            } else if (hi_oct) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t a0[4];
+                    ldmatrix_x4(a0, arow + ks * 32);
+                    const uint2 b1 = sb[(ks * 4 + 1) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
+                    imma_u8s8(acc[1], a0, b1);
+                    imma_u8u8(acc[3], a0, b3);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&fs.empty[c_stage]);  // this warp has read everything it needs from the stage
+        if (++c_stage == kFStages) c_stage = 0, full_parity ^= 1u;
+        if (last_kc) {
+            // row block finished: k = 256 kh + kl, round, shift, clamp -> the u8 intermediate of this warp's 16 rows, transposed
+            const int32_t round_h = 1 << (c_prec_h - 1);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t row = half * 8 + g;
+#pragma unroll
+                for (int oct = 0; oct < 2; ++oct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int32_t v = acc[oct][half * 2 + e] * 256 + acc[2 + oct][half * 2 + e] + round_h;
+                        tw[(oct * 8 + q2 + e) * kFTmpPitch + row] = clip8(v, c_prec_h);
+                    }
+            }
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int z = 0; z < 4; ++z) acc[y][z] = 0;
+            __syncwarp();
+            // half a k-step (these 16 rows; the other half of the B fragment is zero: the pair's other warp adds it) of the vertical
+            // pass: out[oy][ox] += sum_y kv[oy][y] * tmp[y][ox]
+            const uint32_t ah[4] = {va_h.x, va_h.y, va_h.z, va_h.w}, al[4] = {va_l.x, va_l.y, va_l.z, va_l.w};
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const uint32_t bw = *reinterpret_cast<const uint32_t*>(tw + (nt * 8 + g) * kFTmpPitch + 4 * q4);
+                const uint32_t b0 = (warp & 1) ? 0u : bw, b1 = (warp & 1) ? bw : 0u;
+                imma_s8u8(vacc[nt][0], ah, b0, b1);
+                imma_u8u8v(vacc[nt][1], al, b0, b1);
+            }
+            __syncwarp();
+            c_kc = 0;
+            if (++c_rb == c_nrb) {  // frame finished: the eight warps' vertical sums meet in shared memory
+                int32_t* vr = fs.vred[c_ord & 1];
+                mbar_wait(&fs.fin_empty[c_ord & 1], ((c_ord >> 1) & 1u) ^ 1u);  // the finalizer is done with frame c_ord - 2 (passes at once, normally)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int32_t v = vacc[nt][0][half * 2 + e] * 256 + vacc[nt][1][half * 2 + e];
+                            atomicAdd(&vr[(g + half * 8) * 16 + nt * 8 + q2 + e], v);
+                            vacc[nt][0][half * 2 + e] = 0, vacc[nt][1][half * 2 + e] = 0;
+                        }
+                // the finalizer warp clamps, stores and counts: no barrier and no memory fence on the consumers' path
+                if (tid == 0) fs.fin_out[c_ord & 1] = c_out, fs.fin_prec[c_ord & 1] = c_prec_v;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&fs.fin_full[c_ord & 1]);
+                ++c_ord;
+                c_take_slot();
+            }
+        } else {
+            ++c_kc;
+        }
+    }
+    if (tid == 0) {
+        atomicAdd(&a.ctl[11], (uint32_t)((globaltimer_ns() - t_start) >> 10));  // statistics
+        *reinterpret_cast<volatile uint32_t*>(&fs.fin_stop) = c_ord + 1u;      // every thread has the same c_ord: frames this block finished
+    }
 }
 
 // ================================================================================ host side
@@ -1145,7 +1950,32 @@ static int get_table(vdf_ctx* ctx, uint32_t in_size, const CoefTable** out) {
         VDF_ALLOC(ctx, cudaMalloc(&t.d_k, t.h_k.size() * 2));
         VDF_CUDA(ctx, cudaMemcpyAsync(t.d_bounds, t.h_bounds.data(), t.h_bounds.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         VDF_CUDA(ctx, cudaMemcpyAsync(t.d_k, t.h_k.data(), t.h_k.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
-        const CoefRef ref{t.d_bounds, t.d_k, t.window, t.precision};
+        // the same table as A fragments of mma.m16n8k32 for the fused kernel's vertical pass: [32-row k-step][hi, lo][lane] -> (a0..a3);
+        // a0 = rows g, k 4q..4q+3; a1 = rows g+8; a2, a3 = the same at k + 16 (g = lane / 4, q = lane % 4); zero outside the window,
+        // k-steps padded to whole 128-row blocks
+        {
+            const uint32_t n_vk = (in_size + 127) / 128 * 4;
+            std::vector<uint32_t> va((size_t)n_vk * 2 * 32 * 4);
+            for (uint32_t vk = 0; vk < n_vk; ++vk)
+                for (uint32_t hl = 0; hl < 2; ++hl)
+                    for (uint32_t lane = 0; lane < 32; ++lane)
+                        for (uint32_t reg = 0; reg < 4; ++reg) {
+                            const uint32_t o = lane / 4 + (reg & 1) * 8, kbase = vk * 32 + (reg >> 1) * 16 + (lane % 4) * 4;
+                            const uint32_t start = t.h_bounds[2 * o], size = t.h_bounds[2 * o + 1];
+                            uint32_t word = 0;
+                            for (uint32_t i = 0; i < 4; ++i) {
+                                const uint32_t y = kbase + i;
+                                int k = 0;
+                                if (y >= start && y < start + size) k = t.h_k[(size_t)o * t.window + (y - start)];
+                                word |= (hl == 0 ? (uint32_t)((k >> 8) & 0xFF) : (uint32_t)(k & 0xFF)) << (8 * i);
+                            }
+                            va[(((size_t)vk * 2 + hl) * 32 + lane) * 4 + reg] = word;
+                        }
+            VDF_ALLOC(ctx, cudaMalloc(&t.d_kva, va.size() * 4));
+            VDF_CUDA(ctx, cudaMemcpyAsync(t.d_kva, va.data(), va.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `va` goes out of scope
+        }
+        const CoefRef ref{t.d_bounds, t.d_k, t.window, t.precision, reinterpret_cast<const uint4*>(t.d_kva)};
         VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_coef_lut.as<CoefRef>() + in_size, &ref, sizeof ref, cudaMemcpyHostToDevice, ctx->stream));
         VDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors may move when the map rebalances
         it = ctx->coef_cache.emplace(in_size, std::move(t)).first;
@@ -1159,6 +1989,7 @@ void free_coef_cache(vdf_ctx* ctx) {
         if (kv.second.d_bounds) cudaFree(kv.second.d_bounds);
         if (kv.second.d_k) cudaFree(kv.second.d_k);
         if (kv.second.d_kb) cudaFree(kv.second.d_kb);
+        if (kv.second.d_kva) cudaFree(kv.second.d_kva);
     }
     ctx->coef_cache.clear();
     for (auto& kv : ctx->bfrag_cache) cudaFree(kv.second);
@@ -1206,10 +2037,25 @@ static int get_bfrags(vdf_ctx* ctx, const CoefTable& t, uint32_t shift, const ui
                               frag[(((size_t)ks * 4 + 2 + oct) * 32 + lane) * 2 + reg] != 0;
                 if (any || dense) masks[ks / 4] |= (uint8_t)(1u << (2 * (ks % 4) + oct));
             }
+        // the fused kernel's form, behind the masks (16-byte aligned): per 256-pixel chunk the fragments of its two 128-pixel halves
+        // (zeros beyond the last one) and a 16-byte header {mask of half 0, mask of half 1, 0...}
+        const std::vector<uint8_t> mask_copy(masks, masks + n_kch);  // `masks` points into `frag`, which is about to grow
+        const size_t kb2_word0 = (frag.size() + 3) / 4 * 4, n_kc2 = (n_kch + 1) / 2;
+        frag.resize(kb2_word0 + n_kc2 * (kFCoefBytes / 4), 0u);
+        for (size_t c = 0; c < n_kc2; ++c) {
+            uint32_t* dst = frag.data() + kb2_word0 + c * (kFCoefBytes / 4);
+            for (uint32_t h = 0; h < 2; ++h) {
+                const size_t kc = 2 * c + h;
+                if (kc >= n_kch) continue;
+                std::memcpy(dst + h * (kBFragBytes / 4), frag.data() + kc * (kBFragBytes / 4), kBFragBytes);
+                reinterpret_cast<uint8_t*>(dst + 2 * (kBFragBytes / 4))[h] = mask_copy[kc];
+            }
+        }
         void* d = nullptr;
         VDF_ALLOC(ctx, cudaMalloc(&d, frag.size() * 4));
         VDF_CUDA(ctx, cudaMemcpyAsync(d, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        const BFragRef ref{reinterpret_cast<const uint2*>(d), reinterpret_cast<const uint8_t*>(d) + (size_t)n_kch * kBFragBytes};
+        const BFragRef ref{reinterpret_cast<const uint2*>(d), reinterpret_cast<const uint8_t*>(d) + (size_t)n_kch * kBFragBytes,
+                           reinterpret_cast<const uint8_t*>(d) + kb2_word0 * 4};
         VDF_TRY(ensure_luts(ctx));
         VDF_CUDA(ctx, cudaMemcpyAsync(ctx->h_bfrag_lut.as<BFragRef>() + (size_t)t.in_size * 16 + shift, &ref, sizeof ref, cudaMemcpyHostToDevice,
                                       ctx->stream));
@@ -1266,6 +2112,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     const bool four_warps = ctx->hash_variant != 2;  // default: 4 warps, two CTAs per SM
     const size_t ring = four_warps ? ResizeMma<4>::kRingBytes : ResizeMma<8>::kRingBytes;
     const bool allow_fast = ctx->hash_variant != 1;
+    const bool use_fused = allow_fast && ctx->hash_variant == 0 && ctx->hash_fused != 0;  // the fused kernel has no size limits of its own
     // status per stack, decided on the host exactly where the reference decides it; tables of the UNCROPPED sizes are made
     // sure of here (most stacks have no bars), every other size is met through a miss
     VDF_ALLOC(ctx, ctx->pin_b.ensure((size_t)n * (sizeof(StackDev) + 4 + 4)));
@@ -1298,7 +2145,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
             VDF_TRY(get_table(ctx, d.height, &tv));
             const bool fits = (15 + d.width + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring;  // a crop only shrinks both
             all_fit &= fits;
-            if (aligned && fits && allow_fast) {
+            if (aligned && (fits || use_fused) && allow_fast) {
                 const uint2* kb;
                 const uint8_t* km;
                 VDF_TRY(get_bfrags(ctx, *th, 0, &kb, &km));
@@ -1307,7 +2154,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         }
     }
     const size_t tmp_bytes = (size_t)max_h * 16;
-    if (tmp_bytes + ring > 220 * 1024) {
+    if (tmp_bytes + ring > 220 * 1024 && !(use_fused && !any_unaligned)) {
         ctx->err = "frame height beyond the resize kernels' shared-memory budget";
         return VDF_ERR_INVALID;
     }
@@ -1352,7 +2199,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         }
         ctx->hash_smem_set[0] = least;
     }
-    if (tmp_bytes + ring > ctx->hash_smem_set[0] || gen_smem > ctx->hash_smem_set[0]) {
+    if ((tmp_bytes + ring > ctx->hash_smem_set[0] || gen_smem > ctx->hash_smem_set[0]) && !(use_fused && !any_unaligned)) {
         ctx->err = "frame height beyond the resize kernels' shared-memory budget";
         return VDF_ERR_INVALID;
     }
@@ -1365,7 +2212,9 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     auto chunk_begin = [&](uint32_t k) { return (uint32_t)((uint64_t)n * k / n_chunks); };
     const bool letterbox = cropdetect == VDF_CROPDETECT_LETTERBOX;
     cudaStream_t lb = ctx->hash_overlap ? ctx->lb_stream : st;
-    if (letterbox) {
+    if (letterbox && use_fused) {
+        // the fused kernel scans
+    } else if (letterbox) {
         if (any_bad) VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_sides.p, 0, (size_t)n * 8 * 4, st));  // the scan writes every side of every good stack
         if (lb != st) {
             VDF_CUDA(ctx, cudaEventRecord(ctx->ev_in, st));
@@ -1388,7 +2237,43 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     } else {
         VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_crop.p, 0, (size_t)n * 16, st));  // Cropdetect::None: zero crop (:195-199)
     }
+    // ---- default: ONE persistent launch per pass (hash_fused_kernel) does the scan, the crops, the jobs, the resize and the DCT
+    uint32_t* d_ctl = nullptr;
+    if (use_fused) {
+        VDF_ALLOC(ctx, ctx->h_fctl.ensure((16 + 11 * (size_t)n) * 4));
+        d_ctl = ctx->h_fctl.as<uint32_t>();
+        if (!ctx->hash_smem_set[1]) {
+            VDF_CUDA(ctx, cudaFuncSetAttribute((const void*)hash_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
+            ctx->hash_smem_set[1] = kFusedSmemBytes;
+        }
+    }
+    auto run_fused = [&](bool only_missed, bool scan_in_kernel) -> int {
+        VDF_CUDA(ctx, cudaMemsetAsync(d_ctl, 0, (16 + (scan_in_kernel ? 11 : 3) * (size_t)n) * 4, st));
+        FusedArgs fa;
+        fa.frames = d_frames, fa.stacks = d_sd, fa.jobs = d_jobs, fa.n = n, fa.n_lb_items = scan_in_kernel ? n * 8u : 0u;
+        fa.sides = ctx->h_sides.as<uint32_t>(), fa.crop = ctx->h_crop.as<uint32_t>();
+        fa.coef_lut = ctx->h_coef_lut.as<CoefRef>(), fa.bfrag_lut = ctx->h_bfrag_lut.as<BFragRef>();
+        fa.miss = d_miss, fa.n_miss = d_nmiss;
+        fa.ctl = d_ctl, fa.flags = d_ctl + 16, fa.sides_done = d_ctl + 16 + n, fa.dq = d_ctl + 16 + 2 * (size_t)n, fa.wq = d_ctl + 16 + 3 * (size_t)n;
+        fa.done = d_done, fa.small = d_small, fa.out_hash = d_hash32;
+        fa.exp = getenv("VDF_FUSED_EXP") ? (uint32_t)atoi(getenv("VDF_FUSED_EXP")) : 0u;
+        if (!only_missed) kt_begin(ctx, 1);
+        if (!scan_in_kernel) {  // crops known up front (Cropdetect::None / Motion, or the pass for the sizes met for the first time)
+            job_build_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_sd, ctx->h_crop.as<uint32_t>(), n, fa.coef_lut, fa.bfrag_lut, 0xFFFFFFFFu, 0xFFFFFFFFu,
+                                                              1u, only_missed ? 1u : 0u, d_jobs, d_miss, d_nmiss, fa.flags, fa.ctl + 5);
+            VDF_LAUNCHED(ctx);
+        }
+        hash_fused_kernel<<<(unsigned)ctx->sm_count, kFThreads, kFusedSmemBytes, st>>>(fa);
+        VDF_LAUNCHED(ctx);
+        if (!only_missed) kt_end(ctx, 1);
+        if (any_unaligned) {  // stacks whose rows are not 16-byte aligned: the general kernel (it skips every job that is `fast`)
+            resize_general_kernel<<<n * 16, 256, gen_smem, st>>>(d_frames, d_jobs, d_small, d_done, d_hash32);
+            VDF_LAUNCHED(ctx);
+        }
+        return VDF_OK;
+    };
     auto run_pass = [&](bool only_missed) -> int {
+        if (use_fused) return run_fused(only_missed, letterbox && !only_missed);
         for (uint32_t k = 0; k < n_chunks; ++k) {
             const uint32_t s0 = chunk_begin(k), cnt = chunk_begin(k + 1) - s0;
             if (letterbox && !only_missed) {
@@ -1404,8 +2289,9 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
             }
             if (k == 0 && !only_missed) kt_begin(ctx, 1);
             job_build_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(d_sd + s0, ctx->h_crop.as<uint32_t>() + (size_t)s0 * 4, cnt,
-                                                                ctx->h_coef_lut.as<CoefRef>(), ctx->h_bfrag_lut.as<BFragRef>(), (uint32_t)ring,
-                                                                allow_fast ? 1u : 0u, only_missed ? 1u : 0u, d_jobs + s0, d_miss + s0, d_nmiss);
+                                                                ctx->h_coef_lut.as<CoefRef>(), ctx->h_bfrag_lut.as<BFragRef>(), (uint32_t)ring, 256u,
+                                                                allow_fast ? 1u : 0u, only_missed ? 1u : 0u, d_jobs + s0, d_miss + s0, d_nmiss,
+                                                                nullptr, nullptr);
             VDF_LAUNCHED(ctx);
             if (allow_fast) {
                 if (four_warps)
@@ -1441,7 +2327,18 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     uint32_t* h_n = reinterpret_cast<uint32_t*>(ctx->h_misc.as<unsigned long long>() + 24);
     VDF_CUDA(ctx, cudaMemcpyAsync(crop, ctx->h_crop.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
+    if (use_fused) VDF_CUDA(ctx, cudaMemcpyAsync(h_n + 1, d_ctl + 6, 4, cudaMemcpyDeviceToHost, st));
     VDF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (use_fused && h_n[1]) {
+        ctx->err = "hash_fused_kernel: a wait timed out (code " + std::to_string(h_n[1]) + ")";
+        return VDF_ERR_CUDA;
+    }
+    if (use_fused && getenv("VDF_FUSED_STATS")) {  // the kernel's own wait statistics (~us, summed over blocks)
+        uint32_t h_ctl[16];
+        VDF_CUDA(ctx, cudaMemcpy(h_ctl, d_ctl, sizeof h_ctl, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "fused stats: frames %u lb_items %u/%u dct %u/%u nofuse %u | wait_job_us %u wait_first_slot_us %u wait_slot_us %u scan_end_us %u pixel_life_us_sum %u\n", h_ctl[0],
+                h_ctl[1], h_ctl[2], h_ctl[3], h_ctl[4], h_ctl[5], h_ctl[8], h_ctl[14], h_ctl[9], h_ctl[10], h_ctl[11]);
+    }
     if (*h_n) {  // sizes met for the first time: build their tables (host, f64 + libm sin like the reference), run those stacks
         VDF_CUDA(ctx, cudaMemcpyAsync(h_miss, d_miss, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         VDF_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1453,7 +2350,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
             VDF_TRY(get_table(ctx, cw, &th));
             VDF_TRY(get_table(ctx, chh, &tv));
             const uint32_t shift = c[0] & 15u;
-            if (sd[s].aligned && allow_fast && (shift + cw + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring) {
+            if (sd[s].aligned && allow_fast && (use_fused || ((shift + cw + kKch - 1) / kKch <= 256 && (size_t)32 * tv->window <= ring))) {
                 const uint2* kb;
                 const uint8_t* km;
                 VDF_TRY(get_bfrags(ctx, *th, shift, &kb, &km));
@@ -1463,7 +2360,12 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         VDF_TRY(run_pass(true));
         VDF_TRY(separate_dct());
         VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
+        if (use_fused) VDF_CUDA(ctx, cudaMemcpyAsync(h_n + 1, d_ctl + 6, 4, cudaMemcpyDeviceToHost, st));
         VDF_CUDA(ctx, cudaStreamSynchronize(st));
+        if (use_fused && h_n[1]) {
+            ctx->err = "hash_fused_kernel: a wait timed out (code " + std::to_string(h_n[1]) + ")";
+            return VDF_ERR_CUDA;
+        }
         if (*h_n) {
             ctx->err = "resize tables still missing after the second pass";
             return VDF_ERR_CUDA;
