@@ -135,6 +135,64 @@ def test_letterbox_noisy_and_wide_bars(ctx):
     assert crops[0][2] >= 360 // 7 and crops[1][0] >= 640 // 8 and crops[2][0] > 200 and crops[3][2] == 40, crops
 
 
+def test_fused_kernel_machinery(ctx):
+    """hash_fused_kernel's own moving parts against the oracle: (a) 700 stacks of one-tile frames -- the producers run four frames ahead
+    of the consumers, the slot ring, the put-aside list, the double-buffered vertical sums and the finalizer all turn over every
+    few hundred cycles, several frames per block are in flight at once; (b) one call mixing stacks in error, stacks whose rows are
+    not 16-byte aligned (general kernel behind the fused launch), bars, and more stacks than blocks; (c) frames beyond the
+    one-round-trip strip-0 path (wider than 2048, taller than 1152) and beyond the per-frame kernels' shared-memory budget"""
+    rng = np.random.default_rng(77)
+    # (a)
+    n, w, h = 700, 96, 64
+    st = synth.frame_stacks(n, w, h, seed=99).numpy()
+    for s in range(0, n, 5):
+        st[s, :, : int(rng.integers(1, 20)), :] = 16
+        st[s, :, :, w - int(rng.integers(1, 30)):] = 20
+    want_h, want_s, want_c, _ = oracle_all(st)
+    got_h, got_s, got_c = gpu_hash(ctx, st)
+    assert np.array_equal(got_c, want_c) and np.array_equal(got_s, want_s) and np.array_equal(got_h, want_h)
+    # (b)
+    sizes = [(320, 180), (333, 187), (640, 360), (48, 48), (320, 180), (1000, 562), (320, 180)] * 30
+    descs = np.zeros(len(sizes), dtype=_ffi.STACK_DESC_DTYPE)
+    bufs, stacks, off = [], [], 0
+    for k, (w, h) in enumerate(sizes):
+        one = synth.frame_stacks(1, w, h, seed=1000 + k)[0].numpy()
+        if k % 4 == 1:
+            one[:, : h // 8, :] = 16
+            one[:, h - h // 10:, :] = 18
+        if k % 7 == 3:
+            one[:, :, : w // 9] = 12
+        pitch = w + (0 if k % 3 else 7)  # every third stack: rows not 16-byte aligned
+        n_fr = 16 if k % 11 else 9       # every eleventh: NotEnoughFrames
+        buf = np.zeros((n_fr, h, pitch), np.uint8)
+        buf[:, :, :w] = one[:n_fr]
+        descs[k] = (off, pitch * h, w, h, pitch, n_fr, _ffi.STACK_FLAG_MIXED_SIZES if k % 13 == 5 else 0, 0)
+        bufs.append((off, buf.reshape(-1)))
+        stacks.append(one)
+        off += (buf.size + 15) // 16 * 16
+    host = np.zeros(off, np.uint8)
+    for o0, b1 in bufs:
+        host[o0:o0 + b1.size] = b1
+    got_h, got_s, got_c = ctx.hash_stacks(host, descs, 1)
+    for k, one in enumerate(stacks):
+        if k % 13 == 5:
+            assert got_s[k] == _ffi.STACK_VIDPROC and not got_h[k].any(), k
+        elif k % 11 == 0:
+            assert got_s[k] == _ffi.STACK_NOT_ENOUGH_FRAMES and not got_h[k].any(), k
+        else:
+            w_st, w_h, w_crop, _ = o.hash_stack(one, 1)
+            assert got_s[k] == w_st == 0 and tuple(got_c[k]) == w_crop and np.array_equal(got_h[k], w_h), (k, sizes[k])
+    # (c)
+    for (w, h) in [(2304, 400), (640, 1300), (2560, 1440), (256, 9000)]:
+        st = synth.frame_stacks(3, w, h, seed=w + h).numpy()
+        st[1, :, : h // 7, :] = 16
+        st[1, :, h - h // 9:, :] = 16
+        st[2, :, :, : w // 6] = 235
+        want_h, want_s, want_c, _ = oracle_all(st)
+        got_h, got_s, got_c = gpu_hash(ctx, st)
+        assert np.array_equal(got_c, want_c) and np.array_equal(got_s, want_s) and np.array_equal(got_h, want_h), (w, h)
+
+
 def test_chunked_overlapped_pipeline_matches_serial(ctx):
     """the fused kernel (cold tables: sizes met for the first time take a second pass; warm; DCT in the kernel or on its own) and the
     per-frame pipeline it replaced: resize jobs built on the device from the crops (sizes met for the first time take a second pass),
