@@ -823,18 +823,31 @@ def main():
         k_ms = kt[1][0] / max(kt[1][1], 1)
         alg_bytes = ns * (stack_bytes + 128)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if kt[1][1] else None
-        # bytes the fused kernel actually requests: the cropped rows, in whole 128-byte chunks from the 16-byte aligned start
+        # bytes the kernel actually requests: the cropped rows in whole k-chunks (256 bytes in the fused kernel, 128 in the per-frame
+        # kernels) from the 16-byte aligned start, never beyond the row; + strip 0 of the 8 scanned sides and the bars the scan walks
         c = crops["c"].astype(np.int64)
         cw, chh = w - c[:, 0] - c[:, 1], h - c[:, 2] - c[:, 3]
-        moved = int((16 * chh * (((c[:, 0] & 15) + cw + 127) // 128) * 128).sum()) + ns * 128
-        roof = {"bound": "hbm", "kernel": "resize_mma_kernel (crop window + Lanczos3 -> 16x16 per frame, DCT + threshold + pack in the stack's last CTA)",
+        fused = args.hash_variant < 0
+        chunk = 256 if fused else 128
+        x0 = c[:, 0] & ~15
+        row_bytes = np.minimum((((c[:, 0] & 15) + cw + chunk - 1) // chunk) * chunk, w - x0)
+        scan = 2 * (2 * h + 2 * w + (c[:, 0] + c[:, 1] + 64 * (c[:, 0] + c[:, 1] > 0)) * h + (c[:, 2] + c[:, 3] + 64 * (c[:, 2] + c[:, 3] > 0)) * w)
+        moved = int((16 * chh * row_bytes + scan).sum()) + ns * 128
+        kname = "hash_fused_kernel" if fused else "resize_mma_kernel"
+        roof = {"bound": "hbm",
+                "kernel": ("hash_fused_kernel (ONE persistent launch per call: letterbox scan of frames 0 and 8, crop, resize job, Lanczos3 -> 16x16 per "
+                           "frame with both passes on the tensor path, 16^3 DCT, threshold, pack)") if fused else
+                          "resize_mma_kernel (crop window + Lanczos3 -> 16x16 per frame, DCT + threshold + pack in the stack's last CTA), behind the letterbox scan kernels",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                "frac_bytes_moved": (moved / (k_ms * 1e-3) / 1e9 / hbm_peak) if kt[1][1] else None, "bytes_moved_per_launch_set": moved,
-                "traffic": ncu_traffic("resize_mma_kernel", f"stacks_{ns}_{w}x{h}"), "peak_source": peak_src,
+                "frac_bytes_moved": (moved / (k_ms * 1e-3) / 1e9 / hbm_peak) if kt[1][1] else None, "bytes_moved_per_launch": moved,
+                "frac_whole_step": alg_bytes / (secs / steps) / 1e9 / hbm_peak,
+                "traffic": ncu_traffic(kname, f"stacks_{ns}_{w}x{h}"), "peak_source": peak_src,
                 "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_stack": stack_bytes + 128,
-                "note": "kernel_ms = CUDA events around the fused kernel's launches of one call (4 chunks of stacks; includes the job-build "
-                        "kernels and any wait for the letterbox stream)",
-                "step_share": {"resize_dct_pack": kt[1][0], "letterbox_on_its_stream": kt[2][0], "unit": "ms over timed steps"}}
+                "note": ("kernel_ms = CUDA events around the one launch of a call; frac = 16*W*H + 128 bytes per stack over that time (SURVEY M3: cropped "
+                         "stacks read fewer rows, frac_bytes_moved counts what is requested); frac_whole_step = the same bytes over ms_per_step, "
+                         "which also holds the descriptor upload, two memsets, the read-back of the crops and the host's wake-up") if fused else
+                        "kernel_ms = CUDA events around the resize launches of one call (includes the job-build kernels); the letterbox scan runs before it",
+                "step_share": {"fused_kernel" if fused else "resize_dct_pack": kt[1][0], "letterbox_kernels": kt[2][0], "unit": "ms over timed steps"}}
         # e2e: host frames (pinned) -> vdf_hash_stacks -> host hashes, bounded to a few stacks (PCIe-bound)
         ne = min(ns, 32)
         host = pool[:ne].cpu().pin_memory()

@@ -5,6 +5,6 @@ for rep in 1 2; do
     VDF_B200_SO=$PWD/$so python bench.py --workload hash --steps 20 --warmup 3 --hash-total 20480 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; n=d['steps']
-print('$so', 'ms/step %.4f' % d['ms_per_step'], 'resize %.4f' % (r['step_share']['resize_dct_pack']/n), 'letterbox %.4f' % (r['step_share']['letterbox_on_its_stream']/n), d['clocks']['sm_mhz'], d['clocks']['reasons'])"
+print('$so', 'ms/step %.4f' % d['ms_per_step'], 'kernel %.4f' % r['kernel_ms_per_launch'], d['clocks']['sm_mhz'], d['clocks']['reasons'])"
   done
 done

@@ -24,15 +24,16 @@ if [[ $STEP == all || $STEP == ncu ]]; then
       python bench.py --steps 1 --warmup 0 --no-secondary --no-cpu-baseline --e2e-steps 1 --tol-sweep "" --parity-rows 0 > gpurun_out/ncu_tc6.log 2>&1; echo "ncu tc6 rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hamming_tiles -c 1 -f -o gpurun_out/prof_hamming_popc__self_262144_x1 \
       python bench.py --workload popc --steps 1 --warmup 0 --no-cpu-baseline --parity-rows 0 > gpurun_out/ncu_popc.log 2>&1; echo "ncu popc rc=$?"
-  # the third launch: the first call meets crop sizes for the first time (a pass for the known sizes, a pass for the misses)
+  # the third launch: the first call meets crop sizes for the first time (a pass for the known sizes, a pass for the misses), the next call is warm
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:hash_fused -s 2 -c 1 -f -o gpurun_out/prof_hash_fused__stacks_256_1920x1080 \
+      python bench.py --workload hash --steps 1 --warmup 1 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_fused.log 2>&1; echo "ncu fused rc=$?"
+  # the per-frame kernels it replaced (context option hash_fused = 0), for the comparison in profiles/README.md
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:resize_mma -s 2 -c 1 -f -o gpurun_out/prof_resize_mma__stacks_256_1920x1080 \
-      python bench.py --workload hash --steps 1 --warmup 1 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_resize.log 2>&1; echo "ncu resize rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:letterbox_panels -c 1 -f -o gpurun_out/prof_letterbox__stacks_256_1920x1080 \
-      python bench.py --workload hash --steps 1 --warmup 0 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_letterbox.log 2>&1; echo "ncu letterbox rc=$?"
+      python bench.py --workload hash --hash-variant 0 --steps 1 --warmup 1 --hash-total 256 --no-cpu-baseline > gpurun_out/ncu_resize.log 2>&1; echo "ncu resize rc=$?"
 fi
 if [[ $STEP == all || $STEP == sanitizer ]]; then
   timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_search.py tests/test_gpu_hashing.py -m gpu -q -x \
-      -k "fold_is_exact and clusters or prepared_table or many_matches or sort_ties or chunked_overlapped or random_edge_lists or long_dependency or find_with_refs or cropdetect_none" \
+      -k "fold_is_exact and clusters or prepared_table or many_matches or sort_ties or chunked_overlapped or fused_kernel_machinery or random_edge_lists or long_dependency or find_with_refs or cropdetect_none" \
       > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -6 gpurun_out/sanitizer_memcheck.log
 fi
 if [[ $STEP == all || $STEP == bench ]]; then

@@ -1118,7 +1118,7 @@ __global__ void job_build_kernel(const StackDev* __restrict__ stacks, const uint
     } else {
         bool missed;
         j = make_job(d, crop + (size_t)s * 4, coef_lut, bfrag_lut, ring_bytes, max_kch, allow_fast != 0, &missed);
-        if (d.status == VDF_STACK_OK) miss[s] = missed ? 1u : 0u;
+        miss[s] = missed ? 1u : 0u;
         if (missed) atomicAdd(n_miss, 1u);
     }
     jobs[s] = j;
@@ -1254,7 +1254,7 @@ __device__ __forceinline__ void fused_publish_job(const FusedArgs& a, uint32_t s
     for (int k = 0; k < 4; ++k) a.crop[(size_t)s * 4 + k] = out[k];
     bool missed;
     const StackJob j = make_job(d, out, a.coef_lut, a.bfrag_lut, 0xFFFFFFFFu, 0xFFFFFFFFu, true, &missed);
-    if (d.status == VDF_STACK_OK) a.miss[s] = missed ? 1u : 0u;
+    a.miss[s] = missed ? 1u : 0u;
     if (missed) atomicAdd(a.n_miss, 1u);
     a.jobs[s] = j;
     if (!(j.status == VDF_STACK_OK && j.fast)) atomicAdd(&a.ctl[5], 1u);
@@ -2158,7 +2158,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         ctx->err = "frame height beyond the resize kernels' shared-memory budget";
         return VDF_ERR_INVALID;
     }
-    VDF_ALLOC(ctx, ctx->pin_a.ensure((size_t)n * 16));
+    VDF_ALLOC(ctx, ctx->pin_a.ensure(((size_t)n * 5 + 16) * 4));  // crops (+ in fused mode: miss flags, control words) as they come back
     uint32_t* crop = ctx->pin_a.as<uint32_t>();
     VDF_ALLOC(ctx, ctx->h_jobs.ensure((size_t)n * sizeof(StackJob)));
     VDF_ALLOC(ctx, ctx->h_desc.ensure((size_t)n * sizeof(StackDev)));
@@ -2170,6 +2170,18 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     uint32_t* d_done = ctx->h_done.as<uint32_t>();
     uint32_t* d_miss = d_done + n;
     uint32_t* d_nmiss = d_miss + n;
+    uint32_t* d_crop = ctx->h_crop.as<uint32_t>();
+    uint32_t* d_ctl = nullptr;
+    if (use_fused) {
+        // one buffer, so that a call is: descriptors up, ONE memset, ONE launch, ONE read-back.  [crop 4n | miss n] survive a second pass;
+        // [ctl 16 | flags n | sides_done n | dq n | done n | wq 8n] are zeroed before every launch; ctl[15] counts the misses
+        VDF_ALLOC(ctx, ctx->h_fctl.ensure((16 + 17 * (size_t)n) * 4));
+        d_crop = ctx->h_fctl.as<uint32_t>();
+        d_miss = d_crop + 4 * (size_t)n;
+        d_ctl = d_miss + n;
+        d_nmiss = d_ctl + 15;
+        d_done = d_ctl + 16 + 3 * (size_t)n;
+    }
     uint8_t* d_small = d_out_small;
     if (!d_small) {
         VDF_ALLOC(ctx, ctx->h_small.ensure((size_t)n * 4096));
@@ -2180,7 +2192,7 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     for (uint32_t s = 0; s < n && !any_bad; ++s) any_bad = status[s] != VDF_STACK_OK;
     const bool fuse = ctx->hash_fuse_dct != 0;  // DCT + pack in the resize kernel's last CTA per stack, or as a kernel of its own
     VDF_CUDA(ctx, cudaMemcpyAsync(d_sd, sd, (size_t)n * sizeof(StackDev), cudaMemcpyHostToDevice, st));
-    VDF_CUDA(ctx, cudaMemsetAsync(d_done, 0, (size_t)n * 8 + 64, st));
+    if (!use_fused) VDF_CUDA(ctx, cudaMemsetAsync(d_done, 0, (size_t)n * 8 + 64, st));
     if (d_out_hash && any_bad && fuse) VDF_CUDA(ctx, cudaMemsetAsync(d_out_hash, 0, (size_t)n * 128, st));  // stacks that are not hashed read as zero
     // The opt-in is per device AND per function, whoever sets it last wins: every context asks for the device's maximum, once,
     // so that contexts sharing a GPU can never lower each other's limit (kept per context because it is per device).
@@ -2233,33 +2245,30 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
             kt_end(ctx, 2, lb);
         }
     } else if (cropdetect == VDF_CROPDETECT_MOTION) {
-        VDF_TRY(motion_crop_device(ctx, d_frames, d_sd, sd, n, ctx->h_crop.as<uint32_t>()));  // Cropdetect::Motion (motion.cu)
+        VDF_TRY(motion_crop_device(ctx, d_frames, d_sd, sd, n, d_crop));  // Cropdetect::Motion (motion.cu)
     } else {
-        VDF_CUDA(ctx, cudaMemsetAsync(ctx->h_crop.p, 0, (size_t)n * 16, st));  // Cropdetect::None: zero crop (:195-199)
+        VDF_CUDA(ctx, cudaMemsetAsync(d_crop, 0, (size_t)n * 16, st));  // Cropdetect::None: zero crop (:195-199)
     }
     // ---- default: ONE persistent launch per pass (hash_fused_kernel) does the scan, the crops, the jobs, the resize and the DCT
-    uint32_t* d_ctl = nullptr;
     if (use_fused) {
-        VDF_ALLOC(ctx, ctx->h_fctl.ensure((16 + 11 * (size_t)n) * 4));
-        d_ctl = ctx->h_fctl.as<uint32_t>();
         if (!ctx->hash_smem_set[1]) {
             VDF_CUDA(ctx, cudaFuncSetAttribute((const void*)hash_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
             ctx->hash_smem_set[1] = kFusedSmemBytes;
         }
     }
     auto run_fused = [&](bool only_missed, bool scan_in_kernel) -> int {
-        VDF_CUDA(ctx, cudaMemsetAsync(d_ctl, 0, (16 + (scan_in_kernel ? 11 : 3) * (size_t)n) * 4, st));
+        VDF_CUDA(ctx, cudaMemsetAsync(d_ctl, 0, (16 + (scan_in_kernel ? 12 : 4) * (size_t)n) * 4, st));
         FusedArgs fa;
         fa.frames = d_frames, fa.stacks = d_sd, fa.jobs = d_jobs, fa.n = n, fa.n_lb_items = scan_in_kernel ? n * 8u : 0u;
-        fa.sides = ctx->h_sides.as<uint32_t>(), fa.crop = ctx->h_crop.as<uint32_t>();
+        fa.sides = ctx->h_sides.as<uint32_t>(), fa.crop = d_crop;
         fa.coef_lut = ctx->h_coef_lut.as<CoefRef>(), fa.bfrag_lut = ctx->h_bfrag_lut.as<BFragRef>();
         fa.miss = d_miss, fa.n_miss = d_nmiss;
-        fa.ctl = d_ctl, fa.flags = d_ctl + 16, fa.sides_done = d_ctl + 16 + n, fa.dq = d_ctl + 16 + 2 * (size_t)n, fa.wq = d_ctl + 16 + 3 * (size_t)n;
+        fa.ctl = d_ctl, fa.flags = d_ctl + 16, fa.sides_done = d_ctl + 16 + n, fa.dq = d_ctl + 16 + 2 * (size_t)n, fa.wq = d_ctl + 16 + 4 * (size_t)n;
         fa.done = d_done, fa.small = d_small, fa.out_hash = d_hash32;
         fa.exp = getenv("VDF_FUSED_EXP") ? (uint32_t)atoi(getenv("VDF_FUSED_EXP")) : 0u;
         if (!only_missed) kt_begin(ctx, 1);
         if (!scan_in_kernel) {  // crops known up front (Cropdetect::None / Motion, or the pass for the sizes met for the first time)
-            job_build_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_sd, ctx->h_crop.as<uint32_t>(), n, fa.coef_lut, fa.bfrag_lut, 0xFFFFFFFFu, 0xFFFFFFFFu,
+            job_build_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_sd, d_crop, n, fa.coef_lut, fa.bfrag_lut, 0xFFFFFFFFu, 0xFFFFFFFFu,
                                                               1u, only_missed ? 1u : 0u, d_jobs, d_miss, d_nmiss, fa.flags, fa.ctl + 5);
             VDF_LAUNCHED(ctx);
         }
@@ -2325,23 +2334,29 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
     VDF_TRY(separate_dct());
     VDF_ALLOC(ctx, ctx->h_misc.ensure(256));
     uint32_t* h_n = reinterpret_cast<uint32_t*>(ctx->h_misc.as<unsigned long long>() + 24);
-    VDF_CUDA(ctx, cudaMemcpyAsync(crop, ctx->h_crop.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-    VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
-    if (use_fused) VDF_CUDA(ctx, cudaMemcpyAsync(h_n + 1, d_ctl + 6, 4, cudaMemcpyDeviceToHost, st));
+    if (use_fused) {  // crops, miss flags and the control words in one copy
+        VDF_CUDA(ctx, cudaMemcpyAsync(crop, d_crop, ((size_t)n * 5 + 16) * 4, cudaMemcpyDeviceToHost, st));
+        h_miss = crop + 4 * (size_t)n;
+        h_n = crop + 5 * (size_t)n + 15;
+    } else {
+        VDF_CUDA(ctx, cudaMemcpyAsync(crop, d_crop, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+        VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
+    }
+    const uint32_t* h_ctl = crop + 5 * (size_t)n;  // fused mode only
     VDF_CUDA(ctx, cudaStreamSynchronize(st));
-    if (use_fused && h_n[1]) {
-        ctx->err = "hash_fused_kernel: a wait timed out (code " + std::to_string(h_n[1]) + ")";
+    if (use_fused && h_ctl[6]) {
+        ctx->err = "hash_fused_kernel: a wait timed out (code " + std::to_string(h_ctl[6]) + ")";
         return VDF_ERR_CUDA;
     }
     if (use_fused && getenv("VDF_FUSED_STATS")) {  // the kernel's own wait statistics (~us, summed over blocks)
-        uint32_t h_ctl[16];
-        VDF_CUDA(ctx, cudaMemcpy(h_ctl, d_ctl, sizeof h_ctl, cudaMemcpyDeviceToHost));
         fprintf(stderr, "fused stats: frames %u lb_items %u/%u dct %u/%u nofuse %u | wait_job_us %u wait_first_slot_us %u wait_slot_us %u scan_end_us %u pixel_life_us_sum %u\n", h_ctl[0],
                 h_ctl[1], h_ctl[2], h_ctl[3], h_ctl[4], h_ctl[5], h_ctl[8], h_ctl[14], h_ctl[9], h_ctl[10], h_ctl[11]);
     }
     if (*h_n) {  // sizes met for the first time: build their tables (host, f64 + libm sin like the reference), run those stacks
-        VDF_CUDA(ctx, cudaMemcpyAsync(h_miss, d_miss, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        VDF_CUDA(ctx, cudaStreamSynchronize(st));
+        if (!use_fused) {
+            VDF_CUDA(ctx, cudaMemcpyAsync(h_miss, d_miss, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+            VDF_CUDA(ctx, cudaStreamSynchronize(st));
+        }
         for (uint32_t s = 0; s < n; ++s) {
             if (!h_miss[s]) continue;
             const uint32_t* c = &crop[(size_t)s * 4];
@@ -2359,11 +2374,11 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         VDF_CUDA(ctx, cudaMemsetAsync(d_nmiss, 0, 4, st));
         VDF_TRY(run_pass(true));
         VDF_TRY(separate_dct());
-        VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
-        if (use_fused) VDF_CUDA(ctx, cudaMemcpyAsync(h_n + 1, d_ctl + 6, 4, cudaMemcpyDeviceToHost, st));
+        if (use_fused) VDF_CUDA(ctx, cudaMemcpyAsync(crop + 5 * (size_t)n, d_ctl, 64, cudaMemcpyDeviceToHost, st));
+        else VDF_CUDA(ctx, cudaMemcpyAsync(h_n, d_nmiss, 4, cudaMemcpyDeviceToHost, st));
         VDF_CUDA(ctx, cudaStreamSynchronize(st));
-        if (use_fused && h_n[1]) {
-            ctx->err = "hash_fused_kernel: a wait timed out (code " + std::to_string(h_n[1]) + ")";
+        if (use_fused && h_ctl[6]) {
+            ctx->err = "hash_fused_kernel: a wait timed out (code " + std::to_string(h_ctl[6]) + ")";
             return VDF_ERR_CUDA;
         }
         if (*h_n) {
