@@ -1469,7 +1469,7 @@ __device__ __forceinline__ void fused_scheduler(const FusedArgs& a, FusedSmem& f
         const uint32_t gate = (a.exp & 8u) ? (j >= 2 ? 2u * j - 4u : 0u) : (a.exp & 4u) ? (j >= 1 ? 2u * j - 2u : 0u) : (j >= 1 ? 2u * j - 1u : 0u);
         while (gate > *v_pord) {
             if (*v_abort) return;
-            __nanosleep(200);
+            __nanosleep(2000);  // half a frame is ~20 us away
         }
         FrameSlot sl;
         memset(&sl, 0, sizeof sl);
@@ -1580,16 +1580,15 @@ __device__ __forceinline__ void fused_finalizer(const FusedArgs& a, FusedSmem& f
         const uint32_t b = ord & 1u, parity = (ord >> 1) & 1u;
         // wait for frame `ord` or for the end
         for (;;) {
-            uint32_t ready;
-            asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            uint32_t ready;  // suspended in hardware for up to ~4 us at a time: this warp costs no issue slots while it waits
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
                          : "=r"(ready)
-                         : "r"((uint32_t)__cvta_generic_to_shared(&fs.fin_full[b])), "r"(parity)
+                         : "r"((uint32_t)__cvta_generic_to_shared(&fs.fin_full[b])), "r"(parity), "r"(4000u)
                          : "memory");
             if (ready) break;
             const uint32_t stop = *v_stop;
             if (stop && ord + 1u >= stop) return;
             if (*reinterpret_cast<volatile uint32_t*>(&fs.abort_all)) return;
-            __nanosleep(100);
         }
         const uint32_t out = fs.fin_out[b], prec = fs.fin_prec[b];
         int32_t* vr = fs.vred[b];
