@@ -153,9 +153,11 @@ int vdf_peer_close(vdf_ctx* ctx);
  * positions 1000..1023 whenever no hash of either operand sets those bits (every real VideoHash: dct_3d.rs:55-66), which
  * makes its 64-column screen exact at any tolerance; 0 = always the popcount-screen epilogue;
  * "peer_timeout_ms": how long the peer exchange waits for the slowest rank (0 = automatic, grows with the problem);
- * "hash_variant": resize kernel choice; "hash_chunks" (1..4, default 1) / "hash_overlap" (default 0): split a hashing call
- * into chunks of stacks and run the letterbox scan of chunk k+1 beside the resize of chunk k on a second stream (measured
- * slower than the serial order, kept as an experiment knob). */
+ * "hash_fused": 1 (default) a hashing call is ONE persistent kernel (letterbox scan, crop, resize, DCT, pack: hash_fused_kernel),
+ * 0 = the per-frame kernels it replaced (letterbox scan kernels, then one resize block per frame), for which "hash_variant"
+ * picks the resize kernel and "hash_chunks" (1..4, default 1) / "hash_overlap" (default 0) split the call into chunks of
+ * stacks with the scan of chunk k+1 beside the resize of chunk k on a second stream (measured slower; experiment knobs);
+ * "hash_fuse_dct": 1 (default) DCT + pack inside the hashing kernel, 0 = a kernel of its own. */
 int vdf_ctx_set_option(vdf_ctx* ctx, const char* key, int64_t value);
 
 /* The cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the caller). */

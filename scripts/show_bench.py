@@ -25,6 +25,7 @@ print("cplane", d.get("e2e_cplane"))
 print("tol_sweep", [(t["tolerance"], round(t["ms_per_step"], 2), round(t["kernel_ms"], 2), t["edges"]) for t in d.get("tol_sweep", [])])
 s = d.get("secondary") or {}
 print("hash step_share", (s.get("roofline") or {}).get("step_share"), "frac_bytes_moved", (s.get("roofline") or {}).get("frac_bytes_moved"), s.get("bit_mismatch"))
+print("hash burst", s.get("burst"), "sustained clocks", s.get("clocks"))
 x = d.get("secondary_e2e") or {}
 print("e2e10m", x.get("seconds"), x.get("phases_s_rank0"))
 print("clocks", d.get("clocks"))

@@ -571,6 +571,12 @@ def test_two_contexts_in_one_process(ctx):
             assert np.array_equal(other.search_self(H, dur, 300), want)
             ctx.set_option("search_variant", variant)
             assert np.array_equal(ctx.search_self(H, dur, 300), want)
+        # the hashing kernels' opt-in (216 KB of shared memory for the fused kernel) is per device too
+        st = synth.frame_stacks(5, 320, 180, seed=12).numpy()
+        st[1, :, :25, :] = 16
+        descs = _ffi.make_descs(5, 320, 180)
+        a, b = other.hash_stacks(st.reshape(-1), descs, 1), ctx.hash_stacks(st.reshape(-1), descs, 1)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)) and a[2][1][2] == 25
     finally:
         ctx.set_option("search_variant", DEFAULT_VARIANT)
         other.close()
@@ -601,6 +607,12 @@ def test_multi_device_context_matches_one_device(ctx):
         assert vdf.search_with_references(R, table, 0.3, ctx=m) == vdf.search_with_references(R, table, 0.3, ctx=ctx)
         few = vdf.HashTable(H[:3], dur[:3], paths[:3])  # fewer candidates than devices: empty slices still reach the barrier
         assert vdf.search_with_references(R, few, 0.3, ctx=m) == vdf.search_with_references(R, few, 0.3, ctx=ctx)
+        # vdf_hash_stacks on the multi-device context: stacks sharded over the devices, one fused launch each
+        st = synth.frame_stacks(37, 320, 180, seed=13).numpy()
+        st[::4, :, :, :30] = 20
+        descs = _ffi.make_descs(37, 320, 180)
+        a, b = m.hash_stacks(st.reshape(-1), descs, 1), ctx.hash_stacks(st.reshape(-1), descs, 1)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)) and b[2][0][0] == 30
     finally:
         m.close()
 

@@ -19,9 +19,9 @@
 // the reference) and cached in HBM per size; a lookup table in HBM (size -> table) lets a small kernel turn the crops into
 // resize jobs ON THE DEVICE, so a call runs letterbox -> jobs -> resize+DCT+pack without the host in between.  A size met
 // for the first time is a "miss": the host builds its table after the pass and only the missed stacks run again.
-// Kernels per call: the letterbox scan of frames 0 and 8 (a data-dependent pre-pass: its result moves the addresses the
-// resize reads), and ONE fused kernel per stack set that reads every pixel once and writes the 128-byte hash (crop window,
-// Lanczos3 to 16x16 per frame, and -- in the CTA that finishes a stack's 16th frame -- the 16^3 DCT, threshold and pack).
+// Kernels per call: ONE (hash_fused_kernel, below): persistent, warp-specialised; it scans frames 0 and 8 for bars, turns the crops
+// into resize jobs, reads every pixel of the crop windows once and writes the 128-byte hashes.  The per-frame kernels it replaced
+// (letterbox_*_kernel, resize_mma_kernel: context option hash_fused = 0) are kept for comparison and for Cropdetect::Motion's scan.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1129,25 +1129,31 @@ __global__ void job_build_kernel(const StackDev* __restrict__ stacks, const uint
 }
 
 // ================================================================================ the fused kernel
-// ONE launch per call does letterbox -> crop -> resize -> DCT -> threshold -> pack: sm_count persistent thread blocks of 416 threads,
-// warp-specialised into three groups that never share a barrier:
-//   pixel group   (warps 0-7)  the pixel stream.  Frames are claimed one at a time; tiles of 128 rows x 256 bytes travel HBM ->
-//                              shared memory through a 4-stage cp.async ring that never drains between frames (the producer side runs
-//                              ahead ACROSS frames); the horizontal pass is the IMMA contraction of resize_mma_kernel; the u8
-//                              intermediate of a warp's 16 rows goes through 768 bytes of shared memory straight into half a k-step of
-//                              the VERTICAL pass, also on the tensor path (A = the 16 x 32 slice of the vertical coefficients as hi / lo
-//                              bytes, B = the transposed intermediate), accumulated in registers over the frame: no per-frame
-//                              intermediate buffer, no serial tail per frame, shared memory independent of the frame height.
-//   scheduler     (warp 12)    one lane: claims the next frame, waits for its stack's job to be published, fills a slot.
-//   helper group  (warps 8-11) everything that is latency-bound: first the letterbox scan items (one per stack x frame {0, 8} x side:
-//                              strip 0, then panel after panel), the item that completes a stack's eighth side turns the crop into
-//                              the stack's resize job and publishes it; then the 16^3 DCT + threshold + pack of every stack whose
-//                              sixteenth frame the pixel groups have finished.  All of it runs in the shadow of the pixel stream.
+// ONE launch per call does letterbox -> crop -> resize job -> resize -> DCT -> threshold -> pack: sm_count persistent thread blocks of
+// 576 threads (216 KB of shared memory, one block per SM), warp-specialised into five groups that never share a barrier:
+//   consumers  (warps 0-7)    warp w owns rows 16 w .. 16 w + 15 of every tile: the horizontal pass is the IMMA contraction of
+//                             resize_mma_kernel; the u8 intermediate of its 16 rows goes through 768 bytes of shared memory straight
+//                             into half a k-step of the VERTICAL pass, also on the tensor path (A = the 16 x 32 slice of the vertical
+//                             coefficients as hi / lo bytes, B = the transposed intermediate), accumulated in registers over the
+//                             frame: no per-frame intermediate buffer, no serial tail per frame, shared memory independent of the
+//                             frame height.  Arrive on the stage's "empty" mbarrier.
+//   producers  (warps 8-11)   the cp.async side of a 4-stage ring: tiles of 128 rows x 256 bytes (+ the tile's coefficient fragments,
+//                             only the octets of outputs that have taps there) HBM -> shared memory, cp.async.mbarrier.arrive on the
+//                             stage's "full" mbarrier.  They run ahead ACROSS frames (the ring never drains), and they may sit in a
+//                             blocked copy instruction for as long as the memory system likes without holding up a tensor instruction.
+//   helpers    (warps 12-15)  everything that is latency-bound: the letterbox items (strip 0 of a stack's eight sides in one round
+//                             trip; walks of the sides that have a bar), crop -> resize job -> publish; then the 16^3 DCT + threshold
+//                             + pack of every stack whose sixteenth frame is finished.  All of it in the shadow of the pixel stream.
+//   scheduler  (warp 16)      one lane: claims the next frame, checks that its stack's job is published (else puts the frame aside
+//                             and claims another), fills a slot for producers and consumers.
+//   finalizer  (warp 17)      per finished frame: the eight consumer warps' vertical sums -> round, shift, clamp -> 256 bytes of the
+//                             stack's cube; the stack's sixteenth frame goes onto the helpers' DCT queue.
 // Items are claimed in order from global counters and a letterbox item never waits for anything, so every wait in the kernel is
-// for work that a RUNNING group has already claimed: no deadlock, whatever the number of resident blocks.
-// Why: the per-frame kernel moved 5.5 TB/s (128-byte row segments, a vertical-pass tail and a launch slot per frame, a wave tail
+// for work that a RUNNING group has already claimed: no deadlock, whatever the number of resident blocks.  Waits are bounded
+// (kFWaitNs): a kernel that would hang sets ctl[6] and ends, and the call fails loudly.
+// Why: the per-frame kernels moved 5.5 TB/s (128-byte row segments, a vertical-pass tail and a launch slot per frame, a wave tail
 // per launch) and the letterbox scan held the GPU alone for 7 % of a step; a token consumer with this tile shape and ring reads
-// 6.7 TB/s (csrc/microbench_read.cu, profiles/r02_microbench_read.jsonl).
+// 6.7 TB/s (csrc/microbench_read.cu, profiles/r02_microbench_read.jsonl); DESIGN.md section 4 has the steps in between.
 constexpr int kFRows = 128, kFCols = 256, kFPitch = kFCols + 16;
 constexpr int kFStages = 4;
 constexpr int kFCoefBytes = 2 * kBFragBytes + 16;               // two 128-pixel halves + header
