@@ -1162,7 +1162,7 @@ constexpr int kFSlots = 8;
 constexpr int kFSlotMasks = 72;  // frames up to 9216 pixels wide skip untapped octets; wider ones copy every fragment
 constexpr int kFTmpPitch = 48;                                  // transposed intermediate: [16 outputs][32 rows + pad], per warp
 constexpr int kFHelperBytes = kCubeBytes;                       // LbShared (33.5 KB) and the DCT cube (34 KB) share the helpers' arena
-constexpr int kFConsThreads = 256, kFProdThreads = 128, kFHelpThreads = 128;
+constexpr int kFConsThreads = 256, kFProdThreads = 64, kFHelpThreads = 128;
 constexpr int kFThreads = kFConsThreads + kFProdThreads + kFHelpThreads + 64;  // + scheduler warp + finalizer warp
 constexpr uint32_t kFNoFrame = 0xFFFFFFFFu;
 
@@ -1179,7 +1179,8 @@ struct FrameSlot {
 static_assert(sizeof(FrameSlot) == 56 + kFSlotMasks, "slot layout");
 
 struct FusedSmem {  // behind the ring and the helpers' arena
-    uint8_t tmpT[8][16 * kFTmpPitch];
+    uint8_t tmpT[4][16 * kFTmpPitch];
+    int32_t pairbuf[4][16 * 32];  // a consumer pair's partial sums of a row block on their way from the k-half-1 warp to the k-half-0 warp
     int32_t vred[2][256];
     FrameSlot slots[kFSlots];
     uint32_t sched_count;  // slots filled so far (scheduler -> pixel group)
@@ -1484,15 +1485,19 @@ __device__ __forceinline__ void fused_scheduler(const FusedArgs& a, FusedSmem& f
         for (uint32_t spin = 0;;) {
             uint32_t f = kFNoFrame;
             int free_q = -1, n_aside = 0;
+            uint32_t fl[kAside];  // all flags of the frames put aside in one round trip (plain loads; the fence below orders the job read)
+#pragma unroll
+            for (int q = 0; q < kAside; ++q) fl[q] = aside[q] == kFNoFrame ? 0u : ((aside[q] >> 4) == cur_s ? 1u : ld_volatile_u32(&a.flags[aside[q] >> 4]));
 #pragma unroll
             for (int q = 0; q < kAside; ++q) {  // a frame put aside whose job has arrived in the meantime
                 if (aside[q] == kFNoFrame) {
                     free_q = q;
                     continue;
                 }
-                if (f == kFNoFrame && ((aside[q] >> 4) == cur_s || ld_acquire_u32(&a.flags[aside[q] >> 4]))) f = aside[q], aside[q] = kFNoFrame, free_q = q;
+                if (f == kFNoFrame && fl[q]) f = aside[q], aside[q] = kFNoFrame, free_q = q;
                 else ++n_aside;
             }
+            if (f != kFNoFrame) __threadfence();
             const bool room = free_q >= 0;
             if (f == kFNoFrame && !exhausted && room) {
                 f = atomicAdd(&a.ctl[0], 1u);
@@ -1623,13 +1628,13 @@ __device__ __forceinline__ void fused_finalizer(const FusedArgs& a, FusedSmem& f
     }
 }
 
-// ---- producer group (threads 256..383): the cp.async side of the ring.  It may sit in a blocked copy instruction for as long as the
+// ---- producer group (threads 256..319): the cp.async side of the ring.  It may sit in a blocked copy instruction for as long as the
 // memory system likes (that is what back-pressure looks like) without holding up a single tensor instruction of the consumers.
 __device__ __forceinline__ void fused_producer(const FusedArgs& a, uint8_t* ring, FusedSmem& fs) {
     constexpr int NT = kFProdThreads;
     const int tid = threadIdx.x - kFConsThreads;
     volatile uint32_t* v_sched = &fs.sched_count;
-    // 16 threads x 16 bytes cover a 256-byte row segment, 8 rows per pass, 16 passes per tile
+    // 16 threads x 16 bytes cover a 256-byte row segment, 4 rows per pass, 32 passes per tile
     const uint32_t c16 = (tid & 15) * 16, r0 = tid >> 4;
     uint32_t stage = 0, empty_parity = 1;  // a fresh mbarrier passes a wait on the phase before its first
     for (uint32_t ord = 0;; ++ord) {
@@ -1650,14 +1655,14 @@ __device__ __forceinline__ void fused_producer(const FusedArgs& a, uint8_t* ring
         const uint8_t* img = sl.img;
         const uint8_t* kb2 = sl.kb2;
         const uint8_t* pm = sl.masks;
-        // this thread's four coefficient copies of a tile are all of one n-tile = one octet of outputs: ((tid >> 4) & 1); copies q = 0, 1
-        // belong to the tile's first 128-pixel half, q = 2, 3 to the second
+        // this thread's eight coefficient copies of a tile are all of one n-tile = one octet of outputs: ((tid >> 4) & 1); copies q = 0..3
+        // belong to the tile's first 128-pixel half, q = 4..7 to the second
         const uint32_t oct_bits = 0x55u << ((tid >> 4) & 1);
         const uint32_t n_kc = sl.n_kc, n_rb = sl.n_rb, ch = sl.ch, row_bytes = sl.row_bytes;
-        const uint64_t row_step = (uint64_t)8 * sl.pitch;
+        const uint64_t row_step = (uint64_t)4 * sl.pitch;
         if (tid == 0) *reinterpret_cast<volatile uint32_t*>(&fs.p_ord) = 2u * ord + (n_rb < 2u ? 1u : 0u);
         const uint8_t* g_rb = img + (uint64_t)r0 * sl.pitch + c16;
-        for (uint32_t rb = 0; rb < n_rb; ++rb, g_rb += 16 * row_step) {
+        for (uint32_t rb = 0; rb < n_rb; ++rb, g_rb += 32 * row_step) {
             if (tid == 0 && rb == n_rb / 2 && rb) *reinterpret_cast<volatile uint32_t*>(&fs.p_ord) = 2u * ord + 1u;
             for (uint32_t kc = 0; kc < n_kc; ++kc) {
                 mbar_wait(&fs.empty[stage], empty_parity);
@@ -1666,21 +1671,21 @@ __device__ __forceinline__ void fused_producer(const FusedArgs& a, uint8_t* ring
                 const uint8_t* g = g_rb + kc * kFCols;
                 uint32_t row = rb * kFRows + r0;
                 uint8_t* d = st + r0 * kFPitch + c16;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
                     const bool ok = xok && row < ch;
-                    cp_async16(d + i * 8 * kFPitch, ok ? g : img, ok ? 16u : 0u);
+                    cp_async16(d + i * 4 * kFPitch, ok ? g : img, ok ? 16u : 0u);
                     g += row_step;
-                    row += 8;
+                    row += 4;
                 }
                 const uint8_t* csrc = kb2 + (size_t)kc * kFCoefBytes + tid * 16;
                 uint8_t* cdst = st + kFRows * kFPitch + tid * 16;
                 const bool wide = 2 * kc + 1 >= (uint32_t)kFSlotMasks;
                 const bool need0 = wide || (pm[2 * kc] & oct_bits), need1 = wide || (pm[2 * kc + 1] & oct_bits);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q < 2 ? need0 : need1) cp_async16(cdst + q * NT * 16, csrc + q * NT * 16, 16u);
-                if (tid == 0) cp_async16(cdst + 4 * NT * 16, csrc + 4 * NT * 16, 16u);  // the header
+                for (int q = 0; q < 8; ++q)
+                    if (q < 4 ? need0 : need1) cp_async16(cdst + q * NT * 16, csrc + q * NT * 16, 16u);
+                if (tid == 0) cp_async16(cdst + 8 * NT * 16, csrc + 8 * NT * 16, 16u);  // the header
                 mbar_arrive_on_cp_async(&fs.full[stage]);
                 if (++stage == kFStages) stage = 0, empty_parity ^= 1u;
             }
@@ -1699,7 +1704,7 @@ __global__ void __launch_bounds__(kFThreads, 1) hash_fused_kernel(const FusedArg
     if (tid == 0) {
         fs.sched_count = 0, fs.p_ord = 0, fs.abort_all = 0;
         for (int s = 0; s < kFStages; ++s) mbar_init(&fs.full[s], kFProdThreads), mbar_init(&fs.empty[s], kFConsThreads / 32);
-        for (int s = 0; s < 2; ++s) mbar_init(&fs.fin_full[s], kFConsThreads / 32), mbar_init(&fs.fin_empty[s], 1);
+        for (int s = 0; s < 2; ++s) mbar_init(&fs.fin_full[s], kFConsThreads / 64), mbar_init(&fs.fin_empty[s], 1);
         fs.fin_stop = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1723,22 +1728,37 @@ __global__ void __launch_bounds__(kFThreads, 1) hash_fused_kernel(const FusedArg
     // ------------------------------------------------------------------------------------------------ consumer group
     const int lane = tid & 31, warp = tid >> 5;
     volatile uint32_t* v_sched = &fs.sched_count;
-    // warp w owns rows 16 w .. 16 w + 15 of every tile (one m16 tile), all sixteen outputs x {high, low} coefficient bytes
-    int32_t acc[4][4], vacc[2][2][4];
+    // Warp w = (row group r = w >> 1, k-half h = w & 1): rows 32 r .. 32 r + 31 of every tile (two m16 tiles), the 128 pixels of half h,
+    // all sixteen outputs x {high, low} coefficient bytes.  A coefficient fragment is read from shared memory by four warps (not
+    // eight: the consumers' shared-memory traffic is what limits the kernel at the clock the power cap leaves in long runs); the
+    // two warps of a pair add their partial sums once per row block, before the rounding.
+    int32_t acc[2][4][4], vacc[2][2][4];
 #pragma unroll
-    for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 2; ++x)
 #pragma unroll
-        for (int z = 0; z < 4; ++z) acc[y][z] = 0;
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int z = 0; z < 4; ++z) acc[x][y][z] = 0;
 #pragma unroll
     for (int x = 0; x < 2; ++x)
 #pragma unroll
         for (int y = 0; y < 2; ++y)
 #pragma unroll
             for (int z = 0; z < 4; ++z) vacc[x][y][z] = 0;
+    const uint32_t rgrp = warp >> 1, khalf = warp & 1;
     const uint32_t lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lbyte = (lane >> 4) * 16;
-    const uint32_t a_off = (warp * 16 + lrow) * kFPitch + lbyte;
+    const uint32_t a_off = (rgrp * 32 + lrow) * kFPitch + lbyte + khalf * kKch;
     const uint32_t g = lane >> 2, q4 = lane & 3, q2 = q4 * 2;
-    uint8_t* tw = fs.tmpT[warp];
+    uint8_t* tw = fs.tmpT[rgrp];
+    int32_t* pb = fs.pairbuf[rgrp] + lane;
+    // pair barriers (64 threads): A = "the partial sums are in pairbuf", B = "pairbuf has been read"
+    auto pair_arrive = [&](uint32_t id) {
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+    };
+    auto pair_sync = [&](uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); };
+    const uint32_t bar_a = 3u + 2u * rgrp, bar_b = 4u + 2u * rgrp;
+    bool pb_busy = false;  // (k-half 1) the partner has not yet confirmed reading the previous row block's sums
 
     uint32_t c_ord = 0, c_kc = 0, c_rb = 0, c_stage = 0, full_parity = 0;
     uint32_t c_nkc = 0, c_nrb = 0, c_prec_h = 0, c_prec_v = 0, c_out = kFNoFrame;
@@ -1749,6 +1769,7 @@ __global__ void __launch_bounds__(kFThreads, 1) hash_fused_kernel(const FusedArg
             __nanosleep(40);
             if ((spin & 4095u) == 4095u && globaltimer_ns() - t0 > 2 * kFWaitNs) {
                 c_out = kFNoFrame;
+                fs.abort_all = 1;
                 return;
             }
         }
@@ -1767,45 +1788,55 @@ __global__ void __launch_bounds__(kFThreads, 1) hash_fused_kernel(const FusedArg
         const uint32_t masks = *reinterpret_cast<const uint32_t*>(coef + 2 * kBFragBytes);
         const bool last_kc = c_kc + 1 == c_nkc;
         uint4 va_h = make_uint4(0, 0, 0, 0), va_l = make_uint4(0, 0, 0, 0);
-        if (last_kc) {  // the vertical k-step's A fragments: in flight under the row block's last contraction
-            const uint4* p = c_kva + ((size_t)(c_rb * 4 + (warp >> 1)) * 2) * 32 + lane;
+        if (last_kc && khalf == 0) {  // the vertical k-step's A fragments: in flight under the row block's last contraction
+            const uint4* p = c_kva + ((size_t)(c_rb * 4 + rgrp) * 2) * 32 + lane;
             va_h = __ldg(p), va_l = __ldg(p + 32);
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint8_t* arow = st + a_off + h * kKch;
-            const uint2* sb = reinterpret_cast<const uint2*>(coef + h * kBFragBytes);
-            const uint32_t tapmask = (a.exp & 1u) ? 0u : (masks >> (8 * h)) & 0xFFu;
+        {
+            const uint8_t* arow = st + a_off;
+            const uint2* sb = reinterpret_cast<const uint2*>(coef + khalf * kBFragBytes);
+            const uint32_t tapmask = (a.exp & 1u) ? 0u : (masks >> (8 * khalf)) & 0xFFu;
             const bool lo_oct = (tapmask & 0x55u) != 0, hi_oct = (tapmask & 0xAAu) != 0;
             if (lo_oct && hi_oct) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    uint32_t a0[4];
+                    uint32_t a0[4], a1[4];
                     ldmatrix_x4(a0, arow + ks * 32);
+                    ldmatrix_x4(a1, arow + 16 * kFPitch + ks * 32);
                     const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b1 = sb[(ks * 4 + 1) * 32 + lane];
                     const uint2 b2 = sb[(ks * 4 + 2) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
-                    imma_u8s8(acc[0], a0, b0);
-                    imma_u8s8(acc[1], a0, b1);
-                    imma_u8u8(acc[2], a0, b2);
-                    imma_u8u8(acc[3], a0, b3);
+                    imma_u8s8(acc[0][0], a0, b0);
+                    imma_u8s8(acc[1][0], a1, b0);
+                    imma_u8s8(acc[0][1], a0, b1);
+                    imma_u8s8(acc[1][1], a1, b1);
+                    imma_u8u8(acc[0][2], a0, b2);
+                    imma_u8u8(acc[1][2], a1, b2);
+                    imma_u8u8(acc[0][3], a0, b3);
+                    imma_u8u8(acc[1][3], a1, b3);
                 }
             } else if (lo_oct) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    uint32_t a0[4];
+                    uint32_t a0[4], a1[4];
                     ldmatrix_x4(a0, arow + ks * 32);
+                    ldmatrix_x4(a1, arow + 16 * kFPitch + ks * 32);
                     const uint2 b0 = sb[(ks * 4 + 0) * 32 + lane], b2 = sb[(ks * 4 + 2) * 32 + lane];
-                    imma_u8s8(acc[0], a0, b0);
-                    imma_u8u8(acc[2], a0, b2);
+                    imma_u8s8(acc[0][0], a0, b0);
+                    imma_u8s8(acc[1][0], a1, b0);
+                    imma_u8u8(acc[0][2], a0, b2);
+                    imma_u8u8(acc[1][2], a1, b2);
                 }
             } else if (hi_oct) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    uint32_t a0[4];
+                    uint32_t a0[4], a1[4];
                     ldmatrix_x4(a0, arow + ks * 32);
+                    ldmatrix_x4(a1, arow + 16 * kFPitch + ks * 32);
                     const uint2 b1 = sb[(ks * 4 + 1) * 32 + lane], b3 = sb[(ks * 4 + 3) * 32 + lane];
-                    imma_u8s8(acc[1], a0, b1);
-                    imma_u8u8(acc[3], a0, b3);
+                    imma_u8s8(acc[0][1], a0, b1);
+                    imma_u8s8(acc[1][1], a1, b1);
+                    imma_u8u8(acc[0][3], a0, b3);
+                    imma_u8u8(acc[1][3], a1, b3);
                 }
             }
         }
@@ -1813,53 +1844,79 @@ __global__ void __launch_bounds__(kFThreads, 1) hash_fused_kernel(const FusedArg
         if (lane == 0) mbar_arrive(&fs.empty[c_stage]);  // this warp has read everything it needs from the stage
         if (++c_stage == kFStages) c_stage = 0, full_parity ^= 1u;
         if (last_kc) {
-            // row block finished: k = 256 kh + kl, round, shift, clamp -> the u8 intermediate of this warp's 16 rows, transposed
-            const int32_t round_h = 1 << (c_prec_h - 1);
+            // row block finished: this warp's partial sums k = 256 kh + kl over its k-half, 16 per lane
+            int32_t v[2][2][4];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t row = half * 8 + g;
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int oct = 0; oct < 2; ++oct)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int32_t v = acc[oct][half * 2 + e] * 256 + acc[2 + oct][half * 2 + e] + round_h;
-                        tw[(oct * 8 + q2 + e) * kFTmpPitch + row] = clip8(v, c_prec_h);
+                    for (int j = 0; j < 4; ++j) {
+                        v[mt][oct][j] = acc[mt][oct][j] * 256 + acc[mt][2 + oct][j];
+                        acc[mt][oct][j] = 0, acc[mt][2 + oct][j] = 0;
                     }
-            }
+            if (khalf == 1) {
+                if (pb_busy) pair_sync(bar_b);  // the partner's arrival after reading the previous row block's sums
 #pragma unroll
-            for (int y = 0; y < 4; ++y)
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int z = 0; z < 4; ++z) acc[y][z] = 0;
-            __syncwarp();
-            // half a k-step (these 16 rows; the other half of the B fragment is zero: the pair's other warp adds it) of the vertical
-            // pass: out[oy][ox] += sum_y kv[oy][y] * tmp[y][ox]
-            const uint32_t ah[4] = {va_h.x, va_h.y, va_h.z, va_h.w}, al[4] = {va_l.x, va_l.y, va_l.z, va_l.w};
+                    for (int oct = 0; oct < 2; ++oct)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const uint32_t bw = *reinterpret_cast<const uint32_t*>(tw + (nt * 8 + g) * kFTmpPitch + 4 * q4);
-                const uint32_t b0 = (warp & 1) ? 0u : bw, b1 = (warp & 1) ? bw : 0u;
-                imma_s8u8(vacc[nt][0], ah, b0, b1);
-                imma_u8u8v(vacc[nt][1], al, b0, b1);
-            }
-            __syncwarp();
-            c_kc = 0;
-            if (++c_rb == c_nrb) {  // frame finished: the eight warps' vertical sums meet in shared memory
-                int32_t* vr = fs.vred[c_ord & 1];
-                mbar_wait(&fs.fin_empty[c_ord & 1], ((c_ord >> 1) & 1u) ^ 1u);  // the finalizer is done with frame c_ord - 2 (passes at once, normally)
+                        for (int j = 0; j < 4; ++j) pb[((mt * 2 + oct) * 4 + j) * 32] = v[mt][oct][j];
+                pair_arrive(bar_a);
+                pb_busy = true;
+            } else {
+                pair_sync(bar_a);
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int half = 0; half < 2; ++half)
+                    for (int oct = 0; oct < 2; ++oct)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int32_t v = vacc[nt][0][half * 2 + e] * 256 + vacc[nt][1][half * 2 + e];
-                            atomicAdd(&vr[(g + half * 8) * 16 + nt * 8 + q2 + e], v);
-                            vacc[nt][0][half * 2 + e] = 0, vacc[nt][1][half * 2 + e] = 0;
-                        }
-                // the finalizer warp clamps, stores and counts: no barrier and no memory fence on the consumers' path
-                if (tid == 0) fs.fin_out[c_ord & 1] = c_out, fs.fin_prec[c_ord & 1] = c_prec_v;
+                        for (int j = 0; j < 4; ++j) v[mt][oct][j] += pb[((mt * 2 + oct) * 4 + j) * 32];
+                pair_arrive(bar_b);
+                // round, shift, clamp -> the u8 intermediate of the pair's 32 rows, transposed
+                const int32_t round_h = 1 << (c_prec_h - 1);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t row = mt * 16 + half * 8 + g;
+#pragma unroll
+                        for (int oct = 0; oct < 2; ++oct)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) tw[(oct * 8 + q2 + e) * kFTmpPitch + row] = clip8(v[mt][oct][half * 2 + e] + round_h, c_prec_h);
+                    }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&fs.fin_full[c_ord & 1]);
+                // one k-step (these 32 rows) of the vertical pass: out[oy][ox] += sum_y kv[oy][y] * tmp[y][ox]
+                const uint32_t ah[4] = {va_h.x, va_h.y, va_h.z, va_h.w}, al[4] = {va_l.x, va_l.y, va_l.z, va_l.w};
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const uint8_t* bp = tw + (nt * 8 + g) * kFTmpPitch + 4 * q4;
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(bp), b1 = *reinterpret_cast<const uint32_t*>(bp + 16);
+                    imma_s8u8(vacc[nt][0], ah, b0, b1);
+                    imma_u8u8v(vacc[nt][1], al, b0, b1);
+                }
+                __syncwarp();
+            }
+            c_kc = 0;
+            if (++c_rb == c_nrb) {  // frame finished: the four row groups' vertical sums meet in shared memory; the finalizer warp clamps,
+                if (khalf == 0) {    // stores and counts -- no barrier and no memory fence on the consumers' path
+                    int32_t* vr = fs.vred[c_ord & 1];
+                    mbar_wait(&fs.fin_empty[c_ord & 1], ((c_ord >> 1) & 1u) ^ 1u);  // the finalizer is done with frame c_ord - 2 (passes at once, normally)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int half = 0; half < 2; ++half)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int32_t sum = vacc[nt][0][half * 2 + e] * 256 + vacc[nt][1][half * 2 + e];
+                                atomicAdd(&vr[(g + half * 8) * 16 + nt * 8 + q2 + e], sum);
+                                vacc[nt][0][half * 2 + e] = 0, vacc[nt][1][half * 2 + e] = 0;
+                            }
+                    if (tid == 0) fs.fin_out[c_ord & 1] = c_out, fs.fin_prec[c_ord & 1] = c_prec_v;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fs.fin_full[c_ord & 1]);
+                }
                 ++c_ord;
                 c_take_slot();
             }
@@ -1867,6 +1924,7 @@ __global__ void __launch_bounds__(kFThreads, 1) hash_fused_kernel(const FusedArg
             ++c_kc;
         }
     }
+    if (khalf == 1 && pb_busy) pair_sync(bar_b);  // pair barriers end balanced
     if (tid == 0) {
         atomicAdd(&a.ctl[11], (uint32_t)((globaltimer_ns() - t_start) >> 10));  // statistics
         *reinterpret_cast<volatile uint32_t*>(&fs.fin_stop) = c_ord + 1u;      // every thread has the same c_ord: frames this block finished

@@ -403,7 +403,31 @@ int main() {
         CK(cudaMalloc(&buf, bytes));
         CK(cudaMemset(buf, 1, bytes));
         float ms = time_ms([&] { stream_read_kernel<<<sms * 16, 256>>>(buf, bytes / 16, d_out); });
-        printf("{\"op\": \"hbm_stream_read\", \"ms\": %.3f, \"gb_per_s\": %.1f}\n", ms, bytes / (ms * 1e-3) / 1e9);
+        printf("{\"op\": \"hbm_stream_read\", \"run\": \"burst\", \"ms\": %.3f, \"gb_per_s\": %.1f}\n", ms, bytes / (ms * 1e-3) / 1e9);
+        {   // sustained: the same launch back to back for ~1.2 s (the GPU reaches its power cap; bench.py's long hashing run does too)
+            cudaEvent_t e0, e1;
+            CK(cudaEventCreate(&e0));
+            CK(cudaEventCreate(&e1));
+            const int reps = (int)(1200.0f / ms) + 1;
+            CK(cudaEventRecord(e0));
+            for (int r = 0; r < reps; ++r) stream_read_kernel<<<sms * 16, 256>>>(buf, bytes / 16, d_out);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float tot = 0;
+            CK(cudaEventElapsedTime(&tot, e0, e1));
+            printf("{\"op\": \"hbm_stream_read\", \"run\": \"sustained\", \"launches\": %d, \"ms\": %.3f, \"gb_per_s\": %.1f}\n", reps, tot / reps,
+                   bytes / (tot / reps * 1e-3) / 1e9);
+            // and the last 20 % of a second such run alone (the steady state)
+            const int head = reps * 4 / 5;
+            for (int r = 0; r < head; ++r) stream_read_kernel<<<sms * 16, 256>>>(buf, bytes / 16, d_out);
+            CK(cudaEventRecord(e0));
+            for (int r = head; r < reps; ++r) stream_read_kernel<<<sms * 16, 256>>>(buf, bytes / 16, d_out);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&tot, e0, e1));
+            printf("{\"op\": \"hbm_stream_read\", \"run\": \"sustained, last fifth\", \"launches\": %d, \"ms\": %.3f, \"gb_per_s\": %.1f}\n", reps - head,
+                   tot / (reps - head), bytes / (tot / (reps - head) * 1e-3) / 1e9);
+        }
         cudaFree(buf);
     }
     CK(cudaDeviceSynchronize());
