@@ -1130,23 +1130,24 @@ __global__ void job_build_kernel(const StackDev* __restrict__ stacks, const uint
 
 // ================================================================================ the fused kernel
 // ONE launch per call does letterbox -> crop -> resize job -> resize -> DCT -> threshold -> pack: sm_count persistent thread blocks of
-// 576 threads (216 KB of shared memory, one block per SM), warp-specialised into five groups that never share a barrier:
-//   consumers  (warps 0-7)    warp w owns rows 16 w .. 16 w + 15 of every tile: the horizontal pass is the IMMA contraction of
-//                             resize_mma_kernel; the u8 intermediate of its 16 rows goes through 768 bytes of shared memory straight
-//                             into half a k-step of the VERTICAL pass, also on the tensor path (A = the 16 x 32 slice of the vertical
+// 512 threads (224 KB of shared memory, one block per SM), warp-specialised into five groups that never share a block-wide barrier:
+//   consumers  (warps 0-7)    warp = (row group r, k-half h): rows 32 r .. 32 r + 31 of every tile, the 128 pixels of half h: the
+//                             horizontal pass is the IMMA contraction of resize_mma_kernel; once per row block the pair's partial
+//                             sums meet, are rounded to the u8 intermediate, and go through 768 bytes of shared memory straight into
+//                             one k-step of the VERTICAL pass, also on the tensor path (A = the 16 x 32 slice of the vertical
 //                             coefficients as hi / lo bytes, B = the transposed intermediate), accumulated in registers over the
 //                             frame: no per-frame intermediate buffer, no serial tail per frame, shared memory independent of the
-//                             frame height.  Arrive on the stage's "empty" mbarrier.
-//   producers  (warps 8-11)   the cp.async side of a 4-stage ring: tiles of 128 rows x 256 bytes (+ the tile's coefficient fragments,
+//                             frame height.  Every warp arrives on the stage's "empty" mbarrier.
+//   producers  (warps 8-9)    the cp.async side of a 4-stage ring: tiles of 128 rows x 256 bytes (+ the tile's coefficient fragments,
 //                             only the octets of outputs that have taps there) HBM -> shared memory, cp.async.mbarrier.arrive on the
 //                             stage's "full" mbarrier.  They run ahead ACROSS frames (the ring never drains), and they may sit in a
 //                             blocked copy instruction for as long as the memory system likes without holding up a tensor instruction.
-//   helpers    (warps 12-15)  everything that is latency-bound: the letterbox items (strip 0 of a stack's eight sides in one round
+//   helpers    (warps 10-13)  everything that is latency-bound: the letterbox items (strip 0 of a stack's eight sides in one round
 //                             trip; walks of the sides that have a bar), crop -> resize job -> publish; then the 16^3 DCT + threshold
 //                             + pack of every stack whose sixteenth frame is finished.  All of it in the shadow of the pixel stream.
-//   scheduler  (warp 16)      one lane: claims the next frame, checks that its stack's job is published (else puts the frame aside
+//   scheduler  (warp 14)      one lane: claims the next frame, checks that its stack's job is published (else puts the frame aside
 //                             and claims another), fills a slot for producers and consumers.
-//   finalizer  (warp 17)      per finished frame: the eight consumer warps' vertical sums -> round, shift, clamp -> 256 bytes of the
+//   finalizer  (warp 15)      per finished frame: the four row groups' vertical sums -> round, shift, clamp -> 256 bytes of the
 //                             stack's cube; the stack's sixteenth frame goes onto the helpers' DCT queue.
 // Items are claimed in order from global counters and a letterbox item never waits for anything, so every wait in the kernel is
 // for work that a RUNNING group has already claimed: no deadlock, whatever the number of resident blocks.  Waits are bounded
@@ -1245,7 +1246,7 @@ __device__ __forceinline__ void imma_u8u8v(int32_t (&c)[4], const uint32_t (&a)[
 
 constexpr uint64_t kFWaitNs = 8ull * 1000 * 1000 * 1000;  // no wait in the kernel is for more than one letterbox item or one launch
 
-// ---- helper group: letterbox items, job building, DCT items (threads 256..383)
+// ---- helper group: letterbox items, job building, DCT items (threads 320..447)
 __device__ __forceinline__ void fused_publish_job(const FusedArgs& a, uint32_t s) {  // one thread
     const StackDev d = a.stacks[s];
     uint32_t out[4] = {0, 0, 0, 0};
