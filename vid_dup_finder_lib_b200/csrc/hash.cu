@@ -1219,7 +1219,7 @@ struct FusedArgs {
     uint32_t* wq;          // [8 n] letterbox walk queue: side item + 1
     uint8_t* small;
     uint32_t* out_hash;    // nullptr: no DCT here (context option hash_fuse_dct = 0)
-    uint32_t exp;          // experiment bits (VDF_FUSED_EXP, timing studies only -- results are wrong): 1 no contraction, 2 one consumer arrive
+    uint32_t exp;          // builds with -DVDF_TIMING_EXPERIMENTS only (VDF_FUSED_EXP): 1 = no contraction (wrong results, timing studies)
 };
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
@@ -1474,7 +1474,7 @@ __device__ __forceinline__ void fused_scheduler(const FusedArgs& a, FusedSmem& f
         // A claimed frame is a frame no other block can take: the next one is claimed only when the producers are past the middle of
         // the current one (p_prog = 2 * ordinal + past-the-middle), early enough to hide this lane's few dependent round trips to memory
         // and late enough that the blocks finish within half a frame of each other at the end of the launch.
-        const uint32_t gate = (a.exp & 8u) ? (j >= 2 ? 2u * j - 4u : 0u) : (a.exp & 4u) ? (j >= 1 ? 2u * j - 2u : 0u) : (j >= 1 ? 2u * j - 1u : 0u);
+        const uint32_t gate = j >= 1 ? 2u * j - 1u : 0u;
         while (gate > *v_pord) {
             if (*v_abort) return;
             __nanosleep(2000);  // half a frame is ~20 us away
@@ -1796,7 +1796,11 @@ __global__ void __launch_bounds__(kFThreads, 1) hash_fused_kernel(const FusedArg
         {
             const uint8_t* arow = st + a_off;
             const uint2* sb = reinterpret_cast<const uint2*>(coef + khalf * kBFragBytes);
+#ifdef VDF_TIMING_EXPERIMENTS  // make EXTRA=-DVDF_TIMING_EXPERIMENTS + VDF_FUSED_EXP=1: the launch without its contraction (WRONG hashes; timing studies)
             const uint32_t tapmask = (a.exp & 1u) ? 0u : (masks >> (8 * khalf)) & 0xFFu;
+#else
+            const uint32_t tapmask = (masks >> (8 * khalf)) & 0xFFu;
+#endif
             const bool lo_oct = (tapmask & 0x55u) != 0, hi_oct = (tapmask & 0xAAu) != 0;
             if (lo_oct && hi_oct) {
 #pragma unroll
@@ -2329,7 +2333,10 @@ int hash_stacks_device(vdf_ctx* ctx, const uint8_t* d_frames, const vdf_stack_de
         fa.miss = d_miss, fa.n_miss = d_nmiss;
         fa.ctl = d_ctl, fa.flags = d_ctl + 16, fa.sides_done = d_ctl + 16 + n, fa.dq = d_ctl + 16 + 2 * (size_t)n, fa.wq = d_ctl + 16 + 4 * (size_t)n;
         fa.done = d_done, fa.small = d_small, fa.out_hash = d_hash32;
-        fa.exp = getenv("VDF_FUSED_EXP") ? (uint32_t)atoi(getenv("VDF_FUSED_EXP")) : 0u;
+        fa.exp = 0u;
+#ifdef VDF_TIMING_EXPERIMENTS
+        if (getenv("VDF_FUSED_EXP")) fa.exp = (uint32_t)atoi(getenv("VDF_FUSED_EXP"));
+#endif
         if (!only_missed) kt_begin(ctx, 1);
         if (!scan_in_kernel) {  // crops known up front (Cropdetect::None / Motion, or the pass for the sizes met for the first time)
             job_build_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_sd, d_crop, n, fa.coef_lut, fa.bfrag_lut, 0xFFFFFFFFu, 0xFFFFFFFFu,
