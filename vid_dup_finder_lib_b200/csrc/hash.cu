@@ -800,6 +800,10 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint
                  "l"(src), "r"(src_bytes)
                  : "memory");
 }
+// the same through L1 (cp.async.ca): for data a thread block fetches again and again (the fused kernel's coefficient fragments)
+__device__ __forceinline__ void cp_async16_ca(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -1665,7 +1669,10 @@ __device__ __forceinline__ void fused_producer(const FusedArgs& a, uint8_t* ring
         const uint8_t* g_rb = img + (uint64_t)r0 * sl.pitch + c16;
         for (uint32_t rb = 0; rb < n_rb; ++rb, g_rb += 32 * row_step) {
             if (tid == 0 && rb == n_rb / 2 && rb) *reinterpret_cast<volatile uint32_t*>(&fs.p_ord) = 2u * ord + 1u;
-            for (uint32_t kc = 0; kc < n_kc; ++kc) {
+            for (uint32_t kci = 0; kci < n_kc; ++kci) {
+                // k-chunks left to right on even row blocks, right to left on odd ones: the coefficient fragments a row block ends with are
+                // the ones the next one starts with, and they come through L1 (what shared memory leaves of it holds a few chunks)
+                const uint32_t kc = (rb & 1u) ? n_kc - 1u - kci : kci;
                 mbar_wait(&fs.empty[stage], empty_parity);
                 uint8_t* st = ring + (size_t)stage * kFStageBytes;
                 const bool xok = kc * kFCols + c16 < row_bytes;
@@ -1685,8 +1692,8 @@ __device__ __forceinline__ void fused_producer(const FusedArgs& a, uint8_t* ring
                 const bool need0 = wide || (pm[2 * kc] & oct_bits), need1 = wide || (pm[2 * kc + 1] & oct_bits);
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    if (q < 4 ? need0 : need1) cp_async16(cdst + q * NT * 16, csrc + q * NT * 16, 16u);
-                if (tid == 0) cp_async16(cdst + 8 * NT * 16, csrc + 8 * NT * 16, 16u);  // the header
+                    if (q < 4 ? need0 : need1) cp_async16_ca(cdst + q * NT * 16, csrc + q * NT * 16);
+                if (tid == 0) cp_async16_ca(cdst + 8 * NT * 16, csrc + 8 * NT * 16);  // the header
                 mbar_arrive_on_cp_async(&fs.full[stage]);
                 if (++stage == kFStages) stage = 0, empty_parity ^= 1u;
             }
