@@ -571,7 +571,7 @@ def test_two_contexts_in_one_process(ctx):
             assert np.array_equal(other.search_self(H, dur, 300), want)
             ctx.set_option("search_variant", variant)
             assert np.array_equal(ctx.search_self(H, dur, 300), want)
-        # the hashing kernels' opt-in (216 KB of shared memory for the fused kernel) is per device too
+        # the hashing kernels' opt-in (224 KB of shared memory for the fused kernel) is per device too
         st = synth.frame_stacks(5, 320, 180, seed=12).numpy()
         st[1, :, :25, :] = 16
         descs = _ffi.make_descs(5, 320, 180)
